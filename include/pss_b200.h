@@ -1,0 +1,243 @@
+/*
+ * pss_b200.h -- C ABI of the B200-native pileup / binned statistics engine.
+ *
+ * This is the drop-in boundary for the hot path of alimanfoo/pysamstats: everything the
+ * reference computes inside pysamstats/opt.pyx (+ the htslib pileup engine it drives) for
+ * one contig region, expressed over plain pointers and sizes.  No torch / numpy types.
+ * The python host side (pysamstats_b200/_cabi.py) binds these with ctypes; see
+ * INTEGRATION.md for the binding a pysamstats maintainer would add.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success or a negative PSS_E* code; the message is
+ *     available through pss_last_error().  Nothing throws across the ABI.
+ *   - the caller owns every buffer passed in.  "dev" pointers are CUDA device pointers
+ *     (e.g. torch tensors' data_ptr()), "host" pointers are ordinary (preferably pinned)
+ *     host memory.  The context owns only its private scratch workspace.
+ *   - one pss_ctx per (GPU, host thread); no global state.  Work is launched on the
+ *     stream given (a cudaStream_t passed as void*, NULL = default stream); the *_host
+ *     entry points synchronise before returning, the device entry points do not.
+ *   - a read batch is the set of BAM records of ONE contig in file (coordinate) order,
+ *     as structure-of-arrays.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef PSS_B200_H
+#define PSS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSS_OK 0
+#define PSS_EINVAL (-1)   /* bad argument */
+#define PSS_ECUDA (-2)    /* CUDA runtime / launch failure */
+#define PSS_ENOMEM (-3)   /* workspace allocation failed */
+#define PSS_EUNSORTED (-4) /* batch not coordinate sorted (htslib: "unsorted positions") */
+
+/* statistics ids: order of stats_classes_pileup, pysamstats/pileup.py:150-166 */
+enum pss_pileup_stat {
+    PSS_COVERAGE = 0,
+    PSS_COVERAGE_STRAND = 1,
+    PSS_COVERAGE_EXT = 2,
+    PSS_COVERAGE_EXT_STRAND = 3,
+    PSS_VARIATION = 4,
+    PSS_VARIATION_STRAND = 5,
+    PSS_TLEN = 6,
+    PSS_TLEN_STRAND = 7,
+    PSS_MAPQ = 8,
+    PSS_MAPQ_STRAND = 9,
+    PSS_BASEQ = 10,
+    PSS_BASEQ_STRAND = 11,
+    PSS_BASEQ_EXT = 12,
+    PSS_BASEQ_EXT_STRAND = 13,
+    PSS_COVERAGE_GC = 14,
+    PSS_N_PILEUP_STATS = 15
+};
+
+/* order of stats_classes_binned, pysamstats/binned.py:121-127 */
+enum pss_binned_stat {
+    PSS_COVERAGE_BINNED = 0,
+    PSS_COVERAGE_EXT_BINNED = 1,
+    PSS_MAPQ_BINNED = 2,
+    PSS_ALIGNMENT_BINNED = 3,
+    PSS_TLEN_BINNED = 4,
+    PSS_N_BINNED_STATS = 5
+};
+
+/* pysam stepper names, pysamstats/config.py:29-31 */
+enum pss_stepper { PSS_STEPPER_ALL = 0, PSS_STEPPER_NOFILTER = 1, PSS_STEPPER_SAMTOOLS = 2 };
+
+typedef struct pss_ctx pss_ctx;
+
+/*
+ * Structure-of-arrays read batch: the fields of htslib's bam1_t that opt.pyx reads
+ * (opt.pyx:10-14: core.pos/flag/qual/isize/mtid/n_cigar/l_qseq, bam_get_cigar/seq/qual).
+ * Offsets arrays have n_reads + 1 entries.  seq4 is BAM's packed 4-bit sequence
+ * ((l_seq + 1) / 2 bytes per read), qual is l_seq bytes per read.
+ * qual / qual_off / name_prev may be NULL when the request does not depend on base
+ * qualities (no baseq* statistic and min_baseq == 0).
+ * name_prev[i] = index of the previous record in this batch with the same QNAME, or -1:
+ * the QNAME equivalence htslib's mate-overlap hash keys on.
+ */
+typedef struct pss_reads {
+    int64_t n_reads;
+    int64_t n_cigar_words; /* elements in cigar[]  (== cigar_off[n_reads]) */
+    int64_t n_seq_bytes;   /* bytes in seq4[]      (== seq_off[n_reads]) */
+    int64_t n_qual_bytes;  /* bytes in qual[]      (== qual_off[n_reads]), 0 if qual is NULL */
+    int32_t tid;           /* contig id of the batch (col.tid in opt.pyx:272) */
+    int32_t reserved;
+    const int32_t *pos;   /* core.pos, non-decreasing */
+    const uint16_t *flag; /* core.flag */
+    const uint8_t *mapq;  /* core.qual */
+    const int32_t *tlen;  /* core.isize */
+    const int32_t *mtid;  /* core.mtid */
+    const int32_t *l_seq; /* core.l_qseq */
+    const int64_t *cigar_off;
+    const uint32_t *cigar; /* BAM encoding: len << 4 | op */
+    const int64_t *seq_off;
+    const uint8_t *seq4;
+    const int64_t *qual_off;
+    const uint8_t *qual;
+    const int32_t *name_prev;
+} pss_reads;
+
+/*
+ * Pileup request: the keyword arguments of opt.iter_pileup (opt.pyx:1827, :1846-1847) that
+ * reach the engine.  [start, end) is the OUTPUT position range: out column j describes
+ * position start + j.  (The host decides that range from region / truncate / pad and the
+ * fetched reads; the engine does not clip reads to it.)
+ * ref / ref_start / ref_len describe reference bytes (any case) for positions
+ * [ref_start, ref_start + ref_len); positions outside behave like an empty
+ * FastaFile.fetch() (opt.pyx:1987-1994).  ref may be NULL for statistics without `ref`.
+ */
+typedef struct pss_pileup_params {
+    int32_t stat;          /* enum pss_pileup_stat */
+    int32_t stepper;       /* enum pss_stepper */
+    int32_t max_depth;     /* 0 -> htslib default 8000 */
+    int32_t min_mapq;
+    int32_t min_baseq;
+    int32_t no_del;
+    int32_t no_dup;
+    int32_t window_size;   /* coverage_gc only (opt.pyx:1477-1481) */
+    int32_t window_offset; /* coverage_gc only, already defaulted */
+    int32_t reserved;
+    int64_t start;
+    int64_t end;
+    const uint8_t *ref;
+    int64_t ref_start;
+    int64_t ref_len;
+    int64_t contig_len;    /* FASTA length of the contig (clips the coverage_gc window) */
+} pss_pileup_params;
+
+/* Binned request: keyword arguments of opt.iter_binned_chrom (opt.pyx:2026-2028). */
+typedef struct pss_binned_params {
+    int32_t stat;          /* enum pss_binned_stat */
+    int32_t window_size;
+    int32_t min_mapq;
+    int32_t no_dup;
+    int64_t start;         /* normalised region start (bin 0 starts here) */
+    int64_t end;
+    int64_t n_bins;        /* from pss_binned_nbins() */
+    const uint8_t *ref;    /* coverage / coverage_ext: reference bytes, else NULL */
+    int64_t ref_start;
+    int64_t ref_len;
+} pss_binned_params;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device`.  Replaces nothing in the reference (which
+ * has no device); one context per GPU/thread. */
+int pss_create(int device, pss_ctx **out);
+void pss_destroy(pss_ctx *ctx);
+const char *pss_last_error(const pss_ctx *ctx);
+const char *pss_version(void);
+/* Waits for `stream` and reports errors detected on the device by earlier asynchronous
+ * calls on this context (PSS_EUNSORTED: the batch was not coordinate sorted; htslib's
+ * pileup refuses such input too).  The device entry points never synchronise themselves. */
+int pss_synchronize(pss_ctx *ctx, void *stream);
+/* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t pss_launch_count(const pss_ctx *ctx);
+/* Average device time (ms, CUDA events on the launch stream) of the dominant pileup
+ * kernel over the launches since the last call; resets the accumulator.  Used by
+ * bench.py for roofline.achieved.  Returns < 0 if there were none. */
+double pss_pileup_kernel_ms(pss_ctx *ctx, int64_t *n_launches);
+/* Enable/disable the per-launch event timing above (default off: no overhead). */
+void pss_set_kernel_timing(pss_ctx *ctx, int enabled);
+
+/* ---- shapes ---------------------------------------------------------------------- */
+
+/* number of int32 value fields per row (config.py dtype lists minus chrom/pos/ref) */
+int32_t pss_pileup_nfields(int32_t stat);
+int32_t pss_binned_nfields(int32_t stat);
+/* 1 when the statistic carries a `ref` column / needs reference bytes */
+int32_t pss_pileup_needs_ref(int32_t stat);
+/* 1 when the request reads base qualities (so qual/qual_off/name_prev are required) */
+int32_t pss_pileup_needs_qual(int32_t stat, int32_t min_baseq);
+/* number of windows iter_binned_chrom yields for [start, end) (opt.pyx:2043-2102) */
+int64_t pss_binned_nbins(int64_t start, int64_t end, int32_t window_size);
+
+/* ---- pileup statistics ------------------------------------------------------------ */
+
+/*
+ * Replaces opt.iter_pileup_default / stat_pileup (opt.pyx:1846-1919) and the htslib
+ * column builder behind AlignmentFile.pileup (call site opt.pyx:1853-1854) for one
+ * contig: for every position p in [start, end)
+ *     out[f * (end - start) + (p - start)] = field f of the record for p
+ *     rowmask[p - start] = 1 iff htslib would emit a column at p (>= 1 read admitted,
+ *                          before pysamstats' own filters -- opt.pyx:1892-1915)
+ * Field order = pysamstats/config.py dtype_<stat> minus chrom/pos/ref.  Rows with
+ * rowmask 0 hold the values of an empty accumulator (what pad=True emits).
+ * All pointers in `reads`, params->ref, out and rowmask are DEVICE pointers.
+ */
+int pss_pileup(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *params,
+               int32_t *out, uint8_t *rowmask, void *stream);
+
+/*
+ * Same contract with HOST pointers everywhere: copies the batch to the device, runs
+ * pss_pileup over position chunks and copies results back (synchronous).  This is the
+ * call timed as `e2e` in bench.py.
+ */
+int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *params,
+                    int32_t *out, uint8_t *rowmask);
+
+/*
+ * The depth-cap admission rule of bam_plp_push (max_depth, call site opt.pyx:1853-1854)
+ * plus the stepper flag filter, exposed on its own: admitted[i] = 1 iff read i enters the
+ * pileup.  DEVICE pointers.
+ */
+int pss_admit(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth,
+              uint8_t *admitted, void *stream);
+
+/*
+ * The mate-overlap base-quality rewrite htslib applies under pysam's default
+ * ignore_overlaps=True (call site opt.pyx:1853), exposed on its own:
+ * qual_out receives the qualities the pileup sees (same layout as reads->qual),
+ * pair_first[i] = index of the earlier mate read i was paired with, or -1.
+ * DEVICE pointers; pair_first may be NULL.
+ */
+int pss_overlap_tweak(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth,
+                      uint8_t *qual_out, int32_t *pair_first, void *stream);
+
+/* ---- binned statistics ------------------------------------------------------------ */
+
+/*
+ * Replaces opt.iter_binned_chrom (opt.pyx:2026-2102) and the five BinnedStat classes
+ * (opt.pyx:1551-1819) for one contig region: out[f * n_bins + k] = field f of window k,
+ * window k = [start + k*W, start + (k+1)*W).  Field order = config.py dtype_<stat>_binned
+ * minus chrom/pos.  `reads` must be the records IteratorRowRegion yields for the region
+ * (pos < end and endpos > start, file order).  DEVICE pointers.
+ */
+int pss_binned(pss_ctx *ctx, const pss_reads *reads, const pss_binned_params *params,
+               int32_t *out, void *stream);
+
+/* Same with HOST pointers (synchronous). */
+int pss_binned_host(pss_ctx *ctx, const pss_reads *reads, const pss_binned_params *params,
+                    int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSS_B200_H */

@@ -1,0 +1,265 @@
+"""ctypes binding of ``libpss_b200.so`` (the C ABI declared in ``include/pss_b200.h``).
+
+The shared library is built in-tree by ``pysamstats_b200/csrc/Makefile`` (see
+``__graft_entry__.build``).  There is NO CPU fallback: if the library is missing or no
+CUDA device is usable, importing the engine fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'csrc', 'libpss_b200.so')
+
+PSS_OK, PSS_EINVAL, PSS_ECUDA, PSS_ENOMEM, PSS_EUNSORTED = 0, -1, -2, -3, -4
+
+PILEUP_STATS = ('coverage', 'coverage_strand', 'coverage_ext', 'coverage_ext_strand', 'variation',
+                'variation_strand', 'tlen', 'tlen_strand', 'mapq', 'mapq_strand', 'baseq',
+                'baseq_strand', 'baseq_ext', 'baseq_ext_strand', 'coverage_gc')
+BINNED_STATS = ('coverage', 'coverage_ext', 'mapq', 'alignment', 'tlen')
+STEPPERS = {'all': 0, 'nofilter': 1, 'samtools': 2}
+
+
+class PssReads(C.Structure):
+    """struct pss_reads"""
+    _fields_ = [('n_reads', C.c_int64), ('n_cigar_words', C.c_int64), ('n_seq_bytes', C.c_int64),
+                ('n_qual_bytes', C.c_int64), ('tid', C.c_int32), ('reserved', C.c_int32),
+                ('pos', C.c_void_p), ('flag', C.c_void_p), ('mapq', C.c_void_p), ('tlen', C.c_void_p),
+                ('mtid', C.c_void_p), ('l_seq', C.c_void_p), ('cigar_off', C.c_void_p),
+                ('cigar', C.c_void_p), ('seq_off', C.c_void_p), ('seq4', C.c_void_p),
+                ('qual_off', C.c_void_p), ('qual', C.c_void_p), ('name_prev', C.c_void_p)]
+
+
+class PssPileupParams(C.Structure):
+    """struct pss_pileup_params"""
+    _fields_ = [('stat', C.c_int32), ('stepper', C.c_int32), ('max_depth', C.c_int32),
+                ('min_mapq', C.c_int32), ('min_baseq', C.c_int32), ('no_del', C.c_int32),
+                ('no_dup', C.c_int32), ('window_size', C.c_int32), ('window_offset', C.c_int32),
+                ('reserved', C.c_int32), ('start', C.c_int64), ('end', C.c_int64),
+                ('ref', C.c_void_p), ('ref_start', C.c_int64), ('ref_len', C.c_int64),
+                ('contig_len', C.c_int64)]
+
+
+class PssBinnedParams(C.Structure):
+    """struct pss_binned_params"""
+    _fields_ = [('stat', C.c_int32), ('window_size', C.c_int32), ('min_mapq', C.c_int32),
+                ('no_dup', C.c_int32), ('start', C.c_int64), ('end', C.c_int64), ('n_bins', C.c_int64),
+                ('ref', C.c_void_p), ('ref_start', C.c_int64), ('ref_len', C.c_int64)]
+
+
+# every symbol include/pss_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    'pss_create': (C.c_int, [C.c_int, C.POINTER(_P)]),
+    'pss_destroy': (None, [_P]),
+    'pss_last_error': (C.c_char_p, [_P]),
+    'pss_version': (C.c_char_p, []),
+    'pss_synchronize': (C.c_int, [_P, _P]),
+    'pss_launch_count': (C.c_int64, [_P]),
+    'pss_pileup_kernel_ms': (C.c_double, [_P, C.POINTER(C.c_int64)]),
+    'pss_set_kernel_timing': (None, [_P, C.c_int]),
+    'pss_pileup_nfields': (C.c_int32, [C.c_int32]),
+    'pss_binned_nfields': (C.c_int32, [C.c_int32]),
+    'pss_pileup_needs_ref': (C.c_int32, [C.c_int32]),
+    'pss_pileup_needs_qual': (C.c_int32, [C.c_int32, C.c_int32]),
+    'pss_binned_nbins': (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
+    'pss_pileup': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssPileupParams), _P, _P, _P]),
+    'pss_pileup_host': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssPileupParams), _P, _P]),
+    'pss_admit': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P]),
+    'pss_overlap_tweak': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P, _P]),
+    'pss_binned': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssBinnedParams), _P, _P]),
+    'pss_binned_host': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssBinnedParams), _P]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libpss_b200.so and type every entry point.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError('%s is missing: build it with `make -C pysamstats_b200/csrc` '
+                              '(or __graft_entry__.build()); there is no CPU fallback' % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def _addr(a):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, 'data_ptr'):
+        return a.data_ptr()
+    raise TypeError('cannot take the address of %r' % type(a))
+
+
+READ_FIELDS = ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'cigar', 'seq_off', 'seq4',
+               'qual_off', 'qual', 'name_prev')
+READ_DTYPES = {'pos': 'i4', 'flag': 'u2', 'mapq': 'u1', 'tlen': 'i4', 'mtid': 'i4', 'l_seq': 'i4',
+               'cigar_off': 'i8', 'cigar': 'u4', 'seq_off': 'i8', 'seq4': 'u1', 'qual_off': 'i8',
+               'qual': 'u1', 'name_prev': 'i4'}
+
+
+def make_reads_struct(batch, n_reads=None):
+    """Build a struct pss_reads from an object/dict holding the SoA arrays (numpy arrays for
+    the *_host entry points, torch CUDA tensors or raw addresses for the device ones).
+    The sizes come from ``batch['n_reads']`` etc. when given, else from the array lengths."""
+    get = batch.get if isinstance(batch, dict) else (lambda k, d=None: getattr(batch, k, d))
+    r = PssReads()
+
+    def length(x):
+        return int(x.shape[0]) if hasattr(x, 'shape') else None
+
+    n = get('n_reads') if n_reads is None else n_reads
+    if n is None:
+        n = length(get('pos'))
+    r.n_reads = int(n)
+    for key, arr in (('n_cigar_words', 'cigar'), ('n_seq_bytes', 'seq4'), ('n_qual_bytes', 'qual')):
+        v = get(key)
+        if v is None:
+            a = get(arr)
+            v = length(a) if a is not None else 0
+        setattr(r, key, int(v or 0))
+    r.tid = int(get('tid', 0))
+    for f in READ_FIELDS:
+        setattr(r, f, _addr(get(f)))
+    return r
+
+
+class Context(object):
+    """One pss_ctx (one GPU)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _P()
+        rc = self.lib.pss_create(int(device), C.byref(h))
+        if rc != PSS_OK:
+            raise EngineError('pss_create(device=%d) failed (%d): no usable CUDA device; this '
+                              'engine has no CPU fallback' % (device, rc))
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.pss_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc == PSS_OK:
+            return
+        msg = self.lib.pss_last_error(self.h).decode('ascii', 'replace')
+        if rc == PSS_EINVAL or rc == PSS_EUNSORTED:
+            raise ValueError(msg)
+        if rc == PSS_ENOMEM:
+            raise MemoryError(msg)
+        raise EngineError(msg)
+
+    # -- thin wrappers -------------------------------------------------------------
+    def pileup_params(self, stat, stepper='all', max_depth=8000, min_mapq=0, min_baseq=0, no_del=False,
+                      no_dup=False, window_size=300, window_offset=None, start=0, end=0, ref=None,
+                      ref_start=0, ref_len=0, contig_len=0):
+        p = PssPileupParams()
+        p.stat = PILEUP_STATS.index(stat) if isinstance(stat, str) else int(stat)
+        if isinstance(stepper, str):
+            if stepper not in STEPPERS:
+                raise ValueError('unknown stepper: %r' % stepper)
+            stepper = STEPPERS[stepper]
+        p.stepper = stepper
+        p.max_depth = int(max_depth or 0)
+        p.min_mapq, p.min_baseq = int(min_mapq), int(min_baseq)
+        p.no_del, p.no_dup = int(bool(no_del)), int(bool(no_dup))
+        p.window_size = int(window_size)
+        p.window_offset = int(window_size // 2 if window_offset is None else window_offset)
+        p.start, p.end = int(start), int(end)
+        p.ref = _addr(ref)
+        p.ref_start, p.ref_len, p.contig_len = int(ref_start), int(ref_len), int(contig_len)
+        return p
+
+    def pileup_host(self, reads_struct, params, out, rowmask):
+        self.check(self.lib.pss_pileup_host(self.h, C.byref(reads_struct), C.byref(params), _addr(out),
+                                            _addr(rowmask)))
+
+    def pileup(self, reads_struct, params, out, rowmask, stream=None):
+        self.check(self.lib.pss_pileup(self.h, C.byref(reads_struct), C.byref(params), _addr(out),
+                                       _addr(rowmask), stream))
+
+    def binned_params(self, stat, start, end, window_size, min_mapq=0, no_dup=False, ref=None, ref_start=0,
+                      ref_len=0):
+        p = PssBinnedParams()
+        p.stat = BINNED_STATS.index(stat) if isinstance(stat, str) else int(stat)
+        p.window_size = int(window_size)
+        p.min_mapq, p.no_dup = int(min_mapq), int(bool(no_dup))
+        p.start, p.end = int(start), int(end)
+        p.n_bins = self.lib.pss_binned_nbins(int(start), int(end), int(window_size))
+        p.ref = _addr(ref)
+        p.ref_start, p.ref_len = int(ref_start), int(ref_len)
+        return p
+
+    def binned_host(self, reads_struct, params, out):
+        self.check(self.lib.pss_binned_host(self.h, C.byref(reads_struct), C.byref(params), _addr(out)))
+
+    def binned(self, reads_struct, params, out, stream=None):
+        self.check(self.lib.pss_binned(self.h, C.byref(reads_struct), C.byref(params), _addr(out), stream))
+
+    def admit(self, reads_struct, stepper, max_depth, admitted, stream=None):
+        self.check(self.lib.pss_admit(self.h, C.byref(reads_struct), int(stepper), int(max_depth),
+                                      _addr(admitted), stream))
+
+    def overlap_tweak(self, reads_struct, stepper, max_depth, qual_out, pair_first=None, stream=None):
+        self.check(self.lib.pss_overlap_tweak(self.h, C.byref(reads_struct), int(stepper), int(max_depth),
+                                              _addr(qual_out), _addr(pair_first), stream))
+
+    def synchronize(self, stream=None):
+        self.check(self.lib.pss_synchronize(self.h, stream))
+
+    def launch_count(self):
+        return int(self.lib.pss_launch_count(self.h))
+
+    def set_kernel_timing(self, on):
+        self.lib.pss_set_kernel_timing(self.h, int(bool(on)))
+
+    def pileup_kernel_ms(self):
+        n = C.c_int64(0)
+        ms = self.lib.pss_pileup_kernel_ms(self.h, C.byref(n))
+        return float(ms), int(n.value)
+
+
+_contexts = {}
+
+
+def default_device():
+    for k in ('PSS_DEVICE', 'LOCAL_RANK'):
+        if os.environ.get(k, '') != '':
+            return int(os.environ[k])
+    return 0
+
+
+def get_context(device=None):
+    """Process-wide context per device (created on first use; fails loudly without a GPU)."""
+    if device is None:
+        device = default_device()
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx

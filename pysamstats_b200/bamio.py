@@ -1,0 +1,341 @@
+"""Host-side BAM / FASTA decode into structure-of-arrays read batches.
+
+The reference reads alignments through pysam / htslib (``AlignmentFile.pileup`` at
+``pysamstats/opt.pyx:1853``, ``IteratorRowRegion`` at ``opt.pyx:2040``, ``FastaFile.fetch``
+at ``opt.pyx:1989``); neither is available to this package, so it carries its own reader:
+
+* BGZF: a series of gzip members, each at most 64 KiB, inflated independently (``zlib``
+  releases the GIL, so blocks are inflated on a small thread pool).
+* BAM records are parsed with numpy gathers over the inflated buffer -- only the walk over
+  the ``block_size`` chain is a python loop.
+* A batch is the set of records of one contig overlapping ``[start, end)`` in file order:
+  the rule htslib's region iterator applies (``pos < end and endpos > start``), which is
+  what both reference call sites consume.
+
+File objects of other libraries (e.g. ``pysam.AlignmentFile`` / ``pysam.FastaFile``) are
+accepted wherever a path is: only their ``.filename`` is used.
+"""
+import os
+import struct
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_REF_CONSUMING = np.array([1, 0, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0], dtype=bool)  # MIDNSHP=X
+
+
+def _path_of(f):
+    if isinstance(f, (BamFile, FastaFile)):
+        return f.filename
+    if isinstance(f, bytes):
+        return f.decode()
+    if isinstance(f, (str, os.PathLike)):
+        return os.fspath(f)
+    name = getattr(f, 'filename', None)
+    if name is None:
+        raise TypeError('expected a path or an object with a .filename, got %r' % type(f))
+    return name.decode() if isinstance(name, bytes) else str(name)
+
+
+# ------------------------------------------------------------------------------ BGZF
+
+def _bgzf_blocks(data):
+    """Yield (payload_start, payload_end) of every BGZF block's raw deflate stream."""
+    off, n = 0, len(data)
+    while off < n:
+        if data[off:off + 4] != b'\x1f\x8b\x08\x04':
+            raise ValueError('not a BGZF file (bad block header at %d)' % off)
+        xlen, = struct.unpack_from('<H', data, off + 10)
+        x, xend, bsize = off + 12, off + 12 + xlen, None
+        while x < xend:
+            si1, si2, slen = data[x], data[x + 1], struct.unpack_from('<H', data, x + 2)[0]
+            if si1 == 66 and si2 == 67:
+                bsize, = struct.unpack_from('<H', data, x + 4)
+            x += 4 + slen
+        if bsize is None:
+            raise ValueError('BGZF block without BC subfield at %d' % off)
+        yield xend, off + bsize + 1 - 8
+        off += bsize + 1
+
+
+def bgzf_inflate(path, threads=4):
+    with open(path, 'rb') as fh:
+        data = fh.read()
+    spans = list(_bgzf_blocks(data))
+
+    def inflate(span):
+        return zlib.decompress(data[span[0]:span[1]], -15)
+
+    if len(spans) > 8 and threads > 1:
+        with ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(inflate, spans, chunksize=32))
+    else:
+        parts = [inflate(s) for s in spans]
+    return b''.join(parts)
+
+
+# ---------------------------------------------------------------------- read batches
+
+def _ragged_gather(buf, starts, lens):
+    """Concatenate buf[starts[i]:starts[i]+lens[i]] for all i; returns (data, offsets)."""
+    lens = lens.astype(np.int64)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    total = int(off[-1])
+    if total == 0:
+        return np.zeros(0, dtype=buf.dtype), off
+    idx = np.repeat(starts.astype(np.int64) - off[:-1], lens) + np.arange(total, dtype=np.int64)
+    return buf[idx], off
+
+
+class ReadBatch(object):
+    """SoA arrays of the records of one contig, file order (see include/pss_b200.h
+    ``struct pss_reads``)."""
+
+    __slots__ = ('tid', 'pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'cigar', 'seq_off',
+                 'seq4', 'qual_off', 'qual', 'name_prev', 'endpos', 'names')
+
+    @property
+    def n_reads(self):
+        return len(self.pos)
+
+    def subset(self, idx):
+        """Records idx (increasing) as a new contiguous batch."""
+        b = ReadBatch()
+        b.tid = self.tid
+        for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'endpos', 'names'):
+            setattr(b, k, np.ascontiguousarray(getattr(self, k)[idx]))
+        for data, off in (('cigar', 'cigar_off'), ('seq4', 'seq_off'), ('qual', 'qual_off')):
+            o = getattr(self, off)
+            d, no = _ragged_gather(getattr(self, data), o[:-1][idx], (o[1:] - o[:-1])[idx])
+            setattr(b, data, d)
+            setattr(b, off, no)
+        b.name_prev = _name_prev(b.names)
+        return b
+
+    def padded(self):
+        """Arrays safe to hand to the engine (no zero-length buffers)."""
+        for k in ('cigar', 'seq4', 'qual'):
+            if len(getattr(self, k)) == 0:
+                setattr(self, k, np.zeros(1, dtype=getattr(self, k).dtype))
+        return self
+
+
+def _name_prev(names):
+    """Index of the previous record with the same QNAME (or -1), file order."""
+    n = len(names)
+    prev = np.full(n, -1, dtype=np.int32)
+    if n:
+        _, inv = np.unique(names, return_inverse=True)
+        order = np.argsort(inv, kind='stable')
+        same = inv[order][1:] == inv[order][:-1]
+        prev[order[1:][same]] = order[:-1][same]
+    return prev
+
+
+class BamFile(object):
+    """A whole BAM file decoded into memory."""
+
+    def __init__(self, path):
+        self.filename = _path_of(path)
+        raw = bgzf_inflate(self.filename)
+        if raw[:4] != b'BAM\x01':
+            raise ValueError('not a BAM file: %r' % self.filename)
+        l_text, = struct.unpack_from('<i', raw, 4)
+        off = 8 + l_text
+        n_ref, = struct.unpack_from('<i', raw, off)
+        off += 4
+        refs, lens = [], []
+        for _ in range(n_ref):
+            l_name, = struct.unpack_from('<i', raw, off)
+            refs.append(raw[off + 4:off + 4 + l_name - 1].decode('ascii'))
+            lens.append(struct.unpack_from('<i', raw, off + 4 + l_name)[0])
+            off += 8 + l_name
+        self.references = tuple(refs)
+        self.lengths = tuple(lens)
+        self._tid_of = {r: i for i, r in enumerate(refs)}
+        # walk the block_size chain
+        starts = []
+        n = len(raw)
+        unpack = struct.Struct('<i').unpack_from
+        while off < n:
+            starts.append(off + 4)
+            off += 4 + unpack(raw, off)[0]
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        st = np.array(starts, dtype=np.int64)
+        fixed = buf[st[:, None] + np.arange(32)] if len(st) else np.zeros((0, 32), np.uint8)
+        fixed = np.ascontiguousarray(fixed)
+
+        def col(a, b, dt):
+            return np.ascontiguousarray(fixed[:, a:b]).view(dt).ravel()
+
+        self._tid = col(0, 4, '<i4')
+        A = ReadBatch()
+        A.tid = -2
+        A.pos = col(4, 8, '<i4')
+        l_name = fixed[:, 8].astype(np.int64)
+        A.mapq = np.ascontiguousarray(fixed[:, 9])
+        n_cig = col(12, 14, '<u2').astype(np.int64)
+        A.flag = col(14, 16, '<u2')
+        A.l_seq = col(16, 20, '<i4')
+        A.mtid = col(20, 24, '<i4')
+        A.tlen = col(28, 32, '<i4')
+        lseq = A.l_seq.astype(np.int64)
+        name_start = st + 32
+        cig_start = name_start + l_name
+        seq_start = cig_start + 4 * n_cig
+        qual_start = seq_start + (lseq + 1) // 2
+        cig_bytes, coff = _ragged_gather(buf, cig_start, 4 * n_cig)
+        A.cigar = np.ascontiguousarray(cig_bytes).view('<u4')
+        A.cigar_off = coff // 4
+        A.seq4, A.seq_off = _ragged_gather(buf, seq_start, (lseq + 1) // 2)
+        A.qual, A.qual_off = _ragged_gather(buf, qual_start, lseq)
+        # QNAMEs as a fixed-width bytes column (NUL padded)
+        width = int(l_name.max()) if len(l_name) else 1
+        nm = np.zeros((len(st), width), dtype=np.uint8)
+        nb, noff = _ragged_gather(buf, name_start, l_name)
+        if len(nb):
+            rows = np.repeat(np.arange(len(st)), l_name)
+            cols = np.arange(len(nb)) - np.repeat(noff[:-1], l_name)
+            nm[rows, cols] = nb
+        A.names = nm.view('S%d' % width).ravel()
+        # htslib bam_endpos(): reference length of the CIGAR, 1 if unmapped or zero
+        op = (A.cigar & 15).astype(np.int64)
+        ln = (A.cigar >> 4).astype(np.int64)
+        reflen = np.zeros(len(st), dtype=np.int64)
+        if len(op):
+            rid = np.repeat(np.arange(len(st)), n_cig)
+            np.add.at(reflen, rid, np.where(_REF_CONSUMING[op], ln, 0))
+        reflen[(A.flag & 4) != 0] = 0
+        A.endpos = A.pos.astype(np.int64) + np.where(reflen > 0, reflen, 1)
+        A.name_prev = None
+        self._all = A
+        self._contig_cache = {}
+
+    def get_tid(self, chrom):
+        return self._tid_of[chrom]
+
+    def contig_batch(self, chrom):
+        """All records placed on `chrom`, file order."""
+        if chrom not in self._contig_cache:
+            tid = self._tid_of[chrom]
+            idx = np.flatnonzero(self._tid == tid)
+            b = self._all.subset(idx)
+            b.tid = tid
+            if len(idx) > 1 and np.any(np.diff(b.pos) < 0):
+                raise ValueError('BAM file is not coordinate sorted: %r' % self.filename)
+            self._contig_cache[chrom] = b
+        return self._contig_cache[chrom]
+
+    def region_batch(self, chrom, start, end):
+        """Records the region iterator yields for chrom:[start, end)."""
+        b = self.contig_batch(chrom)
+        m = (b.pos < end) & (b.endpos > start)
+        if m.all():
+            return b
+        sub = b.subset(np.flatnonzero(m))
+        sub.tid = b.tid
+        return sub
+
+
+_bam_cache = {}
+
+
+def open_bam(f):
+    """BamFile for a path / BamFile / foreign object with .filename (small in-process cache)."""
+    if isinstance(f, BamFile):
+        return f
+    path = _path_of(f)
+    key = (os.path.abspath(path), os.path.getmtime(path), os.path.getsize(path))
+    bam = _bam_cache.get(key)
+    if bam is None:
+        if len(_bam_cache) >= 4:
+            _bam_cache.pop(next(iter(_bam_cache)))
+        bam = _bam_cache[key] = BamFile(path)
+    return bam
+
+
+# ------------------------------------------------------------------------------ FASTA
+
+class FastaFile(object):
+    """Indexed FASTA access: uses ``<path>.fai`` when present, else scans the file once."""
+
+    def __init__(self, path):
+        self.filename = _path_of(path)
+        self._index = {}
+        self.references = []
+        fai = self.filename + '.fai'
+        if os.path.exists(fai):
+            with open(fai) as fh:
+                for line in fh:
+                    f = line.rstrip('\n').split('\t')
+                    if len(f) >= 5:
+                        self._index[f[0]] = tuple(int(x) for x in f[1:5])
+                        self.references.append(f[0])
+        else:
+            self._scan()
+        self._cache = (None, None)
+
+    def _scan(self):
+        with open(self.filename, 'rb') as fh:
+            off = 0
+            name, length, seq_off, lb, lw = None, 0, 0, 0, 0
+            for line in fh:
+                if line.startswith(b'>'):
+                    if name is not None:
+                        self._index[name] = (length, seq_off, lb, lw)
+                    name = line[1:].split()[0].decode('ascii')
+                    self.references.append(name)
+                    length, seq_off, lb, lw = 0, off + len(line), 0, 0
+                else:
+                    s = line.rstrip(b'\r\n')
+                    if lb == 0:
+                        lb, lw = len(s), len(line)
+                    length += len(s)
+                off += len(line)
+            if name is not None:
+                self._index[name] = (length, seq_off, lb, lw)
+
+    def get_reference_length(self, chrom):
+        return self._index[chrom][0] if chrom in self._index else 0
+
+    def contig(self, chrom):
+        """Whole contig as a uint8 array, case preserved (empty if unknown)."""
+        if self._cache[0] == chrom:
+            return self._cache[1]
+        if chrom not in self._index:
+            a = np.zeros(0, dtype=np.uint8)
+        else:
+            length, off, lb, lw = self._index[chrom]
+            nlines = (length + lb - 1) // lb if lb else 0
+            with open(self.filename, 'rb') as fh:
+                fh.seek(off)
+                raw = fh.read(length + nlines * (lw - lb) if lb else 0)
+            a = np.frombuffer(raw, dtype=np.uint8)
+            a = a[(a != 10) & (a != 13)][:length].copy()
+        self._cache = (chrom, a)
+        return a
+
+    def fetch(self, chrom, start, end):
+        """bytes of chrom[start:end], clipped to the contig like faidx."""
+        a = self.contig(chrom)
+        start = max(0, int(start))
+        end = min(len(a), int(end))
+        return a[start:end].tobytes() if end > start else b''
+
+
+_fa_cache = {}
+
+
+def open_fasta(f):
+    if f is None or isinstance(f, FastaFile):
+        return f
+    path = _path_of(f)
+    key = (os.path.abspath(path), os.path.getmtime(path))
+    fa = _fa_cache.get(key)
+    if fa is None:
+        if len(_fa_cache) >= 4:
+            _fa_cache.pop(next(iter(_fa_cache)))
+        fa = _fa_cache[key] = FastaFile(path)
+    return fa

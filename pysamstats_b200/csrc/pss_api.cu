@@ -1,0 +1,454 @@
+// C ABI of libpss_b200 (include/pss_b200.h): argument checking, workspace management,
+// kernel sequencing and the host-buffer (streaming) entry points.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pss_internal.cuh"
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct pss_ctx {
+    int device = 0;
+    char err[512] = {0};
+    int64_t launches = 0;
+    DevBuf ri, rng, qual, pair, next, small;
+    DevBuf hb[20];          // device copies of host batches (*_host entry points)
+    DevBuf outbuf[2], maskbuf[2];
+    SmallState *small_host = nullptr;   // pinned mirror of the device scalars
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    // dominant-kernel timing
+    int timing = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+};
+
+static int fail(pss_ctx *c, int code, const char *fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, PSS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+static int ensure(pss_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.bytes >= bytes) return PSS_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, PSS_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    b.bytes = want;
+    return PSS_OK;
+}
+
+// ---------------------------------------------------------------------------- shapes
+
+static const int32_t kPileupFields[PSS_N_PILEUP_STATS] = {2, 6, 8, 24, 20, 60, 9, 27, 8, 24, 4, 12, 12, 36, 3};
+static const int32_t kBinnedFields[PSS_N_BINNED_STATS] = {3, 9, 3, 11, 6};
+
+extern "C" int32_t pss_pileup_nfields(int32_t stat) {
+    return (stat >= 0 && stat < PSS_N_PILEUP_STATS) ? kPileupFields[stat] : -1;
+}
+extern "C" int32_t pss_binned_nfields(int32_t stat) {
+    return (stat >= 0 && stat < PSS_N_BINNED_STATS) ? kBinnedFields[stat] : -1;
+}
+extern "C" int32_t pss_pileup_needs_ref(int32_t stat) {
+    return stat == PSS_VARIATION || stat == PSS_VARIATION_STRAND || stat == PSS_BASEQ_EXT ||
+           stat == PSS_BASEQ_EXT_STRAND || stat == PSS_COVERAGE_GC;
+}
+extern "C" int32_t pss_pileup_needs_qual(int32_t stat, int32_t min_baseq) {
+    return (stat >= PSS_BASEQ && stat <= PSS_BASEQ_EXT_STRAND) || min_baseq > 0;
+}
+extern "C" int64_t pss_binned_nbins(int64_t start, int64_t end, int32_t window_size) {
+    if (window_size <= 0) return -1;
+    int64_t span = end - start;
+    int64_t n = span > 0 ? (span + window_size - 1) / window_size : 0;
+    return n < 1 ? 1 : n;
+}
+
+// ------------------------------------------------------------------------ life cycle
+
+extern "C" const char *pss_version(void) { return "pss_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int pss_create(int device, pss_ctx **out) {
+    if (!out) return PSS_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return PSS_ECUDA;
+    }
+    pss_ctx *ctx = new pss_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || ensure(ctx, ctx->small, sizeof(SmallState)) != PSS_OK ||
+        cudaMallocHost((void **)&ctx->small_host, sizeof(SmallState)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return PSS_ECUDA;
+    }
+    memset(ctx->small_host, 0, sizeof(SmallState));
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+    }
+    *out = ctx;
+    return PSS_OK;
+}
+
+extern "C" void pss_destroy(pss_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small,
+                     &ctx->outbuf[0], &ctx->outbuf[1], &ctx->maskbuf[0], &ctx->maskbuf[1]};
+    for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+    for (DevBuf &b : ctx->hb) if (b.p) cudaFree(b.p);
+    if (ctx->small_host) cudaFreeHost(ctx->small_host);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx;
+}
+
+extern "C" const char *pss_last_error(const pss_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+extern "C" int64_t pss_launch_count(const pss_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void pss_set_kernel_timing(pss_ctx *ctx, int enabled) { if (ctx) ctx->timing = enabled; }
+
+extern "C" double pss_pileup_kernel_ms(pss_ctx *ctx, int64_t *n_launches) {
+    if (n_launches) *n_launches = 0;
+    if (!ctx || ctx->ev_used == 0) return -1.0;
+    cudaSetDevice(ctx->device);
+    double sum = 0;
+    int64_t n = 0;
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0;
+        if (cudaEventSynchronize(ctx->ev_pool[i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) {
+            sum += ms; ++n;
+        } else cudaGetLastError();
+    }
+    ctx->ev_used = 0;
+    if (n_launches) *n_launches = n;
+    return n ? sum / (double)n : -1.0;
+}
+
+extern "C" int pss_synchronize(pss_ctx *ctx, void *stream) {
+    if (!ctx) return PSS_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->small_host, ctx->small.p, sizeof(SmallState), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (ctx->small_host->unsorted) return fail(ctx, PSS_EUNSORTED, "read batch is not coordinate sorted");
+    return PSS_OK;
+}
+
+// -------------------------------------------------------------------- pileup (device)
+
+static int check_reads(pss_ctx *ctx, const pss_reads *R, bool need_qual) {
+    if (!R) return fail(ctx, PSS_EINVAL, "reads is NULL");
+    if (R->n_reads < 0 || R->n_reads > 0x7fffffff) return fail(ctx, PSS_EINVAL, "n_reads out of range");
+    if (R->n_reads > 0) {
+        if (!R->pos || !R->flag || !R->mapq || !R->tlen || !R->mtid || !R->l_seq || !R->cigar_off ||
+            !R->cigar || !R->seq_off || !R->seq4)
+            return fail(ctx, PSS_EINVAL, "a required read array is NULL");
+        if (need_qual && (!R->qual || !R->qual_off || !R->name_prev))
+            return fail(ctx, PSS_EINVAL, "qual / qual_off / name_prev are required for this request");
+    }
+    return PSS_OK;
+}
+
+// k_prep + depth cap (+ overlap tweak): everything that depends on the batch and on the
+// read-level parameters but not on the output position range.
+static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_depth, int min_mapq, int no_dup,
+                         bool need_qual, uint8_t *qual_dst, int32_t *pair_dst, cudaStream_t s) {
+    int64_t n = R->n_reads;
+    int rc;
+    if ((rc = ensure(ctx, ctx->ri, sizeof(RInfo) * (size_t)n)) != PSS_OK) return rc;
+    RInfo *ri = (RInfo *)ctx->ri.p;
+    SmallState *st = (SmallState *)ctx->small.p;
+    CU(launch_prep(*R, stepper, min_mapq, no_dup, ri, st, s, &ctx->launches));
+    int maxcnt = max_depth ? max_depth : 8000;   // A.0
+    CU(launch_admit(ri, n, maxcnt, st, s, &ctx->launches));
+    if (need_qual && n > 0) {
+        if (!qual_dst) {
+            if ((rc = ensure(ctx, ctx->qual, (size_t)R->n_qual_bytes)) != PSS_OK) return rc;
+            qual_dst = (uint8_t *)ctx->qual.p;
+        }
+        if (!pair_dst) {
+            if ((rc = ensure(ctx, ctx->pair, sizeof(int32_t) * (size_t)n)) != PSS_OK) return rc;
+            pair_dst = (int32_t *)ctx->pair.p;
+        }
+        if ((rc = ensure(ctx, ctx->next, sizeof(int32_t) * (size_t)n)) != PSS_OK) return rc;
+        if (R->n_qual_bytes > 0)
+            CU(cudaMemcpyAsync(qual_dst, R->qual, (size_t)R->n_qual_bytes, cudaMemcpyDeviceToDevice, s));
+        CU(launch_overlap(*R, ri, qual_dst, pair_dst, (int32_t *)ctx->next.p, s, &ctx->launches));
+    }
+    return PSS_OK;
+}
+
+static cudaEvent_t next_event(pss_ctx *ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+// tile ranges + the pileup kernel (+ gc) for output positions [start, end)
+static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *P, bool need_qual, int64_t start,
+                     int64_t end, int32_t *out, uint8_t *rowmask, cudaStream_t s) {
+    int64_t npos = end - start;
+    if (npos <= 0) return PSS_OK;
+    int64_t ntiles = (npos + PSS_TILE - 1) / PSS_TILE;
+    if (ntiles > 0x7fffffff) return fail(ctx, PSS_EINVAL, "position range too large for one call");
+    int rc;
+    if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)ntiles)) != PSS_OK) return rc;
+    CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, ntiles,
+                          (int2 *)ctx->rng.p, s, &ctx->launches));
+    PileupArgs a;
+    a.ri = (const RInfo *)ctx->ri.p;
+    a.cigar = R->cigar;
+    a.seq4 = R->seq4;
+    a.qual = need_qual ? (const uint8_t *)ctx->qual.p : nullptr;
+    a.qual_off = need_qual ? R->qual_off : nullptr;
+    a.tlen = (P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND) ? R->tlen : nullptr;
+    a.tile_rng = (const int2 *)ctx->rng.p;
+    a.ref = P->ref; a.ref_start = P->ref_start; a.ref_len = P->ref_len;
+    a.start = start; a.end = end;
+    a.min_baseq = P->min_baseq; a.no_del = P->no_del;
+    a.out = out; a.rowmask = rowmask;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->timing) {
+        e0 = next_event(ctx); e1 = next_event(ctx);
+        if (e0 && e1) CU(cudaEventRecord(e0, s));
+    }
+    CU(launch_pileup(P->stat, a, ntiles, s, &ctx->launches));
+    if (e0 && e1) CU(cudaEventRecord(e1, s));
+    if (P->stat == PSS_COVERAGE_GC)
+        CU(launch_gc(P->ref, P->ref_start, P->ref_len, P->contig_len, start, end, P->window_size, P->window_offset,
+                     out, s, &ctx->launches));
+    return PSS_OK;
+}
+
+static int check_params(pss_ctx *ctx, const pss_pileup_params *P) {
+    if (!P) return fail(ctx, PSS_EINVAL, "params is NULL");
+    if (P->stat < 0 || P->stat >= PSS_N_PILEUP_STATS) return fail(ctx, PSS_EINVAL, "unsupported statistics type: %d", P->stat);
+    if (P->stepper < 0 || P->stepper > 2) return fail(ctx, PSS_EINVAL, "unknown stepper: %d", P->stepper);
+    if (P->end < P->start) return fail(ctx, PSS_EINVAL, "end < start");
+    if (P->max_depth < 0) return fail(ctx, PSS_EINVAL, "max_depth < 0");
+    if (pss_pileup_needs_ref(P->stat) && (!P->ref && P->ref_len > 0)) return fail(ctx, PSS_EINVAL, "ref is NULL");
+    if (P->stat == PSS_COVERAGE_GC && P->window_size <= 0) return fail(ctx, PSS_EINVAL, "window_size <= 0");
+    return PSS_OK;
+}
+
+extern "C" int pss_pileup(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *P, int32_t *out,
+                          uint8_t *rowmask, void *stream) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    if ((rc = check_params(ctx, P)) != PSS_OK) return rc;
+    bool need_qual = pss_pileup_needs_qual(P->stat, P->min_baseq);
+    if ((rc = check_reads(ctx, reads, need_qual)) != PSS_OK) return rc;
+    if (P->end > P->start && (!out || !rowmask)) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = prepare_batch(ctx, reads, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, nullptr, nullptr,
+                            s)) != PSS_OK)
+        return rc;
+    return run_range(ctx, reads, P, need_qual, P->start, P->end, out, rowmask, s);
+}
+
+extern "C" int pss_admit(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth, uint8_t *admitted,
+                         void *stream) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    if ((rc = check_reads(ctx, reads, false)) != PSS_OK) return rc;
+    if (stepper < 0 || stepper > 2) return fail(ctx, PSS_EINVAL, "unknown stepper: %d", stepper);
+    if (reads->n_reads > 0 && !admitted) return fail(ctx, PSS_EINVAL, "admitted is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = prepare_batch(ctx, reads, stepper, max_depth, 0, 0, false, nullptr, nullptr, s)) != PSS_OK) return rc;
+    CU(launch_export_admitted((const RInfo *)ctx->ri.p, reads->n_reads, admitted, s, &ctx->launches));
+    return PSS_OK;
+}
+
+extern "C" int pss_overlap_tweak(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth,
+                                 uint8_t *qual_out, int32_t *pair_first, void *stream) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    if ((rc = check_reads(ctx, reads, true)) != PSS_OK) return rc;
+    if (stepper < 0 || stepper > 2) return fail(ctx, PSS_EINVAL, "unknown stepper: %d", stepper);
+    if (reads->n_reads > 0 && !qual_out) return fail(ctx, PSS_EINVAL, "qual_out is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    return prepare_batch(ctx, reads, stepper, max_depth, 0, 0, true, qual_out, pair_first, s);
+}
+
+// ---------------------------------------------------------------------- pileup (host)
+
+template <class T>
+static int to_device(pss_ctx *ctx, DevBuf &b, const T *host, size_t count, const T **dev, cudaStream_t s) {
+    *dev = nullptr;
+    if (!host) return PSS_OK;
+    int rc = ensure(ctx, b, sizeof(T) * count);
+    if (rc != PSS_OK) return rc;
+    if (count) CU(cudaMemcpyAsync(b.p, host, sizeof(T) * count, cudaMemcpyHostToDevice, s));
+    *dev = (const T *)b.p;
+    return PSS_OK;
+}
+
+static int upload_reads(pss_ctx *ctx, const pss_reads *H, pss_reads *D, bool need_seq, bool need_qual, cudaStream_t s) {
+    *D = *H;
+    size_t n = (size_t)H->n_reads;
+    int rc;
+#define UP(idx, field, count) if ((rc = to_device(ctx, ctx->hb[idx], H->field, (count), &D->field, s)) != PSS_OK) return rc
+    UP(0, pos, n); UP(1, flag, n); UP(2, mapq, n); UP(3, tlen, n); UP(4, mtid, n); UP(5, l_seq, n);
+    UP(6, cigar_off, n + 1); UP(7, cigar, (size_t)H->n_cigar_words); UP(8, seq_off, n + 1);
+    if (need_seq) { UP(9, seq4, (size_t)H->n_seq_bytes); }
+    else {   // never dereferenced, but must be non-NULL for the argument check
+        if ((rc = ensure(ctx, ctx->hb[9], 16)) != PSS_OK) return rc;
+        D->seq4 = (const uint8_t *)ctx->hb[9].p;
+    }
+    if (need_qual) { UP(10, qual_off, n + 1); UP(11, qual, (size_t)H->n_qual_bytes); UP(12, name_prev, n); }
+    else { D->qual_off = nullptr; D->qual = nullptr; D->name_prev = nullptr; }
+#undef UP
+    return PSS_OK;
+}
+
+static bool stat_reads_seq(int stat) {
+    return stat == PSS_VARIATION || stat == PSS_VARIATION_STRAND || stat == PSS_BASEQ_EXT || stat == PSS_BASEQ_EXT_STRAND;
+}
+
+extern "C" int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *P, int32_t *out,
+                               uint8_t *rowmask) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    if ((rc = check_params(ctx, P)) != PSS_OK) return rc;
+    bool need_qual = pss_pileup_needs_qual(P->stat, P->min_baseq);
+    if ((rc = check_reads(ctx, reads, need_qual)) != PSS_OK) return rc;
+    int64_t npos = P->end - P->start;
+    if (npos > 0 && (!out || !rowmask)) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = nullptr;   // default stream for compute, ctx->copy_stream for D2H
+    pss_reads D;
+    // the overlap tweak compares the mates' bases, so qualities imply sequence
+    if ((rc = upload_reads(ctx, reads, &D, stat_reads_seq(P->stat) || need_qual, need_qual, s)) != PSS_OK) return rc;
+    pss_pileup_params Pd = *P;
+    if (P->ref && P->ref_len > 0) {
+        if ((rc = to_device(ctx, ctx->hb[13], P->ref, (size_t)P->ref_len, &Pd.ref, s)) != PSS_OK) return rc;
+    } else Pd.ref = nullptr;
+    if ((rc = prepare_batch(ctx, &D, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, nullptr, nullptr, s)) !=
+        PSS_OK)
+        return rc;
+    const int nf = kPileupFields[P->stat];
+    // position chunks: <= ~256 MB of output each, double buffered against the D2H copies
+    int64_t chunk = ((int64_t)(256ll << 20) / (4ll * nf)) / PSS_TILE * PSS_TILE;
+    if (chunk > npos) chunk = (npos + PSS_TILE - 1) / PSS_TILE * PSS_TILE;
+    if (chunk < PSS_TILE) chunk = PSS_TILE;
+    int k = 0;
+    for (int64_t cs = P->start; cs < P->end; cs += chunk, ++k) {
+        int64_t ce = cs + chunk < P->end ? cs + chunk : P->end;
+        int64_t cn = ce - cs;
+        int b = k & 1;
+        if ((rc = ensure(ctx, ctx->outbuf[b], sizeof(int32_t) * (size_t)nf * (size_t)chunk)) != PSS_OK) return rc;
+        if ((rc = ensure(ctx, ctx->maskbuf[b], (size_t)chunk)) != PSS_OK) return rc;
+        if (k >= 2) CU(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));   // buffer free again
+        if ((rc = run_range(ctx, &D, &Pd, need_qual, cs, ce, (int32_t *)ctx->outbuf[b].p, (uint8_t *)ctx->maskbuf[b].p,
+                            s)) != PSS_OK)
+            return rc;
+        CU(cudaEventRecord(ctx->ev_done[b], s));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+        CU(cudaMemcpy2DAsync(out + (cs - P->start), sizeof(int32_t) * (size_t)npos, ctx->outbuf[b].p,
+                             sizeof(int32_t) * (size_t)cn, sizeof(int32_t) * (size_t)cn, (size_t)nf,
+                             cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaMemcpyAsync(rowmask + (cs - P->start), ctx->maskbuf[b].p, (size_t)cn, cudaMemcpyDeviceToHost,
+                           ctx->copy_stream));
+        CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    }
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return pss_synchronize(ctx, s);
+}
+
+// ------------------------------------------------------------------------------ binned
+
+static int check_binned(pss_ctx *ctx, const pss_reads *R, const pss_binned_params *P, const int32_t *out) {
+    if (!P) return fail(ctx, PSS_EINVAL, "params is NULL");
+    if (P->stat < 0 || P->stat >= PSS_N_BINNED_STATS) return fail(ctx, PSS_EINVAL, "unsupported statistics type: %d", P->stat);
+    if (P->window_size <= 0) return fail(ctx, PSS_EINVAL, "window_size <= 0");
+    if (P->n_bins != pss_binned_nbins(P->start, P->end, P->window_size)) return fail(ctx, PSS_EINVAL, "n_bins mismatch");
+    if (!R) return fail(ctx, PSS_EINVAL, "reads is NULL");
+    if (R->n_reads < 0 || R->n_reads > 0x7fffffff) return fail(ctx, PSS_EINVAL, "n_reads out of range");
+    if (R->n_reads > 0 && (!R->pos || !R->flag || !R->mapq || !R->tlen || !R->mtid))
+        return fail(ctx, PSS_EINVAL, "a required read array is NULL");
+    bool need_cigar = P->stat == PSS_COVERAGE_EXT_BINNED || P->stat == PSS_ALIGNMENT_BINNED;
+    if (R->n_reads > 0 && need_cigar && (!R->cigar || !R->cigar_off)) return fail(ctx, PSS_EINVAL, "cigar arrays are NULL");
+    bool need_ref = P->stat == PSS_COVERAGE_BINNED || P->stat == PSS_COVERAGE_EXT_BINNED;
+    if (need_ref && !P->ref) return fail(ctx, PSS_EINVAL, "ref is NULL");
+    if (!out) return fail(ctx, PSS_EINVAL, "out is NULL");
+    return PSS_OK;
+}
+
+extern "C" int pss_binned(pss_ctx *ctx, const pss_reads *reads, const pss_binned_params *P, int32_t *out, void *stream) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    if ((rc = check_binned(ctx, reads, P, out)) != PSS_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_binned(*reads, *P, out, (cudaStream_t)stream, &ctx->launches));
+    return PSS_OK;
+}
+
+extern "C" int pss_binned_host(pss_ctx *ctx, const pss_reads *H, const pss_binned_params *P, int32_t *out) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    if ((rc = check_binned(ctx, H, P, out)) != PSS_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = nullptr;
+    pss_reads D = *H;
+    size_t n = (size_t)H->n_reads;
+    bool need_cigar = P->stat == PSS_COVERAGE_EXT_BINNED || P->stat == PSS_ALIGNMENT_BINNED;
+#define UP(idx, field, count) if ((rc = to_device(ctx, ctx->hb[idx], H->field, (count), &D.field, s)) != PSS_OK) return rc
+    UP(0, pos, n); UP(1, flag, n); UP(2, mapq, n); UP(3, tlen, n); UP(4, mtid, n);
+    if (need_cigar) { UP(6, cigar_off, n + 1); UP(7, cigar, (size_t)H->n_cigar_words); }
+#undef UP
+    pss_binned_params Pd = *P;
+    if (P->ref && P->ref_len > 0) {
+        if ((rc = to_device(ctx, ctx->hb[13], P->ref, (size_t)P->ref_len, &Pd.ref, s)) != PSS_OK) return rc;
+    }
+    const int nf = kBinnedFields[P->stat];
+    size_t obytes = sizeof(int32_t) * (size_t)nf * (size_t)P->n_bins;
+    if ((rc = ensure(ctx, ctx->outbuf[0], obytes)) != PSS_OK) return rc;
+    CU(launch_binned(D, Pd, (int32_t *)ctx->outbuf[0].p, s, &ctx->launches));
+    CU(cudaMemcpyAsync(out, ctx->outbuf[0].p, obytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return PSS_OK;
+}

@@ -1,0 +1,87 @@
+// Internal declarations shared by the CUDA translation units of libpss_b200.
+// Not part of the public ABI (that is include/pss_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pss_b200.h"
+
+// ---------------------------------------------------------------------------------
+// Per-read record produced by k_prep and consumed by every later kernel.  32 bytes,
+// so a tile's candidate reads are one contiguous, 16-byte aligned span in HBM.
+// ---------------------------------------------------------------------------------
+struct __align__(16) RInfo {
+    int32_t pos;        // leftmost reference position
+    int32_t end;        // htslib bam_endpos(): pos + reference length (>= pos + 1)
+    uint32_t cls;       // CLS_* bits below
+    uint32_t n_cigar;
+    int64_t cigar_off;  // word index into the batch's cigar array
+    int64_t seq_off;    // byte index into the batch's seq4 array
+};
+
+enum : uint32_t {
+    CLS_REV = 1u << 0,        // BAM_FREVERSE
+    CLS_PP = 1u << 1,         // BAM_FPROPER_PAIR
+    CLS_ADMITTED = 1u << 2,   // enters htslib's pileup list (stepper passed, mapped, not capped)
+    CLS_COUNTED = 1u << 3,    // ADMITTED and passes the read-level filters min_mapq / no_dup
+    CLS_EXT_SHIFT = 4,        // bits 4..11: all, pp, mate_unmapped, mate_other_chr,
+                              //             mate_same_strand, faceaway, softclipped, duplicate
+    CLS_PAIRED = 1u << 12,    // tlen "paired" class: mate mapped on the same contig
+    CLS_SIMPLE = 1u << 13,    // exactly one CIGAR op and it is M / = / X
+    CLS_HASSEQ = 1u << 14,    // l_seq > 0
+    CLS_NOREF = 1u << 15,     // CIGAR consumes no reference (end == pos + 1 by convention)
+    CLS_MAPQ_SHIFT = 16,      // bits 16..23: mapping quality
+    CLS_PUSHDEL = 1u << 24,   // reaches bam_plp_push but is ignored there (unmapped, nofilter)
+    CLS_DROPPED = 1u << 25,   // refused by the max_depth rule
+    CLS_OVL = 1u << 26,       // qualifies for the mate-overlap hash (A.3)
+};
+
+// BAM CIGAR op codes
+enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X };
+__host__ __device__ __forceinline__ bool op_is_match(int op) { return op == OP_M || op == OP_EQ || op == OP_X; }
+
+#define PSS_TILE 256          // positions per CTA in the pileup kernel (one per thread)
+#define PSS_CHUNK 128         // candidate reads staged in shared memory at a time
+
+struct PileupArgs {
+    const RInfo *ri;
+    const uint32_t *cigar;
+    const uint8_t *seq4;
+    const uint8_t *qual;        // tweaked qualities (workspace copy) or NULL
+    const int64_t *qual_off;
+    const int32_t *tlen;
+    const int2 *tile_rng;       // candidate read range [x, y) per tile
+    const uint8_t *ref;
+    int64_t ref_start, ref_len;
+    int64_t start, end;         // output position range
+    int32_t min_baseq;
+    int32_t no_del;
+    int32_t *out;
+    uint8_t *rowmask;
+};
+
+// device scalars shared between the small kernels
+struct SmallState {
+    int32_t maxspan;       // max over reads of end - pos
+    int32_t unsorted;      // != 0 when pos[] decreases somewhere
+    int32_t first_unsafe;  // depth-cap: first / last read index whose admission is not
+    int32_t last_unsafe;   //            provably unconstrained (else INT_MAX / -1)
+};
+
+// ---- kernel launchers (defined in the .cu files) ----------------------------------
+cudaError_t launch_prep(const pss_reads &R, int stepper, int min_mapq, int no_dup, RInfo *ri,
+                        SmallState *st, cudaStream_t s, int64_t *launches);
+cudaError_t launch_admit(RInfo *ri, int64_t n, int maxcnt, SmallState *st, cudaStream_t s,
+                         int64_t *launches);
+cudaError_t launch_overlap(const pss_reads &R, const RInfo *ri, uint8_t *qual_work, int32_t *pair_first,
+                           int32_t *name_next, cudaStream_t s, int64_t *launches);
+cudaError_t launch_tile_ranges(const RInfo *ri, int64_t n, const SmallState *st, int64_t start,
+                               int64_t ntiles, int2 *rng, cudaStream_t s, int64_t *launches);
+cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, cudaStream_t s, int64_t *launches);
+cudaError_t launch_gc(const uint8_t *ref, int64_t ref_start, int64_t ref_len, int64_t contig_len,
+                      int64_t start, int64_t end, int window_size, int window_offset, int32_t *out_gc,
+                      cudaStream_t s, int64_t *launches);
+cudaError_t launch_binned(const pss_reads &R, const pss_binned_params &P, int32_t *out, cudaStream_t s,
+                          int64_t *launches);
+cudaError_t launch_export_admitted(const RInfo *ri, int64_t n, uint8_t *admitted, cudaStream_t s,
+                                   int64_t *launches);

@@ -1,0 +1,265 @@
+"""The engine seam: drop-in for the reference's compiled module ``pysamstats/opt.pyx``.
+
+The reference's python layer calls ``opt.iter_pileup(stat, ...)`` (``pileup.py:91``) and
+``opt.iter_binned(stat, ...)`` (``binned.py:68``) with an accumulator object taken from its
+class tables and consumes a generator of dicts.  The same names live here: the "stat"
+objects only describe WHICH statistic to compute (the per-read ``recv`` protocol of the
+reference is ``cdef`` and never was a python-level plugin point), the
+work is done by CUDA kernels behind the C ABI (``include/pss_b200.h``).
+
+Two levels are offered:
+
+* ``pileup_tables`` / ``binned_tables`` -- per-contig column arrays straight from the
+  engine (what ``load_*`` assembles recarrays from, no per-row python);
+* ``iter_pileup`` / ``iter_binned`` -- the reference's generator-of-dicts interface, built
+  lazily on top of the tables.
+
+There is no CPU path: everything below ends in ``_cabi.get_context()``, which raises when
+the CUDA library or a GPU is missing.
+"""
+import numpy as np
+
+from . import _cabi, bamio, config
+
+
+# --------------------------------------------------------------------- stat descriptors
+
+class PileupStat(object):
+    """Which per-position statistic to compute (reference: ``opt.pyx:75-81``)."""
+    name = None
+
+    def __init__(self):
+        self.window_size = 300
+        self.window_offset = None
+
+
+class BinnedStat(object):
+    """Which per-window statistic to compute (reference: ``opt.pyx:1542-1548``)."""
+    name = None
+
+
+def _pileup_cls(clsname, stat):
+    return type(clsname, (PileupStat,), {'name': stat, '__doc__': 'reference: opt.pyx class %s' % clsname})
+
+
+Coverage = _pileup_cls('Coverage', 'coverage')
+CoverageStrand = _pileup_cls('CoverageStrand', 'coverage_strand')
+CoverageExt = _pileup_cls('CoverageExt', 'coverage_ext')
+CoverageExtStrand = _pileup_cls('CoverageExtStrand', 'coverage_ext_strand')
+Variation = _pileup_cls('Variation', 'variation')
+VariationStrand = _pileup_cls('VariationStrand', 'variation_strand')
+Tlen = _pileup_cls('Tlen', 'tlen')
+TlenStrand = _pileup_cls('TlenStrand', 'tlen_strand')
+Mapq = _pileup_cls('Mapq', 'mapq')
+MapqStrand = _pileup_cls('MapqStrand', 'mapq_strand')
+Baseq = _pileup_cls('Baseq', 'baseq')
+BaseqStrand = _pileup_cls('BaseqStrand', 'baseq_strand')
+BaseqExt = _pileup_cls('BaseqExt', 'baseq_ext')
+BaseqExtStrand = _pileup_cls('BaseqExtStrand', 'baseq_ext_strand')
+
+
+class CoverageGC(PileupStat):
+    """reference: ``opt.pyx:1471-1481`` (window_offset defaults to window_size // 2)."""
+    name = 'coverage_gc'
+
+    def __init__(self, window_size=300, window_offset=None):
+        self.window_size = window_size
+        self.window_offset = window_size // 2 if window_offset is None else window_offset
+
+
+def _binned_cls(clsname, stat):
+    return type(clsname, (BinnedStat,), {'name': stat, '__doc__': 'reference: opt.pyx class %s' % clsname})
+
+
+CoverageBinned = _binned_cls('CoverageBinned', 'coverage')
+CoverageExtBinned = _binned_cls('CoverageExtBinned', 'coverage_ext')
+MapqBinned = _binned_cls('MapqBinned', 'mapq')
+AlignmentBinned = _binned_cls('AlignmentBinned', 'alignment')
+TlenBinned = _binned_cls('TlenBinned', 'tlen')
+
+
+# ------------------------------------------------------------------------------ helpers
+
+def normalise_coords(alignmentfile, chrom, start, end, one_based):
+    """Zero-based half-open coordinates with defaults filled in (``opt.pyx:2105-2130``,
+    including its quirk that a one-based ``end`` is decremented and stays exclusive)."""
+    if chrom is None:
+        return None, None
+    assert chrom in alignmentfile.references, 'chromosome not in SAM references: %s' % chrom
+    if one_based:
+        start = start - 1 if start is not None else None
+        end = end - 1 if end is not None else None
+    chrlen = alignmentfile.lengths[alignmentfile.references.index(chrom)]
+    if start is None:
+        start = 0
+    if end is None:
+        end = chrlen
+    if end > chrlen:
+        end = chrlen
+    return start, end
+
+
+def _reads_struct(batch, need_qual):
+    batch.padded()
+    d = {k: getattr(batch, k) for k in _cabi.READ_FIELDS}
+    d['tid'] = batch.tid
+    d['n_reads'] = batch.n_reads
+    if not need_qual:
+        d['qual'] = d['qual_off'] = d['name_prev'] = None
+        d['n_qual_bytes'] = 0
+    return _cabi.make_reads_struct(d)
+
+
+def _ref_column(refseq, pos):
+    """Upper-cased reference base per position, '' beyond the FASTA (``opt.pyx:1987-1994``)."""
+    col = np.zeros(len(pos), dtype='S1')
+    ok = (pos >= 0) & (pos < len(refseq))
+    b = refseq[pos[ok]]
+    lower = (b >= 97) & (b <= 122)
+    b = np.where(lower, b - 32, b).astype(np.uint8)
+    col[ok] = b.view('S1')
+    return col
+
+
+# ------------------------------------------------------------------------ pileup tables
+
+def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start=None, end=None,
+                  one_based=False, truncate=False, stepper='all', max_depth=8000, min_mapq=0, min_baseq=0,
+                  no_del=False, no_dup=False):
+    """Yield ``(chrom, pos, ref, fields)`` per contig: ``pos`` int64 (already one-based if
+    asked), ``ref`` an ``S1`` column or None, ``fields`` a dict name -> int32 column.
+
+    Row selection follows ``iter_pileup_default`` / ``iter_pileup_padded_chrom``
+    (``opt.pyx:1846-1863``, ``:1936-1984``): a row for every column htslib builds, plus -- with
+    ``pad`` -- every position of ``[start, end)``; with ``truncate`` only ``[start, end)``.
+    """
+    if stepper not in _cabi.STEPPERS:
+        raise ValueError('unknown stepper: %r' % (stepper,))     # pysam raises ValueError too
+    name = stat.name
+    bam = bamio.open_bam(alignmentfile)
+    fa = bamio.open_fasta(fafile)
+    ctx = _cabi.get_context()
+    names = config.value_fields(name)
+    need_qual = bool(ctx.lib.pss_pileup_needs_qual(_cabi.PILEUP_STATS.index(name), int(min_baseq)))
+    needs_ref = bool(ctx.lib.pss_pileup_needs_ref(_cabi.PILEUP_STATS.index(name)))
+    if chrom is not None:
+        contigs = [chrom]
+    else:
+        contigs = list(bam.references)
+        start = end = None                                        # opt.pyx:2111-2112
+    for c in contigs:
+        if pad:
+            assert c is not None, 'chromosome is None'
+        s, e = normalise_coords(bam, c, start, end, one_based)
+        batch = bam.region_batch(c, s, e)
+        n = batch.n_reads
+        if n == 0 and not pad:
+            continue
+        if truncate:
+            lo, hi = s, e
+        elif n:
+            lo, hi = int(batch.pos[0]), int(batch.endpos.max())
+            if pad:
+                lo, hi = min(lo, s), max(hi, e)
+        else:
+            lo, hi = s, e
+        npos = hi - lo
+        if npos <= 0:
+            continue
+        refseq = fa.contig(c) if (fa is not None and needs_ref) else np.zeros(0, np.uint8)
+        params = ctx.pileup_params(name, stepper=stepper, max_depth=max_depth, min_mapq=min_mapq,
+                                   min_baseq=min_baseq, no_del=no_del, no_dup=no_dup,
+                                   window_size=stat.window_size, window_offset=stat.window_offset,
+                                   start=lo, end=hi, ref=refseq if len(refseq) else None, ref_start=0,
+                                   ref_len=len(refseq), contig_len=len(refseq))
+        out = np.empty((len(names), npos), dtype=np.int32)
+        rowmask = np.empty(npos, dtype=np.uint8)
+        ctx.pileup_host(_reads_struct(batch, need_qual), params, out, rowmask)
+        rows = rowmask.view(bool)
+        if pad:
+            rows = rows.copy()
+            rows[max(s, lo) - lo:max(min(e, hi) - lo, 0)] = True
+        if rows.all():
+            pos = np.arange(lo, hi, dtype=np.int64)
+            fields = {f: out[j] for j, f in enumerate(names)}
+        else:
+            sel = np.flatnonzero(rows)
+            pos = sel.astype(np.int64) + lo
+            fields = {f: out[j][sel] for j, f in enumerate(names)}
+        ref = _ref_column(refseq, pos) if name in config.ref_column_types else None
+        if 'gc' in fields and len(pos) and fields['gc'].min() < 0:
+            # the reference stores gc = -1 for an empty window into a u1 column, which numpy
+            # refuses
+            raise OverflowError('Python integer -1 out of bounds for uint8')
+        if one_based:
+            pos = pos + 1
+        yield c, pos, ref, fields
+
+
+def iter_pileup(stat, alignmentfile, fafile, pad, **kwargs):
+    """Generator of one dict per genome position -- the reference's ``opt.iter_pileup``
+    (``opt.pyx:1827-1843``), same keyword arguments."""
+    for chrom, pos, ref, fields in pileup_tables(stat, alignmentfile, fafile, pad, **kwargs):
+        names = list(fields)
+        cols = [fields[f].tolist() for f in names]
+        refs = [r.decode('ascii') for r in ref.tolist()] if ref is not None else None
+        for i, p in enumerate(pos.tolist()):
+            rec = {f: col[i] for f, col in zip(names, cols)}
+            if refs is not None:
+                rec['ref'] = refs[i]
+            rec['chrom'] = chrom
+            rec['pos'] = p
+            yield rec
+
+
+# ------------------------------------------------------------------------ binned tables
+
+def binned_tables(stat, alignmentfile, fafile=None, chrom=None, window_size=300, window_offset=None,
+                  start=None, end=None, one_based=False, min_mapq=0, no_dup=False):
+    """Yield ``(chrom, pos, None, fields)`` per contig for a binned statistic
+    (``opt.pyx:1997-2102``)."""
+    name = stat.name
+    bam = bamio.open_bam(alignmentfile)
+    fa = bamio.open_fasta(fafile)
+    ctx = _cabi.get_context()
+    names = config.value_fields_binned(name)
+    if window_offset is None:
+        window_offset = window_size / 2          # opt.pyx:2006-2007: a float ...
+    window_offset = int(window_offset)           # ... truncated by the typed C int argument
+    window_size = int(window_size)
+    need_ref = name in ('coverage', 'coverage_ext')
+    if need_ref and fa is None:
+        raise ValueError('reference sequence is required; please provide fafile argument')
+    if chrom is not None:
+        contigs = [chrom]
+    else:
+        contigs = list(bam.references)
+        start = end = None
+    for c in contigs:
+        assert c is not None, 'chromosome is None'
+        s, e = normalise_coords(bam, c, start, end, one_based)
+        batch = bam.region_batch(c, s, e)
+        refseq = fa.contig(c) if need_ref else None
+        params = ctx.binned_params(name, s, e, window_size, min_mapq=min_mapq, no_dup=no_dup,
+                                   ref=refseq, ref_start=0, ref_len=len(refseq) if need_ref else 0)
+        nb = int(params.n_bins)
+        out = np.empty((len(names), nb), dtype=np.int32)
+        ctx.binned_host(_reads_struct(batch, False), params, out)
+        pos = s + np.arange(nb, dtype=np.int64) * window_size + window_offset
+        if one_based:
+            pos = pos + 1
+        yield c, pos, None, {f: out[j] for j, f in enumerate(names)}
+
+
+def iter_binned(stat, alignmentfile, fafile, chrom, window_size=300, window_offset=None, **kwargs):
+    """Generator of one dict per window -- the reference's ``opt.iter_binned``
+    (``opt.pyx:1997-2023``)."""
+    for c, pos, _, fields in binned_tables(stat, alignmentfile, fafile, chrom, window_size, window_offset,
+                                           **kwargs):
+        names = list(fields)
+        cols = [fields[f].tolist() for f in names]
+        for i, p in enumerate(pos.tolist()):
+            rec = {f: col[i] for f, col in zip(names, cols)}
+            rec['chrom'] = c
+            rec['pos'] = p
+            yield rec

@@ -1,0 +1,62 @@
+"""Array assembly for ``load_*`` (reference: ``pysamstats/util.py:31-81``).
+
+The reference turns a generator of dicts into a structured array with ``np.fromiter``; here
+the engine already returns columns, so the array is filled column-wise.  The typing rules
+are the reference's: default dtype list per statistic, ``chrom`` widened to the longest
+contig name of the file, user dtype overrides, optional field subset (a single field
+gives a plain ndarray, unknown fields raise ``ValueError``).
+"""
+import numpy as np
+
+from . import bamio
+
+
+def flatten(recs, *fields):
+    """Convert a record (dict) iterator to a row (tuple) iterator (``util.py:7-28``)."""
+    from operator import itemgetter
+    getter = itemgetter(*fields)
+    return (getter(rec) for rec in recs)
+
+
+def determine_max_seqid(alignmentfile):
+    """Longest contig name in the header (``util.py:76-81``)."""
+    return max(len(x) for x in bamio.open_bam(alignmentfile).references)
+
+
+def load_stats(tablefun, default_dtype, user_dtype, user_fields, **kwargs):
+    """Run ``tablefun(**kwargs)`` (a generator of per-contig column tables, see
+    ``opt.pileup_tables``) and assemble the structured array ``load_*`` returns."""
+    default_fields = [t[0] for t in default_dtype]
+    if user_fields is None:
+        fields = default_fields
+    else:
+        fields = [user_fields] if isinstance(user_fields, str) else list(user_fields)
+        if any(f not in default_fields for f in fields):
+            raise ValueError('invalid fields: %r' % (user_fields,))
+    dtype = dict(default_dtype)
+    dtype['chrom'] = 'S{0}'.format(determine_max_seqid(kwargs['alignmentfile']))
+    if user_dtype is not None:
+        dtype.update(dict(user_dtype))
+    single = len(fields) == 1
+    dt = np.dtype(dtype[fields[0]] if single else [(f, dtype[f]) for f in fields])
+
+    parts = list(tablefun(**kwargs))
+    n = sum(len(p[1]) for p in parts)
+    a = np.zeros(n, dtype=dt)
+    o = 0
+    for chrom, pos, ref, cols in parts:
+        m = len(pos)
+        for f in fields:
+            dst = a[o:o + m] if single else a[f][o:o + m]
+            if f == 'chrom':
+                dst[...] = chrom.encode('ascii')
+            elif f == 'pos':
+                dst[...] = pos
+            elif f == 'ref':
+                dst[...] = ref
+            else:
+                dst[...] = cols[f]
+        o += m
+    if not single:
+        a = a.view(np.recarray)
+    return a

@@ -1,0 +1,214 @@
+"""GPU: the parity tests proper.  Everything goes through the public API (and therefore the
+C ABI, ``pss_pileup_host`` / ``pss_binned_host``) and is compared bit-exactly with
+
+* the reference's golden file ``regression.npz`` (test_regression.py:34-58),
+* the reference's known-answer tests (test_pileup.py:939-1102, test_binned.py:583-626),
+* the CPU oracle for everything the golden vectors do not pin (filters, steppers, rna,
+  deep, one_based, upper-case FASTA -- the cases of test_pileup.py:25-61 / test_binned.py:21-53).
+"""
+import numpy as np
+import pytest
+
+import pysamstats_b200 as pysamstats
+from pysamstats_b200 import config
+from oracle import bamread, oracle as orc
+from _util import fx, assert_recarrays_equal
+
+pytestmark = pytest.mark.gpu
+
+WITHREF = ('variation', 'variation_strand', 'baseq_ext', 'baseq_ext_strand', 'coverage_gc')
+
+
+@pytest.fixture(scope='module')
+def golden():
+    return np.load(fx('regression.npz'))
+
+
+@pytest.fixture(scope='module')
+def obam():
+    return {n: bamread.Bam(fx(n + '.bam')) for n in ('test', 'deep', 'rna', 'longcontignames')}
+
+
+@pytest.fixture(scope='module')
+def ofa():
+    return bamread.Fasta(fx('ref.fa'))
+
+
+def _load(stat, bam, **kw):
+    fa = fx(kw.pop('fasta', 'ref.fa')) if stat in WITHREF else None
+    return getattr(pysamstats, 'load_' + stat)(fx(bam + '.bam'), fafile=fa, **kw)
+
+
+def _oracle(stat, obam, ofa, bam, **kw):
+    kw.pop('fasta', None)
+    return orc.load_pileup(stat, obam[bam], ofa if stat in WITHREF else None, **kw)
+
+
+# ---- golden file -------------------------------------------------------------------
+
+@pytest.mark.parametrize('stat', config.pileup_types)
+def test_regression_pileup(stat, golden):
+    assert_recarrays_equal(golden[stat], _load(stat, 'test'), stat)
+
+
+@pytest.mark.parametrize('stat', config.binned_types)
+def test_regression_binned(stat, golden):
+    a = getattr(pysamstats, 'load_%s_binned' % stat)(fx('test.bam'), fafile=fx('ref.fa'))
+    assert_recarrays_equal(golden[stat + '_binned'], a, stat + '_binned')
+
+
+# ---- differential vs the oracle (the reference's compare_stats cases) -----------------
+
+FILTERS = dict(min_mapq=1, min_baseq=17, no_del=True, no_dup=True)
+
+
+@pytest.mark.parametrize('stat', config.pileup_types)
+def test_region_and_filters(stat, obam, ofa):
+    region = dict(chrom='Pf3D7_01_v3', start=0, end=2000)
+    for kw in (dict(region, one_based=False), dict(region, one_based=True), dict(region, **FILTERS),
+               dict(FILTERS), dict(min_baseq=30), dict(no_del=True), dict(min_mapq=30)):
+        assert_recarrays_equal(_oracle(stat, obam, ofa, 'test', **kw), _load(stat, 'test', **kw),
+                               '%s %r' % (stat, kw))
+
+
+@pytest.mark.parametrize('stat', ['variation', 'variation_strand', 'baseq_ext', 'baseq_ext_strand', 'coverage',
+                                  'coverage_ext', 'baseq', 'mapq', 'tlen'])
+def test_rna_spliced(stat, obam, ofa):
+    for kw in (dict(), dict(no_del=True), dict(min_baseq=20), dict(pad=True, chrom='Pf3D7_01_v3', start=900,
+                                                                  end=1100)):
+        assert_recarrays_equal(_oracle(stat, obam, ofa, 'rna', **kw), _load(stat, 'rna', **kw),
+                               '%s rna %r' % (stat, kw))
+
+
+@pytest.mark.parametrize('stat', ['variation', 'baseq_ext_strand', 'coverage_gc'])
+def test_uppercase_fasta(stat, obam):
+    ofa_up = bamread.Fasta(fx('ref.upper.fa'))
+    e = orc.load_pileup(stat, obam['test'], ofa_up, chrom='Pf3D7_01_v3', start=0, end=2000)
+    a = _load(stat, 'test', fasta='ref.upper.fa', chrom='Pf3D7_01_v3', start=0, end=2000)
+    assert_recarrays_equal(e, a, stat)
+
+
+@pytest.mark.parametrize('stat', ['coverage', 'coverage_ext_strand', 'variation_strand', 'baseq_strand', 'tlen_strand',
+                                  'mapq_strand'])
+@pytest.mark.parametrize('max_depth', [8000, 100, 1, 1000000])
+def test_deep_vs_oracle(stat, max_depth, obam, ofa):
+    for kw in (dict(max_depth=max_depth), dict(max_depth=max_depth, min_baseq=17, no_dup=True)):
+        assert_recarrays_equal(_oracle(stat, obam, ofa, 'deep', **kw), _load(stat, 'deep', **kw),
+                               '%s deep %r' % (stat, kw))
+
+
+@pytest.mark.parametrize('stepper', ['all', 'nofilter', 'samtools'])
+def test_steppers_vs_oracle(stepper, obam, ofa):
+    lc = obam['longcontignames']
+    # contigs with the most records exercise DUP / SECONDARY / unmapped handling
+    counts = np.bincount(lc.tid[lc.tid >= 0], minlength=len(lc.references))
+    for tid in np.argsort(counts)[::-1][:25]:
+        c = lc.references[tid]
+        for stat in ('coverage_ext', 'baseq', 'mapq_strand'):
+            kw = dict(chrom=c, stepper=stepper)
+            assert_recarrays_equal(_oracle(stat, obam, ofa, 'longcontignames', **kw),
+                                   _load(stat, 'longcontignames', **kw), '%s %s %s' % (stat, c, stepper))
+    kw = dict(stepper=stepper, no_dup=True)
+    assert_recarrays_equal(_oracle('coverage', obam, ofa, 'longcontignames', **kw),
+                           _load('coverage', 'longcontignames', **kw), 'wg coverage %s' % stepper)
+
+
+# ---- the reference's known-answer tests ------------------------------------------------
+
+def test_pileup_truncate_kat():
+    for stat in config.pileup_types:
+        a = _load(stat, 'test', chrom='Pf3D7_01_v3', start=2000, end=2100, one_based=False, truncate=False)
+        assert (a['pos'][0], a['pos'][-1]) == (1952, 2154), stat
+        a = _load(stat, 'test', chrom='Pf3D7_01_v3', start=2000, end=2100, one_based=False, truncate=True)
+        assert (a['pos'][0], a['pos'][-1]) == (2000, 2099), stat
+
+
+def test_pileup_pad_kat():
+    for stat in config.pileup_types:
+        a = _load(stat, 'test', chrom='Pf3D7_01_v3', start=0, end=20000, pad=False)
+        assert (a['pos'][0], a['pos'][-1]) == (924, 9935), stat
+        a = _load(stat, 'test', chrom='Pf3D7_01_v3', start=0, end=20000, pad=True)
+        assert (a['pos'][0], a['pos'][-1]) == (0, 19999) and np.all(np.diff(a['pos']) == 1), stat
+
+
+def test_pileup_pad_wg_kat():
+    for stat in config.pileup_types:
+        a = _load(stat, 'test', pad=False)
+        assert sorted(set(a['chrom'])) == [b'Pf3D7_01_v3', b'Pf3D7_02_v3']
+        x = a[a['chrom'] == b'Pf3D7_01_v3']
+        assert (x['pos'][0], x['pos'][-1]) == (924, 9935)
+        x = a[a['chrom'] == b'Pf3D7_02_v3']
+        assert (x['pos'][0], x['pos'][-1]) == (926, 10074)
+        a = _load(stat, 'test', pad=True)
+        assert sorted(set(a['chrom'])) == [b'Pf3D7_01_v3', b'Pf3D7_02_v3', b'Pf3D7_03_v3']
+        for c, last in ((b'Pf3D7_01_v3', 50000), (b'Pf3D7_02_v3', 60000), (b'Pf3D7_03_v3', 70000)):
+            x = a[a['chrom'] == c]
+            assert (x['pos'][0], x['pos'][-1]) == (0, last)
+
+
+def test_pileup_limit_kat():
+    for stat in config.pileup_types:
+        assert _load(stat, 'deep', fields=['reads_all'], max_depth=1000000)[70] == 26169, stat
+        assert _load(stat, 'deep', fields=['reads_all'], max_depth=12000)[70] == 12046, stat
+        assert _load(stat, 'deep', fields=['reads_all'])[70] == 8052, stat
+
+
+def test_long_contig_name_kat():
+    label = 'AS2_scf7180000696055'
+    x = pysamstats.load_coverage(fx('longcontignames.bam'), chrom=label)
+    assert len(label) == x.dtype['chrom'].itemsize
+    x = pysamstats.load_coverage(fx('longcontignames.bam'), chrom=label, dtype={'chrom': 'S10'})
+    assert 10 == x.dtype['chrom'].itemsize
+
+
+def test_steppers_kat():
+    seq, pos = 'AS2_scf7180000695891', 14311
+    for exp_all, exp_pp, step in zip([7, 8, 4], [4, 5, 4], ['all', 'nofilter', 'samtools']):
+        a = pysamstats.load_coverage(fx('longcontignames.bam'), chrom=seq, stepper=step, pad=True)
+        assert (a[pos]['reads_all'], a[pos]['reads_pp']) == (exp_all, exp_pp)
+    with pytest.raises(ValueError):
+        pysamstats.load_coverage(fx('longcontignames.bam'), chrom=seq, stepper='notastepper')
+
+
+def test_binned_kats_and_filters(obam, ofa):
+    for stat in config.binned_types:
+        f = getattr(pysamstats, 'load_%s_binned' % stat)
+        a = f(fx('test.bam'), fafile=fx('ref.fa'), chrom='Pf3D7_01_v3', start=1000, end=20000, window_size=200,
+              window_offset=100)
+        assert set(a['chrom']) == {b'Pf3D7_01_v3'} and (a['pos'][0], a['pos'][-1]) == (1100, 19900)
+        a = f(fx('test.bam'), fafile=fx('ref.fa'), window_size=200, window_offset=100)
+        for c, last in ((b'Pf3D7_01_v3', 50100), (b'Pf3D7_02_v3', 60100), (b'Pf3D7_03_v3', 70100)):
+            x = a[a['chrom'] == c]
+            assert (x['pos'][0], x['pos'][-1]) == (100, last)
+        for kw in (dict(chrom='Pf3D7_01_v3', start=0, end=2000, window_size=50),
+                   dict(chrom='Pf3D7_01_v3', start=1000, end=3000, window_size=77, window_offset=3, one_based=True),
+                   dict(min_mapq=1, no_dup=True), dict(window_size=1000, min_mapq=30)):
+            e = orc.load_binned(stat, obam['test'], ofa, **kw)
+            assert_recarrays_equal(e, f(fx('test.bam'), fafile=fx('ref.fa'), **kw), '%s_binned %r' % (stat, kw))
+        for bam in ('longcontignames', 'deep', 'rna'):
+            c = obam[bam].references[int(np.bincount(obam[bam].tid[obam[bam].tid >= 0]).argmax())]
+            kw = dict(chrom=c, window_size=100, no_dup=True)
+            e = orc.load_binned(stat, obam[bam], ofa if bam != 'longcontignames' else None, **kw) \
+                if not (bam == 'longcontignames' and stat in ('coverage', 'coverage_ext')) else None
+            if e is not None:
+                a = f(fx(bam + '.bam'), fafile=fx('ref.fa') if bam != 'longcontignames' else None, **kw)
+                assert_recarrays_equal(e, a, '%s_binned %s' % (stat, bam))
+
+
+def test_stat_generators_match_load():
+    # stat_* yields dicts equal to the rows load_* returns (compare_iterators, test/util.py:29-51)
+    a = pysamstats.load_variation(fx('test.bam'), fx('ref.fa'), chrom='Pf3D7_01_v3', start=1000, end=1200)
+    recs = list(pysamstats.stat_variation(fx('test.bam'), fx('ref.fa'), chrom='Pf3D7_01_v3', start=1000, end=1200))
+    assert len(recs) == len(a)
+    for rec, row in zip(recs, a):
+        assert set(rec) == set(a.dtype.names)
+        for k in a.dtype.names:
+            v = row[k]
+            assert rec[k] == (v.decode() if isinstance(v, bytes) else v), k
+    b = list(pysamstats.stat_tlen_binned(fx('test.bam'), chrom='Pf3D7_01_v3', start=0, end=3000))
+    assert [r['pos'] for r in b] == list(range(150, 3150, 300))
+    # a file object of another library: only .filename is used
+    class Foreign(object):
+        filename = fx('test.bam').encode()
+    c = pysamstats.load_coverage(Foreign(), chrom='Pf3D7_01_v3', start=1000, end=1200)
+    assert np.array_equal(c['reads_all'], a['reads_all'])

@@ -1,0 +1,128 @@
+"""CPU: host-side logic of the product (decoder, registry, API surface, C-ABI export list)."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pysamstats_b200 as pysamstats
+from pysamstats_b200 import _cabi, bamio, config, opt
+from oracle import bamread
+from _util import fx, ROOT
+
+
+@pytest.mark.parametrize('name', ['test.bam', 'deep.bam', 'rna.bam', 'longcontignames.bam'])
+def test_decoder_matches_oracle_reader(name):
+    mine = bamio.BamFile(fx(name))
+    ref = bamread.Bam(fx(name))
+    assert list(mine.references) == ref.references and list(mine.lengths) == ref.lengths
+    A = mine._all
+    assert np.array_equal(mine._tid, ref.tid)
+    for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq'):
+        assert np.array_equal(getattr(A, k), getattr(ref, k)), k
+    assert np.array_equal(A.endpos, ref.endpos)
+    assert np.array_equal(A.cigar, np.concatenate(ref.cigar))
+    assert np.array_equal(A.seq4, np.concatenate(ref.seq4))
+    assert np.array_equal(A.qual, np.concatenate(ref.qual))
+    assert [bytes(x) for x in A.names] == ref.qname
+
+
+def test_region_batch_rule():
+    mine = bamio.BamFile(fx('test.bam'))
+    ref = bamread.Bam(fx('test.bam'))
+    for (c, s, e) in (('Pf3D7_01_v3', 2000, 2100), ('Pf3D7_02_v3', 0, 60001), ('Pf3D7_03_v3', 0, 70001),
+                      ('Pf3D7_01_v3', 924, 925), ('Pf3D7_01_v3', 9999, 12000)):
+        b = mine.region_batch(c, s, e)
+        idx = ref.region_reads(c, s, e)
+        assert b.n_reads == len(idx)
+        assert np.array_equal(b.pos, ref.pos[idx])
+        assert np.array_equal(b.cigar_off[1:] - b.cigar_off[:-1], [len(ref.cigar[i]) for i in idx])
+        # name_prev links the previous record of the same QNAME inside the batch
+        names = [ref.qname[i] for i in idx]
+        last = {}
+        for j, nm in enumerate(names):
+            assert b.name_prev[j] == last.get(nm, -1)
+            last[nm] = j
+
+
+def test_fasta_fetch():
+    fa = bamio.FastaFile(fx('ref.fa'))
+    ofa = bamread.Fasta(fx('ref.fa'))
+    for c in ('Pf3D7_01_v3', 'Pf3D7_02_v3', 'Pf3D7_03_v3'):
+        assert fa.contig(c).tobytes() == ofa.contig(c)
+    assert fa.fetch('Pf3D7_01_v3', 640850, 640900) == ofa.fetch('Pf3D7_01_v3', 640850, 640900)
+    assert fa.fetch('Pf3D7_01_v3', 700000, 700010) == b''
+
+
+def test_public_api_surface():
+    for t in config.pileup_types:
+        assert getattr(pysamstats, 'stat_' + t).__name__ == 'stat_' + t
+        assert getattr(pysamstats, 'load_' + t).__name__ == 'load_' + t
+        assert hasattr(config, 'dtype_' + t)
+    for t in config.binned_types:
+        assert callable(getattr(pysamstats, 'stat_%s_binned' % t))
+        assert callable(getattr(pysamstats, 'load_%s_binned' % t))
+    sig = inspect.signature(pysamstats.stat_pileup)
+    assert list(sig.parameters) == ['type', 'alignmentfile', 'fafile', 'chrom', 'start', 'end', 'one_based',
+                                    'truncate', 'stepper', 'pad', 'max_depth', 'window_size', 'window_offset',
+                                    'min_mapq', 'min_baseq', 'no_del', 'no_dup']
+    assert sig.parameters['max_depth'].default == 8000 and sig.parameters['stepper'].default == 'all'
+    sig = inspect.signature(pysamstats.load_binned)
+    assert list(sig.parameters) == ['type', 'alignmentfile', 'fafile', 'chrom', 'start', 'end', 'one_based',
+                                    'window_size', 'window_offset', 'min_mapq', 'no_dup', 'dtype', 'fields']
+
+
+def test_errors_without_gpu():
+    # argument errors are raised before the engine is touched (pileup.py:80-89, binned.py:63-66)
+    with pytest.raises(ValueError):
+        pysamstats.stat_pileup('variation', fx('test.bam'))
+    with pytest.raises(ValueError):
+        pysamstats.stat_pileup('nosuchstat', fx('test.bam'))
+    with pytest.raises(ValueError):
+        pysamstats.load_pileup('nosuchstat', fx('test.bam'))
+    with pytest.raises(ValueError):
+        pysamstats.stat_binned('nosuchstat', fx('test.bam'))
+    with pytest.raises(AttributeError):
+        pysamstats.load_binned('nosuchstat', fx('test.bam'))
+    with pytest.raises(ValueError):
+        pysamstats.load_coverage(fx('test.bam'), fields=['nosuchfield'])
+
+
+def test_normalise_coords():
+    bam = bamio.open_bam(fx('test.bam'))
+    assert opt.normalise_coords(bam, None, 5, 10, False) == (None, None)
+    assert opt.normalise_coords(bam, 'Pf3D7_01_v3', None, None, False) == (0, 50001)
+    assert opt.normalise_coords(bam, 'Pf3D7_01_v3', 10, 99999, False) == (10, 50001)
+    assert opt.normalise_coords(bam, 'Pf3D7_01_v3', 10, 20, True) == (9, 19)
+    with pytest.raises(AssertionError):
+        opt.normalise_coords(bam, 'nochrom', None, None, False)
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'pss_b200.h')).read()
+    declared = set(re.findall(r'\b(pss_[a-z_0-9]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    lib = ctypes.CDLL(_cabi.LIB_PATH)      # loads without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    # shape helpers are pure host code
+    lib.pss_pileup_nfields.restype = ctypes.c_int32
+    for i, t in enumerate(_cabi.PILEUP_STATS):
+        assert lib.pss_pileup_nfields(i) == len(config.value_fields(t))
+    for i, t in enumerate(_cabi.BINNED_STATS):
+        assert lib.pss_binned_nfields(i) == len(config.value_fields_binned(t))
+    lib.pss_binned_nbins.restype = ctypes.c_int64
+    lib.pss_binned_nbins.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int32]
+    assert lib.pss_binned_nbins(0, 50001, 300) == 167
+    assert lib.pss_binned_nbins(1000, 20000, 200) == 95
+    assert lib.pss_binned_nbins(5, 5, 300) == 1
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side expects (checked again on the GPU by every call)
+    assert ctypes.sizeof(_cabi.PssReads) == 4 * 8 + 8 + 13 * 8
+    assert ctypes.sizeof(_cabi.PssPileupParams) == 10 * 4 + 6 * 8
+    assert ctypes.sizeof(_cabi.PssBinnedParams) == 4 * 4 + 6 * 8
