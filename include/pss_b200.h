@@ -75,8 +75,13 @@ typedef struct pss_ctx pss_ctx;
 /*
  * Structure-of-arrays read batch: the fields of htslib's bam1_t that opt.pyx reads
  * (opt.pyx:10-14: core.pos/flag/qual/isize/mtid/n_cigar/l_qseq, bam_get_cigar/seq/qual).
- * Offsets arrays have n_reads + 1 entries.  seq4 is BAM's packed 4-bit sequence
- * ((l_seq + 1) / 2 bytes per read), qual is l_seq bytes per read.
+ * Offsets arrays have n_reads + 1 entries and index the cigar / seq4 / qual pointers given
+ * here; they need not start at 0, so a sub-range of a larger batch is a zero-copy view
+ * (advance the per-read pointers, keep the payload pointers).  The *_host entry points read
+ * only [off[0], off[n_reads]) of each payload and ignore n_cigar_words / n_seq_bytes /
+ * n_qual_bytes; the device entry points require qual_off[0] == 0 and n_qual_bytes set.
+ * seq4 is BAM's packed 4-bit sequence ((l_seq + 1) / 2 bytes per read), qual is l_seq
+ * bytes per read.
  * qual / qual_off / name_prev may be NULL when the request does not depend on base
  * qualities (no baseq* statistic and min_baseq == 0).
  * name_prev[i] = index of the previous record in this batch with the same QNAME, or -1:
@@ -160,10 +165,14 @@ const char *pss_version(void);
 int pss_synchronize(pss_ctx *ctx, void *stream);
 /* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t pss_launch_count(const pss_ctx *ctx);
-/* Average device time (ms, CUDA events on the launch stream) of the dominant pileup
- * kernel over the launches since the last call; resets the accumulator.  Used by
- * bench.py for roofline.achieved.  Returns < 0 if there were none. */
-double pss_pileup_kernel_ms(pss_ctx *ctx, int64_t *n_launches);
+/* Bytes the *_host entry points have copied host->device / device->host so far
+ * (bench.py's e2e.h2d_bytes_per_step / d2h_bytes_per_step). */
+void pss_transfer_bytes(const pss_ctx *ctx, int64_t *h2d, int64_t *d2h);
+/* Average device time (ms, CUDA events on the launch stream) of the pileup kernel of
+ * statistic `stat` (enum pss_pileup_stat, -1 = any) over its launches since the last call;
+ * those launches are then forgotten.  Used by bench.py for roofline.achieved.
+ * Returns < 0 if there were none. */
+double pss_pileup_kernel_ms(pss_ctx *ctx, int32_t stat, int64_t *n_launches);
 /* Enable/disable the per-launch event timing above (default off: no overhead). */
 void pss_set_kernel_timing(pss_ctx *ctx, int enabled);
 

@@ -57,7 +57,8 @@ SYMBOLS = {
     'pss_version': (C.c_char_p, []),
     'pss_synchronize': (C.c_int, [_P, _P]),
     'pss_launch_count': (C.c_int64, [_P]),
-    'pss_pileup_kernel_ms': (C.c_double, [_P, C.POINTER(C.c_int64)]),
+    'pss_pileup_kernel_ms': (C.c_double, [_P, C.c_int32, C.POINTER(C.c_int64)]),
+    'pss_transfer_bytes': (None, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'pss_set_kernel_timing': (None, [_P, C.c_int]),
     'pss_pileup_nfields': (C.c_int32, [C.c_int32]),
     'pss_binned_nfields': (C.c_int32, [C.c_int32]),
@@ -236,12 +237,19 @@ class Context(object):
     def launch_count(self):
         return int(self.lib.pss_launch_count(self.h))
 
+    def transfer_bytes(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.lib.pss_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def set_kernel_timing(self, on):
         self.lib.pss_set_kernel_timing(self.h, int(bool(on)))
 
-    def pileup_kernel_ms(self):
+    def pileup_kernel_ms(self, stat=-1):
+        if isinstance(stat, str):
+            stat = PILEUP_STATS.index(stat)
         n = C.c_int64(0)
-        ms = self.lib.pss_pileup_kernel_ms(self.h, C.byref(n))
+        ms = self.lib.pss_pileup_kernel_ms(self.h, int(stat), C.byref(n))
         return float(ms), int(n.value)
 
 

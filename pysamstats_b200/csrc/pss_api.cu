@@ -17,7 +17,9 @@ struct pss_ctx {
     int device = 0;
     char err[512] = {0};
     int64_t launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;   // moved by the *_host entry points
     DevBuf ri, rng, qual, pair, next, small;
+    int64_t qual_bias = 0;  // ctx->qual holds bytes [qual_bias, qual_bias + n) of the batch's qual array
     DevBuf hb[20];          // device copies of host batches (*_host entry points)
     DevBuf outbuf[2], maskbuf[2];
     SmallState *small_host = nullptr;   // pinned mirror of the device scalars
@@ -26,6 +28,7 @@ struct pss_ctx {
     // dominant-kernel timing
     int timing = 0;
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_stat;           // statistic id of event pair i / 2
     size_t ev_used = 0;
 };
 
@@ -142,22 +145,34 @@ extern "C" void pss_destroy(pss_ctx *ctx) {
 
 extern "C" const char *pss_last_error(const pss_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 extern "C" int64_t pss_launch_count(const pss_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void pss_transfer_bytes(const pss_ctx *ctx, int64_t *h2d, int64_t *d2h) {
+    if (h2d) *h2d = ctx ? ctx->h2d_bytes : 0;
+    if (d2h) *d2h = ctx ? ctx->d2h_bytes : 0;
+}
 extern "C" void pss_set_kernel_timing(pss_ctx *ctx, int enabled) { if (ctx) ctx->timing = enabled; }
 
-extern "C" double pss_pileup_kernel_ms(pss_ctx *ctx, int64_t *n_launches) {
+extern "C" double pss_pileup_kernel_ms(pss_ctx *ctx, int32_t stat, int64_t *n_launches) {
     if (n_launches) *n_launches = 0;
     if (!ctx || ctx->ev_used == 0) return -1.0;
     cudaSetDevice(ctx->device);
     double sum = 0;
     int64_t n = 0;
+    size_t kept = 0;
     for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        if (stat >= 0 && ctx->ev_stat[i / 2] != stat) {   // keep pairs of other statistics
+            std::swap(ctx->ev_pool[kept], ctx->ev_pool[i]);
+            std::swap(ctx->ev_pool[kept + 1], ctx->ev_pool[i + 1]);
+            ctx->ev_stat[kept / 2] = ctx->ev_stat[i / 2];
+            kept += 2;
+            continue;
+        }
         float ms = 0;
         if (cudaEventSynchronize(ctx->ev_pool[i + 1]) == cudaSuccess &&
             cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) {
             sum += ms; ++n;
         } else cudaGetLastError();
     }
-    ctx->ev_used = 0;
+    ctx->ev_used = kept;
     if (n_launches) *n_launches = n;
     return n ? sum / (double)n : -1.0;
 }
@@ -190,7 +205,7 @@ static int check_reads(pss_ctx *ctx, const pss_reads *R, bool need_qual) {
 // k_prep + depth cap (+ overlap tweak): everything that depends on the batch and on the
 // read-level parameters but not on the output position range.
 static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_depth, int min_mapq, int no_dup,
-                         bool need_qual, uint8_t *qual_dst, int32_t *pair_dst, cudaStream_t s) {
+                         bool need_qual, uint8_t *qual_dst, int32_t *pair_dst, cudaStream_t s, int64_t qual_lo = 0) {
     int64_t n = R->n_reads;
     int rc;
     if ((rc = ensure(ctx, ctx->ri, sizeof(RInfo) * (size_t)n)) != PSS_OK) return rc;
@@ -202,7 +217,8 @@ static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_
     if (need_qual && n > 0) {
         if (!qual_dst) {
             if ((rc = ensure(ctx, ctx->qual, (size_t)R->n_qual_bytes)) != PSS_OK) return rc;
-            qual_dst = (uint8_t *)ctx->qual.p;
+            qual_dst = (uint8_t *)ctx->qual.p - qual_lo;
+            ctx->qual_bias = qual_lo;
         }
         if (!pair_dst) {
             if ((rc = ensure(ctx, ctx->pair, sizeof(int32_t) * (size_t)n)) != PSS_OK) return rc;
@@ -210,7 +226,7 @@ static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_
         }
         if ((rc = ensure(ctx, ctx->next, sizeof(int32_t) * (size_t)n)) != PSS_OK) return rc;
         if (R->n_qual_bytes > 0)
-            CU(cudaMemcpyAsync(qual_dst, R->qual, (size_t)R->n_qual_bytes, cudaMemcpyDeviceToDevice, s));
+            CU(cudaMemcpyAsync(qual_dst + qual_lo, R->qual + qual_lo, (size_t)R->n_qual_bytes, cudaMemcpyDeviceToDevice, s));
         CU(launch_overlap(*R, ri, qual_dst, pair_dst, (int32_t *)ctx->next.p, s, &ctx->launches));
     }
     return PSS_OK;
@@ -240,7 +256,7 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.ri = (const RInfo *)ctx->ri.p;
     a.cigar = R->cigar;
     a.seq4 = R->seq4;
-    a.qual = need_qual ? (const uint8_t *)ctx->qual.p : nullptr;
+    a.qual = need_qual ? (const uint8_t *)ctx->qual.p - ctx->qual_bias : nullptr;
     a.qual_off = need_qual ? R->qual_off : nullptr;
     a.tlen = (P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND) ? R->tlen : nullptr;
     a.tile_rng = (const int2 *)ctx->rng.p;
@@ -251,7 +267,12 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->timing) {
         e0 = next_event(ctx); e1 = next_event(ctx);
-        if (e0 && e1) CU(cudaEventRecord(e0, s));
+        if (e0 && e1) {
+            size_t pair = ctx->ev_used / 2 - 1;
+            if (ctx->ev_stat.size() <= pair) ctx->ev_stat.resize(pair + 1);
+            ctx->ev_stat[pair] = P->stat;
+            CU(cudaEventRecord(e0, s));
+        }
     }
     CU(launch_pileup(P->stat, a, ntiles, s, &ctx->launches));
     if (e0 && e1) CU(cudaEventRecord(e1, s));
@@ -322,8 +343,28 @@ static int to_device(pss_ctx *ctx, DevBuf &b, const T *host, size_t count, const
     if (!host) return PSS_OK;
     int rc = ensure(ctx, b, sizeof(T) * count);
     if (rc != PSS_OK) return rc;
-    if (count) CU(cudaMemcpyAsync(b.p, host, sizeof(T) * count, cudaMemcpyHostToDevice, s));
+    if (count) {
+        CU(cudaMemcpyAsync(b.p, host, sizeof(T) * count, cudaMemcpyHostToDevice, s));
+        ctx->h2d_bytes += (int64_t)(sizeof(T) * count);
+    }
     *dev = (const T *)b.p;
+    return PSS_OK;
+}
+
+// Ragged payload (cigar / seq4 / qual): only the span [off[0], off[n]) the batch refers to is
+// copied, and the device pointer is biased so the (absolute) offsets keep working.  This is
+// what lets a caller pass a zero-copy sub-range view of a larger host batch.
+template <class T>
+static int to_device_span(pss_ctx *ctx, DevBuf &b, const T *host, const int64_t *off, size_t n, const T **dev,
+                          cudaStream_t s) {
+    *dev = nullptr;
+    if (!host || !off) return PSS_OK;
+    int64_t lo = off[0], hi = off[n];
+    if (hi < lo) return fail(ctx, PSS_EINVAL, "offsets decrease");
+    const T *d;
+    int rc = to_device(ctx, b, host + lo, (size_t)(hi - lo), &d, s);
+    if (rc != PSS_OK) return rc;
+    *dev = d - lo;
     return PSS_OK;
 }
 
@@ -332,16 +373,22 @@ static int upload_reads(pss_ctx *ctx, const pss_reads *H, pss_reads *D, bool nee
     size_t n = (size_t)H->n_reads;
     int rc;
 #define UP(idx, field, count) if ((rc = to_device(ctx, ctx->hb[idx], H->field, (count), &D->field, s)) != PSS_OK) return rc
+#define UPS(idx, field, off) if ((rc = to_device_span(ctx, ctx->hb[idx], H->field, H->off, n, &D->field, s)) != PSS_OK) return rc
     UP(0, pos, n); UP(1, flag, n); UP(2, mapq, n); UP(3, tlen, n); UP(4, mtid, n); UP(5, l_seq, n);
-    UP(6, cigar_off, n + 1); UP(7, cigar, (size_t)H->n_cigar_words); UP(8, seq_off, n + 1);
-    if (need_seq) { UP(9, seq4, (size_t)H->n_seq_bytes); }
+    UP(6, cigar_off, n + 1); UP(8, seq_off, n + 1);
+    if (n > 0) { UPS(7, cigar, cigar_off); }
+    if (need_seq && n > 0) { UPS(9, seq4, seq_off); }
     else {   // never dereferenced, but must be non-NULL for the argument check
         if ((rc = ensure(ctx, ctx->hb[9], 16)) != PSS_OK) return rc;
         D->seq4 = (const uint8_t *)ctx->hb[9].p;
     }
-    if (need_qual) { UP(10, qual_off, n + 1); UP(11, qual, (size_t)H->n_qual_bytes); UP(12, name_prev, n); }
+    if (need_qual && n > 0) {
+        UP(10, qual_off, n + 1); UPS(11, qual, qual_off); UP(12, name_prev, n);
+        D->n_qual_bytes = H->qual_off[n] - H->qual_off[0];
+    }
     else { D->qual_off = nullptr; D->qual = nullptr; D->name_prev = nullptr; }
 #undef UP
+#undef UPS
     return PSS_OK;
 }
 
@@ -367,8 +414,8 @@ extern "C" int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_p
     if (P->ref && P->ref_len > 0) {
         if ((rc = to_device(ctx, ctx->hb[13], P->ref, (size_t)P->ref_len, &Pd.ref, s)) != PSS_OK) return rc;
     } else Pd.ref = nullptr;
-    if ((rc = prepare_batch(ctx, &D, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, nullptr, nullptr, s)) !=
-        PSS_OK)
+    if ((rc = prepare_batch(ctx, &D, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, nullptr, nullptr, s,
+                            (need_qual && reads->n_reads > 0) ? reads->qual_off[0] : 0)) != PSS_OK)
         return rc;
     const int nf = kPileupFields[P->stat];
     // position chunks: <= ~256 MB of output each, double buffered against the D2H copies
@@ -394,6 +441,7 @@ extern "C" int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_p
         CU(cudaMemcpyAsync(rowmask + (cs - P->start), ctx->maskbuf[b].p, (size_t)cn, cudaMemcpyDeviceToHost,
                            ctx->copy_stream));
         CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        ctx->d2h_bytes += (int64_t)(sizeof(int32_t) * (size_t)cn * (size_t)nf + (size_t)cn);
     }
     CU(cudaStreamSynchronize(ctx->copy_stream));
     return pss_synchronize(ctx, s);
@@ -438,7 +486,10 @@ extern "C" int pss_binned_host(pss_ctx *ctx, const pss_reads *H, const pss_binne
     bool need_cigar = P->stat == PSS_COVERAGE_EXT_BINNED || P->stat == PSS_ALIGNMENT_BINNED;
 #define UP(idx, field, count) if ((rc = to_device(ctx, ctx->hb[idx], H->field, (count), &D.field, s)) != PSS_OK) return rc
     UP(0, pos, n); UP(1, flag, n); UP(2, mapq, n); UP(3, tlen, n); UP(4, mtid, n);
-    if (need_cigar) { UP(6, cigar_off, n + 1); UP(7, cigar, (size_t)H->n_cigar_words); }
+    if (need_cigar && n > 0) {
+        UP(6, cigar_off, n + 1);
+        if ((rc = to_device_span(ctx, ctx->hb[7], H->cigar, H->cigar_off, n, &D.cigar, s)) != PSS_OK) return rc;
+    }
 #undef UP
     pss_binned_params Pd = *P;
     if (P->ref && P->ref_len > 0) {
@@ -449,6 +500,7 @@ extern "C" int pss_binned_host(pss_ctx *ctx, const pss_reads *H, const pss_binne
     if ((rc = ensure(ctx, ctx->outbuf[0], obytes)) != PSS_OK) return rc;
     CU(launch_binned(D, Pd, (int32_t *)ctx->outbuf[0].p, s, &ctx->launches));
     CU(cudaMemcpyAsync(out, ctx->outbuf[0].p, obytes, cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += (int64_t)obytes;
     CU(cudaStreamSynchronize(s));
     return PSS_OK;
 }

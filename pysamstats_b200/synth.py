@@ -51,12 +51,34 @@ def make_batch(contig_len, n_pairs, read_len=150, seed=20261019, device='cpu', r
     done = 0
     while done < n_pairs:
         m = min(chunk_pairs, n_pairs - done)
-        parts.append(_make_chunk(m, done, L, lo, max(lo + 1, hi - 700 - 20), ref_base, ref_is_n, g, dev, with_qual))
+        parts.append(_make_chunk(m, done, L, lo, max(lo + 1, hi - 700 - 20), ref_base, 0, ref_is_n, g, dev, with_qual))
         done += m
     cat = {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
     del parts
-    # coordinate sort (stable: equal starts keep generation order), like a sorted BAM
+    return _finish(cat, L, dev, with_qual, None, None), ref
+
+
+def _finish(cat, L, dev, with_qual, lo, hi):
+    """Coordinate sort (stable: equal starts keep generation order, like a sorted BAM), keep
+    the records overlapping [lo, hi) (htslib's region rule: pos < hi and endpos > lo) and
+    lay the batch out as the pss_reads arrays."""
     order = torch.argsort(cat['pos'], stable=True)
+    n_all = order.numel()
+    pos_s = cat['pos'][order]
+    if lo is None:
+        keep = torch.ones(n_all, dtype=torch.bool, device=dev)
+    else:
+        end_s = pos_s.long() + cat['reflen'][order].long()
+        keep = (pos_s.long() < hi) & (end_s > lo)
+    newidx = torch.cumsum(keep.long(), 0) - 1
+    # name_prev: the earlier record of the same pair, if it is in the batch
+    inv = torch.empty(n_all, dtype=torch.int64, device=dev)
+    inv[order] = torch.arange(n_all, device=dev)
+    mate_sorted = inv[order ^ 1]                                # sorted index of each read's mate
+    me = torch.arange(n_all, device=dev)
+    has_prev = (mate_sorted < me) & keep[mate_sorted]
+    prev = torch.where(has_prev, newidx[mate_sorted], torch.full_like(me, -1))
+    order = order[keep]
     n = order.numel()
     out = {}
     for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq'):
@@ -65,8 +87,8 @@ def make_batch(contig_len, n_pairs, read_len=150, seed=20261019, device='cpu', r
     out['cigar_off'] = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     out['cigar_off'][1:] = torch.cumsum(ncig.long(), 0)
     cig = cat['cig3'][order]                                     # [n, 3]
-    keep = torch.arange(3, device=dev)[None, :] < ncig[:, None]
-    out['cigar'] = cig[keep].contiguous()
+    kmask = torch.arange(3, device=dev)[None, :] < ncig[:, None]
+    out['cigar'] = cig[kmask].contiguous()
     nb = (L + 1) // 2
     out['seq_off'] = torch.arange(n + 1, dtype=torch.int64, device=dev) * nb
     out['seq4'] = cat['seq4'][order].reshape(-1).contiguous()
@@ -76,22 +98,63 @@ def make_batch(contig_len, n_pairs, read_len=150, seed=20261019, device='cpu', r
     else:
         out['qual_off'] = None
         out['qual'] = None
-    # name_prev: the earlier record of the same pair, if any
-    inv = torch.empty(n, dtype=torch.int64, device=dev)
-    inv[order] = torch.arange(n, device=dev)
-    mate_sorted = inv[order ^ 1]                                # sorted index of each read's mate
-    me = torch.arange(n, device=dev)
-    prev = torch.where(mate_sorted < me, mate_sorted, torch.full_like(me, -1))
-    out['name_prev'] = prev.to(torch.int32)
+    out['name_prev'] = prev[keep].to(torch.int32)
+    out['endpos'] = (out['pos'].long() + cat['reflen'][order].long())
     out['n_reads'] = n
     out['n_cigar_words'] = int(out['cigar'].numel())
     out['n_seq_bytes'] = int(out['seq4'].numel())
     out['n_qual_bytes'] = int(out['qual'].numel()) if with_qual else 0
     out['tid'] = 0
-    return out, ref
+    return out
 
 
-def _make_chunk(m, pair0, L, lo, hi, ref_base, ref_is_n, g, dev, with_qual):
+def reference_span(lo, hi, seed=1, device='cpu', block=1000000):
+    """Reference bytes of [lo, hi) of the synthetic genome.  The genome is defined block by
+    block (``block`` positions, generator seeded by the block number), so any rank can
+    materialise any interval and neighbouring shards agree on their shared positions.
+    Returns (ascii uint8, 2-bit base, is_N), each of length hi - lo."""
+    b0, b1 = lo // block, (hi + block - 1) // block
+    parts = [make_reference(block, seed=seed * 1000003 + b, device=device) for b in range(b0, max(b1, b0 + 1))]
+    cat = [torch.cat([p[i] for p in parts]) for i in range(3)]
+    o = lo - b0 * block
+    return tuple(c[o:o + (hi - lo)].contiguous() for c in cat)
+
+
+def make_interval_batch(lo, hi, genome_len, depth=30, read_len=150, seed=20261019, device='cpu', with_qual=True,
+                        block=1000000):
+    """The records of a ``depth``-fold synthetic WGS run over a genome of ``genome_len``
+    positions that overlap [lo, hi) (so including the halo of reads that start before lo),
+    coordinate sorted -- exactly what a region query of the sorted BAM would return.
+
+    Pairs are generated per block of leftmost starts with a generator seeded by the block
+    number: every shard of a multi-GPU run sees the same genome-wide read set no matter how
+    the genome is cut.  Returns (batch dict, (ref_ascii, ref_start)) with the reference
+    covering [ref_start, ref_start + len(ref_ascii)) >= [lo, hi)."""
+    dev = torch.device(device)
+    L = read_len
+    pairs_per_block = int(round(depth * block / (2.0 * L)))
+    b0 = max(0, (lo - 720 - L) // block)         # a pair spans <= 700 + deletion <= 720
+    b1 = min((hi + block - 1) // block, (genome_len + block - 1) // block)
+    ref_lo = b0 * block
+    ref_hi = min(genome_len, (b1 + 1) * block)    # reads of the last block reach < b1 * block + 720
+    ref_ascii, ref_base, ref_is_n = reference_span(ref_lo, ref_hi, seed=1, device=device, block=block)
+    parts = []
+    for b in range(b0, b1):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed * 1000003 + b)
+        s_lo = b * block
+        s_hi = min((b + 1) * block, genome_len - 720)
+        if s_hi <= s_lo:
+            continue
+        parts.append(_make_chunk(pairs_per_block, 0, L, s_lo, s_hi, ref_base, ref_lo, ref_is_n, g, dev,
+                                 with_qual))
+    cat = {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
+    del parts
+    out = _finish(cat, L, dev, with_qual, lo, hi)
+    return out, (ref_ascii, ref_lo)
+
+
+def _make_chunk(m, pair0, L, lo, hi, ref_base, ref_lo, ref_is_n, g, dev, with_qual):
     def rnd(*shape):
         return torch.rand(*shape, generator=g, device=dev)
 
@@ -192,8 +255,8 @@ def _make_chunk(m, pair0, L, lo, hi, ref_base, ref_is_n, g, dev, with_qual):
     off = torch.where((t_ == 2) & (q >= a_), q + k_, off)
     off = torch.where((t_ == 3), torch.where(q < k_, torch.full_like(off, -1), q - k_), off)
     off = torch.where((t_ == 4) & (q >= L - k_), torch.full_like(off, -1), off)
-    rpos = pos[:, None] + off
-    templ = (off >= 0) & (rpos < ref_base.numel())
+    rpos = pos[:, None] + off - ref_lo                           # index into the reference span held
+    templ = (off >= 0) & (rpos >= 0) & (rpos < ref_base.numel())
     rb = ref_base[torch.clamp(rpos, 0, ref_base.numel() - 1)].long()
     rn = ref_is_n[torch.clamp(rpos, 0, ref_base.numel() - 1)]
     rand_base = rint(0, 4, n, L)
@@ -208,7 +271,13 @@ def _make_chunk(m, pair0, L, lo, hi, ref_base, ref_is_n, g, dev, with_qual):
     seq4 = (code[:, 0::2] << 4) | code[:, 1::2]
     # flag / cigar are kept as int16 / int32: bit-identical to the ABI's uint16 / uint32 for
     # the values generated here, and fully supported by torch indexing
+    reflen = torch.full((n,), L, dtype=torch.int64, device=dev)
+    reflen = torch.where(typ == 1, L - k, reflen)
+    reflen = torch.where(typ == 2, L + k, reflen)
+    reflen = torch.where((typ == 3) | (typ == 4), L - k, reflen)
+    reflen = torch.where(unmapped, torch.ones_like(reflen), reflen)   # bam_endpos(): pos + 1
     out = {'pos': pos.to(torch.int32), 'flag': flag.to(torch.int16), 'mapq': mapq.to(torch.uint8),
+           'reflen': reflen.to(torch.int32),
            'tlen': tlen.to(torch.int32), 'mtid': mtid.to(torch.int32),
            'l_seq': torch.full((n,), L, dtype=torch.int32, device=dev), 'ncig': ncig,
            'cig3': cig3.to(torch.int32), 'seq4': seq4}
