@@ -36,6 +36,10 @@ extern "C" {
 #define PSS_ECUDA (-2)    /* CUDA runtime / launch failure */
 #define PSS_ENOMEM (-3)   /* workspace allocation failed */
 #define PSS_EUNSORTED (-4) /* batch not coordinate sorted (htslib: "unsorted positions") */
+#define PSS_ETOOLONG (-5)  /* a read longer than ~40 kb met the short-read kernel; see PSS_FLAG_GENERIC_KERNEL */
+
+/* pss_pileup_params.flags */
+#define PSS_FLAG_GENERIC_KERNEL 1 /* always use the generic per-position kernel (any read length) */
 
 /* statistics ids: order of stats_classes_pileup, pysamstats/pileup.py:150-166 */
 enum pss_pileup_stat {
@@ -128,7 +132,7 @@ typedef struct pss_pileup_params {
     int32_t no_dup;
     int32_t window_size;   /* coverage_gc only (opt.pyx:1477-1481) */
     int32_t window_offset; /* coverage_gc only, already defaulted */
-    int32_t reserved;
+    int32_t flags;         /* PSS_FLAG_* */
     int64_t start;
     int64_t end;
     const uint8_t *ref;

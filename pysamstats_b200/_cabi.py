@@ -12,7 +12,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpss_b200.so')
 
-PSS_OK, PSS_EINVAL, PSS_ECUDA, PSS_ENOMEM, PSS_EUNSORTED = 0, -1, -2, -3, -4
+PSS_OK, PSS_EINVAL, PSS_ECUDA, PSS_ENOMEM, PSS_EUNSORTED, PSS_ETOOLONG = 0, -1, -2, -3, -4, -5
+PSS_FLAG_GENERIC_KERNEL = 1
 
 PILEUP_STATS = ('coverage', 'coverage_strand', 'coverage_ext', 'coverage_ext_strand', 'variation',
                 'variation_strand', 'tlen', 'tlen_strand', 'mapq', 'mapq_strand', 'baseq',
@@ -36,7 +37,7 @@ class PssPileupParams(C.Structure):
     _fields_ = [('stat', C.c_int32), ('stepper', C.c_int32), ('max_depth', C.c_int32),
                 ('min_mapq', C.c_int32), ('min_baseq', C.c_int32), ('no_del', C.c_int32),
                 ('no_dup', C.c_int32), ('window_size', C.c_int32), ('window_offset', C.c_int32),
-                ('reserved', C.c_int32), ('start', C.c_int64), ('end', C.c_int64),
+                ('flags', C.c_int32), ('start', C.c_int64), ('end', C.c_int64),
                 ('ref', C.c_void_p), ('ref_start', C.c_int64), ('ref_len', C.c_int64),
                 ('contig_len', C.c_int64)]
 
@@ -170,7 +171,7 @@ class Context(object):
         if rc == PSS_OK:
             return
         msg = self.lib.pss_last_error(self.h).decode('ascii', 'replace')
-        if rc == PSS_EINVAL or rc == PSS_EUNSORTED:
+        if rc in (PSS_EINVAL, PSS_EUNSORTED, PSS_ETOOLONG):
             raise ValueError(msg)
         if rc == PSS_ENOMEM:
             raise MemoryError(msg)
@@ -179,7 +180,7 @@ class Context(object):
     # -- thin wrappers -------------------------------------------------------------
     def pileup_params(self, stat, stepper='all', max_depth=8000, min_mapq=0, min_baseq=0, no_del=False,
                       no_dup=False, window_size=300, window_offset=None, start=0, end=0, ref=None,
-                      ref_start=0, ref_len=0, contig_len=0):
+                      ref_start=0, ref_len=0, contig_len=0, flags=0):
         p = PssPileupParams()
         p.stat = PILEUP_STATS.index(stat) if isinstance(stat, str) else int(stat)
         if isinstance(stepper, str):
@@ -192,6 +193,7 @@ class Context(object):
         p.no_del, p.no_dup = int(bool(no_del)), int(bool(no_dup))
         p.window_size = int(window_size)
         p.window_offset = int(window_size // 2 if window_offset is None else window_offset)
+        p.flags = int(flags)
         p.start, p.end = int(start), int(end)
         p.ref = _addr(ref)
         p.ref_start, p.ref_len, p.contig_len = int(ref_start), int(ref_len), int(contig_len)

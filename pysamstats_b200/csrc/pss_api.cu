@@ -184,6 +184,9 @@ extern "C" int pss_synchronize(pss_ctx *ctx, void *stream) {
     CU(cudaMemcpyAsync(ctx->small_host, ctx->small.p, sizeof(SmallState), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (ctx->small_host->unsorted) return fail(ctx, PSS_EUNSORTED, "read batch is not coordinate sorted");
+    if (ctx->small_host->toolong)
+        return fail(ctx, PSS_ETOOLONG, "a read is too long for the tile kernel's staging buffer; set "
+                                       "PSS_FLAG_GENERIC_KERNEL in pss_pileup_params.flags");
     return PSS_OK;
 }
 
@@ -246,11 +249,15 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
                      int64_t end, int32_t *out, uint8_t *rowmask, cudaStream_t s) {
     int64_t npos = end - start;
     if (npos <= 0) return PSS_OK;
-    int64_t ntiles = (npos + PSS_TILE - 1) / PSS_TILE;
+    // counting statistics without a base-quality filter take the tile (scatter) kernel,
+    // everything else the generic per-position kernel
+    const bool tile = tile_kernel_supports(P->stat, P->min_baseq) && !(P->flags & PSS_FLAG_GENERIC_KERNEL);
+    const int tsize = tile ? PSS_TTILE : PSS_TILE;
+    int64_t ntiles = (npos + tsize - 1) / tsize;
     if (ntiles > 0x7fffffff) return fail(ctx, PSS_EINVAL, "position range too large for one call");
     int rc;
     if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)ntiles)) != PSS_OK) return rc;
-    CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, ntiles,
+    CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, ntiles, tsize,
                           (int2 *)ctx->rng.p, s, &ctx->launches));
     PileupArgs a;
     a.ri = (const RInfo *)ctx->ri.p;
@@ -274,7 +281,10 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
             CU(cudaEventRecord(e0, s));
         }
     }
-    CU(launch_pileup(P->stat, a, ntiles, s, &ctx->launches));
+    if (tile) {
+        int need_raw = (P->min_mapq > 0 || P->no_dup || P->no_del) ? 1 : 0;
+        CU(launch_tile(P->stat, a, R->seq_off, (SmallState *)ctx->small.p, need_raw, ntiles, s, &ctx->launches));
+    } else CU(launch_pileup(P->stat, a, ntiles, s, &ctx->launches));
     if (e0 && e1) CU(cudaEventRecord(e1, s));
     if (P->stat == PSS_COVERAGE_GC)
         CU(launch_gc(P->ref, P->ref_start, P->ref_len, P->contig_len, start, end, P->window_size, P->window_offset,

@@ -42,6 +42,7 @@ __host__ __device__ __forceinline__ bool op_is_match(int op) { return op == OP_M
 
 #define PSS_TILE 256          // positions per CTA in the pileup kernel (one per thread)
 #define PSS_CHUNK 128         // candidate reads staged in shared memory at a time
+#define PSS_TTILE 512         // positions per CTA in the tile (scatter) kernel
 
 struct PileupArgs {
     const RInfo *ri;
@@ -66,6 +67,8 @@ struct SmallState {
     int32_t unsorted;      // != 0 when pos[] decreases somewhere
     int32_t first_unsafe;  // depth-cap: first / last read index whose admission is not
     int32_t last_unsafe;   //            provably unconstrained (else INT_MAX / -1)
+    int32_t toolong;       // != 0 when a read's sequence does not fit the tile kernel's staging buffer
+    int32_t pad_[3];
 };
 
 // ---- kernel launchers (defined in the .cu files) ----------------------------------
@@ -76,7 +79,10 @@ cudaError_t launch_admit(RInfo *ri, int64_t n, int maxcnt, SmallState *st, cudaS
 cudaError_t launch_overlap(const pss_reads &R, const RInfo *ri, uint8_t *qual_work, int32_t *pair_first,
                            int32_t *name_next, cudaStream_t s, int64_t *launches);
 cudaError_t launch_tile_ranges(const RInfo *ri, int64_t n, const SmallState *st, int64_t start,
-                               int64_t ntiles, int2 *rng, cudaStream_t s, int64_t *launches);
+                               int64_t ntiles, int tile, int2 *rng, cudaStream_t s, int64_t *launches);
+bool tile_kernel_supports(int stat, int min_baseq);
+cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, SmallState *st, int need_raw,
+                        int64_t ntiles, cudaStream_t s, int64_t *launches);
 cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, cudaStream_t s, int64_t *launches);
 cudaError_t launch_gc(const uint8_t *ref, int64_t ref_start, int64_t ref_len, int64_t contig_len,
                       int64_t start, int64_t end, int window_size, int window_offset, int32_t *out_gc,

@@ -5,6 +5,7 @@
 // SURVEY.md Appendix A (the htslib semantics behind AlignmentFile.pileup, which the
 // reference consumes at pysamstats/opt.pyx:1853-1854).
 #include <limits.h>
+#include <string.h>
 
 #include "pss_internal.cuh"
 
@@ -379,10 +380,10 @@ __device__ __forceinline__ int64_t lower_bound_pos(const RInfo *ri, int64_t n, l
 
 __global__ void __launch_bounds__(256)
 k_tile_ranges(const RInfo *__restrict__ ri, int64_t n, const SmallState *st, int64_t start,
-              int64_t ntiles, int2 *rng) {
+              int64_t ntiles, int tile, int2 *rng) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
-    long long t0 = start + t * PSS_TILE, t1 = t0 + PSS_TILE;
+    long long t0 = start + t * tile, t1 = t0 + tile;
     int2 r;
     r.x = (int)lower_bound_pos(ri, n, t0 - st->maxspan + 1);
     r.y = (int)lower_bound_pos(ri, n, t1);
@@ -584,6 +585,7 @@ k_binned(pss_reads R, pss_binned_params P, int32_t *__restrict__ out) {
 cudaError_t launch_prep(const pss_reads &R, int stepper, int min_mapq, int no_dup, RInfo *ri,
                         SmallState *st, cudaStream_t s, int64_t *launches) {
     SmallState init;
+    memset(&init, 0, sizeof(init));
     init.maxspan = 1; init.unsorted = 0; init.first_unsafe = INT_MAX; init.last_unsafe = -1;
     cudaError_t e = cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
@@ -634,9 +636,9 @@ cudaError_t launch_overlap(const pss_reads &R, const RInfo *ri, uint8_t *qual_wo
 }
 
 cudaError_t launch_tile_ranges(const RInfo *ri, int64_t n, const SmallState *st, int64_t start,
-                               int64_t ntiles, int2 *rng, cudaStream_t s, int64_t *launches) {
+                               int64_t ntiles, int tile, int2 *rng, cudaStream_t s, int64_t *launches) {
     if (ntiles > 0) {
-        k_tile_ranges<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(ri, n, st, start, ntiles, rng);
+        k_tile_ranges<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(ri, n, st, start, ntiles, tile, rng);
         LAUNCHED();
     }
     return cudaGetLastError();

@@ -152,7 +152,7 @@ struct AccVariation {
         if (act) {
             uint2 inc = lut[code];
             lo[C] += inc.x;
-            hi[C] += inc.y + ((code == refcode) ? 0x100u : 0u) + (ins ? 0x01000000u : 0u);
+            hi[C] += inc.y + ((code == refcode && code < 16) ? 0x100u : 0u) + (ins ? 0x01000000u : 0u);
             ev[C] += 1u;
         }
     }
@@ -260,7 +260,7 @@ struct AccBaseq {
         if (act) {
             unsigned long long s = (unsigned long long)(q * q);
             n[C]++; nnd[C]++; sq[C] += s;
-            if (EXT && code == refcode) { nm[C]++; sqm[C] += s; }
+            if (EXT && code == refcode && code < 16) { nm[C]++; sqm[C] += s; }
         }
     }
     template <int C> __device__ void del(bool act, bool) { n[C] += act; }   // counted, no quality (opt.pyx:1108-1112)
