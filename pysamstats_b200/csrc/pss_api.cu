@@ -18,7 +18,7 @@ struct pss_ctx {
     char err[512] = {0};
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // moved by the *_host entry points
-    DevBuf ri, rng, qual, pair, next, small;
+    DevBuf ri, rng, qual, pair, next, small, tdesc, refpack;
     int64_t qual_bias = 0;  // ctx->qual holds bytes [qual_bias, qual_bias + n) of the batch's qual array
     DevBuf hb[20];          // device copies of host batches (*_host entry points)
     DevBuf outbuf[2], maskbuf[2];
@@ -129,7 +129,7 @@ extern "C" void pss_destroy(pss_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small,
+    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small, &ctx->tdesc, &ctx->refpack,
                      &ctx->outbuf[0], &ctx->outbuf[1], &ctx->maskbuf[0], &ctx->maskbuf[1]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->hb) if (b.p) cudaFree(b.p);
@@ -244,9 +244,9 @@ static cudaEvent_t next_event(pss_ctx *ctx) {
     return ctx->ev_pool[ctx->ev_used++];
 }
 
-// tile ranges + the pileup kernel (+ gc) for output positions [start, end)
+// the pileup kernel (+ gc) for output positions [start, end); out[f * stride + (p - start)]
 static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *P, bool need_qual, int64_t start,
-                     int64_t end, int32_t *out, uint8_t *rowmask, cudaStream_t s) {
+                     int64_t end, int32_t *out, int64_t stride, uint8_t *rowmask, cudaStream_t s) {
     int64_t npos = end - start;
     if (npos <= 0) return PSS_OK;
     // counting statistics without a base-quality filter take the tile (scatter) kernel,
@@ -256,9 +256,6 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     int64_t ntiles = (npos + tsize - 1) / tsize;
     if (ntiles > 0x7fffffff) return fail(ctx, PSS_EINVAL, "position range too large for one call");
     int rc;
-    if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)ntiles)) != PSS_OK) return rc;
-    CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, ntiles, tsize,
-                          (int2 *)ctx->rng.p, s, &ctx->launches));
     PileupArgs a;
     a.ri = (const RInfo *)ctx->ri.p;
     a.cigar = R->cigar;
@@ -266,11 +263,11 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.qual = need_qual ? (const uint8_t *)ctx->qual.p - ctx->qual_bias : nullptr;
     a.qual_off = need_qual ? R->qual_off : nullptr;
     a.tlen = (P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND) ? R->tlen : nullptr;
-    a.tile_rng = (const int2 *)ctx->rng.p;
+    a.tile_rng = nullptr;
     a.ref = P->ref; a.ref_start = P->ref_start; a.ref_len = P->ref_len;
     a.start = start; a.end = end;
     a.min_baseq = P->min_baseq; a.no_del = P->no_del;
-    a.out = out; a.rowmask = rowmask;
+    a.out = out; a.out_stride = stride; a.rowmask = rowmask;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->timing) {
         e0 = next_event(ctx); e1 = next_event(ctx);
@@ -278,14 +275,23 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
             size_t pair = ctx->ev_used / 2 - 1;
             if (ctx->ev_stat.size() <= pair) ctx->ev_stat.resize(pair + 1);
             ctx->ev_stat[pair] = P->stat;
-            CU(cudaEventRecord(e0, s));
-        }
+        } else e0 = e1 = nullptr;
     }
     if (tile) {
+        if ((rc = ensure(ctx, ctx->tdesc, tile_desc_bytes(ntiles))) != PSS_OK) return rc;
+        if ((rc = ensure(ctx, ctx->refpack, tile_refpack_bytes(ntiles))) != PSS_OK) return rc;
         int need_raw = (P->min_mapq > 0 || P->no_dup || P->no_del) ? 1 : 0;
-        CU(launch_tile(P->stat, a, R->seq_off, (SmallState *)ctx->small.p, need_raw, ntiles, s, &ctx->launches));
-    } else CU(launch_pileup(P->stat, a, ntiles, s, &ctx->launches));
-    if (e0 && e1) CU(cudaEventRecord(e1, s));
+        CU(launch_tile(P->stat, a, R->seq_off, R->n_reads, (SmallState *)ctx->small.p, need_raw, ntiles, ctx->tdesc.p,
+                       ctx->refpack.p, s, &ctx->launches, e0, e1));
+    } else {
+        if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)ntiles)) != PSS_OK) return rc;
+        CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, ntiles,
+                              tsize, (int2 *)ctx->rng.p, s, &ctx->launches));
+        a.tile_rng = (const int2 *)ctx->rng.p;
+        if (e0) CU(cudaEventRecord(e0, s));
+        CU(launch_pileup(P->stat, a, ntiles, s, &ctx->launches));
+        if (e1) CU(cudaEventRecord(e1, s));
+    }
     if (P->stat == PSS_COVERAGE_GC)
         CU(launch_gc(P->ref, P->ref_start, P->ref_len, P->contig_len, start, end, P->window_size, P->window_offset,
                      out, s, &ctx->launches));
@@ -316,7 +322,7 @@ extern "C" int pss_pileup(pss_ctx *ctx, const pss_reads *reads, const pss_pileup
     if ((rc = prepare_batch(ctx, reads, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, nullptr, nullptr,
                             s)) != PSS_OK)
         return rc;
-    return run_range(ctx, reads, P, need_qual, P->start, P->end, out, rowmask, s);
+    return run_range(ctx, reads, P, need_qual, P->start, P->end, out, P->end - P->start, rowmask, s);
 }
 
 extern "C" int pss_admit(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth, uint8_t *admitted,
@@ -437,16 +443,17 @@ extern "C" int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_p
         int64_t ce = cs + chunk < P->end ? cs + chunk : P->end;
         int64_t cn = ce - cs;
         int b = k & 1;
-        if ((rc = ensure(ctx, ctx->outbuf[b], sizeof(int32_t) * (size_t)nf * (size_t)chunk)) != PSS_OK) return rc;
-        if ((rc = ensure(ctx, ctx->maskbuf[b], (size_t)chunk)) != PSS_OK) return rc;
+        const int64_t stride = (chunk + 3) & ~(int64_t)3;   // padded rows: 128-bit stores everywhere
+        if ((rc = ensure(ctx, ctx->outbuf[b], sizeof(int32_t) * (size_t)nf * (size_t)stride)) != PSS_OK) return rc;
+        if ((rc = ensure(ctx, ctx->maskbuf[b], (size_t)stride)) != PSS_OK) return rc;
         if (k >= 2) CU(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));   // buffer free again
-        if ((rc = run_range(ctx, &D, &Pd, need_qual, cs, ce, (int32_t *)ctx->outbuf[b].p, (uint8_t *)ctx->maskbuf[b].p,
-                            s)) != PSS_OK)
+        if ((rc = run_range(ctx, &D, &Pd, need_qual, cs, ce, (int32_t *)ctx->outbuf[b].p, stride,
+                            (uint8_t *)ctx->maskbuf[b].p, s)) != PSS_OK)
             return rc;
         CU(cudaEventRecord(ctx->ev_done[b], s));
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
         CU(cudaMemcpy2DAsync(out + (cs - P->start), sizeof(int32_t) * (size_t)npos, ctx->outbuf[b].p,
-                             sizeof(int32_t) * (size_t)cn, sizeof(int32_t) * (size_t)cn, (size_t)nf,
+                             sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)cn, (size_t)nf,
                              cudaMemcpyDeviceToHost, ctx->copy_stream));
         CU(cudaMemcpyAsync(rowmask + (cs - P->start), ctx->maskbuf[b].p, (size_t)cn, cudaMemcpyDeviceToHost,
                            ctx->copy_stream));

@@ -58,6 +58,7 @@ struct PileupArgs {
     int32_t min_baseq;
     int32_t no_del;
     int32_t *out;
+    int64_t out_stride;         // elements between consecutive fields of out (>= end - start)
     uint8_t *rowmask;
 };
 
@@ -81,8 +82,12 @@ cudaError_t launch_overlap(const pss_reads &R, const RInfo *ri, uint8_t *qual_wo
 cudaError_t launch_tile_ranges(const RInfo *ri, int64_t n, const SmallState *st, int64_t start,
                                int64_t ntiles, int tile, int2 *rng, cudaStream_t s, int64_t *launches);
 bool tile_kernel_supports(int stat, int min_baseq);
-cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, SmallState *st, int need_raw,
-                        int64_t ntiles, cudaStream_t s, int64_t *launches);
+size_t tile_desc_bytes(int64_t ntiles);
+size_t tile_refpack_bytes(int64_t ntiles);
+// e0 / e1 (may be NULL) are recorded immediately before / after the tile kernel itself
+cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, int64_t n_reads, SmallState *st,
+                        int need_raw, int64_t ntiles, void *desc_buf, void *refpack_buf, cudaStream_t s,
+                        int64_t *launches, cudaEvent_t e0, cudaEvent_t e1);
 cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, cudaStream_t s, int64_t *launches);
 cudaError_t launch_gc(const uint8_t *ref, int64_t ref_start, int64_t ref_len, int64_t contig_len,
                       int64_t start, int64_t end, int window_size, int window_offset, int32_t *out_gc,

@@ -510,8 +510,7 @@ k_pileup(PileupArgs a) {
     }
     acc.flush();
     if (valid) {
-        const int64_t npos = a.end - a.start;
-        acc.store(a.out + (pl - a.start), npos);
+        acc.store(a.out + (pl - a.start), a.out_stride);
         a.rowmask[pl - a.start] = raw ? 1 : 0;
     }
 }

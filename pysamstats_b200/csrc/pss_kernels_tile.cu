@@ -6,20 +6,22 @@
 //   * one CTA owns a tile of TT genome positions; its per-position counters live in shared
 //     memory (counter-major, 4 bytes each) for the whole life of the tile;
 //   * the tile's candidate reads are a contiguous index range of the start-sorted batch;
-//     their 32-byte records and their packed 4-bit sequences are staged into shared memory
-//     by bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), chunk by
+//     their 32-byte records, their packed 4-bit sequences and the tile of the 4-bit packed
+//     reference are staged into shared memory by bulk async copies (cp.async.bulk ->
+//     UBLKCP, completion on an mbarrier) issued before anything else happens, chunk by
 //     chunk for arbitrarily deep tiles;
-//   * one thread per read walks the CIGAR once.  Everything that is constant along an
-//     aligned span (read counts per strand / proper-pair / mate class, deletions, ref
-//     skips) is an interval add: +1 at the span start, -1 at its end in a difference
-//     array.  Bases are NOT visited one by one: the read's 4-bit codes are XOR-ed, eight
-//     bases per 32-bit word, against the reference tile packed the same way, and only the
-//     mismatching bases (<1 % of them) become point updates.  matches and the A/C/G/T/N
-//     counters follow exactly from  matches = aligned - mismatches  and the reference code
-//     of the position;
+//   * reads are walked once.  Everything that is constant along an aligned span (read
+//     counts per strand / proper-pair / mate class, deletions, ref skips) is an interval
+//     add: +1 at the span start, -1 at its end in a difference array.  Bases are NOT visited
+//     one by one: a warp takes a read, each lane XORs eight of its 4-bit codes (one 32-bit
+//     word) against the reference tile packed the same way, and only the mismatching bases
+//     (<1 % of them) become point updates.  matches and the A/C/G/T/N counters follow
+//     exactly from  matches = aligned - mismatches  and the reference code of the position
+//     (SURVEY.md App. C);
 //   * after the last chunk the difference arrays are prefix-summed in place (warp shuffle
-//     scan), each thread finalises its positions (all 60 fields of variation_strand are
-//     linear in the counters) and writes the SoA columns with 128-byte coalesced stores.
+//     scan) and the tile is finalised: every field of these statistics is linear in the
+//     counters; each thread produces four consecutive positions of a subset of the fields
+//     and writes them as 128-bit stores (512 contiguous bytes per warp and field).
 // Shared-memory atomics are few (a handful per read), so the kernel is bound by the output
 // stream to HBM.
 #include "pss_internal.cuh"
@@ -27,29 +29,44 @@
 #define FULL 0xffffffffu
 
 #define TT PSS_TTILE          // positions per tile
-#define TTHREADS 256
-#define TCH 256               // reads staged per chunk (one thread each)
-#define TSEQ_BYTES 20480      // staged sequence bytes per chunk (256 x 75 B fits)
+#define TTHREADS 512
+#define NWARPS (TTHREADS / 32)
+#define NQUAD (TT / 4)        // finalisation: quads of positions
+#define NPARTS (TTHREADS / NQUAD)
+#define TCH 192               // reads staged per chunk
+#define TSEQ_BYTES 15360      // staged sequence bytes per chunk (192 x 75 B + slack)
+#define REFN_WORDS (TT / 8)
 
 enum { KIND_COV = 0, KIND_EXT = 1, KIND_VAR = 2 };
 
 template <int KIND> struct KindInfo;
 template <> struct KindInfo<KIND_COV> { static const int NDIFF = 4, NPOINT = 0; };    // all[bank]
 template <> struct KindInfo<KIND_EXT> { static const int NDIFF = 16, NPOINT = 0; };   // class k * 2 + strand
-// nondel[b], del[4 + b], skip[8 + b] | ins[b], mismatch class c in A,C,G,T,N,other: [4 + 4 c + b]
+// all[b], match[4 + b], del[8 + b] | ins[12 + b], mismatches[16 + b], mismatch class c in A,C,G,T,N: [20 + 4 c + b]
 template <> struct KindInfo<KIND_VAR> { static const int NDIFF = 12, NPOINT = 28; };
+
+// per-tile descriptor written by k_tile_desc (+ k_refpack for the flag)
+struct __align__(16) TileDesc {
+    int32_t x, y;        // candidate read index range
+    int32_t n0;          // reads of the first chunk
+    uint32_t flags;      // bit 0: a reference position of the tile has no 4-bit code
+    int64_t seq_lo;      // seq_off[x]
+    int64_t seq_hi;      // seq_off[x + n0]
+};
 
 struct TileArgs {
     const RInfo *ri;
     const uint32_t *cigar;
     const uint8_t *seq4;
     const int64_t *seq_off;
-    const int2 *tile_rng;
-    const uint8_t *ref;
+    const TileDesc *desc;
+    const uint32_t *refpack;   // REFN_WORDS words per tile (+ pad), KIND_VAR only
+    const uint8_t *ref;        // ASCII reference (slow path only)
     int64_t ref_start, ref_len;
     int64_t start, end;
+    int64_t stride;            // elements between consecutive fields of `out`
     int32_t no_del;
-    int32_t need_raw;      // read-level filters active: the row mask needs its own counter
+    int32_t need_raw;          // read-level filters active: the row mask needs its own counter
     int32_t *out;
     uint8_t *rowmask;
     SmallState *st;
@@ -82,26 +99,30 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // ------------------------------------------------------------------------- small helpers
 
-__device__ __forceinline__ int ref_code_of(int c) {
-    if (c >= 'a' && c <= 'z') c -= 32;
-    switch (c) {
-    case '=': return 0; case 'A': return 1; case 'C': return 2; case 'M': return 3;
-    case 'G': return 4; case 'R': return 5; case 'S': return 6; case 'V': return 7;
-    case 'T': return 8; case 'W': return 9; case 'Y': return 10; case 'H': return 11;
-    case 'K': return 12; case 'D': return 13; case 'B': return 14; case 'N': return 15;
-    default: return 16;
+__constant__ uint8_t c_refcode[256];   // upper-cased reference character -> 4-bit code, 16 = none
+
+static void refcode_table(uint8_t *t) {
+    memset(t, 16, 256);
+    const char *nt16 = "=ACMGRSVTWYHKDBN";   // opt.pyx:72
+    for (int k = 0; k < 16; ++k) {
+        t[(unsigned char)nt16[k]] = (uint8_t)k;
+        if (nt16[k] >= 'A' && nt16[k] <= 'Z') t[(unsigned char)(nt16[k] + 32)] = (uint8_t)k;   // refbase.upper()
     }
 }
 
-// 4-bit code -> mismatch class A,C,G,T,N,other (0..5), one nibble per code
-#define MMCLASS_LUT 0x4555555355525105ull
-__device__ __forceinline__ int mm_class(int code) { return (int)((MMCLASS_LUT >> (4 * code)) & 15ull); }
+// 4-bit code -> mismatch class A,C,G,T,N,other (0..5)
+__device__ __forceinline__ int mm_class(int code) {
+    // nibble LUTs: codes 0-7 -> 5,0,1,5,2,5,5,5 ; codes 8-15 -> 3,5,5,5,5,5,5,4
+    uint32_t lut = (code & 8) ? 0x45555553u : 0x55525105u;
+    return (lut >> ((code & 7) << 2)) & 15;
+}
 
 struct TileCtx {
     uint32_t *cnt;          // counter arrays, [array][TT]
     const uint32_t *seqw;   // staged sequence bytes viewed as words
     const uint32_t *refn;   // reference tile, 4-bit codes, first position in the top nibble
-    const uint8_t *refc;    // reference code per position (0..16)
+    const uint8_t *ref;     // ASCII reference, for the slow path
+    int64_t ref_start, ref_len;
     int t0, t1;             // tile position range (t1 = t0 + TT)
     int no_del;
     bool slow;              // a reference position without a code: compare base by base
@@ -115,58 +136,141 @@ __device__ __forceinline__ void interval_add(uint32_t *arr, int x, int l, int t0
     }
 }
 
-// ---- variation: one aligned (M / = / X) segment ---------------------------------------
-// x: reference start, l: length, y: query offset of its first base, sn0: nibble index of the
-// read's first base in the staged sequence stream.
-__device__ __forceinline__ void var_match_segment(const TileCtx &T, int bank, int x, int l, int y, uint32_t sn0,
-                                                  bool hasseq, bool ins) {
-    const int a = max(x - T.t0, 0), b = min(x + l - T.t0, TT);
-    if (a >= b) return;
-    uint32_t *nondel = T.cnt + bank * TT;
-    atomicAdd(nondel + a, 1u);
-    if (b < TT) atomicAdd(nondel + b, 0xffffffffu);
-    uint32_t *pt = T.cnt + KindInfo<KIND_VAR>::NDIFF * TT;
-    if (ins) {   // htslib indel > 0 at the last base of the op (A.1), opt.pyx:501
-        int li = x + l - 1 - T.t0;
-        if (li >= 0 && li < TT) atomicAdd(pt + bank * TT + li, 1u);
+// ---- variation: one read per thread, one 8-base word per loop iteration ---------------------
+//
+// Counter arrays (per bank b = rev | pp << 1):
+//   all[b]        difference array: reads covering the position (M, D and N spans)
+//   match[4 + b]  difference array: +1 / -1 around every aligned span, and -1 / +1 around every
+//                 mismatching base, so that its prefix sum IS the number of matches
+//   del[8 + b]    difference array over D spans
+//   ins[12 + b]   point: insertions (at the base before the I)
+//   mmt[16 + b]   point: mismatches
+//   mmc[20 + 4 c + b]  point: mismatching bases of class c = A, C, G, T, N
+// A position's A count is mmc[A] + (reference is A ? matches : 0), etc..
+
+__device__ __forceinline__ void var_mismatch(const TileCtx &T, int bank, int p, int code) {
+    uint32_t *m = T.cnt + (4 + bank) * TT + p;
+    atomicAdd(m, 0xffffffffu);
+    if (p + 1 < TT) atomicAdd(m + 1, 1u);
+    atomicAdd(T.cnt + (16 + bank) * TT + p, 1u);
+    const int c = mm_class(code);
+    if (c < 5) atomicAdd(T.cnt + (20 + 4 * c + bank) * TT + p, 1u);
+}
+
+struct VarCursor {        // per-thread walk state
+    const uint32_t *cg;   // CIGAR words (global)
+    int nc, k;            // number of ops, next op
+    int x, y;             // reference / query cursor at op k
+    int rn;               // tile-relative reference index of the next base of the current span
+    int rem;              // bases left in the current span (inside the tile)
+    uint32_t sn;          // nibble index of the next base in the staged sequence stream
+};
+
+// Advance to the next aligned span that overlaps the tile, applying the side effects of the
+// ops passed on the way (intervals of D spans, insertion points, the span's match interval).
+__device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, int bank, uint32_t sn0) {
+    while (c.k < c.nc && c.x < T.t1) {
+        const uint32_t w = __ldg(c.cg + c.k);
+        const int op = w & 15, l = (int)(w >> 4);
+        const int k = c.k++;
+        if (op_is_match(op)) {
+            const int x = c.x, y = c.y;
+            c.x += l; c.y += l;
+            if (x + l > T.t0) {
+                const int a = max(x - T.t0, 0), b = min(x + l - T.t0, TT);
+                uint32_t *mt = T.cnt + (4 + bank) * TT;
+                atomicAdd(mt + a, 1u);
+                if (b < TT) atomicAdd(mt + b, 0xffffffffu);
+                if (T.no_del) interval_add(T.cnt + bank * TT, x, l, T.t0);   // D / N spans do not count
+                // htslib indel > 0 at the last base of the op (A.1), opt.pyx:501
+                const int li = x + l - 1 - T.t0;
+                if (k + 1 < c.nc && li >= 0 && li < TT) {
+                    const uint32_t w2 = __ldg(c.cg + k + 1);
+                    const int op2 = w2 & 15;
+                    bool ins = false;
+                    if (op2 == OP_I) ins = (w2 >> 4) > 0;
+                    else if (op2 == OP_P && k + 2 < c.nc) {
+                        long long l3 = 0;
+                        for (int j = k + 2; j < c.nc; ++j) {
+                            const uint32_t w3 = __ldg(c.cg + j);
+                            const int op3 = w3 & 15;
+                            if (op3 == OP_I) l3 += (w3 >> 4);
+                            else if (op3 == OP_D || op3 == OP_M || op3 == OP_N || op3 == OP_EQ || op3 == OP_X) break;
+                        }
+                        ins = l3 > 0;
+                    }
+                    if (ins) atomicAdd(T.cnt + (12 + bank) * TT + li, 1u);
+                }
+                c.rn = a; c.rem = b - a;
+                c.sn = sn0 + (uint32_t)(y + (a + T.t0 - x));
+                return true;
+            }
+        } else if (op == OP_D || op == OP_N) {
+            if (op == OP_D && !T.no_del && c.x + l > T.t0) interval_add(T.cnt + (8 + bank) * TT, c.x, l, T.t0);
+            c.x += l;
+        } else if (op == OP_I || op == OP_S) c.y += l;
     }
-    uint32_t *mm = pt + (4 + bank) * TT;       // class c at mm + 4 c TT
-    const int len = b - a;
-    if (!hasseq) {                              // no sequence: every base is an "other" mismatch (opt.pyx:2146-2147)
-        for (int i = 0; i < len; ++i) atomicAdd(mm + 5 * 4 * TT + a + i, 1u);
+    return false;
+}
+
+__device__ __forceinline__ void var_read(const TileCtx &T, const TileArgs &A, const RInfo &r, uint32_t sn0, uint32_t *raw) {
+    const uint32_t cls = r.cls;
+    if (!(cls & CLS_ADMITTED)) return;
+    if (raw) interval_add(raw, r.pos, r.end - r.pos, T.t0);
+    if (!(cls & CLS_COUNTED)) return;
+    const int bank = cls & 3u;
+    if (!T.no_del) interval_add(T.cnt + bank * TT, r.pos, r.end - r.pos, T.t0);   // M, D and N all count
+    if (cls & CLS_NOREF) {   // mapped, CIGAR consumes no reference: one deletion event at pos
+        if (!T.no_del) interval_add(T.cnt + (8 + bank) * TT, r.pos, 1, T.t0);
         return;
     }
-    uint32_t sn = sn0 + (uint32_t)(y + (a + T.t0 - x));
-    if (T.slow) {
-        for (int i = 0; i < len; ++i) {
-            uint32_t k = sn + i;
-            uint32_t w = T.seqw[k >> 3];
-            int code = (w >> (((k & 7) ^ 1) << 2)) & 15;   // byte k/2 of the stream, high nibble first
-            if (code != T.refc[a + i]) atomicAdd(mm + mm_class(code) * 4 * TT + a + i, 1u);
+    VarCursor c;
+    c.cg = A.cigar + r.cigar_off; c.nc = (int)r.n_cigar; c.k = 0; c.x = r.pos; c.y = 0;
+    const bool simple = cls & CLS_SIMPLE;
+    bool have;
+    if (simple) {
+        const int a = max(r.pos - T.t0, 0), b = min(r.end - T.t0, TT);
+        have = a < b;
+        if (have) {
+            uint32_t *mt = T.cnt + (4 + bank) * TT;
+            atomicAdd(mt + a, 1u);
+            if (b < TT) atomicAdd(mt + b, 0xffffffffu);
+            if (T.no_del) interval_add(T.cnt + bank * TT, r.pos, r.end - r.pos, T.t0);
+            c.rn = a; c.rem = b - a; c.sn = sn0 + (uint32_t)(a + T.t0 - r.pos);
         }
-        return;
-    }
-    uint32_t si = sn >> 3, ssh = (sn & 7) << 2;
-    uint32_t ri = (uint32_t)a >> 3, rsh = ((uint32_t)a & 7) << 2;
-    uint32_t s_hi = __byte_perm(T.seqw[si], 0, 0x0123), r_hi = T.refn[ri];
-    for (int i = 0; i < len; i += 8) {
-        uint32_t s_lo = __byte_perm(T.seqw[++si], 0, 0x0123), r_lo = T.refn[++ri];
-        uint32_t sw = __funnelshift_l(s_lo, s_hi, ssh), rw = __funnelshift_l(r_lo, r_hi, rsh);
-        s_hi = s_lo; r_hi = r_lo;
-        uint32_t xr = sw ^ rw;
-        int rem = len - i;
-        if (rem < 8) xr &= 0xffffffffu << ((8 - rem) << 2);
-        while (xr) {
-            int lz = __clz(xr) >> 2;
-            int sh = 28 - (lz << 2);
-            int code = (sw >> sh) & 15;
-            atomicAdd(mm + mm_class(code) * 4 * TT + a + i + lz, 1u);
-            xr &= ~(0xfu << sh);
+    } else have = var_next_span(T, c, bank, sn0);
+    const bool hasseq = cls & CLS_HASSEQ;
+    while (have) {
+        const int n8 = min(c.rem, 8);
+        if (!hasseq) {           // no sequence: every base is a mismatch of no class (opt.pyx:2146-2147)
+            for (int i = 0; i < n8; ++i) var_mismatch(T, bank, c.rn + i, 0);
+        } else if (T.slow) {     // a reference position of this tile has no 4-bit code
+            for (int i = 0; i < n8; ++i) {
+                const uint32_t k = c.sn + i;
+                const int code = (T.seqw[k >> 3] >> (((k & 7) ^ 1) << 2)) & 15;   // byte k / 2, high nibble first
+                const int64_t ro = (int64_t)T.t0 + c.rn + i - T.ref_start;
+                const int rc = (T.ref && ro >= 0 && ro < T.ref_len) ? c_refcode[__ldg(T.ref + ro)] : 16;
+                if (code != rc) var_mismatch(T, bank, c.rn + i, code);
+            }
+        } else {
+            const uint32_t si = c.sn >> 3, ssh = (c.sn & 7) << 2;
+            const uint32_t ri = (uint32_t)c.rn >> 3, rsh = ((uint32_t)c.rn & 7) << 2;
+            const uint32_t sw = __funnelshift_l(__byte_perm(T.seqw[si + 1], 0, 0x0123), __byte_perm(T.seqw[si], 0, 0x0123), ssh);
+            const uint32_t rw = __funnelshift_l(T.refn[ri + 1], T.refn[ri], rsh);
+            uint32_t xr = sw ^ rw;
+            if (n8 < 8) xr &= 0xffffffffu << ((8 - n8) << 2);
+            while (xr) {
+                const int lz = __clz(xr) >> 2, sh = 28 - (lz << 2);
+                var_mismatch(T, bank, c.rn + lz, (sw >> sh) & 15);
+                xr &= ~(0xfu << sh);
+            }
         }
+        c.rn += 8; c.sn += 8; c.rem -= 8;
+        if (c.rem <= 0) have = simple ? false : var_next_span(T, c, bank, sn0);
     }
 }
 
-// ---- generic per-read walk ----------------------------------------------------------------
+// ---- coverage kinds: one read per thread ------------------------------------------------------
 
 template <int KIND>
 __device__ __forceinline__ void cover_segment(const TileCtx &T, uint32_t cls, int x, int l) {
@@ -187,65 +291,26 @@ __device__ __forceinline__ void cover_segment(const TileCtx &T, uint32_t cls, in
 }
 
 template <int KIND>
-__device__ void tile_read(const TileCtx &T, const TileArgs &A, const RInfo &r, uint32_t sn0, uint32_t *raw) {
+__device__ void cover_read(const TileCtx &T, const TileArgs &A, const RInfo &r, uint32_t *raw) {
     const uint32_t cls = r.cls;
     if (!(cls & CLS_ADMITTED)) return;
     if (raw) interval_add(raw, r.pos, r.end - r.pos, T.t0);
     if (!(cls & CLS_COUNTED)) return;
-    const int bank = cls & 3u;
-    if (KIND != KIND_VAR && !T.no_del) {   // D / N / zero-length alignments all count (opt.pyx:1904-1906)
+    if (!T.no_del || (cls & CLS_SIMPLE)) {   // D / N / zero-length alignments all count (opt.pyx:1904-1906)
         cover_segment<KIND>(T, cls, r.pos, r.end - r.pos);
         return;
     }
-    const bool hasseq = cls & CLS_HASSEQ;
-    if (cls & CLS_SIMPLE) {
-        if (KIND == KIND_VAR) var_match_segment(T, bank, r.pos, r.end - r.pos, 0, sn0, hasseq, false);
-        else cover_segment<KIND>(T, cls, r.pos, r.end - r.pos);
-        return;
-    }
-    if (cls & CLS_NOREF) {   // mapped, CIGAR consumes no reference: one deletion event at pos
-        if (!T.no_del) {
-            if (KIND == KIND_VAR) interval_add(T.cnt + (4 + bank) * TT, r.pos, 1, T.t0);
-            else cover_segment<KIND>(T, cls, r.pos, 1);
-        }
-        return;
-    }
+    if (cls & CLS_NOREF) return;             // its only event is deletion-like: dropped by no_del
     const uint32_t *cg = A.cigar + r.cigar_off;
     const int nc = (int)r.n_cigar;
-    int x = r.pos, y = 0;
+    int x = r.pos;
     for (int k = 0; k < nc && x < T.t1; ++k) {
         uint32_t w = __ldg(cg + k);
         int op = w & 15, l = (int)(w >> 4);
         if (op_is_match(op)) {
-            if (x + l > T.t0) {
-                if (KIND == KIND_VAR) {
-                    bool ins = false;
-                    if (k + 1 < nc && x + l - 1 >= T.t0 && x + l - 1 < T.t1) {
-                        uint32_t w2 = __ldg(cg + k + 1);
-                        int op2 = w2 & 15;
-                        if (op2 == OP_I) ins = (w2 >> 4) > 0;
-                        else if (op2 == OP_P && k + 2 < nc) {
-                            long long l3 = 0;
-                            for (int j = k + 2; j < nc; ++j) {
-                                uint32_t w3 = __ldg(cg + j);
-                                int op3 = w3 & 15;
-                                if (op3 == OP_I) l3 += (w3 >> 4);
-                                else if (op3 == OP_D || op3 == OP_M || op3 == OP_N || op3 == OP_EQ || op3 == OP_X) break;
-                            }
-                            ins = l3 > 0;
-                        }
-                    }
-                    var_match_segment(T, bank, x, l, y, sn0, hasseq, ins);
-                } else cover_segment<KIND>(T, cls, x, l);
-            }
-            x += l; y += l;
-        } else if (op == OP_D || op == OP_N) {
-            if (!T.no_del && x + l > T.t0) {
-                if (KIND == KIND_VAR) interval_add(T.cnt + ((op == OP_N ? 8 : 4) + bank) * TT, x, l, T.t0);
-                else cover_segment<KIND>(T, cls, x, l);
-            }
+            if (x + l > T.t0) cover_segment<KIND>(T, cls, x, l);
             x += l;
-        } else if (op == OP_I || op == OP_S) y += l;
+        } else if (op == OP_D || op == OP_N) x += l;
     }
 }
 
@@ -280,62 +345,124 @@ __device__ __forceinline__ void warp_scan_array(uint32_t *arr, int lane) {
 
 // ---- finalisation: rec() of the reference classes, all linear in the counters ------------------
 
-__device__ __forceinline__ void six(const uint32_t *v, int32_t *q, int64_t st) {
-    // banks rev | pp << 1 -> all, fwd, rev, pp, pp_fwd, pp_rev (CountPpStrand, opt.pyx:147-168)
-    uint32_t fwd = v[0] + v[2], rev = v[1] + v[3];
-    q[0] = fwd + rev; q[st] = fwd; q[2 * st] = rev; q[3 * st] = v[2] + v[3]; q[4 * st] = v[2]; q[5 * st] = v[3];
+__device__ __forceinline__ uint4 operator+(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ uint4 operator-(uint4 a, uint4 b) { return make_uint4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
+struct QuadOut {
+    int32_t *p;        // position 4q of the next field to write
+    int64_t stride;
+    bool vec;          // 128-bit stores allowed
+    int nvalid;        // positions of the quad inside [start, end)
+    __device__ __forceinline__ void put(uint4 v) {
+        if (vec) *reinterpret_cast<uint4 *>(p) = v;
+        else {
+            if (nvalid > 0) p[0] = v.x;
+            if (nvalid > 1) p[1] = v.y;
+            if (nvalid > 2) p[2] = v.z;
+            if (nvalid > 3) p[3] = v.w;
+        }
+        p += stride;
+    }
+    __device__ __forceinline__ void skip(int nfields) { p += stride * nfields; }
+    // banks rev | pp << 1 -> all, fwd, rev, pp, pp_fwd, pp_rev (CountPpStrand, opt.pyx:147-168) or all, pp
+    template <bool STRAND>
+    __device__ __forceinline__ void put_group(const uint4 *v) {
+        uint4 fwd = v[0] + v[2], rev = v[1] + v[3], pp = v[2] + v[3];
+        put(fwd + rev);
+        if (STRAND) { put(fwd); put(rev); put(pp); put(v[2]); put(v[3]); }
+        else put(pp);
+    }
+};
+
+__device__ __forceinline__ uint4 ld4(const uint32_t *cnt, int arr, int q) {
+    return *reinterpret_cast<const uint4 *>(cnt + arr * TT + 4 * q);
+}
+// v + (refcode of the position == code ? mt : 0) for the four positions of a quad
+__device__ __forceinline__ uint4 base_count(uint4 m, uint4 mt, uint32_t rc4, uint32_t code) {
+    uint4 r = m;
+    if (((rc4 >> 12) & 15u) == code) r.x += mt.x;
+    if (((rc4 >> 8) & 15u) == code) r.y += mt.y;
+    if (((rc4 >> 4) & 15u) == code) r.z += mt.z;
+    if ((rc4 & 15u) == code) r.w += mt.w;
+    return r;
 }
 
+// Writes the fields owned by (quad q, part) and returns the quad's total read count when this
+// part computes it (part 0), for the row mask.
 template <int STAT>
-__device__ __forceinline__ uint32_t tile_store(const uint32_t *cnt, int i, int refc, int32_t *o, int64_t st) {
+__device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32_t *refn, int q, int part, QuadOut &O) {
+    uint4 all = make_uint4(0, 0, 0, 0);
     if (STAT == PSS_COVERAGE || STAT == PSS_COVERAGE_STRAND || STAT == PSS_COVERAGE_GC) {
-        uint32_t n[4];
+        if (part == 0) {
+            uint4 n[4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) n[b] = cnt[b * TT + i];
-        uint32_t all = n[0] + n[1] + n[2] + n[3], pp = n[2] + n[3];
-        if (STAT == PSS_COVERAGE) { o[0] = all; o[st] = pp; }
-        else if (STAT == PSS_COVERAGE_GC) { o[st] = all; o[2 * st] = pp; }     // field 0 = gc (k_gc)
-        else six(n, o, st);
-        return all;
+            for (int b = 0; b < 4; ++b) n[b] = ld4(cnt, b, q);
+            all = n[0] + n[1] + n[2] + n[3];
+            if (STAT == PSS_COVERAGE_GC) O.skip(1);                      // field 0 = gc (k_gc)
+            if (STAT == PSS_COVERAGE_STRAND) O.put_group<true>(n); else O.put_group<false>(n);
+        }
     } else if (STAT == PSS_COVERAGE_EXT || STAT == PSS_COVERAGE_EXT_STRAND) {
-        uint32_t all = 0;
+        const int per = 8 / NPARTS;       // classes per part
+        if (part == 0) all = ld4(cnt, 0, q) + ld4(cnt, 1, q);
+        O.skip(part * per * (STAT == PSS_COVERAGE_EXT ? 1 : 3));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint32_t f = cnt[(2 * k) * TT + i], r = cnt[(2 * k + 1) * TT + i];
-            if (k == 0) all = f + r;
-            if (STAT == PSS_COVERAGE_EXT) o[k * st] = f + r;
-            else { o[(3 * k) * st] = f + r; o[(3 * k + 1) * st] = f; o[(3 * k + 2) * st] = r; }
+        for (int k = 0; k < per; ++k) {
+            int c = part * per + k;
+            uint4 f = ld4(cnt, 2 * c, q), r = ld4(cnt, 2 * c + 1, q);
+            O.put(f + r);
+            if (STAT == PSS_COVERAGE_EXT_STRAND) { O.put(f); O.put(r); }
         }
-        return all;
     } else {
-        // groups: reads, matches, mismatches, deletions, insertions, A, C, T, G, N
-        uint32_t g[10][4];
-        const uint32_t *pt = cnt + KindInfo<KIND_VAR>::NDIFF * TT;
-        uint32_t all = 0;
+        // groups: 0 reads, 1 matches, 2 mismatches, 3 deletions, 4 insertions, 5 A, 6 C, 7 T, 8 G, 9 N
+        // part 0 -> groups 0-2, part 1 -> 3-5, part 2 -> 6-7, part 3 -> 8-9 (contiguous fields)
+        const bool S = (STAT == PSS_VARIATION_STRAND);
+        const int per = S ? 6 : 2;
+        uint4 v[4];
+        if (part == 0) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            uint32_t nd = cnt[b * TT + i], dl = cnt[(4 + b) * TT + i], sk = cnt[(8 + b) * TT + i];
-            uint32_t m[6], mm = 0;
+            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, b, q);
+            all = v[0] + v[1] + v[2] + v[3];
+            O.put_group<S>(v);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) { m[c] = pt[(4 + 4 * c + b) * TT + i]; mm += m[c]; }
-            uint32_t mt = nd - mm;
-            g[0][b] = nd + dl + sk; g[1][b] = mt; g[2][b] = mm; g[3][b] = dl; g[4][b] = pt[b * TT + i];
-            g[5][b] = m[0] + (refc == 1 ? mt : 0u);    // A
-            g[6][b] = m[1] + (refc == 2 ? mt : 0u);    // C
-            g[7][b] = m[3] + (refc == 8 ? mt : 0u);    // T
-            g[8][b] = m[2] + (refc == 4 ? mt : 0u);    // G
-            g[9][b] = m[4] + (refc == 15 ? mt : 0u);   // N
-            all += g[0][b];
+            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, 4 + b, q);
+            O.put_group<S>(v);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, 16 + b, q);
+            O.put_group<S>(v);
+            return all;
         }
+        const uint32_t rw = refn[q >> 1];
+        const uint32_t rc4 = (q & 1) ? (rw & 0xffffu) : (rw >> 16);
+        if (part == 1) {
+            O.skip(3 * per);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            if (STAT == PSS_VARIATION) {
-                o[(2 * k) * st] = g[k][0] + g[k][1] + g[k][2] + g[k][3];
-                o[(2 * k + 1) * st] = g[k][2] + g[k][3];
-            } else six(g[k], o + (int64_t)(6 * k) * st, st);
+            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, 8 + b, q);
+            O.put_group<S>(v);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, 12 + b, q);
+            O.put_group<S>(v);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 20 + b, q), ld4(cnt, 4 + b, q), rc4, 1u);   // A
+            O.put_group<S>(v);
+        } else if (part == 2) {
+            O.skip(6 * per);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 24 + b, q), ld4(cnt, 4 + b, q), rc4, 2u);   // C
+            O.put_group<S>(v);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 32 + b, q), ld4(cnt, 4 + b, q), rc4, 8u);   // T
+            O.put_group<S>(v);
+        } else {
+            O.skip(8 * per);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 28 + b, q), ld4(cnt, 4 + b, q), rc4, 4u);   // G
+            O.put_group<S>(v);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 36 + b, q), ld4(cnt, 4 + b, q), rc4, 15u);  // N
+            O.put_group<S>(v);
         }
-        return all;
     }
+    return all;
 }
 
 // ------------------------------------------------------------------------------ the kernel
@@ -343,65 +470,88 @@ __device__ __forceinline__ uint32_t tile_store(const uint32_t *cnt, int i, int r
 template <int KIND, int STAT>
 __global__ void __launch_bounds__(TTHREADS, 2)
 k_tile(TileArgs A) {
+    static_assert(NPARTS == 4, "finalisation is written for four parts");
     extern __shared__ __align__(128) uint8_t smem[];
     const int NARR = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
     uint32_t *raw = cnt + NARR * TT;                                   // only touched when need_raw
     RInfo *s_ri = reinterpret_cast<RInfo *>(raw + TT);
     // the rest exists for KIND_VAR only (see tile_smem_bytes)
-    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_ri + TCH);          // TSEQ_BYTES + 32
-    uint32_t *s_refn = reinterpret_cast<uint32_t *>(s_seq + TSEQ_BYTES + 32);   // TT / 8 + 2 words
-    uint8_t *s_refc = reinterpret_cast<uint8_t *>(s_refn + TT / 8 + 2);         // TT bytes
+    uint32_t *s_refn = reinterpret_cast<uint32_t *>(s_ri + TCH);       // REFN_WORDS + 4 words
+    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_refn + REFN_WORDS + 4);   // TSEQ_BYTES + 32
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_n, s_slow;
+    __shared__ int s_n;
     __shared__ long long s_seqlo;      // global byte index staged at s_seq[0]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int64_t t0l = A.start + (int64_t)tile * TT;
-    const int2 rng = A.tile_rng[tile];
 
-    if (tid == 0) { mbar_init(&s_bar, 1); s_slow = 0; }
+    // ---- thread 0 starts the bulk copies of the first chunk before anything else -------------
+    TileDesc d;
+    {
+        const uint4 *dp = reinterpret_cast<const uint4 *>(A.desc + tile);
+        uint4 d0 = __ldg(dp);
+        d.x = (int)d0.x; d.y = (int)d0.y; d.n0 = (int)d0.z; d.flags = d0.w;
+    }
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        uint32_t bytes = 0, sbytes = 0;
+        const uint8_t *src = nullptr;
+        const int n = d.n0;
+        if (KIND == KIND_VAR && n > 0) {
+            uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile) + 1);
+            long long lo = (long long)(((uint64_t)d1.y << 32) | d1.x), hi = (long long)(((uint64_t)d1.w << 32) | d1.z);
+            uintptr_t a0 = reinterpret_cast<uintptr_t>(A.seq4 + lo), a1 = reinterpret_cast<uintptr_t>(A.seq4 + hi);
+            uintptr_t al = a0 & ~(uintptr_t)15, ah = (a1 + 15) & ~(uintptr_t)15;
+            src = reinterpret_cast<const uint8_t *>(al);
+            sbytes = (uint32_t)(ah - al);
+            s_seqlo = lo - (long long)(a0 - al);
+        }
+        s_n = n;
+        if (n > 0) {
+            bytes = (uint32_t)n * (uint32_t)sizeof(RInfo) + sbytes + (KIND == KIND_VAR ? (REFN_WORDS + 4) * 4 : 0);
+            mbar_arrive_expect_tx(&s_bar, bytes);
+            bulk_g2s(s_ri, A.ri + d.x, (uint32_t)n * (uint32_t)sizeof(RInfo), &s_bar);
+            if (sbytes) bulk_g2s(s_seq, src, sbytes, &s_bar);
+            if (KIND == KIND_VAR) bulk_g2s(s_refn, A.refpack + (size_t)tile * REFN_WORDS, (REFN_WORDS + 4) * 4, &s_bar);
+        } else mbar_arrive_expect_tx(&s_bar, 0);
+    }
     {   // zero the counters
         const int nw4 = (NARR + (A.need_raw ? 1 : 0)) * TT / 4;
         uint4 z = make_uint4(0, 0, 0, 0);
         for (int k = tid; k < nw4; k += TTHREADS) reinterpret_cast<uint4 *>(cnt)[k] = z;
     }
-    __syncthreads();
-    if (KIND == KIND_VAR) {   // reference tile: code per position + packed nibbles
-#pragma unroll
-        for (int h = 0; h < TT / TTHREADS; ++h) {
-            int i = tid + h * TTHREADS;
-            int64_t ro = t0l + i - A.ref_start;
-            int c = 16;
-            if (A.ref && ro >= 0 && ro < A.ref_len) c = ref_code_of(__ldg(A.ref + ro));
-            s_refc[i] = (uint8_t)c;
-            if (c == 16 && t0l + i < A.end) s_slow = 1;
-            uint32_t v = (uint32_t)(c & 15) << (28 - ((lane & 7) << 2));
-            v |= __shfl_xor_sync(FULL, v, 1);
-            v |= __shfl_xor_sync(FULL, v, 2);
-            v |= __shfl_xor_sync(FULL, v, 4);
-            if ((lane & 7) == 0) s_refn[i >> 3] = v;
-        }
-        if (tid < 2) s_refn[TT / 8 + tid] = 0;
-    }
+    __syncthreads();           // barrier initialised, counters zeroed
 
     TileCtx T;
-    T.cnt = cnt; T.seqw = reinterpret_cast<const uint32_t *>(s_seq); T.refn = s_refn; T.refc = s_refc;
-    T.t0 = (int)t0l; T.t1 = T.t0 + TT; T.no_del = A.no_del; T.slow = false;
+    T.cnt = cnt; T.seqw = reinterpret_cast<const uint32_t *>(s_seq); T.refn = s_refn;
+    T.ref = A.ref; T.ref_start = A.ref_start; T.ref_len = A.ref_len;
+    T.t0 = (int)t0l; T.t1 = T.t0 + TT; T.no_del = A.no_del; T.slow = (d.flags & 1u) != 0;
+    uint32_t *rawp = A.need_raw ? raw : nullptr;
 
     uint32_t parity = 0;
-    for (int cb = rng.x; cb < rng.y;) {
-        __syncthreads();                       // staging buffers free, s_slow / counters visible
+    for (int cb = d.x;;) {
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
+        const int n = s_n;
+        if (n == 0) break;
+        if (tid < n) {
+            const RInfo r = s_ri[tid];
+            if (KIND == KIND_VAR) var_read(T, A, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp);
+            else cover_read<KIND>(T, A, r, rawp);
+        }
+        cb += n;
+        if (cb >= d.y) break;
+        __syncthreads();                       // staging buffers free again
         if (tid == 0) {
-            int n = min(TCH, rng.y - cb);
-            uint32_t bytes = 0;
-            const uint8_t *src = nullptr;
+            int m = min(TCH, d.y - cb);
             uint32_t sbytes = 0;
+            const uint8_t *src = nullptr;
             if (KIND == KIND_VAR) {
-                long long lo = A.seq_off[cb], hi = A.seq_off[cb + n];
-                while (n > 1 && hi - lo + 32 > TSEQ_BYTES) { n >>= 1; hi = A.seq_off[cb + n]; }
-                if (hi - lo + 32 > TSEQ_BYTES) { atomicOr(&A.st->toolong, 1); n = 0; }
+                long long lo = A.seq_off[cb], hi = A.seq_off[cb + m];
+                while (m > 1 && hi - lo + 32 > TSEQ_BYTES) { m >>= 1; hi = A.seq_off[cb + m]; }
+                if (hi - lo + 32 > TSEQ_BYTES) { atomicOr(&A.st->toolong, 1); m = 0; }
                 else {
                     uintptr_t a0 = reinterpret_cast<uintptr_t>(A.seq4 + lo), a1 = reinterpret_cast<uintptr_t>(A.seq4 + hi);
                     uintptr_t al = a0 & ~(uintptr_t)15, ah = (a1 + 15) & ~(uintptr_t)15;
@@ -410,62 +560,112 @@ k_tile(TileArgs A) {
                     s_seqlo = lo - (long long)(a0 - al);
                 }
             }
-            s_n = n;
+            s_n = m;
             fence_proxy_async();
-            if (n > 0) {
-                bytes = (uint32_t)n * (uint32_t)sizeof(RInfo) + sbytes;
-                mbar_arrive_expect_tx(&s_bar, bytes);
-                bulk_g2s(s_ri, A.ri + cb, (uint32_t)n * (uint32_t)sizeof(RInfo), &s_bar);
+            if (m > 0) {
+                mbar_arrive_expect_tx(&s_bar, (uint32_t)m * (uint32_t)sizeof(RInfo) + sbytes);
+                bulk_g2s(s_ri, A.ri + cb, (uint32_t)m * (uint32_t)sizeof(RInfo), &s_bar);
                 if (sbytes) bulk_g2s(s_seq, src, sbytes, &s_bar);
             } else mbar_arrive_expect_tx(&s_bar, 0);
         }
-        mbar_wait(&s_bar, parity);
-        parity ^= 1;
-        const int n = s_n;
-        if (n == 0) break;
-        T.slow = s_slow != 0;
-        if (tid < n) {
-            const RInfo r = s_ri[tid];
-            uint32_t sn0 = (KIND == KIND_VAR) ? (uint32_t)((r.seq_off - s_seqlo) << 1) : 0u;
-            tile_read<KIND>(T, A, r, sn0, A.need_raw ? raw : nullptr);
-        }
-        cb += n;
     }
     __syncthreads();
     {   // prefix sums of the difference arrays (+ raw)
         const int nscan = KindInfo<KIND>::NDIFF + (A.need_raw ? 1 : 0);
-        for (int a = warp; a < nscan; a += TTHREADS / 32) {
+        for (int a = warp; a < nscan; a += NWARPS) {
             uint32_t *arr = (a < KindInfo<KIND>::NDIFF) ? cnt + a * TT : raw;
             warp_scan_array(arr, lane);
         }
     }
     __syncthreads();
-    const int64_t npos = A.end - A.start;
-#pragma unroll
-    for (int h = 0; h < TT / TTHREADS; ++h) {
-        int i = tid + h * TTHREADS;
-        int64_t pl = t0l + i;
-        if (pl < A.end) {
-            int refc = (KIND == KIND_VAR) ? s_refc[i] : 16;
-            uint32_t all = tile_store<STAT>(cnt, i, refc, A.out + (pl - A.start), npos);
-            uint32_t rw = A.need_raw ? raw[i] : all;
-            A.rowmask[pl - A.start] = rw ? 1 : 0;
+    {
+        const int q = tid & (NQUAD - 1), part = tid / NQUAD;
+        const int64_t pl = t0l + 4 * q;
+        const int64_t rem = A.end - pl;
+        if (rem > 0) {
+            QuadOut O;
+            O.p = A.out + (pl - A.start);
+            O.stride = A.stride;
+            O.nvalid = rem > 4 ? 4 : (int)rem;
+            const bool aligned = ((reinterpret_cast<uintptr_t>(A.out) & 15) == 0) && ((A.stride & 3) == 0) &&
+                                 (((pl - A.start) & 3) == 0);
+            // full quads always; partial quads only when the row is padded (stride beyond the range)
+            O.vec = aligned && (O.nvalid == 4 || (pl - A.start) + 4 <= A.stride);
+            uint4 all = tile_finalize<STAT>(cnt, s_refn, q, part, O);
+            if (part == 0) {
+                if (A.need_raw) all = ld4(raw, 0, q);
+                uint8_t *m = A.rowmask + (pl - A.start);
+                if (O.nvalid > 0) m[0] = all.x ? 1 : 0;
+                if (O.nvalid > 1) m[1] = all.y ? 1 : 0;
+                if (O.nvalid > 2) m[2] = all.z ? 1 : 0;
+                if (O.nvalid > 3) m[3] = all.w ? 1 : 0;
+            }
         }
     }
 }
 
+// ------------------------------------------------------- descriptors + packed reference
+
+// One thread per tile: candidate read range (reads are start-sorted, so it is the index
+// range [first pos >= t0 - maxspan + 1, first pos >= t1)), the first chunk and its sequence span.
+__global__ void __launch_bounds__(256)
+k_tile_desc(const RInfo *__restrict__ ri, const int64_t *__restrict__ seq_off, int64_t n, SmallState *st,
+            int64_t start, int64_t ntiles, int with_seq, TileDesc *__restrict__ desc) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    long long t0 = start + t * TT, t1 = t0 + TT;
+    long long key0 = t0 - st->maxspan + 1;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((long long)ri[mid].pos < key0) lo = mid + 1; else hi = mid; }
+    int64_t x = lo;
+    hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((long long)ri[mid].pos < t1) lo = mid + 1; else hi = mid; }
+    int64_t y = lo;
+    TileDesc d;
+    d.x = (int32_t)x; d.y = (int32_t)y; d.flags = 0; d.seq_lo = 0; d.seq_hi = 0;
+    int m = (int)(y - x < TCH ? y - x : TCH);
+    if (with_seq && m > 0) {
+        long long slo = seq_off[x], shi = seq_off[x + m];
+        while (m > 1 && shi - slo + 32 > TSEQ_BYTES) { m >>= 1; shi = seq_off[x + m]; }
+        if (shi - slo + 32 > TSEQ_BYTES) { atomicOr(&st->toolong, 1); m = 0; }
+        d.seq_lo = slo; d.seq_hi = shi;
+    }
+    d.n0 = m;
+    desc[t] = d;
+}
+
+// The reference as 4-bit codes, eight positions per word (first position in the top nibble),
+// tile-aligned to `start`; flags tiles that contain a position without a code.
+__global__ void __launch_bounds__(256)
+k_refpack(const uint8_t *__restrict__ ref, int64_t ref_start, int64_t ref_len, int64_t start, int64_t end,
+          int64_t nwords, uint32_t *__restrict__ out, TileDesc *desc) {
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    int64_t p0 = start + w * 8;
+    uint32_t v = 0;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int64_t p = p0 + k, ro = p - ref_start;
+        int c = (ref && ro >= 0 && ro < ref_len) ? c_refcode[__ldg(ref + ro)] : 16;
+        if (c == 16 && p < end) bad = true;
+        v |= (uint32_t)(c & 15) << (28 - 4 * k);
+    }
+    out[w] = v;
+    if (bad) atomicOr(&desc[(w * 8) / TT].flags, 1u);
+}
+
 template <int KIND>
-static size_t tile_smem_bytes(bool need_raw) {
-    size_t narr = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT + 1;   // raw slot always reserved (layout)
-    (void)need_raw;
+static size_t tile_smem_bytes() {
+    size_t narr = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT + 1;   // + raw
     size_t b = narr * TT * 4 + sizeof(RInfo) * TCH;
-    if (KIND == KIND_VAR) b += TSEQ_BYTES + 32 + (TT / 8 + 2) * 4 + TT;
+    if (KIND == KIND_VAR) b += (REFN_WORDS + 4) * 4 + TSEQ_BYTES + 32;
     return b;
 }
 
 template <int KIND, int STAT>
 static cudaError_t launch_tile_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
-    size_t smem = tile_smem_bytes<KIND>(a.need_raw);
+    size_t smem = tile_smem_bytes<KIND>();
     static bool configured = false;     // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tile<KIND, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -485,22 +685,50 @@ bool tile_kernel_supports(int stat, int min_baseq) {
     }
 }
 
-cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, SmallState *st, int need_raw,
-                        int64_t ntiles, cudaStream_t s, int64_t *launches) {
+size_t tile_desc_bytes(int64_t ntiles) { return sizeof(TileDesc) * (size_t)ntiles; }
+size_t tile_refpack_bytes(int64_t ntiles) { return ((size_t)ntiles * REFN_WORDS + 8) * 4; }
+
+cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, int64_t n_reads, SmallState *st,
+                        int need_raw, int64_t ntiles, void *desc_buf, void *refpack_buf, cudaStream_t s,
+                        int64_t *launches, cudaEvent_t e0, cudaEvent_t e1) {
     if (ntiles <= 0) return cudaSuccess;
+    static bool table_ready = false;
+    if (!table_ready) {
+        uint8_t t[256];
+        refcode_table(t);
+        cudaError_t e = cudaMemcpyToSymbol(c_refcode, t, 256);
+        if (e != cudaSuccess) return e;
+        table_ready = true;
+    }
+    const bool var = (stat == PSS_VARIATION || stat == PSS_VARIATION_STRAND);
+    TileDesc *desc = (TileDesc *)desc_buf;
+    k_tile_desc<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(p.ri, seq_off, n_reads, st, p.start, ntiles, var ? 1 : 0, desc);
+    if (launches) ++*launches;
+    if (var) {
+        int64_t nwords = ntiles * REFN_WORDS + 8;
+        k_refpack<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(p.ref, p.ref_start, p.ref_len, p.start, p.end, nwords,
+                                                                  (uint32_t *)refpack_buf, desc);
+        if (launches) ++*launches;
+    }
     TileArgs a;
-    a.ri = p.ri; a.cigar = p.cigar; a.seq4 = p.seq4; a.seq_off = seq_off; a.tile_rng = p.tile_rng;
+    a.ri = p.ri; a.cigar = p.cigar; a.seq4 = p.seq4; a.seq_off = seq_off; a.desc = desc;
+    a.refpack = (const uint32_t *)refpack_buf;
     a.ref = p.ref; a.ref_start = p.ref_start; a.ref_len = p.ref_len; a.start = p.start; a.end = p.end;
+    a.stride = p.out_stride;
     a.no_del = p.no_del; a.need_raw = need_raw; a.out = p.out; a.rowmask = p.rowmask; a.st = st;
     if (launches) ++*launches;
+    if (e0) cudaEventRecord(e0, s);
+    cudaError_t e;
     switch (stat) {
-    case PSS_COVERAGE: return launch_tile_one<KIND_COV, PSS_COVERAGE>(a, ntiles, s);
-    case PSS_COVERAGE_STRAND: return launch_tile_one<KIND_COV, PSS_COVERAGE_STRAND>(a, ntiles, s);
-    case PSS_COVERAGE_GC: return launch_tile_one<KIND_COV, PSS_COVERAGE_GC>(a, ntiles, s);
-    case PSS_COVERAGE_EXT: return launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT>(a, ntiles, s);
-    case PSS_COVERAGE_EXT_STRAND: return launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT_STRAND>(a, ntiles, s);
-    case PSS_VARIATION: return launch_tile_one<KIND_VAR, PSS_VARIATION>(a, ntiles, s);
-    case PSS_VARIATION_STRAND: return launch_tile_one<KIND_VAR, PSS_VARIATION_STRAND>(a, ntiles, s);
-    default: return cudaErrorInvalidValue;
+    case PSS_COVERAGE: e = launch_tile_one<KIND_COV, PSS_COVERAGE>(a, ntiles, s); break;
+    case PSS_COVERAGE_STRAND: e = launch_tile_one<KIND_COV, PSS_COVERAGE_STRAND>(a, ntiles, s); break;
+    case PSS_COVERAGE_GC: e = launch_tile_one<KIND_COV, PSS_COVERAGE_GC>(a, ntiles, s); break;
+    case PSS_COVERAGE_EXT: e = launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT>(a, ntiles, s); break;
+    case PSS_COVERAGE_EXT_STRAND: e = launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT_STRAND>(a, ntiles, s); break;
+    case PSS_VARIATION: e = launch_tile_one<KIND_VAR, PSS_VARIATION>(a, ntiles, s); break;
+    case PSS_VARIATION_STRAND: e = launch_tile_one<KIND_VAR, PSS_VARIATION_STRAND>(a, ntiles, s); break;
+    default: e = cudaErrorInvalidValue;
     }
+    if (e1) cudaEventRecord(e1, s);
+    return e;
 }
