@@ -33,8 +33,8 @@
 #define NWARPS (TTHREADS / 32)
 #define NQUAD (TT / 4)        // finalisation: quads of positions
 #define NPARTS (TTHREADS / NQUAD)
-#define TCH 192               // reads staged per chunk
-#define TSEQ_BYTES 15360      // staged sequence bytes per chunk (192 x 75 B + slack)
+#define TCH 224               // reads staged per chunk
+#define TSEQ_BYTES 17408      // staged sequence bytes per chunk (224 x 75 B + slack)
 #define REFN_WORDS (TT / 8)
 
 enum { KIND_COV = 0, KIND_EXT = 1, KIND_VAR = 2 };
@@ -164,11 +164,12 @@ struct VarCursor {        // per-thread walk state
     int rn;               // tile-relative reference index of the next base of the current span
     int rem;              // bases left in the current span (inside the tile)
     uint32_t sn;          // nibble index of the next base in the staged sequence stream
+    int w0, wstep;        // this thread owns the 8-base words w0/8, w0/8 + wstep/8, ... of every span
 };
 
 // Advance to the next aligned span that overlaps the tile, applying the side effects of the
 // ops passed on the way (intervals of D spans, insertion points, the span's match interval).
-__device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, int bank, uint32_t sn0) {
+__device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, int bank, uint32_t sn0, bool fx) {
     while (c.k < c.nc && c.x < T.t1) {
         const uint32_t w = __ldg(c.cg + c.k);
         const int op = w & 15, l = (int)(w >> 4);
@@ -179,12 +180,14 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
             if (x + l > T.t0) {
                 const int a = max(x - T.t0, 0), b = min(x + l - T.t0, TT);
                 uint32_t *mt = T.cnt + (4 + bank) * TT;
-                atomicAdd(mt + a, 1u);
-                if (b < TT) atomicAdd(mt + b, 0xffffffffu);
-                if (T.no_del) interval_add(T.cnt + bank * TT, x, l, T.t0);   // D / N spans do not count
+                if (fx) {
+                    atomicAdd(mt + a, 1u);
+                    if (b < TT) atomicAdd(mt + b, 0xffffffffu);
+                    if (T.no_del) interval_add(T.cnt + bank * TT, x, l, T.t0);   // D / N spans do not count
+                }
                 // htslib indel > 0 at the last base of the op (A.1), opt.pyx:501
                 const int li = x + l - 1 - T.t0;
-                if (k + 1 < c.nc && li >= 0 && li < TT) {
+                if (fx && k + 1 < c.nc && li >= 0 && li < TT) {
                     const uint32_t w2 = __ldg(c.cg + k + 1);
                     const int op2 = w2 & 15;
                     bool ins = false;
@@ -201,44 +204,50 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
                     }
                     if (ins) atomicAdd(T.cnt + (12 + bank) * TT + li, 1u);
                 }
-                c.rn = a; c.rem = b - a;
-                c.sn = sn0 + (uint32_t)(y + (a + T.t0 - x));
-                return true;
+                c.rn = a + c.w0; c.rem = b - a - c.w0;
+                c.sn = sn0 + (uint32_t)(y + (a + T.t0 - x) + c.w0);
+                if (c.rem > 0) return true;
+                continue;                      // this part owns no word of the span
             }
         } else if (op == OP_D || op == OP_N) {
-            if (op == OP_D && !T.no_del && c.x + l > T.t0) interval_add(T.cnt + (8 + bank) * TT, c.x, l, T.t0);
+            if (fx && op == OP_D && !T.no_del && c.x + l > T.t0) interval_add(T.cnt + (8 + bank) * TT, c.x, l, T.t0);
             c.x += l;
         } else if (op == OP_I || op == OP_S) c.y += l;
     }
     return false;
 }
 
-__device__ __forceinline__ void var_read(const TileCtx &T, const TileArgs &A, const RInfo &r, uint32_t sn0, uint32_t *raw) {
+// `part` of `nparts` threads share a read: part k compares the 8-base words k, k + nparts, ... of
+// every aligned span; part 0 also applies the interval / point side effects.
+__device__ __forceinline__ void var_read(const TileCtx &T, const TileArgs &A, const RInfo &r, uint32_t sn0, uint32_t *raw,
+                                         int part, int nparts) {
     const uint32_t cls = r.cls;
     if (!(cls & CLS_ADMITTED)) return;
-    if (raw) interval_add(raw, r.pos, r.end - r.pos, T.t0);
+    const bool fx = part == 0;
+    if (raw && fx) interval_add(raw, r.pos, r.end - r.pos, T.t0);
     if (!(cls & CLS_COUNTED)) return;
     const int bank = cls & 3u;
-    if (!T.no_del) interval_add(T.cnt + bank * TT, r.pos, r.end - r.pos, T.t0);   // M, D and N all count
+    if (!T.no_del && fx) interval_add(T.cnt + bank * TT, r.pos, r.end - r.pos, T.t0);   // M, D and N all count
     if (cls & CLS_NOREF) {   // mapped, CIGAR consumes no reference: one deletion event at pos
-        if (!T.no_del) interval_add(T.cnt + (8 + bank) * TT, r.pos, 1, T.t0);
+        if (!T.no_del && fx) interval_add(T.cnt + (8 + bank) * TT, r.pos, 1, T.t0);
         return;
     }
     VarCursor c;
     c.cg = A.cigar + r.cigar_off; c.nc = (int)r.n_cigar; c.k = 0; c.x = r.pos; c.y = 0;
+    c.w0 = part << 3; c.wstep = nparts << 3;
     const bool simple = cls & CLS_SIMPLE;
     bool have;
     if (simple) {
         const int a = max(r.pos - T.t0, 0), b = min(r.end - T.t0, TT);
-        have = a < b;
-        if (have) {
+        if (a < b && fx) {
             uint32_t *mt = T.cnt + (4 + bank) * TT;
             atomicAdd(mt + a, 1u);
             if (b < TT) atomicAdd(mt + b, 0xffffffffu);
             if (T.no_del) interval_add(T.cnt + bank * TT, r.pos, r.end - r.pos, T.t0);
-            c.rn = a; c.rem = b - a; c.sn = sn0 + (uint32_t)(a + T.t0 - r.pos);
         }
-    } else have = var_next_span(T, c, bank, sn0);
+        c.rn = a + c.w0; c.rem = b - a - c.w0; c.sn = sn0 + (uint32_t)(a + T.t0 - r.pos + c.w0);
+        have = c.rem > 0;
+    } else have = var_next_span(T, c, bank, sn0, fx);
     const bool hasseq = cls & CLS_HASSEQ;
     while (have) {
         const int n8 = min(c.rem, 8);
@@ -265,8 +274,8 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const TileArgs &A, co
                 xr &= ~(0xfu << sh);
             }
         }
-        c.rn += 8; c.sn += 8; c.rem -= 8;
-        if (c.rem <= 0) have = simple ? false : var_next_span(T, c, bank, sn0);
+        c.rn += c.wstep; c.sn += c.wstep; c.rem -= c.wstep;
+        if (c.rem <= 0) have = simple ? false : var_next_span(T, c, bank, sn0, fx);
     }
 }
 
@@ -536,11 +545,15 @@ k_tile(TileArgs A) {
         parity ^= 1;
         const int n = s_n;
         if (n == 0) break;
-        if (tid < n) {
-            const RInfo r = s_ri[tid];
-            if (KIND == KIND_VAR) var_read(T, A, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp);
-            else cover_read<KIND>(T, A, r, rawp);
-        }
+        if (KIND == KIND_VAR) {
+            // up to four threads share a read: threads [k n, (k + 1) n) are part k of reads 0 .. n-1
+            const int nparts = min(4, TTHREADS / n);
+            const int part = tid / n;
+            if (part < nparts) {
+                const RInfo r = s_ri[tid - part * n];
+                var_read(T, A, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
+            }
+        } else if (tid < n) cover_read<KIND>(T, A, s_ri[tid], rawp);
         cb += n;
         if (cb >= d.y) break;
         __syncthreads();                       // staging buffers free again

@@ -30,9 +30,15 @@ for cub in glob.glob(tmp + '/*.cubin'):
         break
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr = rows[1]
+# the page holds one section per profiled launch: "Kernel Name" row, header row, SASS rows
+secs = [k for k, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+want = int(os.environ.get('NCU_LAUNCH', '0'))
+lo = secs[want]
+hi = secs[want + 1] if want + 1 < len(secs) else len(rows)
+print('launch %d of %d: %s' % (want, len(secs), rows[lo][1]))
+hdr = rows[lo + 1]
 si, ii = hdr.index('# Samples'), hdr.index('Instructions Executed')
-body = rows[2:]
+body = [r for r in rows[lo + 2:hi] if len(r) > max(si, ii)]
 print('sass in report %d, in cubin %d' % (len(body), len(lines)))
 agg = {}
 tot = toti = 0
