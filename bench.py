@@ -14,8 +14,9 @@ collective; torch.distributed only provides the barrier and the max-over-ranks r
 
 Numbers on the JSON line:
   value     genome positions / s, whole job, read batch resident in HBM, results left in HBM
-            (C ABI pss_pileup, CUDA events on the launch stream, max over ranks)
-  e2e       same metric through pss_pileup_host: pinned HOST read arrays in, HOST result
+            (C ABI pss_prepare + pss_pileup_prepared per statistic, CUDA events on the launch
+            stream, max over ranks)
+  e2e       same metric through pss_pileup_host_multi: pinned HOST read arrays in, HOST result
             columns out, every copy inside the timed region (wall clock around the calls)
   roofline  dominant kernel (k_pileup<variation_strand>): algorithmic bytes / its mean device
             time (events recorded by the library around the kernel, see pss_pileup_kernel_ms)
@@ -215,8 +216,10 @@ def main():
                                    contig_len=genome) for s in STATS}
 
     def step():
+        # one preparation of the batch (stepper, depth cap, read filters), then both statistics
+        ctx.prepare(reads, stepper='all', max_depth=8000, stream=sptr)
         for s in STATS:
-            ctx.pileup(reads, params[s], outs[s], masks[s], stream=sptr)
+            ctx.pileup_prepared(params[s], outs[s], masks[s], stream=sptr)
 
     # ---- device-resident throughput -----------------------------------------------------
     for _ in range(args.warmup):
@@ -287,28 +290,34 @@ def main():
         mh = {s: torch.empty(chunk, dtype=torch.uint8).pin_memory().numpy() for s in STATS}
         checks = {}
 
-        def e2e_step():
+        def e2e_step(check=False):
             for c_lo in range(lo, hi, chunk):
                 c_hi = min(hi, c_lo + chunk)
-                i0, i1, _ = shard.halo_range(hb['pos'], endpos, c_lo, c_hi, maxspan=maxspan)
+                i0, i1, _ = shard.halo_range(hb['pos'], endpos, c_lo, c_hi, maxspan=maxspan, mask=False)
                 view = dict(n_reads=i1 - i0, tid=0)
                 for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off'):
                     view[k] = hb[k][i0:]
                 view['cigar'], view['seq4'] = hb['cigar'], hb['seq4']
                 rs = _cabi.make_reads_struct(view, n_reads=i1 - i0)
+                n = c_hi - c_lo
+                r0 = c_lo - ref_lo
+                ps, os_, ms = [], [], []
                 for s in STATS:
                     withref = s == 'variation_strand'
-                    r0 = c_lo - ref_lo
-                    p = ctx.pileup_params(s, start=c_lo, end=c_hi, ref=ref_h[r0:] if withref else None,
-                                          ref_start=c_lo, ref_len=(c_hi - c_lo) if withref else 0, contig_len=genome)
-                    n = c_hi - c_lo
-                    o = oh[s] if n == chunk else np.ndarray((nf[s], n), dtype=np.int32, buffer=oh[s])
-                    ctx.pileup_host(rs, p, o, mh[s])
-                    checks[s] = checks.get(s, 0) + int(o[0].sum(dtype=np.int64))
+                    ps.append(ctx.pileup_params(s, start=c_lo, end=c_hi, ref=ref_h[r0:] if withref else None,
+                                                ref_start=c_lo, ref_len=(c_hi - c_lo) if withref else 0,
+                                                contig_len=genome))
+                    os_.append(oh[s] if n == chunk else np.ndarray((nf[s], n), dtype=np.int32, buffer=oh[s]))
+                    ms.append(mh[s])
+                # one call per position chunk: the reads go up once, both statistics come back
+                ctx.pileup_host_multi(rs, ps, os_, ms)
+                if check:
+                    for s, o in zip(STATS, os_):
+                        checks[s] = checks.get(s, 0) + int(o[0].sum(dtype=np.int64))
 
         for _ in range(max(1, min(args.warmup, 2))):
             checks.clear()
-            e2e_step()
+            e2e_step(check=True)
         assert checks == chk, ('host path disagrees with the device path', checks, chk)
         h0, d0 = ctx.transfer_bytes()
         barrier()
@@ -323,8 +332,8 @@ def main():
         e2e = {'value': total_pos / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
                'h2d_bytes_per_step': int(sum_over_ranks((h1 - h0) / args.steps)),
                'd2h_bytes_per_step': int(sum_over_ranks((d1 - d0) / args.steps)),
-               'api': 'pss_pileup_host (pinned host read arrays in, host int32 columns out), %d position chunks of '
-                      '%d per step and statistic' % (-(-npos // chunk), chunk)}
+               'api': 'pss_pileup_host_multi (pinned host read arrays in, host int32 columns of both statistics out), '
+                      '%d position chunks of %d per step' % (-(-npos // chunk), chunk)}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------

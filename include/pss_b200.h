@@ -209,12 +209,38 @@ int pss_pileup(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *pa
                int32_t *out, uint8_t *rowmask, void *stream);
 
 /*
+ * pss_pileup() in two halves, for callers that want several statistics of one batch.
+ * pss_prepare() does everything that depends on the batch and on the read-level arguments
+ * only (stepper flag filter, max_depth admission rule -- call site opt.pyx:1853-1854 --, the
+ * read filters min_mapq / no_dup of opt.pyx:1897-1909 and, if with_qual, the mate-overlap
+ * quality rewrite); pss_pileup_prepared() then computes one statistic over one position
+ * range from the prepared batch.  Its params must carry the same stepper / max_depth /
+ * min_mapq / no_dup.  The arrays of `reads` must stay valid and unchanged until the last
+ * pss_pileup_prepared() call has completed; any other entry point of this context
+ * discards the prepared batch.  DEVICE pointers.
+ */
+int pss_prepare(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth, int32_t min_mapq,
+                int32_t no_dup, int32_t with_qual, void *stream);
+int pss_pileup_prepared(pss_ctx *ctx, const pss_pileup_params *params, int32_t *out, uint8_t *rowmask,
+                        void *stream);
+
+/*
  * Same contract with HOST pointers everywhere: copies the batch to the device, runs
  * pss_pileup over position chunks and copies results back (synchronous).  This is the
  * call timed as `e2e` in bench.py.
  */
 int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *params,
                     int32_t *out, uint8_t *rowmask);
+
+/*
+ * Several statistics of one batch and one position range in one call: the batch is copied
+ * to the device and prepared once.  params[i] / outs[i] / rowmasks[i] describe statistic i;
+ * all params must share stepper, max_depth, min_mapq, no_dup, start, end and the reference
+ * span.  HOST pointers (synchronous).
+ */
+int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats,
+                          const pss_pileup_params *params, int32_t *const *outs,
+                          uint8_t *const *rowmasks);
 
 /*
  * The depth-cap admission rule of bam_plp_push (max_depth, call site opt.pyx:1853-1854)

@@ -67,7 +67,11 @@ SYMBOLS = {
     'pss_pileup_needs_qual': (C.c_int32, [C.c_int32, C.c_int32]),
     'pss_binned_nbins': (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
     'pss_pileup': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssPileupParams), _P, _P, _P]),
+    'pss_prepare': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    'pss_pileup_prepared': (C.c_int, [_P, C.POINTER(PssPileupParams), _P, _P, _P]),
     'pss_pileup_host': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssPileupParams), _P, _P]),
+    'pss_pileup_host_multi': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.POINTER(PssPileupParams),
+                                        C.POINTER(_P), C.POINTER(_P)]),
     'pss_admit': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P]),
     'pss_overlap_tweak': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P, _P]),
     'pss_binned': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssBinnedParams), _P, _P]),
@@ -203,9 +207,28 @@ class Context(object):
         self.check(self.lib.pss_pileup_host(self.h, C.byref(reads_struct), C.byref(params), _addr(out),
                                             _addr(rowmask)))
 
+    def pileup_host_multi(self, reads_struct, params_list, outs, rowmasks):
+        n = len(params_list)
+        pa = (PssPileupParams * n)(*params_list)
+        oa = (_P * n)(*[_addr(o) for o in outs])
+        ma = (_P * n)(*[_addr(m) for m in rowmasks])
+        self.check(self.lib.pss_pileup_host_multi(self.h, C.byref(reads_struct), n, pa, oa, ma))
+
     def pileup(self, reads_struct, params, out, rowmask, stream=None):
         self.check(self.lib.pss_pileup(self.h, C.byref(reads_struct), C.byref(params), _addr(out),
                                        _addr(rowmask), stream))
+
+    def prepare(self, reads_struct, stepper='all', max_depth=8000, min_mapq=0, no_dup=False, with_qual=False,
+                stream=None):
+        if isinstance(stepper, str):
+            if stepper not in STEPPERS:
+                raise ValueError('unknown stepper: %r' % stepper)
+            stepper = STEPPERS[stepper]
+        self.check(self.lib.pss_prepare(self.h, C.byref(reads_struct), int(stepper), int(max_depth or 0), int(min_mapq),
+                                        int(bool(no_dup)), int(bool(with_qual)), stream))
+
+    def pileup_prepared(self, params, out, rowmask, stream=None):
+        self.check(self.lib.pss_pileup_prepared(self.h, C.byref(params), _addr(out), _addr(rowmask), stream))
 
     def binned_params(self, stat, start, end, window_size, min_mapq=0, no_dup=False, ref=None, ref_start=0,
                       ref_len=0):

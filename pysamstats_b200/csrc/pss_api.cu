@@ -2,8 +2,10 @@
 // kernel sequencing and the host-buffer (streaming) entry points.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <vector>
 
 #include "pss_internal.cuh"
@@ -20,6 +22,10 @@ struct pss_ctx {
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // moved by the *_host entry points
     DevBuf ri, rng, qual, pair, next, small, tdesc, refpack;
     int64_t qual_bias = 0;  // ctx->qual holds bytes [qual_bias, qual_bias + n) of the batch's qual array
+    // batch prepared by pss_prepare()
+    bool prepared = false;
+    pss_reads prep_reads;
+    int prep_stepper = 0, prep_max_depth = 0, prep_min_mapq = 0, prep_no_dup = 0, prep_qual = 0;
     DevBuf hb[20];          // device copies of host batches (*_host entry points)
     DevBuf outbuf[2], maskbuf[2];
     SmallState *small_host = nullptr;   // pinned mirror of the device scalars
@@ -309,20 +315,50 @@ static int check_params(pss_ctx *ctx, const pss_pileup_params *P) {
     return PSS_OK;
 }
 
+extern "C" int pss_prepare(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth, int32_t min_mapq,
+                           int32_t no_dup, int32_t with_qual, void *stream) {
+    if (!ctx) return PSS_EINVAL;
+    ctx->prepared = false;
+    int rc;
+    if (stepper < 0 || stepper > 2) return fail(ctx, PSS_EINVAL, "unknown stepper: %d", stepper);
+    if (max_depth < 0) return fail(ctx, PSS_EINVAL, "max_depth < 0");
+    if ((rc = check_reads(ctx, reads, with_qual != 0)) != PSS_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = prepare_batch(ctx, reads, stepper, max_depth, min_mapq, no_dup, with_qual != 0, nullptr, nullptr, s)) != PSS_OK)
+        return rc;
+    ctx->prep_reads = *reads;
+    ctx->prep_stepper = stepper; ctx->prep_max_depth = max_depth; ctx->prep_min_mapq = min_mapq;
+    ctx->prep_no_dup = no_dup ? 1 : 0; ctx->prep_qual = with_qual ? 1 : 0;
+    ctx->prepared = true;
+    return PSS_OK;
+}
+
+extern "C" int pss_pileup_prepared(pss_ctx *ctx, const pss_pileup_params *P, int32_t *out, uint8_t *rowmask, void *stream) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    if ((rc = check_params(ctx, P)) != PSS_OK) return rc;
+    if (!ctx->prepared) return fail(ctx, PSS_EINVAL, "no prepared batch: call pss_prepare first");
+    if (P->stepper != ctx->prep_stepper || P->max_depth != ctx->prep_max_depth || P->min_mapq != ctx->prep_min_mapq ||
+        (P->no_dup ? 1 : 0) != ctx->prep_no_dup)
+        return fail(ctx, PSS_EINVAL, "stepper / max_depth / min_mapq / no_dup differ from the prepared batch");
+    bool need_qual = pss_pileup_needs_qual(P->stat, P->min_baseq);
+    if (need_qual && !ctx->prep_qual) return fail(ctx, PSS_EINVAL, "the batch was prepared without base qualities");
+    if (P->end > P->start && (!out || !rowmask)) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
+    CU(cudaSetDevice(ctx->device));
+    return run_range(ctx, &ctx->prep_reads, P, need_qual, P->start, P->end, out, P->end - P->start, rowmask,
+                     (cudaStream_t)stream);
+}
+
 extern "C" int pss_pileup(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *P, int32_t *out,
                           uint8_t *rowmask, void *stream) {
     if (!ctx) return PSS_EINVAL;
     int rc;
     if ((rc = check_params(ctx, P)) != PSS_OK) return rc;
     bool need_qual = pss_pileup_needs_qual(P->stat, P->min_baseq);
-    if ((rc = check_reads(ctx, reads, need_qual)) != PSS_OK) return rc;
-    if (P->end > P->start && (!out || !rowmask)) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
-    cudaStream_t s = (cudaStream_t)stream;
-    CU(cudaSetDevice(ctx->device));
-    if ((rc = prepare_batch(ctx, reads, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, nullptr, nullptr,
-                            s)) != PSS_OK)
+    if ((rc = pss_prepare(ctx, reads, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, stream)) != PSS_OK)
         return rc;
-    return run_range(ctx, reads, P, need_qual, P->start, P->end, out, P->end - P->start, rowmask, s);
+    return pss_pileup_prepared(ctx, P, out, rowmask, stream);
 }
 
 extern "C" int pss_admit(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth, uint8_t *admitted,
@@ -334,6 +370,7 @@ extern "C" int pss_admit(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, 
     if (reads->n_reads > 0 && !admitted) return fail(ctx, PSS_EINVAL, "admitted is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaSetDevice(ctx->device));
+    ctx->prepared = false;
     if ((rc = prepare_batch(ctx, reads, stepper, max_depth, 0, 0, false, nullptr, nullptr, s)) != PSS_OK) return rc;
     CU(launch_export_admitted((const RInfo *)ctx->ri.p, reads->n_reads, admitted, s, &ctx->launches));
     return PSS_OK;
@@ -348,6 +385,7 @@ extern "C" int pss_overlap_tweak(pss_ctx *ctx, const pss_reads *reads, int32_t s
     if (reads->n_reads > 0 && !qual_out) return fail(ctx, PSS_EINVAL, "qual_out is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaSetDevice(ctx->device));
+    ctx->prepared = false;
     return prepare_batch(ctx, reads, stepper, max_depth, 0, 0, true, qual_out, pair_first, s);
 }
 
@@ -412,56 +450,93 @@ static bool stat_reads_seq(int stat) {
     return stat == PSS_VARIATION || stat == PSS_VARIATION_STRAND || stat == PSS_BASEQ_EXT || stat == PSS_BASEQ_EXT_STRAND;
 }
 
+extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_pileup_params *P,
+                                     int32_t *const *outs, uint8_t *const *rowmasks) {
+    if (!ctx) return PSS_EINVAL;
+    if (n_stats < 1 || !P || !outs || !rowmasks) return fail(ctx, PSS_EINVAL, "n_stats < 1 or a NULL array");
+    int rc;
+    bool need_qual = false, need_seq = false;
+    for (int i = 0; i < n_stats; ++i) {
+        if ((rc = check_params(ctx, &P[i])) != PSS_OK) return rc;
+        if (P[i].stepper != P[0].stepper || P[i].max_depth != P[0].max_depth || P[i].min_mapq != P[0].min_mapq ||
+            (P[i].no_dup != 0) != (P[0].no_dup != 0) || P[i].start != P[0].start || P[i].end != P[0].end)
+            return fail(ctx, PSS_EINVAL, "statistics of one call must share stepper, max_depth, min_mapq, no_dup, start, end");
+        if (P[i].ref && P[0].ref && (P[i].ref != P[0].ref || P[i].ref_start != P[0].ref_start || P[i].ref_len != P[0].ref_len))
+            return fail(ctx, PSS_EINVAL, "statistics of one call must share the reference span");
+        bool q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
+        need_qual |= q;
+        need_seq |= q || stat_reads_seq(P[i].stat);   // the overlap tweak compares the mates' bases
+        if (P[i].end > P[i].start && (!outs[i] || !rowmasks[i])) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
+    }
+    if ((rc = check_reads(ctx, reads, need_qual)) != PSS_OK) return rc;
+    const int64_t npos = P[0].end - P[0].start;
+    CU(cudaSetDevice(ctx->device));
+    ctx->prepared = false;
+    cudaStream_t s = nullptr;   // default stream for compute, ctx->copy_stream for D2H
+    static const bool trace = getenv("PSS_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_begin = trace ? now() : 0, t_up = 0, t_enq = 0;
+    pss_reads D;
+    if ((rc = upload_reads(ctx, reads, &D, need_seq, need_qual, s)) != PSS_OK) return rc;
+    if (trace) { cudaStreamSynchronize(s); t_up = now(); }
+    const uint8_t *ref_host = nullptr, *ref_dev = nullptr;
+    for (int i = 0; i < n_stats && !ref_host; ++i)
+        if (P[i].ref && P[i].ref_len > 0) {
+            ref_host = P[i].ref;
+            if ((rc = to_device(ctx, ctx->hb[13], P[i].ref, (size_t)P[i].ref_len, &ref_dev, s)) != PSS_OK) return rc;
+        }
+    if ((rc = prepare_batch(ctx, &D, P[0].stepper, P[0].max_depth, P[0].min_mapq, P[0].no_dup, need_qual, nullptr, nullptr,
+                            s, (need_qual && reads->n_reads > 0) ? reads->qual_off[0] : 0)) != PSS_OK)
+        return rc;
+    int k = 0;     // running buffer slot: two device buffers alternate against the D2H copies
+    for (int i = 0; i < n_stats; ++i) {
+        pss_pileup_params Pd = P[i];
+        Pd.ref = (P[i].ref && P[i].ref_len > 0) ? ref_dev : nullptr;
+        const bool q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
+        const int nf = kPileupFields[P[i].stat];
+        // position chunks: <= ~256 MB of output each
+        int64_t chunk = ((int64_t)(256ll << 20) / (4ll * nf)) / PSS_TTILE * PSS_TTILE;
+        if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
+        if (chunk < PSS_TTILE) chunk = PSS_TTILE;
+        for (int64_t cs = Pd.start; cs < Pd.end; cs += chunk, ++k) {
+            int64_t ce = cs + chunk < Pd.end ? cs + chunk : Pd.end;
+            int64_t cn = ce - cs;
+            int b = k & 1;
+            const int64_t stride = (chunk + 3) & ~(int64_t)3;   // padded rows: 128-bit stores everywhere
+            if (k >= 2) CU(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));   // buffer free again
+            if (ctx->outbuf[b].bytes < sizeof(int32_t) * (size_t)nf * (size_t)stride || ctx->maskbuf[b].bytes < (size_t)stride) {
+                // growing a buffer frees it: wait for the copy that may still read it
+                CU(cudaStreamSynchronize(ctx->copy_stream));
+                if ((rc = ensure(ctx, ctx->outbuf[b], sizeof(int32_t) * (size_t)nf * (size_t)stride)) != PSS_OK) return rc;
+                if ((rc = ensure(ctx, ctx->maskbuf[b], (size_t)stride)) != PSS_OK) return rc;
+            }
+            if ((rc = run_range(ctx, &D, &Pd, q, cs, ce, (int32_t *)ctx->outbuf[b].p, stride, (uint8_t *)ctx->maskbuf[b].p,
+                                s)) != PSS_OK)
+                return rc;
+            CU(cudaEventRecord(ctx->ev_done[b], s));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+            CU(cudaMemcpy2DAsync(outs[i] + (cs - Pd.start), sizeof(int32_t) * (size_t)npos, ctx->outbuf[b].p,
+                                 sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)cn, (size_t)nf,
+                                 cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CU(cudaMemcpyAsync(rowmasks[i] + (cs - Pd.start), ctx->maskbuf[b].p, (size_t)cn, cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+            CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+            ctx->d2h_bytes += (int64_t)(sizeof(int32_t) * (size_t)cn * (size_t)nf + (size_t)cn);
+        }
+    }
+    if (trace) t_enq = now();
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    if (trace)
+        fprintf(stderr, "[pss] host_multi: upload %.1f ms, enqueue %.1f ms, drain %.1f ms (%d buffers)\n",
+                (t_up - t_begin) * 1e3, (t_enq - t_up) * 1e3, (now() - t_enq) * 1e3, k);
+    return pss_synchronize(ctx, s);
+}
+
 extern "C" int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *P, int32_t *out,
                                uint8_t *rowmask) {
     if (!ctx) return PSS_EINVAL;
-    int rc;
-    if ((rc = check_params(ctx, P)) != PSS_OK) return rc;
-    bool need_qual = pss_pileup_needs_qual(P->stat, P->min_baseq);
-    if ((rc = check_reads(ctx, reads, need_qual)) != PSS_OK) return rc;
-    int64_t npos = P->end - P->start;
-    if (npos > 0 && (!out || !rowmask)) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t s = nullptr;   // default stream for compute, ctx->copy_stream for D2H
-    pss_reads D;
-    // the overlap tweak compares the mates' bases, so qualities imply sequence
-    if ((rc = upload_reads(ctx, reads, &D, stat_reads_seq(P->stat) || need_qual, need_qual, s)) != PSS_OK) return rc;
-    pss_pileup_params Pd = *P;
-    if (P->ref && P->ref_len > 0) {
-        if ((rc = to_device(ctx, ctx->hb[13], P->ref, (size_t)P->ref_len, &Pd.ref, s)) != PSS_OK) return rc;
-    } else Pd.ref = nullptr;
-    if ((rc = prepare_batch(ctx, &D, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, nullptr, nullptr, s,
-                            (need_qual && reads->n_reads > 0) ? reads->qual_off[0] : 0)) != PSS_OK)
-        return rc;
-    const int nf = kPileupFields[P->stat];
-    // position chunks: <= ~256 MB of output each, double buffered against the D2H copies
-    int64_t chunk = ((int64_t)(256ll << 20) / (4ll * nf)) / PSS_TILE * PSS_TILE;
-    if (chunk > npos) chunk = (npos + PSS_TILE - 1) / PSS_TILE * PSS_TILE;
-    if (chunk < PSS_TILE) chunk = PSS_TILE;
-    int k = 0;
-    for (int64_t cs = P->start; cs < P->end; cs += chunk, ++k) {
-        int64_t ce = cs + chunk < P->end ? cs + chunk : P->end;
-        int64_t cn = ce - cs;
-        int b = k & 1;
-        const int64_t stride = (chunk + 3) & ~(int64_t)3;   // padded rows: 128-bit stores everywhere
-        if ((rc = ensure(ctx, ctx->outbuf[b], sizeof(int32_t) * (size_t)nf * (size_t)stride)) != PSS_OK) return rc;
-        if ((rc = ensure(ctx, ctx->maskbuf[b], (size_t)stride)) != PSS_OK) return rc;
-        if (k >= 2) CU(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));   // buffer free again
-        if ((rc = run_range(ctx, &D, &Pd, need_qual, cs, ce, (int32_t *)ctx->outbuf[b].p, stride,
-                            (uint8_t *)ctx->maskbuf[b].p, s)) != PSS_OK)
-            return rc;
-        CU(cudaEventRecord(ctx->ev_done[b], s));
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
-        CU(cudaMemcpy2DAsync(out + (cs - P->start), sizeof(int32_t) * (size_t)npos, ctx->outbuf[b].p,
-                             sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)cn, (size_t)nf,
-                             cudaMemcpyDeviceToHost, ctx->copy_stream));
-        CU(cudaMemcpyAsync(rowmask + (cs - P->start), ctx->maskbuf[b].p, (size_t)cn, cudaMemcpyDeviceToHost,
-                           ctx->copy_stream));
-        CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-        ctx->d2h_bytes += (int64_t)(sizeof(int32_t) * (size_t)cn * (size_t)nf + (size_t)cn);
-    }
-    CU(cudaStreamSynchronize(ctx->copy_stream));
-    return pss_synchronize(ctx, s);
+    if (!P) return fail(ctx, PSS_EINVAL, "params is NULL");
+    return pss_pileup_host_multi(ctx, reads, 1, P, &out, &rowmask);
 }
 
 // ------------------------------------------------------------------------------ binned

@@ -136,8 +136,10 @@ k_prep(pss_reads R, int stepper, int min_mapq, int no_dup, RInfo *__restrict__ r
         span = end - pos;
         if (i > 0 && R.pos[i - 1] > pos) atomicOr(&st->unsorted, 1);
     }
+    // one atomic per warp at most, and only while the running maximum still grows (a
+    // same-address atomic per warp would serialise in L2)
     span = warp_max(span);
-    if ((threadIdx.x & 31) == 0 && span > 0) atomicMax(&st->maxspan, span);
+    if ((threadIdx.x & 31) == 0 && span > *(volatile int32_t *)&st->maxspan) atomicMax(&st->maxspan, span);
 }
 
 // -------------------------------------------------------------- depth cap (A.2)

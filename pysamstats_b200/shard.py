@@ -49,22 +49,34 @@ def plan_windows(start, end, window_size, n_shards):
     return [((n_bins * k) // n_shards, (n_bins * (k + 1)) // n_shards) for k in range(n_shards)]
 
 
-def halo_range(pos, endpos, lo, hi, maxspan=None):
+def _key(pos, v):
+    """Search key in the dtype of ``pos`` (a python int would make numpy convert the whole
+    array on every call)."""
+    info = np.iinfo(pos.dtype)
+    return pos.dtype.type(min(max(int(v), info.min), info.max))
+
+
+def halo_range(pos, endpos, lo, hi, maxspan=None, mask=True):
     """Index range [i0, i1) of a coordinate-sorted batch that contains every read overlapping
-    [lo, hi) (pos < hi and endpos > lo -- htslib's region rule), and the boolean mask of
-    the reads inside that range that really overlap.  The range is contiguous because reads
-    are start-sorted; reads inside it that end before lo are harmless to the kernels (they
-    cover no output position) but are reported so callers can count exactly.
+    [lo, hi) (pos < hi and endpos > lo -- htslib's region rule), and (``mask=True``) the
+    boolean mask of the reads inside that range that really overlap.  The range is contiguous
+    because reads are start-sorted; reads inside it that end before lo are harmless to the
+    kernels (they cover no output position) but are reported so callers can count exactly.
     ``maxspan`` (max over the batch of endpos - pos, if known) bounds the backward scan."""
     pos = np.asarray(pos)
     endpos = np.asarray(endpos)
-    i1 = int(np.searchsorted(pos, hi, side='left'))
-    s0 = 0 if maxspan is None else int(np.searchsorted(pos, lo - int(maxspan) + 1, side='left'))
+    i1 = int(np.searchsorted(pos, _key(pos, hi), side='left'))
+    s0 = 0 if maxspan is None else int(np.searchsorted(pos, _key(pos, lo - int(maxspan) + 1), side='left'))
     s0 = min(s0, i1)
-    ov = endpos[s0:i1] > lo
-    nz = np.flatnonzero(ov)
-    i0 = s0 + int(nz[0]) if len(nz) else i1
-    return i0, i1, ov[i0 - s0:]
+    # every read starting at or after lo overlaps; only the ones before it need a look
+    k0 = min(int(np.searchsorted(pos, _key(pos, lo), side='left')), i1)
+    nz = np.flatnonzero(endpos[s0:k0] > lo)
+    i0 = s0 + int(nz[0]) if len(nz) else k0
+    if not mask:
+        return i0, i1, None
+    ov = np.ones(i1 - i0, dtype=bool)
+    ov[:k0 - i0] = endpos[i0:k0] > lo
+    return i0, i1, ov
 
 
 def window_read_range(pos, start, window_size, k_lo, k_hi, n_bins):
@@ -72,8 +84,8 @@ def window_read_range(pos, start, window_size, k_lo, k_hi, n_bins):
     iter_binned_chrom (opt.pyx:2050: strict '>', so window k >= 1 owns start + k W < pos <=
     start + (k+1) W, window 0 everything up to start + W, the last window everything after)."""
     pos = np.asarray(pos)
-    i0 = 0 if k_lo == 0 else int(np.searchsorted(pos, start + k_lo * window_size, side='right'))
-    i1 = len(pos) if k_hi >= n_bins else int(np.searchsorted(pos, start + k_hi * window_size, side='right'))
+    i0 = 0 if k_lo == 0 else int(np.searchsorted(pos, _key(pos, start + k_lo * window_size), side='right'))
+    i1 = len(pos) if k_hi >= n_bins else int(np.searchsorted(pos, _key(pos, start + k_hi * window_size), side='right'))
     return i0, max(i0, i1)
 
 
@@ -81,7 +93,7 @@ def live_depth_at(pos, endpos, p):
     """Number of reads covering position p (pos <= p < endpos) of a sorted batch."""
     pos = np.asarray(pos)
     endpos = np.asarray(endpos)
-    i1 = int(np.searchsorted(pos, p, side='right'))
+    i1 = int(np.searchsorted(pos, _key(pos, p), side='right'))
     return int(np.count_nonzero(endpos[:i1] > p))
 
 
