@@ -18,7 +18,7 @@ Numbers on the JSON line:
             stream, max over ranks)
   e2e       same metric through pss_pileup_host_multi: pinned HOST read arrays in, HOST result
             columns out, every copy inside the timed region (wall clock around the calls)
-  roofline  dominant kernel (k_pileup<variation_strand>): algorithmic bytes / its mean device
+  roofline  dominant kernel (k_tile<VAR, variation_strand>): algorithmic bytes / its mean device
             time (events recorded by the library around the kernel, see pss_pileup_kernel_ms)
   cpu_baseline   the CPU restatement of the reference algorithm (oracle/, "port") on a bounded
             sample of the same workload, one process per contig chunk on all host cores
@@ -263,7 +263,7 @@ def main():
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     k_ms, k_n = kms['variation_strand']
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-    roofline = {'bound': 'hbm', 'kernel': 'k_pileup<AccVariation<PSS_VARIATION_STRAND>>', 'achieved': achieved,
+    roofline = {'bound': 'hbm', 'kernel': 'k_tile<KIND_VAR, PSS_VARIATION_STRAND>', 'achieved': achieved,
                 'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': None,
                 'peak_source': peak_src, 'kernel_ms': k_ms, 'kernel_launches_timed': k_n,
                 'algorithmic_bytes_per_launch': alg_bytes,

@@ -36,6 +36,7 @@
 #define TCH 224               // reads staged per chunk
 #define TSEQ_BYTES 17408      // staged sequence bytes per chunk (224 x 75 B + slack)
 #define REFN_WORDS (TT / 8)
+#define TCIG_WORDS 512        // staged CIGAR words per chunk (reads beyond it fall back to global loads)
 
 enum { KIND_COV = 0, KIND_EXT = 1, KIND_VAR = 2 };
 
@@ -52,6 +53,8 @@ struct __align__(16) TileDesc {
     uint32_t flags;      // bit 0: a reference position of the tile has no 4-bit code
     int64_t seq_lo;      // seq_off[x]
     int64_t seq_hi;      // seq_off[x + n0]
+    int64_t cig_lo;      // CIGAR word span of the first chunk, cig_hi == cig_lo: not staged
+    int64_t cig_hi;
 };
 
 struct TileArgs {
@@ -136,6 +139,19 @@ __device__ __forceinline__ void interval_add(uint32_t *arr, int x, int l, int t0
     }
 }
 
+// Bulk copies need 16-byte aligned addresses and sizes: widen the element span [lo, hi) of
+// `base` outward to 16-byte boundaries.  *first = element index that lands at offset 0 of
+// the shared buffer (may be fractional for 1-byte elements only in the sense of bytes).
+template <class Tp>
+__device__ __forceinline__ void stage_span(const Tp *base, long long lo, long long hi, int elem, const uint8_t **src,
+                                           uint32_t *bytes, long long *first) {
+    uintptr_t a0 = reinterpret_cast<uintptr_t>(base + lo), a1 = reinterpret_cast<uintptr_t>(base + hi);
+    uintptr_t al = a0 & ~(uintptr_t)15, ah = (a1 + 15) & ~(uintptr_t)15;
+    *src = reinterpret_cast<const uint8_t *>(al);
+    *bytes = (uint32_t)(ah - al);
+    *first = lo - (long long)((a0 - al) / (uintptr_t)elem);
+}
+
 // ---- variation: one read per thread, one 8-base word per loop iteration ---------------------
 //
 // Counter arrays (per bank b = rev | pp << 1):
@@ -158,7 +174,7 @@ __device__ __forceinline__ void var_mismatch(const TileCtx &T, int bank, int p, 
 }
 
 struct VarCursor {        // per-thread walk state
-    const uint32_t *cg;   // CIGAR words (global)
+    const uint32_t *cg;   // CIGAR words of the read (staged in shared memory, else global)
     int nc, k;            // number of ops, next op
     int x, y;             // reference / query cursor at op k
     int rn;               // tile-relative reference index of the next base of the current span
@@ -171,7 +187,7 @@ struct VarCursor {        // per-thread walk state
 // ops passed on the way (intervals of D spans, insertion points, the span's match interval).
 __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, int bank, uint32_t sn0, bool fx) {
     while (c.k < c.nc && c.x < T.t1) {
-        const uint32_t w = __ldg(c.cg + c.k);
+        const uint32_t w = c.cg[c.k];
         const int op = w & 15, l = (int)(w >> 4);
         const int k = c.k++;
         if (op_is_match(op)) {
@@ -188,14 +204,14 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
                 // htslib indel > 0 at the last base of the op (A.1), opt.pyx:501
                 const int li = x + l - 1 - T.t0;
                 if (fx && k + 1 < c.nc && li >= 0 && li < TT) {
-                    const uint32_t w2 = __ldg(c.cg + k + 1);
+                    const uint32_t w2 = c.cg[k + 1];
                     const int op2 = w2 & 15;
                     bool ins = false;
                     if (op2 == OP_I) ins = (w2 >> 4) > 0;
                     else if (op2 == OP_P && k + 2 < c.nc) {
                         long long l3 = 0;
                         for (int j = k + 2; j < c.nc; ++j) {
-                            const uint32_t w3 = __ldg(c.cg + j);
+                            const uint32_t w3 = c.cg[j];
                             const int op3 = w3 & 15;
                             if (op3 == OP_I) l3 += (w3 >> 4);
                             else if (op3 == OP_D || op3 == OP_M || op3 == OP_N || op3 == OP_EQ || op3 == OP_X) break;
@@ -219,7 +235,7 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
 
 // `part` of `nparts` threads share a read: part k compares the 8-base words k, k + nparts, ... of
 // every aligned span; part 0 also applies the interval / point side effects.
-__device__ __forceinline__ void var_read(const TileCtx &T, const TileArgs &A, const RInfo &r, uint32_t sn0, uint32_t *raw,
+__device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, const RInfo &r, uint32_t sn0, uint32_t *raw,
                                          int part, int nparts) {
     const uint32_t cls = r.cls;
     if (!(cls & CLS_ADMITTED)) return;
@@ -233,7 +249,7 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const TileArgs &A, co
         return;
     }
     VarCursor c;
-    c.cg = A.cigar + r.cigar_off; c.nc = (int)r.n_cigar; c.k = 0; c.x = r.pos; c.y = 0;
+    c.cg = cg; c.nc = (int)r.n_cigar; c.k = 0; c.x = r.pos; c.y = 0;
     c.w0 = part << 3; c.wstep = nparts << 3;
     const bool simple = cls & CLS_SIMPLE;
     bool have;
@@ -488,9 +504,11 @@ k_tile(TileArgs A) {
     // the rest exists for KIND_VAR only (see tile_smem_bytes)
     uint32_t *s_refn = reinterpret_cast<uint32_t *>(s_ri + TCH);       // REFN_WORDS + 4 words
     uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_refn + REFN_WORDS + 4);   // TSEQ_BYTES + 32
+    uint32_t *s_cig = reinterpret_cast<uint32_t *>(s_seq + TSEQ_BYTES + 32);  // TCIG_WORDS + 8
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_n;
     __shared__ long long s_seqlo;      // global byte index staged at s_seq[0]
+    __shared__ long long s_ciglo;      // global CIGAR word index staged at s_cig[0], -1: not staged
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -505,24 +523,25 @@ k_tile(TileArgs A) {
     }
     if (tid == 0) {
         mbar_init(&s_bar, 1);
-        uint32_t bytes = 0, sbytes = 0;
-        const uint8_t *src = nullptr;
+        uint32_t bytes = 0, sbytes = 0, cbytes = 0;
+        const uint8_t *src = nullptr, *csrc = nullptr;
         const int n = d.n0;
         if (KIND == KIND_VAR && n > 0) {
             uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile) + 1);
+            uint4 d2 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile) + 2);
             long long lo = (long long)(((uint64_t)d1.y << 32) | d1.x), hi = (long long)(((uint64_t)d1.w << 32) | d1.z);
-            uintptr_t a0 = reinterpret_cast<uintptr_t>(A.seq4 + lo), a1 = reinterpret_cast<uintptr_t>(A.seq4 + hi);
-            uintptr_t al = a0 & ~(uintptr_t)15, ah = (a1 + 15) & ~(uintptr_t)15;
-            src = reinterpret_cast<const uint8_t *>(al);
-            sbytes = (uint32_t)(ah - al);
-            s_seqlo = lo - (long long)(a0 - al);
+            stage_span(A.seq4, lo, hi, 1, &src, &sbytes, &s_seqlo);
+            long long clo = (long long)(((uint64_t)d2.y << 32) | d2.x), chi = (long long)(((uint64_t)d2.w << 32) | d2.z);
+            s_ciglo = -1;
+            if (chi > clo) stage_span(A.cigar, clo, chi, 4, &csrc, &cbytes, &s_ciglo);
         }
         s_n = n;
         if (n > 0) {
-            bytes = (uint32_t)n * (uint32_t)sizeof(RInfo) + sbytes + (KIND == KIND_VAR ? (REFN_WORDS + 4) * 4 : 0);
+            bytes = (uint32_t)n * (uint32_t)sizeof(RInfo) + sbytes + cbytes + (KIND == KIND_VAR ? (REFN_WORDS + 4) * 4 : 0);
             mbar_arrive_expect_tx(&s_bar, bytes);
             bulk_g2s(s_ri, A.ri + d.x, (uint32_t)n * (uint32_t)sizeof(RInfo), &s_bar);
             if (sbytes) bulk_g2s(s_seq, src, sbytes, &s_bar);
+            if (cbytes) bulk_g2s(s_cig, csrc, cbytes, &s_bar);
             if (KIND == KIND_VAR) bulk_g2s(s_refn, A.refpack + (size_t)tile * REFN_WORDS, (REFN_WORDS + 4) * 4, &s_bar);
         } else mbar_arrive_expect_tx(&s_bar, 0);
     }
@@ -551,7 +570,9 @@ k_tile(TileArgs A) {
             const int part = tid / n;
             if (part < nparts) {
                 const RInfo r = s_ri[tid - part * n];
-                var_read(T, A, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
+                const long long ciglo = s_ciglo;
+                const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
+                var_read(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
             }
         } else if (tid < n) cover_read<KIND>(T, A, s_ri[tid], rawp);
         cb += n;
@@ -559,26 +580,26 @@ k_tile(TileArgs A) {
         __syncthreads();                       // staging buffers free again
         if (tid == 0) {
             int m = min(TCH, d.y - cb);
-            uint32_t sbytes = 0;
-            const uint8_t *src = nullptr;
+            uint32_t sbytes = 0, cbytes = 0;
+            const uint8_t *src = nullptr, *csrc = nullptr;
             if (KIND == KIND_VAR) {
                 long long lo = A.seq_off[cb], hi = A.seq_off[cb + m];
                 while (m > 1 && hi - lo + 32 > TSEQ_BYTES) { m >>= 1; hi = A.seq_off[cb + m]; }
                 if (hi - lo + 32 > TSEQ_BYTES) { atomicOr(&A.st->toolong, 1); m = 0; }
                 else {
-                    uintptr_t a0 = reinterpret_cast<uintptr_t>(A.seq4 + lo), a1 = reinterpret_cast<uintptr_t>(A.seq4 + hi);
-                    uintptr_t al = a0 & ~(uintptr_t)15, ah = (a1 + 15) & ~(uintptr_t)15;
-                    src = reinterpret_cast<const uint8_t *>(al);
-                    sbytes = (uint32_t)(ah - al);
-                    s_seqlo = lo - (long long)(a0 - al);
+                    stage_span(A.seq4, lo, hi, 1, &src, &sbytes, &s_seqlo);
+                    long long clo = A.ri[cb].cigar_off, chi = A.ri[cb + m - 1].cigar_off + A.ri[cb + m - 1].n_cigar;
+                    s_ciglo = -1;
+                    if (chi > clo && chi - clo + 8 <= TCIG_WORDS) stage_span(A.cigar, clo, chi, 4, &csrc, &cbytes, &s_ciglo);
                 }
             }
             s_n = m;
             fence_proxy_async();
             if (m > 0) {
-                mbar_arrive_expect_tx(&s_bar, (uint32_t)m * (uint32_t)sizeof(RInfo) + sbytes);
+                mbar_arrive_expect_tx(&s_bar, (uint32_t)m * (uint32_t)sizeof(RInfo) + sbytes + cbytes);
                 bulk_g2s(s_ri, A.ri + cb, (uint32_t)m * (uint32_t)sizeof(RInfo), &s_bar);
                 if (sbytes) bulk_g2s(s_seq, src, sbytes, &s_bar);
+                if (cbytes) bulk_g2s(s_cig, csrc, cbytes, &s_bar);
             } else mbar_arrive_expect_tx(&s_bar, 0);
         }
     }
@@ -635,13 +656,17 @@ k_tile_desc(const RInfo *__restrict__ ri, const int64_t *__restrict__ seq_off, i
     while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((long long)ri[mid].pos < t1) lo = mid + 1; else hi = mid; }
     int64_t y = lo;
     TileDesc d;
-    d.x = (int32_t)x; d.y = (int32_t)y; d.flags = 0; d.seq_lo = 0; d.seq_hi = 0;
+    d.x = (int32_t)x; d.y = (int32_t)y; d.flags = 0; d.seq_lo = 0; d.seq_hi = 0; d.cig_lo = 0; d.cig_hi = 0;
     int m = (int)(y - x < TCH ? y - x : TCH);
     if (with_seq && m > 0) {
         long long slo = seq_off[x], shi = seq_off[x + m];
         while (m > 1 && shi - slo + 32 > TSEQ_BYTES) { m >>= 1; shi = seq_off[x + m]; }
         if (shi - slo + 32 > TSEQ_BYTES) { atomicOr(&st->toolong, 1); m = 0; }
         d.seq_lo = slo; d.seq_hi = shi;
+        if (m > 0) {
+            long long clo = ri[x].cigar_off, chi = ri[x + m - 1].cigar_off + ri[x + m - 1].n_cigar;
+            if (chi - clo + 8 <= TCIG_WORDS) { d.cig_lo = clo; d.cig_hi = chi; }
+        }
     }
     d.n0 = m;
     desc[t] = d;
@@ -672,7 +697,7 @@ template <int KIND>
 static size_t tile_smem_bytes() {
     size_t narr = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT + 1;   // + raw
     size_t b = narr * TT * 4 + sizeof(RInfo) * TCH;
-    if (KIND == KIND_VAR) b += (REFN_WORDS + 4) * 4 + TSEQ_BYTES + 32;
+    if (KIND == KIND_VAR) b += (REFN_WORDS + 4) * 4 + TSEQ_BYTES + 32 + (TCIG_WORDS + 8) * 4;
     return b;
 }
 
