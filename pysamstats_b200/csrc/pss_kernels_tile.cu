@@ -4,24 +4,28 @@
 //
 // Design (sm_100a):
 //   * one CTA owns a tile of TT genome positions; its per-position counters live in shared
-//     memory (counter-major, 4 bytes each) for the whole life of the tile;
+//     memory for the whole life of the tile.  A counter word holds TWO 16-bit counters of
+//     the same position (forward | reverse strand << 16), so variation_strand needs 20 word
+//     arrays (40 KB for 512 positions) and three CTAs fit on an SM;
 //   * the tile's candidate reads are a contiguous index range of the start-sorted batch;
-//     their 32-byte records, their packed 4-bit sequences and the tile of the 4-bit packed
-//     reference are staged into shared memory by bulk async copies (cp.async.bulk ->
+//     their 32-byte records, packed 4-bit sequences, CIGAR words and the tile of the 4-bit
+//     packed reference are staged into shared memory by bulk async copies (cp.async.bulk ->
 //     UBLKCP, completion on an mbarrier) issued before anything else happens, chunk by
 //     chunk for arbitrarily deep tiles;
 //   * reads are walked once.  Everything that is constant along an aligned span (read
-//     counts per strand / proper-pair / mate class, deletions, ref skips) is an interval
-//     add: +1 at the span start, -1 at its end in a difference array.  Bases are NOT visited
-//     one by one: a warp takes a read, each lane XORs eight of its 4-bit codes (one 32-bit
-//     word) against the reference tile packed the same way, and only the mismatching bases
-//     (<1 % of them) become point updates.  matches and the A/C/G/T/N counters follow
-//     exactly from  matches = aligned - mismatches  and the reference code of the position
-//     (SURVEY.md App. C);
+//     counts per strand / proper-pair / mate class, deletions) is an interval add: +1 at
+//     the span start, -1 at its end in a difference array.  Bases are NOT visited one by
+//     one: up to four threads share a read, each XORs eight 4-bit codes (one 32-bit word)
+//     against the reference tile packed the same way, and only the mismatching bases (<1 %)
+//     become point updates.  matches and the A/C/G/T/N counters follow exactly from
+//     matches = aligned - mismatches and the reference code of the position (App. C);
 //   * after the last chunk the difference arrays are prefix-summed in place (warp shuffle
-//     scan) and the tile is finalised: every field of these statistics is linear in the
+//     scan over the packed words: the halves cannot borrow from each other in the final
+//     sums) and the tile is finalised: every field of these statistics is linear in the
 //     counters; each thread produces four consecutive positions of a subset of the fields
-//     and writes them as 128-bit stores (512 contiguous bytes per warp and field).
+//     and writes them as 128-bit stores (512 contiguous bytes per warp and field);
+//   * 16-bit halves hold at most 65535: a tile is processed in passes of at most 65535
+//     reads, later passes ADD their (linear) results to the output, so any depth is exact.
 // Shared-memory atomics are few (a handful per read), so the kernel is bound by the output
 // stream to HBM.
 #include "pss_internal.cuh"
@@ -29,22 +33,32 @@
 #define FULL 0xffffffffu
 
 #define TT PSS_TTILE          // positions per tile
-#define TTHREADS 512
+#ifndef TTHREADS
+#define TTHREADS 384
+#endif
+#ifndef TCTAS
+#define TCTAS 3               // CTAs per SM the kernel is compiled for
+#endif
 #define NWARPS (TTHREADS / 32)
 #define NQUAD (TT / 4)        // finalisation: quads of positions
 #define NPARTS (TTHREADS / NQUAD)
-#define TCH 224               // reads staged per chunk
-#define TSEQ_BYTES 17408      // staged sequence bytes per chunk (224 x 75 B + slack)
+#ifndef TCH
+#define TCH 192               // reads staged per chunk
+#endif
+#define TSEQ_BYTES (TCH * 76 + 64)   // staged sequence bytes per chunk (150 bp reads fit a full chunk)
 #define REFN_WORDS (TT / 8)
-#define TCIG_WORDS 512        // staged CIGAR words per chunk (reads beyond it fall back to global loads)
+#define TCIG_WORDS 384        // staged CIGAR words per chunk (else the chunk's reads load them from global)
+#define PASS_READS 65535      // reads per pass: what a 16-bit counter can hold
 
 enum { KIND_COV = 0, KIND_EXT = 1, KIND_VAR = 2 };
 
+// Word arrays per kind (each word = two 16-bit counters, see the accessors below).
+// NDIFF difference arrays come first (they are prefix-summed), then NPOINT point arrays.
 template <int KIND> struct KindInfo;
-template <> struct KindInfo<KIND_COV> { static const int NDIFF = 4, NPOINT = 0; };    // all[bank]
-template <> struct KindInfo<KIND_EXT> { static const int NDIFF = 16, NPOINT = 0; };   // class k * 2 + strand
-// all[b], match[4 + b], del[8 + b] | ins[12 + b], mismatches[16 + b], mismatch class c in A,C,G,T,N: [20 + 4 c + b]
-template <> struct KindInfo<KIND_VAR> { static const int NDIFF = 12, NPOINT = 28; };
+template <> struct KindInfo<KIND_COV> { static const int NDIFF = 2, NPOINT = 0; };   // all[pp]: fwd | rev << 16
+template <> struct KindInfo<KIND_EXT> { static const int NDIFF = 8, NPOINT = 0; };   // class k: fwd | rev << 16
+// all[pp], match[2 + pp], del[4 + pp] | ins[6 + pp], mismatches[8 + pp], mismatch class c = A,C,G,T,N: [10 + 2 c + pp]
+template <> struct KindInfo<KIND_VAR> { static const int NDIFF = 6, NPOINT = 14; };
 
 // per-tile descriptor written by k_tile_desc (+ k_refpack for the flag)
 struct __align__(16) TileDesc {
@@ -131,11 +145,18 @@ struct TileCtx {
     bool slow;              // a reference position without a code: compare base by base
 };
 
-__device__ __forceinline__ void interval_add(uint32_t *arr, int x, int l, int t0) {
+// Counter words: bank = rev | pp << 1 lives in word array `group + (bank >> 1)`, forward strand
+// in the low half, reverse in the high half.  Adding 1 << 16 or subtracting it (mod 2^32) keeps
+// the word equal to hi * 65536 + lo as integers, so prefix sums of the words are the packed
+// prefix sums as long as every final half is in [0, 65535].
+enum { W_ALL = 0, W_MATCH = 2, W_DEL = 4, W_INS = 6, W_MMT = 8, W_MMC = 10 };
+__device__ __forceinline__ uint32_t half_inc(int rev) { return 1u << ((rev & 1) << 4); }
+
+__device__ __forceinline__ void interval_add(uint32_t *arr, int x, int l, int t0, uint32_t inc) {
     int a = max(x - t0, 0), b = min(x + l - t0, TT);
     if (a < b) {
-        atomicAdd(arr + a, 1u);
-        if (b < TT) atomicAdd(arr + b, 0xffffffffu);
+        atomicAdd(arr + a, inc);
+        if (b < TT) atomicAdd(arr + b, 0u - inc);
     }
 }
 
@@ -165,12 +186,14 @@ __device__ __forceinline__ void stage_span(const Tp *base, long long lo, long lo
 // A position's A count is mmc[A] + (reference is A ? matches : 0), etc..
 
 __device__ __forceinline__ void var_mismatch(const TileCtx &T, int bank, int p, int code) {
-    uint32_t *m = T.cnt + (4 + bank) * TT + p;
-    atomicAdd(m, 0xffffffffu);
-    if (p + 1 < TT) atomicAdd(m + 1, 1u);
-    atomicAdd(T.cnt + (16 + bank) * TT + p, 1u);
+    const int pp = bank >> 1;
+    const uint32_t inc = half_inc(bank);
+    uint32_t *m = T.cnt + (W_MATCH + pp) * TT + p;
+    atomicAdd(m, 0u - inc);
+    if (p + 1 < TT) atomicAdd(m + 1, inc);
+    atomicAdd(T.cnt + (W_MMT + pp) * TT + p, inc);
     const int c = mm_class(code);
-    if (c < 5) atomicAdd(T.cnt + (20 + 4 * c + bank) * TT + p, 1u);
+    if (c < 5) atomicAdd(T.cnt + (W_MMC + 2 * c + pp) * TT + p, inc);
 }
 
 struct VarCursor {        // per-thread walk state
@@ -195,11 +218,12 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
             c.x += l; c.y += l;
             if (x + l > T.t0) {
                 const int a = max(x - T.t0, 0), b = min(x + l - T.t0, TT);
-                uint32_t *mt = T.cnt + (4 + bank) * TT;
+                uint32_t *mt = T.cnt + (W_MATCH + (bank >> 1)) * TT;
+                const uint32_t inc = half_inc(bank);
                 if (fx) {
-                    atomicAdd(mt + a, 1u);
-                    if (b < TT) atomicAdd(mt + b, 0xffffffffu);
-                    if (T.no_del) interval_add(T.cnt + bank * TT, x, l, T.t0);   // D / N spans do not count
+                    atomicAdd(mt + a, inc);
+                    if (b < TT) atomicAdd(mt + b, 0u - inc);
+                    if (T.no_del) interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, x, l, T.t0, inc);   // D / N spans do not count
                 }
                 // htslib indel > 0 at the last base of the op (A.1), opt.pyx:501
                 const int li = x + l - 1 - T.t0;
@@ -218,7 +242,7 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
                         }
                         ins = l3 > 0;
                     }
-                    if (ins) atomicAdd(T.cnt + (12 + bank) * TT + li, 1u);
+                    if (ins) atomicAdd(T.cnt + (W_INS + (bank >> 1)) * TT + li, inc);
                 }
                 c.rn = a + c.w0; c.rem = b - a - c.w0;
                 c.sn = sn0 + (uint32_t)(y + (a + T.t0 - x) + c.w0);
@@ -226,7 +250,8 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
                 continue;                      // this part owns no word of the span
             }
         } else if (op == OP_D || op == OP_N) {
-            if (fx && op == OP_D && !T.no_del && c.x + l > T.t0) interval_add(T.cnt + (8 + bank) * TT, c.x, l, T.t0);
+            if (fx && op == OP_D && !T.no_del && c.x + l > T.t0)
+                interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, c.x, l, T.t0, half_inc(bank));
             c.x += l;
         } else if (op == OP_I || op == OP_S) c.y += l;
     }
@@ -240,12 +265,13 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
     const uint32_t cls = r.cls;
     if (!(cls & CLS_ADMITTED)) return;
     const bool fx = part == 0;
-    if (raw && fx) interval_add(raw, r.pos, r.end - r.pos, T.t0);
+    if (raw && fx) interval_add(raw, r.pos, r.end - r.pos, T.t0, 1u);
     if (!(cls & CLS_COUNTED)) return;
     const int bank = cls & 3u;
-    if (!T.no_del && fx) interval_add(T.cnt + bank * TT, r.pos, r.end - r.pos, T.t0);   // M, D and N all count
+    const uint32_t inc = half_inc(bank);
+    if (!T.no_del && fx) interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, r.pos, r.end - r.pos, T.t0, inc);   // M, D and N all count
     if (cls & CLS_NOREF) {   // mapped, CIGAR consumes no reference: one deletion event at pos
-        if (!T.no_del && fx) interval_add(T.cnt + (8 + bank) * TT, r.pos, 1, T.t0);
+        if (!T.no_del && fx) interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, r.pos, 1, T.t0, inc);
         return;
     }
     VarCursor c;
@@ -256,10 +282,10 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
     if (simple) {
         const int a = max(r.pos - T.t0, 0), b = min(r.end - T.t0, TT);
         if (a < b && fx) {
-            uint32_t *mt = T.cnt + (4 + bank) * TT;
-            atomicAdd(mt + a, 1u);
-            if (b < TT) atomicAdd(mt + b, 0xffffffffu);
-            if (T.no_del) interval_add(T.cnt + bank * TT, r.pos, r.end - r.pos, T.t0);
+            uint32_t *mt = T.cnt + (W_MATCH + (bank >> 1)) * TT;
+            atomicAdd(mt + a, inc);
+            if (b < TT) atomicAdd(mt + b, 0u - inc);
+            if (T.no_del) interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, r.pos, r.end - r.pos, T.t0, inc);
         }
         c.rn = a + c.w0; c.rem = b - a - c.w0; c.sn = sn0 + (uint32_t)(a + T.t0 - r.pos + c.w0);
         have = c.rem > 0;
@@ -299,18 +325,18 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
 
 template <int KIND>
 __device__ __forceinline__ void cover_segment(const TileCtx &T, uint32_t cls, int x, int l) {
-    if (KIND == KIND_COV) interval_add(T.cnt + (cls & 3u) * TT, x, l, T.t0);
-    else {   // KIND_EXT: one array per (class, strand)
+    const uint32_t inc = half_inc(cls & CLS_REV ? 1 : 0);
+    if (KIND == KIND_COV) interval_add(T.cnt + ((cls >> 1) & 1u) * TT, x, l, T.t0, inc);
+    else {   // KIND_EXT: one word array per class
         uint32_t m = (cls >> CLS_EXT_SHIFT) & 255u;
-        const int s = cls & CLS_REV ? 1 : 0;
         const int a = max(x - T.t0, 0), b = min(x + l - T.t0, TT);
         if (a >= b) return;
         while (m) {
             int k = __ffs(m) - 1;
             m &= m - 1;
-            uint32_t *arr = T.cnt + (k * 2 + s) * TT;
-            atomicAdd(arr + a, 1u);
-            if (b < TT) atomicAdd(arr + b, 0xffffffffu);
+            uint32_t *arr = T.cnt + k * TT;
+            atomicAdd(arr + a, inc);
+            if (b < TT) atomicAdd(arr + b, 0u - inc);
         }
     }
 }
@@ -319,7 +345,7 @@ template <int KIND>
 __device__ void cover_read(const TileCtx &T, const TileArgs &A, const RInfo &r, uint32_t *raw) {
     const uint32_t cls = r.cls;
     if (!(cls & CLS_ADMITTED)) return;
-    if (raw) interval_add(raw, r.pos, r.end - r.pos, T.t0);
+    if (raw) interval_add(raw, r.pos, r.end - r.pos, T.t0, 1u);
     if (!(cls & CLS_COUNTED)) return;
     if (!T.no_del || (cls & CLS_SIMPLE)) {   // D / N / zero-length alignments all count (opt.pyx:1904-1906)
         cover_segment<KIND>(T, cls, r.pos, r.end - r.pos);
@@ -371,38 +397,44 @@ __device__ __forceinline__ void warp_scan_array(uint32_t *arr, int lane) {
 // ---- finalisation: rec() of the reference classes, all linear in the counters ------------------
 
 __device__ __forceinline__ uint4 operator+(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ uint4 operator-(uint4 a, uint4 b) { return make_uint4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ uint4 lo16(uint4 a) { return make_uint4(a.x & 0xffffu, a.y & 0xffffu, a.z & 0xffffu, a.w & 0xffffu); }
+__device__ __forceinline__ uint4 hi16(uint4 a) { return make_uint4(a.x >> 16, a.y >> 16, a.z >> 16, a.w >> 16); }
 
+template <bool ACCUM>
 struct QuadOut {
     int32_t *p;        // position 4q of the next field to write
     int64_t stride;
     bool vec;          // 128-bit stores allowed
     int nvalid;        // positions of the quad inside [start, end)
     __device__ __forceinline__ void put(uint4 v) {
-        if (vec) *reinterpret_cast<uint4 *>(p) = v;
-        else {
-            if (nvalid > 0) p[0] = v.x;
-            if (nvalid > 1) p[1] = v.y;
-            if (nvalid > 2) p[2] = v.z;
-            if (nvalid > 3) p[3] = v.w;
+        if (vec) {
+            if (ACCUM) v = v + *reinterpret_cast<const uint4 *>(p);
+            *reinterpret_cast<uint4 *>(p) = v;
+        } else {
+            if (nvalid > 0) p[0] = (ACCUM ? p[0] : 0) + v.x;
+            if (nvalid > 1) p[1] = (ACCUM ? p[1] : 0) + v.y;
+            if (nvalid > 2) p[2] = (ACCUM ? p[2] : 0) + v.z;
+            if (nvalid > 3) p[3] = (ACCUM ? p[3] : 0) + v.w;
         }
         p += stride;
     }
     __device__ __forceinline__ void skip(int nfields) { p += stride * nfields; }
-    // banks rev | pp << 1 -> all, fwd, rev, pp, pp_fwd, pp_rev (CountPpStrand, opt.pyx:147-168) or all, pp
+    // w0 = not-proper-pair word (fwd | rev << 16), w1 = proper-pair word ->
+    // all, fwd, rev, pp, pp_fwd, pp_rev (CountPpStrand, opt.pyx:147-168) or all, pp
     template <bool STRAND>
-    __device__ __forceinline__ void put_group(const uint4 *v) {
-        uint4 fwd = v[0] + v[2], rev = v[1] + v[3], pp = v[2] + v[3];
+    __device__ __forceinline__ void put_group(uint4 w0, uint4 w1) {
+        const uint4 s = w0 + w1;                 // halves stay below 65536: fwd | rev
+        const uint4 fwd = lo16(s), rev = hi16(s), pf = lo16(w1), pr = hi16(w1);
         put(fwd + rev);
-        if (STRAND) { put(fwd); put(rev); put(pp); put(v[2]); put(v[3]); }
-        else put(pp);
+        if (STRAND) { put(fwd); put(rev); put(pf + pr); put(pf); put(pr); }
+        else put(pf + pr);
     }
 };
 
 __device__ __forceinline__ uint4 ld4(const uint32_t *cnt, int arr, int q) {
     return *reinterpret_cast<const uint4 *>(cnt + arr * TT + 4 * q);
 }
-// v + (refcode of the position == code ? mt : 0) for the four positions of a quad
+// m + (refcode of the position == code ? mt : 0) for the four positions of a quad (packed words)
 __device__ __forceinline__ uint4 base_count(uint4 m, uint4 mt, uint32_t rc4, uint32_t code) {
     uint4 r = m;
     if (((rc4 >> 12) & 15u) == code) r.x += mt.x;
@@ -412,28 +444,28 @@ __device__ __forceinline__ uint4 base_count(uint4 m, uint4 mt, uint32_t rc4, uin
     return r;
 }
 
-// Writes the fields owned by (quad q, part) and returns the quad's total read count when this
-// part computes it (part 0), for the row mask.
-template <int STAT>
-__device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32_t *refn, int q, int part, QuadOut &O) {
+// Writes the fields owned by (quad q, sub-part `part` of 4) and returns the quad's total read
+// count when this part computes it (part 0), for the row mask.
+template <int STAT, bool ACCUM>
+__device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32_t *refn, int q, int part,
+                                               QuadOut<ACCUM> &O) {
     uint4 all = make_uint4(0, 0, 0, 0);
     if (STAT == PSS_COVERAGE || STAT == PSS_COVERAGE_STRAND || STAT == PSS_COVERAGE_GC) {
         if (part == 0) {
-            uint4 n[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) n[b] = ld4(cnt, b, q);
-            all = n[0] + n[1] + n[2] + n[3];
+            const uint4 w0 = ld4(cnt, 0, q), w1 = ld4(cnt, 1, q);
+            const uint4 s = w0 + w1;
+            all = lo16(s) + hi16(s);
             if (STAT == PSS_COVERAGE_GC) O.skip(1);                      // field 0 = gc (k_gc)
-            if (STAT == PSS_COVERAGE_STRAND) O.put_group<true>(n); else O.put_group<false>(n);
+            if (STAT == PSS_COVERAGE_STRAND) O.template put_group<true>(w0, w1);
+            else O.template put_group<false>(w0, w1);
         }
     } else if (STAT == PSS_COVERAGE_EXT || STAT == PSS_COVERAGE_EXT_STRAND) {
-        const int per = 8 / NPARTS;       // classes per part
-        if (part == 0) all = ld4(cnt, 0, q) + ld4(cnt, 1, q);
-        O.skip(part * per * (STAT == PSS_COVERAGE_EXT ? 1 : 3));
+        if (part == 0) { const uint4 w = ld4(cnt, 0, q); all = lo16(w) + hi16(w); }
+        O.skip(part * 2 * (STAT == PSS_COVERAGE_EXT ? 1 : 3));          // two classes per part
 #pragma unroll
-        for (int k = 0; k < per; ++k) {
-            int c = part * per + k;
-            uint4 f = ld4(cnt, 2 * c, q), r = ld4(cnt, 2 * c + 1, q);
+        for (int k = 0; k < 2; ++k) {
+            const uint4 w = ld4(cnt, part * 2 + k, q);
+            const uint4 f = lo16(w), r = hi16(w);
             O.put(f + r);
             if (STAT == PSS_COVERAGE_EXT_STRAND) { O.put(f); O.put(r); }
         }
@@ -442,60 +474,79 @@ __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32
         // part 0 -> groups 0-2, part 1 -> 3-5, part 2 -> 6-7, part 3 -> 8-9 (contiguous fields)
         const bool S = (STAT == PSS_VARIATION_STRAND);
         const int per = S ? 6 : 2;
-        uint4 v[4];
         if (part == 0) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, b, q);
-            all = v[0] + v[1] + v[2] + v[3];
-            O.put_group<S>(v);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, 4 + b, q);
-            O.put_group<S>(v);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, 16 + b, q);
-            O.put_group<S>(v);
+            const uint4 w0 = ld4(cnt, W_ALL, q), w1 = ld4(cnt, W_ALL + 1, q);
+            const uint4 s = w0 + w1;
+            all = lo16(s) + hi16(s);
+            O.template put_group<S>(w0, w1);
+            O.template put_group<S>(ld4(cnt, W_MATCH, q), ld4(cnt, W_MATCH + 1, q));
+            O.template put_group<S>(ld4(cnt, W_MMT, q), ld4(cnt, W_MMT + 1, q));
             return all;
         }
         const uint32_t rw = refn[q >> 1];
         const uint32_t rc4 = (q & 1) ? (rw & 0xffffu) : (rw >> 16);
         if (part == 1) {
             O.skip(3 * per);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, 8 + b, q);
-            O.put_group<S>(v);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = ld4(cnt, 12 + b, q);
-            O.put_group<S>(v);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 20 + b, q), ld4(cnt, 4 + b, q), rc4, 1u);   // A
-            O.put_group<S>(v);
+            O.template put_group<S>(ld4(cnt, W_DEL, q), ld4(cnt, W_DEL + 1, q));
+            O.template put_group<S>(ld4(cnt, W_INS, q), ld4(cnt, W_INS + 1, q));
+        } else O.skip((part == 2 ? 6 : 8) * per);
+        const uint4 m0 = ld4(cnt, W_MATCH, q), m1 = ld4(cnt, W_MATCH + 1, q);
+        // mismatch classes A, C, G, T, N = 0..4 with 4-bit codes 1, 2, 4, 8, 15; output order A C T G N
+        if (part == 1) {
+            O.template put_group<S>(base_count(ld4(cnt, W_MMC + 0, q), m0, rc4, 1u), base_count(ld4(cnt, W_MMC + 1, q), m1, rc4, 1u));
         } else if (part == 2) {
-            O.skip(6 * per);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 24 + b, q), ld4(cnt, 4 + b, q), rc4, 2u);   // C
-            O.put_group<S>(v);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 32 + b, q), ld4(cnt, 4 + b, q), rc4, 8u);   // T
-            O.put_group<S>(v);
+            O.template put_group<S>(base_count(ld4(cnt, W_MMC + 2, q), m0, rc4, 2u), base_count(ld4(cnt, W_MMC + 3, q), m1, rc4, 2u));
+            O.template put_group<S>(base_count(ld4(cnt, W_MMC + 6, q), m0, rc4, 8u), base_count(ld4(cnt, W_MMC + 7, q), m1, rc4, 8u));
         } else {
-            O.skip(8 * per);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 28 + b, q), ld4(cnt, 4 + b, q), rc4, 4u);   // G
-            O.put_group<S>(v);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[b] = base_count(ld4(cnt, 36 + b, q), ld4(cnt, 4 + b, q), rc4, 15u);  // N
-            O.put_group<S>(v);
+            O.template put_group<S>(base_count(ld4(cnt, W_MMC + 4, q), m0, rc4, 4u), base_count(ld4(cnt, W_MMC + 5, q), m1, rc4, 4u));
+            O.template put_group<S>(base_count(ld4(cnt, W_MMC + 8, q), m0, rc4, 15u), base_count(ld4(cnt, W_MMC + 9, q), m1, rc4, 15u));
         }
     }
     return all;
 }
 
+template <int STAT, bool ACCUM>
+__device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *cnt, const uint32_t *raw,
+                                            const uint32_t *refn, int64_t t0l, int tid) {
+    const int q = tid % NQUAD;
+    const int64_t pl = t0l + 4 * q;
+    const int64_t rem = A.end - pl;
+    if (rem <= 0) return;
+    const int nvalid = rem > 4 ? 4 : (int)rem;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(A.out) & 15) == 0) && ((A.stride & 3) == 0) &&
+                         (((pl - A.start) & 3) == 0);
+    // full quads always; partial quads only when the row is padded (stride beyond the range)
+    const bool vec = aligned && (nvalid == 4 || (pl - A.start) + 4 <= A.stride);
+    // four sub-parts (18, 18, 12, 12 fields for variation_strand) shared by NPARTS thread groups
+    const int g = tid / NQUAD;
+    const uint32_t mine = NPARTS == 4 ? (1u << g) : NPARTS == 3 ? (g == 2 ? 0xcu : (1u << g))
+                          : NPARTS == 2 ? (g == 0 ? 0x9u : 0x6u) : 0xfu;
+#pragma unroll 1
+    for (int part = 0; part < 4; ++part) {
+        if (!((mine >> part) & 1u)) continue;
+        QuadOut<ACCUM> O;
+        O.p = A.out + (pl - A.start);
+        O.stride = A.stride;
+        O.nvalid = nvalid;
+        O.vec = vec;
+        uint4 all = tile_finalize<STAT, ACCUM>(cnt, refn, q, part, O);
+        if (part == 0) {
+            if (A.need_raw) all = ld4(raw, 0, q);
+            uint8_t *m = A.rowmask + (pl - A.start);
+            if (nvalid > 0) m[0] = (all.x ? 1 : 0) | (ACCUM ? m[0] : 0);
+            if (nvalid > 1) m[1] = (all.y ? 1 : 0) | (ACCUM ? m[1] : 0);
+            if (nvalid > 2) m[2] = (all.z ? 1 : 0) | (ACCUM ? m[2] : 0);
+            if (nvalid > 3) m[3] = (all.w ? 1 : 0) | (ACCUM ? m[3] : 0);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ the kernel
 
 template <int KIND, int STAT>
-__global__ void __launch_bounds__(TTHREADS, 2)
+__global__ void __launch_bounds__(TTHREADS, TCTAS)
 k_tile(TileArgs A) {
-    static_assert(NPARTS == 4, "finalisation is written for four parts");
+    static_assert(TTHREADS % NQUAD == 0 && NPARTS >= 1 && NPARTS <= 4, "finalisation needs 1 to 4 threads per quad");
     extern __shared__ __align__(128) uint8_t smem[];
     const int NARR = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
@@ -545,12 +596,6 @@ k_tile(TileArgs A) {
             if (KIND == KIND_VAR) bulk_g2s(s_refn, A.refpack + (size_t)tile * REFN_WORDS, (REFN_WORDS + 4) * 4, &s_bar);
         } else mbar_arrive_expect_tx(&s_bar, 0);
     }
-    {   // zero the counters
-        const int nw4 = (NARR + (A.need_raw ? 1 : 0)) * TT / 4;
-        uint4 z = make_uint4(0, 0, 0, 0);
-        for (int k = tid; k < nw4; k += TTHREADS) reinterpret_cast<uint4 *>(cnt)[k] = z;
-    }
-    __syncthreads();           // barrier initialised, counters zeroed
 
     TileCtx T;
     T.cnt = cnt; T.seqw = reinterpret_cast<const uint32_t *>(s_seq); T.refn = s_refn;
@@ -559,82 +604,81 @@ k_tile(TileArgs A) {
     uint32_t *rawp = A.need_raw ? raw : nullptr;
 
     uint32_t parity = 0;
-    for (int cb = d.x;;) {
-        mbar_wait(&s_bar, parity);
-        parity ^= 1;
-        const int n = s_n;
-        if (n == 0) break;
-        if (KIND == KIND_VAR) {
-            // up to four threads share a read: threads [k n, (k + 1) n) are part k of reads 0 .. n-1
-            const int nparts = min(4, TTHREADS / n);
-            const int part = tid / n;
-            if (part < nparts) {
-                const RInfo r = s_ri[tid - part * n];
-                const long long ciglo = s_ciglo;
-                const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
-                var_read(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
+    int cb = d.x;
+    bool more = true, staged = false, accum = false;
+    int n = 0;
+    for (;;) {      // passes of at most PASS_READS reads (one pass unless the tile is extremely deep)
+        {   // zero the counters
+            const int nw4 = (NARR + (A.need_raw ? 1 : 0)) * TT / 4;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int k = tid; k < nw4; k += TTHREADS) reinterpret_cast<uint4 *>(cnt)[k] = z;
+        }
+        __syncthreads();           // barrier initialised, counters zeroed
+        int in_pass = 0;
+        while (more) {
+            if (!staged) {
+                mbar_wait(&s_bar, parity);
+                parity ^= 1;
+                n = s_n;
+                staged = true;
+                if (n == 0) { more = false; break; }
             }
-        } else if (tid < n) cover_read<KIND>(T, A, s_ri[tid], rawp);
-        cb += n;
-        if (cb >= d.y) break;
-        __syncthreads();                       // staging buffers free again
-        if (tid == 0) {
-            int m = min(TCH, d.y - cb);
-            uint32_t sbytes = 0, cbytes = 0;
-            const uint8_t *src = nullptr, *csrc = nullptr;
+            if (in_pass + n > PASS_READS) break;       // finalise what we have, then come back to this chunk
             if (KIND == KIND_VAR) {
-                long long lo = A.seq_off[cb], hi = A.seq_off[cb + m];
-                while (m > 1 && hi - lo + 32 > TSEQ_BYTES) { m >>= 1; hi = A.seq_off[cb + m]; }
-                if (hi - lo + 32 > TSEQ_BYTES) { atomicOr(&A.st->toolong, 1); m = 0; }
-                else {
-                    stage_span(A.seq4, lo, hi, 1, &src, &sbytes, &s_seqlo);
-                    long long clo = A.ri[cb].cigar_off, chi = A.ri[cb + m - 1].cigar_off + A.ri[cb + m - 1].n_cigar;
-                    s_ciglo = -1;
-                    if (chi > clo && chi - clo + 8 <= TCIG_WORDS) stage_span(A.cigar, clo, chi, 4, &csrc, &cbytes, &s_ciglo);
+                // up to four threads share a read: threads [k n, (k + 1) n) are part k of reads 0 .. n-1
+                const int nparts = min(4, TTHREADS / n);
+                const int part = tid / n;
+                if (part < nparts) {
+                    const RInfo r = s_ri[tid - part * n];
+                    const long long ciglo = s_ciglo;
+                    const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
+                    var_read(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
                 }
-            }
-            s_n = m;
-            fence_proxy_async();
-            if (m > 0) {
-                mbar_arrive_expect_tx(&s_bar, (uint32_t)m * (uint32_t)sizeof(RInfo) + sbytes + cbytes);
-                bulk_g2s(s_ri, A.ri + cb, (uint32_t)m * (uint32_t)sizeof(RInfo), &s_bar);
-                if (sbytes) bulk_g2s(s_seq, src, sbytes, &s_bar);
-                if (cbytes) bulk_g2s(s_cig, csrc, cbytes, &s_bar);
-            } else mbar_arrive_expect_tx(&s_bar, 0);
-        }
-    }
-    __syncthreads();
-    {   // prefix sums of the difference arrays (+ raw)
-        const int nscan = KindInfo<KIND>::NDIFF + (A.need_raw ? 1 : 0);
-        for (int a = warp; a < nscan; a += NWARPS) {
-            uint32_t *arr = (a < KindInfo<KIND>::NDIFF) ? cnt + a * TT : raw;
-            warp_scan_array(arr, lane);
-        }
-    }
-    __syncthreads();
-    {
-        const int q = tid & (NQUAD - 1), part = tid / NQUAD;
-        const int64_t pl = t0l + 4 * q;
-        const int64_t rem = A.end - pl;
-        if (rem > 0) {
-            QuadOut O;
-            O.p = A.out + (pl - A.start);
-            O.stride = A.stride;
-            O.nvalid = rem > 4 ? 4 : (int)rem;
-            const bool aligned = ((reinterpret_cast<uintptr_t>(A.out) & 15) == 0) && ((A.stride & 3) == 0) &&
-                                 (((pl - A.start) & 3) == 0);
-            // full quads always; partial quads only when the row is padded (stride beyond the range)
-            O.vec = aligned && (O.nvalid == 4 || (pl - A.start) + 4 <= A.stride);
-            uint4 all = tile_finalize<STAT>(cnt, s_refn, q, part, O);
-            if (part == 0) {
-                if (A.need_raw) all = ld4(raw, 0, q);
-                uint8_t *m = A.rowmask + (pl - A.start);
-                if (O.nvalid > 0) m[0] = all.x ? 1 : 0;
-                if (O.nvalid > 1) m[1] = all.y ? 1 : 0;
-                if (O.nvalid > 2) m[2] = all.z ? 1 : 0;
-                if (O.nvalid > 3) m[3] = all.w ? 1 : 0;
+            } else if (tid < n) cover_read<KIND>(T, A, s_ri[tid], rawp);
+            in_pass += n;
+            staged = false;
+            cb += n;
+            if (cb >= d.y) { more = false; break; }
+            __syncthreads();                       // staging buffers free again
+            if (tid == 0) {
+                int m = min(TCH, d.y - cb);
+                uint32_t sbytes = 0, cbytes = 0;
+                const uint8_t *src = nullptr, *csrc = nullptr;
+                if (KIND == KIND_VAR) {
+                    long long lo = A.seq_off[cb], hi = A.seq_off[cb + m];
+                    while (m > 1 && hi - lo + 32 > TSEQ_BYTES) { m >>= 1; hi = A.seq_off[cb + m]; }
+                    if (hi - lo + 32 > TSEQ_BYTES) { atomicOr(&A.st->toolong, 1); m = 0; }
+                    else {
+                        stage_span(A.seq4, lo, hi, 1, &src, &sbytes, &s_seqlo);
+                        long long clo = A.ri[cb].cigar_off, chi = A.ri[cb + m - 1].cigar_off + A.ri[cb + m - 1].n_cigar;
+                        s_ciglo = -1;
+                        if (chi > clo && chi - clo + 8 <= TCIG_WORDS) stage_span(A.cigar, clo, chi, 4, &csrc, &cbytes, &s_ciglo);
+                    }
+                }
+                s_n = m;
+                fence_proxy_async();
+                if (m > 0) {
+                    mbar_arrive_expect_tx(&s_bar, (uint32_t)m * (uint32_t)sizeof(RInfo) + sbytes + cbytes);
+                    bulk_g2s(s_ri, A.ri + cb, (uint32_t)m * (uint32_t)sizeof(RInfo), &s_bar);
+                    if (sbytes) bulk_g2s(s_seq, src, sbytes, &s_bar);
+                    if (cbytes) bulk_g2s(s_cig, csrc, cbytes, &s_bar);
+                } else mbar_arrive_expect_tx(&s_bar, 0);
             }
         }
+        __syncthreads();
+        {   // prefix sums of the difference arrays (+ raw)
+            const int nscan = KindInfo<KIND>::NDIFF + (A.need_raw ? 1 : 0);
+            for (int a = warp; a < nscan; a += NWARPS) {
+                uint32_t *arr = (a < KindInfo<KIND>::NDIFF) ? cnt + a * TT : raw;
+                warp_scan_array(arr, lane);
+            }
+        }
+        __syncthreads();
+        if (accum) tile_output<STAT, true>(A, cnt, raw, s_refn, t0l, tid);
+        else tile_output<STAT, false>(A, cnt, raw, s_refn, t0l, tid);
+        if (!more) break;
+        accum = true;
+        __syncthreads();           // everyone is done reading the counters before they are zeroed
     }
 }
 
