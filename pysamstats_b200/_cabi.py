@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libpss_b200.so')
+LIB_PATH = os.environ.get('PSS_LIB') or os.path.join(HERE, 'csrc', 'libpss_b200.so')   # PSS_LIB: kernel-variant experiments
 
 PSS_OK, PSS_EINVAL, PSS_ECUDA, PSS_ENOMEM, PSS_EUNSORTED, PSS_ETOOLONG = 0, -1, -2, -3, -4, -5
 PSS_FLAG_GENERIC_KERNEL = 1

@@ -42,7 +42,9 @@ __host__ __device__ __forceinline__ bool op_is_match(int op) { return op == OP_M
 
 #define PSS_TILE 256          // positions per CTA in the pileup kernel (one per thread)
 #define PSS_CHUNK 128         // candidate reads staged in shared memory at a time
+#ifndef PSS_TTILE
 #define PSS_TTILE 512         // positions per CTA in the tile (scatter) kernel
+#endif
 
 struct PileupArgs {
     const RInfo *ri;

@@ -34,14 +34,13 @@
 
 #define TT PSS_TTILE          // positions per tile
 #ifndef TTHREADS
-#define TTHREADS 384
+#define TTHREADS 320
 #endif
 #ifndef TCTAS
 #define TCTAS 3               // CTAs per SM the kernel is compiled for
 #endif
 #define NWARPS (TTHREADS / 32)
 #define NQUAD (TT / 4)        // finalisation: quads of positions
-#define NPARTS (TTHREADS / NQUAD)
 #ifndef TCH
 #define TCH 192               // reads staged per chunk
 #endif
@@ -291,34 +290,54 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
         have = c.rem > 0;
     } else have = var_next_span(T, c, bank, sn0, fx);
     const bool hasseq = cls & CLS_HASSEQ;
-    while (have) {
-        const int n8 = min(c.rem, 8);
-        if (!hasseq) {           // no sequence: every base is a mismatch of no class (opt.pyx:2146-2147)
-            for (int i = 0; i < n8; ++i) var_mismatch(T, bank, c.rn + i, 0);
-        } else if (T.slow) {     // a reference position of this tile has no 4-bit code
-            for (int i = 0; i < n8; ++i) {
-                const uint32_t k = c.sn + i;
-                const int code = (T.seqw[k >> 3] >> (((k & 7) ^ 1) << 2)) & 15;   // byte k / 2, high nibble first
-                const int64_t ro = (int64_t)T.t0 + c.rn + i - T.ref_start;
-                const int rc = (T.ref && ro >= 0 && ro < T.ref_len) ? c_refcode[__ldg(T.ref + ro)] : 16;
-                if (code != rc) var_mismatch(T, bank, c.rn + i, code);
+    if (!hasseq || T.slow) {
+        while (have) {
+            const int n8 = min(c.rem, 8);
+            if (!hasseq) {       // no sequence: every base is a mismatch of no class (opt.pyx:2146-2147)
+                for (int i = 0; i < n8; ++i) var_mismatch(T, bank, c.rn + i, 0);
+            } else {             // a reference position of this tile has no 4-bit code
+                for (int i = 0; i < n8; ++i) {
+                    const uint32_t k = c.sn + i;
+                    const int code = (T.seqw[k >> 3] >> (((k & 7) ^ 1) << 2)) & 15;   // byte k / 2, high nibble first
+                    const int64_t ro = (int64_t)T.t0 + c.rn + i - T.ref_start;
+                    const int rc = (T.ref && ro >= 0 && ro < T.ref_len) ? c_refcode[__ldg(T.ref + ro)] : 16;
+                    if (code != rc) var_mismatch(T, bank, c.rn + i, code);
+                }
             }
-        } else {
-            const uint32_t si = c.sn >> 3, ssh = (c.sn & 7) << 2;
-            const uint32_t ri = (uint32_t)c.rn >> 3, rsh = ((uint32_t)c.rn & 7) << 2;
-            const uint32_t sw = __funnelshift_l(__byte_perm(T.seqw[si + 1], 0, 0x0123), __byte_perm(T.seqw[si], 0, 0x0123), ssh);
-            const uint32_t rw = __funnelshift_l(T.refn[ri + 1], T.refn[ri], rsh);
-            uint32_t xr = sw ^ rw;
-            if (n8 < 8) xr &= 0xffffffffu << ((8 - n8) << 2);
-            while (xr) {
-                const int lz = __clz(xr) >> 2, sh = 28 - (lz << 2);
-                var_mismatch(T, bank, c.rn + lz, (sw >> sh) & 15);
-                xr &= ~(0xfu << sh);
-            }
+            c.rn += c.wstep; c.sn += c.wstep; c.rem -= c.wstep;
+            if (c.rem <= 0) have = simple ? false : var_next_span(T, c, bank, sn0, fx);
         }
-        c.rn += c.wstep; c.sn += c.wstep; c.rem -= c.wstep;
-        if (c.rem <= 0) have = simple ? false : var_next_span(T, c, bank, sn0, fx);
+        return;
     }
+    // fast path: the words of the NEXT iteration are loaded before the (rare, atomic) mismatch
+    // handling of the current one, so the shared-memory latency overlaps it
+    uint32_t s0, s1, r0, r1;
+#define VAR_LOAD_WORDS()                                                              \
+    do {                                                                              \
+        const uint32_t si_ = c.sn >> 3, ri_ = (uint32_t)c.rn >> 3;                     \
+        s0 = T.seqw[si_]; s1 = T.seqw[si_ + 1]; r0 = T.refn[ri_]; r1 = T.refn[ri_ + 1]; \
+    } while (0)
+    if (have) VAR_LOAD_WORDS();
+    while (have) {
+        const uint32_t sw = __funnelshift_l(__byte_perm(s1, 0, 0x0123), __byte_perm(s0, 0, 0x0123), (c.sn & 7) << 2);
+        const uint32_t rw = __funnelshift_l(r1, r0, ((uint32_t)c.rn & 7) << 2);
+        uint32_t xr = sw ^ rw;
+        if (c.rem < 8) xr &= 0xffffffffu << ((8 - c.rem) << 2);
+        const int p0 = c.rn;
+        c.rn += c.wstep; c.sn += c.wstep; c.rem -= c.wstep;
+        const bool in_span = c.rem > 0;
+        if (in_span) VAR_LOAD_WORDS();
+        while (xr) {
+            const int lz = __clz(xr) >> 2, sh = 28 - (lz << 2);
+            var_mismatch(T, bank, p0 + lz, (sw >> sh) & 15);
+            xr &= ~(0xfu << sh);
+        }
+        if (!in_span) {
+            have = simple ? false : var_next_span(T, c, bank, sn0, fx);
+            if (have) VAR_LOAD_WORDS();
+        }
+    }
+#undef VAR_LOAD_WORDS
 }
 
 // ---- coverage kinds: one read per thread ------------------------------------------------------
@@ -508,35 +527,30 @@ __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32
 template <int STAT, bool ACCUM>
 __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *cnt, const uint32_t *raw,
                                             const uint32_t *refn, int64_t t0l, int tid) {
-    const int q = tid % NQUAD;
-    const int64_t pl = t0l + 4 * q;
-    const int64_t rem = A.end - pl;
-    if (rem <= 0) return;
-    const int nvalid = rem > 4 ? 4 : (int)rem;
     const bool aligned = ((reinterpret_cast<uintptr_t>(A.out) & 15) == 0) && ((A.stride & 3) == 0) &&
-                         (((pl - A.start) & 3) == 0);
-    // full quads always; partial quads only when the row is padded (stride beyond the range)
-    const bool vec = aligned && (nvalid == 4 || (pl - A.start) + 4 <= A.stride);
-    // four sub-parts (18, 18, 12, 12 fields for variation_strand) shared by NPARTS thread groups
-    const int g = tid / NQUAD;
-    const uint32_t mine = NPARTS == 4 ? (1u << g) : NPARTS == 3 ? (g == 2 ? 0xcu : (1u << g))
-                          : NPARTS == 2 ? (g == 0 ? 0x9u : 0x6u) : 0xfu;
+                         (((t0l - A.start) & 3) == 0);
+    // tasks = (sub-part, quad): 4 NQUAD of them (18, 18, 12, 12 fields per quad for variation_strand),
+    // dealt to the threads round-robin; a warp always holds one sub-part (NQUAD is a multiple of 32)
 #pragma unroll 1
-    for (int part = 0; part < 4; ++part) {
-        if (!((mine >> part) & 1u)) continue;
+    for (int task = tid; task < 4 * NQUAD; task += TTHREADS) {
+        const int part = task / NQUAD, q = task - part * NQUAD;
+        const int64_t pl = t0l + 4 * q;
+        const int64_t rem = A.end - pl;
+        if (rem <= 0) continue;
         QuadOut<ACCUM> O;
         O.p = A.out + (pl - A.start);
         O.stride = A.stride;
-        O.nvalid = nvalid;
-        O.vec = vec;
+        O.nvalid = rem > 4 ? 4 : (int)rem;
+        // full quads always; partial quads only when the row is padded (stride beyond the range)
+        O.vec = aligned && (O.nvalid == 4 || (pl - A.start) + 4 <= A.stride);
         uint4 all = tile_finalize<STAT, ACCUM>(cnt, refn, q, part, O);
         if (part == 0) {
             if (A.need_raw) all = ld4(raw, 0, q);
             uint8_t *m = A.rowmask + (pl - A.start);
-            if (nvalid > 0) m[0] = (all.x ? 1 : 0) | (ACCUM ? m[0] : 0);
-            if (nvalid > 1) m[1] = (all.y ? 1 : 0) | (ACCUM ? m[1] : 0);
-            if (nvalid > 2) m[2] = (all.z ? 1 : 0) | (ACCUM ? m[2] : 0);
-            if (nvalid > 3) m[3] = (all.w ? 1 : 0) | (ACCUM ? m[3] : 0);
+            if (O.nvalid > 0) m[0] = (all.x ? 1 : 0) | (ACCUM ? m[0] : 0);
+            if (O.nvalid > 1) m[1] = (all.y ? 1 : 0) | (ACCUM ? m[1] : 0);
+            if (O.nvalid > 2) m[2] = (all.z ? 1 : 0) | (ACCUM ? m[2] : 0);
+            if (O.nvalid > 3) m[3] = (all.w ? 1 : 0) | (ACCUM ? m[3] : 0);
         }
     }
 }
@@ -546,7 +560,8 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
 template <int KIND, int STAT>
 __global__ void __launch_bounds__(TTHREADS, TCTAS)
 k_tile(TileArgs A) {
-    static_assert(TTHREADS % NQUAD == 0 && NPARTS >= 1 && NPARTS <= 4, "finalisation needs 1 to 4 threads per quad");
+    static_assert(TTHREADS % 32 == 0 && NQUAD % 32 == 0, "whole warps per finalisation sub-part");
+    static_assert(TCH <= TTHREADS, "one thread per staged read at least");
     extern __shared__ __align__(128) uint8_t smem[];
     const int NARR = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
