@@ -132,6 +132,13 @@ static inline int seq_code(const orc_reads *R, int64_t i, int64_t k) {
 }
 static const char NT16[] = "=ACMGRSVTWYHKDBN"; /* opt.pyx:72 */
 
+/* bam_get_qual(b)[qpos] (opt.pyx:1902, :1166).  For a record without SEQ/QUAL (l_seq == 0) the
+ * reference indexes past the empty quality array -- undefined behaviour; oracle and engine
+ * both define that quality as 0. */
+static inline int64_t qual_at(const orc_reads *R, const uint8_t *qual, int64_t i, int64_t qpos) {
+    return qpos < R->l_seq[i] ? (int64_t)qual[R->qual_off[i] + qpos] : 0;
+}
+
 typedef struct {
     int is_del, is_refskip, indel;
     int64_t qpos;
@@ -364,13 +371,13 @@ static void recv(int stat, acc_t *A, const orc_reads *R, const uint8_t *qual, in
     }
     case 10: case 11: { /* Baseq opt.pyx:1153-1169, BaseqStrand :1242-1260 */
         int64_t sq = -1;
-        if (!e->is_del) { int64_t q = qual[R->qual_off[i] + e->qpos]; sq = q * q; }
+        if (!e->is_del) { int64_t q = qual_at(R, qual, i, e->qpos); sq = q * q; }
         bq6_update(A->bq[0], sq, pp, rev);
         break;
     }
     case 12: case 13: { /* BaseqExt opt.pyx:1310-1335, BaseqExtStrand :1385-1410 */
         int64_t sq = -1;
-        if (!e->is_del) { int64_t q = qual[R->qual_off[i] + e->qpos]; sq = q * q; }
+        if (!e->is_del) { int64_t q = qual_at(R, qual, i, e->qpos); sq = q * q; }
         bq6_update(A->bq[0], sq, pp, rev);
         if (!e->is_del) {
             int base = R->l_seq[i] ? NT16[seq_code(R, i, e->qpos)] : -2;
@@ -495,7 +502,7 @@ static void do_column(drv_t *D, int64_t pos, const int64_t *col, int64_t ncol) {
         plp_event e;
         resolve(R, i, pos, &e);
         if (P->min_mapq > 0 && R->mapq[i] < P->min_mapq) continue;
-        if (P->min_baseq > 0 && !e.is_del && D->qual[R->qual_off[i] + e.qpos] < P->min_baseq) continue;
+        if (P->min_baseq > 0 && !e.is_del && qual_at(R, D->qual, i, e.qpos) < P->min_baseq) continue;
         if (P->no_del && e.is_del) continue;
         if (P->no_dup && (R->flag[i] & F_DUP)) continue;
         recv(P->stat, &D->acc, R, D->qual, i, &e, rc);

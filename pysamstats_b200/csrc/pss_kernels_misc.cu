@@ -552,7 +552,9 @@ k_binned(pss_reads R, pss_binned_params P, int32_t *__restrict__ out) {
             c += (ch == 'g' || ch == 'c');
         }
         c = warp_sum(c);
-        gc = (we > ws) ? (int)rint((double)c * 100. / (double)(we - ws)) : 0;
+        // an empty window (beyond the FASTA) makes the reference's gc_content divide by zero
+        // (opt.pyx:1538, ZeroDivisionError); reported as -1, the host layer raises
+        gc = (we > ws) ? (int)rint((double)c * 100. / (double)(we - ws)) : -1;
     }
     if (lane) return;
     const int64_t nb = P.n_bins;

@@ -383,7 +383,7 @@ __device__ __forceinline__ void match_span(ACC &acc, const PileupArgs &a, int p,
         int qpos = y + off;
         if (hasseq) code = (__ldg(seq + (qpos >> 1)) >> ((~qpos & 1) << 2)) & 15;   // opt.pyx:2154
         if (ACC::QUAL || qual) {
-            if (qual) q = qual[qpos];
+            if (qual && hasseq) q = qual[qpos];   // no SEQ / QUAL: quality 0 (the reference reads past the record here)
             if (a.min_baseq > 0 && q < a.min_baseq) act = false;                     // opt.pyx:1900-1903
         }
     }

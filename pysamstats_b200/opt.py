@@ -245,6 +245,9 @@ def binned_tables(stat, alignmentfile, fafile=None, chrom=None, window_size=300,
         nb = int(params.n_bins)
         out = np.empty((len(names), nb), dtype=np.int32)
         ctx.binned_host(_reads_struct(batch, False), params, out)
+        if need_ref and nb and out[names.index('gc')].min() < 0:
+            # gc_content() of an empty window (beyond the FASTA): opt.pyx:1538 divides by zero
+            raise ZeroDivisionError('float division')
         pos = s + np.arange(nb, dtype=np.int64) * window_size + window_offset
         if one_based:
             pos = pos + 1
