@@ -36,10 +36,11 @@ extern "C" {
 #define PSS_ECUDA (-2)    /* CUDA runtime / launch failure */
 #define PSS_ENOMEM (-3)   /* workspace allocation failed */
 #define PSS_EUNSORTED (-4) /* batch not coordinate sorted (htslib: "unsorted positions") */
-#define PSS_ETOOLONG (-5)  /* a read longer than ~40 kb met the short-read kernel; see PSS_FLAG_GENERIC_KERNEL */
+#define PSS_ETOOLONG (-5)  /* a read of several kb met the short-read kernels; see PSS_FLAG_LONG_READS */
 
 /* pss_pileup_params.flags */
-#define PSS_FLAG_GENERIC_KERNEL 1 /* always use the generic per-position kernel (any read length) */
+#define PSS_FLAG_GENERIC_KERNEL 1 /* always use the generic per-position kernel (testing / comparison) */
+#define PSS_FLAG_LONG_READS 2     /* reads of arbitrary length: per-position kernel without shared-memory staging */
 
 /* statistics ids: order of stats_classes_pileup, pysamstats/pileup.py:150-166 */
 enum pss_pileup_stat {

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get('PSS_LIB') or os.path.join(HERE, 'csrc', 'libpss_b200.
 
 PSS_OK, PSS_EINVAL, PSS_ECUDA, PSS_ENOMEM, PSS_EUNSORTED, PSS_ETOOLONG = 0, -1, -2, -3, -4, -5
 PSS_FLAG_GENERIC_KERNEL = 1
+PSS_FLAG_LONG_READS = 2
 
 PILEUP_STATS = ('coverage', 'coverage_strand', 'coverage_ext', 'coverage_ext_strand', 'variation',
                 'variation_strand', 'tlen', 'tlen_strand', 'mapq', 'mapq_strand', 'baseq',

@@ -191,8 +191,8 @@ extern "C" int pss_synchronize(pss_ctx *ctx, void *stream) {
     CU(cudaStreamSynchronize(s));
     if (ctx->small_host->unsorted) return fail(ctx, PSS_EUNSORTED, "read batch is not coordinate sorted");
     if (ctx->small_host->toolong)
-        return fail(ctx, PSS_ETOOLONG, "a read is too long for the tile kernel's staging buffer; set "
-                                       "PSS_FLAG_GENERIC_KERNEL in pss_pileup_params.flags");
+        return fail(ctx, PSS_ETOOLONG, "a read is too long for the kernels' staging buffers; set "
+                                       "PSS_FLAG_LONG_READS in pss_pileup_params.flags");
     return PSS_OK;
 }
 
@@ -257,7 +257,7 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     if (npos <= 0) return PSS_OK;
     // counting statistics without a base-quality filter take the tile (scatter) kernel,
     // everything else the generic per-position kernel
-    const bool tile = tile_kernel_supports(P->stat, P->min_baseq) && !(P->flags & PSS_FLAG_GENERIC_KERNEL);
+    const bool tile = tile_kernel_supports(P->stat, P->min_baseq) && !(P->flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
     const int tsize = tile ? PSS_TTILE : PSS_TILE;
     int64_t ntiles = (npos + tsize - 1) / tsize;
     if (ntiles > 0x7fffffff) return fail(ctx, PSS_EINVAL, "position range too large for one call");
@@ -268,6 +268,9 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.seq4 = R->seq4;
     a.qual = need_qual ? (const uint8_t *)ctx->qual.p - ctx->qual_bias : nullptr;
     a.qual_off = need_qual ? R->qual_off : nullptr;
+    a.seq_off = R->seq_off;
+    a.st_ro = (const SmallState *)ctx->small.p;
+    a.toolong = &((SmallState *)ctx->small.p)->toolong;
     a.tlen = (P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND) ? R->tlen : nullptr;
     a.tile_rng = nullptr;
     a.ref = P->ref; a.ref_start = P->ref_start; a.ref_len = P->ref_len;
@@ -295,7 +298,7 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
                               tsize, (int2 *)ctx->rng.p, s, &ctx->launches));
         a.tile_rng = (const int2 *)ctx->rng.p;
         if (e0) CU(cudaEventRecord(e0, s));
-        CU(launch_pileup(P->stat, a, ntiles, s, &ctx->launches));
+        CU(launch_pileup(P->stat, a, ntiles, !(P->flags & PSS_FLAG_LONG_READS), s, &ctx->launches));
         if (e1) CU(cudaEventRecord(e1, s));
     }
     if (P->stat == PSS_COVERAGE_GC)

@@ -46,24 +46,6 @@ __host__ __device__ __forceinline__ bool op_is_match(int op) { return op == OP_M
 #define PSS_TTILE 512         // positions per CTA in the tile (scatter) kernel
 #endif
 
-struct PileupArgs {
-    const RInfo *ri;
-    const uint32_t *cigar;
-    const uint8_t *seq4;
-    const uint8_t *qual;        // tweaked qualities (workspace copy) or NULL
-    const int64_t *qual_off;
-    const int32_t *tlen;
-    const int2 *tile_rng;       // candidate read range [x, y) per tile
-    const uint8_t *ref;
-    int64_t ref_start, ref_len;
-    int64_t start, end;         // output position range
-    int32_t min_baseq;
-    int32_t no_del;
-    int32_t *out;
-    int64_t out_stride;         // elements between consecutive fields of out (>= end - start)
-    uint8_t *rowmask;
-};
-
 // device scalars shared between the small kernels
 struct SmallState {
     int32_t maxspan;       // max over reads of end - pos
@@ -73,6 +55,69 @@ struct SmallState {
     int32_t toolong;       // != 0 when a read's sequence does not fit the tile kernel's staging buffer
     int32_t pad_[3];
 };
+
+struct PileupArgs {
+    const RInfo *ri;
+    const uint32_t *cigar;
+    const uint8_t *seq4;
+    const uint8_t *qual;        // tweaked qualities (workspace copy) or NULL
+    const int64_t *qual_off;
+    const int64_t *seq_off;
+    const int32_t *tlen;
+    const int2 *tile_rng;       // candidate read range [x, y) per tile
+    const uint8_t *ref;
+    int64_t ref_start, ref_len;
+    int64_t start, end;         // output position range
+    int32_t min_baseq;
+    int32_t no_del;
+    const SmallState *st_ro;    // device scalars (maxspan)
+    int32_t *toolong;           // set when a read does not fit the staging buffers
+    int32_t *out;
+    int64_t out_stride;         // elements between consecutive fields of out (>= end - start)
+    uint8_t *rowmask;
+};
+
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ async-copy plumbing
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Bulk copies need 16-byte aligned addresses and sizes: widen the element span [lo, hi) of
+// `base` outward to 16-byte boundaries.  *first = element index that lands at offset 0 of
+// the shared buffer (may be fractional for 1-byte elements only in the sense of bytes).
+template <class Tp>
+__device__ __forceinline__ void stage_span(const Tp *base, long long lo, long long hi, int elem, const uint8_t **src,
+                                           uint32_t *bytes, long long *first) {
+    uintptr_t a0 = reinterpret_cast<uintptr_t>(base + lo), a1 = reinterpret_cast<uintptr_t>(base + hi);
+    uintptr_t al = a0 & ~(uintptr_t)15, ah = (a1 + 15) & ~(uintptr_t)15;
+    *src = reinterpret_cast<const uint8_t *>(al);
+    *bytes = (uint32_t)(ah - al);
+    *first = lo - (long long)((a0 - al) / (uintptr_t)elem);
+}
+
+#endif  // __CUDACC__
 
 // ---- kernel launchers (defined in the .cu files) ----------------------------------
 cudaError_t launch_prep(const pss_reads &R, int stepper, int min_mapq, int no_dup, RInfo *ri,
@@ -90,7 +135,7 @@ size_t tile_refpack_bytes(int64_t ntiles);
 cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, int64_t n_reads, SmallState *st,
                         int need_raw, int64_t ntiles, void *desc_buf, void *refpack_buf, cudaStream_t s,
                         int64_t *launches, cudaEvent_t e0, cudaEvent_t e1);
-cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, cudaStream_t s, int64_t *launches);
+cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, bool staged, cudaStream_t s, int64_t *launches);
 cudaError_t launch_gc(const uint8_t *ref, int64_t ref_start, int64_t ref_len, int64_t contig_len,
                       int64_t start, int64_t end, int window_size, int window_offset, int32_t *out_gc,
                       cudaStream_t s, int64_t *launches);

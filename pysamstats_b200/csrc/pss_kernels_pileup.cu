@@ -3,9 +3,10 @@
 //
 // Design (B200-first): the reference walks htslib's list of live reads once
 // per column.  Here every thread OWNS one genome position and every warp owns 32
-// consecutive positions; the warp iterates, in file order, over the reads that overlap
-// its 32 positions (a contiguous index range, because reads are start-sorted) and walks
-// each read's CIGAR warp-uniformly.  All counters of a position live in that thread's
+// consecutive positions; the tile's candidate reads (records, packed bases, qualities, tlen)
+// are staged in shared memory by bulk async copies, and the warp iterates, in file order,
+// over the reads that overlap its 32 positions (a contiguous index range, because reads are
+// start-sorted) and walks each read's CIGAR warp-uniformly.  All counters of a position live in that thread's
 // registers, so there are no atomics and no inter-thread traffic at all, the column order
 // of the reference (needed for the order-dependent Welford std of tlen) is preserved, and
 // a warp's stores are 128-byte coalesced rows of the SoA output.  Hot counters are packed
@@ -372,36 +373,37 @@ struct AccTlen {
 };
 
 // ------------------------------------------------------------------- the read walk
+//
+// seq / qual point at the read's first base (shared-memory staging buffers in the normal
+// kernel, global memory in the long-read variant); all lanes of a warp walk the same read.
 
 template <class ACC, int C>
-__device__ __forceinline__ void match_span(ACC &acc, const PileupArgs &a, int p, int x, int l, int y, bool ins_end,
+__device__ __forceinline__ void match_span(ACC &acc, int min_baseq, int p, int x, int l, int y, bool ins_end,
                                            const uint8_t *seq, const uint8_t *qual, bool hasseq, int refcode) {
     int off = p - x;
     bool act = (unsigned)off < (unsigned)l;
     int code = 16, q = 0;
     if (act) {
         int qpos = y + off;
-        if (hasseq) code = (__ldg(seq + (qpos >> 1)) >> ((~qpos & 1) << 2)) & 15;   // opt.pyx:2154
+        if (hasseq) code = (seq[qpos >> 1] >> ((~qpos & 1) << 2)) & 15;                 // opt.pyx:2154
         if (ACC::QUAL || qual) {
             if (qual && hasseq) q = qual[qpos];   // no SEQ / QUAL: quality 0 (the reference reads past the record here)
-            if (a.min_baseq > 0 && q < a.min_baseq) act = false;                     // opt.pyx:1900-1903
+            if (min_baseq > 0 && q < min_baseq) act = false;                            // opt.pyx:1900-1903
         }
     }
     acc.template match<C>(act, code, q, ins_end && off == l - 1, refcode);
 }
 
 template <class ACC, int C>
-__device__ __forceinline__ void process_read(ACC &acc, const PileupArgs &a, const RInfo &r, int64_t ridx, int p,
-                                             int w0, int w1, int refcode) {
+__device__ __forceinline__ void process_read(ACC &acc, const PileupArgs &a, const RInfo &r, int tlen, const uint8_t *seq,
+                                             const uint8_t *qual, int p, int w0, int w1, int refcode) {
     ReadCtx rc;
     rc.cls = r.cls;
-    rc.tlen = a.tlen ? __ldg(a.tlen + ridx) : 0;
+    rc.tlen = tlen;
     acc.begin(rc);
-    const uint8_t *seq = a.seq4 + r.seq_off;
-    const uint8_t *qual = a.qual ? a.qual + __ldg(a.qual_off + ridx) : nullptr;
     const bool hasseq = r.cls & CLS_HASSEQ;
     if (r.cls & CLS_SIMPLE) {
-        match_span<ACC, C>(acc, a, p, r.pos, r.end - r.pos, 0, false, seq, qual, hasseq, refcode);
+        match_span<ACC, C>(acc, a.min_baseq, p, r.pos, r.end - r.pos, 0, false, seq, qual, hasseq, refcode);
         return;
     }
     if (r.cls & CLS_NOREF) {   // mapped, CIGAR consumes no reference: one deletion-like event at pos
@@ -432,7 +434,7 @@ __device__ __forceinline__ void process_read(ACC &acc, const PileupArgs &a, cons
                         ins = l3 > 0;
                     }
                 }
-                match_span<ACC, C>(acc, a, p, x, l, y, ins, seq, qual, hasseq, refcode);
+                match_span<ACC, C>(acc, a.min_baseq, p, x, l, y, ins, seq, qual, hasseq, refcode);
             }
             x += l; y += l;
         } else if (op == OP_D || op == OP_N) {
@@ -444,22 +446,99 @@ __device__ __forceinline__ void process_read(ACC &acc, const PileupArgs &a, cons
 }
 
 template <class ACC>
+__device__ __forceinline__ void dispatch_read(ACC &acc, const PileupArgs &a, const RInfo &r, int tlen, const uint8_t *seq,
+                                              const uint8_t *qual, int p, int w0, int w1, int refcode) {
+    if (ACC::NCELL == 4) {
+        switch (r.cls & 3u) {
+        case 0: process_read<ACC, 0>(acc, a, r, tlen, seq, qual, p, w0, w1, refcode); break;
+        case 1: process_read<ACC, 1>(acc, a, r, tlen, seq, qual, p, w0, w1, refcode); break;
+        case 2: process_read<ACC, 2>(acc, a, r, tlen, seq, qual, p, w0, w1, refcode); break;
+        default: process_read<ACC, 3>(acc, a, r, tlen, seq, qual, p, w0, w1, refcode); break;
+        }
+    } else if (ACC::NCELL == 2) {
+        if (r.cls & CLS_REV) process_read<ACC, 1>(acc, a, r, tlen, seq, qual, p, w0, w1, refcode);
+        else process_read<ACC, 0>(acc, a, r, tlen, seq, qual, p, w0, w1, refcode);
+    } else process_read<ACC, 0>(acc, a, r, tlen, seq, qual, p, w0, w1, refcode);
+}
+
+// staging buffers of the normal kernel (reads up to ~150 bp fill a whole chunk; longer reads
+// shrink the chunk; a read that does not fit at all needs PSS_FLAG_LONG_READS)
+#define GCH 96
+#define GSEQ_BYTES (GCH * 76 + 64)
+#define GQUAL_BYTES (GCH * 152 + 64)
+
+struct GatherSmem {
+    RInfo ri[PSS_CHUNK];                         // GCH used when staged
+    long long qoff[GCH + 4];
+    int32_t tlen[GCH + 8];
+    __align__(16) uint8_t seq[GSEQ_BYTES + 32];
+    __align__(16) uint8_t qual[GQUAL_BYTES + 32];
+};
+
+// STAGED: RInfo, sequence, qualities, quality offsets and tlen of the tile's candidate reads
+// are staged in shared memory by bulk async copies (cp.async.bulk + mbarrier); each warp then
+// binary-searches its first relevant read.  !STAGED: sequence / qualities are read from
+// global memory (any read length).
+template <class ACC, bool STAGED>
 __global__ void __launch_bounds__(PSS_TILE)
 k_pileup(PileupArgs a) {
-    __shared__ RInfo s_ri[PSS_CHUNK];
-    const int tile = blockIdx.x;
-    const int64_t t0 = a.start + (int64_t)tile * PSS_TILE;
-    const int64_t pl = t0 + threadIdx.x;
-    const bool valid = pl < a.end;
-    const int p = (int)pl;
-    const int w0 = (int)(t0 + (threadIdx.x & ~31)), w1 = w0 + 32;
-    const int2 rng = a.tile_rng[tile];
-
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    GatherSmem &S = *reinterpret_cast<GatherSmem *>(smem_raw);
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_n;
+    __shared__ long long s_seqlo, s_quallo, s_qofflo, s_tlenlo;
     // per-base increment table in shared memory: the index diverges across lanes, which the
     // constant cache would serialise
     __shared__ uint2 s_lut[17];
-    if (threadIdx.x < 17) s_lut[threadIdx.x] = c_var_lut[threadIdx.x];
-    __syncthreads();
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t t0 = a.start + (int64_t)tile * PSS_TILE;
+    const int64_t pl = t0 + tid;
+    const bool valid = pl < a.end;
+    const int p = (int)pl;
+    const int w0 = (int)(t0 + (tid & ~31)), w1 = w0 + 32;
+    const int2 rng = a.tile_rng[tile];
+    const bool need_seq = ACC::REF, need_qual = a.qual != nullptr, need_tlen = a.tlen != nullptr;
+
+    // one chunk: thread 0 sizes it and issues the bulk copies
+    auto issue = [&](int cb) {
+        int n = min(GCH, rng.y - cb);
+        uint32_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+        const uint8_t *p1 = nullptr, *p2 = nullptr, *p3 = nullptr, *p4 = nullptr;
+        long long slo = 0, shi = 0, qlo = 0, qhi = 0;
+        while (n > 0) {
+            if (need_seq) { slo = a.seq_off[cb]; shi = a.seq_off[cb + n]; }
+            if (need_qual) { qlo = a.qual_off[cb]; qhi = a.qual_off[cb + n]; }
+            if (shi - slo + 32 <= GSEQ_BYTES && qhi - qlo + 32 <= GQUAL_BYTES) break;
+            if (n == 1) { atomicOr(a.toolong, 1); n = 0; }
+            else n >>= 1;
+        }
+        if (n > 0) {
+            if (need_seq) stage_span(a.seq4, slo, shi, 1, &p1, &b1, &s_seqlo);
+            if (need_qual) {
+                stage_span(a.qual, qlo, qhi, 1, &p2, &b2, &s_quallo);
+                stage_span(a.qual_off, (long long)cb, (long long)cb + n, 8, &p3, &b3, &s_qofflo);
+            }
+            if (need_tlen) stage_span(a.tlen, (long long)cb, (long long)cb + n, 4, &p4, &b4, &s_tlenlo);
+        }
+        s_n = n;
+        fence_proxy_async();
+        if (n > 0) {
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)n * (uint32_t)sizeof(RInfo) + b1 + b2 + b3 + b4);
+            bulk_g2s(S.ri, a.ri + cb, (uint32_t)n * (uint32_t)sizeof(RInfo), &s_bar);
+            if (b1) bulk_g2s(S.seq, p1, b1, &s_bar);
+            if (b2) bulk_g2s(S.qual, p2, b2, &s_bar);
+            if (b3) bulk_g2s(S.qoff, p3, b3, &s_bar);
+            if (b4) bulk_g2s(S.tlen, p4, b4, &s_bar);
+        } else mbar_arrive_expect_tx(&s_bar, 0);
+    };
+
+    if (STAGED && tid == 0) {
+        mbar_init(&s_bar, 1);
+        issue(rng.x);
+    }
+    if (tid < 17) s_lut[tid] = c_var_lut[tid];
     ACC acc;
     acc.init();
     acc.setup(s_lut);
@@ -472,40 +551,66 @@ k_pileup(PileupArgs a) {
             refcode = ref_code(c);
         }
     }
+    __syncthreads();
+    const int maxspan = a.st_ro->maxspan;
     bool raw = false;
     bool done = false;
     int nproc = 0;
-    for (int base = rng.x; base < rng.y; base += PSS_CHUNK) {
-        const int cnt = min(PSS_CHUNK, rng.y - base);
-        __syncthreads();
-        for (int t = threadIdx.x; t < cnt * 2; t += PSS_TILE)
-            reinterpret_cast<uint4 *>(s_ri)[t] = __ldg(reinterpret_cast<const uint4 *>(a.ri + base) + t);
-        __syncthreads();
-        if (done) continue;
-        for (int j = 0; j < cnt; ++j) {
-            const int rpos = s_ri[j].pos;
-            if (rpos >= w1) { done = true; break; }
-            const int rend = s_ri[j].end;
-            const uint32_t cls = s_ri[j].cls;
-            if (rend <= w0 || !(cls & CLS_ADMITTED)) continue;
-            raw |= (p >= rpos && p < rend);
-            if (!(cls & CLS_COUNTED)) continue;
-            const RInfo r = s_ri[j];
-            const int64_t ridx = (int64_t)base + j;
-            if (ACC::NCELL == 4) {
-                switch (cls & 3u) {
-                case 0: process_read<ACC, 0>(acc, a, r, ridx, p, w0, w1, refcode); break;
-                case 1: process_read<ACC, 1>(acc, a, r, ridx, p, w0, w1, refcode); break;
-                case 2: process_read<ACC, 2>(acc, a, r, ridx, p, w0, w1, refcode); break;
-                default: process_read<ACC, 3>(acc, a, r, ridx, p, w0, w1, refcode); break;
-                }
-            } else if (ACC::NCELL == 2) {
-                if (cls & CLS_REV) process_read<ACC, 1>(acc, a, r, ridx, p, w0, w1, refcode);
-                else process_read<ACC, 0>(acc, a, r, ridx, p, w0, w1, refcode);
-            } else {
-                process_read<ACC, 0>(acc, a, r, ridx, p, w0, w1, refcode);
+    uint32_t parity = 0;
+    for (int base = rng.x; base < rng.y;) {
+        int cnt;
+        if (STAGED) {
+            mbar_wait(&s_bar, parity);
+            parity ^= 1;
+            cnt = s_n;
+            if (cnt == 0) break;
+        } else {
+            cnt = min(PSS_CHUNK, rng.y - base);
+            __syncthreads();
+            for (int t = tid; t < cnt * 2; t += PSS_TILE)
+                reinterpret_cast<uint4 *>(S.ri)[t] = __ldg(reinterpret_cast<const uint4 *>(a.ri + base) + t);
+            __syncthreads();
+        }
+        if (!done) {
+            // first read of the chunk that can reach this warp's window: pos >= w0 - maxspan + 1
+            int j = 0;
+            {
+                int lo = 0, hi = cnt;
+                const int key = w0 - maxspan + 1;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (S.ri[mid].pos < key) lo = mid + 1; else hi = mid; }
+                j = lo;
             }
-            if (++nproc == 255) { acc.flush(); nproc = 0; }
+            const long long seqlo = STAGED ? s_seqlo : 0, quallo = STAGED ? s_quallo : 0;
+            const int qskew = STAGED ? (int)(base - s_qofflo) : 0, tskew = STAGED ? (int)(base - s_tlenlo) : 0;
+            for (; j < cnt; ++j) {
+                const uint4 h = *reinterpret_cast<const uint4 *>(&S.ri[j]);     // pos, end, cls, n_cigar
+                const int rpos = (int)h.x, rend = (int)h.y;
+                const uint32_t cls = h.z;
+                if (rpos >= w1) { done = true; break; }
+                if (rend <= w0 || !(cls & CLS_ADMITTED)) continue;
+                raw |= (unsigned)(p - rpos) < (unsigned)(rend - rpos);
+                if (!(cls & CLS_COUNTED)) continue;
+                const RInfo r = S.ri[j];
+                int tlen = 0;
+                const uint8_t *seq, *qual = nullptr;
+                if (STAGED) {
+                    seq = S.seq + (r.seq_off - seqlo);
+                    if (need_qual) qual = S.qual + (S.qoff[j + qskew] - quallo);
+                    if (need_tlen) tlen = S.tlen[j + tskew];
+                } else {
+                    const int64_t ridx = (int64_t)base + j;
+                    seq = a.seq4 + r.seq_off;
+                    if (need_qual) qual = a.qual + __ldg(a.qual_off + ridx);
+                    if (need_tlen) tlen = __ldg(a.tlen + ridx);
+                }
+                dispatch_read<ACC>(acc, a, r, tlen, seq, qual, p, w0, w1, refcode);
+                if (++nproc == 255) { acc.flush(); nproc = 0; }
+            }
+        }
+        base += cnt;
+        if (STAGED && base < rng.y) {
+            __syncthreads();                       // staging buffers free again
+            if (tid == 0) issue(base);
         }
     }
     acc.flush();
@@ -516,30 +621,40 @@ k_pileup(PileupArgs a) {
 }
 
 template <class ACC>
-static cudaError_t launch_one(const PileupArgs &a, int64_t ntiles, cudaStream_t s) {
-    k_pileup<ACC><<<(unsigned)ntiles, PSS_TILE, 0, s>>>(a);
+static cudaError_t launch_one(const PileupArgs &a, int64_t ntiles, bool staged, cudaStream_t s) {
+    const size_t smem = sizeof(GatherSmem);
+    static bool configured = false;     // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_pileup<ACC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_pileup<ACC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (staged) k_pileup<ACC, true><<<(unsigned)ntiles, PSS_TILE, smem, s>>>(a);
+    else k_pileup<ACC, false><<<(unsigned)ntiles, PSS_TILE, smem, s>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, cudaStream_t s, int64_t *launches) {
+cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, bool staged, cudaStream_t s, int64_t *launches) {
     if (ntiles <= 0) return cudaSuccess;
     if (launches) ++*launches;
     switch (stat) {
-    case PSS_COVERAGE: return launch_one<AccCoverage<PSS_COVERAGE>>(a, ntiles, s);
-    case PSS_COVERAGE_STRAND: return launch_one<AccCoverage<PSS_COVERAGE_STRAND>>(a, ntiles, s);
-    case PSS_COVERAGE_GC: return launch_one<AccCoverage<PSS_COVERAGE_GC>>(a, ntiles, s);
-    case PSS_COVERAGE_EXT: return launch_one<AccCoverageExt<PSS_COVERAGE_EXT>>(a, ntiles, s);
-    case PSS_COVERAGE_EXT_STRAND: return launch_one<AccCoverageExt<PSS_COVERAGE_EXT_STRAND>>(a, ntiles, s);
-    case PSS_VARIATION: return launch_one<AccVariation<PSS_VARIATION>>(a, ntiles, s);
-    case PSS_VARIATION_STRAND: return launch_one<AccVariation<PSS_VARIATION_STRAND>>(a, ntiles, s);
-    case PSS_TLEN: return launch_one<AccTlen<PSS_TLEN>>(a, ntiles, s);
-    case PSS_TLEN_STRAND: return launch_one<AccTlen<PSS_TLEN_STRAND>>(a, ntiles, s);
-    case PSS_MAPQ: return launch_one<AccMapq<PSS_MAPQ>>(a, ntiles, s);
-    case PSS_MAPQ_STRAND: return launch_one<AccMapq<PSS_MAPQ_STRAND>>(a, ntiles, s);
-    case PSS_BASEQ: return launch_one<AccBaseq<PSS_BASEQ>>(a, ntiles, s);
-    case PSS_BASEQ_STRAND: return launch_one<AccBaseq<PSS_BASEQ_STRAND>>(a, ntiles, s);
-    case PSS_BASEQ_EXT: return launch_one<AccBaseq<PSS_BASEQ_EXT>>(a, ntiles, s);
-    case PSS_BASEQ_EXT_STRAND: return launch_one<AccBaseq<PSS_BASEQ_EXT_STRAND>>(a, ntiles, s);
+    case PSS_COVERAGE: return launch_one<AccCoverage<PSS_COVERAGE>>(a, ntiles, staged, s);
+    case PSS_COVERAGE_STRAND: return launch_one<AccCoverage<PSS_COVERAGE_STRAND>>(a, ntiles, staged, s);
+    case PSS_COVERAGE_GC: return launch_one<AccCoverage<PSS_COVERAGE_GC>>(a, ntiles, staged, s);
+    case PSS_COVERAGE_EXT: return launch_one<AccCoverageExt<PSS_COVERAGE_EXT>>(a, ntiles, staged, s);
+    case PSS_COVERAGE_EXT_STRAND: return launch_one<AccCoverageExt<PSS_COVERAGE_EXT_STRAND>>(a, ntiles, staged, s);
+    case PSS_VARIATION: return launch_one<AccVariation<PSS_VARIATION>>(a, ntiles, staged, s);
+    case PSS_VARIATION_STRAND: return launch_one<AccVariation<PSS_VARIATION_STRAND>>(a, ntiles, staged, s);
+    case PSS_TLEN: return launch_one<AccTlen<PSS_TLEN>>(a, ntiles, staged, s);
+    case PSS_TLEN_STRAND: return launch_one<AccTlen<PSS_TLEN_STRAND>>(a, ntiles, staged, s);
+    case PSS_MAPQ: return launch_one<AccMapq<PSS_MAPQ>>(a, ntiles, staged, s);
+    case PSS_MAPQ_STRAND: return launch_one<AccMapq<PSS_MAPQ_STRAND>>(a, ntiles, staged, s);
+    case PSS_BASEQ: return launch_one<AccBaseq<PSS_BASEQ>>(a, ntiles, staged, s);
+    case PSS_BASEQ_STRAND: return launch_one<AccBaseq<PSS_BASEQ_STRAND>>(a, ntiles, staged, s);
+    case PSS_BASEQ_EXT: return launch_one<AccBaseq<PSS_BASEQ_EXT>>(a, ntiles, staged, s);
+    case PSS_BASEQ_EXT_STRAND: return launch_one<AccBaseq<PSS_BASEQ_EXT_STRAND>>(a, ntiles, staged, s);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -88,31 +88,6 @@ struct TileArgs {
     SmallState *st;
 };
 
-// ------------------------------------------------------------------ async-copy plumbing
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-// global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // ------------------------------------------------------------------------- small helpers
 
 __constant__ uint8_t c_refcode[256];   // upper-cased reference character -> 4-bit code, 16 = none
@@ -157,19 +132,6 @@ __device__ __forceinline__ void interval_add(uint32_t *arr, int x, int l, int t0
         atomicAdd(arr + a, inc);
         if (b < TT) atomicAdd(arr + b, 0u - inc);
     }
-}
-
-// Bulk copies need 16-byte aligned addresses and sizes: widen the element span [lo, hi) of
-// `base` outward to 16-byte boundaries.  *first = element index that lands at offset 0 of
-// the shared buffer (may be fractional for 1-byte elements only in the sense of bytes).
-template <class Tp>
-__device__ __forceinline__ void stage_span(const Tp *base, long long lo, long long hi, int elem, const uint8_t **src,
-                                           uint32_t *bytes, long long *first) {
-    uintptr_t a0 = reinterpret_cast<uintptr_t>(base + lo), a1 = reinterpret_cast<uintptr_t>(base + hi);
-    uintptr_t al = a0 & ~(uintptr_t)15, ah = (a1 + 15) & ~(uintptr_t)15;
-    *src = reinterpret_cast<const uint8_t *>(al);
-    *bytes = (uint32_t)(ah - al);
-    *first = lo - (long long)((a0 - al) / (uintptr_t)elem);
 }
 
 // ---- variation: one read per thread, one 8-base word per loop iteration ---------------------

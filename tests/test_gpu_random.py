@@ -129,7 +129,7 @@ def run(ctx, nb, ref, stat, lo, hi, flags=0, **kw):
 def check(ctx, nb, ref, reads, stat, lo, hi, **kw):
     withref = stat in config.stats_types_withref
     pos, F, _ = orc.pileup_packed(stat, reads, lo, hi, ref=ref.tobytes() if withref else None, truncate=True, **kw)
-    for flags in ((0, _cabi.PSS_FLAG_GENERIC_KERNEL) if stat != 'coverage_gc' else (0,)):
+    for flags in ((0, _cabi.PSS_FLAG_GENERIC_KERNEL, _cabi.PSS_FLAG_LONG_READS) if stat != 'coverage_gc' else (0,)):
         out, mask = run(ctx, nb, ref, stat, lo, hi, flags=flags, **kw)
         rows = np.flatnonzero(mask)
         label = '%s %r flags=%d' % (stat, kw, flags)
