@@ -261,10 +261,17 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    # DRAM traffic of the same kernel on the same workload from one `ncu --set full` capture
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if int(tj.get('interval_positions', -1)) == per:
+            traffic = tj['traffic_bytes_per_launch']
     k_ms, k_n = kms['variation_strand']
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
     roofline = {'bound': 'hbm', 'kernel': 'k_tile<KIND_VAR, PSS_VARIATION_STRAND>', 'achieved': achieved,
-                'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
                 'peak_source': peak_src, 'kernel_ms': k_ms, 'kernel_launches_timed': k_n,
                 'algorithmic_bytes_per_launch': alg_bytes,
                 'kernel_share_of_step': (k_ms / dev_ms) if k_ms > 0 else None,
@@ -349,13 +356,38 @@ def main():
                          '%.1f s wall' % (cores, cchunk / 1e6, cs),
                'reads_per_s': res['reads_per_step'] / cs}
 
+    # ---- host decode (rank 0, N = 1): synthetic BAM slice -> SoA through csrc/pss_host.cpp ----------
+    host_decode = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            import tempfile
+            from pysamstats_b200 import bamio
+            sl = 8 * 1000 * 1000
+            sb, _ = synth.make_interval_batch(0, sl, sl, depth=args.depth, read_len=args.read_len, device=dev,
+                                              with_qual=True)
+            snb = synth.batch_to_numpy(sb)
+            with tempfile.TemporaryDirectory() as tmp:
+                path = os.path.join(tmp, 'slice.bam')
+                bamio.write_bam(path, ['chrS'], [sl], snb, level=1)
+                t0 = time.perf_counter()
+                bf = bamio.BamFile(path)
+                dt = time.perf_counter() - t0
+                host_decode = {'reads_per_s': snb['n_reads'] / dt, 'seconds': dt, 'reads': int(snb['n_reads']),
+                               'bam_bytes': os.path.getsize(path), 'raw_bytes': bf.decode_seconds['raw_bytes'],
+                               'inflate_seconds': bf.decode_seconds['inflate'], 'threads': os.cpu_count(),
+                               'what': 'BGZF inflate + BAM parse of an 8 Mb slice of the workload written as a real BAM '
+                                       '(libpss_host.so); not part of value / e2e'}
+            del sb, snb
+        except Exception as e:   # noqa: BLE001 -- informative only
+            host_decode = {'error': repr(e)}
+
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': dev_ms, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, world),
                 'reads_per_s': total_reads / (dev_ms * 1e-3), 'gpu_launches': int(launches),
                 'e2e': e2e, 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
-                'reads_per_gpu': n_reads, 'rows_emitted_rank0': rows, 'checksum_rank0': chk,
+                'host_decode': host_decode, 'reads_per_gpu': n_reads, 'rows_emitted_rank0': rows, 'checksum_rank0': chk,
                 'setup_seconds': {'synthetic_batch': t_gen}}
         print(json.dumps(line), flush=True)
     if world > 1:

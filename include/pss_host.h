@@ -1,0 +1,76 @@
+/*
+ * pss_host.h -- C ABI of the host-side BAM decoder / writer (libpss_host.so, plain C++ + zlib,
+ * no CUDA).  It produces the structure-of-arrays read batch that include/pss_b200.h consumes.
+ *
+ * Replaces, for this engine, what the reference obtains from pysam / htslib:
+ *   - BGZF inflate + BAM record parsing behind AlignmentFile.pileup (pysamstats/opt.pyx:1853)
+ *     and IteratorRowRegion / cnext (opt.pyx:2040-2048);
+ *   - bam_endpos() (used for the region rule pos < end && endpos > start);
+ *   - the QNAME equivalence htslib's overlap hash keys on (pss_name_prev).
+ * The python binding is pysamstats_b200/bamio.py.  All functions return 0 on success or a
+ * negative code; pss_host_error() gives the message of the last failure on this thread.
+ */
+#ifndef PSS_HOST_H
+#define PSS_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pss_bam pss_bam;
+
+/* record arrays of a whole BAM file, file order; every pointer is caller-allocated with the
+ * sizes reported by pss_bam_sizes() (offset arrays: n + 1 entries) */
+typedef struct pss_host_arrays {
+    int32_t *tid;
+    int32_t *pos;
+    uint16_t *flag;
+    uint8_t *mapq;
+    int32_t *tlen;
+    int32_t *mtid;
+    int32_t *mpos;
+    int32_t *l_seq;
+    int64_t *endpos;      /* htslib bam_endpos(): pos + reference length (pos + 1 if unmapped / zero) */
+    int64_t *cigar_off;
+    uint32_t *cigar;      /* BAM encoding: len << 4 | op */
+    int64_t *seq_off;
+    uint8_t *seq4;        /* packed 4-bit bases, (l_seq + 1) / 2 bytes per record */
+    int64_t *qual_off;
+    uint8_t *qual;
+    uint8_t *names;       /* n x name_width bytes, NUL padded */
+} pss_host_arrays;
+
+const char *pss_host_error(void);
+
+/* Reads the file, inflates all BGZF blocks on n_threads threads (<= 0: hardware concurrency)
+ * and indexes the BAM records. */
+int pss_bam_open(const char *path, int n_threads, pss_bam **out);
+void pss_bam_close(pss_bam *b);
+
+int32_t pss_bam_n_ref(const pss_bam *b);
+const char *pss_bam_ref_name(const pss_bam *b, int32_t i);
+int64_t pss_bam_ref_len(const pss_bam *b, int32_t i);
+
+/* n records, total cigar words / packed sequence bytes / quality bytes, QNAME column width */
+int pss_bam_sizes(const pss_bam *b, int64_t *n, int64_t *n_cigar, int64_t *n_seq, int64_t *n_qual,
+                  int32_t *name_width);
+/* fills the arrays (parallel over records) */
+int pss_bam_fill(const pss_bam *b, const pss_host_arrays *a);
+/* seconds spent in (file read, inflate, record index) by pss_bam_open and bytes inflated */
+int pss_bam_timing(const pss_bam *b, double *t_read, double *t_inflate, double *t_index, int64_t *raw_bytes);
+
+/* prev[i] = index of the previous row with the same (NUL padded, fixed width) name, or -1 */
+int pss_name_prev(const uint8_t *names, int64_t n, int32_t width, int32_t *prev);
+
+/* Writes a coordinate-sorted BAM (BGZF, deflate level `level`, blocks compressed on n_threads
+ * threads) from SoA arrays of ONE batch: all records get `tid` from the tid array.  `names`
+ * as above.  Used to materialise the synthetic workload as a real BAM file. */
+int pss_bam_write(const char *path, int32_t n_ref, const char *const *ref_names, const int64_t *ref_lens,
+                  int64_t n, const pss_host_arrays *a, int32_t name_width, int level, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSS_HOST_H */

@@ -15,12 +15,62 @@ at ``opt.pyx:1989``); neither is available to this package, so it carries its ow
 File objects of other libraries (e.g. ``pysam.AlignmentFile`` / ``pysam.FastaFile``) are
 accepted wherever a path is: only their ``.filename`` is used.
 """
+import ctypes as C
 import os
 import struct
 import zlib
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(HERE, 'csrc', 'libpss_host.so')
+
+
+class HostArrays(C.Structure):
+    """struct pss_host_arrays (include/pss_host.h)"""
+    FIELDS = ('tid', 'pos', 'flag', 'mapq', 'tlen', 'mtid', 'mpos', 'l_seq', 'endpos', 'cigar_off', 'cigar',
+              'seq_off', 'seq4', 'qual_off', 'qual', 'names')
+    _fields_ = [(k, C.c_void_p) for k in FIELDS]
+
+
+_host_lib = None
+
+
+def host_lib():
+    """libpss_host.so (C++ decoder, include/pss_host.h) or None when it is not built; the numpy
+    decoder below is the (slow) fallback for the HOST side only -- the statistics themselves have
+    no CPU path."""
+    global _host_lib
+    if _host_lib is None:
+        if os.environ.get('PSS_NUMPY_DECODER') or not os.path.exists(HOST_LIB_PATH):
+            _host_lib = False
+        else:
+            lib = C.CDLL(HOST_LIB_PATH)
+            P = C.c_void_p
+            lib.pss_host_error.restype = C.c_char_p
+            lib.pss_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(P)]
+            lib.pss_bam_close.argtypes = [P]
+            lib.pss_bam_close.restype = None
+            lib.pss_bam_n_ref.argtypes = [P]
+            lib.pss_bam_n_ref.restype = C.c_int32
+            lib.pss_bam_ref_name.argtypes = [P, C.c_int32]
+            lib.pss_bam_ref_name.restype = C.c_char_p
+            lib.pss_bam_ref_len.argtypes = [P, C.c_int32]
+            lib.pss_bam_ref_len.restype = C.c_int64
+            lib.pss_bam_sizes.argtypes = [P] + [C.POINTER(C.c_int64)] * 4 + [C.POINTER(C.c_int32)]
+            lib.pss_bam_fill.argtypes = [P, C.POINTER(HostArrays)]
+            lib.pss_bam_timing.argtypes = [P] + [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int64)]
+            lib.pss_name_prev.argtypes = [P, C.c_int64, C.c_int32, P]
+            lib.pss_bam_write.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int64,
+                                          C.POINTER(HostArrays), C.c_int32, C.c_int, C.c_int]
+            _host_lib = lib
+    return _host_lib or None
+
+
+def _host_check(lib, rc):
+    if rc != 0:
+        raise ValueError(lib.pss_host_error().decode('ascii', 'replace'))
 
 _REF_CONSUMING = np.array([1, 0, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0], dtype=bool)  # MIDNSHP=X
 
@@ -126,6 +176,11 @@ def _name_prev(names):
     """Index of the previous record with the same QNAME (or -1), file order."""
     n = len(names)
     prev = np.full(n, -1, dtype=np.int32)
+    lib = host_lib()
+    if lib is not None and n:
+        names = np.ascontiguousarray(names)
+        _host_check(lib, lib.pss_name_prev(names.ctypes.data, n, names.dtype.itemsize, prev.ctypes.data))
+        return prev
     if n:
         _, inv = np.unique(names, return_inverse=True)
         order = np.argsort(inv, kind='stable')
@@ -137,8 +192,56 @@ def _name_prev(names):
 class BamFile(object):
     """A whole BAM file decoded into memory."""
 
-    def __init__(self, path):
+    def __init__(self, path, threads=0):
         self.filename = _path_of(path)
+        self.decode_seconds = None
+        lib = host_lib()
+        if lib is not None:
+            self._init_native(lib, threads)
+        else:
+            self._init_numpy()
+        self._tid_of = {r: i for i, r in enumerate(self.references)}
+        self._contig_cache = {}
+
+    def _init_native(self, lib, threads):
+        """C++ decoder (csrc/pss_host.cpp): threaded BGZF inflate + parallel SoA fill."""
+        h = C.c_void_p()
+        _host_check(lib, lib.pss_bam_open(self.filename.encode(), int(threads), C.byref(h)))
+        try:
+            nref = lib.pss_bam_n_ref(h)
+            self.references = tuple(lib.pss_bam_ref_name(h, i).decode('ascii') for i in range(nref))
+            self.lengths = tuple(int(lib.pss_bam_ref_len(h, i)) for i in range(nref))
+            n, nc, ns, nq, w = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+            _host_check(lib, lib.pss_bam_sizes(h, C.byref(n), C.byref(nc), C.byref(ns), C.byref(nq), C.byref(w)))
+            n, nc, ns, nq, w = n.value, nc.value, ns.value, nq.value, w.value
+            A = ReadBatch()
+            A.tid = -2
+            self._tid = np.empty(n, 'i4')
+            A.pos, A.flag, A.mapq = np.empty(n, 'i4'), np.empty(n, 'u2'), np.empty(n, 'u1')
+            A.tlen, A.mtid, A.l_seq = np.empty(n, 'i4'), np.empty(n, 'i4'), np.empty(n, 'i4')
+            A.endpos = np.empty(n, 'i8')
+            A.cigar_off, A.cigar = np.empty(n + 1, 'i8'), np.empty(max(nc, 1), 'u4')
+            A.seq_off, A.seq4 = np.empty(n + 1, 'i8'), np.empty(max(ns, 1), 'u1')
+            A.qual_off, A.qual = np.empty(n + 1, 'i8'), np.empty(max(nq, 1), 'u1')
+            names = np.zeros(n, dtype='S%d' % w)
+            ha = HostArrays()
+            ha.tid = self._tid.ctypes.data
+            for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'endpos', 'cigar_off', 'cigar', 'seq_off',
+                      'seq4', 'qual_off', 'qual'):
+                setattr(ha, k, getattr(A, k).ctypes.data)
+            ha.names = names.ctypes.data
+            _host_check(lib, lib.pss_bam_fill(h, C.byref(ha)))
+            A.cigar, A.seq4, A.qual = A.cigar[:nc], A.seq4[:ns], A.qual[:nq]
+            A.names = names
+            A.name_prev = None
+            self._all = A
+            tr, ti, tx, rb = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+            lib.pss_bam_timing(h, C.byref(tr), C.byref(ti), C.byref(tx), C.byref(rb))
+            self.decode_seconds = dict(read=tr.value, inflate=ti.value, index=tx.value, raw_bytes=rb.value)
+        finally:
+            lib.pss_bam_close(h)
+
+    def _init_numpy(self):
         raw = bgzf_inflate(self.filename)
         if raw[:4] != b'BAM\x01':
             raise ValueError('not a BAM file: %r' % self.filename)
@@ -154,7 +257,6 @@ class BamFile(object):
             off += 8 + l_name
         self.references = tuple(refs)
         self.lengths = tuple(lens)
-        self._tid_of = {r: i for i, r in enumerate(refs)}
         # walk the block_size chain
         starts = []
         n = len(raw)
@@ -211,7 +313,6 @@ class BamFile(object):
         A.endpos = A.pos.astype(np.int64) + np.where(reflen > 0, reflen, 1)
         A.name_prev = None
         self._all = A
-        self._contig_cache = {}
 
     def get_tid(self, chrom):
         return self._tid_of[chrom]
@@ -221,7 +322,12 @@ class BamFile(object):
         if chrom not in self._contig_cache:
             tid = self._tid_of[chrom]
             idx = np.flatnonzero(self._tid == tid)
-            b = self._all.subset(idx)
+            if len(idx) == len(self._tid):        # single-contig file: no gather needed
+                b = self._all
+                if b.name_prev is None:
+                    b.name_prev = _name_prev(b.names)
+            else:
+                b = self._all.subset(idx)
             b.tid = tid
             if len(idx) > 1 and np.any(np.diff(b.pos) < 0):
                 raise ValueError('BAM file is not coordinate sorted: %r' % self.filename)
@@ -237,6 +343,50 @@ class BamFile(object):
         sub = b.subset(np.flatnonzero(m))
         sub.tid = b.tid
         return sub
+
+
+def write_bam(path, references, lengths, batch, names=None, level=1, threads=0):
+    """Write the records of ONE contig batch (numpy SoA arrays as in ``struct pss_reads`` plus
+    ``endpos``; ``tid`` scalar) as a coordinate-sorted BAM.  ``names``: fixed-width bytes array,
+    default ``r<k>`` with k shared by a record and its ``name_prev`` chain.  Needs
+    libpss_host.so."""
+    lib = host_lib()
+    if lib is None:
+        raise RuntimeError('libpss_host.so is not built (make -C pysamstats_b200/csrc)')
+    n = int(batch['n_reads'])
+    if names is None:
+        prev = np.asarray(batch['name_prev'])
+        ids = np.arange(n, dtype=np.int64)
+        has = prev >= 0
+        # chains are short (mates): resolve to the first record of the chain
+        for _ in range(64):
+            nxt = np.where(has, ids[np.where(has, prev, 0)], ids)
+            if np.array_equal(nxt, ids):
+                break
+            ids = nxt
+        names = np.char.add(b'r', ids.astype('S20')).astype('S21')
+    names = np.ascontiguousarray(names)
+    keep = []
+
+    def arr(k, dt, size=None):
+        a = np.ascontiguousarray(np.asarray(batch[k]).astype(dt, copy=False))
+        keep.append(a)
+        return a.ctypes.data
+
+    ha = HostArrays()
+    tid = np.full(n, int(batch.get('tid', 0)), 'i4')
+    mpos = np.full(n, -1, 'i4')
+    keep += [tid, mpos, names]
+    ha.tid, ha.mpos, ha.names = tid.ctypes.data, mpos.ctypes.data, names.ctypes.data
+    for k, dt in (('pos', 'i4'), ('flag', 'u2'), ('mapq', 'u1'), ('tlen', 'i4'), ('mtid', 'i4'), ('l_seq', 'i4'),
+                  ('endpos', 'i8'), ('cigar_off', 'i8'), ('cigar', 'u4'), ('seq_off', 'i8'), ('seq4', 'u1')):
+        setattr(ha, k, arr(k, dt))
+    if batch.get('qual') is not None:
+        ha.qual_off, ha.qual = arr('qual_off', 'i8'), arr('qual', 'u1')
+    rn = (C.c_char_p * len(references))(*[r.encode() for r in references])
+    rl = (C.c_int64 * len(references))(*[int(x) for x in lengths])
+    _host_check(lib, lib.pss_bam_write(os.fspath(path).encode(), len(references), rn, rl, n, C.byref(ha),
+                                       names.dtype.itemsize, int(level), int(threads)))
 
 
 _bam_cache = {}

@@ -13,9 +13,23 @@ from oracle import bamread
 from _util import fx, ROOT
 
 
+@pytest.fixture(params=['native', 'numpy'])
+def decoder(request, monkeypatch):
+    """Both host decoders: csrc/pss_host.cpp (libpss_host.so) and the numpy fallback."""
+    monkeypatch.setattr(bamio, '_host_lib', None)
+    if request.param == 'numpy':
+        monkeypatch.setenv('PSS_NUMPY_DECODER', '1')
+    else:
+        monkeypatch.delenv('PSS_NUMPY_DECODER', raising=False)
+        assert bamio.host_lib() is not None, 'libpss_host.so is not built'
+    yield request.param
+    bamio._host_lib = None
+
+
 @pytest.mark.parametrize('name', ['test.bam', 'deep.bam', 'rna.bam', 'longcontignames.bam'])
-def test_decoder_matches_oracle_reader(name):
+def test_decoder_matches_oracle_reader(name, decoder):
     mine = bamio.BamFile(fx(name))
+    assert (mine.decode_seconds is not None) == (decoder == 'native')
     ref = bamread.Bam(fx(name))
     assert list(mine.references) == ref.references and list(mine.lengths) == ref.lengths
     A = mine._all
@@ -27,6 +41,36 @@ def test_decoder_matches_oracle_reader(name):
     assert np.array_equal(A.seq4, np.concatenate(ref.seq4))
     assert np.array_equal(A.qual, np.concatenate(ref.qual))
     assert [bytes(x) for x in A.names] == ref.qname
+
+
+def test_bam_writer_roundtrip(tmp_path):
+    from pysamstats_b200 import synth
+    G = 200000
+    batch, _ = synth.make_interval_batch(0, G, G, block=100000, with_qual=True)
+    nb = synth.batch_to_numpy(batch)
+    path = str(tmp_path / 'synthetic.bam')
+    bamio.write_bam(path, ['chrS', 'chrT'], [G, 1000], nb, level=1, threads=2)
+    ref = bamread.Bam(path)                                  # independent (gzip module) reader
+    assert ref.references == ['chrS', 'chrT'] and len(ref.pos) == nb['n_reads']
+    assert np.array_equal(ref.pos, nb['pos']) and np.array_equal(ref.flag, nb['flag'])
+    assert np.array_equal(np.concatenate(ref.seq4), nb['seq4']) and np.array_equal(np.concatenate(ref.qual), nb['qual'])
+    mine = bamio.BamFile(path).contig_batch('chrS')
+    for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'cigar', 'seq_off', 'seq4', 'qual_off',
+              'qual', 'name_prev'):
+        assert np.array_equal(getattr(mine, k), nb[k]), k
+    assert np.array_equal(mine.endpos, nb['endpos'])
+    with pytest.raises(ValueError):
+        bamio.BamFile(fx('ref.fa'))                          # not BGZF
+
+
+def test_name_prev_native_equals_numpy(monkeypatch):
+    names = np.array([b'a', b'bb', b'a', b'c', b'bb', b'a', b'', b''], dtype='S4')
+    expect = [-1, -1, 0, -1, 1, 2, -1, 6]
+    assert bamio._name_prev(names).tolist() == expect
+    monkeypatch.setattr(bamio, '_host_lib', None)
+    monkeypatch.setenv('PSS_NUMPY_DECODER', '1')
+    assert bamio._name_prev(names).tolist() == expect
+    bamio._host_lib = None
 
 
 def test_region_batch_rule():
@@ -119,6 +163,16 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.pss_binned_nbins(0, 50001, 300) == 167
     assert lib.pss_binned_nbins(1000, 20000, 200) == 95
     assert lib.pss_binned_nbins(5, 5, 300) == 1
+
+
+def test_host_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'pss_host.h')).read()
+    declared = set(re.findall(r'\b(pss_[a-z_0-9]+)\s*\(', header))
+    assert {'pss_bam_open', 'pss_bam_fill', 'pss_name_prev', 'pss_bam_write'} <= declared
+    lib = ctypes.CDLL(bamio.HOST_LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert ctypes.sizeof(bamio.HostArrays) == 16 * 8
 
 
 def test_struct_layouts_match_header():
