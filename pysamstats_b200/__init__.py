@@ -9,4 +9,4 @@ __version__ = '1.1.2+b200.0'
 
 from .pileup import *   # noqa: F401,F403
 from .binned import *   # noqa: F401,F403
-from . import config, opt, util, pileup, binned, bamio   # noqa: F401
+from . import config, opt, util, pileup, binned, bamio, io   # noqa: F401

@@ -212,3 +212,40 @@ def test_stat_generators_match_load():
         filename = fx('test.bam').encode()
     c = pysamstats.load_coverage(Foreign(), chrom='Pf3D7_01_v3', start=1000, end=1200)
     assert np.array_equal(c['reads_all'], a['reads_all'])
+
+
+def test_writers_and_cli(tmp_path):
+    # write_csv == csv.writer over the stat_* dicts (what the reference's io.write_csv does), and the
+    # command line front end with the reference's flags (one-based by default)
+    import csv
+    import io
+    import subprocess
+    import sys
+    from pysamstats_b200.io import write_csv
+    from _util import ROOT
+    kw = dict(chrom='Pf3D7_01_v3', start=1000, end=1300)
+    for stat, withref in (('variation', True), ('coverage_ext_strand', False), ('tlen_binned', False),
+                          ('coverage_binned', True)):
+        fa = fx('ref.fa') if withref else None
+        buf = io.StringIO()
+        write_csv(stat, buf, fx('test.bam'), fafile=fa, dialect='excel-tab', **kw)
+        exp = io.StringIO()
+        w = csv.writer(exp, dialect='excel-tab')
+        fields = [t[0] for t in getattr(config, 'dtype_' + stat)]
+        w.writerow(fields)
+        for rec in getattr(pysamstats, 'stat_' + stat)(fx('test.bam'), fafile=fa, **kw):
+            w.writerow([rec[f] for f in fields])
+        assert buf.getvalue() == exp.getvalue(), stat
+    out = tmp_path / 'cov.tsv'
+    cmd = [sys.executable, ROOT + '/scripts/pysamstats', '--type', 'variation', '-f', fx('ref.fa'), '-c', 'Pf3D7_01_v3',
+           '-s', '1001', '-e', '1301', '--min-mapq', '1', '--no-dup', '--fields', 'chrom,pos,ref,reads_all,A',
+           '--output', str(out), fx('test.bam')]
+    subprocess.check_call(cmd)
+    rows = [r.split('\t') for r in out.read_text().replace('\r', '').strip().split('\n')]
+    a = pysamstats.load_variation(fx('test.bam'), fx('ref.fa'), chrom='Pf3D7_01_v3', start=1001, end=1301,
+                                  one_based=True, min_mapq=1, no_dup=True)
+    assert rows[0] == ['chrom', 'pos', 'ref', 'reads_all', 'A'] and len(rows) == len(a) + 1
+    assert [int(r[1]) for r in rows[1:]] == a['pos'].tolist() and [int(r[4]) for r in rows[1:]] == a['A'].tolist()
+    rc = subprocess.call([sys.executable, ROOT + '/scripts/pysamstats', '--type', 'variation', fx('test.bam')],
+                         stderr=subprocess.DEVNULL)
+    assert rc == 2                                            # missing --fasta option

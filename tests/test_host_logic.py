@@ -180,3 +180,23 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_cabi.PssReads) == 4 * 8 + 8 + 13 * 8
     assert ctypes.sizeof(_cabi.PssPileupParams) == 10 * 4 + 6 * 8
     assert ctypes.sizeof(_cabi.PssBinnedParams) == 4 * 4 + 6 * 8
+
+
+def test_csv_block_formatter_equals_csv_writer():
+    import csv
+    import io
+    from pysamstats_b200.io import format_rows
+    n = 50
+    rng = np.random.default_rng(0)
+    pos = np.arange(1000, 1000 + n)
+    ref = np.array(list('ACGTN",\t') * 8, dtype='S1')[:n]
+    cols = {'reads_all': rng.integers(0, 5000, n).astype('i4'), 'gc': rng.integers(0, 100, n).astype('u1')}
+    for chrom in ('Pf3D7_01_v3', 'odd,name', 'tab\tname', 'quo"te'):
+        for dialect in ('excel-tab', 'excel'):
+            fields = ['chrom', 'pos', 'ref', 'reads_all', 'gc']
+            buf = io.StringIO()
+            w = csv.writer(buf, dialect=dialect)
+            for i in range(n):
+                w.writerow([chrom, int(pos[i]), ref[i].decode(), int(cols['reads_all'][i]), int(cols['gc'][i])])
+            assert format_rows(fields, chrom, pos, ref, cols, dialect) == buf.getvalue(), (chrom, dialect)
+    assert format_rows(['pos'], 'x', pos[:0], None, {}, 'excel') == ''
