@@ -30,6 +30,10 @@
 // stream to HBM.
 #include "pss_internal.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
 #define FULL 0xffffffffu
 
 #define TT PSS_TTILE          // positions per tile
@@ -86,6 +90,7 @@ struct TileArgs {
     int32_t *out;
     uint8_t *rowmask;
     SmallState *st;
+    unsigned long long *timing;   // TILE_TIMING builds only
 };
 
 // ------------------------------------------------------------------------- small helpers
@@ -271,24 +276,31 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
         }
         return;
     }
-    // fast path: the words of the NEXT iteration are loaded before the (rare, atomic) mismatch
-    // handling of the current one, so the shared-memory latency overlaps it
-    uint32_t s0, s1, r0, r1;
-#define VAR_LOAD_WORDS()                                                              \
-    do {                                                                              \
-        const uint32_t si_ = c.sn >> 3, ri_ = (uint32_t)c.rn >> 3;                     \
-        s0 = T.seqw[si_]; s1 = T.seqw[si_ + 1]; r0 = T.refn[ri_]; r1 = T.refn[ri_ + 1]; \
+    // fast path.  Within a span the word cursors advance by whole words (wstep = 8 nparts nibbles),
+    // so the nibble shifts are per-span constants and the loop is: 4 loads, 2 byte swaps, 2 funnel
+    // shifts, XOR.  The words of the NEXT iteration are loaded before the (rare, atomic) mismatch
+    // handling of the current one, so the shared-memory latency overlaps it.
+    const int wwords = c.wstep >> 3;
+    const uint32_t *sp = nullptr, *rp = nullptr;
+    uint32_t ssh = 0, rsh = 0, s0 = 0, s1 = 0, r0 = 0, r1 = 0;
+#define VAR_SPAN_BEGIN()                                                        \
+    do {                                                                        \
+        sp = T.seqw + (c.sn >> 3); ssh = (c.sn & 7) << 2;                         \
+        rp = T.refn + ((uint32_t)c.rn >> 3); rsh = ((uint32_t)c.rn & 7) << 2;     \
+        s0 = sp[0]; s1 = sp[1]; r0 = rp[0]; r1 = rp[1];                           \
     } while (0)
-    if (have) VAR_LOAD_WORDS();
+    if (have) VAR_SPAN_BEGIN();
     while (have) {
-        const uint32_t sw = __funnelshift_l(__byte_perm(s1, 0, 0x0123), __byte_perm(s0, 0, 0x0123), (c.sn & 7) << 2);
-        const uint32_t rw = __funnelshift_l(r1, r0, ((uint32_t)c.rn & 7) << 2);
-        uint32_t xr = sw ^ rw;
+        const uint32_t sw = __funnelshift_l(__byte_perm(s1, 0, 0x0123), __byte_perm(s0, 0, 0x0123), ssh);
+        uint32_t xr = sw ^ __funnelshift_l(r1, r0, rsh);
         if (c.rem < 8) xr &= 0xffffffffu << ((8 - c.rem) << 2);
         const int p0 = c.rn;
-        c.rn += c.wstep; c.sn += c.wstep; c.rem -= c.wstep;
+        c.rn += c.wstep; c.rem -= c.wstep;
         const bool in_span = c.rem > 0;
-        if (in_span) VAR_LOAD_WORDS();
+        if (in_span) {
+            sp += wwords; rp += wwords;
+            s0 = sp[0]; s1 = sp[1]; r0 = rp[0]; r1 = rp[1];
+        }
         while (xr) {
             const int lz = __clz(xr) >> 2, sh = 28 - (lz << 2);
             var_mismatch(T, bank, p0 + lz, (sw >> sh) & 15);
@@ -296,10 +308,10 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
         }
         if (!in_span) {
             have = simple ? false : var_next_span(T, c, bank, sn0, fx);
-            if (have) VAR_LOAD_WORDS();
+            if (have) VAR_SPAN_BEGIN();
         }
     }
-#undef VAR_LOAD_WORDS
+#undef VAR_SPAN_BEGIN
 }
 
 // ---- coverage kinds: one read per thread ------------------------------------------------------
@@ -541,6 +553,13 @@ k_tile(TileArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int64_t t0l = A.start + (int64_t)tile * TT;
+#ifdef TILE_TIMING
+    unsigned long long ts[8];
+#define STAMP(k) do { if (tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ts[k])); } while (0)
+    STAMP(0);
+#else
+#define STAMP(k)
+#endif
 
     // ---- thread 0 starts the bulk copies of the first chunk before anything else -------------
     TileDesc d;
@@ -573,6 +592,7 @@ k_tile(TileArgs A) {
             if (KIND == KIND_VAR) bulk_g2s(s_refn, A.refpack + (size_t)tile * REFN_WORDS, (REFN_WORDS + 4) * 4, &s_bar);
         } else mbar_arrive_expect_tx(&s_bar, 0);
     }
+    STAMP(1);
 
     TileCtx T;
     T.cnt = cnt; T.seqw = reinterpret_cast<const uint32_t *>(s_seq); T.refn = s_refn;
@@ -591,10 +611,12 @@ k_tile(TileArgs A) {
             for (int k = tid; k < nw4; k += TTHREADS) reinterpret_cast<uint4 *>(cnt)[k] = z;
         }
         __syncthreads();           // barrier initialised, counters zeroed
+        STAMP(2);
         int in_pass = 0;
         while (more) {
             if (!staged) {
                 mbar_wait(&s_bar, parity);
+                STAMP(3);
                 parity ^= 1;
                 n = s_n;
                 staged = true;
@@ -642,7 +664,9 @@ k_tile(TileArgs A) {
                 } else mbar_arrive_expect_tx(&s_bar, 0);
             }
         }
+        STAMP(4);
         __syncthreads();
+        STAMP(5);
         {   // prefix sums of the difference arrays (+ raw)
             const int nscan = KindInfo<KIND>::NDIFF + (A.need_raw ? 1 : 0);
             for (int a = warp; a < nscan; a += NWARPS) {
@@ -651,8 +675,16 @@ k_tile(TileArgs A) {
             }
         }
         __syncthreads();
+        STAMP(6);
         if (accum) tile_output<STAT, true>(A, cnt, raw, s_refn, t0l, tid);
         else tile_output<STAT, false>(A, cnt, raw, s_refn, t0l, tid);
+        STAMP(7);
+#ifdef TILE_TIMING
+        if (tid == 0 && A.timing && (tile & 63) == 0) {
+            unsigned long long *o = A.timing + (size_t)(tile >> 6) * 8;
+            for (int k = 0; k < 8; ++k) o[k] = ts[k];
+        }
+#endif
         if (!more) break;
         accum = true;
         __syncthreads();           // everyone is done reading the counters before they are zeroed
@@ -775,6 +807,15 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     a.ref = p.ref; a.ref_start = p.ref_start; a.ref_len = p.ref_len; a.start = p.start; a.end = p.end;
     a.stride = p.out_stride;
     a.no_del = p.no_del; a.need_raw = need_raw; a.out = p.out; a.rowmask = p.rowmask; a.st = st;
+    a.timing = nullptr;
+#ifdef TILE_TIMING
+    static unsigned long long *tbuf = nullptr;
+    static size_t tcap = 0;
+    size_t need = ((size_t)ntiles / 64 + 1) * 8;
+    if (need > tcap) { if (tbuf) cudaFree(tbuf); cudaMalloc(&tbuf, need * 8); tcap = need; }
+    cudaMemsetAsync(tbuf, 0, need * 8, s);
+    a.timing = tbuf;
+#endif
     if (launches) ++*launches;
     if (e0) cudaEventRecord(e0, s);
     cudaError_t e;
@@ -789,5 +830,21 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     default: e = cudaErrorInvalidValue;
     }
     if (e1) cudaEventRecord(e1, s);
+#ifdef TILE_TIMING
+    if (var && getenv("PSS_TILE_TIMING")) {
+        std::vector<unsigned long long> h(need);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h.data(), tbuf, need * 8, cudaMemcpyDeviceToHost);
+        double acc[8] = {0}; size_t cnt = 0;
+        for (size_t t = 0; t + 8 <= need; t += 8) {
+            if (!h[t]) continue;
+            for (int k = 1; k < 8; ++k) acc[k] += (double)(h[t + k] - h[t + k - 1]);
+            acc[0] += (double)(h[t + 7] - h[t]);
+            ++cnt;
+        }
+        if (cnt) fprintf(stderr, "[tile timing, ns, %zu tiles] total %.0f | desc+issue %.0f | zero+sync %.0f | tma wait %.0f | reads %.0f | barrier %.0f | scan %.0f | finalise %.0f\n",
+                         cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt, acc[5] / cnt, acc[6] / cnt, acc[7] / cnt);
+    }
+#endif
     return e;
 }
