@@ -41,9 +41,16 @@
 #define TTHREADS 320
 #endif
 #ifndef TCTAS
-#define TCTAS 3               // CTAs per SM the kernel is compiled for
+#define TCTAS 3               // CTAs per SM the variation kernels are compiled for
 #endif
-#define NWARPS (TTHREADS / 32)
+#ifndef TTHREADS_COV
+#define TTHREADS_COV 192      // coverage kinds: little work per tile, so more, smaller CTAs per SM
+#endif
+#ifndef TCTAS_COV
+#define TCTAS_COV 8
+#endif
+template <int KIND> struct KindLaunch { static const int NT = TTHREADS_COV, CTAS = TCTAS_COV; };
+template <> struct KindLaunch<2 /* KIND_VAR */> { static const int NT = TTHREADS, CTAS = TCTAS; };
 #define NQUAD (TT / 4)        // finalisation: quads of positions
 #ifndef TCH
 #define TCH 192               // reads staged per chunk
@@ -59,7 +66,9 @@ enum { KIND_COV = 0, KIND_EXT = 1, KIND_VAR = 2 };
 // NDIFF difference arrays come first (they are prefix-summed), then NPOINT point arrays.
 template <int KIND> struct KindInfo;
 template <> struct KindInfo<KIND_COV> { static const int NDIFF = 2, NPOINT = 0; };   // all[pp]: fwd | rev << 16
-template <> struct KindInfo<KIND_EXT> { static const int NDIFF = 8, NPOINT = 0; };   // class k: fwd | rev << 16
+// strand s, class pair g = (all|pp), (mate unmapped|other chr), (same strand|faceaway), (softclipped|duplicate):
+// word array 4 s + g, first class in the low half -- a typical read touches ONE word per interval end
+template <> struct KindInfo<KIND_EXT> { static const int NDIFF = 8, NPOINT = 0; };
 // all[pp], match[2 + pp], del[4 + pp] | ins[6 + pp], mismatches[8 + pp], mismatch class c = A,C,G,T,N: [10 + 2 c + pp]
 template <> struct KindInfo<KIND_VAR> { static const int NDIFF = 6, NPOINT = 14; };
 
@@ -320,16 +329,19 @@ template <int KIND>
 __device__ __forceinline__ void cover_segment(const TileCtx &T, uint32_t cls, int x, int l) {
     const uint32_t inc = half_inc(cls & CLS_REV ? 1 : 0);
     if (KIND == KIND_COV) interval_add(T.cnt + ((cls >> 1) & 1u) * TT, x, l, T.t0, inc);
-    else {   // KIND_EXT: one word array per class
-        uint32_t m = (cls >> CLS_EXT_SHIFT) & 255u;
+    else {   // KIND_EXT: word arrays of class pairs, per strand
+        const uint32_t m = (cls >> CLS_EXT_SHIFT) & 255u;
         const int a = max(x - T.t0, 0), b = min(x + l - T.t0, TT);
         if (a >= b) return;
-        while (m) {
-            int k = __ffs(m) - 1;
-            m &= m - 1;
-            uint32_t *arr = T.cnt + k * TT;
-            atomicAdd(arr + a, inc);
-            if (b < TT) atomicAdd(arr + b, 0u - inc);
+        uint32_t *base = T.cnt + (cls & CLS_REV ? 4 : 0) * TT;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t bits = (m >> (2 * g)) & 3u;
+            if (bits) {
+                const uint32_t v = (bits & 1u) | ((bits >> 1) << 16);
+                atomicAdd(base + g * TT + a, v);
+                if (b < TT) atomicAdd(base + g * TT + b, 0u - v);
+            }
         }
     }
 }
@@ -453,12 +465,12 @@ __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32
             else O.template put_group<false>(w0, w1);
         }
     } else if (STAT == PSS_COVERAGE_EXT || STAT == PSS_COVERAGE_EXT_STRAND) {
-        if (part == 0) { const uint4 w = ld4(cnt, 0, q); all = lo16(w) + hi16(w); }
-        O.skip(part * 2 * (STAT == PSS_COVERAGE_EXT ? 1 : 3));          // two classes per part
+        const uint4 wf = ld4(cnt, part, q), wr = ld4(cnt, 4 + part, q);   // classes 2 part, 2 part + 1
+        if (part == 0) all = lo16(wf) + lo16(wr);
+        O.skip(part * 2 * (STAT == PSS_COVERAGE_EXT ? 1 : 3));
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const uint4 w = ld4(cnt, part * 2 + k, q);
-            const uint4 f = lo16(w), r = hi16(w);
+            const uint4 f = k ? hi16(wf) : lo16(wf), r = k ? hi16(wr) : lo16(wr);
             O.put(f + r);
             if (STAT == PSS_COVERAGE_EXT_STRAND) { O.put(f); O.put(r); }
         }
@@ -498,7 +510,7 @@ __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32
     return all;
 }
 
-template <int STAT, bool ACCUM>
+template <int STAT, bool ACCUM, int NT>
 __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *cnt, const uint32_t *raw,
                                             const uint32_t *refn, int64_t t0l, int tid) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(A.out) & 15) == 0) && ((A.stride & 3) == 0) &&
@@ -506,7 +518,7 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
     // tasks = (sub-part, quad): 4 NQUAD of them (18, 18, 12, 12 fields per quad for variation_strand),
     // dealt to the threads round-robin; a warp always holds one sub-part (NQUAD is a multiple of 32)
 #pragma unroll 1
-    for (int task = tid; task < 4 * NQUAD; task += TTHREADS) {
+    for (int task = tid; task < 4 * NQUAD; task += NT) {
         const int part = task / NQUAD, q = task - part * NQUAD;
         const int64_t pl = t0l + 4 * q;
         const int64_t rem = A.end - pl;
@@ -532,10 +544,11 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
 // ------------------------------------------------------------------------------ the kernel
 
 template <int KIND, int STAT>
-__global__ void __launch_bounds__(TTHREADS, TCTAS)
+__global__ void __launch_bounds__(KindLaunch<KIND>::NT, KindLaunch<KIND>::CTAS)
 k_tile(TileArgs A) {
-    static_assert(TTHREADS % 32 == 0 && NQUAD % 32 == 0, "whole warps per finalisation sub-part");
-    static_assert(TCH <= TTHREADS, "one thread per staged read at least");
+    constexpr int NT = KindLaunch<KIND>::NT, NWARPS = NT / 32;
+    static_assert(NT % 32 == 0 && NQUAD % 32 == 0, "whole warps per finalisation sub-part");
+    static_assert(TCH <= NT, "one thread per staged read at least");
     extern __shared__ __align__(128) uint8_t smem[];
     const int NARR = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
@@ -608,7 +621,7 @@ k_tile(TileArgs A) {
         {   // zero the counters
             const int nw4 = (NARR + (A.need_raw ? 1 : 0)) * TT / 4;
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (int k = tid; k < nw4; k += TTHREADS) reinterpret_cast<uint4 *>(cnt)[k] = z;
+            for (int k = tid; k < nw4; k += NT) reinterpret_cast<uint4 *>(cnt)[k] = z;
         }
         __syncthreads();           // barrier initialised, counters zeroed
         STAMP(2);
@@ -625,7 +638,7 @@ k_tile(TileArgs A) {
             if (in_pass + n > PASS_READS) break;       // finalise what we have, then come back to this chunk
             if (KIND == KIND_VAR) {
                 // up to four threads share a read: threads [k n, (k + 1) n) are part k of reads 0 .. n-1
-                const int nparts = min(4, TTHREADS / n);
+                const int nparts = min(4, NT / n);
                 const int part = tid / n;
                 if (part < nparts) {
                     const RInfo r = s_ri[tid - part * n];
@@ -676,8 +689,8 @@ k_tile(TileArgs A) {
         }
         __syncthreads();
         STAMP(6);
-        if (accum) tile_output<STAT, true>(A, cnt, raw, s_refn, t0l, tid);
-        else tile_output<STAT, false>(A, cnt, raw, s_refn, t0l, tid);
+        if (accum) tile_output<STAT, true, NT>(A, cnt, raw, s_refn, t0l, tid);
+        else tile_output<STAT, false, NT>(A, cnt, raw, s_refn, t0l, tid);
         STAMP(7);
 #ifdef TILE_TIMING
         if (tid == 0 && A.timing && (tile & 63) == 0) {
@@ -763,7 +776,7 @@ static cudaError_t launch_tile_one(const TileArgs &a, int64_t ntiles, cudaStream
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_tile<KIND, STAT><<<(unsigned)ntiles, TTHREADS, smem, s>>>(a);
+    k_tile<KIND, STAT><<<(unsigned)ntiles, KindLaunch<KIND>::NT, smem, s>>>(a);
     return cudaGetLastError();
 }
 
