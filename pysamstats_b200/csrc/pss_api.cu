@@ -26,6 +26,7 @@ struct pss_ctx {
     bool prepared = false;
     pss_reads prep_reads;
     int prep_stepper = 0, prep_max_depth = 0, prep_min_mapq = 0, prep_no_dup = 0, prep_qual = 0;
+    int64_t desc_start = -1, desc_end = -1;   // position range the tile descriptors in tdesc describe
     DevBuf hb[20];          // device copies of host batches (*_host entry points)
     DevBuf outbuf[2], maskbuf[2];
     SmallState *small_host = nullptr;   // pinned mirror of the device scalars
@@ -222,7 +223,8 @@ static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_
     SmallState *st = (SmallState *)ctx->small.p;
     CU(launch_prep(*R, stepper, min_mapq, no_dup, ri, st, s, &ctx->launches));
     int maxcnt = max_depth ? max_depth : 8000;   // A.0
-    CU(launch_admit(ri, n, maxcnt, st, s, &ctx->launches));
+    CU(launch_admit(ri, R->pos, n, maxcnt, st, s, &ctx->launches));
+    ctx->desc_start = ctx->desc_end = -1;   // tile descriptors belong to the previous batch
     if (need_qual && n > 0) {
         if (!qual_dst) {
             if ((rc = ensure(ctx, ctx->qual, (size_t)R->n_qual_bytes)) != PSS_OK) return rc;
@@ -290,8 +292,11 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
         if ((rc = ensure(ctx, ctx->tdesc, tile_desc_bytes(ntiles))) != PSS_OK) return rc;
         if ((rc = ensure(ctx, ctx->refpack, tile_refpack_bytes(ntiles))) != PSS_OK) return rc;
         int need_raw = (P->min_mapq > 0 || P->no_dup || P->no_del) ? 1 : 0;
+        // descriptors depend on the batch and the position range only: reused by the next statistic
+        const bool desc_valid = ctx->desc_start == start && ctx->desc_end == end;
         CU(launch_tile(P->stat, a, R->seq_off, R->n_reads, (SmallState *)ctx->small.p, need_raw, ntiles, ctx->tdesc.p,
-                       ctx->refpack.p, s, &ctx->launches, e0, e1));
+                       ctx->refpack.p, desc_valid, s, &ctx->launches, e0, e1));
+        ctx->desc_start = start; ctx->desc_end = end;
     } else {
         if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)ntiles)) != PSS_OK) return rc;
         CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, ntiles,

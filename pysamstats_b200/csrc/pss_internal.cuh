@@ -122,7 +122,7 @@ __device__ __forceinline__ void stage_span(const Tp *base, long long lo, long lo
 // ---- kernel launchers (defined in the .cu files) ----------------------------------
 cudaError_t launch_prep(const pss_reads &R, int stepper, int min_mapq, int no_dup, RInfo *ri,
                         SmallState *st, cudaStream_t s, int64_t *launches);
-cudaError_t launch_admit(RInfo *ri, int64_t n, int maxcnt, SmallState *st, cudaStream_t s,
+cudaError_t launch_admit(RInfo *ri, const int32_t *pos, int64_t n, int maxcnt, SmallState *st, cudaStream_t s,
                          int64_t *launches);
 cudaError_t launch_overlap(const pss_reads &R, const RInfo *ri, uint8_t *qual_work, int32_t *pair_first,
                            int32_t *name_next, cudaStream_t s, int64_t *launches);
@@ -133,8 +133,8 @@ size_t tile_desc_bytes(int64_t ntiles);
 size_t tile_refpack_bytes(int64_t ntiles);
 // e0 / e1 (may be NULL) are recorded immediately before / after the tile kernel itself
 cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, int64_t n_reads, SmallState *st,
-                        int need_raw, int64_t ntiles, void *desc_buf, void *refpack_buf, cudaStream_t s,
-                        int64_t *launches, cudaEvent_t e0, cudaEvent_t e1);
+                        int need_raw, int64_t ntiles, void *desc_buf, void *refpack_buf, bool desc_valid,
+                        cudaStream_t s, int64_t *launches, cudaEvent_t e0, cudaEvent_t e1);
 cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, bool staged, cudaStream_t s, int64_t *launches);
 cudaError_t launch_gc(const uint8_t *ref, int64_t ref_start, int64_t ref_len, int64_t contig_len,
                       int64_t start, int64_t end, int window_size, int window_offset, int32_t *out_gc,

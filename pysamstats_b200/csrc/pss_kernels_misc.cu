@@ -153,11 +153,11 @@ k_prep(pss_reads R, int stepper, int min_mapq, int no_dup, RInfo *__restrict__ r
 // resolves that range exactly, group by group, with one CTA.
 
 __global__ void __launch_bounds__(256)
-k_safe(const RInfo *__restrict__ ri, int64_t n, int maxcnt, SmallState *st) {
+k_safe(const int32_t *__restrict__ pos, int64_t n, int maxcnt, SmallState *st) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + maxcnt;
     int lo = INT_MAX, hi = -1;
     if (i < n) {
-        if (ri[i].pos - ri[i - maxcnt].pos <= st->maxspan) { lo = (int)i; hi = (int)i; }
+        if (pos[i] - pos[i - maxcnt] <= st->maxspan) { lo = (int)i; hi = (int)i; }
     }
     lo = warp_min(lo);
     hi = warp_max(hi);
@@ -601,11 +601,11 @@ cudaError_t launch_prep(const pss_reads &R, int stepper, int min_mapq, int no_du
     return cudaGetLastError();
 }
 
-cudaError_t launch_admit(RInfo *ri, int64_t n, int maxcnt, SmallState *st, cudaStream_t s,
+cudaError_t launch_admit(RInfo *ri, const int32_t *pos, int64_t n, int maxcnt, SmallState *st, cudaStream_t s,
                          int64_t *launches) {
     if (n > maxcnt) {
         unsigned grid = (unsigned)((n - maxcnt + 255) / 256);
-        k_safe<<<grid, 256, 0, s>>>(ri, n, maxcnt, st);
+        k_safe<<<grid, 256, 0, s>>>(pos, n, maxcnt, st);
         LAUNCHED();
         k_admit_slow<<<1, 1024, 0, s>>>(ri, n, maxcnt, st);   // returns at once when nothing is unsafe
         LAUNCHED();

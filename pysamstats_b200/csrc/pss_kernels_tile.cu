@@ -76,7 +76,7 @@ template <> struct KindInfo<KIND_VAR> { static const int NDIFF = 6, NPOINT = 14;
 struct __align__(16) TileDesc {
     int32_t x, y;        // candidate read index range
     int32_t n0;          // reads of the first chunk
-    uint32_t flags;      // bit 0: a reference position of the tile has no 4-bit code
+    uint32_t flags;      // unused
     int64_t seq_lo;      // seq_off[x]
     int64_t seq_hi;      // seq_off[x + n0]
     int64_t cig_lo;      // CIGAR word span of the first chunk, cig_hi == cig_lo: not staged
@@ -90,6 +90,7 @@ struct TileArgs {
     const int64_t *seq_off;
     const TileDesc *desc;
     const uint32_t *refpack;   // REFN_WORDS words per tile (+ pad), KIND_VAR only
+    const uint32_t *tflags;    // per tile, bit 0: a reference position of the tile has no 4-bit code (KIND_VAR)
     const uint8_t *ref;        // ASCII reference (slow path only)
     int64_t ref_start, ref_len;
     int64_t start, end;
@@ -579,7 +580,8 @@ k_tile(TileArgs A) {
     {
         const uint4 *dp = reinterpret_cast<const uint4 *>(A.desc + tile);
         uint4 d0 = __ldg(dp);
-        d.x = (int)d0.x; d.y = (int)d0.y; d.n0 = (int)d0.z; d.flags = d0.w;
+        d.x = (int)d0.x; d.y = (int)d0.y; d.n0 = (int)d0.z;
+        d.flags = (KIND == KIND_VAR) ? __ldg(A.tflags + tile) : 0u;
     }
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -742,7 +744,12 @@ k_tile_desc(const RInfo *__restrict__ ri, const int64_t *__restrict__ seq_off, i
 // tile-aligned to `start`; flags tiles that contain a position without a code.
 __global__ void __launch_bounds__(256)
 k_refpack(const uint8_t *__restrict__ ref, int64_t ref_start, int64_t ref_len, int64_t start, int64_t end,
-          int64_t nwords, uint32_t *__restrict__ out, TileDesc *desc) {
+          int64_t nwords, uint32_t *__restrict__ out, uint32_t *tflags) {
+    // the code table in shared memory: lanes look up different characters, which the constant
+    // cache would serialise
+    __shared__ uint8_t s_code[256];
+    s_code[threadIdx.x] = c_refcode[threadIdx.x];
+    __syncthreads();
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     int64_t p0 = start + w * 8;
@@ -751,12 +758,12 @@ k_refpack(const uint8_t *__restrict__ ref, int64_t ref_start, int64_t ref_len, i
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         int64_t p = p0 + k, ro = p - ref_start;
-        int c = (ref && ro >= 0 && ro < ref_len) ? c_refcode[__ldg(ref + ro)] : 16;
+        int c = (ref && ro >= 0 && ro < ref_len) ? s_code[__ldg(ref + ro)] : 16;
         if (c == 16 && p < end) bad = true;
         v |= (uint32_t)(c & 15) << (28 - 4 * k);
     }
     out[w] = v;
-    if (bad) atomicOr(&desc[(w * 8) / TT].flags, 1u);
+    if (bad) atomicOr(&tflags[(w * 8) / TT], 1u);
 }
 
 template <int KIND>
@@ -790,11 +797,11 @@ bool tile_kernel_supports(int stat, int min_baseq) {
 }
 
 size_t tile_desc_bytes(int64_t ntiles) { return sizeof(TileDesc) * (size_t)ntiles; }
-size_t tile_refpack_bytes(int64_t ntiles) { return ((size_t)ntiles * REFN_WORDS + 8) * 4; }
+size_t tile_refpack_bytes(int64_t ntiles) { return ((size_t)ntiles * REFN_WORDS + 8 + (size_t)ntiles) * 4; }   // packed reference + tile flags
 
 cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, int64_t n_reads, SmallState *st,
-                        int need_raw, int64_t ntiles, void *desc_buf, void *refpack_buf, cudaStream_t s,
-                        int64_t *launches, cudaEvent_t e0, cudaEvent_t e1) {
+                        int need_raw, int64_t ntiles, void *desc_buf, void *refpack_buf, bool desc_valid,
+                        cudaStream_t s, int64_t *launches, cudaEvent_t e0, cudaEvent_t e1) {
     if (ntiles <= 0) return cudaSuccess;
     static bool table_ready = false;
     if (!table_ready) {
@@ -806,17 +813,24 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     }
     const bool var = (stat == PSS_VARIATION || stat == PSS_VARIATION_STRAND);
     TileDesc *desc = (TileDesc *)desc_buf;
-    k_tile_desc<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(p.ri, seq_off, n_reads, st, p.start, ntiles, var ? 1 : 0, desc);
-    if (launches) ++*launches;
+    if (!desc_valid) {
+        // always with the sequence / CIGAR spans: the descriptors are shared by all statistics of the batch
+        k_tile_desc<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(p.ri, seq_off, n_reads, st, p.start, ntiles, 1, desc);
+        if (launches) ++*launches;
+    }
     if (var) {
         int64_t nwords = ntiles * REFN_WORDS + 8;
+        uint32_t *tflags = (uint32_t *)refpack_buf + nwords;
+        cudaError_t em = cudaMemsetAsync(tflags, 0, sizeof(uint32_t) * (size_t)ntiles, s);
+        if (em != cudaSuccess) return em;
         k_refpack<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(p.ref, p.ref_start, p.ref_len, p.start, p.end, nwords,
-                                                                  (uint32_t *)refpack_buf, desc);
+                                                                  (uint32_t *)refpack_buf, tflags);
         if (launches) ++*launches;
     }
     TileArgs a;
     a.ri = p.ri; a.cigar = p.cigar; a.seq4 = p.seq4; a.seq_off = seq_off; a.desc = desc;
     a.refpack = (const uint32_t *)refpack_buf;
+    a.tflags = (const uint32_t *)refpack_buf + (ntiles * REFN_WORDS + 8);
     a.ref = p.ref; a.ref_start = p.ref_start; a.ref_len = p.ref_len; a.start = p.start; a.end = p.end;
     a.stride = p.out_stride;
     a.no_del = p.no_del; a.need_raw = need_raw; a.out = p.out; a.rowmask = p.rowmask; a.st = st;
