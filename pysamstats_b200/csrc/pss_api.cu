@@ -8,6 +8,7 @@
 #include <chrono>
 #include <vector>
 
+#include "pss_expand.h"
 #include "pss_internal.cuh"
 
 struct DevBuf {
@@ -29,6 +30,12 @@ struct pss_ctx {
     int64_t desc_start = -1, desc_end = -1;   // position range the tile descriptors in tdesc describe
     DevBuf hb[20];          // device copies of host batches (*_host entry points)
     DevBuf outbuf[2], maskbuf[2];
+    // narrow (16-bit) result transport of the host entry points: 3 device buffers, 3 pinned staging buffers
+    DevBuf nbuf[3], nmask[3];
+    void *hstage[3] = {nullptr, nullptr, nullptr};
+    size_t hstage_bytes[3] = {0, 0, 0};
+    cudaEvent_t nev_done[3] = {nullptr, nullptr, nullptr}, nev_copied[3] = {nullptr, nullptr, nullptr};
+    pss_pool *pool = nullptr;
     SmallState *small_host = nullptr;   // pinned mirror of the device scalars
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -147,6 +154,14 @@ extern "C" void pss_destroy(pss_ctx *ctx) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->nbuf[i].p) cudaFree(ctx->nbuf[i].p);
+        if (ctx->nmask[i].p) cudaFree(ctx->nmask[i].p);
+        if (ctx->hstage[i]) cudaFreeHost(ctx->hstage[i]);
+        if (ctx->nev_done[i]) cudaEventDestroy(ctx->nev_done[i]);
+        if (ctx->nev_copied[i]) cudaEventDestroy(ctx->nev_copied[i]);
+    }
+    pss_pool_destroy(ctx->pool);
     delete ctx;
 }
 
@@ -254,7 +269,7 @@ static cudaEvent_t next_event(pss_ctx *ctx) {
 
 // the pileup kernel (+ gc) for output positions [start, end); out[f * stride + (p - start)]
 static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *P, bool need_qual, int64_t start,
-                     int64_t end, int32_t *out, int64_t stride, uint8_t *rowmask, cudaStream_t s) {
+                     int64_t end, int32_t *out, int64_t stride, uint8_t *rowmask, cudaStream_t s, bool narrow = false) {
     int64_t npos = end - start;
     if (npos <= 0) return PSS_OK;
     // counting statistics without a base-quality filter take the tile (scatter) kernel,
@@ -279,6 +294,7 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.start = start; a.end = end;
     a.min_baseq = P->min_baseq; a.no_del = P->no_del;
     a.out = out; a.out_stride = stride; a.rowmask = rowmask;
+    a.narrow = (narrow && tile) ? 1 : 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->timing) {
         e0 = next_event(ctx); e1 = next_event(ctx);
@@ -458,6 +474,131 @@ static bool stat_reads_seq(int stat) {
     return stat == PSS_VARIATION || stat == PSS_VARIATION_STRAND || stat == PSS_BASEQ_EXT || stat == PSS_BASEQ_EXT_STRAND;
 }
 
+// One statistic over [start, end), int32 columns straight to the caller's host buffer: position
+// chunks of <= ~256 MB of output, two device buffers alternating against the D2H copies.
+static int host_stat_wide(pss_ctx *ctx, const pss_reads *D, const pss_pileup_params *Pd, bool q, int32_t *out,
+                          uint8_t *rowmask, cudaStream_t s, int *slot) {
+    int rc;
+    const int nf = kPileupFields[Pd->stat];
+    const int64_t npos = Pd->end - Pd->start;
+    int64_t chunk = ((int64_t)(256ll << 20) / (4ll * nf)) / PSS_TTILE * PSS_TTILE;
+    if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
+    if (chunk < PSS_TTILE) chunk = PSS_TTILE;
+    int &k = *slot;
+    for (int64_t cs = Pd->start; cs < Pd->end; cs += chunk, ++k) {
+        int64_t ce = cs + chunk < Pd->end ? cs + chunk : Pd->end;
+        int64_t cn = ce - cs;
+        int b = k & 1;
+        const int64_t stride = (chunk + 3) & ~(int64_t)3;   // padded rows: 128-bit stores everywhere
+        if (k >= 2) CU(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));   // buffer free again
+        if (ctx->outbuf[b].bytes < sizeof(int32_t) * (size_t)nf * (size_t)stride || ctx->maskbuf[b].bytes < (size_t)stride) {
+            // growing a buffer frees it: wait for the copy that may still read it
+            CU(cudaStreamSynchronize(ctx->copy_stream));
+            if ((rc = ensure(ctx, ctx->outbuf[b], sizeof(int32_t) * (size_t)nf * (size_t)stride)) != PSS_OK) return rc;
+            if ((rc = ensure(ctx, ctx->maskbuf[b], (size_t)stride)) != PSS_OK) return rc;
+        }
+        if ((rc = run_range(ctx, D, Pd, q, cs, ce, (int32_t *)ctx->outbuf[b].p, stride, (uint8_t *)ctx->maskbuf[b].p, s)) != PSS_OK)
+            return rc;
+        CU(cudaEventRecord(ctx->ev_done[b], s));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+        CU(cudaMemcpy2DAsync(out + (cs - Pd->start), sizeof(int32_t) * (size_t)npos, ctx->outbuf[b].p,
+                             sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)cn, (size_t)nf,
+                             cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaMemcpyAsync(rowmask + (cs - Pd->start), ctx->maskbuf[b].p, (size_t)cn, cudaMemcpyDeviceToHost,
+                           ctx->copy_stream));
+        CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        ctx->d2h_bytes += (int64_t)(sizeof(int32_t) * (size_t)cn * (size_t)nf + (size_t)cn);
+    }
+    return PSS_OK;
+}
+
+#define PSS_ERETRY_WIDE (-100)   // internal: a tile needed several passes, 16-bit transport cannot express it
+
+// Same, for the statistics of the tile kernel: the device writes 16-bit columns (every count
+// of a single-pass tile is < 65536), half the bytes cross PCIe into pinned staging buffers,
+// and the worker pool widens them into the caller's int32 columns while the next chunks are
+// computed and copied.  Three buffers rotate: compute k, copy k - 1, widen k - 2.
+static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_params *Pd, bool q, int32_t *out,
+                            uint8_t *rowmask, cudaStream_t s) {
+    int rc;
+    const int nf = kPileupFields[Pd->stat];
+    const int64_t npos = Pd->end - Pd->start;
+    int64_t chunk = ((int64_t)(128ll << 20) / (2ll * nf)) / PSS_TTILE * PSS_TTILE;
+    if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
+    if (chunk < PSS_TTILE) chunk = PSS_TTILE;
+    const int64_t stride = chunk;                       // multiple of 512: rows 8-byte aligned
+    const size_t bytes = sizeof(uint16_t) * (size_t)nf * (size_t)stride;
+    if (!ctx->pool) ctx->pool = pss_pool_create(0);
+    CU(cudaStreamSynchronize(ctx->copy_stream));        // nothing of an earlier statistic is in flight
+    for (int b = 0; b < 3; ++b) {
+        if ((rc = ensure(ctx, ctx->nbuf[b], bytes)) != PSS_OK) return rc;
+        if ((rc = ensure(ctx, ctx->nmask[b], (size_t)stride)) != PSS_OK) return rc;
+        if (ctx->hstage_bytes[b] < bytes) {
+            if (ctx->hstage[b]) cudaFreeHost(ctx->hstage[b]);
+            ctx->hstage[b] = nullptr; ctx->hstage_bytes[b] = 0;
+            CU(cudaMallocHost(&ctx->hstage[b], bytes));
+            ctx->hstage_bytes[b] = bytes;
+        }
+        if (!ctx->nev_done[b]) {
+            CU(cudaEventCreateWithFlags(&ctx->nev_done[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->nev_copied[b], cudaEventDisableTiming));
+        }
+    }
+    // clear the overflow flag of this batch's device state
+    CU(cudaMemsetAsync(&((SmallState *)ctx->small.p)->overflow16, 0, sizeof(int32_t), s));
+    size_t ticket[3] = {0, 0, 0};
+    int64_t cstart[3] = {0, 0, 0}, clen[3] = {0, 0, 0};
+    pss_pool *pool = ctx->pool;
+    auto widen_chunk = [&](int b) {      // D2H of buffer b has completed: hand its rows to the pool
+        const uint16_t *src = (const uint16_t *)ctx->hstage[b];
+        const int64_t cs = cstart[b], cn = clen[b];
+        const int64_t piece = 1 << 20;
+        size_t t = 0;
+        for (int f = 0; f < nf; ++f)
+            for (int64_t o = 0; o < cn; o += piece) {
+                const uint16_t *sp = src + (size_t)f * stride + o;
+                int32_t *dp = out + (size_t)f * npos + (cs - Pd->start) + o;
+                size_t len = (size_t)((cn - o) < piece ? (cn - o) : piece);
+                t = pss_pool_submit(pool, [sp, dp, len] { pss_widen_u16(sp, dp, len); });
+            }
+        ticket[b] = t;
+    };
+    int k = 0;
+    for (int64_t cs = Pd->start; cs < Pd->end; cs += chunk, ++k) {
+        const int64_t ce = cs + chunk < Pd->end ? cs + chunk : Pd->end, cn = ce - cs;
+        const int b = k % 3;
+        if (k >= 3) {
+            pss_pool_wait(pool, ticket[b]);                          // staging buffer b widened
+            CU(cudaStreamWaitEvent(s, ctx->nev_copied[b], 0));        // device buffer b copied out
+        }
+        if ((rc = run_range(ctx, D, Pd, q, cs, ce, (int32_t *)ctx->nbuf[b].p, stride, (uint8_t *)ctx->nmask[b].p, s, true)) != PSS_OK)
+            return rc;
+        CU(cudaEventRecord(ctx->nev_done[b], s));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->nev_done[b], 0));
+        CU(cudaMemcpyAsync(ctx->hstage[b], ctx->nbuf[b].p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaMemcpyAsync(rowmask + (cs - Pd->start), ctx->nmask[b].p, (size_t)cn, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaEventRecord(ctx->nev_copied[b], ctx->copy_stream));
+        ctx->d2h_bytes += (int64_t)(bytes + (size_t)cn);
+        cstart[b] = cs; clen[b] = cn;
+        if (k >= 1) {                                                // widen the previous chunk meanwhile
+            const int pb = (k - 1) % 3;
+            CU(cudaEventSynchronize(ctx->nev_copied[pb]));
+            widen_chunk(pb);
+        }
+    }
+    if (k >= 1) {
+        const int pb = (k - 1) % 3;
+        CU(cudaEventSynchronize(ctx->nev_copied[pb]));
+        widen_chunk(pb);
+    }
+    for (int b = 0; b < 3; ++b) pss_pool_wait(pool, ticket[b]);
+    // a tile that needed several passes (> 65535 reads) cannot be expressed in 16 bits
+    int32_t ovf = 0;
+    CU(cudaMemcpyAsync(&ovf, &((SmallState *)ctx->small.p)->overflow16, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return ovf ? PSS_ERETRY_WIDE : PSS_OK;
+}
+
 extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_pileup_params *P,
                                      int32_t *const *outs, uint8_t *const *rowmasks) {
     if (!ctx) return PSS_EINVAL;
@@ -496,41 +637,20 @@ extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32
     if ((rc = prepare_batch(ctx, &D, P[0].stepper, P[0].max_depth, P[0].min_mapq, P[0].no_dup, need_qual, nullptr, nullptr,
                             s, (need_qual && reads->n_reads > 0) ? reads->qual_off[0] : 0)) != PSS_OK)
         return rc;
-    int k = 0;     // running buffer slot: two device buffers alternate against the D2H copies
+    int k = 0;     // running buffer slot of the int32 pipeline
     for (int i = 0; i < n_stats; ++i) {
         pss_pileup_params Pd = P[i];
         Pd.ref = (P[i].ref && P[i].ref_len > 0) ? ref_dev : nullptr;
         const bool q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
-        const int nf = kPileupFields[P[i].stat];
-        // position chunks: <= ~256 MB of output each
-        int64_t chunk = ((int64_t)(256ll << 20) / (4ll * nf)) / PSS_TTILE * PSS_TTILE;
-        if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
-        if (chunk < PSS_TTILE) chunk = PSS_TTILE;
-        for (int64_t cs = Pd.start; cs < Pd.end; cs += chunk, ++k) {
-            int64_t ce = cs + chunk < Pd.end ? cs + chunk : Pd.end;
-            int64_t cn = ce - cs;
-            int b = k & 1;
-            const int64_t stride = (chunk + 3) & ~(int64_t)3;   // padded rows: 128-bit stores everywhere
-            if (k >= 2) CU(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));   // buffer free again
-            if (ctx->outbuf[b].bytes < sizeof(int32_t) * (size_t)nf * (size_t)stride || ctx->maskbuf[b].bytes < (size_t)stride) {
-                // growing a buffer frees it: wait for the copy that may still read it
-                CU(cudaStreamSynchronize(ctx->copy_stream));
-                if ((rc = ensure(ctx, ctx->outbuf[b], sizeof(int32_t) * (size_t)nf * (size_t)stride)) != PSS_OK) return rc;
-                if ((rc = ensure(ctx, ctx->maskbuf[b], (size_t)stride)) != PSS_OK) return rc;
-            }
-            if ((rc = run_range(ctx, &D, &Pd, q, cs, ce, (int32_t *)ctx->outbuf[b].p, stride, (uint8_t *)ctx->maskbuf[b].p,
-                                s)) != PSS_OK)
-                return rc;
-            CU(cudaEventRecord(ctx->ev_done[b], s));
-            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
-            CU(cudaMemcpy2DAsync(outs[i] + (cs - Pd.start), sizeof(int32_t) * (size_t)npos, ctx->outbuf[b].p,
-                                 sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)cn, (size_t)nf,
-                                 cudaMemcpyDeviceToHost, ctx->copy_stream));
-            CU(cudaMemcpyAsync(rowmasks[i] + (cs - Pd.start), ctx->maskbuf[b].p, (size_t)cn, cudaMemcpyDeviceToHost,
-                               ctx->copy_stream));
-            CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-            ctx->d2h_bytes += (int64_t)(sizeof(int32_t) * (size_t)cn * (size_t)nf + (size_t)cn);
+        static const bool no_narrow = getenv("PSS_NO_NARROW") != nullptr;
+        // (coverage_gc's gc column is written as int32 by k_gc, so it stays on the int32 pipeline)
+        const bool narrow = !no_narrow && tile_kernel_supports(P[i].stat, P[i].min_baseq) && P[i].stat != PSS_COVERAGE_GC &&
+                            !(P[i].flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
+        if (narrow) {
+            rc = host_stat_narrow(ctx, &D, &Pd, q, outs[i], rowmasks[i], s);
+            if (rc != PSS_ERETRY_WIDE) { if (rc != PSS_OK) return rc; continue; }
         }
+        if ((rc = host_stat_wide(ctx, &D, &Pd, q, outs[i], rowmasks[i], s, &k)) != PSS_OK) return rc;
     }
     if (trace) t_enq = now();
     CU(cudaStreamSynchronize(ctx->copy_stream));

@@ -1,0 +1,118 @@
+// Host side of the narrow result transport (see pss_pileup_host_multi): the counting statistics
+// come back from the device as 16-bit columns (half the PCIe bytes) and are widened here into
+// the caller's int32 columns by a small pool of worker threads, with non-temporal stores so the
+// host memory traffic is one read of the narrow data and one write of the wide data.
+#include <immintrin.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "pss_expand.h"
+
+struct pss_pool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::function<void()>> queue;
+    size_t next = 0, done = 0, submitted = 0;
+    bool stop = false;
+};
+
+pss_pool *pss_pool_create(int n_threads) {
+    if (n_threads <= 0) {
+        // PSS_HOST_THREADS, else the host's cores shared between the ranks of this node (torchrun
+        // exports LOCAL_WORLD_SIZE), capped at 32
+        const char *e = getenv("PSS_HOST_THREADS");
+        if (e && atoi(e) > 0) n_threads = atoi(e);
+        else {
+            unsigned hc = std::thread::hardware_concurrency();
+            n_threads = hc ? (int)hc : 4;
+            const char *lw = getenv("LOCAL_WORLD_SIZE");
+            if (lw && atoi(lw) > 1) n_threads = n_threads / atoi(lw);
+            if (n_threads > 32) n_threads = 32;
+            if (n_threads < 2) n_threads = 2;
+        }
+    }
+    pss_pool *p = new pss_pool();
+    for (int t = 0; t < n_threads; ++t)
+        p->threads.emplace_back([p] {
+            for (;;) {
+                std::function<void()> job;
+                {
+                    std::unique_lock<std::mutex> lk(p->mu);
+                    p->cv_work.wait(lk, [p] { return p->stop || p->next < p->queue.size(); });
+                    if (p->next >= p->queue.size()) return;      // stop requested and nothing left
+                    job = std::move(p->queue[p->next++]);
+                }
+                job();
+                {
+                    std::lock_guard<std::mutex> lk(p->mu);
+                    ++p->done;
+                }
+                p->cv_done.notify_all();
+            }
+        });
+    return p;
+}
+
+void pss_pool_destroy(pss_pool *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stop = true;
+    }
+    p->cv_work.notify_all();
+    for (auto &t : p->threads) t.join();
+    delete p;
+}
+
+int pss_pool_size(const pss_pool *p) { return p ? (int)p->threads.size() : 0; }
+
+// returns a ticket: pss_pool_wait(ticket) returns once every job submitted up to it has run
+size_t pss_pool_submit(pss_pool *p, std::function<void()> job) {
+    size_t ticket;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (p->next == p->queue.size() && p->done == p->submitted) {   // idle: recycle the queue storage
+            p->queue.clear();
+            p->next = 0;
+            p->done = p->submitted = 0;
+        }
+        p->queue.push_back(std::move(job));
+        ticket = ++p->submitted;
+    }
+    p->cv_work.notify_one();
+    return ticket;
+}
+
+void pss_pool_wait(pss_pool *p, size_t ticket) {
+    std::unique_lock<std::mutex> lk(p->mu);
+    // jobs finish out of order; waiting for `done >= ticket` is conservative only in that it may
+    // wait for unrelated earlier jobs too -- every caller here waits for whole batches
+    p->cv_done.wait(lk, [&] { return p->done >= ticket || p->submitted < ticket; });
+}
+
+__attribute__((target("avx2"))) static void widen_avx2(const uint16_t *src, int32_t *dst, size_t n) {
+    size_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31)) { dst[i] = src[i]; ++i; }
+    for (; i + 16 <= n; i += 16) {
+        __m256i a = _mm256_cvtepu16_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i)));
+        __m256i b = _mm256_cvtepu16_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 8)));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 8), b);
+    }
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+
+void pss_widen_u16(const uint16_t *src, int32_t *dst, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { widen_avx2(src, dst, n); return; }
+    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
+}

@@ -53,7 +53,8 @@ struct SmallState {
     int32_t first_unsafe;  // depth-cap: first / last read index whose admission is not
     int32_t last_unsafe;   //            provably unconstrained (else INT_MAX / -1)
     int32_t toolong;       // != 0 when a read's sequence does not fit the tile kernel's staging buffer
-    int32_t pad_[3];
+    int32_t overflow16;    // != 0 when a tile needed several passes while writing 16-bit output
+    int32_t pad_[2];
 };
 
 struct PileupArgs {
@@ -74,6 +75,7 @@ struct PileupArgs {
     int32_t *toolong;           // set when a read does not fit the staging buffers
     int32_t *out;
     int64_t out_stride;         // elements between consecutive fields of out (>= end - start)
+    int32_t narrow;             // tile kernel only: out holds uint16 elements (host transport)
     uint8_t *rowmask;
 };
 

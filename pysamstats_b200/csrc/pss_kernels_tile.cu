@@ -97,6 +97,7 @@ struct TileArgs {
     int64_t stride;            // elements between consecutive fields of `out`
     int32_t no_del;
     int32_t need_raw;          // read-level filters active: the row mask needs its own counter
+    int32_t narrow;            // out is uint16 [field][stride] (padded rows): the host entry points' transport
     int32_t *out;
     uint8_t *rowmask;
     SmallState *st;
@@ -406,25 +407,38 @@ __device__ __forceinline__ uint4 operator+(uint4 a, uint4 b) { return make_uint4
 __device__ __forceinline__ uint4 lo16(uint4 a) { return make_uint4(a.x & 0xffffu, a.y & 0xffffu, a.z & 0xffffu, a.w & 0xffffu); }
 __device__ __forceinline__ uint4 hi16(uint4 a) { return make_uint4(a.x >> 16, a.y >> 16, a.z >> 16, a.w >> 16); }
 
-template <bool ACCUM>
+enum { OUT_STORE = 0, OUT_ACCUM = 1, OUT_NARROW = 2 };   // int32 store / int32 add / 16-bit store
+
+template <int MODE>
 struct QuadOut {
-    int32_t *p;        // position 4q of the next field to write
+    // position 4q of the next field to write; int32 elements, or uint16 elements in OUT_NARROW
+    // mode (then p advances in uint16 units: the pointer is reinterpreted)
+    int32_t *p;
     int64_t stride;
-    bool vec;          // 128-bit stores allowed
+    bool vec;          // vector stores allowed
     int nvalid;        // positions of the quad inside [start, end)
     __device__ __forceinline__ void put(uint4 v) {
+        if (MODE == OUT_NARROW) {      // rows are padded and 8-byte aligned in this mode
+            uint16_t *h = reinterpret_cast<uint16_t *>(p);
+            *reinterpret_cast<uint2 *>(h) = make_uint2(v.x | (v.y << 16), v.z | (v.w << 16));
+            p = reinterpret_cast<int32_t *>(h + stride);
+            return;
+        }
         if (vec) {
-            if (ACCUM) v = v + *reinterpret_cast<const uint4 *>(p);
+            if (MODE == OUT_ACCUM) v = v + *reinterpret_cast<const uint4 *>(p);
             *reinterpret_cast<uint4 *>(p) = v;
         } else {
-            if (nvalid > 0) p[0] = (ACCUM ? p[0] : 0) + v.x;
-            if (nvalid > 1) p[1] = (ACCUM ? p[1] : 0) + v.y;
-            if (nvalid > 2) p[2] = (ACCUM ? p[2] : 0) + v.z;
-            if (nvalid > 3) p[3] = (ACCUM ? p[3] : 0) + v.w;
+            if (nvalid > 0) p[0] = (MODE == OUT_ACCUM ? p[0] : 0) + v.x;
+            if (nvalid > 1) p[1] = (MODE == OUT_ACCUM ? p[1] : 0) + v.y;
+            if (nvalid > 2) p[2] = (MODE == OUT_ACCUM ? p[2] : 0) + v.z;
+            if (nvalid > 3) p[3] = (MODE == OUT_ACCUM ? p[3] : 0) + v.w;
         }
         p += stride;
     }
-    __device__ __forceinline__ void skip(int nfields) { p += stride * nfields; }
+    __device__ __forceinline__ void skip(int nfields) {
+        if (MODE == OUT_NARROW) p = reinterpret_cast<int32_t *>(reinterpret_cast<uint16_t *>(p) + stride * nfields);
+        else p += stride * nfields;
+    }
     // w0 = not-proper-pair word (fwd | rev << 16), w1 = proper-pair word ->
     // all, fwd, rev, pp, pp_fwd, pp_rev (CountPpStrand, opt.pyx:147-168) or all, pp
     template <bool STRAND>
@@ -452,9 +466,9 @@ __device__ __forceinline__ uint4 base_count(uint4 m, uint4 mt, uint32_t rc4, uin
 
 // Writes the fields owned by (quad q, sub-part `part` of 4) and returns the quad's total read
 // count when this part computes it (part 0), for the row mask.
-template <int STAT, bool ACCUM>
+template <int STAT, int MODE>
 __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32_t *refn, int q, int part,
-                                               QuadOut<ACCUM> &O) {
+                                               QuadOut<MODE> &O) {
     uint4 all = make_uint4(0, 0, 0, 0);
     if (STAT == PSS_COVERAGE || STAT == PSS_COVERAGE_STRAND || STAT == PSS_COVERAGE_GC) {
         if (part == 0) {
@@ -511,7 +525,7 @@ __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32
     return all;
 }
 
-template <int STAT, bool ACCUM, int NT>
+template <int STAT, int MODE, int NT>
 __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *cnt, const uint32_t *raw,
                                             const uint32_t *refn, int64_t t0l, int tid) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(A.out) & 15) == 0) && ((A.stride & 3) == 0) &&
@@ -524,20 +538,22 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
         const int64_t pl = t0l + 4 * q;
         const int64_t rem = A.end - pl;
         if (rem <= 0) continue;
-        QuadOut<ACCUM> O;
-        O.p = A.out + (pl - A.start);
+        QuadOut<MODE> O;
+        O.p = (MODE == OUT_NARROW) ? reinterpret_cast<int32_t *>(reinterpret_cast<uint16_t *>(A.out) + (pl - A.start))
+                                   : A.out + (pl - A.start);
         O.stride = A.stride;
         O.nvalid = rem > 4 ? 4 : (int)rem;
         // full quads always; partial quads only when the row is padded (stride beyond the range)
         O.vec = aligned && (O.nvalid == 4 || (pl - A.start) + 4 <= A.stride);
-        uint4 all = tile_finalize<STAT, ACCUM>(cnt, refn, q, part, O);
+        uint4 all = tile_finalize<STAT, MODE>(cnt, refn, q, part, O);
         if (part == 0) {
             if (A.need_raw) all = ld4(raw, 0, q);
             uint8_t *m = A.rowmask + (pl - A.start);
-            if (O.nvalid > 0) m[0] = (all.x ? 1 : 0) | (ACCUM ? m[0] : 0);
-            if (O.nvalid > 1) m[1] = (all.y ? 1 : 0) | (ACCUM ? m[1] : 0);
-            if (O.nvalid > 2) m[2] = (all.z ? 1 : 0) | (ACCUM ? m[2] : 0);
-            if (O.nvalid > 3) m[3] = (all.w ? 1 : 0) | (ACCUM ? m[3] : 0);
+            const bool acc = MODE == OUT_ACCUM;
+            if (O.nvalid > 0) m[0] = (all.x ? 1 : 0) | (acc ? m[0] : 0);
+            if (O.nvalid > 1) m[1] = (all.y ? 1 : 0) | (acc ? m[1] : 0);
+            if (O.nvalid > 2) m[2] = (all.z ? 1 : 0) | (acc ? m[2] : 0);
+            if (O.nvalid > 3) m[3] = (all.w ? 1 : 0) | (acc ? m[3] : 0);
         }
     }
 }
@@ -691,8 +707,12 @@ k_tile(TileArgs A) {
         }
         __syncthreads();
         STAMP(6);
-        if (accum) tile_output<STAT, true, NT>(A, cnt, raw, s_refn, t0l, tid);
-        else tile_output<STAT, false, NT>(A, cnt, raw, s_refn, t0l, tid);
+        if (A.narrow) {
+            // 16-bit transport cannot add passes: flag it, the host repeats the call with int32 output
+            if (accum || more) { if (tid == 0) atomicOr(&A.st->overflow16, 1); }
+            else tile_output<STAT, OUT_NARROW, NT>(A, cnt, raw, s_refn, t0l, tid);
+        } else if (accum) tile_output<STAT, OUT_ACCUM, NT>(A, cnt, raw, s_refn, t0l, tid);
+        else tile_output<STAT, OUT_STORE, NT>(A, cnt, raw, s_refn, t0l, tid);
         STAMP(7);
 #ifdef TILE_TIMING
         if (tid == 0 && A.timing && (tile & 63) == 0) {
@@ -834,6 +854,7 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     a.ref = p.ref; a.ref_start = p.ref_start; a.ref_len = p.ref_len; a.start = p.start; a.end = p.end;
     a.stride = p.out_stride;
     a.no_del = p.no_del; a.need_raw = need_raw; a.out = p.out; a.rowmask = p.rowmask; a.st = st;
+    a.narrow = p.narrow;
     a.timing = nullptr;
 #ifdef TILE_TIMING
     static unsigned long long *tbuf = nullptr;
