@@ -182,3 +182,33 @@ def test_very_deep_single_position(ctx):
     # the depth cap at the default 8000: the first read is always admitted, then up to the cap
     out, mask = _run_host(ctx, nb, ref, 'coverage', 900, 1300)
     assert out[0][150] == 8000
+
+
+@pytest.mark.parametrize('stat', config.binned_types)
+def test_binned_synthetic_vs_oracle_and_sharded(stat, ctx, small):
+    nb, ref, reads = small
+    W = 300
+    p = ctx.binned_params(stat, 0, G, W, ref=ref, ref_start=0, ref_len=len(ref))
+    nbins = int(p.n_bins)
+    nf = len(config.value_fields_binned(stat))
+    d = dict(nb)
+    d['qual'] = d['qual_off'] = d['name_prev'] = None
+    whole = np.empty((nf, nbins), dtype=np.int32)
+    ctx.binned_host(_cabi.make_reads_struct(d), p, whole)
+    pos, F = orc.binned_packed(stat, reads, 0, G, W, W // 2, ref=ref.tobytes())
+    assert np.array_equal(whole.T, F), stat
+    # window-range shards: bin edges use the global start, every read belongs to exactly one shard
+    parts = []
+    for k_lo, k_hi in shard.plan_windows(0, G, W, 3):
+        i0, i1 = shard.window_read_range(nb['pos'], 0, W, k_lo, k_hi, nbins)
+        view = {k: (nb[k][i0:] if k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off') else nb[k])
+                for k in _cabi.READ_FIELDS}
+        view['qual'] = view['qual_off'] = view['name_prev'] = None
+        view['n_reads'], view['tid'] = i1 - i0, 0
+        s0, s1 = k_lo * W, min(G, k_hi * W)
+        ps = ctx.binned_params(stat, s0, s1, W, ref=ref, ref_start=0, ref_len=len(ref))
+        assert int(ps.n_bins) == k_hi - k_lo
+        o = np.empty((nf, k_hi - k_lo), dtype=np.int32)
+        ctx.binned_host(_cabi.make_reads_struct(view, n_reads=i1 - i0), ps, o)
+        parts.append((o,))
+    assert np.array_equal(shard.concat_shards(parts)[0], whole), stat
