@@ -30,9 +30,11 @@ struct pss_ctx {
     int64_t desc_start = -1, desc_end = -1;   // position range the tile descriptors in tdesc describe
     DevBuf hb[20];          // device copies of host batches (*_host entry points)
     DevBuf outbuf[2], maskbuf[2];
-    // narrow (16-bit) result transport of the host entry points: 3 device buffers, 3 pinned staging buffers
+    // narrow (8- / 16-bit) result transport of the host entry points: 3 device buffers, 3 pinned staging buffers
     DevBuf nbuf[3], nmask[3];
     void *hstage[3] = {nullptr, nullptr, nullptr};
+    DevBuf nflag;                       // per-buffer "a count needs more than 8 bits" flags
+    int32_t *hflag = nullptr;           // pinned mirror
     size_t hstage_bytes[3] = {0, 0, 0};
     cudaEvent_t nev_done[3] = {nullptr, nullptr, nullptr}, nev_copied[3] = {nullptr, nullptr, nullptr};
     pss_pool *pool = nullptr;
@@ -161,6 +163,8 @@ extern "C" void pss_destroy(pss_ctx *ctx) {
         if (ctx->nev_done[i]) cudaEventDestroy(ctx->nev_done[i]);
         if (ctx->nev_copied[i]) cudaEventDestroy(ctx->nev_copied[i]);
     }
+    if (ctx->nflag.p) cudaFree(ctx->nflag.p);
+    if (ctx->hflag) cudaFreeHost(ctx->hflag);
     pss_pool_destroy(ctx->pool);
     delete ctx;
 }
@@ -269,7 +273,8 @@ static cudaEvent_t next_event(pss_ctx *ctx) {
 
 // the pileup kernel (+ gc) for output positions [start, end); out[f * stride + (p - start)]
 static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *P, bool need_qual, int64_t start,
-                     int64_t end, int32_t *out, int64_t stride, uint8_t *rowmask, cudaStream_t s, bool narrow = false) {
+                     int64_t end, int32_t *out, int64_t stride, uint8_t *rowmask, cudaStream_t s, int narrow = 0,
+                     int32_t *ovf8 = nullptr) {
     int64_t npos = end - start;
     if (npos <= 0) return PSS_OK;
     // counting statistics without a base-quality filter take the tile (scatter) kernel,
@@ -294,7 +299,8 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.start = start; a.end = end;
     a.min_baseq = P->min_baseq; a.no_del = P->no_del;
     a.out = out; a.out_stride = stride; a.rowmask = rowmask;
-    a.narrow = (narrow && tile) ? 1 : 0;
+    a.narrow = tile ? narrow : 0;      // 1: uint16 columns, 2: uint8 columns + overflow flag
+    a.ovf8 = ovf8;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->timing) {
         e0 = next_event(ctx); e1 = next_event(ctx);
@@ -512,56 +518,98 @@ static int host_stat_wide(pss_ctx *ctx, const pss_reads *D, const pss_pileup_par
     return PSS_OK;
 }
 
-#define PSS_ERETRY_WIDE (-100)   // internal: a tile needed several passes, 16-bit transport cannot express it
+#define PSS_ERETRY_WIDE (-100)   // internal: a tile needed several passes, narrow transport cannot express it
 
-// Same, for the statistics of the tile kernel: the device writes 16-bit columns (every count
-// of a single-pass tile is < 65536), half the bytes cross PCIe into pinned staging buffers,
-// and the worker pool widens them into the caller's int32 columns while the next chunks are
-// computed and copied.  Three buffers rotate: compute k, copy k - 1, widen k - 2.
+// Same, for the statistics of the tile kernel.  What bounds the host path is host memory
+// traffic (measured on the GPU box: ~160 GB/s over 16 cores, scripts/host_probe.cu): every
+// result byte is written by the DMA engine into a pinned staging buffer, read back by a worker
+// and written as int32 into the caller's column.  So the device writes the NARROWEST columns
+// that hold the counts: 8-bit when every count of a position chunk is < 256 (any ordinary WGS
+// depth), else the chunk is redone with 16-bit columns (< 65536: every single-pass tile), else
+// the caller repeats the statistic on the int32 pipeline.  A quarter / half of the bytes cross
+// PCIe, and the worker pool widens them into the caller's int32 columns while the next chunks
+// are computed and copied.  Three buffers rotate: compute k, copy k - 1, widen k - 2.
 static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_params *Pd, bool q, int32_t *out,
                             uint8_t *rowmask, cudaStream_t s) {
     int rc;
     const int nf = kPileupFields[Pd->stat];
     const int64_t npos = Pd->end - Pd->start;
     int64_t chunk = ((int64_t)(128ll << 20) / (2ll * nf)) / PSS_TTILE * PSS_TTILE;
+    if (const char *hc = getenv("PSS_HOST_CHUNK"))      // positions per chunk (tests: many chunks on small inputs)
+        if (atoll(hc) > 0) chunk = (atoll(hc) + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
     if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
     if (chunk < PSS_TTILE) chunk = PSS_TTILE;
     const int64_t stride = chunk;                       // multiple of 512: rows 8-byte aligned
-    const size_t bytes = sizeof(uint16_t) * (size_t)nf * (size_t)stride;
+    const size_t bytes16 = sizeof(uint16_t) * (size_t)nf * (size_t)stride;
+    static const bool no_narrow8 = getenv("PSS_NO_NARROW8") != nullptr;
     if (!ctx->pool) ctx->pool = pss_pool_create(0);
     CU(cudaStreamSynchronize(ctx->copy_stream));        // nothing of an earlier statistic is in flight
     for (int b = 0; b < 3; ++b) {
-        if ((rc = ensure(ctx, ctx->nbuf[b], bytes)) != PSS_OK) return rc;
+        if ((rc = ensure(ctx, ctx->nbuf[b], bytes16)) != PSS_OK) return rc;
         if ((rc = ensure(ctx, ctx->nmask[b], (size_t)stride)) != PSS_OK) return rc;
-        if (ctx->hstage_bytes[b] < bytes) {
+        if (ctx->hstage_bytes[b] < bytes16) {
             if (ctx->hstage[b]) cudaFreeHost(ctx->hstage[b]);
             ctx->hstage[b] = nullptr; ctx->hstage_bytes[b] = 0;
-            CU(cudaMallocHost(&ctx->hstage[b], bytes));
-            ctx->hstage_bytes[b] = bytes;
+            CU(cudaMallocHost(&ctx->hstage[b], bytes16));
+            ctx->hstage_bytes[b] = bytes16;
         }
         if (!ctx->nev_done[b]) {
             CU(cudaEventCreateWithFlags(&ctx->nev_done[b], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&ctx->nev_copied[b], cudaEventDisableTiming));
         }
     }
+    if ((rc = ensure(ctx, ctx->nflag, 4 * sizeof(int32_t))) != PSS_OK) return rc;
+    if (!ctx->hflag) CU(cudaMallocHost((void **)&ctx->hflag, 4 * sizeof(int32_t)));
+    int32_t *dflag = (int32_t *)ctx->nflag.p;
     // clear the overflow flag of this batch's device state
     CU(cudaMemsetAsync(&((SmallState *)ctx->small.p)->overflow16, 0, sizeof(int32_t), s));
     size_t ticket[3] = {0, 0, 0};
     int64_t cstart[3] = {0, 0, 0}, clen[3] = {0, 0, 0};
+    int esz[3] = {2, 2, 2};
+    int cool = 0;          // chunks left that go straight to 16 bits after an 8-bit overflow
     pss_pool *pool = ctx->pool;
-    auto widen_chunk = [&](int b) {      // D2H of buffer b has completed: hand its rows to the pool
-        const uint16_t *src = (const uint16_t *)ctx->hstage[b];
+    // compute chunk [cs, cs + cn) into device buffer b with `e`-byte elements and copy it to staging buffer b
+    auto produce = [&](int b, int64_t cs, int64_t cn, int e) -> int {
+        if (e == 1) CU(cudaMemsetAsync(dflag + b, 0, sizeof(int32_t), s));
+        int r = run_range(ctx, D, Pd, q, cs, cs + cn, (int32_t *)ctx->nbuf[b].p, stride, (uint8_t *)ctx->nmask[b].p, s,
+                          e == 1 ? 2 : 1, dflag + b);
+        if (r != PSS_OK) return r;
+        const size_t bytes = (size_t)e * (size_t)nf * (size_t)stride;
+        CU(cudaEventRecord(ctx->nev_done[b], s));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->nev_done[b], 0));
+        CU(cudaMemcpyAsync(ctx->hstage[b], ctx->nbuf[b].p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaMemcpyAsync(rowmask + (cs - Pd->start), ctx->nmask[b].p, (size_t)cn, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (e == 1) CU(cudaMemcpyAsync(ctx->hflag + b, dflag + b, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaEventRecord(ctx->nev_copied[b], ctx->copy_stream));
+        ctx->d2h_bytes += (int64_t)(bytes + (size_t)cn);
+        cstart[b] = cs; clen[b] = cn; esz[b] = e;
+        return PSS_OK;
+    };
+    // the D2H of buffer b has been enqueued: wait for it, redo the chunk with 16 bits if its counts
+    // did not fit 8, then hand its rows to the pool
+    auto consume = [&](int b) -> int {
+        CU(cudaEventSynchronize(ctx->nev_copied[b]));
+        if (esz[b] == 1 && ctx->hflag[b]) {
+            cool = 8;
+            int r = produce(b, cstart[b], clen[b], 2);
+            if (r != PSS_OK) return r;
+            CU(cudaEventSynchronize(ctx->nev_copied[b]));
+        }
+        const uint8_t *src = (const uint8_t *)ctx->hstage[b];
         const int64_t cs = cstart[b], cn = clen[b];
+        const int e = esz[b];
         const int64_t piece = 1 << 20;
         size_t t = 0;
         for (int f = 0; f < nf; ++f)
             for (int64_t o = 0; o < cn; o += piece) {
-                const uint16_t *sp = src + (size_t)f * stride + o;
+                const uint8_t *sp = src + ((size_t)f * stride + o) * e;
                 int32_t *dp = out + (size_t)f * npos + (cs - Pd->start) + o;
                 size_t len = (size_t)((cn - o) < piece ? (cn - o) : piece);
-                t = pss_pool_submit(pool, [sp, dp, len] { pss_widen_u16(sp, dp, len); });
+                if (e == 1) t = pss_pool_submit(pool, [sp, dp, len] { pss_widen_u8(sp, dp, len); });
+                else t = pss_pool_submit(pool, [sp, dp, len] { pss_widen_u16((const uint16_t *)sp, dp, len); });
             }
         ticket[b] = t;
+        return PSS_OK;
     };
     int k = 0;
     for (int64_t cs = Pd->start; cs < Pd->end; cs += chunk, ++k) {
@@ -571,26 +619,13 @@ static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_p
             pss_pool_wait(pool, ticket[b]);                          // staging buffer b widened
             CU(cudaStreamWaitEvent(s, ctx->nev_copied[b], 0));        // device buffer b copied out
         }
-        if ((rc = run_range(ctx, D, Pd, q, cs, ce, (int32_t *)ctx->nbuf[b].p, stride, (uint8_t *)ctx->nmask[b].p, s, true)) != PSS_OK)
-            return rc;
-        CU(cudaEventRecord(ctx->nev_done[b], s));
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->nev_done[b], 0));
-        CU(cudaMemcpyAsync(ctx->hstage[b], ctx->nbuf[b].p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        CU(cudaMemcpyAsync(rowmask + (cs - Pd->start), ctx->nmask[b].p, (size_t)cn, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        CU(cudaEventRecord(ctx->nev_copied[b], ctx->copy_stream));
-        ctx->d2h_bytes += (int64_t)(bytes + (size_t)cn);
-        cstart[b] = cs; clen[b] = cn;
-        if (k >= 1) {                                                // widen the previous chunk meanwhile
-            const int pb = (k - 1) % 3;
-            CU(cudaEventSynchronize(ctx->nev_copied[pb]));
-            widen_chunk(pb);
-        }
+        int e = 1;
+        if (no_narrow8) e = 2;
+        else if (cool > 0) { e = 2; --cool; }
+        if ((rc = produce(b, cs, cn, e)) != PSS_OK) return rc;
+        if (k >= 1 && (rc = consume((k - 1) % 3)) != PSS_OK) return rc;   // widen the previous chunk meanwhile
     }
-    if (k >= 1) {
-        const int pb = (k - 1) % 3;
-        CU(cudaEventSynchronize(ctx->nev_copied[pb]));
-        widen_chunk(pb);
-    }
+    if (k >= 1 && (rc = consume((k - 1) % 3)) != PSS_OK) return rc;
     for (int b = 0; b < 3; ++b) pss_pool_wait(pool, ticket[b]);
     // a tile that needed several passes (> 65535 reads) cannot be expressed in 16 bits
     int32_t ovf = 0;
@@ -618,7 +653,6 @@ extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32
         if (P[i].end > P[i].start && (!outs[i] || !rowmasks[i])) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
     }
     if ((rc = check_reads(ctx, reads, need_qual)) != PSS_OK) return rc;
-    const int64_t npos = P[0].end - P[0].start;
     CU(cudaSetDevice(ctx->device));
     ctx->prepared = false;
     cudaStream_t s = nullptr;   // default stream for compute, ctx->copy_stream for D2H

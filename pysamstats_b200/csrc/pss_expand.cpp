@@ -1,5 +1,6 @@
 // Host side of the narrow result transport (see pss_pileup_host_multi): the counting statistics
-// come back from the device as 16-bit columns (half the PCIe bytes) and are widened here into
+// come back from the device as 8-bit or 16-bit columns (a quarter / half of the PCIe bytes and of
+// the staging traffic in host memory, which is what bounds the host path) and are widened here into
 // the caller's int32 columns by a small pool of worker threads, with non-temporal stores so the
 // host memory traffic is one read of the narrow data and one write of the wide data.
 #include <immintrin.h>
@@ -20,7 +21,10 @@ struct pss_pool {
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
     std::vector<std::function<void()>> queue;
+    std::vector<char> finished;            // per job of `queue`
     size_t next = 0, done = 0, submitted = 0;
+    size_t low = 0;                        // every job with index < low has finished
+    size_t base = 0;                       // jobs of earlier (recycled) queues: tickets stay monotonic
     bool stop = false;
 };
 
@@ -44,16 +48,20 @@ pss_pool *pss_pool_create(int n_threads) {
         p->threads.emplace_back([p] {
             for (;;) {
                 std::function<void()> job;
+                size_t idx;
                 {
                     std::unique_lock<std::mutex> lk(p->mu);
                     p->cv_work.wait(lk, [p] { return p->stop || p->next < p->queue.size(); });
                     if (p->next >= p->queue.size()) return;      // stop requested and nothing left
-                    job = std::move(p->queue[p->next++]);
+                    idx = p->next++;
+                    job = std::move(p->queue[idx]);
                 }
                 job();
                 {
                     std::lock_guard<std::mutex> lk(p->mu);
                     ++p->done;
+                    p->finished[idx] = 1;
+                    while (p->low < p->finished.size() && p->finished[p->low]) ++p->low;
                 }
                 p->cv_done.notify_all();
             }
@@ -80,12 +88,17 @@ size_t pss_pool_submit(pss_pool *p, std::function<void()> job) {
     {
         std::lock_guard<std::mutex> lk(p->mu);
         if (p->next == p->queue.size() && p->done == p->submitted) {   // idle: recycle the queue storage
+            p->base += p->queue.size();
             p->queue.clear();
+            p->finished.clear();
             p->next = 0;
             p->done = p->submitted = 0;
+            p->low = 0;
         }
         p->queue.push_back(std::move(job));
-        ticket = ++p->submitted;
+        p->finished.push_back(0);
+        ++p->submitted;
+        ticket = p->base + p->queue.size();
     }
     p->cv_work.notify_one();
     return ticket;
@@ -93,9 +106,9 @@ size_t pss_pool_submit(pss_pool *p, std::function<void()> job) {
 
 void pss_pool_wait(pss_pool *p, size_t ticket) {
     std::unique_lock<std::mutex> lk(p->mu);
-    // jobs finish out of order; waiting for `done >= ticket` is conservative only in that it may
-    // wait for unrelated earlier jobs too -- every caller here waits for whole batches
-    p->cv_done.wait(lk, [&] { return p->done >= ticket || p->submitted < ticket; });
+    // jobs finish out of order: `low` is the watermark below which every job of the current queue
+    // has finished; every job of an earlier queue has (the queue is only recycled when idle)
+    p->cv_done.wait(lk, [&] { return p->base + p->low >= ticket; });
 }
 
 __attribute__((target("avx2"))) static void widen_avx2(const uint16_t *src, int32_t *dst, size_t n) {
@@ -109,6 +122,24 @@ __attribute__((target("avx2"))) static void widen_avx2(const uint16_t *src, int3
     }
     for (; i < n; ++i) dst[i] = src[i];
     _mm_sfence();
+}
+
+__attribute__((target("avx2"))) static void widen8_avx2(const uint8_t *src, int32_t *dst, size_t n) {
+    size_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31)) { dst[i] = src[i]; ++i; }
+    for (; i + 16 <= n; i += 16) {
+        __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_cvtepu8_epi32(v));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 8), _mm256_cvtepu8_epi32(_mm_srli_si128(v, 8)));
+    }
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+
+void pss_widen_u8(const uint8_t *src, int32_t *dst, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { widen8_avx2(src, dst, n); return; }
+    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
 }
 
 void pss_widen_u16(const uint16_t *src, int32_t *dst, size_t n) {

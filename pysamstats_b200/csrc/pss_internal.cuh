@@ -75,7 +75,8 @@ struct PileupArgs {
     int32_t *toolong;           // set when a read does not fit the staging buffers
     int32_t *out;
     int64_t out_stride;         // elements between consecutive fields of out (>= end - start)
-    int32_t narrow;             // tile kernel only: out holds uint16 elements (host transport)
+    int32_t narrow;             // tile kernel only: out holds uint16 (1) / uint8 (2) elements (host transport)
+    int32_t *ovf8;              // narrow == 2: set when a count does not fit 8 bits
     uint8_t *rowmask;
 };
 

@@ -97,7 +97,8 @@ struct TileArgs {
     int64_t stride;            // elements between consecutive fields of `out`
     int32_t no_del;
     int32_t need_raw;          // read-level filters active: the row mask needs its own counter
-    int32_t narrow;            // out is uint16 [field][stride] (padded rows): the host entry points' transport
+    int32_t narrow;            // 1: out is uint16 [field][stride], 2: uint8 [field][stride] (padded rows): the host entry points' transport
+    int32_t *ovf8;             // narrow == 2: set when a count does not fit 8 bits
     int32_t *out;
     uint8_t *rowmask;
     SmallState *st;
@@ -407,17 +408,25 @@ __device__ __forceinline__ uint4 operator+(uint4 a, uint4 b) { return make_uint4
 __device__ __forceinline__ uint4 lo16(uint4 a) { return make_uint4(a.x & 0xffffu, a.y & 0xffffu, a.z & 0xffffu, a.w & 0xffffu); }
 __device__ __forceinline__ uint4 hi16(uint4 a) { return make_uint4(a.x >> 16, a.y >> 16, a.z >> 16, a.w >> 16); }
 
-enum { OUT_STORE = 0, OUT_ACCUM = 1, OUT_NARROW = 2 };   // int32 store / int32 add / 16-bit store
+enum { OUT_STORE = 0, OUT_ACCUM = 1, OUT_NARROW = 2, OUT_NARROW8 = 3 };   // int32 store / int32 add / 16-bit store / 8-bit store
 
 template <int MODE>
 struct QuadOut {
-    // position 4q of the next field to write; int32 elements, or uint16 elements in OUT_NARROW
-    // mode (then p advances in uint16 units: the pointer is reinterpreted)
+    // position 4q of the next field to write; int32 elements, or uint16 / uint8 elements in the
+    // OUT_NARROW / OUT_NARROW8 modes (then p advances in those units: the pointer is reinterpreted)
     int32_t *p;
     int64_t stride;
     bool vec;          // vector stores allowed
     int nvalid;        // positions of the quad inside [start, end)
+    uint32_t seen;     // OUT_NARROW8: OR of every value written (a bit >= 8 set: the chunk needs 16 bits)
     __device__ __forceinline__ void put(uint4 v) {
+        if (MODE == OUT_NARROW8) {     // rows are padded and 4-byte aligned in this mode
+            uint8_t *h = reinterpret_cast<uint8_t *>(p);
+            seen |= v.x | v.y | v.z | v.w;
+            *reinterpret_cast<uint32_t *>(h) = (v.x & 255u) | ((v.y & 255u) << 8) | ((v.z & 255u) << 16) | (v.w << 24);
+            p = reinterpret_cast<int32_t *>(h + stride);
+            return;
+        }
         if (MODE == OUT_NARROW) {      // rows are padded and 8-byte aligned in this mode
             uint16_t *h = reinterpret_cast<uint16_t *>(p);
             *reinterpret_cast<uint2 *>(h) = make_uint2(v.x | (v.y << 16), v.z | (v.w << 16));
@@ -436,7 +445,8 @@ struct QuadOut {
         p += stride;
     }
     __device__ __forceinline__ void skip(int nfields) {
-        if (MODE == OUT_NARROW) p = reinterpret_cast<int32_t *>(reinterpret_cast<uint16_t *>(p) + stride * nfields);
+        if (MODE == OUT_NARROW8) p = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(p) + stride * nfields);
+        else if (MODE == OUT_NARROW) p = reinterpret_cast<int32_t *>(reinterpret_cast<uint16_t *>(p) + stride * nfields);
         else p += stride * nfields;
     }
     // w0 = not-proper-pair word (fwd | rev << 16), w1 = proper-pair word ->
@@ -532,6 +542,7 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
                          (((t0l - A.start) & 3) == 0);
     // tasks = (sub-part, quad): 4 NQUAD of them (18, 18, 12, 12 fields per quad for variation_strand),
     // dealt to the threads round-robin; a warp always holds one sub-part (NQUAD is a multiple of 32)
+    uint32_t seen = 0;
 #pragma unroll 1
     for (int task = tid; task < 4 * NQUAD; task += NT) {
         const int part = task / NQUAD, q = task - part * NQUAD;
@@ -539,9 +550,11 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
         const int64_t rem = A.end - pl;
         if (rem <= 0) continue;
         QuadOut<MODE> O;
-        O.p = (MODE == OUT_NARROW) ? reinterpret_cast<int32_t *>(reinterpret_cast<uint16_t *>(A.out) + (pl - A.start))
-                                   : A.out + (pl - A.start);
+        O.p = (MODE == OUT_NARROW8) ? reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(A.out) + (pl - A.start))
+              : (MODE == OUT_NARROW) ? reinterpret_cast<int32_t *>(reinterpret_cast<uint16_t *>(A.out) + (pl - A.start))
+                                     : A.out + (pl - A.start);
         O.stride = A.stride;
+        O.seen = 0;
         O.nvalid = rem > 4 ? 4 : (int)rem;
         // full quads always; partial quads only when the row is padded (stride beyond the range)
         O.vec = aligned && (O.nvalid == 4 || (pl - A.start) + 4 <= A.stride);
@@ -555,7 +568,9 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
             if (O.nvalid > 2) m[2] = (all.z ? 1 : 0) | (acc ? m[2] : 0);
             if (O.nvalid > 3) m[3] = (all.w ? 1 : 0) | (acc ? m[3] : 0);
         }
+        if (MODE == OUT_NARROW8) seen |= O.seen;
     }
+    if (MODE == OUT_NARROW8 && (seen >> 8)) atomicOr(A.ovf8, 1);
 }
 
 // ------------------------------------------------------------------------------ the kernel
@@ -710,6 +725,7 @@ k_tile(TileArgs A) {
         if (A.narrow) {
             // 16-bit transport cannot add passes: flag it, the host repeats the call with int32 output
             if (accum || more) { if (tid == 0) atomicOr(&A.st->overflow16, 1); }
+            else if (A.narrow == 2) tile_output<STAT, OUT_NARROW8, NT>(A, cnt, raw, s_refn, t0l, tid);
             else tile_output<STAT, OUT_NARROW, NT>(A, cnt, raw, s_refn, t0l, tid);
         } else if (accum) tile_output<STAT, OUT_ACCUM, NT>(A, cnt, raw, s_refn, t0l, tid);
         else tile_output<STAT, OUT_STORE, NT>(A, cnt, raw, s_refn, t0l, tid);
@@ -854,7 +870,7 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     a.ref = p.ref; a.ref_start = p.ref_start; a.ref_len = p.ref_len; a.start = p.start; a.end = p.end;
     a.stride = p.out_stride;
     a.no_del = p.no_del; a.need_raw = need_raw; a.out = p.out; a.rowmask = p.rowmask; a.st = st;
-    a.narrow = p.narrow;
+    a.narrow = p.narrow; a.ovf8 = p.ovf8;
     a.timing = nullptr;
 #ifdef TILE_TIMING
     static unsigned long long *tbuf = nullptr;

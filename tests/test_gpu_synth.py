@@ -212,3 +212,41 @@ def test_binned_synthetic_vs_oracle_and_sharded(stat, ctx, small):
         ctx.binned_host(_cabi.make_reads_struct(view, n_reads=i1 - i0), ps, o)
         parts.append((o,))
     assert np.array_equal(shard.concat_shards(parts)[0], whole), stat
+
+
+@pytest.mark.parametrize('stat', ('coverage_strand', 'coverage_ext', 'variation_strand'))
+def test_narrow_transport_levels(stat, ctx, monkeypatch):
+    # The host entry points bring the counts back as 8-bit columns, redo a position chunk with
+    # 16-bit columns when a count does not fit, and then skip the 8-bit attempt for a few chunks:
+    # depth 20 / 300 / 20 / 600 / 20 along the range, 1024 positions per chunk.
+    monkeypatch.setenv('PSS_HOST_CHUNK', '1024')
+    rng = np.random.default_rng(7)
+    L, G = 100, 40000
+    dens = np.full(G - L, 0.2)
+    dens[9000:9600] = 3.0
+    dens[30000:30300] = 6.0
+    pos = np.repeat(np.arange(G - L), rng.poisson(dens)).astype('i4')
+    n = len(pos)
+    ref = rng.choice(list(b'ACGT'), G).astype('u1')
+    code = np.zeros(256, 'u1')
+    code[list(b'ACGT')] = (1, 2, 4, 8)
+    bases = code[ref[pos[:, None] + np.arange(L)[None, :]]]
+    sub = rng.random(bases.shape) < 0.01
+    bases[sub] = rng.choice([1, 2, 4, 8, 15], int(sub.sum()))
+    flag = (rng.choice([0, 16], n) | rng.choice([0, 3], n) | rng.choice([0, 1024], n, p=[.95, .05])).astype('u2')
+    nb = dict(n_reads=n, tid=0, pos=pos, flag=flag, mapq=np.full(n, 60, 'u1'),
+              tlen=rng.choice([-300, 300], n).astype('i4'), mtid=np.zeros(n, 'i4'), l_seq=np.full(n, L, 'i4'),
+              cigar_off=np.arange(n + 1, dtype='i8'), cigar=np.full(n, L << 4, 'u4'),
+              seq_off=np.arange(n + 1, dtype='i8') * (L // 2),
+              seq4=((bases[:, 0::2] << 4) | bases[:, 1::2]).astype('u1').ravel(),
+              qual=None, qual_off=None, name_prev=np.full(n, -1, 'i4'))
+    reads = oracle_reads_from_arrays(nb)
+    for kw in (dict(max_depth=100000), dict(max_depth=100000, stepper='nofilter', no_dup=True)):
+        h0, d0 = ctx.transfer_bytes()
+        out, mask = _run_host(ctx, nb, ref, stat, 0, G, **kw)
+        h1, d1 = ctx.transfer_bytes()
+        pos_o, F = _oracle(stat, reads, ref, 0, G, **kw)
+        _compare(out, mask, pos_o, F, 0, '%s %r' % (stat, kw))
+        assert out.max() > 255
+        # most chunks travelled as bytes: well under the 16-bit volume
+        assert d1 - d0 < 0.9 * (2 * out.size + mask.size), (d1 - d0, out.size)
