@@ -21,7 +21,7 @@ struct pss_ctx {
     char err[512] = {0};
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // moved by the *_host entry points
-    DevBuf ri, rng, qual, pair, next, small, tdesc, refpack;
+    DevBuf ri, rng, qual, pair, next, small, tdesc, refpack, bwork;
     int64_t qual_bias = 0;  // ctx->qual holds bytes [qual_bias, qual_bias + n) of the batch's qual array
     // batch prepared by pss_prepare()
     bool prepared = false;
@@ -145,7 +145,7 @@ extern "C" void pss_destroy(pss_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small, &ctx->tdesc, &ctx->refpack,
+    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small, &ctx->tdesc, &ctx->refpack, &ctx->bwork,
                      &ctx->outbuf[0], &ctx->outbuf[1], &ctx->maskbuf[0], &ctx->maskbuf[1]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->hb) if (b.p) cudaFree(b.p);
@@ -725,7 +725,8 @@ extern "C" int pss_binned(pss_ctx *ctx, const pss_reads *reads, const pss_binned
     int rc;
     if ((rc = check_binned(ctx, reads, P, out)) != PSS_OK) return rc;
     CU(cudaSetDevice(ctx->device));
-    CU(launch_binned(*reads, *P, out, (cudaStream_t)stream, &ctx->launches));
+    if ((rc = ensure(ctx, ctx->bwork, binned_work_bytes(*P))) != PSS_OK) return rc;
+    CU(launch_binned(*reads, *P, out, ctx->bwork.p, (cudaStream_t)stream, &ctx->launches));
     return PSS_OK;
 }
 
@@ -752,7 +753,8 @@ extern "C" int pss_binned_host(pss_ctx *ctx, const pss_reads *H, const pss_binne
     const int nf = kBinnedFields[P->stat];
     size_t obytes = sizeof(int32_t) * (size_t)nf * (size_t)P->n_bins;
     if ((rc = ensure(ctx, ctx->outbuf[0], obytes)) != PSS_OK) return rc;
-    CU(launch_binned(D, Pd, (int32_t *)ctx->outbuf[0].p, s, &ctx->launches));
+    if ((rc = ensure(ctx, ctx->bwork, binned_work_bytes(Pd))) != PSS_OK) return rc;
+    CU(launch_binned(D, Pd, (int32_t *)ctx->outbuf[0].p, ctx->bwork.p, s, &ctx->launches));
     CU(cudaMemcpyAsync(out, ctx->outbuf[0].p, obytes, cudaMemcpyDeviceToHost, s));
     ctx->d2h_bytes += (int64_t)obytes;
     CU(cudaStreamSynchronize(s));

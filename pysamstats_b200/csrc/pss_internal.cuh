@@ -142,7 +142,8 @@ cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, bool st
 cudaError_t launch_gc(const uint8_t *ref, int64_t ref_start, int64_t ref_len, int64_t contig_len,
                       int64_t start, int64_t end, int window_size, int window_offset, int32_t *out_gc,
                       cudaStream_t s, int64_t *launches);
-cudaError_t launch_binned(const pss_reads &R, const pss_binned_params &P, int32_t *out, cudaStream_t s,
+size_t binned_work_bytes(const pss_binned_params &P);
+cudaError_t launch_binned(const pss_reads &R, const pss_binned_params &P, int32_t *out, void *work, cudaStream_t s,
                           int64_t *launches);
 cudaError_t launch_export_admitted(const RInfo *ri, int64_t n, uint8_t *admitted, cudaStream_t s,
                                    int64_t *launches);
