@@ -279,7 +279,7 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     if (npos <= 0) return PSS_OK;
     // counting statistics without a base-quality filter take the tile (scatter) kernel,
     // everything else the generic per-position kernel
-    const bool tile = tile_kernel_supports(P->stat, P->min_baseq) && !(P->flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
+    const bool tile = tile_kernel_supports(P->stat, P->min_baseq, P->no_del) && !(P->flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
     const int tsize = tile ? PSS_TTILE : PSS_TILE;
     int64_t ntiles = (npos + tsize - 1) / tsize;
     if (ntiles > 0x7fffffff) return fail(ctx, PSS_EINVAL, "position range too large for one call");
@@ -299,7 +299,7 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.start = start; a.end = end;
     a.min_baseq = P->min_baseq; a.no_del = P->no_del;
     a.out = out; a.out_stride = stride; a.rowmask = rowmask;
-    a.narrow = tile ? narrow : 0;      // 1: uint16 columns, 2: uint8 columns + overflow flag
+    a.narrow = (tile && tile_kernel_counting(P->stat)) ? narrow : 0;      // 1: uint16 columns, 2: uint8 columns + overflow flag
     a.ovf8 = ovf8;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->timing) {
@@ -678,7 +678,7 @@ extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32
         const bool q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
         static const bool no_narrow = getenv("PSS_NO_NARROW") != nullptr;
         // (coverage_gc's gc column is written as int32 by k_gc, so it stays on the int32 pipeline)
-        const bool narrow = !no_narrow && tile_kernel_supports(P[i].stat, P[i].min_baseq) && P[i].stat != PSS_COVERAGE_GC &&
+        const bool narrow = !no_narrow && tile_kernel_counting(P[i].stat) && P[i].min_baseq <= 0 && P[i].stat != PSS_COVERAGE_GC &&
                             !(P[i].flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
         if (narrow) {
             rc = host_stat_narrow(ctx, &D, &Pd, q, outs[i], rowmasks[i], s);

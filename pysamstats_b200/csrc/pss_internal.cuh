@@ -131,7 +131,8 @@ cudaError_t launch_overlap(const pss_reads &R, const RInfo *ri, uint8_t *qual_wo
                            int32_t *name_next, cudaStream_t s, int64_t *launches);
 cudaError_t launch_tile_ranges(const RInfo *ri, int64_t n, const SmallState *st, int64_t start,
                                int64_t ntiles, int tile, int2 *rng, cudaStream_t s, int64_t *launches);
-bool tile_kernel_supports(int stat, int min_baseq);
+bool tile_kernel_supports(int stat, int min_baseq, int no_del);
+bool tile_kernel_counting(int stat);
 size_t tile_desc_bytes(int64_t ntiles);
 size_t tile_refpack_bytes(int64_t ntiles);
 // e0 / e1 (may be NULL) are recorded immediately before / after the tile kernel itself

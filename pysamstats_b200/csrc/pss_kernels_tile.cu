@@ -88,6 +88,8 @@ struct TileArgs {
     const uint32_t *cigar;
     const uint8_t *seq4;
     const int64_t *seq_off;
+    const uint8_t *qual;       // quality kinds: qualities after the overlap rewrite
+    const int64_t *qual_off;
     const TileDesc *desc;
     const uint32_t *refpack;   // REFN_WORDS words per tile (+ pad), KIND_VAR only
     const uint32_t *tflags;    // per tile, bit 0: a reference position of the tile has no 4-bit code (KIND_VAR)
@@ -130,6 +132,7 @@ struct TileCtx {
     const uint32_t *seqw;   // staged sequence bytes viewed as words
     const uint32_t *refn;   // reference tile, 4-bit codes, first position in the top nibble
     const uint8_t *ref;     // ASCII reference, for the slow path
+    const uint8_t *qual;    // staged base qualities (quality kinds only)
     int64_t ref_start, ref_len;
     int t0, t1;             // tile position range (t1 = t0 + TT)
     int no_del;
@@ -163,15 +166,32 @@ __device__ __forceinline__ void interval_add(uint32_t *arr, int x, int l, int t0
 //   mmc[20 + 4 c + b]  point: mismatching bases of class c = A, C, G, T, N
 // A position's A count is mmc[A] + (reference is A ? matches : 0), etc..
 
-__device__ __forceinline__ void var_mismatch(const TileCtx &T, int bank, int p, int code) {
-    const int pp = bank >> 1;
-    const uint32_t inc = half_inc(bank);
-    uint32_t *m = T.cnt + (W_MATCH + pp) * TT + p;
+// Counter layouts of the read walk below.  LayVar: the variation statistics, 16-bit counter pairs
+// (bank >> 1 selects the word array, the strand the half).  LayBqx: baseq_ext(_strand), one
+// 32-bit word array per bank (so any depth fits one pass; root mean squares are not additive
+// over passes) and the squared qualities of mismatching bases as 64-bit point sums.
+struct LayVar { static const bool PACKED = true, VAR = true; enum { ALL = W_ALL, MATCH = W_MATCH, DEL = W_DEL, INS = W_INS, MMT = W_MMT }; };
+struct LayBqx { static const bool PACKED = false, VAR = false; enum { ALL = 0, MATCH = 4, DEL = 0, INS = 0, MMT = 8, SQMM = 20 }; };
+template <class L> __device__ __forceinline__ uint32_t *carr(const TileCtx &T, int group, int bank) {
+    return T.cnt + (group + (L::PACKED ? (bank >> 1) : bank)) * TT;
+}
+template <class L> __device__ __forceinline__ uint32_t cinc(int bank) { return L::PACKED ? half_inc(bank) : 1u; }
+
+// qidx: index of the base's quality in T.qual (LayBqx), < 0: no quality (reads without sequence)
+template <class L>
+__device__ __forceinline__ void var_mismatch(const TileCtx &T, int bank, int p, int code, int qidx) {
+    const uint32_t inc = cinc<L>(bank);
+    uint32_t *m = carr<L>(T, L::MATCH, bank) + p;
     atomicAdd(m, 0u - inc);
     if (p + 1 < TT) atomicAdd(m + 1, inc);
-    atomicAdd(T.cnt + (W_MMT + pp) * TT + p, inc);
-    const int c = mm_class(code);
-    if (c < 5) atomicAdd(T.cnt + (W_MMC + 2 * c + pp) * TT + p, inc);
+    atomicAdd(carr<L>(T, L::MMT, bank) + p, inc);
+    if (L::VAR) {
+        const int c = mm_class(code);
+        if (c < 5) atomicAdd(T.cnt + (W_MMC + 2 * c + (bank >> 1)) * TT + p, inc);
+    } else {
+        const unsigned long long q = qidx >= 0 ? T.qual[qidx] : 0;
+        if (q) atomicAdd(reinterpret_cast<unsigned long long *>(T.cnt + LayBqx::SQMM * TT) + bank * TT + p, q * q);
+    }
 }
 
 struct VarCursor {        // per-thread walk state
@@ -181,11 +201,13 @@ struct VarCursor {        // per-thread walk state
     int rn;               // tile-relative reference index of the next base of the current span
     int rem;              // bases left in the current span (inside the tile)
     uint32_t sn;          // nibble index of the next base in the staged sequence stream
+    int qd;               // query index of a base = its tile-relative position + qd (current span)
     int w0, wstep;        // this thread owns the 8-base words w0/8, w0/8 + wstep/8, ... of every span
 };
 
 // Advance to the next aligned span that overlaps the tile, applying the side effects of the
 // ops passed on the way (intervals of D spans, insertion points, the span's match interval).
+template <class L>
 __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, int bank, uint32_t sn0, bool fx) {
     while (c.k < c.nc && c.x < T.t1) {
         const uint32_t w = c.cg[c.k];
@@ -196,16 +218,16 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
             c.x += l; c.y += l;
             if (x + l > T.t0) {
                 const int a = max(x - T.t0, 0), b = min(x + l - T.t0, TT);
-                uint32_t *mt = T.cnt + (W_MATCH + (bank >> 1)) * TT;
-                const uint32_t inc = half_inc(bank);
+                uint32_t *mt = carr<L>(T, L::MATCH, bank);
+                const uint32_t inc = cinc<L>(bank);
                 if (fx) {
                     atomicAdd(mt + a, inc);
                     if (b < TT) atomicAdd(mt + b, 0u - inc);
-                    if (T.no_del) interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, x, l, T.t0, inc);   // D / N spans do not count
+                    if (T.no_del) interval_add(carr<L>(T, L::ALL, bank), x, l, T.t0, inc);   // D / N spans do not count
                 }
                 // htslib indel > 0 at the last base of the op (A.1), opt.pyx:501
                 const int li = x + l - 1 - T.t0;
-                if (fx && k + 1 < c.nc && li >= 0 && li < TT) {
+                if (L::VAR && fx && k + 1 < c.nc && li >= 0 && li < TT) {
                     const uint32_t w2 = c.cg[k + 1];
                     const int op2 = w2 & 15;
                     bool ins = false;
@@ -220,16 +242,17 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
                         }
                         ins = l3 > 0;
                     }
-                    if (ins) atomicAdd(T.cnt + (W_INS + (bank >> 1)) * TT + li, inc);
+                    if (ins) atomicAdd(carr<L>(T, L::INS, bank) + li, inc);
                 }
+                c.qd = y + T.t0 - x;
                 c.rn = a + c.w0; c.rem = b - a - c.w0;
                 c.sn = sn0 + (uint32_t)(y + (a + T.t0 - x) + c.w0);
                 if (c.rem > 0) return true;
                 continue;                      // this part owns no word of the span
             }
         } else if (op == OP_D || op == OP_N) {
-            if (fx && op == OP_D && !T.no_del && c.x + l > T.t0)
-                interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, c.x, l, T.t0, half_inc(bank));
+            if (L::VAR && fx && op == OP_D && !T.no_del && c.x + l > T.t0)
+                interval_add(carr<L>(T, L::DEL, bank), c.x, l, T.t0, cinc<L>(bank));
             c.x += l;
         } else if (op == OP_I || op == OP_S) c.y += l;
     }
@@ -238,18 +261,20 @@ __device__ __forceinline__ bool var_next_span(const TileCtx &T, VarCursor &c, in
 
 // `part` of `nparts` threads share a read: part k compares the 8-base words k, k + nparts, ... of
 // every aligned span; part 0 also applies the interval / point side effects.
+// qb: index of the read's first base quality in T.qual (LayBqx only)
+template <class L>
 __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, const RInfo &r, uint32_t sn0, uint32_t *raw,
-                                         int part, int nparts) {
+                                         int part, int nparts, int qb = 0) {
     const uint32_t cls = r.cls;
     if (!(cls & CLS_ADMITTED)) return;
     const bool fx = part == 0;
     if (raw && fx) interval_add(raw, r.pos, r.end - r.pos, T.t0, 1u);
     if (!(cls & CLS_COUNTED)) return;
     const int bank = cls & 3u;
-    const uint32_t inc = half_inc(bank);
-    if (!T.no_del && fx) interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, r.pos, r.end - r.pos, T.t0, inc);   // M, D and N all count
+    const uint32_t inc = cinc<L>(bank);
+    if (!T.no_del && fx) interval_add(carr<L>(T, L::ALL, bank), r.pos, r.end - r.pos, T.t0, inc);   // M, D and N all count
     if (cls & CLS_NOREF) {   // mapped, CIGAR consumes no reference: one deletion event at pos
-        if (!T.no_del && fx) interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, r.pos, 1, T.t0, inc);
+        if (L::VAR && !T.no_del && fx) interval_add(carr<L>(T, L::DEL, bank), r.pos, 1, T.t0, inc);
         return;
     }
     VarCursor c;
@@ -260,31 +285,32 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
     if (simple) {
         const int a = max(r.pos - T.t0, 0), b = min(r.end - T.t0, TT);
         if (a < b && fx) {
-            uint32_t *mt = T.cnt + (W_MATCH + (bank >> 1)) * TT;
+            uint32_t *mt = carr<L>(T, L::MATCH, bank);
             atomicAdd(mt + a, inc);
             if (b < TT) atomicAdd(mt + b, 0u - inc);
-            if (T.no_del) interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, r.pos, r.end - r.pos, T.t0, inc);
+            if (T.no_del) interval_add(carr<L>(T, L::ALL, bank), r.pos, r.end - r.pos, T.t0, inc);
         }
+        c.qd = T.t0 - r.pos;
         c.rn = a + c.w0; c.rem = b - a - c.w0; c.sn = sn0 + (uint32_t)(a + T.t0 - r.pos + c.w0);
         have = c.rem > 0;
-    } else have = var_next_span(T, c, bank, sn0, fx);
+    } else have = var_next_span<L>(T, c, bank, sn0, fx);
     const bool hasseq = cls & CLS_HASSEQ;
     if (!hasseq || T.slow) {
         while (have) {
             const int n8 = min(c.rem, 8);
             if (!hasseq) {       // no sequence: every base is a mismatch of no class (opt.pyx:2146-2147)
-                for (int i = 0; i < n8; ++i) var_mismatch(T, bank, c.rn + i, 0);
+                for (int i = 0; i < n8; ++i) var_mismatch<L>(T, bank, c.rn + i, 0, -1);
             } else {             // a reference position of this tile has no 4-bit code
                 for (int i = 0; i < n8; ++i) {
                     const uint32_t k = c.sn + i;
                     const int code = (T.seqw[k >> 3] >> (((k & 7) ^ 1) << 2)) & 15;   // byte k / 2, high nibble first
                     const int64_t ro = (int64_t)T.t0 + c.rn + i - T.ref_start;
                     const int rc = (T.ref && ro >= 0 && ro < T.ref_len) ? c_refcode[__ldg(T.ref + ro)] : 16;
-                    if (code != rc) var_mismatch(T, bank, c.rn + i, code);
+                    if (code != rc) var_mismatch<L>(T, bank, c.rn + i, code, qb + c.rn + i + c.qd);
                 }
             }
             c.rn += c.wstep; c.sn += c.wstep; c.rem -= c.wstep;
-            if (c.rem <= 0) have = simple ? false : var_next_span(T, c, bank, sn0, fx);
+            if (c.rem <= 0) have = simple ? false : var_next_span<L>(T, c, bank, sn0, fx);
         }
         return;
     }
@@ -307,6 +333,7 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
         uint32_t xr = sw ^ __funnelshift_l(r1, r0, rsh);
         if (c.rem < 8) xr &= 0xffffffffu << ((8 - c.rem) << 2);
         const int p0 = c.rn;
+        const int qd0 = c.qd;
         c.rn += c.wstep; c.rem -= c.wstep;
         const bool in_span = c.rem > 0;
         if (in_span) {
@@ -315,11 +342,11 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
         }
         while (xr) {
             const int lz = __clz(xr) >> 2, sh = 28 - (lz << 2);
-            var_mismatch(T, bank, p0 + lz, (sw >> sh) & 15);
+            var_mismatch<L>(T, bank, p0 + lz, (sw >> sh) & 15, qb + p0 + lz + qd0);
             xr &= ~(0xfu << sh);
         }
         if (!in_span) {
-            have = simple ? false : var_next_span(T, c, bank, sn0, fx);
+            have = simple ? false : var_next_span<L>(T, c, bank, sn0, fx);
             if (have) VAR_SPAN_BEGIN();
         }
     }
@@ -642,7 +669,7 @@ k_tile(TileArgs A) {
 
     TileCtx T;
     T.cnt = cnt; T.seqw = reinterpret_cast<const uint32_t *>(s_seq); T.refn = s_refn;
-    T.ref = A.ref; T.ref_start = A.ref_start; T.ref_len = A.ref_len;
+    T.ref = A.ref; T.qual = nullptr; T.ref_start = A.ref_start; T.ref_len = A.ref_len;
     T.t0 = (int)t0l; T.t1 = T.t0 + TT; T.no_del = A.no_del; T.slow = (d.flags & 1u) != 0;
     uint32_t *rawp = A.need_raw ? raw : nullptr;
 
@@ -677,7 +704,7 @@ k_tile(TileArgs A) {
                     const RInfo r = s_ri[tid - part * n];
                     const long long ciglo = s_ciglo;
                     const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
-                    var_read(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
+                    var_read<LayVar>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
                 }
             } else if (tid < n) cover_read<KIND>(T, A, s_ri[tid], rawp);
             in_pass += n;
@@ -739,6 +766,399 @@ k_tile(TileArgs A) {
         if (!more) break;
         accum = true;
         __syncthreads();           // everyone is done reading the counters before they are zeroed
+    }
+}
+
+// ------------------------------------------------------------------ the quality kinds
+//
+// mapq(_strand), baseq(_strand), baseq_ext(_strand) (opt.pyx:912-1462) when min_baseq == 0.
+// Their sums are not all interval adds: max(mapq) and the per-base sum of squared base
+// qualities depend on every (read, position) event.  k_tileq splits the work of a tile in two
+// kinds of passes over the same staged reads:
+//   scatter  one read per thread (baseq_ext: the XOR read walk of the variation kernel):
+//            everything constant along a span as +1 / -1 in 32-bit difference arrays per bank
+//            (reads, non-deletion events, mapq == 0, mapq^2 as two byte planes), mismatching
+//            bases as point updates (count and squared quality);
+//   gather   position-owned, no atomics in the loop: a warp owns 128 consecutive positions
+//            (4 per lane) and one parity of the reads, walks the reads that reach its window
+//            in file order and accumulates max(mapq) / sum(q^2) per bank in registers; the
+//            registers are folded into shared-memory arrays once per tile.
+// Counters are full 32-bit words (64-bit for the squared sums), so a tile is always a single
+// pass whatever its depth: root mean squares are not additive over passes.
+// rec() is fused as in k_tile; the fp64 rootmean (opt.pyx:2159-2163) is evaluated per field.
+
+enum { KIND_MAPQ = 3, KIND_BQ = 4, KIND_BQX = 5 };
+#define QNT 256
+#define QCH 160                        // reads staged per chunk (a 512-position tile of 30x / 150 bp has ~135 candidates)
+#define QSEQ_BYTES (QCH * 76 + 64)
+#define QQUAL_BYTES (QCH * 152 + 64)
+#define QCIG_WORDS 256
+
+// word arrays of TT (bank = rev | pp << 1):
+//   KIND_MAPQ  n[0..3] nz[4..7] sqlo[8..11] sqhi[12..15] (difference arrays)  max[16..19]
+//   KIND_BQ    n[0..3] nnd[4..7] (difference arrays)  sq64[8..15]
+//   KIND_BQX   n[0..3] match[4..7] (difference arrays)  mmt[8..11]  sq64[12..19]  sqmm64[20..27]   (LayBqx)
+template <int KIND> struct QKind;
+template <> struct QKind<KIND_MAPQ> { static const int NDIFF = 16, NWORDS = 20, SQ = 0; static const bool QUAL = false, SEQ = false, CIG = false; };
+template <> struct QKind<KIND_BQ> { static const int NDIFF = 8, NWORDS = 16, SQ = 8; static const bool QUAL = true, SEQ = false, CIG = true; };
+template <> struct QKind<KIND_BQX> { static const int NDIFF = 8, NWORDS = 28, SQ = 12; static const bool QUAL = true, SEQ = true, CIG = true; };
+
+struct QSmem {       // byte offsets into the dynamic shared memory
+    int raw, ri, qoff, refn, seq, qual, cig, total;
+};
+template <int KIND>
+__host__ __device__ constexpr QSmem q_layout() {
+    QSmem L{};
+    int o = QKind<KIND>::NWORDS * TT * 4;
+    L.raw = o; o += TT * 4;
+    L.ri = o; o += QCH * 32;
+    L.qoff = o; if (QKind<KIND>::QUAL) o += (QCH + 4) * 8;
+    L.refn = o; if (QKind<KIND>::SEQ) o += (REFN_WORDS + 4) * 4;
+    L.seq = o; if (QKind<KIND>::SEQ) o += QSEQ_BYTES + 32;
+    L.qual = o; if (QKind<KIND>::QUAL) o += QQUAL_BYTES + 32;
+    L.cig = o; if (QKind<KIND>::CIG) o += (QCIG_WORDS + 8) * 4;
+    L.total = (o + 15) & ~15;
+    return L;
+}
+
+__device__ __forceinline__ void six32(const uint32_t *b, uint32_t *o6) {   // CountPpStrand order from the banks
+    o6[0] = b[0] + b[1] + b[2] + b[3]; o6[1] = b[0] + b[2]; o6[2] = b[1] + b[3]; o6[3] = b[2] + b[3]; o6[4] = b[2]; o6[5] = b[3];
+}
+__device__ __forceinline__ void six64(const unsigned long long *b, unsigned long long *o6) {
+    o6[0] = b[0] + b[1] + b[2] + b[3]; o6[1] = b[0] + b[2]; o6[2] = b[1] + b[3]; o6[3] = b[2] + b[3]; o6[4] = b[2]; o6[5] = b[3];
+}
+__device__ __forceinline__ int q_rootmean(unsigned long long sq, uint32_t n) {
+    return n > 0 ? (int)rint(sqrt((double)sq / (double)n)) : 0;   // opt.pyx:2159-2163
+}
+
+// one aligned span [x, x + l) of a read whose first base is query index y: the lanes' four positions
+template <int BANK>
+__device__ __forceinline__ void q_gather_span(uint32_t (&acc)[4][4], const uint8_t *qual, int p0, int x, int l, int y) {
+    const int off0 = p0 - x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int off = off0 + i;
+        if ((unsigned)off < (unsigned)l) {
+            const uint32_t q = qual[y + off];
+            acc[BANK][i] += q * q;
+        }
+    }
+}
+
+template <int KIND, int STAT>
+__global__ void __launch_bounds__(QNT, KIND == KIND_BQX ? 2 : 3)
+k_tileq(TileArgs A) {
+    constexpr QSmem L = q_layout<KIND>();
+    constexpr int NWARPS = QNT / 32;
+    using K = QKind<KIND>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *raw = reinterpret_cast<uint32_t *>(smem + L.raw);
+    RInfo *s_ri = reinterpret_cast<RInfo *>(smem + L.ri);
+    long long *s_qoff = reinterpret_cast<long long *>(smem + L.qoff);
+    uint32_t *s_refn = reinterpret_cast<uint32_t *>(smem + L.refn);
+    uint8_t *s_seq = smem + L.seq;
+    uint8_t *s_qual = smem + L.qual;
+    uint32_t *s_cig = reinterpret_cast<uint32_t *>(smem + L.cig);
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_n;
+    __shared__ long long s_seqlo, s_quallo, s_qofflo, s_ciglo;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int64_t t0l = A.start + (int64_t)tile * TT;
+    int dx, dy;
+    uint32_t dflags = 0;
+    {
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile));
+        dx = (int)d0.x; dy = (int)d0.y;
+        if (K::SEQ) dflags = __ldg(A.tflags + tile);
+    }
+    // thread 0 sizes a chunk (sequence / quality spans must fit the staging buffers) and issues its bulk copies
+    auto issue = [&](int cb, bool first) {
+        int n = min(QCH, dy - cb);
+        uint32_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+        const uint8_t *p1 = nullptr, *p2 = nullptr, *p3 = nullptr, *p4 = nullptr;
+        long long slo = 0, shi = 0, qlo = 0, qhi = 0;
+        while (n > 0) {
+            if (K::SEQ) { slo = A.seq_off[cb]; shi = A.seq_off[cb + n]; }
+            if (K::QUAL) { qlo = A.qual_off[cb]; qhi = A.qual_off[cb + n]; }
+            if (shi - slo + 32 <= QSEQ_BYTES && qhi - qlo + 32 <= QQUAL_BYTES) break;
+            if (n == 1) { atomicOr(&A.st->toolong, 1); n = 0; }
+            else n >>= 1;
+        }
+        s_ciglo = -1;
+        if (n > 0) {
+            if (K::SEQ) stage_span(A.seq4, slo, shi, 1, &p1, &b1, &s_seqlo);
+            if (K::QUAL) {
+                stage_span(A.qual, qlo, qhi, 1, &p2, &b2, &s_quallo);
+                stage_span(A.qual_off, (long long)cb, (long long)cb + n, 8, &p3, &b3, &s_qofflo);
+            }
+            if (K::CIG) {
+                const long long clo = A.ri[cb].cigar_off, chi = A.ri[cb + n - 1].cigar_off + A.ri[cb + n - 1].n_cigar;
+                if (chi > clo && chi - clo + 8 <= QCIG_WORDS) stage_span(A.cigar, clo, chi, 4, &p4, &b4, &s_ciglo);
+            }
+        }
+        s_n = n;
+        fence_proxy_async();
+        if (n > 0) {
+            const uint32_t rb = (K::SEQ && first) ? (REFN_WORDS + 4) * 4 : 0;
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)n * (uint32_t)sizeof(RInfo) + b1 + b2 + b3 + b4 + rb);
+            bulk_g2s(s_ri, A.ri + cb, (uint32_t)n * (uint32_t)sizeof(RInfo), &s_bar);
+            if (b1) bulk_g2s(s_seq, p1, b1, &s_bar);
+            if (b2) bulk_g2s(s_qual, p2, b2, &s_bar);
+            if (b3) bulk_g2s(s_qoff, p3, b3, &s_bar);
+            if (b4) bulk_g2s(s_cig, p4, b4, &s_bar);
+            if (rb) bulk_g2s(s_refn, A.refpack + (size_t)tile * REFN_WORDS, rb, &s_bar);
+        } else mbar_arrive_expect_tx(&s_bar, 0);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        issue(dx, true);
+    }
+    {   // zero the counters (+ raw)
+        const int nw4 = (K::NWORDS + 1) * TT / 4;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < nw4; k += QNT) reinterpret_cast<uint4 *>(cnt)[k] = z;
+    }
+    TileCtx T;
+    T.cnt = cnt; T.seqw = reinterpret_cast<const uint32_t *>(s_seq); T.refn = s_refn;
+    T.ref = A.ref; T.qual = s_qual; T.ref_start = A.ref_start; T.ref_len = A.ref_len;
+    T.t0 = (int)t0l; T.t1 = T.t0 + TT; T.no_del = A.no_del; T.slow = (dflags & 1u) != 0;
+    uint32_t *rawp = A.need_raw ? raw : nullptr;
+    __syncthreads();           // barrier initialised, counters zeroed
+    const int maxspan = A.st->maxspan;
+
+    // gather state: this warp's window and read parity; per bank, per owned position
+    const int gw0 = T.t0 + (warp & 3) * 128, gw1 = gw0 + 128, gpar = warp >> 2;
+    const int gp0 = gw0 + 4 * lane;
+    uint32_t acc[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[b][i] = 0;
+
+    uint32_t parity = 0;
+    for (int cb = dx; cb < dy;) {
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
+        const int n = s_n;
+        if (n == 0) break;
+        const long long ciglo = s_ciglo, quallo = K::QUAL ? s_quallo : 0;
+        const int qskew = K::QUAL ? (int)(cb - s_qofflo) : 0;
+        // ---- scatter ------------------------------------------------------------------------
+        if (KIND == KIND_BQX) {
+            const int nparts = min(4, QNT / n);
+            const int part = tid / n;
+            if (part < nparts) {
+                const int j = tid - part * n;
+                const RInfo r = s_ri[j];
+                const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
+                var_read<LayBqx>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts,
+                                 (int)(s_qoff[j + qskew] - quallo));
+            }
+        } else if (tid < n) {
+            const RInfo r = s_ri[tid];
+            const uint32_t cls = r.cls;
+            if (cls & CLS_ADMITTED) {
+                if (rawp) interval_add(rawp, r.pos, r.end - r.pos, T.t0, 1u);
+                if (cls & CLS_COUNTED) {
+                    const int bank = cls & 3u;
+                    if (KIND == KIND_MAPQ) {       // every event of the column counts, deletions included (opt.pyx:927-937)
+                        const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u;
+                        interval_add(cnt + bank * TT, r.pos, r.end - r.pos, T.t0, 1u);
+                        if (q == 0) interval_add(cnt + (4 + bank) * TT, r.pos, r.end - r.pos, T.t0, 1u);
+                        else {
+                            const uint32_t sq = q * q;
+                            if (sq & 255u) interval_add(cnt + (8 + bank) * TT, r.pos, r.end - r.pos, T.t0, sq & 255u);
+                            if (sq >> 8) interval_add(cnt + (12 + bank) * TT, r.pos, r.end - r.pos, T.t0, sq >> 8);
+                        }
+                    } else {                       // KIND_BQ: n counts every event, nnd the non-deletions (opt.pyx:1108-1112)
+                        if (!T.no_del) interval_add(cnt + bank * TT, r.pos, r.end - r.pos, T.t0, 1u);
+                        if (cls & CLS_SIMPLE) interval_add(cnt + (4 + bank) * TT, r.pos, r.end - r.pos, T.t0, 1u);
+                        else if (!(cls & CLS_NOREF)) {
+                            const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
+                            const int nc = (int)r.n_cigar;
+                            int x = r.pos;
+                            for (int k = 0; k < nc && x < T.t1; ++k) {
+                                const uint32_t w = cg[k];
+                                const int op = w & 15, l = (int)(w >> 4);
+                                if (op_is_match(op)) {
+                                    if (x + l > T.t0) interval_add(cnt + (4 + bank) * TT, x, l, T.t0, 1u);
+                                    x += l;
+                                } else if (op == OP_D || op == OP_N) x += l;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // the lanes of a warp leave the scatter at different times; the gather below is warp-uniform
+        // work and must run once per warp, not once per group of lanes that drifted apart
+        __syncwarp();
+        // ---- gather -------------------------------------------------------------------------
+        {
+            int j;
+            {   // first read of the chunk that can reach this warp's window
+                int lo = 0, hi = n;
+                const int key = gw0 - maxspan + 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_ri[mid].pos < key) lo = mid + 1; else hi = mid; }
+                j = lo + (((lo ^ cb) & 1) != gpar);     // parity of the read's index in the batch
+            }
+            for (; j < n; j += 2) {
+                const uint4 h = *reinterpret_cast<const uint4 *>(&s_ri[j]);     // pos, end, cls, n_cigar
+                const int rpos = (int)h.x, rend = (int)h.y;
+                const uint32_t cls = h.z;
+                if (rpos >= gw1) break;
+                if (rend <= gw0 || !(cls & CLS_COUNTED)) continue;
+                const int bank = cls & 3u;
+                if (KIND == KIND_MAPQ) {
+                    const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u;
+                    if (q == 0) continue;
+                    const int off0 = gp0 - rpos, l = rend - rpos;
+#define QMAX(B) _Pragma("unroll") for (int i = 0; i < 4; ++i) if ((unsigned)(off0 + i) < (unsigned)l) acc[B][i] = max(acc[B][i], q);
+                    switch (bank) {
+                    case 0: QMAX(0) break;
+                    case 1: QMAX(1) break;
+                    case 2: QMAX(2) break;
+                    default: QMAX(3) break;
+                    }
+#undef QMAX
+                } else {
+                    if (!(cls & CLS_HASSEQ) || (cls & CLS_NOREF)) continue;     // quality 0 / no base at all
+                    const uint8_t *qual = s_qual + (s_qoff[j + qskew] - quallo);
+#define QSPAN(B, x, l, y) q_gather_span<B>(acc, qual, gp0, x, l, y)
+#define QSPANS(x, l, y) do { switch (bank) { case 0: QSPAN(0, x, l, y); break; case 1: QSPAN(1, x, l, y); break; \
+                                             case 2: QSPAN(2, x, l, y); break; default: QSPAN(3, x, l, y); break; } } while (0)
+                    if (cls & CLS_SIMPLE) QSPANS(rpos, rend - rpos, 0);
+                    else {
+                        const long long co = (long long)(((uint64_t)s_ri[j].cigar_off));
+                        const uint32_t *cg = ciglo >= 0 ? s_cig + (co - ciglo) : A.cigar + co;
+                        const int nc = (int)h.w;
+                        int x = rpos, y = 0;
+                        for (int k = 0; k < nc && x < gw1; ++k) {
+                            const uint32_t w = cg[k];
+                            const int op = w & 15, l = (int)(w >> 4);
+                            if (op_is_match(op)) {
+                                if (x + l > gw0) QSPANS(x, l, y);
+                                x += l; y += l;
+                            } else if (op == OP_D || op == OP_N) x += l;
+                            else if (op == OP_I || op == OP_S) y += l;
+                        }
+                    }
+#undef QSPANS
+#undef QSPAN
+                }
+            }
+        }
+        cb += n;
+        if (cb >= dy) break;
+        __syncthreads();                       // staging buffers free again
+        if (tid == 0) issue(cb, false);
+    }
+    // fold the gather registers into the shared arrays (two warps own each position)
+    {
+        const int pi = (warp & 3) * 128 + 4 * lane;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (acc[b][i]) {
+                    if (KIND == KIND_MAPQ) atomicMax(cnt + (16 + b) * TT + pi + i, acc[b][i]);
+                    else atomicAdd(reinterpret_cast<unsigned long long *>(cnt + K::SQ * TT) + b * TT + pi + i,
+                                   (unsigned long long)acc[b][i]);
+                }
+    }
+    __syncthreads();
+    {   // prefix sums of the difference arrays (+ raw)
+        const int nscan = K::NDIFF + (A.need_raw ? 1 : 0);
+        for (int a = warp; a < nscan; a += NWARPS) warp_scan_array(a < K::NDIFF ? cnt + a * TT : raw, lane);
+    }
+    __syncthreads();
+    // ---- rec(): one position per thread and iteration, 128-byte rows per warp and field ------------
+    const unsigned long long *sq64 = reinterpret_cast<const unsigned long long *>(cnt + K::SQ * TT);
+    const int64_t st = A.stride;
+#pragma unroll 1
+    for (int p = tid; p < TT; p += QNT) {
+        const int64_t pl = t0l + p;
+        if (pl >= A.end) break;
+        int32_t *o = A.out + (pl - A.start);
+        uint32_t nb[4], N[6];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) nb[b] = cnt[b * TT + p];
+        if (KIND == KIND_MAPQ) {
+            uint32_t zb[4], mb[4], Z[6];
+            unsigned long long sb[4], S[6];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                zb[b] = cnt[(4 + b) * TT + p];
+                sb[b] = (unsigned long long)cnt[(8 + b) * TT + p] + ((unsigned long long)cnt[(12 + b) * TT + p] << 8);
+                mb[b] = cnt[(16 + b) * TT + p];
+            }
+            six32(nb, N); six32(zb, Z); six64(sb, S);
+            const uint32_t M[6] = {max(max(mb[0], mb[1]), max(mb[2], mb[3])), max(mb[0], mb[2]), max(mb[1], mb[3]),
+                                   max(mb[2], mb[3]), mb[2], mb[3]};
+            if (STAT == PSS_MAPQ) {
+                o[0] = N[0]; o[st] = N[3]; o[2 * st] = Z[0]; o[3 * st] = Z[3];
+                o[4 * st] = q_rootmean(S[0], N[0]); o[5 * st] = q_rootmean(S[3], N[3]);
+                o[6 * st] = M[0]; o[7 * st] = M[3];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    o[k * st] = N[k]; o[(6 + k) * st] = Z[k];
+                    o[(12 + k) * st] = q_rootmean(S[k], N[k]); o[(18 + k) * st] = M[k];
+                }
+            }
+        } else {
+            uint32_t db[4], D[6];
+            unsigned long long sb[4], S[6];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) sb[b] = sq64[b * TT + p];
+            six64(sb, S);
+            if (KIND == KIND_BQ) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) db[b] = cnt[(4 + b) * TT + p];
+                if (A.no_del) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) nb[b] = db[b];
+                }
+                six32(nb, N); six32(db, D);
+                if (STAT == PSS_BASEQ) {
+                    o[0] = N[0]; o[st] = N[3]; o[2 * st] = q_rootmean(S[0], D[0]); o[3 * st] = q_rootmean(S[3], D[3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { o[k * st] = N[k]; o[(6 + k) * st] = q_rootmean(S[k], D[k]); }
+                }
+            } else {
+                uint32_t mtb[4], mmb[4], Mn[6], Mm[6];
+                unsigned long long smb[4], Sm[6];
+                const unsigned long long *sqmm = reinterpret_cast<const unsigned long long *>(cnt + LayBqx::SQMM * TT);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    mtb[b] = cnt[(LayBqx::MATCH + b) * TT + p]; mmb[b] = cnt[(LayBqx::MMT + b) * TT + p];
+                    smb[b] = sqmm[b * TT + p];
+                }
+                six32(nb, N); six32(mtb, Mn); six32(mmb, Mm); six64(smb, Sm);     // Sm: squared qualities of the mismatches
+                if (STAT == PSS_BASEQ_EXT) {
+                    const int idx[2] = {0, 3};
+#pragma unroll
+                    for (int jx = 0; jx < 2; ++jx) {
+                        const int k = idx[jx];
+                        o[jx * st] = N[k]; o[(2 + jx) * st] = Mn[k]; o[(4 + jx) * st] = Mm[k];
+                        o[(6 + jx) * st] = q_rootmean(S[k], Mn[k] + Mm[k]); o[(8 + jx) * st] = q_rootmean(S[k] - Sm[k], Mn[k]);
+                        o[(10 + jx) * st] = q_rootmean(Sm[k], Mm[k]);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        o[k * st] = N[k]; o[(6 + k) * st] = Mn[k]; o[(12 + k) * st] = Mm[k];
+                        o[(18 + k) * st] = q_rootmean(S[k], Mn[k] + Mm[k]); o[(24 + k) * st] = q_rootmean(S[k] - Sm[k], Mn[k]);
+                        o[(30 + k) * st] = q_rootmean(Sm[k], Mm[k]);
+                    }
+                }
+            }
+        }
+        A.rowmask[pl - A.start] = (A.need_raw ? raw[p] : N[0]) ? 1 : 0;
     }
 }
 
@@ -823,11 +1243,34 @@ static cudaError_t launch_tile_one(const TileArgs &a, int64_t ntiles, cudaStream
     return cudaGetLastError();
 }
 
-bool tile_kernel_supports(int stat, int min_baseq) {
-    if (min_baseq > 0) return false;
+template <int KIND, int STAT>
+static cudaError_t launch_tileq_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
+    const size_t smem = (size_t)q_layout<KIND>().total;
+    static bool configured = false;     // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_tileq<KIND, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_tileq<KIND, STAT><<<(unsigned)ntiles, QNT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// statistics whose counts come back through the narrow (8- / 16-bit) host transport
+bool tile_kernel_counting(int stat) {
     switch (stat) {
     case PSS_COVERAGE: case PSS_COVERAGE_STRAND: case PSS_COVERAGE_GC: case PSS_COVERAGE_EXT:
     case PSS_COVERAGE_EXT_STRAND: case PSS_VARIATION: case PSS_VARIATION_STRAND: return true;
+    default: return false;
+    }
+}
+
+bool tile_kernel_supports(int stat, int min_baseq, int no_del) {
+    if (min_baseq > 0) return false;      // every event depends on its base: the generic kernel
+    if (tile_kernel_counting(stat)) return true;
+    switch (stat) {
+    case PSS_MAPQ: case PSS_MAPQ_STRAND: return !no_del;     // the max needs the CIGAR then: generic kernel
+    case PSS_BASEQ: case PSS_BASEQ_STRAND: case PSS_BASEQ_EXT: case PSS_BASEQ_EXT_STRAND: return true;
     default: return false;
     }
 }
@@ -847,7 +1290,8 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
         if (e != cudaSuccess) return e;
         table_ready = true;
     }
-    const bool var = (stat == PSS_VARIATION || stat == PSS_VARIATION_STRAND);
+    const bool var = (stat == PSS_VARIATION || stat == PSS_VARIATION_STRAND || stat == PSS_BASEQ_EXT ||
+                      stat == PSS_BASEQ_EXT_STRAND);
     TileDesc *desc = (TileDesc *)desc_buf;
     if (!desc_valid) {
         // always with the sequence / CIGAR spans: the descriptors are shared by all statistics of the batch
@@ -865,6 +1309,7 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     }
     TileArgs a;
     a.ri = p.ri; a.cigar = p.cigar; a.seq4 = p.seq4; a.seq_off = seq_off; a.desc = desc;
+    a.qual = p.qual; a.qual_off = p.qual_off;
     a.refpack = (const uint32_t *)refpack_buf;
     a.tflags = (const uint32_t *)refpack_buf + (ntiles * REFN_WORDS + 8);
     a.ref = p.ref; a.ref_start = p.ref_start; a.ref_len = p.ref_len; a.start = p.start; a.end = p.end;
@@ -891,6 +1336,12 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     case PSS_COVERAGE_EXT_STRAND: e = launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT_STRAND>(a, ntiles, s); break;
     case PSS_VARIATION: e = launch_tile_one<KIND_VAR, PSS_VARIATION>(a, ntiles, s); break;
     case PSS_VARIATION_STRAND: e = launch_tile_one<KIND_VAR, PSS_VARIATION_STRAND>(a, ntiles, s); break;
+    case PSS_MAPQ: e = launch_tileq_one<KIND_MAPQ, PSS_MAPQ>(a, ntiles, s); break;
+    case PSS_MAPQ_STRAND: e = launch_tileq_one<KIND_MAPQ, PSS_MAPQ_STRAND>(a, ntiles, s); break;
+    case PSS_BASEQ: e = launch_tileq_one<KIND_BQ, PSS_BASEQ>(a, ntiles, s); break;
+    case PSS_BASEQ_STRAND: e = launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND>(a, ntiles, s); break;
+    case PSS_BASEQ_EXT: e = launch_tileq_one<KIND_BQX, PSS_BASEQ_EXT>(a, ntiles, s); break;
+    case PSS_BASEQ_EXT_STRAND: e = launch_tileq_one<KIND_BQX, PSS_BASEQ_EXT_STRAND>(a, ntiles, s); break;
     default: e = cudaErrorInvalidValue;
     }
     if (e1) cudaEventRecord(e1, s);

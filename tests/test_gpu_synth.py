@@ -12,7 +12,8 @@ from _util import oracle_reads_from_arrays
 pytestmark = pytest.mark.gpu
 
 G = 300_000          # oracle-checkable in about a second per statistic
-TILE_STATS = ('coverage', 'coverage_strand', 'coverage_ext', 'coverage_ext_strand', 'variation', 'variation_strand')
+TILE_STATS = ('coverage', 'coverage_strand', 'coverage_ext', 'coverage_ext_strand', 'variation', 'variation_strand',
+              'mapq', 'mapq_strand', 'baseq', 'baseq_strand', 'baseq_ext', 'baseq_ext_strand')
 
 
 @pytest.fixture(scope='module')
