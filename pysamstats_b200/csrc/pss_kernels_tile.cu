@@ -788,7 +788,6 @@ k_tile(TileArgs A) {
 // rec() is fused as in k_tile; the fp64 rootmean (opt.pyx:2159-2163) is evaluated per field.
 
 enum { KIND_MAPQ = 3, KIND_BQ = 4, KIND_BQX = 5 };
-#define QNT 256
 #define QCH 160                        // reads staged per chunk (a 512-position tile of 30x / 150 bp has ~135 candidates)
 #define QSEQ_BYTES (QCH * 76 + 64)
 #define QQUAL_BYTES (QCH * 152 + 64)
@@ -799,9 +798,10 @@ enum { KIND_MAPQ = 3, KIND_BQ = 4, KIND_BQX = 5 };
 //   KIND_BQ    n[0..3] nnd[4..7] (difference arrays)  sq64[8..15]
 //   KIND_BQX   n[0..3] match[4..7] (difference arrays)  mmt[8..11]  sq64[12..19]  sqmm64[20..27]   (LayBqx)
 template <int KIND> struct QKind;
-template <> struct QKind<KIND_MAPQ> { static const int NDIFF = 16, NWORDS = 20, SQ = 0; static const bool QUAL = false, SEQ = false, CIG = false; };
-template <> struct QKind<KIND_BQ> { static const int NDIFF = 8, NWORDS = 16, SQ = 8; static const bool QUAL = true, SEQ = false, CIG = true; };
-template <> struct QKind<KIND_BQX> { static const int NDIFF = 8, NWORDS = 28, SQ = 12; static const bool QUAL = true, SEQ = true, CIG = true; };
+// NT: threads per CTA (the first 8 warps gather; baseq_ext wants two threads per staged read in the scatter)
+template <> struct QKind<KIND_MAPQ> { static const int NDIFF = 16, NWORDS = 20, SQ = 0, NT = 256, CTAS = 4; static const bool QUAL = false, SEQ = false, CIG = false; };
+template <> struct QKind<KIND_BQ> { static const int NDIFF = 8, NWORDS = 16, SQ = 8, NT = 256, CTAS = 3; static const bool QUAL = true, SEQ = false, CIG = true; };
+template <> struct QKind<KIND_BQX> { static const int NDIFF = 8, NWORDS = 28, SQ = 12, NT = 320, CTAS = 2; static const bool QUAL = true, SEQ = true, CIG = true; };
 
 struct QSmem {       // byte offsets into the dynamic shared memory
     int raw, ri, qoff, refn, seq, qual, cig, total;
@@ -827,8 +827,29 @@ __device__ __forceinline__ void six32(const uint32_t *b, uint32_t *o6) {   // Co
 __device__ __forceinline__ void six64(const unsigned long long *b, unsigned long long *o6) {
     o6[0] = b[0] + b[1] + b[2] + b[3]; o6[1] = b[0] + b[2]; o6[2] = b[1] + b[3]; o6[3] = b[2] + b[3]; o6[4] = b[2]; o6[5] = b[3];
 }
+// rootmean (opt.pyx:2159-2163): int(numpy.around(sqrt(sq / n))) in doubles.  Evaluated in integers:
+// r is the answer iff (2r - 1)^2 n <= 4 sq <= (2r + 1)^2 n, a tie (sqrt exactly r +- 0.5, which is
+// representable, so the reference sees it too) going to the even neighbour.  When the two sides
+// of a comparison differ they differ by >= 1 in 4 sq < 2^46, i.e. by more than 2^-46 relative,
+// far outside what the two correctly rounded double operations (2^-53 each) can move, so the
+// integer decision IS the double-precision result (checked against the double formula on 1.5e8
+// cases incl. every tie neighbourhood: scripts/rootmean_check.cpp).  The float guess is within 1.
 __device__ __forceinline__ int q_rootmean(unsigned long long sq, uint32_t n) {
-    return n > 0 ? (int)rint(sqrt((double)sq / (double)n)) : 0;   // opt.pyx:2159-2163
+    if (n == 0 || sq == 0) return 0;
+    const float x = __fdividef((float)sq, (float)n);
+    // the mean of squared bytes is < 2^16; anything else (and sums beyond 2^44) takes the double path
+    if ((sq >> 44) || x > 1.0e9f) return (int)rint(sqrt((double)sq / (double)n));
+    const uint32_t r = (uint32_t)(x * rsqrtf(x) + 0.5f);       // < 2^15: the squares below fit 32 bits
+    const unsigned long long f = 4 * sq;
+    const uint32_t a = 2 * r + 1;
+    const unsigned long long hi = (unsigned long long)(a * a) * n;
+    if (f > hi || (f == hi && (r & 1u))) return (int)(r + 1);
+    if (r > 0) {
+        const uint32_t b = 2 * r - 1;
+        const unsigned long long lo = (unsigned long long)(b * b) * n;
+        if (f < lo || (f == lo && (r & 1u))) return (int)(r - 1);
+    }
+    return (int)r;
 }
 
 // one aligned span [x, x + l) of a read whose first base is query index y: the lanes' four positions
@@ -846,11 +867,12 @@ __device__ __forceinline__ void q_gather_span(uint32_t (&acc)[4][4], const uint8
 }
 
 template <int KIND, int STAT>
-__global__ void __launch_bounds__(QNT, KIND == KIND_BQX ? 2 : 3)
+__global__ void __launch_bounds__(QKind<KIND>::NT, QKind<KIND>::CTAS)
 k_tileq(TileArgs A) {
     constexpr QSmem L = q_layout<KIND>();
-    constexpr int NWARPS = QNT / 32;
     using K = QKind<KIND>;
+    constexpr int QNT = K::NT, NWARPS = QNT / 32;
+    static_assert(QNT >= 256 && QNT >= QCH, "eight gather warps, one scatter thread per staged read");
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
     uint32_t *raw = reinterpret_cast<uint32_t *>(smem + L.raw);
@@ -997,7 +1019,7 @@ k_tileq(TileArgs A) {
         // work and must run once per warp, not once per group of lanes that drifted apart
         __syncwarp();
         // ---- gather -------------------------------------------------------------------------
-        {
+        if (warp < 8) {
             int j;
             {   // first read of the chunk that can reach this warp's window
                 int lo = 0, hi = n;
@@ -1005,16 +1027,25 @@ k_tileq(TileArgs A) {
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_ri[mid].pos < key) lo = mid + 1; else hi = mid; }
                 j = lo + (((lo ^ cb) & 1) != gpar);     // parity of the read's index in the batch
             }
+            // the record of the next read is loaded before the current one is processed (its latency
+            // hides behind the span work); s_ri has room for the read past the last one
+            uint4 h = *reinterpret_cast<const uint4 *>(&s_ri[min(j, QCH - 1)]);     // pos, end, cls, n_cigar
+            long long qo = K::QUAL ? s_qoff[min(j, QCH - 1) + qskew] : 0;
             for (; j < n; j += 2) {
-                const uint4 h = *reinterpret_cast<const uint4 *>(&s_ri[j]);     // pos, end, cls, n_cigar
-                const int rpos = (int)h.x, rend = (int)h.y;
+                const int rpos = (int)h.x, rend = (int)h.y, nc = (int)h.w;
                 const uint32_t cls = h.z;
+                const long long qoff = qo;
+                const int jj = j;
+                {
+                    const int jn = min(j + 2, QCH - 1);
+                    h = *reinterpret_cast<const uint4 *>(&s_ri[jn]);
+                    if (K::QUAL) qo = s_qoff[jn + qskew];
+                }
                 if (rpos >= gw1) break;
-                if (rend <= gw0 || !(cls & CLS_COUNTED)) continue;
                 const int bank = cls & 3u;
                 if (KIND == KIND_MAPQ) {
                     const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u;
-                    if (q == 0) continue;
+                    if (rend <= gw0 || !(cls & CLS_COUNTED) || q == 0) continue;
                     const int off0 = gp0 - rpos, l = rend - rpos;
 #define QMAX(B) _Pragma("unroll") for (int i = 0; i < 4; ++i) if ((unsigned)(off0 + i) < (unsigned)l) acc[B][i] = max(acc[B][i], q);
                     switch (bank) {
@@ -1025,16 +1056,16 @@ k_tileq(TileArgs A) {
                     }
 #undef QMAX
                 } else {
-                    if (!(cls & CLS_HASSEQ) || (cls & CLS_NOREF)) continue;     // quality 0 / no base at all
-                    const uint8_t *qual = s_qual + (s_qoff[j + qskew] - quallo);
+                    // counted, with sequence (else quality 0) and with bases at all
+                    if (rend <= gw0 || (cls & (CLS_COUNTED | CLS_HASSEQ | CLS_NOREF)) != (CLS_COUNTED | CLS_HASSEQ)) continue;
+                    const uint8_t *qual = s_qual + (int)(qoff - quallo);
 #define QSPAN(B, x, l, y) q_gather_span<B>(acc, qual, gp0, x, l, y)
 #define QSPANS(x, l, y) do { switch (bank) { case 0: QSPAN(0, x, l, y); break; case 1: QSPAN(1, x, l, y); break; \
                                              case 2: QSPAN(2, x, l, y); break; default: QSPAN(3, x, l, y); break; } } while (0)
                     if (cls & CLS_SIMPLE) QSPANS(rpos, rend - rpos, 0);
                     else {
-                        const long long co = (long long)(((uint64_t)s_ri[j].cigar_off));
+                        const long long co = (long long)(((uint64_t)s_ri[jj].cigar_off));
                         const uint32_t *cg = ciglo >= 0 ? s_cig + (co - ciglo) : A.cigar + co;
-                        const int nc = (int)h.w;
                         int x = rpos, y = 0;
                         for (int k = 0; k < nc && x < gw1; ++k) {
                             const uint32_t w = cg[k];
@@ -1057,7 +1088,7 @@ k_tileq(TileArgs A) {
         if (tid == 0) issue(cb, false);
     }
     // fold the gather registers into the shared arrays (two warps own each position)
-    {
+    if (warp < 8) {
         const int pi = (warp & 3) * 128 + 4 * lane;
 #pragma unroll
         for (int b = 0; b < 4; ++b)
@@ -1252,7 +1283,7 @@ static cudaError_t launch_tileq_one(const TileArgs &a, int64_t ntiles, cudaStrea
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_tileq<KIND, STAT><<<(unsigned)ntiles, QNT, smem, s>>>(a);
+    k_tileq<KIND, STAT><<<(unsigned)ntiles, QKind<KIND>::NT, smem, s>>>(a);
     return cudaGetLastError();
 }
 
