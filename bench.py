@@ -370,7 +370,7 @@ def main():
                 path = os.path.join(tmp, 'slice.bam')
                 bamio.write_bam(path, ['chrS'], [sl], snb, level=1)
                 t0 = time.perf_counter()
-                bf = bamio.BamFile(path)
+                bf = bamio.BamFile(path).load()
                 dt = time.perf_counter() - t0
                 host_decode = {'reads_per_s': snb['n_reads'] / dt, 'seconds': dt, 'reads': int(snb['n_reads']),
                                'bam_bytes': os.path.getsize(path), 'raw_bytes': bf.decode_seconds['raw_bytes'],

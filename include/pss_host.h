@@ -47,6 +47,15 @@ const char *pss_host_error(void);
 /* Reads the file, inflates all BGZF blocks on n_threads threads (<= 0: hardware concurrency)
  * and indexes the BAM records. */
 int pss_bam_open(const char *path, int n_threads, pss_bam **out);
+/* Region open through the BAI index (replaces pysam's IteratorRowRegion / hts_itr_query behind
+ * alignmentfile.fetch / pileup with a region, opt.pyx:1853-1854, :2038-2041): reads and inflates
+ * only the BGZF blocks the index lists for reference `tid`:[beg, end) and keeps the records with
+ * pos < end && bam_endpos > beg, in file order.  bai_path NULL: "<path>.bai".  tid < 0: header
+ * only (no index needed, no records). */
+int pss_bam_open_region(const char *path, const char *bai_path, int32_t tid, int64_t beg, int64_t end,
+                        int n_threads, pss_bam **out);
+/* Writes the BAI index of a coordinate-sorted BAM (bai_path NULL: "<path>.bai"). */
+int pss_bam_index_build(const char *path, const char *bai_path, int n_threads);
 void pss_bam_close(pss_bam *b);
 
 int32_t pss_bam_n_ref(const pss_bam *b);

@@ -50,6 +50,9 @@ def host_lib():
             P = C.c_void_p
             lib.pss_host_error.restype = C.c_char_p
             lib.pss_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(P)]
+            lib.pss_bam_open_region.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.c_int,
+                                                C.POINTER(P)]
+            lib.pss_bam_index_build.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
             lib.pss_bam_close.argtypes = [P]
             lib.pss_bam_close.restype = None
             lib.pss_bam_n_ref.argtypes = [P]
@@ -190,56 +193,98 @@ def _name_prev(names):
 
 
 class BamFile(object):
-    """A whole BAM file decoded into memory."""
+    """A BAM file.  With the native decoder the file is read lazily: the header at once, the
+    records either whole (first use of ``contig_batch`` / a region query without an index) or,
+    when a ``.bai`` index sits next to a file of at least ``PSS_BAI_MIN_BYTES`` (default 32 MiB),
+    only the BGZF blocks the index lists for the region asked (``pss_bam_open_region``)."""
 
     def __init__(self, path, threads=0):
         self.filename = _path_of(path)
         self.decode_seconds = None
+        self._threads = int(threads)
+        self._all = None
+        self._tid = None
         lib = host_lib()
         if lib is not None:
-            self._init_native(lib, threads)
+            h = C.c_void_p()
+            _host_check(lib, lib.pss_bam_open_region(self.filename.encode(), None, -1, 0, 0, 1, C.byref(h)))
+            try:
+                self._read_header(lib, h)
+            finally:
+                lib.pss_bam_close(h)
         else:
             self._init_numpy()
         self._tid_of = {r: i for i, r in enumerate(self.references)}
         self._contig_cache = {}
 
-    def _init_native(self, lib, threads):
-        """C++ decoder (csrc/pss_host.cpp): threaded BGZF inflate + parallel SoA fill."""
+    def _read_header(self, lib, h):
+        nref = lib.pss_bam_n_ref(h)
+        self.references = tuple(lib.pss_bam_ref_name(h, i).decode('ascii') for i in range(nref))
+        self.lengths = tuple(int(lib.pss_bam_ref_len(h, i)) for i in range(nref))
+
+    def index_path(self):
+        """Path of the BAI index next to the file (``x.bam.bai`` or ``x.bai``) or None."""
+        for cand in (self.filename + '.bai', os.path.splitext(self.filename)[0] + '.bai'):
+            if os.path.exists(cand):
+                return cand
+        return None
+
+    def _decode(self, lib, h):
+        """SoA arrays of the records behind an open native handle -> (ReadBatch, tid array)."""
+        n, nc, ns, nq, w = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        _host_check(lib, lib.pss_bam_sizes(h, C.byref(n), C.byref(nc), C.byref(ns), C.byref(nq), C.byref(w)))
+        n, nc, ns, nq, w = n.value, nc.value, ns.value, nq.value, w.value
+        A = ReadBatch()
+        A.tid = -2
+        tid = np.empty(n, 'i4')
+        A.pos, A.flag, A.mapq = np.empty(n, 'i4'), np.empty(n, 'u2'), np.empty(n, 'u1')
+        A.tlen, A.mtid, A.l_seq = np.empty(n, 'i4'), np.empty(n, 'i4'), np.empty(n, 'i4')
+        A.endpos = np.empty(n, 'i8')
+        A.cigar_off, A.cigar = np.empty(n + 1, 'i8'), np.empty(max(nc, 1), 'u4')
+        A.seq_off, A.seq4 = np.empty(n + 1, 'i8'), np.empty(max(ns, 1), 'u1')
+        A.qual_off, A.qual = np.empty(n + 1, 'i8'), np.empty(max(nq, 1), 'u1')
+        names = np.zeros(n, dtype='S%d' % w)
+        ha = HostArrays()
+        ha.tid = tid.ctypes.data
+        for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'endpos', 'cigar_off', 'cigar', 'seq_off',
+                  'seq4', 'qual_off', 'qual'):
+            setattr(ha, k, getattr(A, k).ctypes.data)
+        ha.names = names.ctypes.data
+        _host_check(lib, lib.pss_bam_fill(h, C.byref(ha)))
+        A.cigar, A.seq4, A.qual = A.cigar[:nc], A.seq4[:ns], A.qual[:nq]
+        A.names = names
+        A.name_prev = None
+        tr, ti, tx, rb = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        lib.pss_bam_timing(h, C.byref(tr), C.byref(ti), C.byref(tx), C.byref(rb))
+        self.decode_seconds = dict(read=tr.value, inflate=ti.value, index=tx.value, raw_bytes=rb.value)
+        return A, tid
+
+    def _load_all(self):
+        """Whole-file decode (C++ decoder, csrc/pss_host.cpp: threaded BGZF inflate + parallel SoA fill)."""
+        if self._all is None:
+            lib = host_lib()
+            h = C.c_void_p()
+            _host_check(lib, lib.pss_bam_open(self.filename.encode(), self._threads, C.byref(h)))
+            try:
+                self._all, self._tid = self._decode(lib, h)
+            finally:
+                lib.pss_bam_close(h)
+        return self._all
+
+    def _region_native(self, tid, start, end, bai):
+        lib = host_lib()
         h = C.c_void_p()
-        _host_check(lib, lib.pss_bam_open(self.filename.encode(), int(threads), C.byref(h)))
+        _host_check(lib, lib.pss_bam_open_region(self.filename.encode(), bai.encode(), int(tid), int(start), int(end),
+                                                 self._threads, C.byref(h)))
         try:
-            nref = lib.pss_bam_n_ref(h)
-            self.references = tuple(lib.pss_bam_ref_name(h, i).decode('ascii') for i in range(nref))
-            self.lengths = tuple(int(lib.pss_bam_ref_len(h, i)) for i in range(nref))
-            n, nc, ns, nq, w = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
-            _host_check(lib, lib.pss_bam_sizes(h, C.byref(n), C.byref(nc), C.byref(ns), C.byref(nq), C.byref(w)))
-            n, nc, ns, nq, w = n.value, nc.value, ns.value, nq.value, w.value
-            A = ReadBatch()
-            A.tid = -2
-            self._tid = np.empty(n, 'i4')
-            A.pos, A.flag, A.mapq = np.empty(n, 'i4'), np.empty(n, 'u2'), np.empty(n, 'u1')
-            A.tlen, A.mtid, A.l_seq = np.empty(n, 'i4'), np.empty(n, 'i4'), np.empty(n, 'i4')
-            A.endpos = np.empty(n, 'i8')
-            A.cigar_off, A.cigar = np.empty(n + 1, 'i8'), np.empty(max(nc, 1), 'u4')
-            A.seq_off, A.seq4 = np.empty(n + 1, 'i8'), np.empty(max(ns, 1), 'u1')
-            A.qual_off, A.qual = np.empty(n + 1, 'i8'), np.empty(max(nq, 1), 'u1')
-            names = np.zeros(n, dtype='S%d' % w)
-            ha = HostArrays()
-            ha.tid = self._tid.ctypes.data
-            for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'endpos', 'cigar_off', 'cigar', 'seq_off',
-                      'seq4', 'qual_off', 'qual'):
-                setattr(ha, k, getattr(A, k).ctypes.data)
-            ha.names = names.ctypes.data
-            _host_check(lib, lib.pss_bam_fill(h, C.byref(ha)))
-            A.cigar, A.seq4, A.qual = A.cigar[:nc], A.seq4[:ns], A.qual[:nq]
-            A.names = names
-            A.name_prev = None
-            self._all = A
-            tr, ti, tx, rb = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
-            lib.pss_bam_timing(h, C.byref(tr), C.byref(ti), C.byref(tx), C.byref(rb))
-            self.decode_seconds = dict(read=tr.value, inflate=ti.value, index=tx.value, raw_bytes=rb.value)
+            b, _ = self._decode(lib, h)
         finally:
             lib.pss_bam_close(h)
+        b.tid = tid
+        b.name_prev = _name_prev(b.names)
+        if b.n_reads > 1 and np.any(np.diff(b.pos) < 0):
+            raise ValueError('BAM file is not coordinate sorted: %r' % self.filename)
+        return b
 
     def _init_numpy(self):
         raw = bgzf_inflate(self.filename)
@@ -314,12 +359,21 @@ class BamFile(object):
         A.name_prev = None
         self._all = A
 
+    def _load_all_any(self):
+        return self._all if self._all is not None else self._load_all()
+
+    def load(self):
+        """Decode the whole file now (it is otherwise decoded on first use)."""
+        self._load_all_any()
+        return self
+
     def get_tid(self, chrom):
         return self._tid_of[chrom]
 
     def contig_batch(self, chrom):
         """All records placed on `chrom`, file order."""
         if chrom not in self._contig_cache:
+            self._load_all_any()
             tid = self._tid_of[chrom]
             idx = np.flatnonzero(self._tid == tid)
             if len(idx) == len(self._tid):        # single-contig file: no gather needed
@@ -336,6 +390,12 @@ class BamFile(object):
 
     def region_batch(self, chrom, start, end):
         """Records the region iterator yields for chrom:[start, end)."""
+        if self._all is None and chrom not in self._contig_cache and host_lib() is not None:
+            bai = self.index_path()
+            full = start <= 0 and end >= self.lengths[self._tid_of[chrom]] and len(self.references) == 1
+            if bai is not None and not full and \
+                    os.path.getsize(self.filename) >= int(os.environ.get('PSS_BAI_MIN_BYTES', 32 << 20)):
+                return self._region_native(self._tid_of[chrom], start, end, bai)
         b = self.contig_batch(chrom)
         m = (b.pos < end) & (b.endpos > start)
         if m.all():
@@ -390,6 +450,18 @@ def write_bam(path, references, lengths, batch, names=None, level=1, threads=0):
 
 
 _bam_cache = {}
+
+
+def index_bam(path, index_path=None, threads=0):
+    """Write the BAI index of a coordinate-sorted BAM (what ``samtools index`` / ``pysam.index`` do for the
+    reference's users); returns the index path."""
+    lib = host_lib()
+    if lib is None:
+        raise RuntimeError('libpss_host.so is not built')
+    path = _path_of(path)
+    out = index_path or path + '.bai'
+    _host_check(lib, lib.pss_bam_index_build(path.encode(), out.encode(), int(threads)))
+    return out
 
 
 def open_bam(f):

@@ -54,7 +54,10 @@ static void parallel_for(int64_t n, int n_threads, F f) {
     for (auto &x : th) x.join();
 }
 
+struct Blk { int64_t in_off, in_len, out_off, out_len, file_off; };   // payload span, inflated span, block start in the file
+
 struct pss_bam {
+    std::vector<Blk> blocks;             // BGZF blocks behind `raw` (whole-file open only)
     std::vector<uint8_t> raw;            // inflated BAM stream
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
@@ -82,7 +85,6 @@ extern "C" int pss_bam_open(const char *path, int n_threads, pss_bam **out) {
     fclose(fh);
     double t1 = now();
     // block table
-    struct Blk { int64_t in_off, in_len, out_off, out_len; };
     std::vector<Blk> blocks;
     int64_t off = 0, total = 0;
     while (off < fsize) {
@@ -98,7 +100,7 @@ extern "C" int pss_bam_open(const char *path, int n_threads, pss_bam **out) {
         }
         if (bsize < 0 || off + bsize + 1 > fsize) return fail(-3, "BGZF block without BC subfield / truncated at %lld", (long long)off);
         int64_t isize = rd32(&comp[off + bsize + 1 - 4]);
-        blocks.push_back({xend, off + bsize + 1 - 8 - xend, total, isize});
+        blocks.push_back({xend, off + bsize + 1 - 8 - xend, total, isize, off});
         total += isize;
         off += bsize + 1;
     }
@@ -172,8 +174,410 @@ extern "C" int pss_bam_open(const char *path, int n_threads, pss_bam **out) {
         p += 4 + bs;
     }
     b->name_width = std::max(1, maxname);
+    b->blocks.swap(blocks);
     b->t_read = t1 - t0; b->t_inflate = t2 - t1; b->t_index = now() - t2;
     *out = b;
+    return 0;
+}
+
+static inline void wr16(std::vector<uint8_t> &v, uint16_t x) { v.push_back(x & 255); v.push_back(x >> 8); }
+static inline void wr32(std::vector<uint8_t> &v, uint32_t x) { for (int k = 0; k < 4; ++k) v.push_back((x >> (8 * k)) & 255); }
+
+static int reg2bin(int64_t beg, int64_t end) {     // SAM spec section 5.3
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+// ------------------------------------------------------------------- BAI: region open + index build
+//
+// BAI (SAM spec section 5.2): per reference a binning index (bin -> chunks of virtual offsets
+// [beg, end), virtual offset = block start in the file << 16 | offset in the inflated block) and a
+// linear index (smallest virtual offset of a record overlapping each 16 kb window).
+
+struct Chunk { uint64_t beg, end; };
+
+static void reg2bins(int64_t beg, int64_t end, std::vector<uint32_t> &bins) {     // SAM spec section 5.3
+    --end;
+    bins.push_back(0);
+    for (int64_t k = 1 + (beg >> 26); k <= 1 + (end >> 26); ++k) bins.push_back((uint32_t)k);
+    for (int64_t k = 9 + (beg >> 23); k <= 9 + (end >> 23); ++k) bins.push_back((uint32_t)k);
+    for (int64_t k = 73 + (beg >> 20); k <= 73 + (end >> 20); ++k) bins.push_back((uint32_t)k);
+    for (int64_t k = 585 + (beg >> 17); k <= 585 + (end >> 17); ++k) bins.push_back((uint32_t)k);
+    for (int64_t k = 4681 + (beg >> 14); k <= 4681 + (end >> 14); ++k) bins.push_back((uint32_t)k);
+}
+
+static bool read_file(const char *path, std::vector<uint8_t> &out) {
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return false;
+    fseek(fh, 0, SEEK_END);
+    long long n = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    out.resize((size_t)n);
+    bool ok = n == 0 || fread(out.data(), 1, (size_t)n, fh) == (size_t)n;
+    fclose(fh);
+    return ok;
+}
+
+// chunks of reference `tid` that can hold records overlapping [beg, end), sorted and merged
+static int bai_chunks(const char *bai_path, int32_t tid, int64_t beg, int64_t end, std::vector<Chunk> &out) {
+    std::vector<uint8_t> d;
+    if (!read_file(bai_path, d)) return fail(-2, "cannot read index %s", bai_path);
+    const int64_t n = (int64_t)d.size();
+    if (n < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return fail(-6, "not a BAI index: %s", bai_path);
+    const int32_t n_ref = rdi32(&d[4]);
+    if (tid < 0 || tid >= n_ref) return fail(-6, "reference %d is not in the index (%d references)", tid, n_ref);
+    std::vector<uint32_t> want;
+    reg2bins(beg, end, want);
+    std::sort(want.begin(), want.end());
+    int64_t p = 8;
+    auto rd64 = [&](int64_t o) { uint64_t v; memcpy(&v, &d[o], 8); return v; };
+    for (int32_t r = 0; r <= tid; ++r) {
+        if (p + 4 > n) return fail(-6, "truncated BAI index");
+        const int32_t n_bin = rdi32(&d[p]);
+        p += 4;
+        for (int32_t k = 0; k < n_bin; ++k) {
+            if (p + 8 > n) return fail(-6, "truncated BAI index");
+            const uint32_t bin = rd32(&d[p]);
+            const int32_t n_chunk = rdi32(&d[p + 4]);
+            p += 8;
+            if (n_chunk < 0 || p + 16ll * n_chunk > n) return fail(-6, "truncated BAI index");
+            if (r == tid && bin != 37450u && std::binary_search(want.begin(), want.end(), bin))
+                for (int32_t c = 0; c < n_chunk; ++c) out.push_back({rd64(p + 16ll * c), rd64(p + 16ll * c + 8)});
+            p += 16ll * n_chunk;
+        }
+        if (p + 4 > n) return fail(-6, "truncated BAI index");
+        const int32_t n_intv = rdi32(&d[p]);
+        p += 4;
+        if (n_intv < 0 || p + 8ll * n_intv > n) return fail(-6, "truncated BAI index");
+        if (r == tid && n_intv > 0) {
+            // every record overlapping the region overlaps window beg >> 14 or starts later:
+            // its virtual offset is >= the linear index entry of that window
+            int64_t w = beg >> 14;
+            if (w >= n_intv) w = n_intv - 1;
+            const uint64_t min_off = rd64(p + 8 * w);
+            std::vector<Chunk> kept;
+            for (Chunk c : out) {
+                if (c.end <= min_off) continue;
+                if (c.beg < min_off) c.beg = min_off;
+                kept.push_back(c);
+            }
+            out.swap(kept);
+        }
+        p += 8ll * n_intv;
+    }
+    std::sort(out.begin(), out.end(), [](const Chunk &a, const Chunk &b) { return a.beg < b.beg; });
+    // merge chunks that overlap or sit within 64 KiB of file of each other: records read on the
+    // way are filtered by position anyway, and no BGZF block is inflated twice
+    std::vector<Chunk> merged;
+    for (const Chunk &c : out) {
+        if (!merged.empty() && (c.beg >> 16) <= (merged.back().end >> 16) + 65536) {
+            if (c.end > merged.back().end) merged.back().end = c.end;
+        } else merged.push_back(c);
+    }
+    out.swap(merged);
+    return 0;
+}
+
+// BGZF block at file offset `off`: total size (0 = not a block header)
+static int64_t bgzf_block_size(const uint8_t *h, int64_t avail, int64_t *payload_off) {
+    if (avail < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+    const int xlen = rd16(h + 10);
+    int64_t x = 12, xend = 12 + xlen;
+    if (xend > avail) return 0;
+    int bsize = -1;
+    while (x + 4 <= xend) {
+        const int slen = rd16(h + x + 2);
+        if (h[x] == 66 && h[x + 1] == 67 && slen == 2) bsize = rd16(h + x + 4);
+        x += 4 + slen;
+    }
+    if (bsize < 0) return 0;
+    *payload_off = xend;
+    return (int64_t)bsize + 1;
+}
+
+static int parse_header(pss_bam *b, const uint8_t *r, int64_t n, int64_t *consumed) {   // 1: incomplete
+    if (n < 12) return 1;
+    if (memcmp(r, "BAM\1", 4) != 0) return fail(-4, "not a BAM file");
+    int64_t p = 8 + (int64_t)rdi32(r + 4);
+    if (p + 4 > n) return 1;
+    const int32_t n_ref = rdi32(r + p);
+    p += 4;
+    b->ref_names.clear(); b->ref_lens.clear();
+    for (int32_t i = 0; i < n_ref; ++i) {
+        if (p + 4 > n) return 1;
+        const int32_t l_name = rdi32(r + p);
+        if (l_name < 1) return fail(-4, "bad BAM header");
+        if (p + 8 + l_name > n) return 1;
+        b->ref_names.emplace_back((const char *)(r + p + 4), (size_t)(l_name - 1));
+        b->ref_lens.push_back(rdi32(r + p + 4 + l_name));
+        p += 8 + l_name;
+    }
+    *consumed = p;
+    return 0;
+}
+
+static int inflate_one(z_stream &zs, const uint8_t *src, int64_t in_len, uint8_t *dst, int64_t out_len) {
+    if (out_len == 0) return 0;
+    inflateReset(&zs);
+    zs.next_in = (Bytef *)src; zs.avail_in = (uInt)in_len;
+    zs.next_out = dst; zs.avail_out = (uInt)out_len;
+    const int rc = inflate(&zs, Z_FINISH);
+    return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
+}
+
+extern "C" int pss_bam_open_region(const char *path, const char *bai_path, int32_t tid, int64_t beg, int64_t end,
+                                   int n_threads, pss_bam **out) {
+    if (!out || !path) return fail(-1, "NULL argument");
+    *out = nullptr;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const double t0 = now();
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return fail(-2, "cannot open %s", path);
+    fseek(fh, 0, SEEK_END);
+    const int64_t fsize = ftell(fh);
+    struct Closer { FILE *f; ~Closer() { fclose(f); } } closer{fh};
+    auto read_at = [&](int64_t off, int64_t len, uint8_t *dst) -> bool {
+        if (off < 0 || off + len > fsize) return false;
+        if (fseek(fh, (long)off, SEEK_SET) != 0) return false;
+        return len == 0 || fread(dst, 1, (size_t)len, fh) == (size_t)len;
+    };
+    pss_bam *b = new pss_bam();
+    b->n_threads = n_threads;
+    struct Guard { pss_bam *b; ~Guard() { delete b; } } guard{b};
+    // ---- header: inflate blocks from the start of the file until it parses
+    {
+        std::vector<uint8_t> head, comp(65536 + 64);
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) return fail(-3, "zlib init failed");
+        int64_t off = 0, consumed = 0;
+        int rc = 1;
+        while (rc == 1 && off < fsize) {
+            const int64_t avail = std::min<int64_t>(fsize - off, (int64_t)comp.size());
+            if (!read_at(off, avail, comp.data())) { rc = fail(-2, "read error on %s", path); break; }
+            int64_t pay = 0;
+            const int64_t bs = bgzf_block_size(comp.data(), avail, &pay);
+            if (bs <= 0 || bs > avail) { rc = fail(-3, "not a BGZF file: %s", path); break; }
+            const int64_t isize = rd32(&comp[bs - 4]);
+            const size_t old = head.size();
+            head.resize(old + (size_t)isize);
+            if (inflate_one(zs, comp.data() + pay, bs - 8 - pay, head.data() + old, isize) != 0) { rc = fail(-3, "corrupt BGZF block in %s", path); break; }
+            off += bs;
+            rc = parse_header(b, head.data(), (int64_t)head.size(), &consumed);
+        }
+        inflateEnd(&zs);
+        if (rc == 1) return fail(-4, "truncated BAM header in %s", path);
+        if (rc != 0) return rc;
+    }
+    b->cig_off.push_back(0); b->seq_off.push_back(0); b->qual_off.push_back(0);
+    if (tid < 0) {            // header only
+        b->t_read = now() - t0;
+        guard.b = nullptr;
+        *out = b;
+        return 0;
+    }
+    if (tid >= (int32_t)b->ref_names.size()) return fail(-1, "reference %d out of range", tid);
+    std::string bai = bai_path ? bai_path : std::string(path) + ".bai";
+    std::vector<Chunk> chunks;
+    int rc = bai_chunks(bai.c_str(), tid, beg, end, chunks);
+    if (rc != 0) return rc;
+    // ---- the compressed bytes of every chunk, its block table
+    struct Piece { int64_t file_lo, file_hi; size_t comp_off; int64_t first_blk, n_blk; int64_t start, stop; };   // start / stop: offsets in raw
+    std::vector<Piece> pieces;
+    std::vector<uint8_t> comp;
+    std::vector<Blk> blocks;
+    int64_t total = 0;
+    for (const Chunk &c : chunks) {
+        const int64_t lo = (int64_t)(c.beg >> 16), last = (int64_t)(c.end >> 16);
+        if (lo >= fsize) continue;
+        // the block at `last` is needed up to c.end & 0xffff: read its header to learn its size
+        int64_t hi = last;
+        if ((c.end & 0xffff) != 0 && last < fsize) {
+            uint8_t h[64];
+            const int64_t avail = std::min<int64_t>(64, fsize - last);
+            int64_t pay = 0;
+            if (!read_at(last, avail, h)) return fail(-2, "read error on %s", path);
+            const int64_t bs = bgzf_block_size(h, avail, &pay);
+            if (bs <= 0) return fail(-6, "index %s does not match %s (no BGZF block at %lld)", bai.c_str(), path, (long long)last);
+            hi = last + bs;
+        }
+        if (hi > fsize) hi = fsize;
+        Piece pc{lo, hi, comp.size(), (int64_t)blocks.size(), 0, 0, 0};
+        comp.resize(comp.size() + (size_t)(hi - lo));
+        if (!read_at(lo, hi - lo, comp.data() + pc.comp_off)) return fail(-2, "read error on %s", path);
+        int64_t off = 0;
+        pc.start = total + (int64_t)(c.beg & 0xffff);
+        pc.stop = -1;
+        while (off < hi - lo) {
+            int64_t pay = 0;
+            const int64_t bs = bgzf_block_size(comp.data() + pc.comp_off + off, hi - lo - off, &pay);
+            if (bs <= 0 || off + bs > hi - lo)
+                return fail(-6, "index %s does not match %s (bad BGZF block at %lld)", bai.c_str(), path, (long long)(lo + off));
+            const int64_t isize = rd32(comp.data() + pc.comp_off + off + bs - 4);
+            if (lo + off == last) pc.stop = total + (int64_t)(c.end & 0xffff);
+            blocks.push_back({(int64_t)pc.comp_off + off + pay, bs - 8 - pay, total, isize, lo + off});
+            total += isize;
+            off += bs;
+        }
+        if (pc.stop < 0) pc.stop = total;          // chunk ends exactly at a block boundary
+        pc.n_blk = (int64_t)blocks.size() - pc.first_blk;
+        pieces.push_back(pc);
+    }
+    const double t1 = now();
+    b->raw.resize((size_t)total);
+    {
+        std::atomic<int> bad(0);
+        std::atomic<int64_t> next(0);
+        std::vector<std::thread> th;
+        const int nt = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, (int64_t)blocks.size() / 4));
+        for (int t = 0; t < nt; ++t)
+            th.emplace_back([&] {
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+                for (;;) {
+                    const int64_t k0 = next.fetch_add(8);
+                    if (k0 >= (int64_t)blocks.size()) break;
+                    const int64_t k1 = std::min<int64_t>(blocks.size(), k0 + 8);
+                    for (int64_t k = k0; k < k1; ++k)
+                        if (inflate_one(zs, comp.data() + blocks[k].in_off, blocks[k].in_len, b->raw.data() + blocks[k].out_off, blocks[k].out_len) != 0) bad = 1;
+                }
+                inflateEnd(&zs);
+            });
+        for (auto &x : th) x.join();
+        if (bad) return fail(-3, "corrupt BGZF block in %s", path);
+    }
+    const double t2 = now();
+    // ---- records of each chunk that overlap the region (pos < end && bam_endpos > beg)
+    const uint8_t *r = b->raw.data();
+    int maxname = 1;
+    for (const Piece &pc : pieces) {
+        int64_t p = pc.start;
+        while (p < pc.stop) {
+            if (p + 36 > total) return fail(-6, "index %s does not match %s (record beyond the chunk)", bai.c_str(), path);
+            const int32_t bs = rdi32(r + p);
+            if (bs < 32 || p + 4 + bs > total) return fail(-6, "index %s does not match %s (bad record size)", bai.c_str(), path);
+            const uint8_t *q = r + p + 4;
+            const int l_name = q[8], n_cig = rd16(q + 12);
+            const int32_t l_seq = rdi32(q + 16), rtid = rdi32(q), pos = rdi32(q + 4);
+            if (l_seq < 0 || 32 + (int64_t)l_name + 4ll * n_cig + (l_seq + 1) / 2 + l_seq > bs)
+                return fail(-4, "inconsistent BAM record in %s", path);
+            p += 4 + bs;
+            if (rtid != tid) { if (rtid > tid || rtid < 0) break; continue; }
+            if (pos >= end) break;                       // coordinate sorted: nothing further can overlap
+            int64_t reflen = 0;
+            const uint8_t *cig = q + 32 + l_name;
+            for (int k = 0; k < n_cig; ++k) {
+                const uint32_t w = rd32(cig + 4 * k);
+                if (REF_CONSUMING[w & 15]) reflen += (w >> 4);
+            }
+            if (rd16(q + 14) & 4) reflen = 0;
+            if ((int64_t)pos + (reflen > 0 ? reflen : 1) <= beg) continue;
+            b->rec.push_back((int64_t)(q - r));
+            b->cig_off.push_back(b->cig_off.back() + n_cig);
+            b->seq_off.push_back(b->seq_off.back() + (l_seq + 1) / 2);
+            b->qual_off.push_back(b->qual_off.back() + l_seq);
+            maxname = std::max(maxname, l_name > 0 ? l_name - 1 : 0);
+        }
+    }
+    b->name_width = std::max(1, maxname);
+    b->t_read = t1 - t0; b->t_inflate = t2 - t1; b->t_index = now() - t2;
+    guard.b = nullptr;
+    *out = b;
+    return 0;
+}
+
+// Builds the BAI index of a coordinate-sorted BAM (what `samtools index` writes: binning index with
+// merged chunks per bin, 16 kb linear index, the per-reference pseudo-bin 37450 and n_no_coor).
+extern "C" int pss_bam_index_build(const char *path, const char *bai_path, int n_threads) {
+    pss_bam *b = nullptr;
+    int rc = pss_bam_open(path, n_threads, &b);
+    if (rc != 0) return rc;
+    struct Guard { pss_bam *b; ~Guard() { delete b; } } guard{b};
+    const uint8_t *r = b->raw.data();
+    const int64_t n = (int64_t)b->rec.size();
+    const int32_t n_ref = (int32_t)b->ref_names.size();
+    // virtual offset of a position of the inflated stream
+    size_t bk = 0;
+    auto voff = [&](int64_t p) -> uint64_t {      // p non-decreasing across calls
+        while (bk + 1 < b->blocks.size() && (p >= b->blocks[bk].out_off + b->blocks[bk].out_len)) ++bk;
+        return ((uint64_t)b->blocks[bk].file_off << 16) | (uint64_t)(p - b->blocks[bk].out_off);
+    };
+    struct RefIdx {
+        std::vector<std::pair<uint32_t, Chunk>> chunks;    // (bin, chunk) in file order
+        std::vector<uint64_t> lin;
+        uint64_t off_beg = 0, off_end = 0, n_mapped = 0, n_unmapped = 0;
+        bool any = false;
+    };
+    std::vector<RefIdx> idx((size_t)n_ref);
+    uint64_t n_no_coor = 0;
+    int32_t last_tid = -1, last_pos = -1;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t *q = r + b->rec[i];
+        const int32_t tid = rdi32(q), pos = rdi32(q + 4), bs = rdi32(q - 4);
+        const uint16_t flag = rd16(q + 14);
+        const uint64_t v0 = voff(b->rec[i] - 4), v1 = voff(b->rec[i] + bs);
+        if (tid < 0) { ++n_no_coor; continue; }
+        if (tid >= n_ref) return fail(-4, "record with reference %d beyond the header", tid);
+        if (tid < last_tid || (tid == last_tid && pos < last_pos)) return fail(-7, "BAM file is not coordinate sorted: %s", path);
+        last_tid = tid; last_pos = pos;
+        const int l_name = q[8], n_cig = rd16(q + 12);
+        int64_t reflen = 0;
+        const uint8_t *cig = q + 32 + l_name;
+        for (int k = 0; k < n_cig; ++k) {
+            const uint32_t w = rd32(cig + 4 * k);
+            if (REF_CONSUMING[w & 15]) reflen += (w >> 4);
+        }
+        if (flag & 4) reflen = 0;
+        const int64_t beg = pos < 0 ? 0 : pos, end = beg + (reflen > 0 ? reflen : 1);
+        RefIdx &R = idx[(size_t)tid];
+        if (!R.any) { R.off_beg = v0; R.any = true; }
+        R.off_end = v1;
+        if (flag & 4) ++R.n_unmapped; else ++R.n_mapped;
+        const uint32_t bin = (uint32_t)reg2bin(beg, end);
+        if (!R.chunks.empty() && R.chunks.back().first == bin && R.chunks.back().second.end == v0) R.chunks.back().second.end = v1;
+        else R.chunks.push_back({bin, {v0, v1}});
+        const int64_t w0 = beg >> 14, w1 = (end - 1) >> 14;
+        if ((int64_t)R.lin.size() <= w1) R.lin.resize((size_t)w1 + 1, 0);
+        for (int64_t w = w0; w <= w1; ++w) if (R.lin[(size_t)w] == 0) R.lin[(size_t)w] = v0;
+    }
+    std::vector<uint8_t> o;
+    o.insert(o.end(), {'B', 'A', 'I', 1});
+    auto w64 = [&](uint64_t x) { for (int k = 0; k < 8; ++k) o.push_back((uint8_t)(x >> (8 * k))); };
+    wr32(o, (uint32_t)n_ref);
+    for (RefIdx &R : idx) {
+        std::stable_sort(R.chunks.begin(), R.chunks.end(), [](const std::pair<uint32_t, Chunk> &a, const std::pair<uint32_t, Chunk> &c) { return a.first < c.first; });
+        int32_t n_bin = 0;
+        for (size_t k = 0; k < R.chunks.size(); ++k) if (k == 0 || R.chunks[k].first != R.chunks[k - 1].first) ++n_bin;
+        wr32(o, (uint32_t)(n_bin + (R.any ? 1 : 0)));
+        for (size_t k = 0; k < R.chunks.size();) {
+            size_t e = k;
+            while (e < R.chunks.size() && R.chunks[e].first == R.chunks[k].first) ++e;
+            wr32(o, R.chunks[k].first);
+            wr32(o, (uint32_t)(e - k));
+            for (size_t c = k; c < e; ++c) { w64(R.chunks[c].second.beg); w64(R.chunks[c].second.end); }
+            k = e;
+        }
+        if (R.any) {
+            wr32(o, 37450u); wr32(o, 2u);
+            w64(R.off_beg); w64(R.off_end); w64(R.n_mapped); w64(R.n_unmapped);
+        }
+        // empty windows inherit the previous entry, as htslib writes them
+        for (size_t w = 1; w < R.lin.size(); ++w) if (R.lin[w] == 0) R.lin[w] = R.lin[w - 1];
+        wr32(o, (uint32_t)R.lin.size());
+        for (uint64_t v : R.lin) w64(v);
+    }
+    w64(n_no_coor);
+    std::string bai = bai_path ? bai_path : std::string(path) + ".bai";
+    FILE *fh = fopen(bai.c_str(), "wb");
+    if (!fh) return fail(-2, "cannot create %s", bai.c_str());
+    fwrite(o.data(), 1, o.size(), fh);
+    if (fclose(fh) != 0) return fail(-2, "write error on %s", bai.c_str());
     return 0;
 }
 
@@ -281,19 +685,6 @@ extern "C" int pss_name_prev(const uint8_t *names, int64_t n, int32_t width, int
 }
 
 // ---------------------------------------------------------------------------------- writer
-
-static inline void wr16(std::vector<uint8_t> &v, uint16_t x) { v.push_back(x & 255); v.push_back(x >> 8); }
-static inline void wr32(std::vector<uint8_t> &v, uint32_t x) { for (int k = 0; k < 4; ++k) v.push_back((x >> (8 * k)) & 255); }
-
-static int reg2bin(int64_t beg, int64_t end) {     // SAM spec section 5.3
-    --end;
-    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
-    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
-    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
-    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
-    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
-    return 0;
-}
 
 static bool bgzf_block(const uint8_t *src, size_t len, int level, std::vector<uint8_t> &out) {
     z_stream zs;

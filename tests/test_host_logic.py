@@ -28,7 +28,7 @@ def decoder(request, monkeypatch):
 
 @pytest.mark.parametrize('name', ['test.bam', 'deep.bam', 'rna.bam', 'longcontignames.bam'])
 def test_decoder_matches_oracle_reader(name, decoder):
-    mine = bamio.BamFile(fx(name))
+    mine = bamio.BamFile(fx(name)).load()
     assert (mine.decode_seconds is not None) == (decoder == 'native')
     ref = bamread.Bam(fx(name))
     assert list(mine.references) == ref.references and list(mine.lengths) == ref.lengths
@@ -89,6 +89,72 @@ def test_region_batch_rule():
         for j, nm in enumerate(names):
             assert b.name_prev[j] == last.get(nm, -1)
             last[nm] = j
+
+
+BATCH_KEYS = ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'endpos', 'cigar_off', 'cigar', 'seq_off', 'seq4', 'qual_off',
+              'qual', 'names', 'name_prev')
+
+
+def _same_batch(a, b, label):
+    assert a.n_reads == b.n_reads, (label, a.n_reads, b.n_reads)
+    for k in BATCH_KEYS:
+        x, y = getattr(a, k), getattr(b, k)
+        if k in ('cigar', 'seq4', 'qual') and a.n_reads == 0:
+            continue
+        assert np.array_equal(x, y), (label, k)
+
+
+@pytest.mark.parametrize('name', ['test.bam', 'deep.bam', 'rna.bam', 'longcontignames.bam'])
+def test_indexed_region_decode_equals_whole_file_decode(name, monkeypatch):
+    # the BAI path (pss_bam_open_region: only the BGZF blocks the index lists) against the in-memory filter
+    monkeypatch.setenv('PSS_BAI_MIN_BYTES', '0')
+    whole = bamio.BamFile(fx(name)).load()
+    rng = np.random.default_rng(3)
+    refs = list(zip(whole.references, whole.lengths))
+    picks = [refs[i] for i in rng.choice(len(refs), min(len(refs), 6), replace=False)]
+    for chrom, ln in picks:
+        for _ in range(4):
+            s = int(rng.integers(0, max(1, ln)))
+            e = s + int(rng.choice([1, 50, 1000, 40000]))
+            via_index = bamio.BamFile(fx(name))
+            assert via_index.index_path() is not None
+            got = via_index.region_batch(chrom, s, e)
+            assert via_index._all is None                     # the whole file was never decoded
+            _same_batch(got, whole.region_batch(chrom, s, e), (name, chrom, s, e))
+
+
+def test_index_build_and_region_decode_on_a_multi_block_bam(tmp_path, monkeypatch):
+    from pysamstats_b200 import synth
+    monkeypatch.setenv('PSS_BAI_MIN_BYTES', '0')
+    G = 400000
+    batch, _ = synth.make_interval_batch(0, G, G, block=100000, with_qual=True)
+    nb = synth.batch_to_numpy(batch)
+    path = str(tmp_path / 'synthetic.bam')
+    bamio.write_bam(path, ['chrS', 'chrT'], [G, 1000], nb, level=1, threads=2)
+    assert bamio.index_bam(path, threads=2) == path + '.bai'
+    assert os.path.getsize(path) > 40 * 65536                  # many BGZF blocks, chunks that span them
+    whole = bamio.BamFile(path).load()
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        s = int(rng.integers(0, G))
+        e = s + int(rng.choice([1, 300, 20000, 150000]))
+        f = bamio.BamFile(path)
+        got = f.region_batch('chrS', s, e)
+        assert f._all is None
+        _same_batch(got, whole.region_batch('chrS', s, e), (s, e))
+        if e - s <= 300:                                       # a small region touches a small part of the file
+            assert f.decode_seconds['raw_bytes'] < 0.2 * whole.decode_seconds['raw_bytes']
+    assert bamio.BamFile(path).region_batch('chrT', 0, 1000).n_reads == 0
+    # the index this package writes and the one samtools wrote select the same records
+    own = str(tmp_path / 'test.own.bai')
+    bamio.index_bam(fx('test.bam'), index_path=own)
+    a = bamio.BamFile(fx('test.bam'))
+    b = bamio.BamFile(fx('test.bam'))
+    b.index_path = lambda: own
+    for (c, s, e) in (('Pf3D7_01_v3', 2000, 2100), ('Pf3D7_02_v3', 0, 60001), ('Pf3D7_03_v3', 100, 70001)):
+        _same_batch(a.region_batch(c, s, e), b.region_batch(c, s, e), (c, s, e))
+    with pytest.raises(ValueError):
+        bamio.index_bam(fx('ref.fa'), index_path=str(tmp_path / 'x.bai'))
 
 
 def test_fasta_fetch():
