@@ -249,3 +249,20 @@ def test_writers_and_cli(tmp_path):
     rc = subprocess.call([sys.executable, ROOT + '/scripts/pysamstats', '--type', 'variation', fx('test.bam')],
                          stderr=subprocess.DEVNULL)
     assert rc == 2                                            # missing --fasta option
+
+
+def test_region_queries_through_the_bai_index(obam, ofa, monkeypatch):
+    # same answers when the reads of a region come through the BAI index (only the listed BGZF blocks
+    # are inflated) instead of a whole-file decode
+    from pysamstats_b200 import bamio
+    monkeypatch.setenv('PSS_BAI_MIN_BYTES', '0')
+    monkeypatch.setattr(bamio, '_bam_cache', {})
+    for stat, kw in (('variation_strand', dict(chrom='Pf3D7_02_v3', start=20000, end=24000)),
+                     ('baseq_ext', dict(chrom='Pf3D7_01_v3', start=1000, end=3000, truncate=True)),
+                     ('coverage_ext', dict(chrom='Pf3D7_03_v3', start=100, end=50000, pad=True)),
+                     ('tlen', dict(chrom='Pf3D7_01_v3', start=5000, end=9000, one_based=True))):
+        assert_recarrays_equal(_oracle(stat, obam, ofa, 'test', **kw), _load(stat, 'test', **kw), '%s %r' % (stat, kw))
+    bam = bamio.open_bam(fx('test.bam'))
+    assert bam._all is None                                       # nothing decoded the whole file
+    a = pysamstats.load_mapq_binned(fx('test.bam'), chrom='Pf3D7_01_v3', start=2000, end=20000)
+    assert_recarrays_equal(orc.load_binned('mapq', obam['test'], None, chrom='Pf3D7_01_v3', start=2000, end=20000), a, 'mapq_binned')
