@@ -244,6 +244,20 @@ int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats,
                           uint8_t *const *rowmasks);
 
 /*
+ * The same over a long position range, streamed: the library cuts [start, end) into chunks of
+ * `chunk_positions` positions (0: 25 M), and uploads the reads of chunk k + 1 -- those with
+ * pos in (chunk start - max_span, chunk end), a sub-range of the start-sorted batch -- while
+ * chunk k is computed, copied back and widened.  `max_span` >= max(bam_endpos - pos) over the
+ * batch (the decoder knows it; a larger value only costs bandwidth).  outs[i] is
+ * [n_fields][end - start] as for pss_pileup_host_multi.  Requests that read base qualities
+ * (the mate links of name_prev index the whole batch) and coverage_gc fall back to one
+ * pss_pileup_host_multi call.  HOST pointers, pinned for the copies to overlap (synchronous).
+ */
+int pss_pileup_host_stream(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats,
+                           const pss_pileup_params *params, int32_t *const *outs,
+                           uint8_t *const *rowmasks, int64_t max_span, int64_t chunk_positions);
+
+/*
  * The depth-cap admission rule of bam_plp_push (max_depth, call site opt.pyx:1853-1854)
  * plus the stepper flag filter, exposed on its own: admitted[i] = 1 iff read i enters the
  * pileup.  DEVICE pointers.

@@ -73,6 +73,8 @@ SYMBOLS = {
     'pss_pileup_host': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssPileupParams), _P, _P]),
     'pss_pileup_host_multi': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.POINTER(PssPileupParams),
                                         C.POINTER(_P), C.POINTER(_P)]),
+    'pss_pileup_host_stream': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.POINTER(PssPileupParams),
+                                         C.POINTER(_P), C.POINTER(_P), C.c_int64, C.c_int64]),
     'pss_admit': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P]),
     'pss_overlap_tweak': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P, _P]),
     'pss_binned': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssBinnedParams), _P, _P]),
@@ -214,6 +216,14 @@ class Context(object):
         oa = (_P * n)(*[_addr(o) for o in outs])
         ma = (_P * n)(*[_addr(m) for m in rowmasks])
         self.check(self.lib.pss_pileup_host_multi(self.h, C.byref(reads_struct), n, pa, oa, ma))
+
+    def pileup_host_stream(self, reads_struct, params_list, outs, rowmasks, max_span, chunk_positions=0):
+        n = len(params_list)
+        pa = (PssPileupParams * n)(*params_list)
+        oa = (_P * n)(*[_addr(o) for o in outs])
+        ma = (_P * n)(*[_addr(m) for m in rowmasks])
+        self.check(self.lib.pss_pileup_host_stream(self.h, C.byref(reads_struct), n, pa, oa, ma, int(max_span),
+                                                   int(chunk_positions)))
 
     def pileup(self, reads_struct, params, out, rowmask, stream=None):
         self.check(self.lib.pss_pileup(self.h, C.byref(reads_struct), C.byref(params), _addr(out),

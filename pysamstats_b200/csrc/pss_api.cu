@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <vector>
 
@@ -29,6 +30,9 @@ struct pss_ctx {
     int prep_stepper = 0, prep_max_depth = 0, prep_min_mapq = 0, prep_no_dup = 0, prep_qual = 0;
     int64_t desc_start = -1, desc_end = -1;   // position range the tile descriptors in tdesc describe
     DevBuf hb[20];          // device copies of host batches (*_host entry points)
+    DevBuf hb2[20];         // second set: pss_pileup_host_stream uploads chunk k + 1 while chunk k is computed
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     DevBuf outbuf[2], maskbuf[2];
     // narrow (8- / 16-bit) result transport of the host entry points: 3 device buffers, 3 pinned staging buffers
     DevBuf nbuf[3], nmask[3];
@@ -149,6 +153,12 @@ extern "C" void pss_destroy(pss_ctx *ctx) {
                      &ctx->outbuf[0], &ctx->outbuf[1], &ctx->maskbuf[0], &ctx->maskbuf[1]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->hb) if (b.p) cudaFree(b.p);
+    for (DevBuf &b : ctx->hb2) if (b.p) cudaFree(b.p);
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
+        if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+    }
     if (ctx->small_host) cudaFreeHost(ctx->small_host);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; ++i) {
@@ -452,19 +462,21 @@ static int to_device_span(pss_ctx *ctx, DevBuf &b, const T *host, const int64_t 
     return PSS_OK;
 }
 
-static int upload_reads(pss_ctx *ctx, const pss_reads *H, pss_reads *D, bool need_seq, bool need_qual, cudaStream_t s) {
+static int upload_reads(pss_ctx *ctx, const pss_reads *H, pss_reads *D, bool need_seq, bool need_qual, cudaStream_t s,
+                        DevBuf *hb = nullptr) {
+    if (!hb) hb = ctx->hb;
     *D = *H;
     size_t n = (size_t)H->n_reads;
     int rc;
-#define UP(idx, field, count) if ((rc = to_device(ctx, ctx->hb[idx], H->field, (count), &D->field, s)) != PSS_OK) return rc
-#define UPS(idx, field, off) if ((rc = to_device_span(ctx, ctx->hb[idx], H->field, H->off, n, &D->field, s)) != PSS_OK) return rc
+#define UP(idx, field, count) if ((rc = to_device(ctx, hb[idx], H->field, (count), &D->field, s)) != PSS_OK) return rc
+#define UPS(idx, field, off) if ((rc = to_device_span(ctx, hb[idx], H->field, H->off, n, &D->field, s)) != PSS_OK) return rc
     UP(0, pos, n); UP(1, flag, n); UP(2, mapq, n); UP(3, tlen, n); UP(4, mtid, n); UP(5, l_seq, n);
     UP(6, cigar_off, n + 1); UP(8, seq_off, n + 1);
     if (n > 0) { UPS(7, cigar, cigar_off); }
     if (need_seq && n > 0) { UPS(9, seq4, seq_off); }
     else {   // never dereferenced, but must be non-NULL for the argument check
-        if ((rc = ensure(ctx, ctx->hb[9], 16)) != PSS_OK) return rc;
-        D->seq4 = (const uint8_t *)ctx->hb[9].p;
+        if ((rc = ensure(ctx, hb[9], 16)) != PSS_OK) return rc;
+        D->seq4 = (const uint8_t *)hb[9].p;
     }
     if (need_qual && n > 0) {
         UP(10, qual_off, n + 1); UPS(11, qual, qual_off); UP(12, name_prev, n);
@@ -483,7 +495,7 @@ static bool stat_reads_seq(int stat) {
 // One statistic over [start, end), int32 columns straight to the caller's host buffer: position
 // chunks of <= ~256 MB of output, two device buffers alternating against the D2H copies.
 static int host_stat_wide(pss_ctx *ctx, const pss_reads *D, const pss_pileup_params *Pd, bool q, int32_t *out,
-                          uint8_t *rowmask, cudaStream_t s, int *slot) {
+                          int64_t ostride, uint8_t *rowmask, cudaStream_t s, int *slot) {
     int rc;
     const int nf = kPileupFields[Pd->stat];
     const int64_t npos = Pd->end - Pd->start;
@@ -507,7 +519,7 @@ static int host_stat_wide(pss_ctx *ctx, const pss_reads *D, const pss_pileup_par
             return rc;
         CU(cudaEventRecord(ctx->ev_done[b], s));
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
-        CU(cudaMemcpy2DAsync(out + (cs - Pd->start), sizeof(int32_t) * (size_t)npos, ctx->outbuf[b].p,
+        CU(cudaMemcpy2DAsync(out + (cs - Pd->start), sizeof(int32_t) * (size_t)ostride, ctx->outbuf[b].p,
                              sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)cn, (size_t)nf,
                              cudaMemcpyDeviceToHost, ctx->copy_stream));
         CU(cudaMemcpyAsync(rowmask + (cs - Pd->start), ctx->maskbuf[b].p, (size_t)cn, cudaMemcpyDeviceToHost,
@@ -530,7 +542,7 @@ static int host_stat_wide(pss_ctx *ctx, const pss_reads *D, const pss_pileup_par
 // PCIe, and the worker pool widens them into the caller's int32 columns while the next chunks
 // are computed and copied.  Three buffers rotate: compute k, copy k - 1, widen k - 2.
 static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_params *Pd, bool q, int32_t *out,
-                            uint8_t *rowmask, cudaStream_t s) {
+                            int64_t ostride, uint8_t *rowmask, cudaStream_t s) {
     int rc;
     const int nf = kPileupFields[Pd->stat];
     const int64_t npos = Pd->end - Pd->start;
@@ -603,7 +615,7 @@ static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_p
         for (int f = 0; f < nf; ++f)
             for (int64_t o = 0; o < cn; o += piece) {
                 const uint8_t *sp = src + ((size_t)f * stride + o) * e;
-                int32_t *dp = out + (size_t)f * npos + (cs - Pd->start) + o;
+                int32_t *dp = out + (size_t)f * (size_t)ostride + (cs - Pd->start) + o;
                 size_t len = (size_t)((cn - o) < piece ? (cn - o) : piece);
                 if (e == 1) t = pss_pool_submit(pool, [sp, dp, len] { pss_widen_u8(sp, dp, len); });
                 else t = pss_pool_submit(pool, [sp, dp, len] { pss_widen_u16((const uint16_t *)sp, dp, len); });
@@ -634,42 +646,15 @@ static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_p
     return ovf ? PSS_ERETRY_WIDE : PSS_OK;
 }
 
-extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_pileup_params *P,
-                                     int32_t *const *outs, uint8_t *const *rowmasks) {
-    if (!ctx) return PSS_EINVAL;
-    if (n_stats < 1 || !P || !outs || !rowmasks) return fail(ctx, PSS_EINVAL, "n_stats < 1 or a NULL array");
+// One batch (already the reads of [P[0].start, P[0].end) plus their halo), all statistics: prepare once, then
+// every statistic through the narrow / int32 result pipelines.  D: device copy of the batch, on stream s.
+// outs[i] rows are `ostride` elements apart.
+static int host_multi_run(pss_ctx *ctx, const pss_reads *H, const pss_reads *D, int32_t n_stats, const pss_pileup_params *P,
+                          const uint8_t *ref_dev, bool need_qual, int32_t *const *outs, int64_t ostride, uint8_t *const *rowmasks,
+                          cudaStream_t s) {
     int rc;
-    bool need_qual = false, need_seq = false;
-    for (int i = 0; i < n_stats; ++i) {
-        if ((rc = check_params(ctx, &P[i])) != PSS_OK) return rc;
-        if (P[i].stepper != P[0].stepper || P[i].max_depth != P[0].max_depth || P[i].min_mapq != P[0].min_mapq ||
-            (P[i].no_dup != 0) != (P[0].no_dup != 0) || P[i].start != P[0].start || P[i].end != P[0].end)
-            return fail(ctx, PSS_EINVAL, "statistics of one call must share stepper, max_depth, min_mapq, no_dup, start, end");
-        if (P[i].ref && P[0].ref && (P[i].ref != P[0].ref || P[i].ref_start != P[0].ref_start || P[i].ref_len != P[0].ref_len))
-            return fail(ctx, PSS_EINVAL, "statistics of one call must share the reference span");
-        bool q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
-        need_qual |= q;
-        need_seq |= q || stat_reads_seq(P[i].stat);   // the overlap tweak compares the mates' bases
-        if (P[i].end > P[i].start && (!outs[i] || !rowmasks[i])) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
-    }
-    if ((rc = check_reads(ctx, reads, need_qual)) != PSS_OK) return rc;
-    CU(cudaSetDevice(ctx->device));
-    ctx->prepared = false;
-    cudaStream_t s = nullptr;   // default stream for compute, ctx->copy_stream for D2H
-    static const bool trace = getenv("PSS_TRACE") != nullptr;
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_begin = trace ? now() : 0, t_up = 0, t_enq = 0;
-    pss_reads D;
-    if ((rc = upload_reads(ctx, reads, &D, need_seq, need_qual, s)) != PSS_OK) return rc;
-    if (trace) { cudaStreamSynchronize(s); t_up = now(); }
-    const uint8_t *ref_host = nullptr, *ref_dev = nullptr;
-    for (int i = 0; i < n_stats && !ref_host; ++i)
-        if (P[i].ref && P[i].ref_len > 0) {
-            ref_host = P[i].ref;
-            if ((rc = to_device(ctx, ctx->hb[13], P[i].ref, (size_t)P[i].ref_len, &ref_dev, s)) != PSS_OK) return rc;
-        }
-    if ((rc = prepare_batch(ctx, &D, P[0].stepper, P[0].max_depth, P[0].min_mapq, P[0].no_dup, need_qual, nullptr, nullptr,
-                            s, (need_qual && reads->n_reads > 0) ? reads->qual_off[0] : 0)) != PSS_OK)
+    if ((rc = prepare_batch(ctx, D, P[0].stepper, P[0].max_depth, P[0].min_mapq, P[0].no_dup, need_qual, nullptr, nullptr,
+                            s, (need_qual && H->n_reads > 0) ? H->qual_off[0] : 0)) != PSS_OK)
         return rc;
     int k = 0;     // running buffer slot of the int32 pipeline
     for (int i = 0; i < n_stats; ++i) {
@@ -681,17 +666,145 @@ extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32
         const bool narrow = !no_narrow && tile_kernel_counting(P[i].stat) && P[i].min_baseq <= 0 && P[i].stat != PSS_COVERAGE_GC &&
                             !(P[i].flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
         if (narrow) {
-            rc = host_stat_narrow(ctx, &D, &Pd, q, outs[i], rowmasks[i], s);
+            rc = host_stat_narrow(ctx, D, &Pd, q, outs[i], ostride, rowmasks[i], s);
             if (rc != PSS_ERETRY_WIDE) { if (rc != PSS_OK) return rc; continue; }
         }
-        if ((rc = host_stat_wide(ctx, &D, &Pd, q, outs[i], rowmasks[i], s, &k)) != PSS_OK) return rc;
+        if ((rc = host_stat_wide(ctx, D, &Pd, q, outs[i], ostride, rowmasks[i], s, &k)) != PSS_OK) return rc;
     }
-    if (trace) t_enq = now();
     CU(cudaStreamSynchronize(ctx->copy_stream));
-    if (trace)
-        fprintf(stderr, "[pss] host_multi: upload %.1f ms, enqueue %.1f ms, drain %.1f ms (%d buffers)\n",
-                (t_up - t_begin) * 1e3, (t_enq - t_up) * 1e3, (now() - t_enq) * 1e3, k);
+    return PSS_OK;
+}
+
+static int check_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_pileup_params *P,
+                       int32_t *const *outs, uint8_t *const *rowmasks, bool *need_qual, bool *need_seq) {
+    if (n_stats < 1 || !P || !outs || !rowmasks) return fail(ctx, PSS_EINVAL, "n_stats < 1 or a NULL array");
+    int rc;
+    *need_qual = *need_seq = false;
+    for (int i = 0; i < n_stats; ++i) {
+        if ((rc = check_params(ctx, &P[i])) != PSS_OK) return rc;
+        if (P[i].stepper != P[0].stepper || P[i].max_depth != P[0].max_depth || P[i].min_mapq != P[0].min_mapq ||
+            (P[i].no_dup != 0) != (P[0].no_dup != 0) || P[i].start != P[0].start || P[i].end != P[0].end)
+            return fail(ctx, PSS_EINVAL, "statistics of one call must share stepper, max_depth, min_mapq, no_dup, start, end");
+        if (P[i].ref && P[0].ref && (P[i].ref != P[0].ref || P[i].ref_start != P[0].ref_start || P[i].ref_len != P[0].ref_len))
+            return fail(ctx, PSS_EINVAL, "statistics of one call must share the reference span");
+        bool q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
+        *need_qual |= q;
+        *need_seq |= q || stat_reads_seq(P[i].stat);   // the overlap tweak compares the mates' bases
+        if (P[i].end > P[i].start && (!outs[i] || !rowmasks[i])) return fail(ctx, PSS_EINVAL, "out / rowmask is NULL");
+    }
+    return check_reads(ctx, reads, *need_qual);
+}
+
+extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_pileup_params *P,
+                                     int32_t *const *outs, uint8_t *const *rowmasks) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    bool need_qual = false, need_seq = false;
+    if ((rc = check_multi(ctx, reads, n_stats, P, outs, rowmasks, &need_qual, &need_seq)) != PSS_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    ctx->prepared = false;
+    cudaStream_t s = nullptr;   // default stream for compute, ctx->copy_stream for D2H
+    pss_reads D;
+    if ((rc = upload_reads(ctx, reads, &D, need_seq, need_qual, s)) != PSS_OK) return rc;
+    const uint8_t *ref_dev = nullptr;
+    for (int i = 0; i < n_stats && !ref_dev; ++i)
+        if (P[i].ref && P[i].ref_len > 0)
+            if ((rc = to_device(ctx, ctx->hb[13], P[i].ref, (size_t)P[i].ref_len, &ref_dev, s)) != PSS_OK) return rc;
+    if ((rc = host_multi_run(ctx, reads, &D, n_stats, P, ref_dev, need_qual, outs, P[0].end - P[0].start, rowmasks, s)) != PSS_OK)
+        return rc;
     return pss_synchronize(ctx, s);
+}
+
+// Whole-range streaming.  The range is cut into position chunks; chunk k + 1's reads (and reference slice)
+// go up on their own stream into the second set of device buffers while chunk k is computed, copied
+// back and widened, so the host -> device copies are hidden behind the (longer) result path.
+extern "C" int pss_pileup_host_stream(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_pileup_params *P,
+                                      int32_t *const *outs, uint8_t *const *rowmasks, int64_t max_span,
+                                      int64_t chunk_positions) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    bool need_qual = false, need_seq = false;
+    if ((rc = check_multi(ctx, reads, n_stats, P, outs, rowmasks, &need_qual, &need_seq)) != PSS_OK) return rc;
+    const int64_t start = P[0].start, end = P[0].end, npos = end - start;
+    if (chunk_positions <= 0) chunk_positions = 25000000;
+    chunk_positions = (chunk_positions + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
+    // name_prev indexes the whole batch, which a sub-range view cannot express: one call then
+    if (need_qual || max_span < 1 || npos <= chunk_positions || reads->n_reads == 0)
+        return pss_pileup_host_multi(ctx, reads, n_stats, P, outs, rowmasks);
+    for (int i = 0; i < n_stats; ++i)
+        if (P[i].stat == PSS_COVERAGE_GC) return pss_pileup_host_multi(ctx, reads, n_stats, P, outs, rowmasks);
+    CU(cudaSetDevice(ctx->device));
+    ctx->prepared = false;
+    if (!ctx->up_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t s = nullptr;
+    const int64_t n = reads->n_reads;
+    const int32_t *pos = reads->pos;
+    auto lower = [&](int64_t key) {     // first read index with pos >= key
+        int64_t lo = 0, hi = n;
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((int64_t)pos[mid] < key) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    const int64_t nchunks = (npos + chunk_positions - 1) / chunk_positions;
+    const uint8_t *ref_host = nullptr;
+    int64_t ref_start = 0, ref_len = 0;
+    for (int i = 0; i < n_stats && !ref_host; ++i)
+        if (P[i].ref && P[i].ref_len > 0) { ref_host = P[i].ref; ref_start = P[i].ref_start; ref_len = P[i].ref_len; }
+    pss_reads Hk[2], Dk[2];
+    const uint8_t *refd[2] = {nullptr, nullptr};
+    int64_t refs[2] = {0, 0}, refl[2] = {0, 0};
+    auto upload = [&](int64_t k) -> int {        // enqueue the upload of chunk k on up_stream
+        const int b = (int)(k & 1);
+        const int64_t c_lo = start + k * chunk_positions, c_hi = std::min(end, c_lo + chunk_positions);
+        const int64_t i0 = lower(c_lo - max_span + 1), i1 = lower(c_hi);
+        pss_reads v = *reads;
+        v.n_reads = i1 - i0;
+        v.pos += i0; v.flag += i0; v.mapq += i0; v.tlen += i0; v.mtid += i0; v.l_seq += i0;
+        v.cigar_off += i0; v.seq_off += i0;
+        Hk[b] = v;
+        DevBuf *hb = b ? ctx->hb2 : ctx->hb;
+        if (k >= 2) CU(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_free[b], 0));   // chunk k - 2 is done with these buffers
+        int r = upload_reads(ctx, &v, &Dk[b], need_seq, false, ctx->up_stream, hb);
+        if (r != PSS_OK) return r;
+        refd[b] = nullptr;
+        if (ref_host) {                          // the chunk's slice of the reference
+            int64_t lo = std::max(ref_start, c_lo), hi = std::min(ref_start + ref_len, c_hi);
+            if (hi > lo) {
+                if ((r = to_device(ctx, hb[13], ref_host + (lo - ref_start), (size_t)(hi - lo), &refd[b], ctx->up_stream)) != PSS_OK) return r;
+                refs[b] = lo; refl[b] = hi - lo;
+            }
+        }
+        CU(cudaEventRecord(ctx->ev_up[b], ctx->up_stream));
+        return PSS_OK;
+    };
+    if ((rc = upload(0)) != PSS_OK) return rc;
+    std::vector<pss_pileup_params> Pc((size_t)n_stats);
+    std::vector<int32_t *> oc((size_t)n_stats);
+    std::vector<uint8_t *> mc((size_t)n_stats);
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int b = (int)(k & 1);
+        const int64_t c_lo = start + k * chunk_positions, c_hi = std::min(end, c_lo + chunk_positions);
+        if (k + 1 < nchunks && (rc = upload(k + 1)) != PSS_OK) return rc;
+        CU(cudaStreamWaitEvent(s, ctx->ev_up[b], 0));
+        for (int i = 0; i < n_stats; ++i) {
+            Pc[(size_t)i] = P[i];
+            Pc[(size_t)i].start = c_lo; Pc[(size_t)i].end = c_hi;
+            if (P[i].ref && P[i].ref_len > 0) { Pc[(size_t)i].ref = refd[b] ? P[i].ref : nullptr; Pc[(size_t)i].ref_start = refs[b]; Pc[(size_t)i].ref_len = refd[b] ? refl[b] : 0; }
+            oc[(size_t)i] = outs[i] + (c_lo - start);
+            mc[(size_t)i] = rowmasks[i] + (c_lo - start);
+        }
+        if ((rc = host_multi_run(ctx, &Hk[b], &Dk[b], n_stats, Pc.data(), refd[b], false, oc.data(), npos, mc.data(), s)) != PSS_OK)
+            return rc;
+        CU(cudaEventRecord(ctx->ev_free[b], s));
+        if ((rc = pss_synchronize(ctx, s)) != PSS_OK) return rc;       // unsorted / too long reads are reported per chunk
+    }
+    CU(cudaStreamSynchronize(ctx->up_stream));
+    return PSS_OK;
 }
 
 extern "C" int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *P, int32_t *out,

@@ -251,3 +251,28 @@ def test_narrow_transport_levels(stat, ctx, monkeypatch):
         assert out.max() > 255
         # most chunks travelled as bytes: well under the 16-bit volume
         assert d1 - d0 < 0.9 * (2 * out.size + mask.size), (d1 - d0, out.size)
+
+
+def test_streamed_host_call_equals_single_call(ctx, small, monkeypatch):
+    # pss_pileup_host_stream: the range is cut into chunks, chunk k + 1's reads are uploaded (a sub-range of
+    # the batch found from max_span) while chunk k is computed; same columns as one pss_pileup_host call
+    nb, ref, _ = small
+    monkeypatch.setenv('PSS_HOST_CHUNK', '4096')
+    d = dict(nb)
+    d['qual'] = d['qual_off'] = d['name_prev'] = None
+    rs = _cabi.make_reads_struct(d)
+    lo, hi = 1000, G - 321
+    stats = ('variation_strand', 'coverage_ext', 'coverage')
+    max_span = int((nb['endpos'] - nb['pos']).max())
+    for kw in (dict(), dict(no_del=True, min_mapq=30)):
+        ps, outs, masks = [], [], []
+        for s in stats:
+            withref = s in config.stats_types_withref
+            ps.append(ctx.pileup_params(s, start=lo, end=hi, ref=ref if withref else None, ref_start=0,
+                                        ref_len=len(ref) if withref else 0, contig_len=len(ref), **kw))
+            outs.append(np.full((len(config.value_fields(s)), hi - lo), -7, dtype=np.int32))
+            masks.append(np.full(hi - lo, 9, dtype=np.uint8))
+        ctx.pileup_host_stream(rs, ps, outs, masks, max_span, 20480)
+        for s, o, m in zip(stats, outs, masks):
+            e, em = _run_host(ctx, nb, ref, s, lo, hi, **kw)
+            assert np.array_equal(o, e) and np.array_equal(m, em), (s, kw)
