@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument('--depth', type=int, default=30)
     ap.add_argument('--read-len', type=int, default=150)
     ap.add_argument('--e2e-chunk-mb', type=float, default=25.0, help='positions per host call (size of the host result buffers)')
-    ap.add_argument('--e2e-inner-mb', type=float, default=6.25, help='positions per upload chunk inside one host call')
+    ap.add_argument('--e2e-stream', action='store_true', help='e2e through pss_pileup_host_stream (uploads in pieces, overlapped)')
+    ap.add_argument('--e2e-inner-mb', type=float, default=12.5, help='--e2e-stream: positions per upload piece inside one host call')
     ap.add_argument('--cpu-chunk-mb', type=float, default=1.0, help='CPU arm: positions per process, in Mb')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -318,9 +319,11 @@ def main():
                                                 contig_len=genome))
                     os_.append(oh[s] if n == chunk else np.ndarray((nf[s], n), dtype=np.int32, buffer=oh[s]))
                     ms.append(mh[s])
-                # one call per position chunk: the reads go up once (in pieces, behind the result path of the
-                # previous piece), both statistics come back
-                ctx.pileup_host_stream(rs, ps, os_, ms, maxspan, inner)
+                # one call per position chunk: the reads go up once, both statistics come back
+                if args.e2e_stream:
+                    ctx.pileup_host_stream(rs, ps, os_, ms, maxspan, inner)
+                else:
+                    ctx.pileup_host_multi(rs, ps, os_, ms)
                 if check:
                     for s, o in zip(STATS, os_):
                         checks[s] = checks.get(s, 0) + int(o[0].sum(dtype=np.int64))
@@ -342,9 +345,11 @@ def main():
         e2e = {'value': total_pos / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
                'h2d_bytes_per_step': int(sum_over_ranks((h1 - h0) / args.steps)),
                'd2h_bytes_per_step': int(sum_over_ranks((d1 - d0) / args.steps)),
-               'api': 'pss_pileup_host_stream (pinned host read arrays in, host int32 columns of both statistics out), '
-                      '%d calls of %d positions per step, reads uploaded in pieces of %d positions'
-                      % (-(-npos // chunk), chunk, inner)}
+               'api': ('pss_pileup_host_stream (pinned host read arrays in, host int32 columns of both statistics out), '
+                       '%d calls of %d positions per step, reads uploaded in pieces of %d positions'
+                       % (-(-npos // chunk), chunk, inner)) if args.e2e_stream else
+                      ('pss_pileup_host_multi (pinned host read arrays in, host int32 columns of both statistics out), '
+                       '%d position chunks of %d per step' % (-(-npos // chunk), chunk))}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
