@@ -70,6 +70,18 @@ int pss_bam_fill(const pss_bam *b, const pss_host_arrays *a);
 /* seconds spent in (file read, inflate, record index) by pss_bam_open and bytes inflated */
 int pss_bam_timing(const pss_bam *b, double *t_read, double *t_inflate, double *t_index, int64_t *raw_bytes);
 
+/* Packs columns into `n_rows` records of `row_bytes` bytes (the packed structured array load_* returns;
+ * replaces the np.fromiter row assembly of pysamstats/util.py:61-71): column c contributes n_bytes[c] bytes
+ * at offset dst_off[c] of every record, read from src[c] + row * src_stride[c] (stride 0: one constant value
+ * for every row; stride 8 with n_bytes 4: the low half of a little-endian int64). */
+int pss_pack_rows(uint8_t *dst, int64_t n_rows, int32_t row_bytes, int32_t n_cols, const void *const *src,
+                  const int32_t *src_stride, const int32_t *n_bytes, const int32_t *dst_off, int n_threads);
+
+/* dst[c * dst_stride + k] = src[c * src_stride + idx[k]] for n_cols int32 columns: compaction of the engine's
+ * per-position columns to the emitted rows (strides in elements). */
+int pss_take_cols_i32(const int32_t *src, int64_t src_stride, int32_t n_cols, const int64_t *idx, int64_t n,
+                      int32_t *dst, int64_t dst_stride, int n_threads);
+
 /* prev[i] = index of the previous row with the same (NUL padded, fixed width) name, or -1 */
 int pss_name_prev(const uint8_t *names, int64_t n, int32_t width, int32_t *prev);
 

@@ -172,7 +172,7 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
                                    window_size=stat.window_size, window_offset=stat.window_offset,
                                    start=lo, end=hi, ref=refseq if len(refseq) else None, ref_start=0,
                                    ref_len=len(refseq), contig_len=len(refseq))
-        out = np.empty((len(names), npos), dtype=np.int32)
+        out = bamio.alloc_big((len(names), npos), np.int32)
         rowmask = np.empty(npos, dtype=np.uint8)
         ctx.pileup_host(_reads_struct(batch, need_qual), params, out, rowmask)
         rows = rowmask.view(bool)
@@ -185,7 +185,8 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
         else:
             sel = np.flatnonzero(rows)
             pos = sel.astype(np.int64) + lo
-            fields = {f: out[j][sel] for j, f in enumerate(names)}
+            taken = bamio.take_cols(out, sel)
+            fields = {f: taken[j] for j, f in enumerate(names)}
         ref = _ref_column(refseq, pos) if name in config.ref_column_types else None
         if 'gc' in fields and len(pos) and fields['gc'].min() < 0:
             # the reference stores gc = -1 for an empty window into a u1 column, which numpy

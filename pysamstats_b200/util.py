@@ -6,9 +6,53 @@ are the reference's: default dtype list per statistic, ``chrom`` widened to the 
 contig name of the file, user dtype overrides, optional field subset (a single field
 gives a plain ndarray, unknown fields raise ``ValueError``).
 """
+import ctypes as C
+
 import numpy as np
 
 from . import bamio
+
+
+def _pack_native(a, o, m, fields, chrom, pos, ref, cols):
+    """Fill records a[o:o + m] through libpss_host's row packer; False when a column's type is not a plain
+    byte copy of what the engine produced (user dtype overrides), so the numpy path has to convert."""
+    lib = bamio.host_lib()
+    if lib is None or m == 0:
+        return False
+    dt = a.dtype
+    keep, src, stride, nbytes, off = [], [], [], [], []
+    for f in fields:
+        ft, fo = dt.fields[f][0], dt.fields[f][1]
+        if f == 'chrom':
+            if ft.kind != 'S':
+                return False
+            v = np.zeros(1, dtype=ft)
+            v[0] = chrom.encode('ascii')
+            col, st = v, 0
+        elif f == 'pos':
+            if ft != np.dtype('<i4') or pos.dtype != np.dtype('<i8'):
+                return False
+            col, st = np.ascontiguousarray(pos), 8            # low half of the little-endian int64
+        elif f == 'ref':
+            if ft != np.dtype('S1'):
+                return False
+            col, st = np.ascontiguousarray(ref), 1
+        else:
+            col = cols[f]
+            if ft != col.dtype or not col.flags.c_contiguous:
+                return False
+            st = col.dtype.itemsize
+        keep.append(col)
+        src.append(col.ctypes.data)
+        stride.append(st)
+        nbytes.append(ft.itemsize)
+        off.append(fo)
+    n = len(fields)
+    rc = lib.pss_pack_rows(a.ctypes.data + o * dt.itemsize, m, dt.itemsize, n, (C.c_void_p * n)(*src),
+                           (C.c_int32 * n)(*stride), (C.c_int32 * n)(*nbytes), (C.c_int32 * n)(*off), 0)
+    if rc != 0:
+        raise ValueError(lib.pss_host_error().decode('ascii', 'replace'))
+    return True
 
 
 def flatten(recs, *fields):
@@ -42,10 +86,13 @@ def load_stats(tablefun, default_dtype, user_dtype, user_fields, **kwargs):
 
     parts = list(tablefun(**kwargs))
     n = sum(len(p[1]) for p in parts)
-    a = np.zeros(n, dtype=dt)
+    a = np.zeros(n, dtype=dt) if single or bamio.host_lib() is None else bamio.alloc_big(n, dt)
     o = 0
     for chrom, pos, ref, cols in parts:
         m = len(pos)
+        if not single and _pack_native(a, o, m, fields, chrom, pos, ref, cols):
+            o += m
+            continue
         for f in fields:
             dst = a[o:o + m] if single else a[f][o:o + m]
             if f == 'chrom':

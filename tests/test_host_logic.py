@@ -266,3 +266,34 @@ def test_csv_block_formatter_equals_csv_writer():
                 w.writerow([chrom, int(pos[i]), ref[i].decode(), int(cols['reads_all'][i]), int(cols['gc'][i])])
             assert format_rows(fields, chrom, pos, ref, cols, dialect) == buf.getvalue(), (chrom, dialect)
     assert format_rows(['pos'], 'x', pos[:0], None, {}, 'excel') == ''
+
+
+def test_native_row_packer_and_column_gather_equal_numpy():
+    # load_* assembles its packed structured array through libpss_host (pss_pack_rows) and compacts the
+    # engine's per-position columns with pss_take_cols_i32: same bytes as the numpy field-by-field path
+    from pysamstats_b200 import util
+    rng = np.random.default_rng(11)
+    names = config.value_fields('variation_strand')
+    n = 70001
+    dt = np.dtype([('chrom', 'S11'), ('pos', 'i4'), ('ref', 'S1')] + [(f, 'i4') for f in names])
+    assert dt.itemsize == 256                                   # the packed layout of regression.npz
+    cols = {f: rng.integers(0, 1 << 20, n).astype('i4') for f in names}
+    pos = rng.integers(0, 1 << 30, n).astype('i8')
+    ref = rng.choice([b'A', b'C', b'', b'N'], n).astype('S1')
+    a = np.empty(n + 5, dtype=dt)
+    a[:] = a[0]
+    assert util._pack_native(a, 3, n, list(dt.names), 'Pf3D7_01_v3', pos, ref, cols)
+    b = np.zeros(n, dtype=dt)
+    b['chrom'], b['pos'], b['ref'] = b'Pf3D7_01_v3', pos, ref
+    for f in names:
+        b[f] = cols[f]
+    assert a[3:3 + n].tobytes() == b.tobytes()
+    # a user dtype the packer cannot copy byte for byte falls back to numpy
+    dt2 = np.dtype([('chrom', 'S4'), ('pos', 'i8'), ('reads_all', 'i4')])
+    assert not util._pack_native(np.empty(n, dtype=dt2), 0, n, list(dt2.names), 'c', pos, None, cols)
+    out = rng.integers(0, 100, (7, 1 << 20)).astype('i4')
+    sel = np.flatnonzero(rng.random(out.shape[1]) < 0.7)
+    assert np.array_equal(bamio.take_cols(out, sel), out[:, sel])
+    big = bamio.alloc_big((3, 12_000_000), np.int32)            # huge-page backed
+    big[:] = 5
+    assert big.shape == (3, 12_000_000) and int(big.sum()) == 5 * big.size
