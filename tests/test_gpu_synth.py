@@ -183,6 +183,16 @@ def test_very_deep_single_position(ctx):
     # the depth cap at the default 8000: the first read is always admitted, then up to the cap
     out, mask = _run_host(ctx, nb, ref, 'coverage', 900, 1300)
     assert out[0][150] == 8000
+    # the quality kinds keep 64-bit squared sums: a tile this deep is still one exact pass
+    nq = dict(nb, qual=np.full(n * L, 30, 'u1'), qual_off=np.arange(n + 1, dtype='i8') * L,
+              name_prev=np.full(n, -1, 'i4'))
+    for stat, rms in (('baseq_strand', 'rms_baseq'), ('mapq_strand', 'rms_mapq'), ('baseq_ext', 'rms_baseq')):
+        out, mask = _run_host(ctx, nq, ref, stat, 900, 1300, max_depth=1000000)
+        col = {f: out[j] for j, f in enumerate(config.value_fields(stat))}
+        assert np.array_equal(col['reads_all'], cov), stat
+        assert np.array_equal(col[rms], np.where(cov > 0, 30 if 'baseq' in stat else 60, 0)), stat
+        if stat == 'mapq_strand':
+            assert np.array_equal(col['max_mapq_fwd'], np.where(cov > 0, 60, 0))
 
 
 @pytest.mark.parametrize('stat', config.binned_types)
