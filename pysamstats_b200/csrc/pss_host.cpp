@@ -8,6 +8,10 @@
 //  next_pos, tlen, read_name, cigar, seq, qual, aux}.
 #include "../../include/pss_host.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -54,11 +58,62 @@ static void parallel_for(int64_t n, int n_threads, F f) {
     for (auto &x : th) x.join();
 }
 
+// Large byte buffer that is NOT zero-filled on allocation and asks for transparent huge pages: the
+// inflate threads are the first to touch it, and with 4 KiB pages their page faults (serialised in
+// the kernel) cost more than the inflation itself.
+struct BigBuf {
+    uint8_t *p = nullptr;
+    size_t n = 0, cap = 0;
+    BigBuf() {}
+    BigBuf(const BigBuf &) = delete;
+    BigBuf &operator=(const BigBuf &) = delete;
+    ~BigBuf() { release(); }
+    void release() { if (p) munmap(p, cap); p = nullptr; n = cap = 0; }
+    bool resize(size_t bytes) {         // contents are not preserved
+        release();
+        if (bytes == 0) { n = 0; return true; }
+        const size_t huge = (size_t)2 << 20;
+        cap = (bytes + huge - 1) / huge * huge;
+        void *m = mmap(nullptr, cap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m == MAP_FAILED) { cap = 0; return false; }
+#ifdef MADV_HUGEPAGE
+        madvise(m, cap, MADV_HUGEPAGE);
+#endif
+        p = (uint8_t *)m; n = bytes;
+        return true;
+    }
+    uint8_t *data() { return p; }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return n; }
+};
+
+// read-only mapping of a whole file (no copy into a buffer of our own)
+struct FileMap {
+    const uint8_t *p = nullptr;
+    size_t n = 0;
+    ~FileMap() { if (p) munmap((void *)p, n); }
+    bool open(const char *path) {
+        int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { ::close(fd); return false; }
+        n = (size_t)st.st_size;
+        if (n == 0) { ::close(fd); p = nullptr; return true; }
+        void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        ::close(fd);
+        if (m == MAP_FAILED) { n = 0; return false; }
+        madvise(m, n, MADV_SEQUENTIAL);
+        madvise(m, n, MADV_WILLNEED);
+        p = (const uint8_t *)m;
+        return true;
+    }
+};
+
 struct Blk { int64_t in_off, in_len, out_off, out_len, file_off; };   // payload span, inflated span, block start in the file
 
 struct pss_bam {
     std::vector<Blk> blocks;             // BGZF blocks behind `raw` (whole-file open only)
-    std::vector<uint8_t> raw;            // inflated BAM stream
+    BigBuf raw;                          // inflated BAM stream
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
     std::vector<int64_t> rec;            // offset of each record's refID field in raw
@@ -75,14 +130,10 @@ extern "C" int pss_bam_open(const char *path, int n_threads, pss_bam **out) {
     *out = nullptr;
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     double t0 = now();
-    FILE *fh = fopen(path, "rb");
-    if (!fh) return fail(-2, "cannot open %s", path);
-    fseek(fh, 0, SEEK_END);
-    long long fsize = ftell(fh);
-    fseek(fh, 0, SEEK_SET);
-    std::vector<uint8_t> comp((size_t)fsize);
-    if (fsize > 0 && fread(comp.data(), 1, (size_t)fsize, fh) != (size_t)fsize) { fclose(fh); return fail(-2, "short read on %s", path); }
-    fclose(fh);
+    FileMap fm;
+    if (!fm.open(path)) return fail(-2, "cannot open %s", path);
+    const long long fsize = (long long)fm.n;
+    const uint8_t *comp = fm.p;
     double t1 = now();
     // block table
     std::vector<Blk> blocks;
@@ -106,48 +157,68 @@ extern "C" int pss_bam_open(const char *path, int n_threads, pss_bam **out) {
     }
     pss_bam *b = new pss_bam();
     b->n_threads = n_threads;
-    b->raw.resize((size_t)total);
+    if (!b->raw.resize((size_t)total)) { delete b; return fail(-8, "cannot allocate %lld bytes", (long long)total); }
     std::atomic<int> bad(0);
     std::atomic<int64_t> next(0);
-    {
-        std::vector<std::thread> th;
-        for (int t = 0; t < n_threads; ++t)
-            th.emplace_back([&] {
-                z_stream zs;
-                memset(&zs, 0, sizeof(zs));
-                if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-                for (;;) {
-                    int64_t k0 = next.fetch_add(16);
-                    if (k0 >= (int64_t)blocks.size()) break;
-                    int64_t k1 = std::min<int64_t>(blocks.size(), k0 + 16);
-                    for (int64_t k = k0; k < k1; ++k) {
-                        const Blk &bl = blocks[k];
-                        if (bl.out_len == 0) continue;
+    // the blocks are inflated by n_threads workers while THIS thread already parses the header and walks the
+    // block_size chain of the records behind the frontier of contiguously inflated blocks
+    std::vector<std::atomic<uint8_t>> done(blocks.size());
+    for (auto &d : done) d.store(0, std::memory_order_relaxed);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&] {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+            for (;;) {
+                int64_t k0 = next.fetch_add(16);
+                if (k0 >= (int64_t)blocks.size()) break;
+                int64_t k1 = std::min<int64_t>(blocks.size(), k0 + 16);
+                for (int64_t k = k0; k < k1; ++k) {
+                    const Blk &bl = blocks[k];
+                    if (bl.out_len != 0) {
                         inflateReset(&zs);
-                        zs.next_in = comp.data() + bl.in_off; zs.avail_in = (uInt)bl.in_len;
+                        zs.next_in = (Bytef *)(comp + bl.in_off); zs.avail_in = (uInt)bl.in_len;
                         zs.next_out = b->raw.data() + bl.out_off; zs.avail_out = (uInt)bl.out_len;
                         int rc = inflate(&zs, Z_FINISH);
                         if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
                     }
+                    done[(size_t)k].store(1, std::memory_order_release);
                 }
-                inflateEnd(&zs);
-            });
-        for (auto &x : th) x.join();
-    }
-    if (bad) { delete b; return fail(-3, "corrupt BGZF block in %s", path); }
-    std::vector<uint8_t>().swap(comp);
-    double t2 = now();
+            }
+            inflateEnd(&zs);
+        });
+    auto join_all = [&] { for (auto &x : th) if (x.joinable()) x.join(); };
+    struct Joiner { std::vector<std::thread> &t; ~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); } } joiner{th};
+    size_t frontier = 0;
+    int64_t avail = 0;
+    auto wait_for = [&](int64_t need) -> bool {        // bytes [0, need) of the stream are inflated (need <= total)
+        while (avail < need) {
+            while (frontier < blocks.size() && done[frontier].load(std::memory_order_acquire)) ++frontier;
+            avail = frontier < blocks.size() ? blocks[frontier].out_off : total;
+            if (avail >= need) break;
+            if (bad) return false;
+            std::this_thread::yield();
+        }
+        return true;
+    };
+#define NEED(x) do { if (!wait_for(x)) { join_all(); delete b; return fail(-3, "corrupt BGZF block in %s", path); } } while (0)
     const uint8_t *r = b->raw.data();
-    const int64_t n = (int64_t)b->raw.size();
-    if (n < 12 || memcmp(r, "BAM\1", 4) != 0) { delete b; return fail(-4, "not a BAM file: %s", path); }
+    const int64_t n = total;
+    if (n < 12) { join_all(); delete b; return fail(-4, "not a BAM file: %s", path); }
+    NEED(12);
+    if (memcmp(r, "BAM\1", 4) != 0) { join_all(); delete b; return fail(-4, "not a BAM file: %s", path); }
     int64_t p = 8 + rdi32(r + 4);
-    if (p + 4 > n) { delete b; return fail(-4, "truncated BAM header"); }
+    if (p + 4 > n) { join_all(); delete b; return fail(-4, "truncated BAM header"); }
+    NEED(p + 4);
     int32_t n_ref = rdi32(r + p);
     p += 4;
     for (int32_t i = 0; i < n_ref; ++i) {
-        if (p + 4 > n) { delete b; return fail(-4, "truncated BAM header"); }
+        if (p + 4 > n) { join_all(); delete b; return fail(-4, "truncated BAM header"); }
+        NEED(p + 4);
         int32_t l_name = rdi32(r + p);
-        if (l_name < 1 || p + 8 + l_name > n) { delete b; return fail(-4, "truncated BAM header"); }
+        if (l_name < 1 || p + 8 + l_name > n) { join_all(); delete b; return fail(-4, "truncated BAM header"); }
+        NEED(p + 8 + l_name);
         b->ref_names.emplace_back((const char *)(r + p + 4), (size_t)(l_name - 1));
         b->ref_lens.push_back(rdi32(r + p + 4 + l_name));
         p += 8 + l_name;
@@ -156,13 +227,15 @@ extern "C" int pss_bam_open(const char *path, int n_threads, pss_bam **out) {
     int maxname = 1;
     b->cig_off.push_back(0); b->seq_off.push_back(0); b->qual_off.push_back(0);
     while (p < n) {
-        if (p + 36 > n) { delete b; return fail(-4, "truncated BAM record at %lld", (long long)p); }
+        if (p + 36 > n) { join_all(); delete b; return fail(-4, "truncated BAM record at %lld", (long long)p); }
+        NEED(p + 36);
         int32_t bs = rdi32(r + p);
-        if (bs < 32 || p + 4 + bs > n) { delete b; return fail(-4, "bad BAM record size at %lld", (long long)p); }
+        if (bs < 32 || p + 4 + bs > n) { join_all(); delete b; return fail(-4, "bad BAM record size at %lld", (long long)p); }
         const uint8_t *q = r + p + 4;
         int l_name = q[8], n_cig = rd16(q + 12);
         int32_t l_seq = rdi32(q + 16);
         if (l_seq < 0 || 32 + (int64_t)l_name + 4ll * n_cig + (l_seq + 1) / 2 + l_seq > bs) {
+            join_all();
             delete b;
             return fail(-4, "inconsistent BAM record at %lld", (long long)p);
         }
@@ -173,6 +246,11 @@ extern "C" int pss_bam_open(const char *path, int n_threads, pss_bam **out) {
         maxname = std::max(maxname, l_name > 0 ? l_name - 1 : 0);
         p += 4 + bs;
     }
+    NEED(total);
+#undef NEED
+    join_all();
+    if (bad) { delete b; return fail(-3, "corrupt BGZF block in %s", path); }
+    double t2 = now();          // inflate and the (overlapped) record index are done
     b->name_width = std::max(1, maxname);
     b->blocks.swap(blocks);
     b->t_read = t1 - t0; b->t_inflate = t2 - t1; b->t_index = now() - t2;
@@ -429,7 +507,7 @@ extern "C" int pss_bam_open_region(const char *path, const char *bai_path, int32
         pieces.push_back(pc);
     }
     const double t1 = now();
-    b->raw.resize((size_t)total);
+    if (!b->raw.resize((size_t)total)) return fail(-8, "cannot allocate %lld bytes", (long long)total);
     {
         std::atomic<int> bad(0);
         std::atomic<int64_t> next(0);
