@@ -22,7 +22,7 @@ struct pss_ctx {
     char err[512] = {0};
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // moved by the *_host entry points
-    DevBuf ri, rng, qual, pair, next, small, tdesc, refpack, bwork;
+    DevBuf ri, rng, qual, pair, next, small, tdesc, refpack, bwork, redo;
     int64_t qual_bias = 0;  // ctx->qual holds bytes [qual_bias, qual_bias + n) of the batch's qual array
     // batch prepared by pss_prepare()
     bool prepared = false;
@@ -149,7 +149,7 @@ extern "C" void pss_destroy(pss_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small, &ctx->tdesc, &ctx->refpack, &ctx->bwork,
+    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small, &ctx->tdesc, &ctx->refpack, &ctx->bwork, &ctx->redo,
                      &ctx->outbuf[0], &ctx->outbuf[1], &ctx->maskbuf[0], &ctx->maskbuf[1]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->hb) if (b.p) cudaFree(b.p);
@@ -305,6 +305,8 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.toolong = &((SmallState *)ctx->small.p)->toolong;
     a.tlen = (P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND) ? R->tlen : nullptr;
     a.tile_rng = nullptr;
+    a.tile_redo = nullptr;
+    a.n_reads = R->n_reads;
     a.ref = P->ref; a.ref_start = P->ref_start; a.ref_len = P->ref_len;
     a.start = start; a.end = end;
     a.min_baseq = P->min_baseq; a.no_del = P->no_del;
@@ -326,9 +328,25 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
         int need_raw = (P->min_mapq > 0 || P->no_dup || P->no_del) ? 1 : 0;
         // descriptors depend on the batch and the position range only: reused by the next statistic
         const bool desc_valid = ctx->desc_start == start && ctx->desc_end == end;
+        const bool is_tlen = P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND;
+        if (is_tlen) {
+            if ((rc = ensure(ctx, ctx->redo, tile_redo_bytes(ntiles))) != PSS_OK) return rc;
+            CU(cudaMemsetAsync(ctx->redo.p, 0, tile_redo_bytes(ntiles), s));
+            a.tile_redo = (int32_t *)ctx->redo.p;
+        }
         CU(launch_tile(P->stat, a, R->seq_off, R->n_reads, (SmallState *)ctx->small.p, need_raw, ntiles, ctx->tdesc.p,
                        ctx->refpack.p, desc_valid, s, &ctx->launches, e0, e1));
         ctx->desc_start = start; ctx->desc_end = end;
+        if (is_tlen) {
+            // the in-order Welford replay for the tiles whose std_tlen is too close to a rounding boundary to be
+            // decided from the exact sums (its CTAs return at once for every other tile)
+            const int64_t gtiles = (npos + PSS_TILE - 1) / PSS_TILE;
+            if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)gtiles)) != PSS_OK) return rc;
+            CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, gtiles,
+                                  PSS_TILE, (int2 *)ctx->rng.p, s, &ctx->launches));
+            a.tile_rng = (const int2 *)ctx->rng.p;
+            CU(launch_pileup(P->stat, a, gtiles, true, s, &ctx->launches));
+        }
     } else {
         if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)ntiles)) != PSS_OK) return rc;
         CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, ntiles,

@@ -493,6 +493,8 @@ k_pileup(PileupArgs a) {
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
+    // replay pass behind k_tilet: only the 512-position tiles it flagged
+    if (a.tile_redo && a.tile_redo[(int64_t)tile * PSS_TILE / PSS_TTILE] == 0) return;
     const int64_t t0 = a.start + (int64_t)tile * PSS_TILE;
     const int64_t pl = t0 + tid;
     const bool valid = pl < a.end;

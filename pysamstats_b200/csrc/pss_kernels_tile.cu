@@ -1219,6 +1219,225 @@ k_tileq(TileArgs A) {
     }
 }
 
+// ------------------------------------------------------------------ tlen, tlen_strand
+//
+// TlenHelper (opt.pyx:679-727) keeps, per class, n, sum(tlen), sum(tlen^2) -- constant along a read, so pure
+// interval adds like the coverage counters (32-bit counts, 64-bit sums, difference arrays + prefix scan)
+// -- and Welford's running mean / M2 in doubles, whose rounding depends on the column (file) order.
+// The finalisation computes std_tlen = rint(sqrt(M2 / (n - 1))) from the EXACT integer sums:
+// M2 = A / n with A = n sum(t^2) - sum(t)^2, so the decision between k and k + 1 is the sign of
+// 4 A - (2k + 1)^2 n (n - 1), evaluated in 128-bit integers.  Welford's computed M2 differs from the exact
+// one by at most a few n u kappa^2 relative (u = 2^-53, kappa^2 = n sum(t^2) / A the condition number of the
+// variance; Chan, Golub & LeVeque 1983), so whenever |4 A - (2k + 1)^2 n (n - 1)| is above
+// 256 n^2 sum(t^2) u -- 64x that bound -- the rounded value is the reference's whatever the order.
+// Positions that are closer to a rounding boundary than that (in practice: exact ties, e.g. std = 0.5)
+// flag their tile, and k_pileup<AccTlen> -- the in-order Welford replay -- recomputes the flagged
+// tiles right after this kernel (its CTAs return at once for all other tiles).
+//
+// word arrays of TT: nfwd[0] nrev[1] | class c = paired fwd, paired rev, pp fwd, pp rev: n[2 + c] (32-bit
+// difference arrays) | sum[c] 64-bit at words 6.., sumsq[c] 64-bit at words 14.. (64-bit difference arrays)
+#define TLEN_NW 22
+#define TLEN_NT 256
+
+__device__ __forceinline__ void interval_add64(unsigned long long *arr, int x, int l, int t0, unsigned long long inc) {
+    int a = max(x - t0, 0), b = min(x + l - t0, TT);
+    if (a < b) {
+        atomicAdd(arr + a, inc);
+        if (b < TT) atomicAdd(arr + b, 0ull - inc);
+    }
+}
+
+// in-place inclusive prefix sum of TT 64-bit words by one warp (lane l owns words [64 k + 2 l, 64 k + 2 l + 2))
+__device__ __forceinline__ void warp_scan_array64(unsigned long long *arr, int lane) {
+    unsigned long long carry = 0;
+#pragma unroll 1
+    for (int k = 0; k < TT / 64; ++k) {
+        ulonglong2 v = *reinterpret_cast<ulonglong2 *>(arr + 64 * k + 2 * lane);
+        v.y += v.x;
+        unsigned long long inc = v.y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const unsigned long long off = carry + inc - v.y;
+        carry += __shfl_sync(FULL, inc, 31);
+        v.x += off; v.y += off;
+        *reinterpret_cast<ulonglong2 *>(arr + 64 * k + 2 * lane) = v;
+    }
+}
+
+// std from the exact sums; *amb: the reference's (order dependent) Welford value could round differently
+template <class U>       // U = unsigned long long when every product below fits 64 bits, else unsigned __int128
+__device__ __forceinline__ int tlen_std_t(unsigned long long n, U ss, unsigned long long Q, bool *amb, float force) {
+    const U nq = (U)n * (U)Q;
+    const U A = nq >= ss ? nq - ss : 0;                    // n sum(t^2) - sum(t)^2 >= 0
+    const U B = (U)n * (U)(n - 1);
+    const double est = sqrt((double)A / (double)B);
+    unsigned long long k = est > 0.5 ? (unsigned long long)(est - 0.5) : 0;        // <= floor(sqrt(A / B)) up to rounding
+    while ((U)k * k * B > A) --k;
+    while ((U)(k + 1) * (k + 1) * B <= A) ++k;
+    const U T = (U)(2 * k + 1) * (2 * k + 1) * B, F = 4 * A;
+    const U D = F > T ? F - T : T - F;
+    const double thr = 256.0 * (double)n * (double)n * (double)Q * 1.1102230246251565e-16 + force;
+    if (D == 0 || (double)D <= thr) *amb = true;
+    return (int)(k + (F > T ? 1u : F == T ? (k & 1u) : 0u));
+}
+__device__ __forceinline__ int tlen_std(long long n, long long S, unsigned long long Q, bool *amb, float force) {
+    if (n < 2) return 0;
+    // n sum(t^2) < 2^60: sum(t)^2 <= n sum(t^2), 4 A and (2k + 1)^2 n (n - 1) ~ 4 A stay below 2^63
+    if (n < (1 << 20) && Q < (1ull << 40)) {
+        const unsigned long long a = (unsigned long long)(S < 0 ? -S : S);
+        return tlen_std_t<unsigned long long>((unsigned long long)n, a * a, Q, amb, force);
+    }
+    return tlen_std_t<unsigned __int128>((unsigned long long)n, (unsigned __int128)((__int128)S * (__int128)S), Q, amb, force);
+}
+
+struct TlenOut { int n, mean, rms, sd; };
+__device__ __forceinline__ TlenOut tlen_class(unsigned n, long long S, unsigned long long Q, bool *amb, float force) {
+    TlenOut o;
+    o.n = (int)n;
+    o.mean = n > 0 ? (int)rint((double)S / (double)n) : 0;                 // opt.pyx:2166-2170
+    o.rms = q_rootmean(Q, n);                                              // opt.pyx:2159-2163, decided in integers
+    o.sd = tlen_std((long long)n, S, Q, amb, force);
+    return o;
+}
+
+template <int STAT>
+__global__ void __launch_bounds__(TLEN_NT, 3)
+k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ tile_redo, float force) {
+    constexpr int NWARPS = TLEN_NT / 32;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *raw = cnt + TLEN_NW * TT;
+    RInfo *s_ri = reinterpret_cast<RInfo *>(raw + TT);
+    int32_t *s_tlen = reinterpret_cast<int32_t *>(s_ri + QCH);            // QCH + 8
+    unsigned long long *sum = reinterpret_cast<unsigned long long *>(cnt + 6 * TT);
+    unsigned long long *sumsq = reinterpret_cast<unsigned long long *>(cnt + 14 * TT);
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_n;
+    __shared__ long long s_tlenlo;
+    __shared__ int s_amb;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int64_t t0l = A.start + (int64_t)tile * TT;
+    const int t0 = (int)t0l;
+    int dx, dy;
+    {
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile));
+        dx = (int)d0.x; dy = (int)d0.y;
+    }
+    auto issue = [&](int cb) {
+        const int n = min(QCH, dy - cb);
+        uint32_t b1 = 0;
+        const uint8_t *p1 = nullptr;
+        if (n > 0) stage_span(tlen, (long long)cb, (long long)cb + n, 4, &p1, &b1, &s_tlenlo);
+        s_n = n;
+        fence_proxy_async();
+        if (n > 0) {
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)n * (uint32_t)sizeof(RInfo) + b1);
+            bulk_g2s(s_ri, A.ri + cb, (uint32_t)n * (uint32_t)sizeof(RInfo), &s_bar);
+            bulk_g2s(s_tlen, p1, b1, &s_bar);
+        } else mbar_arrive_expect_tx(&s_bar, 0);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        s_amb = 0;
+        issue(dx);
+    }
+    {
+        const int nw4 = (TLEN_NW + 1) * TT / 4;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < nw4; k += TLEN_NT) reinterpret_cast<uint4 *>(cnt)[k] = z;
+    }
+    uint32_t *rawp = A.need_raw ? raw : nullptr;
+    __syncthreads();
+    uint32_t parity = 0;
+    for (int cb = dx; cb < dy;) {
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
+        const int n = s_n;
+        if (n == 0) break;
+        const int tskew = (int)(cb - s_tlenlo);
+        if (tid < n) {
+            const RInfo r = s_ri[tid];
+            const uint32_t cls = r.cls;
+            if (cls & CLS_ADMITTED) {
+                const int len = r.end - r.pos;                    // every event of the column counts (opt.pyx:700-727)
+                if (rawp) interval_add(rawp, r.pos, len, t0, 1u);
+                if (cls & CLS_COUNTED) {
+                    const int rev = cls & CLS_REV ? 1 : 0;
+                    const long long t = s_tlen[tid + tskew];
+                    interval_add(cnt + rev * TT, r.pos, len, t0, 1u);
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        if (cls & (g ? CLS_PP : CLS_PAIRED)) {
+                            const int c = 2 * g + rev;
+                            interval_add(cnt + (2 + c) * TT, r.pos, len, t0, 1u);
+                            if (t) {
+                                interval_add64(sum + c * TT, r.pos, len, t0, (unsigned long long)t);
+                                interval_add64(sumsq + c * TT, r.pos, len, t0, (unsigned long long)(t * t));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cb += n;
+        if (cb >= dy) break;
+        __syncthreads();
+        if (tid == 0) issue(cb);
+    }
+    __syncthreads();
+    {   // 6 (+ raw) 32-bit and 8 64-bit difference arrays
+        const int n32 = 6 + (A.need_raw ? 1 : 0);
+        for (int a = warp; a < n32 + 8; a += NWARPS) {
+            if (a < 6) warp_scan_array(cnt + a * TT, lane);
+            else if (a < n32) warp_scan_array(raw, lane);
+            else warp_scan_array64(sum + (a - n32) * TT, lane);          // sum[0..3] and sumsq[0..3] are contiguous
+        }
+    }
+    __syncthreads();
+    const int64_t st = A.stride;
+    bool amb = false;
+#pragma unroll 1
+    for (int p = tid; p < TT; p += TLEN_NT) {
+        const int64_t pl = t0l + p;
+        if (pl >= A.end) break;
+        int32_t *o = A.out + (pl - A.start);
+        const uint32_t nf = cnt[p], nr = cnt[TT + p];
+        uint32_t nc[4];
+        long long S[4];
+        unsigned long long Q[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { nc[c] = cnt[(2 + c) * TT + p]; S[c] = (long long)sum[c * TT + p]; Q[c] = sumsq[c * TT + p]; }
+        if (STAT == PSS_TLEN) {
+            const TlenOut h0 = tlen_class(nc[0] + nc[1], S[0] + S[1], Q[0] + Q[1], &amb, force);
+            const TlenOut h1 = tlen_class(nc[2] + nc[3], S[2] + S[3], Q[2] + Q[3], &amb, force);
+            o[0] = nf + nr; o[st] = h0.n; o[2 * st] = h1.n; o[3 * st] = h0.mean; o[4 * st] = h1.mean;
+            o[5 * st] = h0.rms; o[6 * st] = h1.rms; o[7 * st] = h0.sd; o[8 * st] = h1.sd;
+        } else {
+            o[0] = nf + nr; o[st] = nf; o[2 * st] = nr;
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {          // paired, pp: all, fwd, rev
+                const int c = 2 * g;
+                const TlenOut h[3] = {tlen_class(nc[c] + nc[c + 1], S[c] + S[c + 1], Q[c] + Q[c + 1], &amb, force),
+                                      tlen_class(nc[c], S[c], Q[c], &amb, force), tlen_class(nc[c + 1], S[c + 1], Q[c + 1], &amb, force)};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int f = 3 * g + k;
+                    o[(3 + f) * st] = h[k].n; o[(9 + f) * st] = h[k].mean; o[(15 + f) * st] = h[k].rms; o[(21 + f) * st] = h[k].sd;
+                }
+            }
+        }
+        A.rowmask[pl - A.start] = (A.need_raw ? raw[p] : nf + nr) ? 1 : 0;
+    }
+    if (amb) s_amb = 1;
+    __syncthreads();
+    if (tid == 0 && s_amb) tile_redo[tile] = 1;
+}
+
 // ------------------------------------------------------- descriptors + packed reference
 
 // One thread per tile: candidate read range (reads are start-sorted, so it is the index
@@ -1322,10 +1541,27 @@ bool tile_kernel_counting(int stat) {
     }
 }
 
+size_t tile_redo_bytes(int64_t ntiles) { return sizeof(int32_t) * (size_t)ntiles; }
+
+template <int STAT>
+static cudaError_t launch_tilet_one(const TileArgs &a, const int32_t *tlen, int32_t *redo, int64_t ntiles, cudaStream_t s) {
+    const size_t smem = (size_t)(TLEN_NW + 1) * TT * 4 + (size_t)QCH * sizeof(RInfo) + (QCH + 8) * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_tilet<STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const float force = getenv("PSS_TLEN_FORCE_REPLAY") ? 3.0e38f : 0.0f;   // tests: every tile takes the replay
+    k_tilet<STAT><<<(unsigned)ntiles, TLEN_NT, smem, s>>>(a, tlen, redo, force);
+    return cudaGetLastError();
+}
+
 bool tile_kernel_supports(int stat, int min_baseq, int no_del) {
     if (min_baseq > 0) return false;      // every event depends on its base: the generic kernel
     if (tile_kernel_counting(stat)) return true;
     switch (stat) {
+    case PSS_TLEN: case PSS_TLEN_STRAND: return !no_del;     // intervals are whole reads: deletions need the CIGAR
     case PSS_MAPQ: case PSS_MAPQ_STRAND: return !no_del;     // the max needs the CIGAR then: generic kernel
     case PSS_BASEQ: case PSS_BASEQ_STRAND: case PSS_BASEQ_EXT: case PSS_BASEQ_EXT_STRAND: return true;
     default: return false;
@@ -1399,6 +1635,8 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     case PSS_BASEQ_STRAND: e = launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND>(a, ntiles, s); break;
     case PSS_BASEQ_EXT: e = launch_tileq_one<KIND_BQX, PSS_BASEQ_EXT>(a, ntiles, s); break;
     case PSS_BASEQ_EXT_STRAND: e = launch_tileq_one<KIND_BQX, PSS_BASEQ_EXT_STRAND>(a, ntiles, s); break;
+    case PSS_TLEN: e = launch_tilet_one<PSS_TLEN>(a, p.tlen, p.tile_redo, ntiles, s); break;
+    case PSS_TLEN_STRAND: e = launch_tilet_one<PSS_TLEN_STRAND>(a, p.tlen, p.tile_redo, ntiles, s); break;
     default: e = cudaErrorInvalidValue;
     }
     if (e1) cudaEventRecord(e1, s);

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 G = 300_000          # oracle-checkable in about a second per statistic
 TILE_STATS = ('coverage', 'coverage_strand', 'coverage_ext', 'coverage_ext_strand', 'variation', 'variation_strand',
-              'mapq', 'mapq_strand', 'baseq', 'baseq_strand', 'baseq_ext', 'baseq_ext_strand')
+              'mapq', 'mapq_strand', 'baseq', 'baseq_strand', 'baseq_ext', 'baseq_ext_strand', 'tlen', 'tlen_strand')
 
 
 @pytest.fixture(scope='module')
@@ -286,3 +286,39 @@ def test_streamed_host_call_equals_single_call(ctx, small, monkeypatch):
         for s, o, m in zip(stats, outs, masks):
             e, em = _run_host(ctx, nb, ref, s, lo, hi, **kw)
             assert np.array_equal(o, e) and np.array_equal(m, em), (s, kw)
+
+
+@pytest.mark.parametrize('stat', ('tlen', 'tlen_strand'))
+def test_tlen_rounding_boundaries_and_replay(stat, ctx, small, monkeypatch):
+    # std_tlen is decided from exact integer sums unless it is too close to a rounding boundary; then the tile
+    # is redone by the in-order Welford replay.  Nine reads with tlen 1,1,1,0,0,0,0,0,0 have std exactly 0.5
+    # (a tie whose rounding depends on the order the reference saw the reads in); other multisets sit on
+    # (k + 0.5) boundaries too.  Every permutation must agree with the oracle's in-order replay.
+    rng = np.random.default_rng(21)
+    L = 50
+    groups = []
+    for base in ([1, 1, 1, 0, 0, 0, 0, 0, 0], [3, 3, 3, 0, 0, 0, 0, 0, 0], [401, 401, 401, 400, 400, 400, 400, 400, 400],
+                 [-7, -7, -7, -8, -8, -8, -8, -8, -8], [100000001, 100000001, 100000001] + [100000000] * 6):
+        for _ in range(6):
+            groups.append(rng.permutation(base))
+    n = sum(len(g) for g in groups)
+    pos = np.repeat(np.arange(len(groups)) * 700 + 100, [len(g) for g in groups]).astype('i4')
+    nb = dict(n_reads=n, tid=0, pos=pos, flag=np.where(rng.random(n) < 0.5, 99, 147).astype('u2'),
+              mapq=np.full(n, 60, 'u1'), tlen=np.concatenate(groups).astype('i4'), mtid=np.zeros(n, 'i4'),
+              l_seq=np.full(n, L, 'i4'), cigar_off=np.arange(n + 1, dtype='i8'), cigar=np.full(n, L << 4, 'u4'),
+              seq_off=np.arange(n + 1, dtype='i8') * (L // 2), seq4=np.full(n * L // 2, 0x11, 'u1'),
+              qual=None, qual_off=None, name_prev=np.full(n, -1, 'i4'), endpos=pos.astype('i8') + L)
+    reads = oracle_reads_from_arrays(nb)
+    ref = np.frombuffer(b'A' * (int(pos.max()) + 200), dtype='u1')
+    hi = int(pos.max()) + 100
+    out, mask = _run_host(ctx, nb, ref, stat, 0, hi)
+    pos_o, F = _oracle(stat, reads, ref, 0, hi)
+    _compare(out, mask, pos_o, F, 0, stat)
+    j = config.value_fields(stat).index('std_tlen')
+    assert set(np.unique(out[j][mask.astype(bool)])) >= {0, 2}            # 0.5 -> 0 (half-even), 1.5 -> 2, ...
+    # every tile through the replay path: same answer on the synthetic batch
+    nbs, refs, rs = small
+    a, ma = _run_host(ctx, nbs, refs, stat, 0, G)
+    monkeypatch.setenv('PSS_TLEN_FORCE_REPLAY', '1')
+    b, mb = _run_host(ctx, nbs, refs, stat, 0, G)
+    assert np.array_equal(a, b) and np.array_equal(ma, mb)
