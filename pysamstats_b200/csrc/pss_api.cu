@@ -22,7 +22,8 @@ struct pss_ctx {
     char err[512] = {0};
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // moved by the *_host entry points
-    DevBuf ri, rng, qual, pair, next, small, tdesc, refpack, bwork, redo;
+    DevBuf ri, rng, qual, pair, next, small, tdesc, refpack, bwork, redo, lowq;
+    int lowq_minq = -1;     // min_baseq the marks in `lowq` were made for (-1: none; reset with every prepared batch)
     int64_t qual_bias = 0;  // ctx->qual holds bytes [qual_bias, qual_bias + n) of the batch's qual array
     // batch prepared by pss_prepare()
     bool prepared = false;
@@ -149,7 +150,7 @@ extern "C" void pss_destroy(pss_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small, &ctx->tdesc, &ctx->refpack, &ctx->bwork, &ctx->redo,
+    DevBuf *all[] = {&ctx->ri, &ctx->rng, &ctx->qual, &ctx->pair, &ctx->next, &ctx->small, &ctx->tdesc, &ctx->refpack, &ctx->bwork, &ctx->redo, &ctx->lowq,
                      &ctx->outbuf[0], &ctx->outbuf[1], &ctx->maskbuf[0], &ctx->maskbuf[1]};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->hb) if (b.p) cudaFree(b.p);
@@ -254,6 +255,7 @@ static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_
     int maxcnt = max_depth ? max_depth : 8000;   // A.0
     CU(launch_admit(ri, R->pos, n, maxcnt, st, s, &ctx->launches));
     ctx->desc_start = ctx->desc_end = -1;   // tile descriptors belong to the previous batch
+    ctx->lowq_minq = -1;
     if (need_qual && n > 0) {
         if (!qual_dst) {
             if ((rc = ensure(ctx, ctx->qual, (size_t)R->n_qual_bytes)) != PSS_OK) return rc;
@@ -306,6 +308,7 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.tlen = (P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND) ? R->tlen : nullptr;
     a.tile_rng = nullptr;
     a.tile_redo = nullptr;
+    a.lowq = nullptr;
     a.n_reads = R->n_reads;
     a.ref = P->ref; a.ref_start = P->ref_start; a.ref_len = P->ref_len;
     a.start = start; a.end = end;
@@ -325,7 +328,15 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     if (tile) {
         if ((rc = ensure(ctx, ctx->tdesc, tile_desc_bytes(ntiles))) != PSS_OK) return rc;
         if ((rc = ensure(ctx, ctx->refpack, tile_refpack_bytes(ntiles))) != PSS_OK) return rc;
-        int need_raw = (P->min_mapq > 0 || P->no_dup || P->no_del) ? 1 : 0;
+        int need_raw = (P->min_mapq > 0 || P->no_dup || P->no_del || P->min_baseq > 0) ? 1 : 0;
+        if (P->min_baseq > 0) {       // mark the bases below the threshold once per batch and threshold
+            if (ctx->lowq_minq != P->min_baseq) {
+                if ((rc = ensure(ctx, ctx->lowq, tile_lowq_bytes(R->n_reads, R->n_seq_bytes))) != PSS_OK) return rc;
+                CU(launch_lowq(*R, a.qual, P->min_baseq, ctx->lowq.p, s, &ctx->launches));
+                ctx->lowq_minq = P->min_baseq;
+            }
+            a.lowq = (const uint32_t *)ctx->lowq.p;
+        }
         // descriptors depend on the batch and the position range only: reused by the next statistic
         const bool desc_valid = ctx->desc_start == start && ctx->desc_end == end;
         const bool is_tlen = P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND;

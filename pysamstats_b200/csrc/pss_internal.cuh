@@ -66,6 +66,7 @@ struct PileupArgs {
     const int64_t *seq_off;
     const int32_t *tlen;
     const int2 *tile_rng;       // candidate read range [x, y) per tile
+    const uint32_t *lowq;       // tile kernel, min_baseq > 0: bit per base below the threshold (k_lowq)
     int32_t *tile_redo;         // tlen: per 512-position tile, set by k_tilet when the in-order replay must redo it;
                                 // k_pileup (256-position tiles) returns at once for tiles whose flag is 0
     int64_t n_reads;
@@ -138,6 +139,8 @@ bool tile_kernel_supports(int stat, int min_baseq, int no_del);
 bool tile_kernel_counting(int stat);
 size_t tile_desc_bytes(int64_t ntiles);
 size_t tile_redo_bytes(int64_t ntiles);
+size_t tile_lowq_bytes(int64_t n_reads, int64_t n_seq_bytes);
+cudaError_t launch_lowq(const pss_reads &R, const uint8_t *qual, int min_baseq, void *lowq_buf, cudaStream_t s, int64_t *launches);
 size_t tile_refpack_bytes(int64_t ntiles);
 // e0 / e1 (may be NULL) are recorded immediately before / after the tile kernel itself
 cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, int64_t n_reads, SmallState *st,

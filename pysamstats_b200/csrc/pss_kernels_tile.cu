@@ -90,6 +90,7 @@ struct TileArgs {
     const int64_t *seq_off;
     const uint8_t *qual;       // quality kinds: qualities after the overlap rewrite
     const int64_t *qual_off;
+    const uint32_t *lowq;      // min_baseq > 0: one bit per read base, set when its quality is below min_baseq (k_lowq)
     const TileDesc *desc;
     const uint32_t *refpack;   // REFN_WORDS words per tile (+ pad), KIND_VAR only
     const uint32_t *tflags;    // per tile, bit 0: a reference position of the tile has no 4-bit code (KIND_VAR)
@@ -420,6 +421,175 @@ __device__ void cover_read(const TileCtx &T, const TileArgs &A, const RInfo &r, 
     }
 }
 
+// ---- min_baseq > 0: corrections for the bases below the threshold -----------------------------
+//
+// stat_pileup drops the event of a read at a column when min_baseq > 0, the read has a base there
+// (not a deletion) and its quality is below the threshold (opt.pyx:1900-1903).  The scatter above
+// runs as if every base passed; k_lowq has marked the failing bases (one bit per base, word index
+// (seq_off >> 4) + read index + qpos / 32), and the read's thread now takes each of them back out:
+// -1 at the position in the read-count difference arrays (+1 at the next), and for the variation
+// kinds the match / mismatch / base-class / insertion contribution of that base.  Everything is
+// linear in the counters, so the order against the main pass does not matter.
+
+// calls f(p, qi, last) for every marked base of the aligned span [x, x + l) (first base query index y)
+// that lies in the tile: p tile-relative position, qi query index, last: it is the last base of the span
+template <class F>
+__device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int y, int t0, F f) {
+    const int a = max(x - t0, 0), b = min(x + l - t0, TT);
+    if (a >= b) return;
+    const int qa = y + (a + t0 - x), qb = y + (b + t0 - x);       // query range [qa, qb)
+    for (int w = qa >> 5; w <= (qb - 1) >> 5; ++w) {
+        uint32_t m = __ldg(mw + w);
+        const int base = w << 5;
+        if (base < qa) m &= 0xffffffffu << (qa - base);
+        if (base + 32 > qb) m &= 0xffffffffu >> (base + 32 - qb);
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int qi = base + bit;
+            f(a + (qi - qa), qi, qi == y + l - 1);
+        }
+    }
+}
+
+// does an insertion follow CIGAR op k (htslib `indel > 0` at the last base of the op, A.1)?
+__device__ __forceinline__ bool ins_follows(const uint32_t *cg, int nc, int k) {
+    if (k + 1 >= nc) return false;
+    const uint32_t w2 = cg[k + 1];
+    const int op2 = w2 & 15;
+    if (op2 == OP_I) return (w2 >> 4) > 0;
+    if (op2 == OP_P && k + 2 < nc) {
+        long long l3 = 0;
+        for (int j = k + 2; j < nc; ++j) {
+            const uint32_t w3 = cg[j];
+            const int op3 = w3 & 15;
+            if (op3 == OP_I) l3 += (w3 >> 4);
+            else if (op3 == OP_D || op3 == OP_M || op3 == OP_N || op3 == OP_EQ || op3 == OP_X) break;
+        }
+        return l3 > 0;
+    }
+    return false;
+}
+
+// variation kinds (LayVar).  Reads without sequence have quality 0 at every base: they keep only their
+// deletion / ref-skip events, which var_read is told through `drop_bases`.
+__device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t *cg, const RInfo &r, uint32_t sn0, int ridx) {
+    const uint32_t cls = r.cls;
+    if (!(cls & CLS_COUNTED) || (cls & CLS_NOREF) || !(cls & CLS_HASSEQ)) return;
+    const int bank = cls & 3u, pp = bank >> 1;
+    const uint32_t inc = half_inc(bank);
+    const uint32_t *mw = A.lowq + (r.seq_off >> 4) + ridx;
+    const int nc = (int)r.n_cigar;
+    int x = r.pos, y = 0;
+    for (int k = 0; k < nc && x < T.t1; ++k) {
+        const uint32_t w = cg[k];
+        const int op = w & 15, l = (int)(w >> 4);
+        if (op_is_match(op)) {
+            if (x + l > T.t0) {
+                const bool ins = ins_follows(cg, nc, k);
+                lowq_span(mw, x, l, y, T.t0, [&](int p, int qi, bool last) {
+                    uint32_t *al = T.cnt + (W_ALL + pp) * TT + p;
+                    atomicAdd(al, 0u - inc);
+                    if (p + 1 < TT) atomicAdd(al + 1, inc);
+                    const uint32_t kk = sn0 + (uint32_t)qi;
+                    const int code = (T.seqw[kk >> 3] >> (((kk & 7) ^ 1) << 2)) & 15;
+                    int rc;
+                    if (T.slow) {
+                        const int64_t ro = (int64_t)T.t0 + p - T.ref_start;
+                        rc = (T.ref && ro >= 0 && ro < T.ref_len) ? c_refcode[__ldg(T.ref + ro)] : 16;
+                    } else rc = (T.refn[p >> 3] >> ((7 - (p & 7)) << 2)) & 15;
+                    if (code == rc) {
+                        uint32_t *m = T.cnt + (W_MATCH + pp) * TT + p;
+                        atomicAdd(m, 0u - inc);
+                        if (p + 1 < TT) atomicAdd(m + 1, inc);
+                    } else {
+                        atomicAdd(T.cnt + (W_MMT + pp) * TT + p, 0u - inc);
+                        const int c = mm_class(code);
+                        if (c < 5) atomicAdd(T.cnt + (W_MMC + 2 * c + pp) * TT + p, 0u - inc);
+                    }
+                    if (last && ins) atomicAdd(T.cnt + (W_INS + pp) * TT + p, 0u - inc);
+                });
+            }
+            x += l; y += l;
+        } else if (op == OP_D || op == OP_N) x += l;
+        else if (op == OP_I || op == OP_S) y += l;
+    }
+}
+
+// coverage kinds: the read-count words of every marked base
+template <int KIND>
+__device__ void cover_lowq_fix(const TileCtx &T, const TileArgs &A, const RInfo &r, int ridx) {
+    const uint32_t cls = r.cls;
+    if (!(cls & CLS_COUNTED) || (cls & CLS_NOREF) || !(cls & CLS_HASSEQ)) return;
+    const uint32_t *mw = A.lowq + (r.seq_off >> 4) + ridx;
+    const uint32_t *cg = A.cigar + r.cigar_off;
+    const int nc = (int)r.n_cigar;
+    auto undo = [&](int p, int, bool) {
+        if (KIND == KIND_COV) {
+            const uint32_t inc = half_inc(cls & CLS_REV ? 1 : 0);
+            uint32_t *al = T.cnt + ((cls >> 1) & 1u) * TT + p;
+            atomicAdd(al, 0u - inc);
+            if (p + 1 < TT) atomicAdd(al + 1, inc);
+        } else {
+            const uint32_t m = (cls >> CLS_EXT_SHIFT) & 255u;
+            uint32_t *base = T.cnt + (cls & CLS_REV ? 4 : 0) * TT + p;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t bits = (m >> (2 * g)) & 3u;
+                if (bits) {
+                    const uint32_t v = (bits & 1u) | ((bits >> 1) << 16);
+                    atomicAdd(base + g * TT, 0u - v);
+                    if (p + 1 < TT) atomicAdd(base + g * TT + 1, v);
+                }
+            }
+        }
+    };
+    int x = r.pos, y = 0;
+    for (int k = 0; k < nc && x < T.t1; ++k) {
+        const uint32_t w = __ldg(cg + k);
+        const int op = w & 15, l = (int)(w >> 4);
+        if (op_is_match(op)) {
+            if (x + l > T.t0) lowq_span(mw, x, l, y, T.t0, undo);
+            x += l; y += l;
+        } else if (op == OP_D || op == OP_N) x += l;
+        else if (op == OP_I || op == OP_S) y += l;
+    }
+}
+
+// a read without sequence under min_baseq > 0: only its deletion / ref-skip events remain
+template <int KIND>
+__device__ void noseq_minq_read(const TileCtx &T, const TileArgs &A, const RInfo &r, uint32_t *raw) {
+    const uint32_t cls = r.cls;
+    if (!(cls & CLS_ADMITTED)) return;
+    if (raw) interval_add(raw, r.pos, r.end - r.pos, T.t0, 1u);
+    if (!(cls & CLS_COUNTED) || T.no_del) return;
+    const int bank = cls & 3u;
+    if (cls & CLS_NOREF) {         // one deletion-like event at pos
+        if (KIND == KIND_VAR) {
+            interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, r.pos, 1, T.t0, half_inc(bank));
+            interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, r.pos, 1, T.t0, half_inc(bank));
+        } else cover_segment<KIND>(T, cls, r.pos, 1);
+        return;
+    }
+    const uint32_t *cg = A.cigar + r.cigar_off;
+    const int nc = (int)r.n_cigar;
+    int x = r.pos;
+    for (int k = 0; k < nc && x < T.t1; ++k) {
+        const uint32_t w = __ldg(cg + k);
+        const int op = w & 15, l = (int)(w >> 4);
+        if (op_is_match(op)) x += l;
+        else if (op == OP_D || op == OP_N) {
+            if (x + l > T.t0) {
+                if (KIND == KIND_VAR) {
+                    interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, x, l, T.t0, half_inc(bank));
+                    if (op == OP_D) interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, x, l, T.t0, half_inc(bank));
+                } else cover_segment<KIND>(T, cls, x, l);
+            }
+            x += l;
+        }
+    }
+}
+
 // ---- in-place inclusive prefix sum of one TT-word array by one warp --------------------------
 // lane l owns words [128 k + 4 l, 128 k + 4 l + 4) for k = 0 .. TT/128-1 (conflict-free 128-bit
 // accesses).
@@ -622,7 +792,7 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
 
 // ------------------------------------------------------------------------------ the kernel
 
-template <int KIND, int STAT>
+template <int KIND, int STAT, bool MINQ>
 __global__ void __launch_bounds__(KindLaunch<KIND>::NT, KindLaunch<KIND>::CTAS)
 k_tile(TileArgs A) {
     constexpr int NT = KindLaunch<KIND>::NT, NWARPS = NT / 32;
@@ -725,11 +895,24 @@ k_tile(TileArgs A) {
                     const RInfo r = s_ri[tid - part * n];
                     const long long ciglo = s_ciglo;
                     const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
+                    if (MINQ && !(r.cls & CLS_HASSEQ)) {     // quality 0 everywhere: the bases are all dropped
+                        if (part == 0) noseq_minq_read<KIND>(T, A, r, rawp);
+                    } else {
 #ifndef PSS_EXP_SKIP_WALK      // experiment builds only (scripts/build_variant.sh): time of the phases in isolation
-                    var_read<LayVar>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
+                        var_read<LayVar>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
 #endif
+                        if (MINQ && part == 0)
+                            var_lowq_fix(T, A, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), cb + tid);
+                    }
                 }
-            } else if (tid < n) cover_read<KIND>(T, A, s_ri[tid], rawp);
+            } else if (tid < n) {
+                const RInfo r = s_ri[tid];
+                if (MINQ && !(r.cls & CLS_HASSEQ)) noseq_minq_read<KIND>(T, A, r, rawp);
+                else {
+                    cover_read<KIND>(T, A, r, rawp);
+                    if (MINQ) cover_lowq_fix<KIND>(T, A, r, cb + tid);
+                }
+            }
             in_pass += n;
             staged = false;
             cb += n;
@@ -1506,16 +1689,49 @@ static size_t tile_smem_bytes() {
     return b;
 }
 
-template <int KIND, int STAT>
-static cudaError_t launch_tile_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
+template <int KIND, int STAT, bool MINQ>
+static cudaError_t launch_tile_mq(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
     size_t smem = tile_smem_bytes<KIND>();
     static bool configured = false;     // per instantiation
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_tile<KIND, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_tile<KIND, STAT, MINQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_tile<KIND, STAT><<<(unsigned)ntiles, KindLaunch<KIND>::NT, smem, s>>>(a);
+    k_tile<KIND, STAT, MINQ><<<(unsigned)ntiles, KindLaunch<KIND>::NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+template <int KIND, int STAT>
+static cudaError_t launch_tile_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
+    return a.lowq ? launch_tile_mq<KIND, STAT, true>(a, ntiles, s) : launch_tile_mq<KIND, STAT, false>(a, ntiles, s);
+}
+
+// one bit per read base: quality (after the overlap rewrite) below min_baseq.  One warp per read; the bits of
+// read i start at word (seq_off[i] >> 4) + i (its packed sequence takes ceil(l / 2) bytes, so that leaves at
+// least ceil(l / 32) words per read without a second offset array).
+__global__ void __launch_bounds__(256)
+k_lowq(const uint8_t *__restrict__ qual, const int64_t *__restrict__ qual_off, const int64_t *__restrict__ seq_off,
+       const int32_t *__restrict__ l_seq, int64_t n, int min_baseq, uint32_t *__restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int l = l_seq[i];
+    const uint8_t *q = qual + qual_off[i];
+    uint32_t *o = out + (seq_off[i] >> 4) + i;
+    for (int b = 0; b < l; b += 32) {
+        const bool low = (b + lane < l) && (int)q[b + lane] < min_baseq;
+        const uint32_t m = __ballot_sync(FULL, low);
+        if (lane == 0) o[b >> 5] = m;
+    }
+}
+
+size_t tile_lowq_bytes(int64_t n_reads, int64_t n_seq_bytes) { return sizeof(uint32_t) * (size_t)((n_seq_bytes >> 4) + n_reads + 8); }
+
+cudaError_t launch_lowq(const pss_reads &R, const uint8_t *qual, int min_baseq, void *lowq_buf, cudaStream_t s, int64_t *launches) {
+    if (R.n_reads <= 0) return cudaSuccess;
+    k_lowq<<<(unsigned)((R.n_reads * 32 + 255) / 256), 256, 0, s>>>(qual, R.qual_off, R.seq_off, R.l_seq, R.n_reads, min_baseq,
+                                                                    (uint32_t *)lowq_buf);
+    if (launches) ++*launches;
     return cudaGetLastError();
 }
 
@@ -1558,8 +1774,8 @@ static cudaError_t launch_tilet_one(const TileArgs &a, const int32_t *tlen, int3
 }
 
 bool tile_kernel_supports(int stat, int min_baseq, int no_del) {
-    if (min_baseq > 0) return false;      // every event depends on its base: the generic kernel
-    if (tile_kernel_counting(stat)) return true;
+    if (tile_kernel_counting(stat)) return true;      // min_baseq > 0: the bases below it are taken back out (k_lowq)
+    if (min_baseq > 0) return false;                  // the other kinds: every event depends on its base, generic kernel
     switch (stat) {
     case PSS_TLEN: case PSS_TLEN_STRAND: return !no_del;     // intervals are whole reads: deletions need the CIGAR
     case PSS_MAPQ: case PSS_MAPQ_STRAND: return !no_del;     // the max needs the CIGAR then: generic kernel
@@ -1603,6 +1819,7 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     TileArgs a;
     a.ri = p.ri; a.cigar = p.cigar; a.seq4 = p.seq4; a.seq_off = seq_off; a.desc = desc;
     a.qual = p.qual; a.qual_off = p.qual_off;
+    a.lowq = (p.min_baseq > 0 && tile_kernel_counting(stat)) ? p.lowq : nullptr;
     a.refpack = (const uint32_t *)refpack_buf;
     a.tflags = (const uint32_t *)refpack_buf + (ntiles * REFN_WORDS + 8);
     a.ref = p.ref; a.ref_start = p.ref_start; a.ref_len = p.ref_len; a.start = p.start; a.end = p.end;

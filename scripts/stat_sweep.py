@@ -12,6 +12,7 @@ ap.add_argument('--mb', type=float, default=50.0)
 ap.add_argument('--reps', type=int, default=5)
 ap.add_argument('--generic', action='store_true')
 ap.add_argument('--only', default='')
+ap.add_argument('--min-baseq', type=int, default=0)
 args = ap.parse_args()
 dev = torch.device('cuda', 0)
 L = int(args.mb * 1e6) // 512 * 512
@@ -28,10 +29,10 @@ for stat in config.pileup_types:
     out = torch.empty((nf, L), dtype=torch.int32, device=dev)
     mask = torch.empty(L, dtype=torch.uint8, device=dev)
     withref = stat in config.stats_types_withref
-    need_qual = stat.startswith('baseq')
+    need_qual = stat.startswith('baseq') or args.min_baseq > 0
     p = ctx.pileup_params(stat, start=0, end=L, ref=ref if withref else None, ref_start=ref_lo,
                           ref_len=int(ref.numel()) if withref else 0, contig_len=L,
-                          flags=_cabi.PSS_FLAG_GENERIC_KERNEL if args.generic else 0)
+                          flags=_cabi.PSS_FLAG_GENERIC_KERNEL if args.generic else 0, min_baseq=args.min_baseq)
     ctx.prepare(rs, with_qual=need_qual, stream=s)
     for _ in range(2):
         ctx.pileup_prepared(p, out, mask, stream=s)
