@@ -692,7 +692,7 @@ static int host_multi_run(pss_ctx *ctx, const pss_reads *H, const pss_reads *D, 
         const bool q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
         static const bool no_narrow = getenv("PSS_NO_NARROW") != nullptr;
         // (coverage_gc's gc column is written as int32 by k_gc, so it stays on the int32 pipeline)
-        const bool narrow = !no_narrow && tile_kernel_counting(P[i].stat) && P[i].min_baseq <= 0 && P[i].stat != PSS_COVERAGE_GC &&
+        const bool narrow = !no_narrow && tile_kernel_counting(P[i].stat) && P[i].stat != PSS_COVERAGE_GC &&
                             !(P[i].flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
         if (narrow) {
             rc = host_stat_narrow(ctx, D, &Pd, q, outs[i], ostride, rowmasks[i], s);
