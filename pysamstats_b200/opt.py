@@ -172,29 +172,68 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
                                    window_size=stat.window_size, window_offset=stat.window_offset,
                                    start=lo, end=hi, ref=refseq if len(refseq) else None, ref_start=0,
                                    ref_len=len(refseq), contig_len=len(refseq))
-        out = bamio.alloc_big((len(names), npos), np.int32)
-        rowmask = np.empty(npos, dtype=np.uint8)
-        ctx.pileup_host(_reads_struct(batch, need_qual), params, out, rowmask)
-        rows = rowmask.view(bool)
-        if pad:
-            rows = rows.copy()
-            rows[max(s, lo) - lo:max(min(e, hi) - lo, 0)] = True
-        if rows.all():
-            pos = np.arange(lo, hi, dtype=np.int64)
-            fields = {f: out[j] for j, f in enumerate(names)}
-        else:
-            sel = np.flatnonzero(rows)
-            pos = sel.astype(np.int64) + lo
-            taken = bamio.take_cols(out, sel)
-            fields = {f: taken[j] for j, f in enumerate(names)}
-        ref = _ref_column(refseq, pos) if name in config.ref_column_types else None
-        if 'gc' in fields and len(pos) and fields['gc'].min() < 0:
-            # the reference stores gc = -1 for an empty window into a u1 column, which numpy
-            # refuses
-            raise OverflowError('Python integer -1 out of bounds for uint8')
-        if one_based:
-            pos = pos + 1
-        yield c, pos, ref, fields
+        for c_lo, c_hi, reads in _position_chunks(batch, lo, hi, need_qual, max_depth):
+            cn = c_hi - c_lo
+            params.start, params.end = c_lo, c_hi
+            out = bamio.alloc_big((len(names), cn), np.int32)
+            rowmask = np.empty(cn, dtype=np.uint8)
+            ctx.pileup_host(reads, params, out, rowmask)
+            rows = rowmask.view(bool)
+            if pad:
+                rows = rows.copy()
+                rows[max(min(max(s, lo), c_hi) - c_lo, 0):max(min(e, hi, c_hi) - c_lo, 0)] = True
+            if rows.all():
+                pos = np.arange(c_lo, c_hi, dtype=np.int64)
+                fields = {f: out[j] for j, f in enumerate(names)}
+            else:
+                sel = np.flatnonzero(rows)
+                if len(sel) == 0:
+                    continue
+                pos = sel.astype(np.int64) + c_lo
+                taken = bamio.take_cols(out, sel)
+                fields = {f: taken[j] for j, f in enumerate(names)}
+            ref = _ref_column(refseq, pos) if name in config.ref_column_types else None
+            if 'gc' in fields and len(pos) and fields['gc'].min() < 0:
+                # the reference stores gc = -1 for an empty window into a u1 column, which numpy
+                # refuses
+                raise OverflowError('Python integer -1 out of bounds for uint8')
+            if one_based:
+                pos = pos + 1
+            yield c, pos, ref, fields
+
+
+def _position_chunks(batch, lo, hi, need_qual, max_depth):
+    """Cut the positions [lo, hi) of one contig batch into pieces of PSS_TABLE_CHUNK (default 16 Mi) positions,
+    each with the sub-batch of reads that overlap it (a zero-copy view: the reads are start sorted), so a whole
+    chromosome streams through bounded host memory.  Yields (c_lo, c_hi, struct pss_reads).
+
+    The ``max_depth`` admission rule is order dependent: a read before a cut can only be refused because of
+    earlier reads the next piece would not see.  So the range is only cut when no read of the batch can be
+    refused at all (fewer than ``max_depth`` reads start within one maximal read span of any read)."""
+    import os
+    from . import shard
+    n = batch.n_reads
+    chunk = max(shard.TILE * 2, int(os.environ.get('PSS_TABLE_CHUNK', 16 << 20)) // 512 * 512)
+    # requests that read base qualities are not cut either: the mate-overlap rewrite pairs consecutive reads of a
+    # QNAME, and a piece that misses an earlier read of a three-read chain would pair the rest differently
+    if hi - lo <= chunk or n == 0 or need_qual:
+        yield lo, hi, _reads_struct(batch, need_qual)
+        return
+    maxspan = int((batch.endpos - batch.pos).max())
+    first = np.searchsorted(batch.pos, batch.pos - maxspan, side='left')
+    if int((np.arange(n) - first).max()) + 1 >= (max_depth or 8000):
+        yield lo, hi, _reads_struct(batch, need_qual)
+        return
+    batch.padded()
+    for c_lo in range(lo, hi, chunk):
+        c_hi = min(hi, c_lo + chunk)
+        i0, i1, _ = shard.halo_range(batch.pos, batch.endpos, c_lo, c_hi, maxspan=maxspan, mask=False)
+        d = dict(n_reads=i1 - i0, tid=batch.tid)
+        for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off'):
+            d[k] = getattr(batch, k)[i0:]
+        d['cigar'], d['seq4'] = batch.cigar, batch.seq4
+        d['qual'] = d['qual_off'] = d['name_prev'] = None
+        yield c_lo, c_hi, _cabi.make_reads_struct(d, n_reads=i1 - i0)
 
 
 def iter_pileup(stat, alignmentfile, fafile, pad, **kwargs):

@@ -266,3 +266,19 @@ def test_region_queries_through_the_bai_index(obam, ofa, monkeypatch):
     assert bam._all is None                                       # nothing decoded the whole file
     a = pysamstats.load_mapq_binned(fx('test.bam'), chrom='Pf3D7_01_v3', start=2000, end=20000)
     assert_recarrays_equal(orc.load_binned('mapq', obam['test'], None, chrom='Pf3D7_01_v3', start=2000, end=20000), a, 'mapq_binned')
+
+
+def test_chunked_tables_equal_single_call(monkeypatch):
+    # a contig streams through pileup_tables in pieces of PSS_TABLE_CHUNK positions (bounded host memory for
+    # stat_* / the writers); same rows as one call, with pad / truncate / one_based and on every kernel family
+    cases = (('variation_strand', dict()), ('coverage_ext', dict(chrom='Pf3D7_02_v3', start=1000, end=40000, pad=True)),
+             ('coverage', dict(chrom='Pf3D7_01_v3', start=500, end=30000, truncate=True, one_based=True)),
+             ('mapq_strand', dict(chrom='Pf3D7_03_v3')), ('tlen', dict(chrom='Pf3D7_01_v3', pad=True, start=0, end=50000)),
+             ('variation', dict(no_del=True, min_mapq=20)))
+    expect = [_load(stat, 'test', **kw) for stat, kw in cases]
+    monkeypatch.setenv('PSS_TABLE_CHUNK', '4096')
+    for (stat, kw), e in zip(cases, expect):
+        assert_recarrays_equal(e, _load(stat, 'test', **kw), '%s %r chunked' % (stat, kw))
+    rows = list(pysamstats.stat_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=1000, end=20000))
+    monkeypatch.delenv('PSS_TABLE_CHUNK')
+    assert rows == list(pysamstats.stat_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=1000, end=20000))
