@@ -431,6 +431,13 @@ __device__ void cover_read(const TileCtx &T, const TileArgs &A, const RInfo &r, 
 // kinds the match / mismatch / base-class / insertion contribution of that base.  Everything is
 // linear in the counters, so the order against the main pass does not matter.
 
+__device__ __forceinline__ void lowq_prefetch(const TileArgs &A, const RInfo &r, int ridx) {
+    // the read's mark words are wanted after its walk: start them towards L1 now (a 150 bp read: 20 bytes)
+    const uint32_t *mw = A.lowq + (r.seq_off >> 4) + ridx;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(mw));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(mw + 4));
+}
+
 // calls f(p, qi, last) for every marked base of the aligned span [x, x + l) (first base query index y)
 // that lies in the tile: p tile-relative position, qi query index, last: it is the last base of the span
 template <class F>
@@ -438,8 +445,8 @@ __device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int 
     const int a = max(x - t0, 0), b = min(x + l - t0, TT);
     if (a >= b) return;
     const int qa = y + (a + t0 - x), qb = y + (b + t0 - x);       // query range [qa, qb)
-    for (int w = qa >> 5; w <= (qb - 1) >> 5; ++w) {
-        uint32_t m = __ldg(mw + w);
+    const int w0 = qa >> 5, w1 = (qb - 1) >> 5;
+    auto word = [&](uint32_t m, int w) {
         const int base = w << 5;
         if (base < qa) m &= 0xffffffffu << (qa - base);
         if (base + 32 > qb) m &= 0xffffffffu >> (base + 32 - qb);
@@ -449,7 +456,8 @@ __device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int 
             const int qi = base + bit;
             f(a + (qi - qa), qi, qi == y + l - 1);
         }
-    }
+    };
+    for (int w = w0; w <= w1; ++w) word(__ldg(mw + w), w);
 }
 
 // does an insertion follow CIGAR op k (htslib `indel > 0` at the last base of the op, A.1)?
@@ -544,6 +552,7 @@ __device__ void cover_lowq_fix(const TileCtx &T, const TileArgs &A, const RInfo 
             }
         }
     };
+    if (cls & CLS_SIMPLE) { lowq_span(mw, r.pos, r.end - r.pos, 0, T.t0, undo); return; }
     int x = r.pos, y = 0;
     for (int k = 0; k < nc && x < T.t1; ++k) {
         const uint32_t w = __ldg(cg + k);
@@ -898,6 +907,7 @@ k_tile(TileArgs A) {
                     if (MINQ && !(r.cls & CLS_HASSEQ)) {     // quality 0 everywhere: the bases are all dropped
                         if (part == 0) noseq_minq_read<KIND>(T, A, r, rawp);
                     } else {
+                        if (MINQ && part == 0) lowq_prefetch(A, r, cb + tid);
 #ifndef PSS_EXP_SKIP_WALK      // experiment builds only (scripts/build_variant.sh): time of the phases in isolation
                         var_read<LayVar>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
 #endif
@@ -909,6 +919,7 @@ k_tile(TileArgs A) {
                 const RInfo r = s_ri[tid];
                 if (MINQ && !(r.cls & CLS_HASSEQ)) noseq_minq_read<KIND>(T, A, r, rawp);
                 else {
+                    if (MINQ) lowq_prefetch(A, r, cb + tid);
                     cover_read<KIND>(T, A, r, rawp);
                     if (MINQ) cover_lowq_fix<KIND>(T, A, r, cb + tid);
                 }
