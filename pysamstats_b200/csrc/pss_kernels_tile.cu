@@ -374,6 +374,144 @@ __device__ __forceinline__ void var_read(const TileCtx &T, const uint32_t *cg, c
     }
 }
 
+// does an insertion follow CIGAR op k (htslib `indel > 0` at the last base of the op, A.1)?
+__device__ __forceinline__ bool ins_follows(const uint32_t *cg, int nc, int k) {
+    if (k + 1 >= nc) return false;
+    const uint32_t w2 = cg[k + 1];
+    const int op2 = w2 & 15;
+    if (op2 == OP_I) return (w2 >> 4) > 0;
+    if (op2 == OP_P && k + 2 < nc) {
+        long long l3 = 0;
+        for (int j = k + 2; j < nc; ++j) {
+            const uint32_t w3 = cg[j];
+            const int op3 = w3 & 15;
+            if (op3 == OP_I) l3 += (w3 >> 4);
+            else if (op3 == OP_D || op3 == OP_M || op3 == OP_N || op3 == OP_EQ || op3 == OP_X) break;
+        }
+        return l3 > 0;
+    }
+    return false;
+}
+
+// ---- variation, balanced walk -----------------------------------------------------------------
+//
+// var_read gives a read to one or two threads, so a thread's work is the read's overlap with the tile
+// (0 .. 19 words) and the threads beyond 2 n idle; everybody then waits at the barrier for the longest.
+// The balanced walk splits the chunk in two steps: (A) one thread per read applies what is constant
+// along spans (interval adds, insertion points) and emits a record per aligned span that overlaps the
+// tile; (B) after a prefix sum over the spans' word counts every thread takes the same number of
+// consecutive 8-base words, wherever they fall among the spans.
+// Measured on the 250 Mb workload (parity-green): 14.7 ms against 13.6 ms for var_read -- the extra block
+// barrier, the prefix sums and the per-thread binary search cost more than the balance gains -- so it is off.
+#ifndef TBAL
+#define TBAL 0               // 1: balanced walk; 0: the read-per-thread walk (var_read) for every chunk
+#endif
+#define SPAN_MAX (TCH + 64)  // span records per chunk
+
+struct SpanRec;
+__device__ __forceinline__ void var_walk_span(const TileCtx &T, const SpanRec &sr, int k, int kend);
+
+struct __align__(16) SpanRec {
+    uint32_t a_len;      // tile-relative start | length << 16 (length <= TT)
+    uint32_t sn;         // nibble index of the span's first base in the staged sequence stream
+    uint32_t bank;
+    uint32_t wbase;      // exclusive prefix sum of the spans' word counts
+};
+
+// step A for one read (spans beyond the list's capacity are walked on the spot)
+__device__ __forceinline__ bool var_emit_spans(const TileCtx &T, const uint32_t *cg, const RInfo &r, uint32_t sn0, uint32_t *raw,
+                                               SpanRec *spans, int *nspan) {
+    const uint32_t cls = r.cls;
+    if (!(cls & CLS_ADMITTED)) return true;
+    if (raw) interval_add(raw, r.pos, r.end - r.pos, T.t0, 1u);
+    if (!(cls & CLS_COUNTED)) return true;
+    const int bank = cls & 3u;
+    const uint32_t inc = half_inc(bank);
+    if (!T.no_del) interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, r.pos, r.end - r.pos, T.t0, inc);   // M, D and N all count
+    if (cls & CLS_NOREF) {   // mapped, CIGAR consumes no reference: one deletion event at pos
+        if (!T.no_del) interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, r.pos, 1, T.t0, inc);
+        return true;
+    }
+    uint32_t *mt = T.cnt + (W_MATCH + (bank >> 1)) * TT;
+    auto span = [&](int x, int l, int y) -> bool {
+        const int a = max(x - T.t0, 0), b = min(x + l - T.t0, TT);
+        if (a >= b) return true;
+        atomicAdd(mt + a, inc);
+        if (b < TT) atomicAdd(mt + b, 0u - inc);
+        if (T.no_del) interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, x, l, T.t0, inc);   // D / N spans do not count
+        SpanRec s;
+        s.a_len = (uint32_t)a | ((uint32_t)(b - a) << 16);
+        s.sn = sn0 + (uint32_t)(y + (a + T.t0 - x));
+        s.bank = (uint32_t)bank;
+        s.wbase = 0;
+        const int k = atomicAdd(nspan, 1);
+        if (k < SPAN_MAX) spans[k] = s;
+        else var_walk_span(T, s, 0, (b - a + 7) >> 3);      // the list is full: this thread walks the span itself
+        return true;
+    };
+    if (cls & CLS_SIMPLE) return span(r.pos, r.end - r.pos, 0);
+    const int nc = (int)r.n_cigar;
+    int x = r.pos, y = 0;
+    for (int k = 0; k < nc && x < T.t1; ++k) {
+        const uint32_t w = cg[k];
+        const int op = w & 15, l = (int)(w >> 4);
+        if (op_is_match(op)) {
+            if (x + l > T.t0) {
+                if (!span(x, l, y)) return false;
+                const int li = x + l - 1 - T.t0;            // htslib indel > 0 at the last base of the op (A.1), opt.pyx:501
+                if (li >= 0 && li < TT && ins_follows(cg, nc, k)) atomicAdd(T.cnt + (W_INS + (bank >> 1)) * TT + li, inc);
+            }
+            x += l; y += l;
+        } else if (op == OP_D || op == OP_N) {
+            if (op == OP_D && !T.no_del && x + l > T.t0) interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, x, l, T.t0, inc);
+            x += l;
+        } else if (op == OP_I || op == OP_S) y += l;
+    }
+    return true;
+}
+
+// words [k, kend) of one span
+__device__ __forceinline__ void var_walk_span(const TileCtx &T, const SpanRec &sr, int k, int kend) {
+    const int a = (int)(sr.a_len & 0xffffu), len = (int)(sr.a_len >> 16);
+    const int bank = (int)sr.bank;
+    const uint32_t sn = sr.sn + 8u * (uint32_t)k;
+    int p0 = a + 8 * k;
+    const uint32_t *sp = T.seqw + (sn >> 3), *rp = T.refn + ((uint32_t)p0 >> 3);
+    const uint32_t ssh = (sn & 7u) << 2, rsh = ((uint32_t)p0 & 7u) << 2;
+    uint32_t s0 = __byte_perm(sp[0], 0, 0x0123), r0 = rp[0];
+    for (; k < kend; ++k, p0 += 8) {
+        ++sp; ++rp;
+        const uint32_t s1 = __byte_perm(sp[0], 0, 0x0123), r1 = rp[0];
+        const uint32_t sw = __funnelshift_l(s1, s0, ssh);
+        uint32_t xr = sw ^ __funnelshift_l(r1, r0, rsh);
+        const int rem = len - 8 * k;
+        if (rem < 8) xr &= 0xffffffffu << ((8 - rem) << 2);
+        s0 = s1; r0 = r1;
+        while (xr) {
+            const int lz = __clz(xr) >> 2, sh = 28 - (lz << 2);
+            var_mismatch<LayVar>(T, bank, p0 + lz, (sw >> sh) & 15, -1);
+            xr &= ~(0xfu << sh);
+        }
+    }
+}
+
+// step B: words [g0, g1) of the chunk's span list
+__device__ __forceinline__ void var_walk_words(const TileCtx &T, const SpanRec *spans, int nspan, int g0, int g1) {
+    if (g0 >= g1) return;
+    int lo = 0, hi = nspan - 1;                      // last span whose wbase <= g0
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)spans[mid].wbase <= g0) lo = mid; else hi = mid - 1; }
+    int i = lo, g = g0;
+    while (g < g1) {
+        const SpanRec sr = spans[i];
+        const int nw = (int)((sr.a_len >> 16) + 7) >> 3;
+        const int k = g - (int)sr.wbase;
+        const int kend = min(nw, k + (g1 - g));
+        var_walk_span(T, sr, k, kend);
+        g += kend - k;
+        ++i;
+    }
+}
+
 // ---- coverage kinds: one read per thread ------------------------------------------------------
 
 template <int KIND>
@@ -458,25 +596,6 @@ __device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int 
         }
     };
     for (int w = w0; w <= w1; ++w) word(__ldg(mw + w), w);
-}
-
-// does an insertion follow CIGAR op k (htslib `indel > 0` at the last base of the op, A.1)?
-__device__ __forceinline__ bool ins_follows(const uint32_t *cg, int nc, int k) {
-    if (k + 1 >= nc) return false;
-    const uint32_t w2 = cg[k + 1];
-    const int op2 = w2 & 15;
-    if (op2 == OP_I) return (w2 >> 4) > 0;
-    if (op2 == OP_P && k + 2 < nc) {
-        long long l3 = 0;
-        for (int j = k + 2; j < nc; ++j) {
-            const uint32_t w3 = cg[j];
-            const int op3 = w3 & 15;
-            if (op3 == OP_I) l3 += (w3 >> 4);
-            else if (op3 == OP_D || op3 == OP_M || op3 == OP_N || op3 == OP_EQ || op3 == OP_X) break;
-        }
-        return l3 > 0;
-    }
-    return false;
 }
 
 // variation kinds (LayVar).  Reads without sequence have quality 0 at every base: they keep only their
@@ -816,11 +935,13 @@ k_tile(TileArgs A) {
     uint32_t *s_refn = reinterpret_cast<uint32_t *>(s_ri + TCH);       // REFN_WORDS + 4 words
     uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_refn + REFN_WORDS + 4);   // TSEQ_BYTES + 32
     uint32_t *s_cig = reinterpret_cast<uint32_t *>(s_seq + TSEQ_BYTES + 32);  // TCIG_WORDS + 8
-    uint16_t *s_ev = reinterpret_cast<uint16_t *>(s_cig + TCIG_WORDS + 8);    // EV_SLOTS x EV_STRIDE
+    SpanRec *s_span = reinterpret_cast<SpanRec *>(s_cig + TCIG_WORDS + 8);     // SPAN_MAX records (balanced walk)
+    uint16_t *s_ev = reinterpret_cast<uint16_t *>(s_span + (TBAL ? SPAN_MAX : 0));   // EV_SLOTS x EV_STRIDE (DEFER layouts)
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_n;
     __shared__ long long s_seqlo;      // global byte index staged at s_seq[0]
     __shared__ long long s_ciglo;      // global CIGAR word index staged at s_cig[0], -1: not staged
+    __shared__ int s_nspan;            // span records of the current chunk
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -843,6 +964,7 @@ k_tile(TileArgs A) {
     }
     if (tid == 0) {
         mbar_init(&s_bar, 1);
+        s_nspan = 0;
         uint32_t bytes = 0, sbytes = 0, cbytes = 0;
         const uint8_t *src = nullptr, *csrc = nullptr;
         const int n = d.n0;
@@ -896,7 +1018,45 @@ k_tile(TileArgs A) {
                 if (n == 0) { more = false; break; }
             }
             if (in_pass + n > PASS_READS) break;       // finalise what we have, then come back to this chunk
-            if (KIND == KIND_VAR) {
+            if (KIND == KIND_VAR && TBAL && !T.slow) {
+                // balanced walk: (A) one thread per read -- interval adds, insertion points, span records
+                if (tid < n) {
+                    const RInfo r = s_ri[tid];
+                    const long long ciglo = s_ciglo;
+                    const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
+                    const uint32_t sn0 = (uint32_t)((r.seq_off - s_seqlo) << 1);
+                    if (!(r.cls & CLS_HASSEQ)) {       // every base a mismatch of no class (or, under min_baseq, dropped)
+                        if (MINQ) noseq_minq_read<KIND>(T, A, r, rawp);
+                        else var_read<LayVar>(T, cg, r, sn0, rawp, 0, 1);
+                    } else {
+                        if (MINQ) lowq_prefetch(A, r, cb + tid);
+#ifndef PSS_EXP_SKIP_WALK
+                        var_emit_spans(T, cg, r, sn0, rawp, s_span, &s_nspan);
+#endif
+                        if (MINQ) var_lowq_fix(T, A, cg, r, sn0, cb + tid);
+                    }
+                }
+                __syncthreads();
+                // (B) every warp computes the prefix sums of the spans' word counts itself (cheaper than one more
+                // block barrier), then every thread walks the same number of consecutive words
+                const int ns = min(s_nspan, SPAN_MAX);
+                int total = 0;
+                for (int base = 0; base < ns; base += 32) {
+                    const int i = base + lane;
+                    const int nw = i < ns ? (int)((s_span[i].a_len >> 16) + 7) >> 3 : 0;
+                    int inc = nw;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    if (i < ns) s_span[i].wbase = (uint32_t)(total + inc - nw);
+                    total += __shfl_sync(FULL, inc, 31);
+                }
+                __syncwarp();
+                const int quota = (total + NT - 1) / NT;
+                var_walk_words(T, s_span, ns, tid * quota, min(total, (tid + 1) * quota));
+            } else if (KIND == KIND_VAR) {
                 // up to four threads share a read: threads [k n, (k + 1) n) are part k of reads 0 .. n-1
                 const int nparts = min(4, NT / n);
                 const int part = tid / n;
@@ -945,6 +1105,7 @@ k_tile(TileArgs A) {
                     }
                 }
                 s_n = m;
+                s_nspan = 0;
                 fence_proxy_async();
                 if (m > 0) {
                     mbar_arrive_expect_tx(&s_bar, (uint32_t)m * (uint32_t)sizeof(RInfo) + sbytes + cbytes);
@@ -1696,7 +1857,7 @@ template <int KIND>
 static size_t tile_smem_bytes() {
     size_t narr = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT + 1;   // + raw
     size_t b = narr * TT * 4 + sizeof(RInfo) * TCH;
-    if (KIND == KIND_VAR) b += (REFN_WORDS + 4) * 4 + TSEQ_BYTES + 32 + (TCIG_WORDS + 8) * 4 + EV_SLOTS * EV_STRIDE * 2;
+    if (KIND == KIND_VAR) b += (REFN_WORDS + 4) * 4 + TSEQ_BYTES + 32 + (TCIG_WORDS + 8) * 4 + (TBAL ? SPAN_MAX * sizeof(SpanRec) : 0) + (LayVar::DEFER ? EV_SLOTS * EV_STRIDE * 2 : 0);
     return b;
 }
 
