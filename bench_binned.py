@@ -73,8 +73,20 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # algorithmic bytes of one sweep on this rank: coverage_gc = 3 int32 columns + row mask +
+    # reference byte per position and 29 + 4 n_ops bytes per read; every binned statistic 15 bytes per read
+    # (pos, flag, mapq, tlen, mtid) + its int32 columns per window; coverage_binned also reads the reference
+    nwin = per // W
+    alg = (hi - lo) * (4 * 3 + 1 + 1) + n_reads * 29 + 4 * int(batch['n_cigar_words'])
+    alg += sum(n_reads * 15 + 4 * len(config.value_fields_binned(t)) * nwin for t in binned) + (hi - lo)
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    peak = float(json.load(open(peaks_path))['hbm_gbs']) if os.path.exists(peaks_path) else 6650.0
     if rank == 0:
-        print(json.dumps({'metric': 'genome positions/sec (coverage_gc + coverage/mapq/tlen binned sweep, window 300)',
+        achieved = alg / (ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'algorithmic_bytes_per_step': alg, 'what': 'the whole sweep (tile kernel for coverage + k_gc + 3 x (k_binned_acc, '
+                    'k_binned_fin) + k_binned_gc), not one kernel'}
+        print(json.dumps({'roofline': roofline, 'metric': 'genome positions/sec (coverage_gc + coverage/mapq/tlen binned sweep, window 300)',
                           'value': genome / (ms * 1e-3), 'unit': 'positions/s', 'reads_per_s': n_reads * world / (ms * 1e-3),
                           'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'scaling': 'weak',
                           'windows_per_gpu': per // W, 'reads_per_gpu': n_reads, 'data': 'synthetic',

@@ -579,7 +579,7 @@ __device__ __forceinline__ void lowq_prefetch(const TileArgs &A, const RInfo &r,
 // calls f(p, qi, last) for every marked base of the aligned span [x, x + l) (first base query index y)
 // that lies in the tile: p tile-relative position, qi query index, last: it is the last base of the span
 template <class F>
-__device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int y, int t0, F f) {
+__device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int y, int t0, F f, int part = 0, int nparts = 1) {
     const int a = max(x - t0, 0), b = min(x + l - t0, TT);
     if (a >= b) return;
     const int qa = y + (a + t0 - x), qb = y + (b + t0 - x);       // query range [qa, qb)
@@ -595,12 +595,13 @@ __device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int 
             f(a + (qi - qa), qi, qi == y + l - 1);
         }
     };
-    for (int w = w0; w <= w1; ++w) word(__ldg(mw + w), w);
+    for (int w = w0 + part; w <= w1; w += nparts) word(__ldg(mw + w), w);       // the threads sharing a read take words in turn
 }
 
 // variation kinds (LayVar).  Reads without sequence have quality 0 at every base: they keep only their
 // deletion / ref-skip events, which var_read is told through `drop_bases`.
-__device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t *cg, const RInfo &r, uint32_t sn0, int ridx) {
+__device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t *cg, const RInfo &r, uint32_t sn0, int ridx,
+                             int part, int nparts) {
     const uint32_t cls = r.cls;
     if (!(cls & CLS_COUNTED) || (cls & CLS_NOREF) || !(cls & CLS_HASSEQ)) return;
     const int bank = cls & 3u, pp = bank >> 1;
@@ -635,7 +636,7 @@ __device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t
                         if (c < 5) atomicAdd(T.cnt + (W_MMC + 2 * c + pp) * TT + p, 0u - inc);
                     }
                     if (last && ins) atomicAdd(T.cnt + (W_INS + pp) * TT + p, 0u - inc);
-                });
+                }, part, nparts);
             }
             x += l; y += l;
         } else if (op == OP_D || op == OP_N) x += l;
@@ -1033,7 +1034,7 @@ k_tile(TileArgs A) {
 #ifndef PSS_EXP_SKIP_WALK
                         var_emit_spans(T, cg, r, sn0, rawp, s_span, &s_nspan);
 #endif
-                        if (MINQ) var_lowq_fix(T, A, cg, r, sn0, cb + tid);
+                        if (MINQ) var_lowq_fix(T, A, cg, r, sn0, cb + tid, 0, 1);
                     }
                 }
                 __syncthreads();
@@ -1067,12 +1068,11 @@ k_tile(TileArgs A) {
                     if (MINQ && !(r.cls & CLS_HASSEQ)) {     // quality 0 everywhere: the bases are all dropped
                         if (part == 0) noseq_minq_read<KIND>(T, A, r, rawp);
                     } else {
-                        if (MINQ && part == 0) lowq_prefetch(A, r, cb + tid);
+                        if (MINQ) lowq_prefetch(A, r, cb + tid - part * n);
 #ifndef PSS_EXP_SKIP_WALK      // experiment builds only (scripts/build_variant.sh): time of the phases in isolation
                         var_read<LayVar>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
 #endif
-                        if (MINQ && part == 0)
-                            var_lowq_fix(T, A, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), cb + tid);
+                        if (MINQ) var_lowq_fix(T, A, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), cb + tid - part * n, part, nparts);
                     }
                 }
             } else if (tid < n) {
