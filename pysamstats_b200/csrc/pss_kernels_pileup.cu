@@ -625,7 +625,10 @@ k_pileup(PileupArgs a) {
 template <class ACC>
 static cudaError_t launch_one(const PileupArgs &a, int64_t ntiles, bool staged, cudaStream_t s) {
     const size_t smem = sizeof(GatherSmem);
-    static bool configured = false;     // per instantiation
+    static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
+    int dev__ = 0;
+    cudaGetDevice(&dev__);
+    bool &configured = configured_dev[dev__ & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_pileup<ACC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)

@@ -1864,7 +1864,10 @@ static size_t tile_smem_bytes() {
 template <int KIND, int STAT, bool MINQ>
 static cudaError_t launch_tile_mq(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
     size_t smem = tile_smem_bytes<KIND>();
-    static bool configured = false;     // per instantiation
+    static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
+    int dev__ = 0;
+    cudaGetDevice(&dev__);
+    bool &configured = configured_dev[dev__ & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tile<KIND, STAT, MINQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1910,7 +1913,10 @@ cudaError_t launch_lowq(const pss_reads &R, const uint8_t *qual, int min_baseq, 
 template <int KIND, int STAT>
 static cudaError_t launch_tileq_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
     const size_t smem = (size_t)q_layout<KIND>().total;
-    static bool configured = false;     // per instantiation
+    static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
+    int dev__ = 0;
+    cudaGetDevice(&dev__);
+    bool &configured = configured_dev[dev__ & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tileq<KIND, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1934,7 +1940,10 @@ size_t tile_redo_bytes(int64_t ntiles) { return sizeof(int32_t) * (size_t)ntiles
 template <int STAT>
 static cudaError_t launch_tilet_one(const TileArgs &a, const int32_t *tlen, int32_t *redo, int64_t ntiles, cudaStream_t s) {
     const size_t smem = (size_t)(TLEN_NW + 1) * TT * 4 + (size_t)QCH * sizeof(RInfo) + (QCH + 8) * 4;
-    static bool configured = false;
+    static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
+    int dev__ = 0;
+    cudaGetDevice(&dev__);
+    bool &configured = configured_dev[dev__ & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tilet<STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1963,7 +1972,10 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
                         int need_raw, int64_t ntiles, void *desc_buf, void *refpack_buf, bool desc_valid,
                         cudaStream_t s, int64_t *launches, cudaEvent_t e0, cudaEvent_t e1) {
     if (ntiles <= 0) return cudaSuccess;
-    static bool table_ready = false;
+    static bool table_ready_dev[64] = {false};   // the __constant__ table exists per device
+    int dev_t = 0;
+    cudaGetDevice(&dev_t);
+    bool &table_ready = table_ready_dev[dev_t & 63];
     if (!table_ready) {
         uint8_t t[256];
         refcode_table(t);
