@@ -36,7 +36,8 @@ extern "C" {
 #define PSS_ECUDA (-2)    /* CUDA runtime / launch failure */
 #define PSS_ENOMEM (-3)   /* workspace allocation failed */
 #define PSS_EUNSORTED (-4) /* batch not coordinate sorted (htslib: "unsorted positions") */
-#define PSS_ETOOLONG (-5)  /* a read of several kb met the short-read kernels; see PSS_FLAG_LONG_READS */
+#define PSS_ETOOLONG (-5)  /* a read of several kb met the short-read kernels; see PSS_FLAG_LONG_READS (the *_host
+                              entry points repeat such a call with that flag themselves) */
 
 /* pss_pileup_params.flags */
 #define PSS_FLAG_GENERIC_KERNEL 1 /* always use the generic per-position kernel (testing / comparison) */

@@ -741,7 +741,19 @@ extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32
             if ((rc = to_device(ctx, ctx->hb[13], P[i].ref, (size_t)P[i].ref_len, &ref_dev, s)) != PSS_OK) return rc;
     if ((rc = host_multi_run(ctx, reads, &D, n_stats, P, ref_dev, need_qual, outs, P[0].end - P[0].start, rowmasks, s)) != PSS_OK)
         return rc;
-    return pss_synchronize(ctx, s);
+    rc = pss_synchronize(ctx, s);
+    if (rc == PSS_ETOOLONG) {
+        // a read did not fit the kernels' staging buffers (long-read data): repeat the call on the per-position
+        // kernel that reads bases / qualities from global memory -- callers of the reference API cannot set flags
+        bool all_long = true;
+        std::vector<pss_pileup_params> Pl(P, P + n_stats);
+        for (auto &q : Pl) { all_long = all_long && (q.flags & PSS_FLAG_LONG_READS); q.flags |= PSS_FLAG_LONG_READS; }
+        if (all_long) return rc;
+        if ((rc = host_multi_run(ctx, reads, &D, n_stats, Pl.data(), ref_dev, need_qual, outs, P[0].end - P[0].start, rowmasks, s)) != PSS_OK)
+            return rc;
+        rc = pss_synchronize(ctx, s);
+    }
+    return rc;
 }
 
 // Whole-range streaming.  The range is cut into position chunks; chunk k + 1's reads (and reference slice)

@@ -322,3 +322,37 @@ def test_tlen_rounding_boundaries_and_replay(stat, ctx, small, monkeypatch):
     monkeypatch.setenv('PSS_TLEN_FORCE_REPLAY', '1')
     b, mb = _run_host(ctx, nbs, refs, stat, 0, G)
     assert np.array_equal(a, b) and np.array_equal(ma, mb)
+
+
+@pytest.mark.parametrize('stat', ('coverage', 'variation_strand', 'baseq_ext', 'mapq', 'tlen'))
+def test_long_reads_need_no_flag(stat, ctx):
+    # reads of several kb do not fit the staging buffers of the short-read kernels; the host entry point repeats
+    # the call on the long-read kernel by itself (the reference API has no way to pass PSS_FLAG_LONG_READS)
+    rng = np.random.default_rng(5)
+    G = 60000
+    ref = rng.choice(list(b'ACGT'), G).astype('u1')
+    code = np.zeros(256, 'u1')
+    code[list(b'ACGT')] = (1, 2, 4, 8)
+    lens = np.array([12000, 150, 7000, 150, 150, 9001, 150])
+    pos = np.sort(rng.integers(0, G - 13000, len(lens))).astype('i4')
+    n = len(lens)
+    seqs, quals, seq_off, qual_off = [], [], [0], [0]
+    for p, ln in zip(pos, lens):
+        b = code[ref[p:p + ln]].copy()
+        sub = rng.random(ln) < 0.02
+        b[sub] = rng.choice([1, 2, 4, 8], int(sub.sum()))
+        if ln % 2:
+            b = np.append(b, 0).astype('u1')
+        seqs.append(((b[0::2] << 4) | b[1::2]).astype('u1'))
+        quals.append(rng.integers(2, 41, ln).astype('u1'))
+        seq_off.append(seq_off[-1] + len(seqs[-1]))
+        qual_off.append(qual_off[-1] + ln)
+    nb = dict(n_reads=n, tid=0, pos=pos, flag=rng.choice([0, 16], n).astype('u2'), mapq=rng.choice([0, 30, 60], n).astype('u1'),
+              tlen=np.zeros(n, 'i4'), mtid=np.full(n, -1, 'i4'), l_seq=lens.astype('i4'),
+              cigar_off=np.arange(n + 1, dtype='i8'), cigar=(lens << 4).astype('u4'),
+              seq_off=np.array(seq_off, 'i8'), seq4=np.concatenate(seqs), qual_off=np.array(qual_off, 'i8'),
+              qual=np.concatenate(quals), name_prev=np.full(n, -1, 'i4'), endpos=pos.astype('i8') + lens)
+    reads = oracle_reads_from_arrays(nb)
+    out, mask = _run_host(ctx, nb, ref, stat, 0, G)
+    pos_o, F = _oracle(stat, reads, ref, 0, G)
+    _compare(out, mask, pos_o, F, 0, stat)
