@@ -167,17 +167,19 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
         if npos <= 0:
             continue
         refseq = fa.contig(c) if (fa is not None and needs_ref) else np.zeros(0, np.uint8)
-        params = ctx.pileup_params(name, stepper=stepper, max_depth=max_depth, min_mapq=min_mapq,
-                                   min_baseq=min_baseq, no_del=no_del, no_dup=no_dup,
-                                   window_size=stat.window_size, window_offset=stat.window_offset,
-                                   start=lo, end=hi, ref=refseq if len(refseq) else None, ref_start=0,
-                                   ref_len=len(refseq), contig_len=len(refseq))
-        for c_lo, c_hi, reads in _position_chunks(batch, lo, hi, need_qual, max_depth):
+        pkw = dict(stepper=stepper, max_depth=max_depth, min_mapq=min_mapq, min_baseq=min_baseq, no_del=no_del,
+                   no_dup=no_dup, window_size=stat.window_size, window_offset=stat.window_offset,
+                   ref=refseq if len(refseq) else None, ref_start=0, ref_len=len(refseq), contig_len=len(refseq))
+
+        def run_piece(piece, device):
+            """One position piece on one GPU -> (pos, ref column, fields) or None when it has no rows."""
+            c_lo, c_hi, reads = piece
+            pctx = _cabi.get_context(device)
             cn = c_hi - c_lo
-            params.start, params.end = c_lo, c_hi
+            params = pctx.pileup_params(name, start=c_lo, end=c_hi, **pkw)
             out = bamio.alloc_big((len(names), cn), np.int32)
             rowmask = np.empty(cn, dtype=np.uint8)
-            ctx.pileup_host(reads, params, out, rowmask)
+            pctx.pileup_host(reads, params, out, rowmask)
             rows = rowmask.view(bool)
             if pad:
                 rows = rows.copy()
@@ -188,7 +190,7 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
             else:
                 sel = np.flatnonzero(rows)
                 if len(sel) == 0:
-                    continue
+                    return None
                 pos = sel.astype(np.int64) + c_lo
                 taken = bamio.take_cols(out, sel)
                 fields = {f: taken[j] for j, f in enumerate(names)}
@@ -199,7 +201,45 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
                 raise OverflowError('Python integer -1 out of bounds for uint8')
             if one_based:
                 pos = pos + 1
-            yield c, pos, ref, fields
+            return pos, ref, fields
+
+        for res in _run_pieces(run_piece, _position_chunks(batch, lo, hi, need_qual, max_depth), ctx.device):
+            if res is not None:
+                yield (c,) + res
+
+
+def _devices(default):
+    """GPUs the pieces of a contig are spread over: PSS_GPUS = a count or 'all' (default: one, the context's)."""
+    import os
+    v = os.environ.get('PSS_GPUS', '').strip().lower()
+    if v in ('', '0', '1'):
+        return [default]
+    import torch
+    n = torch.cuda.device_count()
+    k = n if v == 'all' else min(int(v), n)
+    return list(range(k)) if k > 1 else [default]
+
+
+def _run_pieces(fn, pieces, default_device):
+    """Results of fn(piece, device) in piece order.  With several GPUs (PSS_GPUS) piece i goes to GPU i mod n from a
+    thread per GPU -- the interval sharding of SURVEY.md section 8e behind the public API: contiguous position
+    intervals, the halo of reads that start before them, no collective, pieces concatenated in order -- and at most
+    n pieces are in flight, so a GPU never runs two at once."""
+    devs = _devices(default_device)
+    if len(devs) == 1:
+        for piece in pieces:
+            yield fn(piece, devs[0])
+        return
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(devs)) as ex:
+        pending = deque()
+        for i, piece in enumerate(pieces):
+            if len(pending) == len(devs):
+                yield pending.popleft().result()
+            pending.append(ex.submit(fn, piece, devs[i % len(devs)]))
+        while pending:
+            yield pending.popleft().result()
 
 
 def _position_chunks(batch, lo, hi, need_qual, max_depth):

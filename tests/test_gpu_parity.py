@@ -282,3 +282,18 @@ def test_chunked_tables_equal_single_call(monkeypatch):
     rows = list(pysamstats.stat_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=1000, end=20000))
     monkeypatch.delenv('PSS_TABLE_CHUNK')
     assert rows == list(pysamstats.stat_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=1000, end=20000))
+
+
+def test_pieces_across_gpus(monkeypatch):
+    # PSS_GPUS: the position pieces of a contig go to the GPUs of the box in turn (a thread per GPU, no collective),
+    # the host concatenates them in order -- same rows as one GPU
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    cases = (('variation_strand', dict()), ('coverage_ext', dict(chrom='Pf3D7_02_v3', start=1000, end=40000, pad=True)),
+             ('mapq', dict(chrom='Pf3D7_01_v3')), ('tlen_strand', dict(chrom='Pf3D7_03_v3')))
+    expect = [_load(stat, 'test', **kw) for stat, kw in cases]
+    monkeypatch.setenv('PSS_TABLE_CHUNK', '4096')
+    monkeypatch.setenv('PSS_GPUS', 'all')
+    for (stat, kw), e in zip(cases, expect):
+        assert_recarrays_equal(e, _load(stat, 'test', **kw), '%s %r on %d GPUs' % (stat, kw, torch.cuda.device_count()))
