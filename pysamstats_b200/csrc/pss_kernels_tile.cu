@@ -59,6 +59,9 @@ template <> struct KindLaunch<2 /* KIND_VAR */> { static const int NT = TTHREADS
 #define REFN_WORDS (TT / 8)
 #define TCIG_WORDS 384        // staged CIGAR words per chunk (else the chunk's reads load them from global)
 #define PASS_READS 65535      // reads per pass: what a 16-bit counter can hold
+#ifndef TPREFETCH
+#define TPREFETCH 176         // tiles ahead whose staging data a CTA asks into L2 (0: off); 64 .. 300 measure the same
+#endif
 
 enum { KIND_COV = 0, KIND_EXT = 1, KIND_VAR = 2 };
 
@@ -989,6 +992,29 @@ k_tile(TileArgs A) {
         } else mbar_arrive_expect_tx(&s_bar, 0);
     }
     STAMP(1);
+#if TPREFETCH > 0
+    // CTAs start in tile order, so tile + TPREFETCH starts about when this one ends: the first lane of the last warp
+    // (no part in the walk of a typical tile) asks for that tile's records / sequences / CIGARs to be brought into
+    // L2, so its bulk copies do not wait for DRAM
+    if (tid == NT - 32 && tile + TPREFETCH < (int)gridDim.x) {
+        const uint4 *dp = reinterpret_cast<const uint4 *>(A.desc + tile + TPREFETCH);
+        const uint4 p0 = __ldg(dp), p1 = __ldg(dp + 1), p2 = __ldg(dp + 2);
+        const int pn = (int)p0.z;
+        if (pn > 0) {
+            const uint8_t *src;
+            uint32_t nb;
+            long long first;
+            bulk_prefetch_l2(A.ri + (int)p0.x, (uint32_t)pn * (uint32_t)sizeof(RInfo));
+            if (KIND == KIND_VAR) {
+            const long long lo = (long long)(((uint64_t)p1.y << 32) | p1.x), hi = (long long)(((uint64_t)p1.w << 32) | p1.z);
+            stage_span(A.seq4, lo, hi, 1, &src, &nb, &first);
+            if (nb) bulk_prefetch_l2(src, nb);
+            const long long clo = (long long)(((uint64_t)p2.y << 32) | p2.x), chi = (long long)(((uint64_t)p2.w << 32) | p2.z);
+            if (chi > clo) { stage_span(A.cigar, clo, chi, 4, &src, &nb, &first); bulk_prefetch_l2(src, nb); }
+            }
+        }
+    }
+#endif
 
     TileCtx T;
     T.cnt = cnt; T.seqw = reinterpret_cast<const uint32_t *>(s_seq); T.refn = s_refn;
@@ -1319,6 +1345,22 @@ k_tileq(TileArgs A) {
         mbar_init(&s_bar, 1);
         issue(dx, true);
     }
+#if TPREFETCH > 0
+    if (tid == QNT - 32 && tile + TPREFETCH < (int)gridDim.x) {      // a later tile's records (+ qualities) into L2, as in k_tile
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile + TPREFETCH));
+        const int px = (int)p0.x, pn = min(QCH, (int)p0.y - px);
+        if (pn > 0) {
+            bulk_prefetch_l2(A.ri + px, (uint32_t)pn * (uint32_t)sizeof(RInfo));
+            if (K::QUAL) {
+                const uint8_t *src;
+                uint32_t nb;
+                long long first;
+                stage_span(A.qual, A.qual_off[px], A.qual_off[px + pn], 1, &src, &nb, &first);
+                if (nb) bulk_prefetch_l2(src, nb);
+            }
+        }
+    }
+#endif
     {   // zero the counters (+ raw)
         const int nw4 = (K::NWORDS + 1) * TT / 4;
         const uint4 z = make_uint4(0, 0, 0, 0);
@@ -1701,6 +1743,13 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ tile
         s_amb = 0;
         issue(dx);
     }
+#if TPREFETCH > 0
+    if (tid == TLEN_NT - 32 && tile + TPREFETCH < (int)gridDim.x) {
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile + TPREFETCH));
+        const int px = (int)p0.x, pn = min(QCH, (int)p0.y - px);
+        if (pn > 0) bulk_prefetch_l2(A.ri + px, (uint32_t)pn * (uint32_t)sizeof(RInfo));
+    }
+#endif
     {
         const int nw4 = (TLEN_NW + 1) * TT / 4;
         const uint4 z = make_uint4(0, 0, 0, 0);
