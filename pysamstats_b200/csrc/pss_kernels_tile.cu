@@ -971,9 +971,12 @@ k_tile(TileArgs A) {
 
     // ---- thread 0 starts the bulk copies of the first chunk before anything else -------------
     TileDesc d;
+    uint4 d1 = make_uint4(0, 0, 0, 0), d2 = d1;
     {
+        // the whole descriptor in one round trip (thread 0 needs all of it before it can issue the copies)
         const uint4 *dp = reinterpret_cast<const uint4 *>(A.desc + tile);
-        uint4 d0 = __ldg(dp);
+        const uint4 d0 = __ldg(dp);
+        if (KIND == KIND_VAR && tid == 0) { d1 = __ldg(dp + 1); d2 = __ldg(dp + 2); }
         d.x = (int)d0.x; d.y = (int)d0.y; d.n0 = (int)d0.z;
         d.flags = (KIND == KIND_VAR) ? __ldg(A.tflags + tile) : 0u;
     }
@@ -984,8 +987,6 @@ k_tile(TileArgs A) {
         const uint8_t *src = nullptr, *csrc = nullptr;
         const int n = d.n0;
         if (KIND == KIND_VAR && n > 0) {
-            uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile) + 1);
-            uint4 d2 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile) + 2);
             long long lo = (long long)(((uint64_t)d1.y << 32) | d1.x), hi = (long long)(((uint64_t)d1.w << 32) | d1.z);
             stage_span(A.seq4, lo, hi, 1, &src, &sbytes, &s_seqlo);
             long long clo = (long long)(((uint64_t)d2.y << 32) | d2.x), chi = (long long)(((uint64_t)d2.w << 32) | d2.z);
