@@ -59,6 +59,9 @@ template <> struct KindLaunch<2 /* KIND_VAR */> { static const int NT = TTHREADS
 #define REFN_WORDS (TT / 8)
 #define TCIG_WORDS 384        // staged CIGAR words per chunk (else the chunk's reads load them from global)
 #define PASS_READS 65535      // reads per pass: what a 16-bit counter can hold
+#ifndef TFIN_LOOP
+#define TFIN_LOOP 1           // variation_strand: the finalisation as a rolled loop over the field groups
+#endif
 #ifndef TSTCS
 #define TSTCS 1               // int32 result columns are written once and never read again: streaming stores (13.20 -> 13.04 ms)
 #endif
@@ -860,6 +863,36 @@ __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32
         // part 0 -> groups 0-2, part 1 -> 3-5, part 2 -> 6-7, part 3 -> 8-9 (contiguous fields)
         const bool S = (STAT == PSS_VARIATION_STRAND);
         const int per = S ? 6 : 2;
+        if (TFIN_LOOP && S) {
+        // a rolled loop over the groups: the unrolled form is ~600 straight-line instructions per output mode, and
+        // thirty warps streaming through it miss the instruction caches (ncu: stall_no_instruction 2.2 per issue)
+        const int g0 = part == 0 ? 0 : part == 1 ? 3 : part == 2 ? 6 : 8, g1 = part == 0 ? 3 : part == 1 ? 6 : part == 2 ? 8 : 10;
+        // counter array (5 bits) and reference code whose positions also get the matches (4 bits) per group;
+        // mismatch classes A, C, G, T, N = 0..4 with 4-bit codes 1, 2, 4, 8, 15; output order A C T G N
+        const unsigned long long ARR = (unsigned long long)W_ALL | ((unsigned long long)W_MATCH << 5) | ((unsigned long long)W_MMT << 10) |
+                                       ((unsigned long long)W_DEL << 15) | ((unsigned long long)W_INS << 20) | ((unsigned long long)(W_MMC + 0) << 25) |
+                                       ((unsigned long long)(W_MMC + 2) << 30) | ((unsigned long long)(W_MMC + 6) << 35) |
+                                       ((unsigned long long)(W_MMC + 4) << 40) | ((unsigned long long)(W_MMC + 8) << 45);
+        const unsigned long long CODE = (1ull << 20) | (2ull << 24) | (8ull << 28) | (4ull << 32) | (15ull << 36);
+        O.skip(g0 * per);
+        uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+        uint32_t rc4 = 0;
+        if (part != 0) {
+            const uint32_t rw = refn[q >> 1];
+            rc4 = (q & 1) ? (rw & 0xffffu) : (rw >> 16);
+            m0 = ld4(cnt, W_MATCH, q); m1 = ld4(cnt, W_MATCH + 1, q);
+        }
+#pragma unroll 1
+        for (int g = g0; g < g1; ++g) {
+            const int arr = (int)((ARR >> (5 * g)) & 31u);
+            const uint32_t code = (uint32_t)((CODE >> (4 * g)) & 15u);
+            uint4 a0 = ld4(cnt, arr, q), a1 = ld4(cnt, arr + 1, q);
+            if (g == 0) { const uint4 sa = a0 + a1; all = lo16(sa) + hi16(sa); }
+            if (code) { a0 = base_count(a0, m0, rc4, code); a1 = base_count(a1, m1, rc4, code); }
+            O.template put_group<S>(a0, a1);
+        }
+        return all;
+        }
         if (part == 0) {
             const uint4 w0 = ld4(cnt, W_ALL, q), w1 = ld4(cnt, W_ALL + 1, q);
             const uint4 s = w0 + w1;
