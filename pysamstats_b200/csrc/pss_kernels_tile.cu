@@ -835,6 +835,13 @@ __device__ __forceinline__ uint4 base_count(uint4 m, uint4 mt, uint32_t rc4, uin
 
 // Writes the fields owned by (quad q, sub-part `part` of 4) and returns the quad's total read
 // count when this part computes it (part 0), for the row mask.
+// sub-parts a quad's fields are split into (tasks of tile_output): the per-task overhead (pointer arithmetic, range
+// checks) is worth sharing between more fields when a statistic has few
+template <int STAT> struct FinParts {
+    static const int N = (STAT == PSS_COVERAGE || STAT == PSS_COVERAGE_STRAND || STAT == PSS_COVERAGE_GC) ? 1
+                         : 4;      // (coverage_ext with 1 or 2: slower, the 192 threads are no longer all busy)
+};
+
 template <int STAT, int MODE>
 __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32_t *refn, int q, int part,
                                                QuadOut<MODE> &O) {
@@ -849,14 +856,20 @@ __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32
             else O.template put_group<false>(w0, w1);
         }
     } else if (STAT == PSS_COVERAGE_EXT || STAT == PSS_COVERAGE_EXT_STRAND) {
-        const uint4 wf = ld4(cnt, part, q), wr = ld4(cnt, 4 + part, q);   // classes 2 part, 2 part + 1
-        if (part == 0) all = lo16(wf) + lo16(wr);
-        O.skip(part * 2 * (STAT == PSS_COVERAGE_EXT ? 1 : 3));
+        // word array g (forward) / 4 + g (reverse) holds classes 2 g (low half), 2 g + 1; a sub-part takes 4 / N arrays
+        constexpr int GP = 4 / FinParts<STAT>::N;
+        O.skip(part * GP * 2 * (STAT == PSS_COVERAGE_EXT ? 1 : 3));
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint4 f = k ? hi16(wf) : lo16(wf), r = k ? hi16(wr) : lo16(wr);
-            O.put(f + r);
-            if (STAT == PSS_COVERAGE_EXT_STRAND) { O.put(f); O.put(r); }
+        for (int gg = 0; gg < GP; ++gg) {
+            const int g = part * GP + gg;
+            const uint4 wf = ld4(cnt, g, q), wr = ld4(cnt, 4 + g, q);
+            if (g == 0) all = lo16(wf) + lo16(wr);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint4 f = k ? hi16(wf) : lo16(wf), r = k ? hi16(wr) : lo16(wr);
+                O.put(f + r);
+                if (STAT == PSS_COVERAGE_EXT_STRAND) { O.put(f); O.put(r); }
+            }
         }
     } else {
         // groups: 0 reads, 1 matches, 2 mismatches, 3 deletions, 4 insertions, 5 A, 6 C, 7 T, 8 G, 9 N
@@ -933,7 +946,7 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
     // dealt to the threads round-robin; a warp always holds one sub-part (NQUAD is a multiple of 32)
     uint32_t seen = 0;
 #pragma unroll 1
-    for (int task = tid; task < 4 * NQUAD; task += NT) {
+    for (int task = tid; task < FinParts<STAT>::N * NQUAD; task += NT) {
         const int part = task / NQUAD, q = task - part * NQUAD;
         const int64_t pl = t0l + 4 * q;
         const int64_t rem = A.end - pl;
