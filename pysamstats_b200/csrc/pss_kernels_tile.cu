@@ -1911,12 +1911,33 @@ k_tile_desc(const RInfo *__restrict__ ri, const int64_t *__restrict__ seq_off, i
     if (t >= ntiles) return;
     long long t0 = start + t * TT, t1 = t0 + TT;
     long long key0 = t0 - st->maxspan + 1;
-    int64_t lo = 0, hi = n;
-    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((long long)ri[mid].pos < key0) lo = mid + 1; else hi = mid; }
-    int64_t x = lo;
-    hi = n;
-    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((long long)ri[mid].pos < t1) lo = mid + 1; else hi = mid; }
-    int64_t y = lo;
+    // first index with pos >= key, searched outward from a guess (exponential steps, then bisection): with
+    // evenly spread reads that is a handful of probes instead of log2(n) dependent loads
+    auto lower = [&](long long key, int64_t guess) -> int64_t {
+        if (n <= 0) return 0;
+        if (guess < 0) guess = 0;
+        if (guess > n - 1) guess = n - 1;
+        int64_t lo, hi;                       // invariant at the end: pos[lo - 1] < key (or lo == 0), pos[hi] >= key (or hi == n)
+        if ((long long)ri[guess].pos < key) {
+            lo = guess + 1; hi = n;
+            for (int64_t step = 32, p = guess + step; ; step <<= 1, p += step) {
+                if (p >= n) break;
+                if ((long long)ri[p].pos < key) lo = p + 1; else { hi = p; break; }
+            }
+        } else {
+            hi = guess; lo = 0;
+            for (int64_t step = 32, p = guess - step; ; step <<= 1, p -= step) {
+                if (p < 0) break;
+                if ((long long)ri[p].pos < key) { lo = p + 1; break; } else hi = p;
+            }
+        }
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((long long)ri[mid].pos < key) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    const long long p_first = n > 0 ? ri[0].pos : 0, p_last = n > 0 ? ri[n - 1].pos : 0;
+    const double dens = p_last > p_first ? (double)(n - 1) / (double)(p_last - p_first) : 0.0;
+    const int64_t x = lower(key0, (int64_t)((double)(key0 - p_first) * dens));
+    const int64_t y = lower(t1, x + (int64_t)((double)(t1 - key0) * dens));
     TileDesc d;
     d.x = (int32_t)x; d.y = (int32_t)y; d.flags = 0; d.seq_lo = 0; d.seq_hi = 0; d.cig_lo = 0; d.cig_hi = 0;
     int m = (int)(y - x < TCH ? y - x : TCH);
