@@ -297,3 +297,34 @@ def test_native_row_packer_and_column_gather_equal_numpy():
     big = bamio.alloc_big((3, 12_000_000), np.int32)            # huge-page backed
     big[:] = 5
     assert big.shape == (3, 12_000_000) and int(big.sum()) == 5 * big.size
+
+
+def test_position_chunks_cover_every_overlapping_read(monkeypatch):
+    # pileup_tables cuts a contig into position pieces with zero-copy sub-batch views: every read overlapping a piece
+    # must be inside its view, pieces must tile [lo, hi), and the range must not be cut when max_depth could bite or
+    # base qualities are read
+    import ctypes as C
+    from pysamstats_b200 import synth
+    G = 300000
+    batch, _ = synth.make_interval_batch(0, G, G, block=100000, with_qual=True)
+    nb = synth.batch_to_numpy(batch)
+    b = bamio.ReadBatch()
+    for k in bamio.ReadBatch.__slots__:
+        setattr(b, k, nb.get(k))
+    b.tid = 0
+    b.names = None
+    monkeypatch.setenv('PSS_TABLE_CHUNK', '20000')
+    lo, hi = 1000, G - 500
+    pieces = list(opt._position_chunks(b, lo, hi, False, 8000))
+    assert len(pieces) > 10 and pieces[0][0] == lo and pieces[-1][1] == hi
+    assert all(p[1] == q[0] for p, q in zip(pieces, pieces[1:]))
+    addr0 = b.pos.ctypes.data
+    for c_lo, c_hi, rs in pieces:
+        i0 = (C.cast(rs.pos, C.c_void_p).value - addr0) // 4
+        i1 = i0 + rs.n_reads
+        want = np.flatnonzero((b.pos < c_hi) & (b.endpos > c_lo))
+        assert len(want) == 0 or (i0 <= want[0] and want[-1] < i1), (c_lo, c_hi)
+        assert rs.qual is None or C.cast(rs.qual, C.c_void_p).value is None      # no qualities requested
+    # qualities wanted, or max_depth within reach of the local read density: one piece
+    assert len(list(opt._position_chunks(b, lo, hi, True, 8000))) == 1
+    assert len(list(opt._position_chunks(b, lo, hi, False, 20))) == 1
