@@ -570,29 +570,49 @@ static int host_stat_wide(pss_ctx *ctx, const pss_reads *D, const pss_pileup_par
 // the caller repeats the statistic on the int32 pipeline.  A quarter / half of the bytes cross
 // PCIe, and the worker pool widens them into the caller's int32 columns while the next chunks
 // are computed and copied.  Three buffers rotate: compute k, copy k - 1, widen k - 2.
-static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_params *Pd, bool q, int32_t *out,
-                            int64_t ostride, uint8_t *rowmask, cudaStream_t s) {
+struct NarrowStat {           // one statistic of a host call on the narrow transport
+    pss_pileup_params Pd;     // with the device reference pointer
+    bool q;
+    int32_t *out;
+    uint8_t *rowmask;
+};
+
+// All the narrow statistics of a call share ONE pipeline: the position chunks of statistic i + 1 follow those of
+// statistic i through the three buffers without a drain in between (a drain costs the compute + copy of a first
+// chunk and the widening of a last one, per statistic and call).
+static int host_stats_narrow(pss_ctx *ctx, const pss_reads *D, const std::vector<NarrowStat> &stats, int64_t ostride,
+                             cudaStream_t s) {
     int rc;
-    const int nf = kPileupFields[Pd->stat];
-    const int64_t npos = Pd->end - Pd->start;
-    int64_t chunk = ((int64_t)(128ll << 20) / (2ll * nf)) / PSS_TTILE * PSS_TTILE;
-    if (const char *hc = getenv("PSS_HOST_CHUNK"))      // positions per chunk (tests: many chunks on small inputs)
-        if (atoll(hc) > 0) chunk = (atoll(hc) + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
-    if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
-    if (chunk < PSS_TTILE) chunk = PSS_TTILE;
-    const int64_t stride = chunk;                       // multiple of 512: rows 8-byte aligned
-    const size_t bytes16 = sizeof(uint16_t) * (size_t)nf * (size_t)stride;
+    if (stats.empty()) return PSS_OK;
+    struct Item { int st; int64_t cs, cn, stride; };
+    std::vector<Item> items;
+    size_t max_bytes16 = 0;
+    int64_t max_stride = 0;
+    for (size_t i = 0; i < stats.size(); ++i) {
+        const pss_pileup_params &Pd = stats[i].Pd;
+        const int nf = kPileupFields[Pd.stat];
+        const int64_t npos = Pd.end - Pd.start;
+        int64_t chunk = ((int64_t)(128ll << 20) / (2ll * nf)) / PSS_TTILE * PSS_TTILE;
+        if (const char *hc = getenv("PSS_HOST_CHUNK"))      // positions per chunk (tests: many chunks on small inputs)
+            if (atoll(hc) > 0) chunk = (atoll(hc) + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
+        if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
+        if (chunk < PSS_TTILE) chunk = PSS_TTILE;
+        for (int64_t cs = Pd.start; cs < Pd.end; cs += chunk)
+            items.push_back({(int)i, cs, (cs + chunk < Pd.end ? cs + chunk : Pd.end) - cs, chunk});   // stride = chunk: rows 8-byte aligned
+        max_bytes16 = std::max(max_bytes16, sizeof(uint16_t) * (size_t)nf * (size_t)chunk);
+        max_stride = std::max(max_stride, chunk);
+    }
     static const bool no_narrow8 = getenv("PSS_NO_NARROW8") != nullptr;
     if (!ctx->pool) ctx->pool = pss_pool_create(0);
-    CU(cudaStreamSynchronize(ctx->copy_stream));        // nothing of an earlier statistic is in flight
+    CU(cudaStreamSynchronize(ctx->copy_stream));        // nothing of an earlier call is in flight
     for (int b = 0; b < 3; ++b) {
-        if ((rc = ensure(ctx, ctx->nbuf[b], bytes16)) != PSS_OK) return rc;
-        if ((rc = ensure(ctx, ctx->nmask[b], (size_t)stride)) != PSS_OK) return rc;
-        if (ctx->hstage_bytes[b] < bytes16) {
+        if ((rc = ensure(ctx, ctx->nbuf[b], max_bytes16)) != PSS_OK) return rc;
+        if ((rc = ensure(ctx, ctx->nmask[b], (size_t)max_stride)) != PSS_OK) return rc;
+        if (ctx->hstage_bytes[b] < max_bytes16) {
             if (ctx->hstage[b]) cudaFreeHost(ctx->hstage[b]);
             ctx->hstage[b] = nullptr; ctx->hstage_bytes[b] = 0;
-            CU(cudaMallocHost(&ctx->hstage[b], bytes16));
-            ctx->hstage_bytes[b] = bytes16;
+            CU(cudaMallocHost(&ctx->hstage[b], max_bytes16));
+            ctx->hstage_bytes[b] = max_bytes16;
         }
         if (!ctx->nev_done[b]) {
             CU(cudaEventCreateWithFlags(&ctx->nev_done[b], cudaEventDisableTiming));
@@ -605,25 +625,28 @@ static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_p
     // clear the overflow flag of this batch's device state
     CU(cudaMemsetAsync(&((SmallState *)ctx->small.p)->overflow16, 0, sizeof(int32_t), s));
     size_t ticket[3] = {0, 0, 0};
-    int64_t cstart[3] = {0, 0, 0}, clen[3] = {0, 0, 0};
+    int held[3] = {-1, -1, -1};      // item in buffer b
     int esz[3] = {2, 2, 2};
     int cool = 0;          // chunks left that go straight to 16 bits after an 8-bit overflow
     pss_pool *pool = ctx->pool;
-    // compute chunk [cs, cs + cn) into device buffer b with `e`-byte elements and copy it to staging buffer b
-    auto produce = [&](int b, int64_t cs, int64_t cn, int e) -> int {
+    // compute item it into device buffer b with `e`-byte elements and copy it to staging buffer b
+    auto produce = [&](int b, int it, int e) -> int {
+        const Item &I = items[(size_t)it];
+        const NarrowStat &S = stats[(size_t)I.st];
+        const int nf = kPileupFields[S.Pd.stat];
         if (e == 1) CU(cudaMemsetAsync(dflag + b, 0, sizeof(int32_t), s));
-        int r = run_range(ctx, D, Pd, q, cs, cs + cn, (int32_t *)ctx->nbuf[b].p, stride, (uint8_t *)ctx->nmask[b].p, s,
+        int r = run_range(ctx, D, &S.Pd, S.q, I.cs, I.cs + I.cn, (int32_t *)ctx->nbuf[b].p, I.stride, (uint8_t *)ctx->nmask[b].p, s,
                           e == 1 ? 2 : 1, dflag + b);
         if (r != PSS_OK) return r;
-        const size_t bytes = (size_t)e * (size_t)nf * (size_t)stride;
+        const size_t bytes = (size_t)e * (size_t)nf * (size_t)I.stride;
         CU(cudaEventRecord(ctx->nev_done[b], s));
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->nev_done[b], 0));
         CU(cudaMemcpyAsync(ctx->hstage[b], ctx->nbuf[b].p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        CU(cudaMemcpyAsync(rowmask + (cs - Pd->start), ctx->nmask[b].p, (size_t)cn, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaMemcpyAsync(S.rowmask + (I.cs - S.Pd.start), ctx->nmask[b].p, (size_t)I.cn, cudaMemcpyDeviceToHost, ctx->copy_stream));
         if (e == 1) CU(cudaMemcpyAsync(ctx->hflag + b, dflag + b, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
         CU(cudaEventRecord(ctx->nev_copied[b], ctx->copy_stream));
-        ctx->d2h_bytes += (int64_t)(bytes + (size_t)cn);
-        cstart[b] = cs; clen[b] = cn; esz[b] = e;
+        ctx->d2h_bytes += (int64_t)(bytes + (size_t)I.cn);
+        held[b] = it; esz[b] = e;
         return PSS_OK;
     };
     // the D2H of buffer b has been enqueued: wait for it, redo the chunk with 16 bits if its counts
@@ -632,29 +655,30 @@ static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_p
         CU(cudaEventSynchronize(ctx->nev_copied[b]));
         if (esz[b] == 1 && ctx->hflag[b]) {
             cool = 8;
-            int r = produce(b, cstart[b], clen[b], 2);
+            int r = produce(b, held[b], 2);
             if (r != PSS_OK) return r;
             CU(cudaEventSynchronize(ctx->nev_copied[b]));
         }
+        const Item &I = items[(size_t)held[b]];
+        const NarrowStat &S = stats[(size_t)I.st];
+        const int nf = kPileupFields[S.Pd.stat];
         const uint8_t *src = (const uint8_t *)ctx->hstage[b];
-        const int64_t cs = cstart[b], cn = clen[b];
         const int e = esz[b];
         const int64_t piece = 1 << 20;
         size_t t = 0;
         for (int f = 0; f < nf; ++f)
-            for (int64_t o = 0; o < cn; o += piece) {
-                const uint8_t *sp = src + ((size_t)f * stride + o) * e;
-                int32_t *dp = out + (size_t)f * (size_t)ostride + (cs - Pd->start) + o;
-                size_t len = (size_t)((cn - o) < piece ? (cn - o) : piece);
+            for (int64_t o = 0; o < I.cn; o += piece) {
+                const uint8_t *sp = src + ((size_t)f * I.stride + o) * e;
+                int32_t *dp = S.out + (size_t)f * (size_t)ostride + (I.cs - S.Pd.start) + o;
+                size_t len = (size_t)((I.cn - o) < piece ? (I.cn - o) : piece);
                 if (e == 1) t = pss_pool_submit(pool, [sp, dp, len] { pss_widen_u8(sp, dp, len); });
                 else t = pss_pool_submit(pool, [sp, dp, len] { pss_widen_u16((const uint16_t *)sp, dp, len); });
             }
         ticket[b] = t;
         return PSS_OK;
     };
-    int k = 0;
-    for (int64_t cs = Pd->start; cs < Pd->end; cs += chunk, ++k) {
-        const int64_t ce = cs + chunk < Pd->end ? cs + chunk : Pd->end, cn = ce - cs;
+    const int n_items = (int)items.size();
+    for (int k = 0; k < n_items; ++k) {
         const int b = k % 3;
         if (k >= 3) {
             pss_pool_wait(pool, ticket[b]);                          // staging buffer b widened
@@ -663,10 +687,10 @@ static int host_stat_narrow(pss_ctx *ctx, const pss_reads *D, const pss_pileup_p
         int e = 1;
         if (no_narrow8) e = 2;
         else if (cool > 0) { e = 2; --cool; }
-        if ((rc = produce(b, cs, cn, e)) != PSS_OK) return rc;
+        if ((rc = produce(b, k, e)) != PSS_OK) return rc;
         if (k >= 1 && (rc = consume((k - 1) % 3)) != PSS_OK) return rc;   // widen the previous chunk meanwhile
     }
-    if (k >= 1 && (rc = consume((k - 1) % 3)) != PSS_OK) return rc;
+    if (n_items >= 1 && (rc = consume((n_items - 1) % 3)) != PSS_OK) return rc;
     for (int b = 0; b < 3; ++b) pss_pool_wait(pool, ticket[b]);
     // a tile that needed several passes (> 65535 reads) cannot be expressed in 16 bits
     int32_t ovf = 0;
@@ -686,18 +710,31 @@ static int host_multi_run(pss_ctx *ctx, const pss_reads *H, const pss_reads *D, 
                             s, (need_qual && H->n_reads > 0) ? H->qual_off[0] : 0)) != PSS_OK)
         return rc;
     int k = 0;     // running buffer slot of the int32 pipeline
+    static const bool no_narrow = getenv("PSS_NO_NARROW") != nullptr;
+    // the counting statistics of the tile kernel travel narrow, all of them through one pipeline
+    // (coverage_gc's gc column is written as int32 by k_gc, so it stays on the int32 pipeline)
+    std::vector<NarrowStat> narrow;
+    std::vector<char> is_narrow((size_t)n_stats, 0);
     for (int i = 0; i < n_stats; ++i) {
+        if (no_narrow || !tile_kernel_counting(P[i].stat) || P[i].stat == PSS_COVERAGE_GC ||
+            (P[i].flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS)))
+            continue;
+        NarrowStat ns;
+        ns.Pd = P[i];
+        ns.Pd.ref = (P[i].ref && P[i].ref_len > 0) ? ref_dev : nullptr;
+        ns.q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
+        ns.out = outs[i]; ns.rowmask = rowmasks[i];
+        narrow.push_back(ns);
+        is_narrow[(size_t)i] = 1;
+    }
+    rc = host_stats_narrow(ctx, D, narrow, ostride, s);
+    if (rc == PSS_ERETRY_WIDE) std::fill(is_narrow.begin(), is_narrow.end(), 0);      // > 65535 reads in a tile: int32 for all
+    else if (rc != PSS_OK) return rc;
+    for (int i = 0; i < n_stats; ++i) {
+        if (is_narrow[(size_t)i]) continue;
         pss_pileup_params Pd = P[i];
         Pd.ref = (P[i].ref && P[i].ref_len > 0) ? ref_dev : nullptr;
         const bool q = pss_pileup_needs_qual(P[i].stat, P[i].min_baseq);
-        static const bool no_narrow = getenv("PSS_NO_NARROW") != nullptr;
-        // (coverage_gc's gc column is written as int32 by k_gc, so it stays on the int32 pipeline)
-        const bool narrow = !no_narrow && tile_kernel_counting(P[i].stat) && P[i].stat != PSS_COVERAGE_GC &&
-                            !(P[i].flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
-        if (narrow) {
-            rc = host_stat_narrow(ctx, D, &Pd, q, outs[i], ostride, rowmasks[i], s);
-            if (rc != PSS_ERETRY_WIDE) { if (rc != PSS_OK) return rc; continue; }
-        }
         if ((rc = host_stat_wide(ctx, D, &Pd, q, outs[i], ostride, rowmasks[i], s, &k)) != PSS_OK) return rc;
     }
     CU(cudaStreamSynchronize(ctx->copy_stream));
