@@ -399,63 +399,120 @@ k_tile_ranges(const RInfo *__restrict__ ri, int64_t n, const SmallState *st, int
 // g/c (any case) over the ACTUAL window length, round-half-even.  Each CTA builds a
 // prefix sum of its reference span in shared memory.
 
-#define GC_BLK 1024
+#define GC_BLK 2048
 #define GC_REGION 8192
+#define GC_TAB 1024
 
+// per-byte "is g / c (either case)" flags of four reference bytes, gathered into a nibble
+__device__ __forceinline__ unsigned gc_nibble(unsigned w) {
+    unsigned y = ((w | 0x20202020u) & 0xFBFBFBFBu) ^ 0x63636363u;        // 'g' = 0x67, 'c' = 0x63: zero byte <=> g / c
+    unsigned z = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;   // bit 7 of every zero byte
+    return (((z >> 7) * 0x01020408u) >> 24);
+}
+
+// int(np.around(cnt * 100. / n)) in integers: the correctly rounded double quotient of two integers below 2^45
+// cannot land on a half unless the exact quotient is one (its distance from a half is >= 1 / 2n), and rounding
+// is monotone, so the double expression of gc_content and the exact rational agree.
+__device__ __forceinline__ int gc_percent(unsigned long long cnt, unsigned long long n) {
+    unsigned long long v = cnt * 100ull, q = v / n, r = v - q * n;
+    return (int)(q + ((2 * r > n) || (2 * r == n && (q & 1))));
+}
+__device__ __forceinline__ int gc_percent32(unsigned cnt, unsigned n) {
+    unsigned v = cnt * 100u, q = v / n, r = v - q * n;
+    return (int)(q + ((2 * r > n) || (2 * r == n && (q & 1))));
+}
+
+// A CTA turns its reference span into one 32-bit flag mask + one running count per 32 bytes (16-byte vector
+// loads); a window count is two of those lookups, the percentage a table lookup while the window is not
+// clipped by the contig ends (else an integer division); four positions per thread and 128-bit stores.
 __global__ void __launch_bounds__(256)
 k_gc(const uint8_t *__restrict__ ref, int64_t ref_start, int64_t ref_len, int64_t contig_len,
      int64_t start, int64_t end, int wsize, int woff, int32_t *__restrict__ out) {
-    __shared__ int pre[GC_REGION + 1];
+    __shared__ int s_pre[257];
+    __shared__ unsigned s_mask[257];
     __shared__ int s_red[33];
-    int64_t b0 = start + (int64_t)blockIdx.x * GC_BLK;
+    __shared__ uint8_t s_tab[GC_TAB + 1];
+    const int64_t b0 = start + (int64_t)blockIdx.x * GC_BLK;
     int64_t b1 = b0 + GC_BLK;
     if (b1 > end) b1 = end;
     int64_t rlo = b0 - woff, rhi = (b1 - 1) - woff + wsize;  // region of reference needed
+    const bool unclipped = rlo >= 0 && rhi <= contig_len && wsize > 0 && wsize <= GC_TAB;
     if (rlo < 0) rlo = 0;
     if (rhi > contig_len) rhi = contig_len;
-    int64_t rn = rhi - rlo;
-    const bool fast = rn <= GC_REGION;
-    if (fast && rn > 0) {
-        int per = (int)((rn + 255) / 256);
-        int64_t k0 = (int64_t)threadIdx.x * per, k1 = k0 + per;
-        if (k1 > rn) k1 = rn;
-        int c = 0;
-        for (int64_t k = k0; k < k1; ++k) {
-            int64_t ro = rlo + k - ref_start;
-            uint8_t ch = (ro >= 0 && ro < ref_len) ? (ref[ro] | 0x20) : 0;
-            c += (ch == 'g' || ch == 'c');
+    const int64_t rn = rhi - rlo;
+    // smem index i <-> address abase + i; the region starts at index shift
+    const long long raddr = (long long)(uintptr_t)ref, gaddr = raddr + (rlo - ref_start);
+    const long long abase = gaddr & ~15ll;
+    const int shift = (int)(gaddr - abase);
+    const bool fast = rn > 0 && shift + rn <= GC_REGION;
+    if (fast) {
+        const long long a = abase + 32ll * threadIdx.x;
+        unsigned m = 0;
+        if (a < gaddr + rn && a + 32 > gaddr) {
+            if (a >= raddr && a + 32 <= raddr + ref_len) {
+                const uint4 *vp = (const uint4 *)(uintptr_t)a;
+                uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1);
+                m = gc_nibble(v0.x) | gc_nibble(v0.y) << 4 | gc_nibble(v0.z) << 8 | gc_nibble(v0.w) << 12 |
+                    gc_nibble(v1.x) << 16 | gc_nibble(v1.y) << 20 | gc_nibble(v1.z) << 24 | gc_nibble(v1.w) << 28;
+            } else {
+                for (int j = 0; j < 32; ++j) {
+                    long long ad = a + j;
+                    if (ad >= raddr && ad < raddr + ref_len) {
+                        uint8_t ch = *(const uint8_t *)(uintptr_t)ad | 0x20;
+                        m |= (unsigned)(ch == 'g' || ch == 'c') << j;
+                    }
+                }
+            }
         }
         int total;
-        int run = block_excl_scan(c, s_red, &total);
-        for (int64_t k = k0; k < k1; ++k) {
-            pre[k] = run;
-            int64_t ro = rlo + k - ref_start;
-            uint8_t ch = (ro >= 0 && ro < ref_len) ? (ref[ro] | 0x20) : 0;
-            run += (ch == 'g' || ch == 'c');
-        }
-        if (k0 < rn && k1 == rn) pre[rn] = run;
+        int run = block_excl_scan(__popc(m), s_red, &total);
+        s_pre[threadIdx.x] = run;
+        s_mask[threadIdx.x] = m;
+        if (threadIdx.x == 0) { s_pre[256] = total; s_mask[256] = 0; }
+        if (unclipped)
+            for (int c = threadIdx.x; c <= wsize; c += 256) s_tab[c] = (uint8_t)gc_percent32((unsigned)c, (unsigned)wsize);
         __syncthreads();
     }
-    for (int64_t p = b0 + threadIdx.x; p < b1; p += 256) {
+    auto prefix = [&](int i) { return s_pre[i >> 5] + __popc(s_mask[i >> 5] & ((1u << (i & 31)) - 1u)); };
+    auto gc_at = [&](int64_t p) -> int {
         int64_t ws = p - woff, we = ws + wsize;
         if (ws < 0) ws = 0;
         if (we > contig_len) we = contig_len;
-        int gc;
-        if (we <= ws) gc = -1;
-        else {
-            int cnt;
-            if (fast) cnt = pre[we - rlo] - pre[ws - rlo];
-            else {
-                cnt = 0;
-                for (int64_t k = ws; k < we; ++k) {
-                    int64_t ro = k - ref_start;
-                    uint8_t ch = (ro >= 0 && ro < ref_len) ? (ref[ro] | 0x20) : 0;
-                    cnt += (ch == 'g' || ch == 'c');
-                }
-            }
-            gc = (int)rint((double)cnt * 100. / (double)(we - ws));
+        if (we <= ws) return -1;
+        if (fast) {
+            int cnt = prefix((int)(we - rlo) + shift) - prefix((int)(ws - rlo) + shift);
+            return gc_percent32((unsigned)cnt, (unsigned)(we - ws));
         }
-        out[p - start] = gc;
+        unsigned long long cnt = 0;
+        for (int64_t k = ws; k < we; ++k) {
+            int64_t ro = k - ref_start;
+            uint8_t ch = (ro >= 0 && ro < ref_len) ? (ref[ro] | 0x20) : 0;
+            cnt += (ch == 'g' || ch == 'c');
+        }
+        return gc_percent(cnt, (unsigned long long)(we - ws));
+    };
+    const int nb = (int)(b1 - b0);
+    int32_t *o = out + (b0 - start);
+    const bool vec = (((uintptr_t)o) & 15) == 0;
+    for (int q = threadIdx.x * 4; q < nb; q += 1024) {
+        if (vec && q + 4 <= nb) {
+            int4 g;
+            if (fast && unclipped) {
+                const int lo = (int)(b0 - woff - rlo) + shift + q;     // window start of position b0 + q
+                int c0 = prefix(lo + wsize) - prefix(lo);
+                // the window slides by one base per position
+                auto bit = [&](int i) { return (int)((s_mask[i >> 5] >> (i & 31)) & 1u); };
+                int c1 = c0 - bit(lo) + bit(lo + wsize);
+                int c2 = c1 - bit(lo + 1) + bit(lo + 1 + wsize);
+                int c3 = c2 - bit(lo + 2) + bit(lo + 2 + wsize);
+                g = make_int4(s_tab[c0], s_tab[c1], s_tab[c2], s_tab[c3]);
+            } else {
+                g = make_int4(gc_at(b0 + q), gc_at(b0 + q + 1), gc_at(b0 + q + 2), gc_at(b0 + q + 3));
+            }
+            __stcs((int4 *)(o + q), g);
+        } else {
+            for (int j = q; j < q + 4 && j < nb; ++j) o[j] = gc_at(b0 + j);
+        }
     }
 }
 

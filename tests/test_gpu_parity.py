@@ -88,6 +88,18 @@ def test_uppercase_fasta(stat, obam):
     assert_recarrays_equal(e, a, stat)
 
 
+@pytest.mark.parametrize('kw', [dict(window_size=1), dict(window_size=7, window_offset=0), dict(window_size=301, window_offset=300),
+                                dict(window_size=64, window_offset=200), dict(window_size=1500), dict(window_size=9001),
+                                dict(window_size=100000), dict(window_size=50, pad=True, chrom='Pf3D7_02_v3'),
+                                dict(window_size=300, chrom='Pf3D7_01_v3', start=1001, end=7003, pad=True),
+                                dict(window_size=1024, window_offset=1023, chrom='Pf3D7_03_v3', start=69000, pad=True)])
+def test_coverage_gc_windows(kw, obam, ofa):
+    # k_gc: table path (unclipped, window <= 1024), division path (clipped by the contig ends or a wider window),
+    # per-position path (the window does not fit the CTA's reference span); gc_content opt.pyx:1527-1539
+    assert_recarrays_equal(_oracle('coverage_gc', obam, ofa, 'test', **kw), _load('coverage_gc', 'test', **kw),
+                           'coverage_gc %r' % (kw,))
+
+
 @pytest.mark.parametrize('stat', ['coverage', 'coverage_ext_strand', 'variation_strand', 'baseq_strand', 'tlen_strand',
                                   'mapq_strand'])
 @pytest.mark.parametrize('max_depth', [8000, 100, 1, 1000000])
