@@ -245,6 +245,37 @@ int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats,
                           uint8_t *const *rowmasks);
 
 /*
+ * The same statistic delivered as packed RECORDS -- what load_* returns (util.load_stats,
+ * /root/reference/pysamstats/util.py:31-73: one structured-array record per emitted genome
+ * position, field order and packing of config.py:33-402).  The result chunks are packed from the
+ * pinned staging buffers straight into the caller's records by the worker threads, compacted to the
+ * rows the reference emits: a position gets a row iff htslib builds a column there (rowmask) or it
+ * lies in [pad_start, pad_end) (pad=True, opt.pyx:1936-1984).  field_off[j] < 0 leaves value field j
+ * out (fields=...); field_bytes[j] is 4 (int32) or 1 (low byte: coverage_gc's gc is u1).  chrom
+ * (chrom_bytes bytes, zero padded by the caller), pos (int32, position + pos_add) and ref (one byte,
+ * the upper-cased base of params->ref, 0 outside it: opt.pyx:1987-1994) are written when their offset
+ * is >= 0.  Rows are written from `rows` on, at most capacity_rows of them (PSS_EINVAL beyond);
+ * *n_rows receives their number, *n_negative how many emitted values of field `check_field` were
+ * negative (gc = -1 of an empty window, which the reference cannot store).  HOST pointers, synchronous.
+ */
+typedef struct pss_row_layout {
+    int32_t row_bytes;
+    int32_t n_fields;              /* must equal pss_pileup_nfields(params->stat) */
+    const int32_t *field_off;
+    const int32_t *field_bytes;
+    const uint8_t *chrom;
+    int32_t chrom_off, chrom_bytes;
+    int32_t pos_off, ref_off;
+    int32_t check_field, reserved;
+    int64_t pos_add;
+    int64_t pad_start, pad_end;
+} pss_row_layout;
+
+int pss_pileup_host_rows(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *params,
+                         const pss_row_layout *layout, void *rows, int64_t capacity_rows,
+                         int64_t *n_rows, int64_t *n_negative);
+
+/*
  * The same over a long position range, streamed: the library cuts [start, end) into chunks of
  * `chunk_positions` positions (0: 25 M), and uploads the reads of chunk k + 1 -- those with
  * pos in (chunk start - max_span, chunk end), a sub-range of the start-sorted batch -- while

@@ -50,6 +50,15 @@ class PssBinnedParams(C.Structure):
                 ('ref', C.c_void_p), ('ref_start', C.c_int64), ('ref_len', C.c_int64)]
 
 
+class PssRowLayout(C.Structure):
+    """struct pss_row_layout"""
+    _fields_ = [('row_bytes', C.c_int32), ('n_fields', C.c_int32), ('field_off', C.c_void_p),
+                ('field_bytes', C.c_void_p), ('chrom', C.c_void_p), ('chrom_off', C.c_int32),
+                ('chrom_bytes', C.c_int32), ('pos_off', C.c_int32), ('ref_off', C.c_int32),
+                ('check_field', C.c_int32), ('reserved', C.c_int32), ('pos_add', C.c_int64),
+                ('pad_start', C.c_int64), ('pad_end', C.c_int64)]
+
+
 # every symbol include/pss_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -73,6 +82,8 @@ SYMBOLS = {
     'pss_pileup_host': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssPileupParams), _P, _P]),
     'pss_pileup_host_multi': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.POINTER(PssPileupParams),
                                         C.POINTER(_P), C.POINTER(_P)]),
+    'pss_pileup_host_rows': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssPileupParams), C.POINTER(PssRowLayout), _P,
+                                       C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'pss_pileup_host_stream': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.POINTER(PssPileupParams),
                                          C.POINTER(_P), C.POINTER(_P), C.c_int64, C.c_int64]),
     'pss_admit': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P]),
@@ -216,6 +227,63 @@ class Context(object):
         oa = (_P * n)(*[_addr(o) for o in outs])
         ma = (_P * n)(*[_addr(m) for m in rowmasks])
         self.check(self.lib.pss_pileup_host_multi(self.h, C.byref(reads_struct), n, pa, oa, ma))
+
+    def row_layout(self, stat, dtype, value_fields, chrom=None, pos_add=0, pad=None, check_field=None):
+        """struct pss_row_layout for records of ``dtype`` (a numpy structured dtype): the value fields of the
+        statistic that ``dtype`` names (int32, or one byte), plus ``chrom`` / ``pos`` / ``ref`` when present.
+        None when a field's type is not one the row sink writes."""
+        names = dtype.names or ()
+        nf = len(value_fields)
+        off = np.full(nf, -1, dtype=np.int32)
+        nby = np.full(nf, 4, dtype=np.int32)
+        for j, f in enumerate(value_fields):
+            if f in names:
+                ft = dtype.fields[f][0]
+                if ft == np.dtype('<i4'):
+                    nby[j] = 4
+                elif ft == np.dtype('u1'):
+                    nby[j] = 1
+                else:
+                    return None
+                off[j] = dtype.fields[f][1]
+        L = PssRowLayout()
+        L.row_bytes, L.n_fields = dtype.itemsize, nf
+        L.chrom_off = L.pos_off = L.ref_off = L.check_field = -1
+        keep = [off, nby]
+        if 'chrom' in names:
+            ft = dtype.fields['chrom'][0]
+            if ft.kind != 'S':
+                return None
+            cb = np.zeros(1, dtype=ft)
+            cb[0] = chrom.encode('ascii')
+            if cb[0] != chrom.encode('ascii'):
+                return None
+            keep.append(cb)
+            L.chrom, L.chrom_off, L.chrom_bytes = cb.ctypes.data, dtype.fields['chrom'][1], ft.itemsize
+        if 'pos' in names:
+            if dtype.fields['pos'][0] != np.dtype('<i4'):
+                return None
+            L.pos_off = dtype.fields['pos'][1]
+        if 'ref' in names:
+            if dtype.fields['ref'][0] != np.dtype('S1'):
+                return None
+            L.ref_off = dtype.fields['ref'][1]
+        if check_field is not None and check_field in value_fields and check_field in names:
+            L.check_field = list(value_fields).index(check_field)
+        L.field_off, L.field_bytes = off.ctypes.data, nby.ctypes.data
+        L.pos_add = int(pos_add)
+        L.pad_start, L.pad_end = (int(pad[0]), int(pad[1])) if pad else (0, 0)
+        L._keep = keep
+        return L
+
+    def pileup_host_rows(self, reads_struct, params, layout, rows, row0, capacity):
+        """Records of one statistic into rows[row0:row0 + capacity] (a C-contiguous structured array);
+        returns (rows written, negative values seen in the layout's check_field)."""
+        n, neg = C.c_int64(0), C.c_int64(0)
+        self.check(self.lib.pss_pileup_host_rows(self.h, C.byref(reads_struct), C.byref(params), C.byref(layout),
+                                                 rows.ctypes.data + int(row0) * rows.dtype.itemsize, int(capacity),
+                                                 C.byref(n), C.byref(neg)))
+        return int(n.value), int(neg.value)
 
     def pileup_host_stream(self, reads_struct, params_list, outs, rowmasks, max_span, chunk_positions=0):
         n = len(params_list)

@@ -92,6 +92,24 @@ def alloc_big(shape, dtype):
     return np.frombuffer(mm, dtype=dtype, count=count).reshape(shape)
 
 
+def alloc_rows(n, dtype):
+    """Address space for up to ``n`` records that are filled from the front (``opt.pileup_rows``): an anonymous
+    mapping that is not charged before it is touched, so a sparse contig costs what its rows cost."""
+    import mmap
+    dtype = np.dtype(dtype)
+    nbytes = int(n) * dtype.itemsize
+    if nbytes < (32 << 20):
+        return np.empty(int(n), dtype=dtype)
+    flags = mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS | getattr(mmap, 'MAP_NORESERVE', 0)
+    mm = mmap.mmap(-1, (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20), flags=flags)
+    if hasattr(mmap, 'MADV_HUGEPAGE'):
+        try:
+            mm.madvise(mmap.MADV_HUGEPAGE)
+        except OSError:
+            pass
+    return np.frombuffer(mm, dtype=dtype, count=int(n))
+
+
 def take_cols(out, sel):
     """out[:, sel] for a C-contiguous int32 [n_cols][n] array, threaded (libpss_host) when it is large."""
     lib = host_lib()

@@ -570,11 +570,19 @@ static int host_stat_wide(pss_ctx *ctx, const pss_reads *D, const pss_pileup_par
 // the caller repeats the statistic on the int32 pipeline.  A quarter / half of the bytes cross
 // PCIe, and the worker pool widens them into the caller's int32 columns while the next chunks
 // are computed and copied.  Three buffers rotate: compute k, copy k - 1, widen k - 2.
+struct RowSink {              // records instead of columns (pss_pileup_host_rows)
+    pss_row_pack pack;
+    int64_t pad_start = 0, pad_end = 0;
+    int64_t capacity = 0, n_rows = 0;
+};
+
 struct NarrowStat {           // one statistic of a host call on the narrow transport
     pss_pileup_params Pd;     // with the device reference pointer
     bool q;
     int32_t *out;
     uint8_t *rowmask;
+    int esz_fixed = 0;        // 4: int32 columns through the same pipeline (statistics without narrow output; sink only)
+    RowSink *sink = nullptr;  // chunks are packed into records instead of widened into `out`
 };
 
 // All the narrow statistics of a call share ONE pipeline: the position chunks of statistic i + 1 follow those of
@@ -592,14 +600,15 @@ static int host_stats_narrow(pss_ctx *ctx, const pss_reads *D, const std::vector
         const pss_pileup_params &Pd = stats[i].Pd;
         const int nf = kPileupFields[Pd.stat];
         const int64_t npos = Pd.end - Pd.start;
-        int64_t chunk = ((int64_t)(128ll << 20) / (2ll * nf)) / PSS_TTILE * PSS_TTILE;
+        const int64_t bpe = stats[i].esz_fixed == 4 ? 4 : 2;
+        int64_t chunk = ((int64_t)(128ll << 20) / (bpe * nf)) / PSS_TTILE * PSS_TTILE;
         if (const char *hc = getenv("PSS_HOST_CHUNK"))      // positions per chunk (tests: many chunks on small inputs)
             if (atoll(hc) > 0) chunk = (atoll(hc) + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
         if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
         if (chunk < PSS_TTILE) chunk = PSS_TTILE;
         for (int64_t cs = Pd.start; cs < Pd.end; cs += chunk)
             items.push_back({(int)i, cs, (cs + chunk < Pd.end ? cs + chunk : Pd.end) - cs, chunk});   // stride = chunk: rows 8-byte aligned
-        max_bytes16 = std::max(max_bytes16, sizeof(uint16_t) * (size_t)nf * (size_t)chunk);
+        max_bytes16 = std::max(max_bytes16, (size_t)bpe * (size_t)nf * (size_t)chunk);
         max_stride = std::max(max_stride, chunk);
     }
     static const bool no_narrow8 = getenv("PSS_NO_NARROW8") != nullptr;
@@ -634,9 +643,10 @@ static int host_stats_narrow(pss_ctx *ctx, const pss_reads *D, const std::vector
         const Item &I = items[(size_t)it];
         const NarrowStat &S = stats[(size_t)I.st];
         const int nf = kPileupFields[S.Pd.stat];
+        if (S.esz_fixed) e = S.esz_fixed;
         if (e == 1) CU(cudaMemsetAsync(dflag + b, 0, sizeof(int32_t), s));
         int r = run_range(ctx, D, &S.Pd, S.q, I.cs, I.cs + I.cn, (int32_t *)ctx->nbuf[b].p, I.stride, (uint8_t *)ctx->nmask[b].p, s,
-                          e == 1 ? 2 : 1, dflag + b);
+                          e == 1 ? 2 : (e == 2 ? 1 : 0), e == 1 ? dflag + b : nullptr);
         if (r != PSS_OK) return r;
         const size_t bytes = (size_t)e * (size_t)nf * (size_t)I.stride;
         CU(cudaEventRecord(ctx->nev_done[b], s));
@@ -664,8 +674,31 @@ static int host_stats_narrow(pss_ctx *ctx, const pss_reads *D, const std::vector
         const int nf = kPileupFields[S.Pd.stat];
         const uint8_t *src = (const uint8_t *)ctx->hstage[b];
         const int e = esz[b];
-        const int64_t piece = 1 << 20;
         size_t t = 0;
+        if (S.sink) {
+            // rows: count the emitted positions of every piece (this thread, in position order), then the
+            // workers pack the pieces into the records from their first row on
+            RowSink *K = S.sink;
+            uint8_t *m = S.rowmask + (I.cs - S.Pd.start);
+            const int64_t pa = std::max(K->pad_start, I.cs), pz = std::min(K->pad_end, I.cs + I.cn);
+            if (pz > pa) memset(m + (pa - I.cs), 1, (size_t)(pz - pa));
+            const int64_t rpiece = 1 << 15;
+            for (int64_t o = 0; o < I.cn; o += rpiece) {
+                const int64_t len = std::min(rpiece, I.cn - o);
+                const int64_t cnt = pss_count_rows(m + o, len);
+                if (cnt == 0) continue;
+                if (K->n_rows + cnt > K->capacity) return fail(ctx, PSS_EINVAL, "rows: more than capacity_rows (%lld) rows", (long long)K->capacity);
+                const int64_t row0 = K->n_rows;
+                K->n_rows += cnt;
+                const uint8_t *sp = src + (size_t)o * e, *mp = m + o;
+                const int64_t stride = I.stride, p0 = I.cs + o;
+                pss_row_pack *pk = &K->pack;
+                t = pss_pool_submit(pool, [pk, sp, stride, e, mp, p0, len, row0] { pss_pack_piece(pk, sp, stride, e, mp, p0, len, row0); });
+            }
+            ticket[b] = t;
+            return PSS_OK;
+        }
+        const int64_t piece = 1 << 20;
         for (int f = 0; f < nf; ++f)
             for (int64_t o = 0; o < I.cn; o += piece) {
                 const uint8_t *sp = src + ((size_t)f * I.stride + o) * e;
@@ -791,6 +824,98 @@ extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32
         rc = pss_synchronize(ctx, s);
     }
     return rc;
+}
+
+// ---------------------------------------------------------------------- pileup rows (host)
+
+// One statistic as packed records: the narrow pipeline with a row sink; statistics without narrow output (the
+// quality kinds, tlen, coverage_gc, the generic kernel) and batches with a > 65535-read tile go through the
+// same three buffers as int32 columns.
+static int host_rows_run(pss_ctx *ctx, const pss_reads *H, const pss_reads *D, const pss_pileup_params *P,
+                         const uint8_t *ref_dev, bool need_qual, RowSink *K, uint8_t *mask, cudaStream_t s) {
+    int rc;
+    if ((rc = prepare_batch(ctx, D, P->stepper, P->max_depth, P->min_mapq, P->no_dup, need_qual, nullptr, nullptr, s,
+                            (need_qual && H->n_reads > 0) ? H->qual_off[0] : 0)) != PSS_OK)
+        return rc;
+    static const bool no_narrow = getenv("PSS_NO_NARROW") != nullptr;
+    NarrowStat ns;
+    ns.Pd = *P;
+    ns.Pd.ref = (P->ref && P->ref_len > 0) ? ref_dev : nullptr;
+    ns.q = need_qual;
+    ns.out = nullptr; ns.rowmask = mask; ns.sink = K;
+    const bool narrow = !no_narrow && tile_kernel_counting(P->stat) && P->stat != PSS_COVERAGE_GC &&
+                        !(P->flags & (PSS_FLAG_GENERIC_KERNEL | PSS_FLAG_LONG_READS));
+    ns.esz_fixed = narrow ? 0 : 4;
+    for (;;) {
+        K->n_rows = 0;
+        K->pack.n_negative = 0;
+        rc = host_stats_narrow(ctx, D, std::vector<NarrowStat>(1, ns), 0, s);
+        if (rc == PSS_ERETRY_WIDE && ns.esz_fixed == 0) { ns.esz_fixed = 4; continue; }
+        break;
+    }
+    // no worker still reads the staging buffers / the mask when this returns, whatever happened
+    if (ctx->pool) pss_pool_wait(ctx->pool, pss_pool_submit(ctx->pool, [] {}));
+    if (rc != PSS_OK) return rc;
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return PSS_OK;
+}
+
+extern "C" int pss_pileup_host_rows(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_params *P, const pss_row_layout *L,
+                                    void *rows, int64_t capacity_rows, int64_t *n_rows, int64_t *n_negative) {
+    if (!ctx) return PSS_EINVAL;
+    if (!P || !L || !n_rows) return fail(ctx, PSS_EINVAL, "params / layout / n_rows is NULL");
+    int rc;
+    *n_rows = 0;
+    if (n_negative) *n_negative = 0;
+    if ((rc = check_params(ctx, P)) != PSS_OK) return rc;
+    const int nf = kPileupFields[P->stat];
+    if (L->n_fields != nf || nf > 96) return fail(ctx, PSS_EINVAL, "layout: n_fields %d, the statistic has %d", L->n_fields, nf);
+    if (L->row_bytes < 1 || !L->field_off || !L->field_bytes || capacity_rows < 0 || (capacity_rows > 0 && !rows))
+        return fail(ctx, PSS_EINVAL, "layout: bad row_bytes / field arrays / rows");
+    RowSink K;
+    pss_row_pack &pk = K.pack;
+    pk.rows = (uint8_t *)rows; pk.row_bytes = L->row_bytes;
+    for (int j = 0; j < nf; ++j) {
+        if (L->field_off[j] < 0) continue;
+        const int fb = L->field_bytes[j];
+        if ((fb != 4 && fb != 1) || L->field_off[j] + fb > L->row_bytes) return fail(ctx, PSS_EINVAL, "layout: bad field %d", j);
+        pk.f_idx[pk.n_want] = j; pk.f_off[pk.n_want] = L->field_off[j]; pk.f_bytes[pk.n_want] = fb;
+        ++pk.n_want;
+    }
+    if (L->chrom_off >= 0 && (!L->chrom || L->chrom_bytes < 0 || L->chrom_off + L->chrom_bytes > L->row_bytes))
+        return fail(ctx, PSS_EINVAL, "layout: bad chrom");
+    if ((L->pos_off >= 0 && L->pos_off + 4 > L->row_bytes) || (L->ref_off >= 0 && L->ref_off + 1 > L->row_bytes) || L->check_field >= nf)
+        return fail(ctx, PSS_EINVAL, "layout: bad pos / ref offset or check_field");
+    pk.chrom = L->chrom; pk.chrom_off = L->chrom_off; pk.chrom_bytes = L->chrom_bytes;
+    pk.pos_off = L->pos_off; pk.ref_off = L->ref_off; pk.check_field = L->check_field; pk.pos_add = L->pos_add;
+    pk.ref = P->ref; pk.ref_start = P->ref_start; pk.ref_len = P->ref ? P->ref_len : 0;
+    K.pad_start = L->pad_start; K.pad_end = L->pad_end; K.capacity = capacity_rows;
+    const bool need_qual = pss_pileup_needs_qual(P->stat, P->min_baseq);
+    const bool need_seq = need_qual || stat_reads_seq(P->stat);
+    if ((rc = check_reads(ctx, reads, need_qual)) != PSS_OK) return rc;
+    const int64_t npos = P->end - P->start;
+    if (npos <= 0) return PSS_OK;
+    CU(cudaSetDevice(ctx->device));
+    ctx->prepared = false;
+    cudaStream_t s = nullptr;
+    pss_reads D;
+    if ((rc = upload_reads(ctx, reads, &D, need_seq, need_qual, s)) != PSS_OK) return rc;
+    const uint8_t *ref_dev = nullptr;
+    if (P->ref && P->ref_len > 0)
+        if ((rc = to_device(ctx, ctx->hb[13], P->ref, (size_t)P->ref_len, &ref_dev, s)) != PSS_OK) return rc;
+    std::vector<uint8_t> mask((size_t)npos);
+    if ((rc = host_rows_run(ctx, reads, &D, P, ref_dev, need_qual, &K, mask.data(), s)) != PSS_OK) return rc;
+    rc = pss_synchronize(ctx, s);
+    if (rc == PSS_ETOOLONG && !(P->flags & PSS_FLAG_LONG_READS)) {     // long reads: the per-position kernel (see pss_pileup_host_multi)
+        pss_pileup_params Pl = *P;
+        Pl.flags |= PSS_FLAG_LONG_READS;
+        if ((rc = host_rows_run(ctx, reads, &D, &Pl, ref_dev, need_qual, &K, mask.data(), s)) != PSS_OK) return rc;
+        rc = pss_synchronize(ctx, s);
+    }
+    if (rc != PSS_OK) return rc;
+    *n_rows = K.n_rows;
+    if (n_negative) *n_negative = K.pack.n_negative;
+    return PSS_OK;
 }
 
 // Whole-range streaming.  The range is cut into position chunks; chunk k + 1's reads (and reference slice)

@@ -147,3 +147,65 @@ void pss_widen_u16(const uint16_t *src, int32_t *dst, size_t n) {
     if (avx2) { widen_avx2(src, dst, n); return; }
     for (size_t i = 0; i < n; ++i) dst[i] = src[i];
 }
+
+// ------------------------------------------------------------------------------ row sink
+
+int64_t pss_count_rows(const uint8_t *mask, int64_t n) {
+    int64_t c = 0;
+    for (int64_t i = 0; i < n; ++i) c += mask[i] != 0;
+    return c;
+}
+
+template <class T>
+static inline void pack_field(const T *col, const int32_t *sel, int m, uint8_t *o, int32_t row_bytes, int fb) {
+    if (fb == 4) {
+        for (int r = 0; r < m; ++r, o += row_bytes) { int32_t v = (int32_t)col[sel[r]]; memcpy(o, &v, 4); }
+    } else {
+        for (int r = 0; r < m; ++r, o += row_bytes) *o = (uint8_t)col[sel[r]];
+    }
+}
+
+void pss_pack_piece(pss_row_pack *K, const uint8_t *src, int64_t stride, int esz, const uint8_t *mask, int64_t p0,
+                    int64_t len, int64_t row0) {
+    const int BLK = 64;               // 64 records of ~250 bytes stay in L1 while the columns stream through
+    int32_t sel[BLK + 1];
+    const int32_t rb = K->row_bytes;
+    int64_t i = 0, row = row0, neg = 0;
+    while (i < len) {
+        int m = 0;
+        while (i < len && m < BLK) { sel[m] = (int32_t)i; m += mask[i] != 0; ++i; }
+        if (m == 0) break;
+        uint8_t *out = K->rows + (size_t)row * (size_t)rb;
+        for (int w = 0; w < K->n_want; ++w) {
+            const uint8_t *col = src + (size_t)K->f_idx[w] * (size_t)stride * (size_t)esz;
+            uint8_t *o = out + K->f_off[w];
+            if (esz == 1) pack_field((const uint8_t *)col, sel, m, o, rb, K->f_bytes[w]);
+            else if (esz == 2) pack_field((const uint16_t *)col, sel, m, o, rb, K->f_bytes[w]);
+            else {
+                const int32_t *c4 = (const int32_t *)col;
+                if (K->f_idx[w] == K->check_field)
+                    for (int r = 0; r < m; ++r) neg += c4[sel[r]] < 0;
+                pack_field(c4, sel, m, o, rb, K->f_bytes[w]);
+            }
+        }
+        if (K->chrom_off >= 0) {
+            uint8_t *o = out + K->chrom_off;
+            for (int r = 0; r < m; ++r, o += rb) memcpy(o, K->chrom, (size_t)K->chrom_bytes);
+        }
+        if (K->pos_off >= 0) {
+            uint8_t *o = out + K->pos_off;
+            for (int r = 0; r < m; ++r, o += rb) { int32_t v = (int32_t)(p0 + sel[r] + K->pos_add); memcpy(o, &v, 4); }
+        }
+        if (K->ref_off >= 0) {
+            uint8_t *o = out + K->ref_off;
+            for (int r = 0; r < m; ++r, o += rb) {
+                int64_t ro = p0 + sel[r] - K->ref_start;
+                uint8_t c = (ro >= 0 && ro < K->ref_len) ? K->ref[ro] : 0;
+                if (c >= 'a' && c <= 'z') c -= 32;
+                *o = c;
+            }
+        }
+        row += m;
+    }
+    if (neg) __atomic_fetch_add(&K->n_negative, neg, __ATOMIC_RELAXED);
+}

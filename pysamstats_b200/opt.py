@@ -123,23 +123,17 @@ def _ref_column(refseq, pos):
 
 # ------------------------------------------------------------------------ pileup tables
 
-def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start=None, end=None,
-                  one_based=False, truncate=False, stepper='all', max_depth=8000, min_mapq=0, min_baseq=0,
-                  no_del=False, no_dup=False):
-    """Yield ``(chrom, pos, ref, fields)`` per contig: ``pos`` int64 (already one-based if
-    asked), ``ref`` an ``S1`` column or None, ``fields`` a dict name -> int32 column.
-
-    Row selection follows ``iter_pileup_default`` / ``iter_pileup_padded_chrom``
-    (``opt.pyx:1846-1863``, ``:1936-1984``): a row for every column htslib builds, plus -- with
-    ``pad`` -- every position of ``[start, end)``; with ``truncate`` only ``[start, end)``.
-    """
+def _pileup_plan(stat, alignmentfile, fafile, pad, chrom, start, end, one_based, truncate, stepper, max_depth,
+                 min_mapq, min_baseq, no_del, no_dup):
+    """Per contig of the request: (contig, s, e, lo, hi, read batch, reference bytes, engine keyword arguments,
+    need_qual) -- [s, e) the normalised region, [lo, hi) the positions that can get a row (row selection of
+    ``iter_pileup_default`` / ``iter_pileup_padded_chrom``, ``opt.pyx:1846-1863``, ``:1936-1984``)."""
     if stepper not in _cabi.STEPPERS:
         raise ValueError('unknown stepper: %r' % (stepper,))     # pysam raises ValueError too
     name = stat.name
     bam = bamio.open_bam(alignmentfile)
     fa = bamio.open_fasta(fafile)
     ctx = _cabi.get_context()
-    names = config.value_fields(name)
     need_qual = bool(ctx.lib.pss_pileup_needs_qual(_cabi.PILEUP_STATS.index(name), int(min_baseq)))
     needs_ref = bool(ctx.lib.pss_pileup_needs_ref(_cabi.PILEUP_STATS.index(name)))
     if chrom is not None:
@@ -163,13 +157,31 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
                 lo, hi = min(lo, s), max(hi, e)
         else:
             lo, hi = s, e
-        npos = hi - lo
-        if npos <= 0:
+        if hi - lo <= 0:
             continue
         refseq = fa.contig(c) if (fa is not None and needs_ref) else np.zeros(0, np.uint8)
         pkw = dict(stepper=stepper, max_depth=max_depth, min_mapq=min_mapq, min_baseq=min_baseq, no_del=no_del,
                    no_dup=no_dup, window_size=stat.window_size, window_offset=stat.window_offset,
                    ref=refseq if len(refseq) else None, ref_start=0, ref_len=len(refseq), contig_len=len(refseq))
+        yield c, s, e, lo, hi, batch, refseq, pkw, need_qual
+
+
+def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start=None, end=None,
+                  one_based=False, truncate=False, stepper='all', max_depth=8000, min_mapq=0, min_baseq=0,
+                  no_del=False, no_dup=False):
+    """Yield ``(chrom, pos, ref, fields)`` per contig: ``pos`` int64 (already one-based if
+    asked), ``ref`` an ``S1`` column or None, ``fields`` a dict name -> int32 column.
+
+    Row selection follows ``iter_pileup_default`` / ``iter_pileup_padded_chrom``
+    (``opt.pyx:1846-1863``, ``:1936-1984``): a row for every column htslib builds, plus -- with
+    ``pad`` -- every position of ``[start, end)``; with ``truncate`` only ``[start, end)``.
+    """
+    name = stat.name
+    names = config.value_fields(name)
+    for c, s, e, lo, hi, batch, refseq, pkw, need_qual in _pileup_plan(
+            stat, alignmentfile, fafile, pad, chrom, start, end, one_based, truncate, stepper, max_depth, min_mapq,
+            min_baseq, no_del, no_dup):
+        ctx = _cabi.get_context()
 
         def run_piece(piece, device):
             """One position piece on one GPU -> (pos, ref column, fields) or None when it has no rows."""
@@ -206,6 +218,54 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
         for res in _run_pieces(run_piece, _position_chunks(batch, lo, hi, need_qual, max_depth), ctx.device):
             if res is not None:
                 yield (c,) + res
+
+
+def pileup_rows(stat, dtype, alignmentfile, fafile=None, pad=False, chrom=None, start=None, end=None,
+                one_based=False, truncate=False, stepper='all', max_depth=8000, min_mapq=0, min_baseq=0,
+                no_del=False, no_dup=False):
+    """What ``load_*`` needs, without the column tables in between: a list of record arrays of ``dtype`` (one per
+    contig, in order), packed by the engine's host pipeline straight from its result chunks
+    (``pss_pileup_host_rows``) -- same rows and values as ``pileup_tables``.  None when the request has to take
+    the column path (a field type the row sink does not write, several GPUs, no address space for the records).
+    """
+    name = stat.name
+    names = config.value_fields(name)
+    ctx = _cabi.get_context()
+    if len(_devices(ctx.device)) > 1:
+        return None
+    if ctx.row_layout(name, dtype, names, chrom='') is None:
+        return None
+    parts = []
+    for c, s, e, lo, hi, batch, refseq, pkw, need_qual in _pileup_plan(
+            stat, alignmentfile, fafile, pad, chrom, start, end, one_based, truncate, stepper, max_depth, min_mapq,
+            min_baseq, no_del, no_dup):
+        layout = ctx.row_layout(name, dtype, names, chrom=c, pos_add=1 if one_based else 0,
+                                pad=(s, e) if pad else None, check_field='gc')
+        if layout is None:
+            return None
+        cap = hi - lo
+        try:
+            buf = bamio.alloc_rows(cap, dtype)
+        except (MemoryError, OSError, ValueError):
+            return None
+        n = 0
+        for c_lo, c_hi, reads in _position_chunks(batch, lo, hi, need_qual, max_depth):
+            params = ctx.pileup_params(name, start=c_lo, end=c_hi, **pkw)
+            m, neg = ctx.pileup_host_rows(reads, params, layout, buf, n, cap - n)
+            if neg:
+                # the reference stores gc = -1 for an empty window into a u1 column, which numpy
+                # refuses (SURVEY.md A.5)
+                raise OverflowError('Python integer -1 out of bounds for uint8')
+            n += m
+        if n == 0:
+            continue
+        if n * 2 < cap and n * dtype.itemsize < (1 << 30):
+            part = np.empty(n, dtype=dtype)          # sparse contig: do not keep the position-sized mapping alive
+            part[...] = buf[:n]
+        else:
+            part = buf[:n]
+        parts.append(part)
+    return parts
 
 
 def _devices(default):

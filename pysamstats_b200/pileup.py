@@ -94,6 +94,11 @@ def _pileup_tables(type, fafile=None, window_size=300, window_offset=None, **kwa
     return opt.pileup_tables(stat, fafile=fafile, **kwargs)
 
 
+def _pileup_rows(type, dtype, fafile=None, window_size=300, window_offset=None, **kwargs):
+    stat = _make_stat(type, fafile, window_size, window_offset)
+    return opt.pileup_rows(stat, dtype, fafile=fafile, **kwargs)
+
+
 # noinspection PyShadowingBuiltins
 def load_pileup(type, alignmentfile, fafile=None, chrom=None, start=None, end=None, one_based=False,
                 truncate=False, stepper="all", pad=False, max_depth=8000, window_size=300,
@@ -114,7 +119,8 @@ def load_pileup(type, alignmentfile, fafile=None, chrom=None, start=None, end=No
         default_dtype = getattr(config, 'dtype_' + type)
     except (AttributeError, TypeError):
         raise ValueError('unsupported statistics type: %r' % (type,))
-    return util.load_stats(functools.partial(_pileup_tables, type), user_dtype=dtype,
+    return util.load_stats(functools.partial(_pileup_tables, type), rowsfun=functools.partial(_pileup_rows, type),
+                           user_dtype=dtype,
                            default_dtype=default_dtype, user_fields=fields, alignmentfile=alignmentfile,
                            fafile=fafile, chrom=chrom, start=start, end=end, one_based=one_based,
                            truncate=truncate, stepper=stepper, pad=pad, max_depth=max_depth,

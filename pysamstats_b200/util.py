@@ -7,6 +7,7 @@ contig name of the file, user dtype overrides, optional field subset (a single f
 gives a plain ndarray, unknown fields raise ``ValueError``).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -67,9 +68,10 @@ def determine_max_seqid(alignmentfile):
     return max(len(x) for x in bamio.open_bam(alignmentfile).references)
 
 
-def load_stats(tablefun, default_dtype, user_dtype, user_fields, **kwargs):
+def load_stats(tablefun, default_dtype, user_dtype, user_fields, rowsfun=None, **kwargs):
     """Run ``tablefun(**kwargs)`` (a generator of per-contig column tables, see
-    ``opt.pileup_tables``) and assemble the structured array ``load_*`` returns."""
+    ``opt.pileup_tables``) and assemble the structured array ``load_*`` returns.  With ``rowsfun``
+    (``opt.pileup_rows``) the engine packs the records itself whenever the record type allows it."""
     default_fields = [t[0] for t in default_dtype]
     if user_fields is None:
         fields = default_fields
@@ -84,6 +86,11 @@ def load_stats(tablefun, default_dtype, user_dtype, user_fields, **kwargs):
     single = len(fields) == 1
     dt = np.dtype(dtype[fields[0]] if single else [(f, dtype[f]) for f in fields])
 
+    if rowsfun is not None and not single and os.environ.get('PSS_NO_ROWS') is None:
+        recs = rowsfun(dt, **kwargs)
+        if recs is not None:
+            a = recs[0] if len(recs) == 1 else (np.concatenate(recs) if recs else np.zeros(0, dtype=dt))
+            return a.view(np.recarray)
     parts = list(tablefun(**kwargs))
     n = sum(len(p[1]) for p in parts)
     a = np.zeros(n, dtype=dt) if single or bamio.host_lib() is None else bamio.alloc_big(n, dt)

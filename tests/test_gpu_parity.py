@@ -309,3 +309,42 @@ def test_pieces_across_gpus(monkeypatch):
     monkeypatch.setenv('PSS_GPUS', 'all')
     for (stat, kw), e in zip(cases, expect):
         assert_recarrays_equal(e, _load(stat, 'test', **kw), '%s %r on %d GPUs' % (stat, kw, torch.cuda.device_count()))
+
+
+# ---- load_*: records packed by the engine (pss_pileup_host_rows) vs the column tables --------------
+
+@pytest.mark.parametrize('stat', ['coverage', 'variation_strand', 'baseq_ext', 'tlen_strand', 'mapq', 'coverage_gc'])
+def test_rows_path_equals_column_path(stat, monkeypatch):
+    from pysamstats_b200 import opt
+    calls = []
+    real = opt.pileup_rows
+    monkeypatch.setattr(opt, 'pileup_rows', lambda *a, **k: calls.append(1) or real(*a, **k))
+    cases = [dict(), dict(chrom='Pf3D7_01_v3', start=1000, end=20000, pad=True),
+             dict(chrom='Pf3D7_02_v3', start=500, end=3000, truncate=True, one_based=True),
+             dict(chrom='Pf3D7_03_v3', pad=True, min_mapq=20, no_dup=True),
+             dict(fields=['pos', 'reads_all', 'chrom']), dict(chrom='Pf3D7_01_v3', start=60000, end=70000)]
+    for chunk in (None, '1024'):
+        for kw in cases:
+            if chunk:
+                monkeypatch.setenv('PSS_HOST_CHUNK', chunk)
+            else:
+                monkeypatch.delenv('PSS_HOST_CHUNK', raising=False)
+            monkeypatch.delenv('PSS_NO_ROWS', raising=False)
+            n0 = len(calls)
+            a = _load(stat, 'test', **kw)
+            assert len(calls) == n0 + 1                       # the rows path ran ...
+            monkeypatch.setenv('PSS_NO_ROWS', '1')
+            b = _load(stat, 'test', **kw)
+            assert len(calls) == n0 + 1                       # ... and the column path did not use it
+            assert a.dtype == b.dtype and a.shape == b.shape, (stat, kw)
+            assert a.tobytes() == b.tobytes(), (stat, kw, chunk)
+
+
+def test_rows_path_declines_what_it_cannot_write():
+    # user dtype overrides and single fields take the numpy path, with the reference's typing rules
+    a = pysamstats.load_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=0, end=2000, dtype={'reads_all': 'i8'})
+    assert a.dtype['reads_all'] == np.dtype('i8')
+    b = pysamstats.load_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=0, end=2000)
+    assert np.array_equal(a['reads_all'], b['reads_all']) and np.array_equal(a['pos'], b['pos'])
+    c = pysamstats.load_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=0, end=2000, fields='reads_all')
+    assert c.dtype == np.dtype('i4') and np.array_equal(c, b['reads_all'])
