@@ -198,11 +198,23 @@ class ReadBatch(object):
     ``struct pss_reads``)."""
 
     __slots__ = ('tid', 'pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'cigar', 'seq_off',
-                 'seq4', 'qual_off', 'qual', 'name_prev', 'endpos', 'names')
+                 'seq4', 'qual_off', 'qual', '_name_prev', 'endpos', 'names')
 
     @property
     def n_reads(self):
         return len(self.pos)
+
+    @property
+    def name_prev(self):
+        """Index of the previous record of the same QNAME (mate-overlap rewrite); hashed on first use -- only
+        requests that read base qualities need it."""
+        if getattr(self, '_name_prev', None) is None:
+            self._name_prev = _name_prev(self.names)
+        return self._name_prev
+
+    @name_prev.setter
+    def name_prev(self, v):
+        self._name_prev = v
 
     def subset(self, idx):
         """Records idx (increasing) as a new contiguous batch."""
@@ -215,7 +227,7 @@ class ReadBatch(object):
             d, no = _ragged_gather(getattr(self, data), o[:-1][idx], (o[1:] - o[:-1])[idx])
             setattr(b, data, d)
             setattr(b, off, no)
-        b.name_prev = _name_prev(b.names)
+        b.name_prev = None
         return b
 
     def padded(self):
@@ -429,8 +441,6 @@ class BamFile(object):
             idx = np.flatnonzero(self._tid == tid)
             if len(idx) == len(self._tid):        # single-contig file: no gather needed
                 b = self._all
-                if b.name_prev is None:
-                    b.name_prev = _name_prev(b.names)
             else:
                 b = self._all.subset(idx)
             b.tid = tid

@@ -101,7 +101,7 @@ def normalise_coords(alignmentfile, chrom, start, end, one_based):
 
 def _reads_struct(batch, need_qual):
     batch.padded()
-    d = {k: getattr(batch, k) for k in _cabi.READ_FIELDS}
+    d = {k: getattr(batch, k) for k in _cabi.READ_FIELDS if need_qual or k != 'name_prev'}
     d['tid'] = batch.tid
     d['n_reads'] = batch.n_reads
     if not need_qual:
