@@ -198,7 +198,14 @@ class ReadBatch(object):
     ``struct pss_reads``)."""
 
     __slots__ = ('tid', 'pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'cigar', 'seq_off',
-                 'seq4', 'qual_off', 'qual', '_name_prev', 'endpos', 'names')
+                 'seq4', 'qual_off', 'qual', '_name_prev', 'endpos', 'names', '_cache')
+
+    @property
+    def cache(self):
+        """Derived facts about the batch that several calls share (``opt._position_chunks``)."""
+        if getattr(self, '_cache', None) is None:
+            self._cache = {}
+        return self._cache
 
     @property
     def n_reads(self):

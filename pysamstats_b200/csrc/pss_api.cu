@@ -602,6 +602,9 @@ static int host_stats_narrow(pss_ctx *ctx, const pss_reads *D, const std::vector
         const int64_t npos = Pd.end - Pd.start;
         const int64_t bpe = stats[i].esz_fixed == 4 ? 4 : 2;
         int64_t chunk = ((int64_t)(128ll << 20) / (bpe * nf)) / PSS_TTILE * PSS_TTILE;
+        // a short range still gets ~8 chunks (>= 1 Mi positions each) so that compute, copy and host work overlap
+        const int64_t eighth = std::max<int64_t>(1 << 20, ((npos + 7) / 8 + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE);
+        if (chunk > eighth) chunk = eighth;
         if (const char *hc = getenv("PSS_HOST_CHUNK"))      // positions per chunk (tests: many chunks on small inputs)
             if (atoll(hc) > 0) chunk = (atoll(hc) + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;
         if (chunk > npos) chunk = (npos + PSS_TTILE - 1) / PSS_TTILE * PSS_TTILE;

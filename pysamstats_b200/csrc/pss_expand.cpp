@@ -165,18 +165,103 @@ static inline void pack_field(const T *col, const int32_t *sel, int m, uint8_t *
     }
 }
 
+// 16 positions x 16 one-byte fields -> 16 records: the byte columns are transposed in registers (four rounds of
+// unpacks) and every record receives its 16 fields as one widened 64-byte run.  col(f) = column f at the first
+// position; `nst` leading int32 of the run are stored (16, or 8 for an eight-field statistic).
+__attribute__((target("avx2"))) static inline void pack16x16_u8(const uint8_t *c0, size_t col_stride, int ncols, uint8_t *out,
+                                                                 int32_t row_bytes) {
+    __m128i a[16], t[16];
+    for (int f = 0; f < 16; ++f)
+        a[f] = f < ncols ? _mm_loadu_si128(reinterpret_cast<const __m128i *>(c0 + (size_t)f * col_stride)) : _mm_setzero_si128();
+    for (int k = 0; k < 8; ++k) {                 // bytes of field pairs
+        t[2 * k] = _mm_unpacklo_epi8(a[2 * k], a[2 * k + 1]);
+        t[2 * k + 1] = _mm_unpackhi_epi8(a[2 * k], a[2 * k + 1]);
+    }
+    for (int q = 0; q < 4; ++q) {                 // fields 4q .. 4q + 3, positions 0-3 | 4-7 | 8-11 | 12-15
+        a[4 * q] = _mm_unpacklo_epi16(t[4 * q], t[4 * q + 2]);
+        a[4 * q + 1] = _mm_unpackhi_epi16(t[4 * q], t[4 * q + 2]);
+        a[4 * q + 2] = _mm_unpacklo_epi16(t[4 * q + 1], t[4 * q + 3]);
+        a[4 * q + 3] = _mm_unpackhi_epi16(t[4 * q + 1], t[4 * q + 3]);
+    }
+    for (int h = 0; h < 2; ++h)                   // fields 8h .. 8h + 7, two positions per register
+        for (int j = 0; j < 4; ++j) {
+            t[8 * h + 2 * j] = _mm_unpacklo_epi32(a[8 * h + j], a[8 * h + 4 + j]);
+            t[8 * h + 2 * j + 1] = _mm_unpackhi_epi32(a[8 * h + j], a[8 * h + 4 + j]);
+        }
+    for (int k = 0; k < 8; ++k) {                 // all 16 fields of positions 2k, 2k + 1
+        __m128i p0 = _mm_unpacklo_epi64(t[k], t[8 + k]), p1 = _mm_unpackhi_epi64(t[k], t[8 + k]);
+        uint8_t *o0 = out + (size_t)(2 * k) * row_bytes, *o1 = o0 + row_bytes;
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(o0), _mm256_cvtepu8_epi32(p0));
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(o1), _mm256_cvtepu8_epi32(p1));
+        if (ncols > 8) {
+            _mm256_storeu_si256(reinterpret_cast<__m256i *>(o0 + 32), _mm256_cvtepu8_epi32(_mm_srli_si128(p0, 8)));
+            _mm256_storeu_si256(reinterpret_cast<__m256i *>(o1 + 32), _mm256_cvtepu8_epi32(_mm_srli_si128(p1, 8)));
+        }
+    }
+}
+
+// the value fields of 64 consecutive positions (all emitted) from one-byte columns, fields consecutive in the record
+__attribute__((target("avx2"))) static void pack_dense_u8(const pss_row_pack *K, const uint8_t *src, size_t stride, int64_t i0,
+                                                           int m, uint8_t *out) {
+    const int nw = K->n_want;
+    const uint8_t *c0 = src + (size_t)K->f_idx[0] * stride + i0;
+    uint8_t *o = out + K->f_off[0];
+    for (int w = 0; w < nw; ++w) __builtin_prefetch(c0 + (size_t)w * stride + 128);
+    for (int p = 0; p + 16 <= m; p += 16) {
+        if (nw == 8) pack16x16_u8(c0 + p, stride, 8, o + (size_t)p * K->row_bytes, K->row_bytes);
+        else
+            for (int g = 0; g < nw; g += 16) {
+                const int gg = g + 16 <= nw ? g : nw - 16;      // the last group overlaps the one before
+                pack16x16_u8(c0 + (size_t)gg * stride + p, stride, 16, o + (size_t)p * K->row_bytes + 4 * gg, K->row_bytes);
+            }
+    }
+}
+
+// block of finished records -> its place in the caller's array with non-temporal stores: the records are never
+// read back by the workers, and a regular store would first fetch every destination line from memory
+__attribute__((target("avx2"))) static void copy_out_nt(uint8_t *dst, const uint8_t *src, size_t n) {
+    size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;
+    if (head > n) head = n;
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    for (; n >= 64; n -= 64, dst += 64, src += 64) {
+        __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src));
+        __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 32));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + 32), b);
+    }
+    memcpy(dst, src, n);
+}
+
+static bool pack_simd_ok(const pss_row_pack *K) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (!avx2 || !(K->n_want == 8 || K->n_want >= 16)) return false;
+    for (int w = 0; w < K->n_want; ++w)
+        if (K->f_bytes[w] != 4 || K->f_idx[w] != K->f_idx[0] + w || K->f_off[w] != K->f_off[0] + 4 * w) return false;
+    // the 64-byte runs of a record's last group may not reach past the record (they are overwritten by nothing)
+    return K->f_off[0] + 4 * K->n_want <= K->row_bytes;
+}
+
 void pss_pack_piece(pss_row_pack *K, const uint8_t *src, int64_t stride, int esz, const uint8_t *mask, int64_t p0,
                     int64_t len, int64_t row0) {
     const int BLK = 64;               // 64 records of ~250 bytes stay in L1 while the columns stream through
     int32_t sel[BLK + 1];
     const int32_t rb = K->row_bytes;
+    const bool simd = esz == 1 && pack_simd_ok(K);
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    static thread_local std::vector<uint8_t> block;      // the records of a block are assembled here (L1) ...
+    if (avx2) block.assign((size_t)BLK * (size_t)rb + 64, 0);     // (bytes of a record that no field covers leave as zeros)
     int64_t i = 0, row = row0, neg = 0;
     while (i < len) {
         int m = 0;
+        const int64_t i0 = i;
         while (i < len && m < BLK) { sel[m] = (int32_t)i; m += mask[i] != 0; ++i; }
         if (m == 0) break;
-        uint8_t *out = K->rows + (size_t)row * (size_t)rb;
-        for (int w = 0; w < K->n_want; ++w) {
+        uint8_t *const dst = K->rows + (size_t)row * (size_t)rb;
+        uint8_t *out = avx2 ? block.data() : dst;
+        const bool dense = simd && m == BLK && i - i0 == BLK;       // 64 consecutive positions, all emitted
+        if (dense) pack_dense_u8(K, src, (size_t)stride, i0, m, out);
+        for (int w = 0; w < (dense ? 0 : K->n_want); ++w) {
             const uint8_t *col = src + (size_t)K->f_idx[w] * (size_t)stride * (size_t)esz;
             uint8_t *o = out + K->f_off[w];
             if (esz == 1) pack_field((const uint8_t *)col, sel, m, o, rb, K->f_bytes[w]);
@@ -205,7 +290,9 @@ void pss_pack_piece(pss_row_pack *K, const uint8_t *src, int64_t stride, int esz
                 *o = c;
             }
         }
+        if (avx2) copy_out_nt(dst, out, (size_t)m * (size_t)rb);     // ... and leave with streaming stores
         row += m;
     }
+    if (avx2) _mm_sfence();
     if (neg) __atomic_fetch_add(&K->n_negative, neg, __ATOMIC_RELAXED);
 }

@@ -319,9 +319,15 @@ def _position_chunks(batch, lo, hi, need_qual, max_depth):
     if hi - lo <= chunk or n == 0 or need_qual:
         yield lo, hi, _reads_struct(batch, need_qual)
         return
-    maxspan = int((batch.endpos - batch.pos).max())
-    first = np.searchsorted(batch.pos, batch.pos - maxspan, side='left')
-    if int((np.arange(n) - first).max()) + 1 >= (max_depth or 8000):
+    k = (max_depth or 8000) - 1
+    key = ('cut', k)
+    if key not in batch.cache:
+        maxspan = int((batch.endpos - batch.pos).max())
+        # read i has max_depth - 1 earlier reads within maxspan of its start iff pos[i] - pos[i - (max_depth - 1)] <=
+        # maxspan (the reads are start sorted): one subtraction over the batch instead of a binary search per read
+        batch.cache[key] = (maxspan, k <= 0 or (n > k and int((batch.pos[k:] - batch.pos[:n - k]).min()) <= maxspan))
+    maxspan, refusable = batch.cache[key]
+    if refusable:
         yield lo, hi, _reads_struct(batch, need_qual)
         return
     batch.padded()

@@ -323,12 +323,14 @@ def test_rows_path_equals_column_path(stat, monkeypatch):
              dict(chrom='Pf3D7_02_v3', start=500, end=3000, truncate=True, one_based=True),
              dict(chrom='Pf3D7_03_v3', pad=True, min_mapq=20, no_dup=True),
              dict(fields=['pos', 'reads_all', 'chrom']), dict(chrom='Pf3D7_01_v3', start=60000, end=70000)]
-    for chunk in (None, '1024'):
+    for chunk, table_chunk in ((None, None), ('1024', None), ('512', '4096')):
         for kw in cases:
-            if chunk:
-                monkeypatch.setenv('PSS_HOST_CHUNK', chunk)
-            else:
-                monkeypatch.delenv('PSS_HOST_CHUNK', raising=False)
+            # PSS_HOST_CHUNK: result chunks inside one engine call; PSS_TABLE_CHUNK: position pieces = engine calls
+            for var, val in (('PSS_HOST_CHUNK', chunk), ('PSS_TABLE_CHUNK', table_chunk)):
+                if val:
+                    monkeypatch.setenv(var, val)
+                else:
+                    monkeypatch.delenv(var, raising=False)
             monkeypatch.delenv('PSS_NO_ROWS', raising=False)
             n0 = len(calls)
             a = _load(stat, 'test', **kw)
