@@ -329,3 +329,16 @@ def test_position_chunks_cover_every_overlapping_read(monkeypatch):
     # qualities wanted, or max_depth within reach of the local read density: one piece
     assert len(list(opt._position_chunks(b, lo, hi, True, 8000))) == 1
     assert len(list(opt._position_chunks(b, lo, hi, False, 20))) == 1
+
+
+def test_row_sink_packer_cpp(tmp_path):
+    # the packer behind pss_pileup_host_rows, without a GPU: tests/cpp/pack_rows_test.cpp against csrc/pss_expand.cpp
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, 'pysamstats_b200', 'csrc')
+    exe = str(tmp_path / 'pack_rows_test')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-I', csrc, '-o', exe, os.path.join(root, 'tests', 'cpp', 'pack_rows_test.cpp'),
+                           os.path.join(csrc, 'pss_expand.cpp'), '-lpthread'])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count('bad 0') == 21
