@@ -465,10 +465,18 @@ class BamFile(object):
                     os.path.getsize(self.filename) >= int(os.environ.get('PSS_BAI_MIN_BYTES', 32 << 20)):
                 return self._region_native(self._tid_of[chrom], start, end, bai)
         b = self.contig_batch(chrom)
-        m = (b.pos < end) & (b.endpos > start)
-        if m.all():
+        n = b.n_reads
+        if n == 0:
             return b
-        sub = b.subset(np.flatnonzero(m))
+        # the records are start sorted: only those starting in [start - longest span, end) can overlap the region
+        if 'maxspan' not in b.cache:
+            b.cache['maxspan'] = int((b.endpos - b.pos).max())
+        i0 = int(np.searchsorted(b.pos, start - b.cache['maxspan'], side='left'))
+        i1 = int(np.searchsorted(b.pos, end, side='left'))
+        idx = i0 + np.flatnonzero(b.endpos[i0:i1] > start)
+        if len(idx) == n:
+            return b
+        sub = b.subset(idx)
         sub.tid = b.tid
         return sub
 
