@@ -82,6 +82,15 @@ int pss_pack_rows(uint8_t *dst, int64_t n_rows, int32_t row_bytes, int32_t n_col
 int pss_take_cols_i32(const int32_t *src, int64_t src_stride, int32_t n_cols, const int64_t *idx, int64_t n,
                       int32_t *dst, int64_t dst_stride, int n_threads);
 
+/* Text of n_rows rows as csv.writer would write them for values that need no quoting (replaces the per-row
+ * csv.writer.writerow of pysamstats/io.py:60-75): column c is kind 0 = constant text (src = its bytes, width =
+ * their number), 1 = int32, 2 = int64 (decimal), 3 = one-byte text (NUL = empty); src_stride in bytes; cells
+ * joined by `delimiter`, rows ended by `terminator`.  *out is malloc'ed; release it with pss_host_free. */
+int pss_format_rows(int64_t n_rows, int32_t n_cols, const int32_t *kind, const void *const *src,
+                    const int32_t *src_stride, const int32_t *width, const char *delimiter, int32_t delimiter_len,
+                    const char *terminator, int32_t terminator_len, int n_threads, char **out, int64_t *out_len);
+void pss_host_free(void *p);
+
 /* prev[i] = index of the previous row with the same (NUL padded, fixed width) name, or -1 */
 int pss_name_prev(const uint8_t *names, int64_t n, int32_t width, int32_t *prev);
 

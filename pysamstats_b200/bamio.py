@@ -68,6 +68,11 @@ def host_lib():
             lib.pss_take_cols_i32.argtypes = [P, C.c_int64, C.c_int32, P, C.c_int64, P, C.c_int64, C.c_int]
             lib.pss_pack_rows.argtypes = [P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(P), C.POINTER(C.c_int32),
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+            lib.pss_format_rows.argtypes = [C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(P), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32), C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int,
+                                            C.POINTER(P), C.POINTER(C.c_int64)]
+            lib.pss_host_free.argtypes = [P]
+            lib.pss_host_free.restype = None
             lib.pss_bam_write.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int64,
                                           C.POINTER(HostArrays), C.c_int32, C.c_int, C.c_int]
             _host_lib = lib
@@ -108,6 +113,49 @@ def alloc_rows(n, dtype):
         except OSError:
             pass
     return np.frombuffer(mm, dtype=dtype, count=int(n))
+
+
+def format_rows_native(columns, delimiter, terminator):
+    """Text (str) of the rows made of ``columns`` -- a list of str (constant cell), int32 / int64 arrays or S1 arrays
+    -- formatted on all host threads by libpss_host; None when the library or a column type is not available."""
+    lib = host_lib()
+    if lib is None:
+        return None
+    n = None
+    kinds, srcs, strides, widths, keep = [], [], [], [], []
+    for col in columns:
+        if isinstance(col, str):
+            b = col.encode('utf-8')
+            buf = C.create_string_buffer(b, len(b) + 1)
+            keep.append(buf)
+            kinds.append(0); srcs.append(C.addressof(buf)); strides.append(0); widths.append(len(b))
+            continue
+        col = np.asarray(col)
+        if col.ndim != 1 or (n is not None and len(col) != n):
+            return None
+        n = len(col)
+        if col.dtype == np.dtype('<i4'):
+            kinds.append(1)
+        elif col.dtype == np.dtype('<i8'):
+            kinds.append(2)
+        elif col.dtype == np.dtype('S1'):
+            kinds.append(3)
+        else:
+            return None
+        keep.append(col)
+        srcs.append(col.ctypes.data if n else C.addressof(C.create_string_buffer(8)))
+        strides.append(col.strides[0]); widths.append(0)
+    if n is None:
+        return None
+    k = len(columns)
+    out, out_len = C.c_void_p(), C.c_int64(0)
+    d, t = delimiter.encode('utf-8'), terminator.encode('utf-8')
+    _host_check(lib, lib.pss_format_rows(n, k, (C.c_int32 * k)(*kinds), (C.c_void_p * k)(*srcs), (C.c_int32 * k)(*strides),
+                                         (C.c_int32 * k)(*widths), d, len(d), t, len(t), 0, C.byref(out), C.byref(out_len)))
+    try:
+        return C.string_at(out.value, out_len.value).decode('utf-8')
+    finally:
+        lib.pss_host_free(out)
 
 
 def take_cols(out, sel):

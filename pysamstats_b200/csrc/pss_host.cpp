@@ -793,6 +793,109 @@ extern "C" int pss_take_cols_i32(const int32_t *src, int64_t src_stride, int32_t
     return 0;
 }
 
+// ------------------------------------------------------------------------------ text rows
+//
+// write_csv (pysamstats/io.py:14-88) pushes one dict per row through csv.writer; here a block of rows is
+// formatted from the columns on all host threads: decimal integers, a constant (already quoted if it had to
+// be) chrom text, one-character ref bases, joined by the dialect's delimiter and line terminator -- the bytes
+// csv.writer writes for values that need no quoting (the caller keeps quoting cases to itself).
+
+static inline int dec_digits(uint64_t u) {
+    if (u < 100) return u < 10 ? 1 : 2;
+    if (u < 10000) return u < 1000 ? 3 : 4;
+    if (u < 1000000) return u < 100000 ? 5 : 6;
+    if (u < 100000000) return u < 10000000 ? 7 : 8;
+    int n = 9;
+    for (uint64_t t = 1000000000ull; n < 20 && u >= t; t *= 10) ++n;
+    return n;
+}
+
+static inline int dec_len(int64_t v) {
+    return v < 0 ? 1 + dec_digits((uint64_t)0 - (uint64_t)v) : dec_digits((uint64_t)v);
+}
+
+static inline char *dec_put(char *p, int64_t v) {
+    static const char lut[201] =
+        "00010203040506070809101112131415161718192021222324252627282930313233343536373839"
+        "40414243444546474849505152535455565758596061626364656667686970717273747576777879"
+        "8081828384858687888990919293949596979899";
+    uint64_t u = (uint64_t)v;
+    if (v < 0) { *p++ = '-'; u = (uint64_t)0 - u; }
+    const int n = dec_digits(u);
+    char *e = p + n;
+    while (u >= 100) { const uint64_t q = u / 100; e -= 2; e[0] = lut[2 * (u - q * 100)]; e[1] = lut[2 * (u - q * 100) + 1]; u = q; }
+    if (u >= 10) { e[-2] = lut[2 * u]; e[-1] = lut[2 * u + 1]; }
+    else e[-1] = (char)('0' + u);
+    return p + n;
+}
+
+// kind[c]: 0 constant text (src = bytes, width = length), 1 int32 column, 2 int64 column, 3 one-byte text
+// column (a NUL byte is the empty string); src_stride in bytes.  *out is malloc'ed (pss_host_free).
+extern "C" int pss_format_rows(int64_t n_rows, int32_t n_cols, const int32_t *kind, const void *const *src,
+                               const int32_t *src_stride, const int32_t *width, const char *delimiter, int32_t delimiter_len,
+                               const char *terminator, int32_t terminator_len, int n_threads, char **out, int64_t *out_len) {
+    if (n_rows < 0 || n_cols < 1 || !kind || !src || !src_stride || !width || !out || !out_len || delimiter_len < 0 ||
+        terminator_len < 0 || (delimiter_len > 0 && !delimiter) || (terminator_len > 0 && !terminator))
+        return fail(-1, "bad argument");
+    for (int c = 0; c < n_cols; ++c)
+        if (kind[c] < 0 || kind[c] > 3 || !src[c] || (kind[c] == 0 && width[c] < 0)) return fail(-1, "bad column %d", c);
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int64_t BLK = 4096;
+    const int64_t nblk = (n_rows + BLK - 1) / BLK;
+    std::vector<int64_t> off((size_t)nblk + 1, 0);
+    auto rows_of = [&](int64_t b, auto &&cell) {
+        const int64_t r0 = b * BLK, r1 = std::min(n_rows, r0 + BLK);
+        for (int64_t r = r0; r < r1; ++r)
+            for (int c = 0; c < n_cols; ++c) cell(r, c);
+    };
+    const int nt = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, nblk / 2));
+    parallel_for(nblk, nt, [&](int64_t b0, int64_t b1, int) {
+        for (int64_t b = b0; b < b1; ++b) {
+            int64_t len = 0;
+            rows_of(b, [&](int64_t r, int c) {
+                const uint8_t *p = (const uint8_t *)src[c] + (size_t)r * (size_t)src_stride[c];
+                switch (kind[c]) {
+                    case 0: len += width[c]; break;
+                    case 1: { int32_t v; memcpy(&v, p, 4); len += dec_len(v); break; }
+                    case 2: { int64_t v; memcpy(&v, p, 8); len += dec_len(v); break; }
+                    default: len += *p != 0;
+                }
+            });
+            const int64_t nr = std::min(n_rows, (b + 1) * BLK) - b * BLK;
+            off[(size_t)b + 1] = len + nr * ((int64_t)(n_cols - 1) * delimiter_len + terminator_len);
+        }
+    });
+    for (int64_t b = 0; b < nblk; ++b) off[(size_t)b + 1] += off[(size_t)b];
+    const int64_t total = off[(size_t)nblk];
+    char *buf = (char *)malloc((size_t)std::max<int64_t>(total, 1));
+    if (!buf) return fail(-1, "out of memory (%lld bytes of text)", (long long)total);
+    parallel_for(nblk, nt, [&](int64_t b0, int64_t b1, int) {
+        for (int64_t b = b0; b < b1; ++b) {
+            char *o = buf + off[(size_t)b];
+            rows_of(b, [&](int64_t r, int c) {
+                const uint8_t *p = (const uint8_t *)src[c] + (size_t)r * (size_t)src_stride[c];
+                switch (kind[c]) {
+                    case 0: memcpy(o, src[c], (size_t)width[c]); o += width[c]; break;
+                    case 1: { int32_t v; memcpy(&v, p, 4); o = dec_put(o, v); break; }
+                    case 2: { int64_t v; memcpy(&v, p, 8); o = dec_put(o, v); break; }
+                    default: if (*p) *o++ = (char)*p;
+                }
+                if (c + 1 < n_cols) {
+                    if (delimiter_len == 1) *o++ = delimiter[0];
+                    else { memcpy(o, delimiter, (size_t)delimiter_len); o += delimiter_len; }
+                } else {
+                    for (int k = 0; k < terminator_len; ++k) *o++ = terminator[k];
+                }
+            });
+        }
+    });
+    *out = buf;
+    *out_len = total;
+    return 0;
+}
+
+extern "C" void pss_host_free(void *p) { free(p); }
+
 // ------------------------------------------------------------------------------ name_prev
 
 extern "C" int pss_name_prev(const uint8_t *names, int64_t n, int32_t width, int32_t *prev) {

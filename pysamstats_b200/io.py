@@ -42,14 +42,47 @@ def format_rows(fields, chrom, pos, ref, cols, dialect):
     n = len(pos)
     if n == 0:
         return ''
+    chrom_text = chrom
+    if any(c in chrom for c in special):                         # let csv do the quoting
+        buf = _io.StringIO()
+        csv.writer(buf, dialect=dialect).writerow([chrom])
+        chrom_text = buf.getvalue()[:-len(d.lineterminator)]
+    if d.quoting != csv.QUOTE_MINIMAL or d.escapechar or not d.doublequote:
+        # any other dialect: csv.writer itself, row by row (the tsv / csv formats of the CLI never come here)
+        buf = _io.StringIO()
+        columns = []
+        for f in fields:
+            if f == 'chrom':
+                columns.append([chrom] * n)
+            elif f == 'pos':
+                columns.append(np.asarray(pos).tolist())
+            elif f == 'ref':
+                columns.append([r.decode('ascii') for r in np.asarray(ref).tolist()])
+            else:
+                columns.append(np.asarray(cols[f]).tolist())
+        csv.writer(buf, dialect=dialect).writerows(zip(*columns))
+        return buf.getvalue()
+    # native formatter (libpss_host, all host threads) whenever no cell of the block needs quoting
+    if d.quoting == csv.QUOTE_MINIMAL and ('ref' not in fields or ref is None or
+                                           not np.isin(np.asarray(ref), [c.encode() for c in special]).any()):
+        native = []
+        for f in fields:
+            if f == 'chrom':
+                native.append(chrom_text)
+            elif f == 'pos':
+                native.append(np.ascontiguousarray(pos))
+            elif f == 'ref':
+                native.append(np.asarray(ref))
+            else:
+                native.append(np.asarray(cols[f]))
+        from . import bamio
+        text = bamio.format_rows_native(native, d.delimiter, d.lineterminator)
+        if text is not None:
+            return text
     parts = []
     for f in fields:
         if f == 'chrom':
-            text = chrom
-            if any(c in chrom for c in special):                 # let csv do the quoting
-                buf = _io.StringIO()
-                csv.writer(buf, dialect=dialect).writerow([chrom])
-                text = buf.getvalue()[:-len(d.lineterminator)]
+            text = chrom_text
             parts.append(np.full(n, text, dtype='U%d' % max(1, len(text))))
         elif f == 'pos':
             parts.append(np.asarray(pos).astype('U'))

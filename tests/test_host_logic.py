@@ -231,6 +231,35 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.pss_binned_nbins(5, 5, 300) == 1
 
 
+def test_native_row_formatter_equals_csv_writer(monkeypatch):
+    # pss_format_rows (libpss_host): the path write_csv takes when no cell needs quoting -- int32 extremes, int64
+    # positions, empty ref cells, a chrom that csv has to quote, several 4096-row blocks
+    import csv
+    import io
+    from pysamstats_b200 import io as pio
+    calls = []
+    real = bamio.format_rows_native
+    monkeypatch.setattr(bamio, 'format_rows_native', lambda *a: calls.append(1) or real(*a))
+    n = 9001
+    rng = np.random.default_rng(1)
+    pos = np.arange(10 ** 6 - 5, 10 ** 6 - 5 + n, dtype=np.int64)
+    pos[:3] = [0, 2 ** 40, 9999999999]
+    ref = rng.choice(np.array([b'A', b'c', b'', b'N'], dtype='S1'), n)
+    fields = ['chrom', 'pos', 'ref'] + ['f%d' % i for i in range(20)]
+    cols = {f: rng.integers(0, 10 ** int(rng.integers(1, 10)), n).astype('i4') for f in fields[3:]}
+    cols['f0'][:8] = [-2 ** 31, 2 ** 31 - 1, 0, -1, 9, 10, 99, 100]
+    for chrom in ('Pf3D7_01_v3', 'odd,na\tme'):
+        for dialect in ('excel-tab', 'excel', 'unix'):
+            buf = io.StringIO()
+            w = csv.writer(buf, dialect=dialect)
+            for i in range(n):
+                w.writerow([chrom, int(pos[i]), ref[i].decode()] + [int(cols[f][i]) for f in fields[3:]])
+            got, exp = pio.format_rows(fields, chrom, pos, ref, cols, dialect), buf.getvalue()
+            same = got == exp                      # (no pytest diff of megabyte strings)
+            assert same, (chrom, dialect, next((i for i, (a, b) in enumerate(zip(got, exp)) if a != b), min(len(got), len(exp))))
+    assert len(calls) == 4          # 'unix' quotes every cell (QUOTE_ALL): csv.writer itself
+
+
 def test_host_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, 'include', 'pss_host.h')).read()
     declared = set(re.findall(r'\b(pss_[a-z_0-9]+)\s*\(', header))
