@@ -43,6 +43,14 @@ with tempfile.TemporaryDirectory() as tmp:
         print('rep %d: decode %.2f s | load_variation_strand %.2f s (%.1f M rows/s, %d rows, itemsize %d) | '
               'load_coverage_ext %.2f s | load_coverage_binned %.3f s | 100 kb region %.3f s'
               % (rep, t1 - t0, t2 - t1, len(a) / (t2 - t1) / 1e6, len(a), a.dtype.itemsize, t3 - t2, t4 - t3, t5 - t4))
+    from pysamstats_b200.io import write_csv
+    for st in ('coverage', 'variation_strand'):
+        with open(os.path.join(tmp, 'out.tsv'), 'w') as f:
+            t0 = time.time()
+            write_csv(st, f, bam, fafile=fa if st == 'variation_strand' else None)
+            dt = time.time() - t0
+            size = f.tell()
+        print('write_csv %s (tsv to a file): %.2f s, %.2f M rows/s, %.0f MB/s' % (st, dt, len(a) / dt / 1e6, size / dt / 1e6))
     bamio._bam_cache.clear()
     t0 = time.time()
     r = pysamstats.load_variation(bam, fafile=fa, chrom='chrS', start=G // 2, end=G // 2 + 100000)
