@@ -342,20 +342,25 @@ def _position_chunks(batch, lo, hi, need_qual, max_depth):
         yield c_lo, c_hi, _cabi.make_reads_struct(d, n_reads=i1 - i0)
 
 
+_ITER_BLOCK = 1 << 16
+
+
 def iter_pileup(stat, alignmentfile, fafile, pad, **kwargs):
     """Generator of one dict per genome position -- the reference's ``opt.iter_pileup``
     (``opt.pyx:1827-1843``), same keyword arguments."""
     for chrom, pos, ref, fields in pileup_tables(stat, alignmentfile, fafile, pad, **kwargs):
         names = list(fields)
-        cols = [fields[f].tolist() for f in names]
-        refs = [r.decode('ascii') for r in ref.tolist()] if ref is not None else None
-        for i, p in enumerate(pos.tolist()):
-            rec = {f: col[i] for f, col in zip(names, cols)}
-            if refs is not None:
-                rec['ref'] = refs[i]
-            rec['chrom'] = chrom
-            rec['pos'] = p
-            yield rec
+        for o in range(0, len(pos), _ITER_BLOCK):     # python objects for a block of rows at a time (bounded memory)
+            sl = slice(o, o + _ITER_BLOCK)
+            cols = [fields[f][sl].tolist() for f in names]
+            refs = [r.decode('ascii') for r in ref[sl].tolist()] if ref is not None else None
+            for i, p in enumerate(pos[sl].tolist()):
+                rec = {f: col[i] for f, col in zip(names, cols)}
+                if refs is not None:
+                    rec['ref'] = refs[i]
+                rec['chrom'] = chrom
+                rec['pos'] = p
+                yield rec
 
 
 # ------------------------------------------------------------------------ binned tables
