@@ -256,7 +256,9 @@ int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats,
  * the upper-cased base of params->ref, 0 outside it: opt.pyx:1987-1994) are written when their offset
  * is >= 0.  Rows are written from `rows` on, at most capacity_rows of them (PSS_EINVAL beyond);
  * *n_rows receives their number, *n_negative how many emitted values of field `check_field` were
- * negative (gc = -1 of an empty window, which the reference cannot store).  HOST pointers, synchronous.
+ * negative (gc = -1 of an empty window, which the reference cannot store).  Records beyond *n_rows (inside the
+ * capacity) are unspecified: an attempt that had to be repeated with wider columns may have written them.
+ * HOST pointers, synchronous.
  */
 typedef struct pss_row_layout {
     int32_t row_bytes;

@@ -356,3 +356,88 @@ def test_long_reads_need_no_flag(stat, ctx):
     out, mask = _run_host(ctx, nb, ref, stat, 0, G)
     pos_o, F = _oracle(stat, reads, ref, 0, G)
     _compare(out, mask, pos_o, F, 0, stat)
+
+
+# ---- pss_pileup_host_rows: packed records == the int32 columns of pss_pileup_host -------------------
+
+def _run_rows(ctx, nb, ref, stat, lo, hi, pad=None, capacity=None, flags=0, **kw):
+    need_qual = bool(ctx.lib.pss_pileup_needs_qual(_cabi.PILEUP_STATS.index(stat), int(kw.get('min_baseq', 0))))
+    d = dict(nb)
+    if not need_qual:
+        d['qual'] = d['qual_off'] = d['name_prev'] = None
+    rs = _cabi.make_reads_struct(d)
+    withref = stat in config.stats_types_withref
+    p = ctx.pileup_params(stat, start=lo, end=hi, ref=ref if withref else None, ref_start=0,
+                          ref_len=len(ref) if withref else 0, contig_len=len(ref), flags=flags, **kw)
+    names = config.value_fields(stat)
+    dt = np.dtype([('chrom', 'S5'), ('pos', '<i4')] + ([('ref', 'S1')] if withref else []) + [(f, '<i4') for f in names])
+    layout = ctx.row_layout(stat, dt, names, chrom='chrS', pos_add=1, pad=pad)
+    cap = hi - lo if capacity is None else capacity
+    rows = np.full(cap + 2, 0x55, dtype='u1').repeat(dt.itemsize).view(dt)       # guard records around the result
+    n, neg = ctx.pileup_host_rows(rs, p, layout, rows, 1, cap)
+    guard = np.full(1, 0x55, dtype='u1').repeat(dt.itemsize).view(dt)
+    # nothing outside rows[row0 : row0 + capacity] is touched (records beyond the n returned may have been written by an
+    # attempt that had to be repeated with wider columns)
+    assert rows[0].tobytes() == guard.tobytes() and rows[cap + 1].tobytes() == guard.tobytes()
+    return rows[1:n + 1]
+
+
+def _rows_from_columns(out, mask, lo, ref, stat, pad=None):
+    emit = mask.astype(bool)
+    if pad:
+        emit[max(pad[0] - lo, 0):max(pad[1] - lo, 0)] = True
+    sel = np.flatnonzero(emit)
+    names = config.value_fields(stat)
+    withref = stat in config.stats_types_withref
+    dt = np.dtype([('chrom', 'S5'), ('pos', '<i4')] + ([('ref', 'S1')] if withref else []) + [(f, '<i4') for f in names])
+    a = np.zeros(len(sel), dtype=dt)
+    a['chrom'] = b'chrS'
+    a['pos'] = sel + lo + 1
+    if withref:
+        p = sel + lo
+        ok = p < len(ref)
+        r = np.zeros(len(sel), 'u1')
+        r[ok] = ref[p[ok]]
+        lower = (r >= 97) & (r <= 122)
+        a['ref'] = np.where(lower, r - 32, r).astype('u1').view('S1')
+    for j, f in enumerate(names):
+        a[f] = out[j][sel]
+    return a
+
+
+@pytest.mark.parametrize('stat', ['coverage', 'coverage_ext', 'variation', 'variation_strand', 'baseq_ext_strand', 'tlen',
+                                  'mapq_strand', 'coverage_gc'])
+def test_rows_entry_equals_columns(stat, ctx, small, monkeypatch):
+    nb, ref, _ = small
+    for chunk in (None, '2048'):
+        if chunk:
+            monkeypatch.setenv('PSS_HOST_CHUNK', chunk)
+        else:
+            monkeypatch.delenv('PSS_HOST_CHUNK', raising=False)
+        for lo, hi, pad, kw in ((0, G, None, {}), (1000, 90001, (500, 3000), dict(no_dup=True, min_mapq=30)),
+                                (G - 5000, G + 700, (G, G + 650), dict(min_baseq=20))):
+            out, mask = _run_host(ctx, nb, ref, stat, lo, hi, **kw)
+            exp = _rows_from_columns(out, mask, lo, ref, stat, pad)
+            got = _run_rows(ctx, nb, ref, stat, lo, hi, pad=pad, **kw)
+            assert got.shape == exp.shape and got.tobytes() == exp.tobytes(), (stat, lo, hi, pad, kw, chunk)
+    with pytest.raises(ValueError):
+        _run_rows(ctx, nb, ref, stat, 0, G, capacity=1000)
+
+
+def test_rows_entry_beyond_16_bits(ctx):
+    # 70 000 reads on one position: the 8-bit chunk is redone with 16 bits, those need several passes, so the records
+    # come through the int32 columns of the same pipeline
+    n, L = 70000, 100
+    nb = dict(n_reads=n, tid=0,
+              pos=np.full(n, 1000, 'i4'), flag=np.where(np.arange(n) % 2, 16, 0).astype('u2'),
+              mapq=np.full(n, 60, 'u1'), tlen=np.zeros(n, 'i4'), mtid=np.full(n, -1, 'i4'),
+              l_seq=np.full(n, L, 'i4'), cigar_off=np.arange(n + 1, dtype='i8'),
+              cigar=np.full(n, (L << 4), 'u4'), seq_off=np.arange(n + 1, dtype='i8') * (L // 2),
+              seq4=np.tile(np.array([0x12, 0x48], 'u1'), n * L // 4), qual=None, qual_off=None, name_prev=None)
+    ref = np.frombuffer(b'ACGT' * 600, dtype='u1')
+    for stat in ('variation_strand', 'coverage'):
+        out, mask = _run_host(ctx, nb, ref, stat, 900, 1300, max_depth=1000000)
+        exp = _rows_from_columns(out, mask, 900, ref, stat)
+        got = _run_rows(ctx, nb, ref, stat, 900, 1300, max_depth=1000000)
+        assert len(got) == 100 and got.tobytes() == exp.tobytes(), stat
+        assert got['reads_all'].max() == n
