@@ -82,6 +82,12 @@ int pss_pack_rows(uint8_t *dst, int64_t n_rows, int32_t row_bytes, int32_t n_col
 int pss_take_cols_i32(const int32_t *src, int64_t src_stride, int32_t n_cols, const int64_t *idx, int64_t n,
                       int32_t *dst, int64_t dst_stride, int n_threads);
 
+/* One raw DEFLATE stream (the payload of a BGZF block; htslib bgzf.c inflates these behind every pysam read,
+ * opt.pyx:1853-1854, :2038-2048) inflated whole into dst[0, out_len): mode 0 = the decoder of the BAM path
+ * (pss_inflate.cpp, zlib for whatever it declines), 1 = that decoder alone (-1 when it declines), 2 = zlib alone.
+ * 0 on success.  For tests and timing. */
+int pss_inflate_raw(const uint8_t *src, int64_t in_len, uint8_t *dst, int64_t out_len, int mode);
+
 /* Text of n_rows rows as csv.writer would write them for values that need no quoting (replaces the per-row
  * csv.writer.writerow of pysamstats/io.py:60-75): column c is kind 0 = constant text (src = its bytes, width =
  * their number), 1 = int32, 2 = int64 (decimal), 3 = one-byte text (NUL = empty); src_stride in bytes; cells

@@ -7,6 +7,7 @@
 // {block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, l_seq, next_refID,
 //  next_pos, tlen, read_name, cigar, seq, qual, aux}.
 #include "../../include/pss_host.h"
+#include "pss_inflate.h"
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -44,6 +45,8 @@ static double now() {
 static inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline int32_t rdi32(const uint8_t *p) { int32_t v; memcpy(&v, p, 4); return v; }
+
+static int inflate_one(z_stream &zs, const uint8_t *src, int64_t in_len, uint8_t *dst, int64_t out_len);
 
 template <class F>
 static void parallel_for(int64_t n, int n_threads, F f) {
@@ -176,13 +179,7 @@ extern "C" int pss_bam_open(const char *path, int n_threads, pss_bam **out) {
                 int64_t k1 = std::min<int64_t>(blocks.size(), k0 + 16);
                 for (int64_t k = k0; k < k1; ++k) {
                     const Blk &bl = blocks[k];
-                    if (bl.out_len != 0) {
-                        inflateReset(&zs);
-                        zs.next_in = (Bytef *)(comp + bl.in_off); zs.avail_in = (uInt)bl.in_len;
-                        zs.next_out = b->raw.data() + bl.out_off; zs.avail_out = (uInt)bl.out_len;
-                        int rc = inflate(&zs, Z_FINISH);
-                        if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
-                    }
+                    if (inflate_one(zs, comp + bl.in_off, bl.in_len, b->raw.data() + bl.out_off, bl.out_len) != 0) bad = 1;
                     done[(size_t)k].store(1, std::memory_order_release);
                 }
             }
@@ -401,6 +398,9 @@ static int parse_header(pss_bam *b, const uint8_t *r, int64_t n, int64_t *consum
 
 static int inflate_one(z_stream &zs, const uint8_t *src, int64_t in_len, uint8_t *dst, int64_t out_len) {
     if (out_len == 0) return 0;
+    // own decoder first (pss_inflate.cpp, ~2x zlib); whatever it declines is repeated with zlib, which decides
+    static const bool zlib_only = getenv("PSS_ZLIB_INFLATE") != nullptr;
+    if (!zlib_only && pss_inflate_fast(src, (size_t)in_len, dst, (size_t)out_len) == 0) return 0;
     inflateReset(&zs);
     zs.next_in = (Bytef *)src; zs.avail_in = (uInt)in_len;
     zs.next_out = dst; zs.avail_out = (uInt)out_len;
@@ -791,6 +791,24 @@ extern "C" int pss_take_cols_i32(const int32_t *src, int64_t src_stride, int32_t
         }
     });
     return 0;
+}
+
+// One raw DEFLATE stream, whole: mode 0 = the decoder of the BAM path (own decoder, zlib for what it declines),
+// 1 = own decoder only (-1 when it declines), 2 = zlib only.  For tests and timing.
+extern "C" int pss_inflate_raw(const uint8_t *src, int64_t in_len, uint8_t *dst, int64_t out_len, int mode) {
+    if (!src || !dst || in_len < 0 || out_len < 0) return fail(-1, "bad argument");
+    if (mode == 1) return pss_inflate_fast(src, (size_t)in_len, dst, (size_t)out_len);
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return fail(-3, "zlib init failed");
+    int rc;
+    if (mode == 2) {
+        zs.next_in = (Bytef *)src; zs.avail_in = (uInt)in_len;
+        zs.next_out = dst; zs.avail_out = (uInt)out_len;
+        rc = (out_len == 0 || (inflate(&zs, Z_FINISH) == Z_STREAM_END && zs.avail_out == 0)) ? 0 : -1;
+    } else rc = inflate_one(zs, src, in_len, dst, out_len);
+    inflateEnd(&zs);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------ text rows

@@ -371,3 +371,56 @@ def test_row_sink_packer_cpp(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count('bad 0') == 21
+
+
+def test_own_inflate_equals_zlib():
+    # pss_inflate.cpp (the BGZF decode path): every stream zlib writes -- stored / fixed / dynamic blocks, flush points,
+    # long distances, short runs -- inflates to the same bytes; streams it accepts after corruption are streams zlib
+    # accepts with the same bytes; wrong output sizes are refused
+    import zlib
+    lib = ctypes.CDLL(bamio.HOST_LIB_PATH)
+    lib.pss_inflate_raw.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
+    rng = np.random.default_rng(5)
+
+    def own(comp, n, mode=1):
+        out = ctypes.create_string_buffer(max(n, 1))
+        rc = lib.pss_inflate_raw(comp, len(comp), out, n, mode)
+        return rc, out.raw[:n]
+
+    datasets = [b'', b'a', b'ab' * 40000, bytes(65280), rng.integers(0, 256, 65280, dtype=np.uint8).tobytes(),
+                rng.choice(np.frombuffer(b'ACGT', dtype=np.uint8), 65280).tobytes(),
+                np.clip(rng.normal(35, 5, 65280), 2, 41).astype(np.uint8).tobytes()]
+    base = rng.integers(0, 256, 20000, dtype=np.uint8).tobytes()
+    datasets.append(base + base[5000:15000] + base[:12345] + base)
+    for n in (1, 2, 3, 8, 9, 257, 258, 259, 32768, 32769):
+        datasets.append(rng.integers(0, 7, n, dtype=np.uint8).tobytes())
+    n_corrupt = 0
+    for data in datasets:
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+                half = len(data) // 2
+                comp = co.compress(data[:half]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(data[half:]) + co.flush()
+                assert own(comp, len(data)) == (0, data), (len(data), level, strategy)
+                assert own(comp, len(data), 0) == (0, data)
+                assert own(comp, len(data) + 1)[0] != 0 and (not data or own(comp, len(data) - 1)[0] != 0)
+                if len(comp) > 8:
+                    bad = bytearray(comp)
+                    bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+                    bad = bytes(bad[:int(rng.integers(len(bad) // 2, len(bad) + 1))])
+                    rc, got = own(bad, len(data))
+                    if rc == 0:
+                        n_corrupt += 1
+                        d = zlib.decompressobj(-15)
+                        assert d.decompress(bad) == got and d.eof      # (a flipped literal bit is still a valid stream)
+    # fixture BAMs: every BGZF block through both decoders
+    import struct
+    for name in ('test.bam', 'rna.bam'):
+        raw = open(fx(name), 'rb').read()
+        p = 0
+        while p < len(raw):
+            xlen, = struct.unpack_from('<H', raw, p + 10)
+            bsize = struct.unpack_from('<H', raw, p + 16)[0] + 1
+            pay, isize = raw[p + 12 + xlen:p + bsize - 8], struct.unpack_from('<I', raw, p + bsize - 4)[0]
+            assert own(pay, isize) == (0, zlib.decompress(pay, -15))
+            p += bsize
