@@ -201,17 +201,18 @@ int pss_inflate_fast(const uint8_t *src, size_t in_len, uint8_t *dst, size_t out
         for (;;) {
             // fast path: far enough from both ends that no single symbol can run out of input or output, so the
             // only checks left are holes and offsets before the block
-            while (in_end - in >= 32 && out_end - out >= 280) {     // three 8-byte loads at in + <= 14, 3 literals + 258 + 15 bytes out
+            while (in_end - in >= 32 && out_end - out >= 280) {     // three 8-byte loads at in + <= 14; 3 literals + 258 + 15 bytes out
 #define REFILL_FAST() do { bitbuf |= load64(in) << bitcnt; in += (63 - bitcnt) >> 3; bitcnt |= 56; } while (0)
                 REFILL_FAST();
                 uint32_t e = ll[bitbuf & ((1u << LL_BITS) - 1)];
+#define PUT_LITS(e) do { *out++ = (uint8_t)((e) >> 16); } while (0)
                 if (e & F_LIT) {                          // up to three literals per refill (3 x 15 bits)
-                    DROP(e & 15); *out++ = (uint8_t)(e >> 16);
+                    DROP(e & 15); PUT_LITS(e);
                     e = ll[bitbuf & ((1u << LL_BITS) - 1)];
                     if (e & F_LIT) {
-                        DROP(e & 15); *out++ = (uint8_t)(e >> 16);
+                        DROP(e & 15); PUT_LITS(e);
                         e = ll[bitbuf & ((1u << LL_BITS) - 1)];
-                        if (e & F_LIT) { DROP(e & 15); *out++ = (uint8_t)(e >> 16); continue; }
+                        if (e & F_LIT) { DROP(e & 15); PUT_LITS(e); continue; }
                     }
                     REFILL_FAST();
                     e = ll[bitbuf & ((1u << LL_BITS) - 1)];
@@ -220,7 +221,7 @@ int pss_inflate_fast(const uint8_t *src, size_t in_len, uint8_t *dst, size_t out
                 unsigned l = e & 15;
                 if (!l) return -1;
                 DROP(l);
-                if (e & F_LIT) { *out++ = (uint8_t)(e >> 16); continue; }
+                if (e & F_LIT) { PUT_LITS(e); continue; }
                 if (e & F_EOB) goto block_done;
                 unsigned x = (e >> 8) & 0xff;
                 const unsigned length = (e >> 16) + ((unsigned)bitbuf & ((1u << x) - 1));
@@ -248,6 +249,7 @@ int pss_inflate_fast(const uint8_t *src, size_t in_len, uint8_t *dst, size_t out
                     do { *o++ = *from++; } while (o < out);
                 }
 #undef REFILL_FAST
+#undef PUT_LITS
             }
             REFILL();
             uint32_t e = ll[bitbuf & ((1u << LL_BITS) - 1)];
@@ -257,15 +259,6 @@ int pss_inflate_fast(const uint8_t *src, size_t in_len, uint8_t *dst, size_t out
             DROP(l);
             if (e & F_LIT) {
                 if (out == out_end) return -1;
-                *out++ = (uint8_t)(e >> 16);
-                // a second and third literal from the same refill (a litlen code is at most 15 bits)
-                e = ll[bitbuf & ((1u << LL_BITS) - 1)];
-                if (!(e & F_LIT) || (e & 15) > bitcnt || out == out_end) continue;
-                DROP(e & 15);
-                *out++ = (uint8_t)(e >> 16);
-                e = ll[bitbuf & ((1u << LL_BITS) - 1)];
-                if (!(e & F_LIT) || (e & 15) > bitcnt || out == out_end) continue;
-                DROP(e & 15);
                 *out++ = (uint8_t)(e >> 16);
                 continue;
             }
