@@ -279,7 +279,7 @@ class ReadBatch(object):
             setattr(b, k, np.ascontiguousarray(getattr(self, k)[idx]))
         for data, off in (('cigar', 'cigar_off'), ('seq4', 'seq_off'), ('qual', 'qual_off')):
             o = getattr(self, off)
-            d, no = _ragged_gather(getattr(self, data), o[:-1][idx], (o[1:] - o[:-1])[idx])
+            d, no = _ragged_gather(getattr(self, data), o[idx], o[idx + 1] - o[idx])    # (no pass over the whole batch)
             setattr(b, data, d)
             setattr(b, off, no)
         b.name_prev = None

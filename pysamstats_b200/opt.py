@@ -152,7 +152,9 @@ def _pileup_plan(stat, alignmentfile, fafile, pad, chrom, start, end, one_based,
         if truncate:
             lo, hi = s, e
         elif n:
-            lo, hi = int(batch.pos[0]), int(batch.endpos.max())
+            if 'span' not in batch.cache:
+                batch.cache['span'] = (int(batch.pos[0]), int(batch.endpos.max()))
+            lo, hi = batch.cache['span']
             if pad:
                 lo, hi = min(lo, s), max(hi, e)
         else:

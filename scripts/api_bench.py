@@ -12,6 +12,7 @@ from pysamstats_b200 import bamio, synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--mb', type=float, default=16.0)
+ap.add_argument('--no-csv', action='store_true', help='skip the write_csv timings (large runs)')
 args = ap.parse_args()
 G = int(args.mb * 1e6)
 dev = 'cuda' if torch.cuda.is_available() else 'cpu'
@@ -44,7 +45,7 @@ with tempfile.TemporaryDirectory() as tmp:
               'load_coverage_ext %.2f s | load_coverage_binned %.3f s | 100 kb region %.3f s'
               % (rep, t1 - t0, t2 - t1, len(a) / (t2 - t1) / 1e6, len(a), a.dtype.itemsize, t3 - t2, t4 - t3, t5 - t4))
     from pysamstats_b200.io import write_csv
-    for st in ('coverage', 'variation_strand'):
+    for st in (() if args.no_csv else ('coverage', 'variation_strand')):
         with open(os.path.join(tmp, 'out.tsv'), 'w') as f:
             t0 = time.time()
             write_csv(st, f, bam, fafile=fa if st == 'variation_strand' else None)
