@@ -555,12 +555,33 @@ __device__ __forceinline__ unsigned long long seg_sum64(unsigned mask, unsigned 
     return s0 + (s1 << 27) + (s2 << 54);
 }
 
+#ifndef BINNED_U
+#define BINNED_U 4
+#endif
+
 template <int STAT>
 __global__ void __launch_bounds__(256)
 k_binned_acc(pss_reads R, pss_binned_params P, unsigned long long *__restrict__ sums) {
     constexpr int NS = binned_nsums(STAT);
+    constexpr int U = BINNED_U;          // reads per lane: their record loads are all in flight before the first is used
+    constexpr bool NEED_T = STAT == PSS_COVERAGE_EXT_BINNED || STAT == PSS_TLEN_BINNED;
     const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * U) + lane;
+    int pos_[U], tlen_[U], mtid_[U];
+    uint32_t flag_[U], mapq_[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = base + 32 * u;
+        const bool live = i < R.n_reads;
+        pos_[u] = live ? R.pos[i] : 0;
+        flag_[u] = live ? R.flag[i] : 4u;
+        mapq_[u] = live ? R.mapq[i] : 0u;
+        tlen_[u] = (NEED_T && live) ? R.tlen[i] : 0;
+        mtid_[u] = (STAT == PSS_COVERAGE_EXT_BINNED && live) ? R.mtid[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+    const int64_t i = base + 32 * u;
     const bool live = i < R.n_reads;
     long long w = -1;                    // window of this lane's read
     unsigned c[10];                      // 32-bit safe contributions (counts, small sums, wrapping int sums)
@@ -570,11 +591,11 @@ k_binned_acc(pss_reads R, pss_binned_params P, unsigned long long *__restrict__ 
 #pragma unroll
     for (int k = 0; k < 4; ++k) d[k] = 0;
     if (live) {
-        const long long rel = (long long)R.pos[i] - P.start - 1;
-        w = rel < 0 ? 0 : rel / P.window_size;
+        const long long rel = (long long)pos_[u] - P.start - 1;
+        w = rel < 0 ? 0 : (rel >> 32) ? rel / P.window_size : (long long)((uint32_t)rel / (uint32_t)P.window_size);   // (64-bit division only when needed)
         if (w > P.n_bins - 1) w = P.n_bins - 1;
-        const uint32_t flag = R.flag[i];
-        const int mapq = R.mapq[i];
+        const uint32_t flag = flag_[u];
+        const int mapq = (int)mapq_[u];
         bool keep = !(flag & 4);                                   // every BinnedStat.recv
         if (P.min_mapq > 0 && mapq < P.min_mapq) keep = false;
         if (P.no_dup && (flag & 1024)) keep = false;
@@ -584,10 +605,10 @@ k_binned_acc(pss_reads R, pss_binned_params P, unsigned long long *__restrict__ 
                 c[0] = 1; c[1] = pp;
             } else if (STAT == PSS_COVERAGE_EXT_BINNED) {              // opt.pyx:1629-1662
                 const bool mun = flag & 8, mrev = flag & 32;
-                const int tlen = R.tlen[i];
+                const int tlen = tlen_[u];
                 c[0] = 1; c[1] = pp;
                 if (mun) c[2] = 1;
-                else if (R.tid != R.mtid[i]) c[3] = 1;
+                else if (R.tid != mtid_[u]) c[3] = 1;
                 else if (rev == mrev) c[4] = 1;
                 else if ((rev && tlen > 0) || (!rev && tlen < 0)) c[5] = 1;
                 int soft = 0;
@@ -605,7 +626,7 @@ k_binned_acc(pss_reads R, pss_binned_params P, unsigned long long *__restrict__ 
                 }
                 c[0] = 1;
             } else {                                                   // tlen opt.pyx:1801-1819
-                const long long t = R.tlen[i];
+                const long long t = tlen_[u];
                 c[0] = 1; d[0] = (unsigned long long)t; d[1] = (unsigned long long)(t * t);
                 if (pp) { c[1] = 1; d[2] = d[0]; d[3] = d[1]; }
             }
@@ -620,13 +641,23 @@ k_binned_acc(pss_reads R, pss_binned_params P, unsigned long long *__restrict__ 
     if (STAT == PSS_TLEN_BINNED) {
         // slots: n, n_pp, sum, sum_pp, sumsq, sumsq_pp
         EMIT(0, seg_sum32(mask, c[0])); EMIT(1, seg_sum32(mask, c[1]));
-        EMIT(2, seg_sum64(mask, d[0])); EMIT(3, seg_sum64(mask, d[2]));
-        EMIT(4, seg_sum64(mask, d[1])); EMIT(5, seg_sum64(mask, d[3]));
+        const long long t = (long long)d[0];
+        if (__all_sync(FULL, t > -8192 && t < 8192)) {
+            // ordinary insert sizes: 32 lanes of |t| < 2^13 sum below 2^18, their squares below 2^31 -- one REDUX per sum
+            // (the signed sums are sign extended; the 64-bit accumulators wrap like the reference's C arithmetic)
+            EMIT(2, (unsigned long long)(long long)(int)__reduce_add_sync(mask, (unsigned)d[0]));
+            EMIT(3, (unsigned long long)(long long)(int)__reduce_add_sync(mask, (unsigned)d[2]));
+            EMIT(4, seg_sum32(mask, (unsigned)d[1])); EMIT(5, seg_sum32(mask, (unsigned)d[3]));
+        } else {
+            EMIT(2, seg_sum64(mask, d[0])); EMIT(3, seg_sum64(mask, d[2]));
+            EMIT(4, seg_sum64(mask, d[1])); EMIT(5, seg_sum64(mask, d[3]));
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < NS; ++k) EMIT(k, seg_sum32(mask, c[k]));
     }
 #undef EMIT
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -772,7 +803,7 @@ template <int STAT>
 static void launch_binned_one(const pss_reads &R, const pss_binned_params &P, unsigned long long *sums, int32_t *out,
                               cudaStream_t s, int64_t *launches) {
     if (R.n_reads > 0) {
-        k_binned_acc<STAT><<<(unsigned)((R.n_reads + 255) / 256), 256, 0, s>>>(R, P, sums);
+        k_binned_acc<STAT><<<(unsigned)((R.n_reads + 256 * BINNED_U - 1) / (256 * BINNED_U)), 256, 0, s>>>(R, P, sums);
         LAUNCHED();
     }
     k_binned_fin<STAT><<<(unsigned)((P.n_bins + 255) / 256), 256, 0, s>>>(P, sums, out);

@@ -322,7 +322,9 @@ def test_rows_path_equals_column_path(stat, monkeypatch):
     cases = [dict(), dict(chrom='Pf3D7_01_v3', start=1000, end=20000, pad=True),
              dict(chrom='Pf3D7_02_v3', start=500, end=3000, truncate=True, one_based=True),
              dict(chrom='Pf3D7_03_v3', pad=True, min_mapq=20, no_dup=True),
-             dict(fields=['pos', 'reads_all', 'chrom']), dict(chrom='Pf3D7_01_v3', start=60000, end=70000)]
+             dict(fields=['pos', 'reads_all', 'chrom']), dict(chrom='Pf3D7_01_v3', start=60000, end=70000),
+             dict(chrom='Pf3D7_01_v3', start=3, end=40, pad=True, truncate=True),          # (no read starts this early)
+             dict(chrom='Pf3D7_02_v3', start=100, end=100, pad=True)]
     for chunk, table_chunk in ((None, None), ('1024', None), ('512', '4096')):
         for kw in cases:
             # PSS_HOST_CHUNK: result chunks inside one engine call; PSS_TABLE_CHUNK: position pieces = engine calls

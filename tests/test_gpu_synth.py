@@ -441,3 +441,24 @@ def test_rows_entry_beyond_16_bits(ctx):
         got = _run_rows(ctx, nb, ref, stat, 900, 1300, max_depth=1000000)
         assert len(got) == 100 and got.tobytes() == exp.tobytes(), stat
         assert got['reads_all'].max() == n
+
+
+def test_tlen_binned_small_and_huge_template_lengths(ctx, small):
+    # k_binned_acc<tlen> sums |tlen| < 8192 with one 32-bit REDUX per sum and everything else in 64-bit pieces:
+    # warps that mix both, the thresholds themselves, and the int32 extremes (sum of squares near 2^62 per read)
+    nb, ref, _ = small
+    nb = dict(nb)
+    t = nb['tlen'].copy()
+    rng = np.random.default_rng(7)
+    idx = rng.choice(len(t), len(t) // 150, replace=False)
+    t[idx] = rng.choice(np.array([8191, -8191, 8192, -8192, 2 ** 31 - 1, -2 ** 31 + 1, 100000, -70000, 0], 'i8'), len(idx)).astype('i4')
+    nb['tlen'] = t
+    reads = oracle_reads_from_arrays(nb)
+    for W in (300, 7):
+        p = ctx.binned_params('tlen', 0, G, W)
+        d = dict(nb)
+        d['qual'] = d['qual_off'] = d['name_prev'] = None
+        out = np.empty((len(config.value_fields_binned('tlen')), int(p.n_bins)), dtype=np.int32)
+        ctx.binned_host(_cabi.make_reads_struct(d), p, out)
+        pos, F = orc.binned_packed('tlen', reads, 0, G, W, W // 2)
+        assert np.array_equal(out.T, F), W
