@@ -494,7 +494,29 @@ k_gc(const uint8_t *__restrict__ ref, int64_t ref_start, int64_t ref_len, int64_
     const int nb = (int)(b1 - b0);
     int32_t *o = out + (b0 - start);
     const bool vec = (((uintptr_t)o) & 15) == 0;
-    for (int q = threadIdx.x * 4; q < nb; q += 1024) {
+    int q0 = 0;
+    if (fast && unclipped && vec) {
+        // eight positions per thread: one window count from the running counts, then the window slides over flag bits
+        // held in two registers (the 32 bases from the window's first / one-past-last base on)
+        const int n8 = nb & ~7;
+        for (int q = threadIdx.x * 8; q < n8; q += 2048) {
+            const int lo = shift + q, hi = lo + wsize;
+            const unsigned wl = __funnelshift_r(s_mask[lo >> 5], s_mask[(lo >> 5) + 1], lo & 31);
+            const unsigned wh = __funnelshift_r(s_mask[hi >> 5], s_mask[(hi >> 5) + 1], hi & 31);
+            int c = prefix(hi) - prefix(lo);
+            int g[8];
+            g[0] = s_tab[c];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) {
+                c += (int)((wh >> (k - 1)) & 1u) - (int)((wl >> (k - 1)) & 1u);
+                g[k] = s_tab[c];
+            }
+            __stcs((int4 *)(o + q), make_int4(g[0], g[1], g[2], g[3]));
+            __stcs((int4 *)(o + q + 4), make_int4(g[4], g[5], g[6], g[7]));
+        }
+        q0 = n8;
+    }
+    for (int q = q0 + threadIdx.x * 4; q < nb; q += 1024) {
         if (vec && q + 4 <= nb) {
             int4 g;
             if (fast && unclipped) {
