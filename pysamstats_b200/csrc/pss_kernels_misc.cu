@@ -580,12 +580,14 @@ __device__ __forceinline__ unsigned long long seg_sum64(unsigned mask, unsigned 
 #ifndef BINNED_U
 #define BINNED_U 4
 #endif
+// reads per lane of k_binned_acc (alignment_binned walks every CIGAR: one read per lane stays faster there)
+__host__ __device__ constexpr int binned_u(int stat) { return stat == PSS_ALIGNMENT_BINNED ? 1 : BINNED_U; }
 
 template <int STAT>
 __global__ void __launch_bounds__(256)
 k_binned_acc(pss_reads R, pss_binned_params P, unsigned long long *__restrict__ sums) {
     constexpr int NS = binned_nsums(STAT);
-    constexpr int U = BINNED_U;          // reads per lane: their record loads are all in flight before the first is used
+    constexpr int U = binned_u(STAT);    // reads per lane: their record loads are all in flight before the first is used
     constexpr bool NEED_T = STAT == PSS_COVERAGE_EXT_BINNED || STAT == PSS_TLEN_BINNED;
     const int lane = threadIdx.x & 31;
     const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * U) + lane;
@@ -825,7 +827,7 @@ template <int STAT>
 static void launch_binned_one(const pss_reads &R, const pss_binned_params &P, unsigned long long *sums, int32_t *out,
                               cudaStream_t s, int64_t *launches) {
     if (R.n_reads > 0) {
-        k_binned_acc<STAT><<<(unsigned)((R.n_reads + 256 * BINNED_U - 1) / (256 * BINNED_U)), 256, 0, s>>>(R, P, sums);
+        k_binned_acc<STAT><<<(unsigned)((R.n_reads + 256 * binned_u(STAT) - 1) / (256 * binned_u(STAT))), 256, 0, s>>>(R, P, sums);
         LAUNCHED();
     }
     k_binned_fin<STAT><<<(unsigned)((P.n_bins + 255) / 256), 256, 0, s>>>(P, sums, out);

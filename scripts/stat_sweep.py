@@ -55,8 +55,8 @@ for stat, ms, gp, gb in rows:
 print()
 print('%-22s %9s %12s' % ('statistic (binned)', 'ms', 'Greads/s'))
 for stat in config.binned_types:
-    if args.only:
-        break
+    if args.only and stat + '_binned' not in args.only.split(','):
+        continue
     nf = len(config.value_fields_binned(stat))
     p = ctx.binned_params(stat, 0, L, 300, ref=ref, ref_start=ref_lo, ref_len=int(ref.numel()))
     out = torch.empty((nf, int(p.n_bins)), dtype=torch.int32, device=dev)
