@@ -153,7 +153,8 @@ def format_rows_native(columns, delimiter, terminator):
     _host_check(lib, lib.pss_format_rows(n, k, (C.c_int32 * k)(*kinds), (C.c_void_p * k)(*srcs), (C.c_int32 * k)(*strides),
                                          (C.c_int32 * k)(*widths), d, len(d), t, len(t), 0, C.byref(out), C.byref(out_len)))
     try:
-        return C.string_at(out.value, out_len.value).decode('utf-8')
+        # decoded straight from the library's buffer (no intermediate bytes object)
+        return str((C.c_char * out_len.value).from_address(out.value), 'utf-8') if out_len.value else ''
     finally:
         lib.pss_host_free(out)
 
