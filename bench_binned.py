@@ -24,7 +24,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG=VERSION on the GPU
+        # boxes); stdout carries the one JSON line, so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     W = args.window_size
     per = int(args.interval_mb * 1e6) // (shard.TILE * W) * (shard.TILE * W) if False else int(args.interval_mb * 1e6) // 76800 * 76800
     genome = per * world                         # 76800 = lcm(256, 300): shard cuts are tile AND window aligned
