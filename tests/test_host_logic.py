@@ -424,3 +424,29 @@ def test_own_inflate_equals_zlib():
             pay, isize = raw[p + 12 + xlen:p + bsize - 8], struct.unpack_from('<I', raw, p + bsize - 4)[0]
             assert own(pay, isize) == (0, zlib.decompress(pay, -15))
             p += bsize
+
+
+def test_region_batch_equals_brute_force_overlap():
+    # BamFile.region_batch narrows the start-sorted contig by binary search (longest span behind the region start)
+    # and gathers only the selected records: same records, same ragged payloads as a mask over the whole contig
+    bam = bamio.BamFile(fx('test.bam'))
+    rng = np.random.default_rng(3)
+    for chrom in bam.references[:3]:
+        whole = bam.contig_batch(chrom)
+        clen = bam.lengths[bam.references.index(chrom)]
+        for _ in range(25):
+            start = int(rng.integers(-50, clen + 50))
+            end = start + int(rng.integers(0, 3000))
+            sub = bam.region_batch(chrom, start, end)
+            want = np.flatnonzero((whole.pos < end) & (whole.endpos > start))
+            assert sub.n_reads == len(want), (chrom, start, end)
+            assert np.array_equal(sub.pos, whole.pos[want]) and np.array_equal(sub.flag, whole.flag[want])
+            assert np.array_equal(sub.names, whole.names[want])
+            for data, off in (('cigar', 'cigar_off'), ('seq4', 'seq_off'), ('qual', 'qual_off')):
+                o, so = getattr(whole, off), getattr(sub, off)
+                if len(want):
+                    exp = np.concatenate([getattr(whole, data)[o[i]:o[i + 1]] for i in want.tolist()])
+                    assert np.array_equal(getattr(sub, data)[so[0]:so[-1]], exp), (chrom, start, end, data)
+                    assert np.array_equal(np.diff(so), (o[want + 1] - o[want]))
+            if sub.n_reads:
+                assert np.array_equal(sub.name_prev >= 0, np.array([n in set(sub.names[:j].tolist()) for j, n in enumerate(sub.names.tolist())]))
