@@ -450,3 +450,16 @@ def test_region_batch_equals_brute_force_overlap():
                     assert np.array_equal(np.diff(so), (o[want + 1] - o[want]))
             if sub.n_reads:
                 assert np.array_equal(sub.name_prev >= 0, np.array([n in set(sub.names[:j].tolist()) for j, n in enumerate(sub.names.tolist())]))
+
+
+def test_alloc_rows_is_lazy_address_space():
+    # the record buffer load_* fills from the front: writable, right dtype, and a big request costs no memory until
+    # it is touched (an untouched 8 GiB reservation must not fail or commit on this machine)
+    dt = np.dtype([('chrom', 'S12'), ('pos', '<i4'), ('x', '<i4')])
+    small = bamio.alloc_rows(1000, dt)
+    assert small.dtype == dt and len(small) == 1000 and small.flags.writeable
+    big = bamio.alloc_rows((8 << 30) // dt.itemsize, dt)
+    big[:3]['pos'] = [1, 2, 3]
+    part = big[:3]
+    assert part['pos'].tolist() == [1, 2, 3] and part.base is not None
+    del part, big
