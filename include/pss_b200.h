@@ -191,6 +191,9 @@ int32_t pss_binned_nfields(int32_t stat);
 int32_t pss_pileup_needs_ref(int32_t stat);
 /* 1 when the request reads base qualities (so qual/qual_off/name_prev are required) */
 int32_t pss_pileup_needs_qual(int32_t stat, int32_t min_baseq);
+/* positions per tile of the scatter kernel: callers that cut a range themselves (shards, chunks) align interior
+ * cuts to a multiple of this relative to `start`, so that no piece begins with a partial tile */
+int32_t pss_tile_positions(void);
 /* number of windows iter_binned_chrom yields for [start, end) (opt.pyx:2043-2102) */
 int64_t pss_binned_nbins(int64_t start, int64_t end, int32_t window_size);
 
@@ -283,9 +286,12 @@ int pss_pileup_host_rows(pss_ctx *ctx, const pss_reads *reads, const pss_pileup_
  * pos in (chunk start - max_span, chunk end), a sub-range of the start-sorted batch -- while
  * chunk k is computed, copied back and widened.  `max_span` >= max(bam_endpos - pos) over the
  * batch (the decoder knows it; a larger value only costs bandwidth).  outs[i] is
- * [n_fields][end - start] as for pss_pileup_host_multi.  Requests that read base qualities
- * (the mate links of name_prev index the whole batch) and coverage_gc fall back to one
- * pss_pileup_host_multi call.  HOST pointers, pinned for the copies to overlap (synchronous).
+ * [n_fields][end - start] as for pss_pileup_host_multi.  The results are those of ONE
+ * pss_pileup_host_multi call over the whole batch, always: requests that read base qualities
+ * (the mate links of name_prev index the whole batch), coverage_gc, and batches in which the
+ * order-dependent max_depth rule could refuse a read at all (max_depth reads start within
+ * max_span of some read: a chunk would not see the live reads of the previous one) are not cut
+ * but fall back to that one call.  HOST pointers, pinned for the copies to overlap (synchronous).
  */
 int pss_pileup_host_stream(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats,
                            const pss_pileup_params *params, int32_t *const *outs,

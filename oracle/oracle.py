@@ -319,8 +319,10 @@ def load_pileup(type, alignmentfile, fafile=None, chrom=None, start=None, end=No
     chroms = [chrom] if chrom is not None else list(bam.references)
     parts = []
     for c in chroms:
-        s, e = normalise_coords(bam, c, start if chrom is not None else None,
-                                end if chrom is not None else None, one_based)
+        # chrom=None: iter_pileup_default drops start / end (opt.pyx:2111-2112), iter_pileup_padded hands them to
+        # every contig (opt.pyx:1927-1932)
+        keep = chrom is not None or pad
+        s, e = normalise_coords(bam, c, start if keep else None, end if keep else None, one_based)
         reads = pack_region(bam, c, s, e)
         ref = fa.contig(c) if fa is not None else None
         pos, F, refcol = pileup_packed(type, reads, s, e, ref=ref, stepper=stepper, max_depth=max_depth,
@@ -346,8 +348,7 @@ def load_binned(type, alignmentfile, fafile=None, chrom=None, start=None, end=No
     chroms = [chrom] if chrom is not None else list(bam.references)
     parts = []
     for c in chroms:
-        s, e = normalise_coords(bam, c, start if chrom is not None else None,
-                                end if chrom is not None else None, one_based)
+        s, e = normalise_coords(bam, c, start, end, one_based)    # iter_binned keeps start / end per contig (opt.pyx:2009-2015)
         reads = pack_region(bam, c, s, e)
         ref = fa.contig(c) if fa is not None else None
         pos, F = binned_packed(type, reads, s, e, window_size, window_offset, min_mapq, no_dup, ref)

@@ -75,6 +75,7 @@ SYMBOLS = {
     'pss_binned_nfields': (C.c_int32, [C.c_int32]),
     'pss_pileup_needs_ref': (C.c_int32, [C.c_int32]),
     'pss_pileup_needs_qual': (C.c_int32, [C.c_int32, C.c_int32]),
+    'pss_tile_positions': (C.c_int32, []),
     'pss_binned_nbins': (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
     'pss_pileup': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssPileupParams), _P, _P, _P]),
     'pss_prepare': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

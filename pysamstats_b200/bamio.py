@@ -393,8 +393,14 @@ class BamFile(object):
     def _region_native(self, tid, start, end, bai):
         lib = host_lib()
         h = C.c_void_p()
-        _host_check(lib, lib.pss_bam_open_region(self.filename.encode(), bai.encode(), int(tid), int(start), int(end),
-                                                 self._threads, C.byref(h)))
+        rc = lib.pss_bam_open_region(self.filename.encode(), bai.encode(), int(tid), int(start), int(end),
+                                     self._threads, C.byref(h))
+        if rc == -6:
+            # the index does not belong to this file (stale / truncated .bai): decode the whole file instead
+            import warnings
+            warnings.warn('ignoring BAM index %s: %s' % (bai, lib.pss_host_error().decode('ascii', 'replace')))
+            return None
+        _host_check(lib, rc)
         try:
             b, _ = self._decode(lib, h)
         finally:
@@ -512,7 +518,9 @@ class BamFile(object):
             full = start <= 0 and end >= self.lengths[self._tid_of[chrom]] and len(self.references) == 1
             if bai is not None and not full and \
                     os.path.getsize(self.filename) >= int(os.environ.get('PSS_BAI_MIN_BYTES', 32 << 20)):
-                return self._region_native(self._tid_of[chrom], start, end, bai)
+                b = self._region_native(self._tid_of[chrom], start, end, bai)
+                if b is not None:
+                    return b
         b = self.contig_batch(chrom)
         n = b.n_reads
         if n == 0:
@@ -648,11 +656,12 @@ class FastaFile(object):
         return self._index[chrom][0] if chrom in self._index else 0
 
     def contig(self, chrom):
-        """Whole contig as a uint8 array, case preserved (empty if unknown)."""
+        """Whole contig as a uint8 array, case preserved.  An unknown contig raises KeyError, as
+        ``pysam.FastaFile.fetch`` does where the reference asks for its bases (``opt.pyx:1989``)."""
         if self._cache[0] == chrom:
             return self._cache[1]
         if chrom not in self._index:
-            a = np.zeros(0, dtype=np.uint8)
+            raise KeyError("sequence '%s' not present" % (chrom,))
         else:
             length, off, lb, lw = self._index[chrom]
             nlines = (length + lb - 1) // lb if lb else 0

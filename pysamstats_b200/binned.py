@@ -81,11 +81,12 @@ def load_binned(type, alignmentfile, fafile=None, chrom=None, start=None, end=No
     """
     # like the reference (binned.py:106-109) an unknown type surfaces as AttributeError here
     default_dtype = getattr(config, 'dtype_' + type + '_binned')
-    return util.load_stats(functools.partial(_binned_tables, type), user_dtype=dtype,
-                           default_dtype=default_dtype, user_fields=fields, alignmentfile=alignmentfile,
-                           fafile=fafile, chrom=chrom, start=start, end=end, one_based=one_based,
-                           window_size=window_size, window_offset=window_offset, min_mapq=min_mapq,
-                           no_dup=no_dup)
+    statfun = functools.partial(stat_binned, type)
+    statfun._pss_tables = functools.partial(_binned_tables, type)
+    return util.load_stats(statfun, user_dtype=dtype, default_dtype=default_dtype, user_fields=fields,
+                           alignmentfile=alignmentfile, fafile=fafile, chrom=chrom, start=start, end=end,
+                           one_based=one_based, window_size=window_size, window_offset=window_offset,
+                           min_mapq=min_mapq, no_dup=no_dup)
 
 
 stat_binned.__doc__ = stat_binned.__doc__.format(params=_doc_params)

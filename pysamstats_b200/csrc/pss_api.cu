@@ -108,6 +108,7 @@ extern "C" int32_t pss_pileup_needs_ref(int32_t stat) {
 extern "C" int32_t pss_pileup_needs_qual(int32_t stat, int32_t min_baseq) {
     return (stat >= PSS_BASEQ && stat <= PSS_BASEQ_EXT_STRAND) || min_baseq > 0;
 }
+extern "C" int32_t pss_tile_positions(void) { return PSS_TTILE; }
 extern "C" int64_t pss_binned_nbins(int64_t start, int64_t end, int32_t window_size) {
     if (window_size <= 0) return -1;
     int64_t span = end - start;
@@ -937,6 +938,17 @@ extern "C" int pss_pileup_host_stream(pss_ctx *ctx, const pss_reads *reads, int3
     // name_prev indexes the whole batch, which a sub-range view cannot express: one call then
     if (need_qual || max_span < 1 || npos <= chunk_positions || reads->n_reads == 0)
         return pss_pileup_host_multi(ctx, reads, n_stats, P, outs, rowmasks);
+    {
+        // The depth cap (bam_plp_push) is order dependent: the first reads of a chunk would not see
+        // the live reads of the previous one.  A read can only be refused when max_depth earlier reads start within
+        // one maximal read span before it (the test of k_safe, on the host); if any read could be, the range is
+        // not cut -- one call over the whole batch, whose admission pass sees every read in file order.
+        const int64_t nr = reads->n_reads, maxcnt = P[0].max_depth ? P[0].max_depth : 8000;
+        const int32_t *ps = reads->pos;
+        bool refusable = false;
+        for (int64_t i = maxcnt; i < nr && !refusable; ++i) refusable = (int64_t)ps[i] - (int64_t)ps[i - maxcnt] <= max_span;
+        if (refusable) return pss_pileup_host_multi(ctx, reads, n_stats, P, outs, rowmasks);
+    }
     for (int i = 0; i < n_stats; ++i)
         if (P[i].stat == PSS_COVERAGE_GC) return pss_pileup_host_multi(ctx, reads, n_stats, P, outs, rowmasks);
     CU(cudaSetDevice(ctx->device));

@@ -299,13 +299,18 @@ static bool read_file(const char *path, std::vector<uint8_t> &out) {
 }
 
 // chunks of reference `tid` that can hold records overlapping [beg, end), sorted and merged
-static int bai_chunks(const char *bai_path, int32_t tid, int64_t beg, int64_t end, std::vector<Chunk> &out) {
+// (an index that cannot belong to this file -- other number of references, offsets beyond its end: a stale .bai --
+// is refused with -6 and the caller decodes the whole file instead)
+static int bai_chunks(const char *bai_path, int32_t tid, int64_t beg, int64_t end, std::vector<Chunk> &out,
+                      int32_t bam_n_ref = -1, int64_t bam_size = -1) {
     std::vector<uint8_t> d;
     if (!read_file(bai_path, d)) return fail(-2, "cannot read index %s", bai_path);
     const int64_t n = (int64_t)d.size();
     if (n < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return fail(-6, "not a BAI index: %s", bai_path);
     const int32_t n_ref = rdi32(&d[4]);
     if (tid < 0 || tid >= n_ref) return fail(-6, "reference %d is not in the index (%d references)", tid, n_ref);
+    if (bam_n_ref >= 0 && n_ref != bam_n_ref)
+        return fail(-6, "index %s has %d references, the BAM header %d: stale index", bai_path, n_ref, bam_n_ref);
     std::vector<uint32_t> want;
     reg2bins(beg, end, want);
     std::sort(want.begin(), want.end());
@@ -345,6 +350,10 @@ static int bai_chunks(const char *bai_path, int32_t tid, int64_t beg, int64_t en
         }
         p += 8ll * n_intv;
     }
+    if (bam_size >= 0)
+        for (const Chunk &c : out)
+            if ((int64_t)(c.beg >> 16) > bam_size || (int64_t)(c.end >> 16) > bam_size)
+                return fail(-6, "index %s points beyond the end of the BAM file: stale index", bai_path);
     std::sort(out.begin(), out.end(), [](const Chunk &a, const Chunk &b) { return a.beg < b.beg; });
     // merge chunks that overlap or sit within 64 KiB of file of each other: records read on the
     // way are filtered by position anyway, and no BGZF block is inflated twice
@@ -462,7 +471,11 @@ extern "C" int pss_bam_open_region(const char *path, const char *bai_path, int32
     if (tid >= (int32_t)b->ref_names.size()) return fail(-1, "reference %d out of range", tid);
     std::string bai = bai_path ? bai_path : std::string(path) + ".bai";
     std::vector<Chunk> chunks;
-    int rc = bai_chunks(bai.c_str(), tid, beg, end, chunks);
+    // a negative start (one_based=True with start=0 gives -1, opt.pyx:2116) selects what start 0 selects; the
+    // linear index has no window -1 and reg2bins no bins below 0
+    if (beg < 0) beg = 0;
+    if (end < beg + 1) end = beg + 1;
+    int rc = bai_chunks(bai.c_str(), tid, beg, end, chunks, (int32_t)b->ref_names.size(), fsize);
     if (rc != 0) return rc;
     // ---- the compressed bytes of every chunk, its block table
     struct Piece { int64_t file_lo, file_hi; size_t comp_off; int64_t first_blk, n_blk; int64_t start, stop; };   // start / stop: offsets in raw

@@ -140,11 +140,16 @@ def _pileup_plan(stat, alignmentfile, fafile, pad, chrom, start, end, one_based,
         contigs = [chrom]
     else:
         contigs = list(bam.references)
-        start = end = None                                        # opt.pyx:2111-2112
+        if not pad:
+            # iter_pileup_default hands chrom=None to normalise_coords, which drops start / end (opt.pyx:2111-2112);
+            # iter_pileup_padded forwards the caller's start / end to every contig (opt.pyx:1927-1932)
+            start = end = None
     for c in contigs:
         if pad:
             assert c is not None, 'chromosome is None'
         s, e = normalise_coords(bam, c, start, end, one_based)
+        if s > e:
+            raise ValueError('invalid coordinates: start (%i) > stop (%i)' % (s, e))     # pysam parse_region
         batch = bam.region_batch(c, s, e)
         n = batch.n_reads
         if n == 0 and not pad:
@@ -386,11 +391,12 @@ def binned_tables(stat, alignmentfile, fafile=None, chrom=None, window_size=300,
     if chrom is not None:
         contigs = [chrom]
     else:
-        contigs = list(bam.references)
-        start = end = None
+        contigs = list(bam.references)       # iter_binned forwards start / end to every contig (opt.pyx:2009-2015)
     for c in contigs:
         assert c is not None, 'chromosome is None'
         s, e = normalise_coords(bam, c, start, end, one_based)
+        if s > e:
+            raise ValueError('invalid coordinates: start (%i) > stop (%i)' % (s, e))     # pysam parse_region
         batch = bam.region_batch(c, s, e)
         refseq = fa.contig(c) if need_ref else None
         params = ctx.binned_params(name, s, e, window_size, min_mapq=min_mapq, no_dup=no_dup,

@@ -119,11 +119,12 @@ def load_pileup(type, alignmentfile, fafile=None, chrom=None, start=None, end=No
         default_dtype = getattr(config, 'dtype_' + type)
     except (AttributeError, TypeError):
         raise ValueError('unsupported statistics type: %r' % (type,))
-    return util.load_stats(functools.partial(_pileup_tables, type), rowsfun=functools.partial(_pileup_rows, type),
-                           user_dtype=dtype,
-                           default_dtype=default_dtype, user_fields=fields, alignmentfile=alignmentfile,
-                           fafile=fafile, chrom=chrom, start=start, end=end, one_based=one_based,
-                           truncate=truncate, stepper=stepper, pad=pad, max_depth=max_depth,
+    statfun = functools.partial(stat_pileup, type)
+    statfun._pss_tables = functools.partial(_pileup_tables, type)     # column tables / packed records of the same
+    statfun._pss_rows = functools.partial(_pileup_rows, type)         # statistic straight from the engine
+    return util.load_stats(statfun, user_dtype=dtype, default_dtype=default_dtype, user_fields=fields,
+                           alignmentfile=alignmentfile, fafile=fafile, chrom=chrom, start=start, end=end,
+                           one_based=one_based, truncate=truncate, stepper=stepper, pad=pad, max_depth=max_depth,
                            window_size=window_size, window_offset=window_offset, min_mapq=min_mapq,
                            min_baseq=min_baseq, no_del=no_del, no_dup=no_dup)
 

@@ -13,21 +13,30 @@ What crosses a shard boundary besides the halo reads:
   the live depth reaches ``max_depth``; shards must not be cut inside such a run.
   ``safe_cut`` moves a boundary to the nearest position where the live depth is below the
   cap (ordinary WGS never saturates, so boundaries stay where they are).
-* the mate-overlap quality rewrite pairs reads by QNAME; both mates of a pair overlap every
-  position the rewrite touches, so a shard that holds all reads overlapping its interval
-  holds every pair whose rewrite is visible in it.
+* the mate-overlap quality rewrite pairs reads by QNAME in push order.  Both mates of a pair overlap
+  every position the rewrite touches, but WHICH reads of a name pair up depends on every earlier read
+  of that name (a three-read chain pairs differently when its first read is missing), so a shard that
+  only holds the reads overlapping its interval can pair the rest of a chain differently.  Requests
+  that read base qualities (``pss_pileup_needs_qual``: the baseq* statistics, any ``min_baseq > 0``)
+  are therefore NOT cut by these helpers: ``plan_intervals(..., need_qual=True)`` returns one shard
+  holding the whole range (the same rule as ``opt._position_chunks``).
 """
 import numpy as np
 
-TILE = 256   # PSS_TILE of the pileup kernel: shard boundaries are tile aligned
+TILE = 512   # pss_tile_positions() (PSS_TTILE, the scatter kernel's tile): interior shard boundaries are tile
+             # aligned, so no shard starts with a partial tile (tests/test_host_logic.py checks it against the library)
 
 
-def plan_intervals(start, end, n_shards, align=TILE):
+def plan_intervals(start, end, n_shards, align=TILE, need_qual=False):
     """Cut [start, end) into n_shards contiguous intervals of (almost) equal length whose
     inner boundaries are multiples of ``align`` relative to ``start``.
-    Returns a list of (lo, hi); empty intervals (lo == hi) are possible for tiny regions."""
+    Returns a list of (lo, hi); empty intervals (lo == hi) are possible for tiny regions.
+    With ``need_qual`` (the request reads base qualities) the range is not cut: the first shard
+    gets all of it, the others are empty (see the module docstring)."""
     if n_shards < 1:
         raise ValueError('n_shards must be >= 1')
+    if need_qual:
+        return [(int(start), max(int(start), int(end)))] + [(max(int(start), int(end)),) * 2] * (n_shards - 1)
     span = max(0, int(end) - int(start))
     cuts = [int(start)]
     for k in range(1, n_shards):

@@ -68,10 +68,14 @@ def determine_max_seqid(alignmentfile):
     return max(len(x) for x in bamio.open_bam(alignmentfile).references)
 
 
-def load_stats(tablefun, default_dtype, user_dtype, user_fields, rowsfun=None, **kwargs):
-    """Run ``tablefun(**kwargs)`` (a generator of per-contig column tables, see
-    ``opt.pileup_tables``) and assemble the structured array ``load_*`` returns.  With ``rowsfun``
-    (``opt.pileup_rows``) the engine packs the records itself whenever the record type allows it."""
+def load_stats(statfun, default_dtype, user_dtype, user_fields, **kwargs):
+    """Assemble the structured array ``load_*`` returns (``util.py:31-73``, same signature).
+
+    ``statfun(**kwargs)`` is a generator of dicts, as in the reference.  The engine's own
+    ``stat_*`` partials carry two attributes, ``_pss_tables`` (a generator of per-contig column
+    tables, ``opt.pileup_tables``) and optionally ``_pss_rows`` (``opt.pileup_rows``: records packed
+    by the engine's host pipeline); for them the array is filled column-wise / by the engine instead
+    of row by row.  Any other ``statfun`` takes the reference's path (``flatten`` + ``np.fromiter``)."""
     default_fields = [t[0] for t in default_dtype]
     if user_fields is None:
         fields = default_fields
@@ -86,6 +90,12 @@ def load_stats(tablefun, default_dtype, user_dtype, user_fields, rowsfun=None, *
     single = len(fields) == 1
     dt = np.dtype(dtype[fields[0]] if single else [(f, dtype[f]) for f in fields])
 
+    tablefun = getattr(statfun, '_pss_tables', None)
+    rowsfun = getattr(statfun, '_pss_rows', None)
+    if tablefun is None:
+        # a caller-supplied generator of dicts: util.py:61-71
+        a = np.fromiter(flatten(statfun(**kwargs), *fields), dtype=dt)
+        return a if single else a.view(np.recarray)
     if rowsfun is not None and not single and os.environ.get('PSS_NO_ROWS') is None:
         recs = rowsfun(dt, **kwargs)
         if recs is not None:

@@ -352,3 +352,69 @@ def test_rows_path_declines_what_it_cannot_write():
     assert np.array_equal(a['reads_all'], b['reads_all']) and np.array_equal(a['pos'], b['pos'])
     c = pysamstats.load_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=0, end=2000, fields='reads_all')
     assert c.dtype == np.dtype('i4') and np.array_equal(c, b['reads_all'])
+
+
+# ---- round-2 boundary fixes ---------------------------------------------------------------------------
+
+def test_chrom_none_keeps_start_end_for_pad_and_binned(obam, ofa):
+    # iter_pileup_padded / iter_binned hand the caller's start / end to every contig (opt.pyx:1927-1932, :2009-2015);
+    # only the unpadded pileup drops them with chrom=None (opt.pyx:2111-2112)
+    for stat in ('coverage', 'variation'):
+        kw = dict(pad=True, start=1000, end=3000)
+        a = _load(stat, 'test', **kw)
+        assert_recarrays_equal(_oracle(stat, obam, ofa, 'test', **kw), a, '%s %r' % (stat, kw))
+        kw = dict(start=1000, end=3000)                    # no pad: whole contigs
+        assert_recarrays_equal(_oracle(stat, obam, ofa, 'test', **kw), _load(stat, 'test', **kw), '%s %r' % (stat, kw))
+    a = pysamstats.load_coverage(fx('test.bam'), pad=True, start=1000, end=3000, truncate=True)
+    assert len(a) == 2000 * len(obam['test'].references) and a['pos'].min() == 1000 and a['pos'].max() == 2999
+    for stat in config.binned_types:
+        kw = dict(start=1000, end=5000, window_size=250)
+        e = orc.load_binned(stat, obam['test'], ofa, **kw)
+        a = getattr(pysamstats, 'load_%s_binned' % stat)(fx('test.bam'), fafile=fx('ref.fa'), **kw)
+        assert_recarrays_equal(e, a, '%s_binned %r' % (stat, kw))
+        assert len(a) == 16 * len(obam['test'].references)
+
+
+def test_one_based_start_zero_through_the_index(obam, ofa, monkeypatch):
+    # one_based=True, start=0 normalises to -1 (opt.pyx:2116): the BAI query treats it as 0
+    kw = dict(chrom='Pf3D7_01_v3', start=0, end=3000, one_based=True)
+    e = _oracle('coverage', obam, ofa, 'test', **kw)
+    monkeypatch.setenv('PSS_BAI_MIN_BYTES', '0')
+    from pysamstats_b200 import bamio
+    bamio._bam_cache.clear()
+    assert_recarrays_equal(e, _load('coverage', 'test', **kw), 'one_based start=0')
+
+
+def test_unknown_fasta_contig_raises(tmp_path):
+    fa = tmp_path / 'other.fa'
+    fa.write_text('>someone_else\nACGTACGT\n')
+    with pytest.raises(KeyError):
+        pysamstats.load_variation(fx('test.bam'), str(fa), chrom='Pf3D7_01_v3', start=1000, end=1100)
+
+
+def test_write_hdf5_through_the_engine(tmp_path, monkeypatch):
+    # the reference's own test (pysamstats/test/test_io.py:14-40) with the stand-in for PyTables (tests/fake_tables.py),
+    # plus the values: the dataset equals load_*
+    import sys
+    import fake_tables
+    monkeypatch.setitem(sys.modules, 'tables', fake_tables)
+    label = 'AS2_scf7180000696055'
+    bam = fx('longcontignames.bam')
+    class Foreign(object):
+        filename = bam
+    for dtype, alignment, expect in ((None, Foreign(), len(label)), ({'chrom': 'S20'}, Foreign(), 20), ({'chrom': 'S20'}, bam, 20)):
+        out = str(tmp_path / 'c.h5')
+        pysamstats.io.write_hdf5('coverage', out, alignment, chrom=label, dtype=dtype)
+        with fake_tables.open_file(out, mode='r') as h5:
+            assert h5.root.data.dtype['chrom'].itemsize == expect
+            a = h5.root.data.read()
+        e = pysamstats.load_coverage(bam, chrom=label, dtype=dtype)
+        assert a.dtype == e.dtype and np.array_equal(a, np.asarray(e))
+    out = str(tmp_path / 'v.h5')
+    pysamstats.io.write_hdf5('variation_strand', out, fx('test.bam'), fafile=fx('ref.fa'), chrom='Pf3D7_02_v3', start=500, end=9000,
+                          hdf5_chunksize=1 << 16, hdf5_dataset='vs')
+    pysamstats.io.write_hdf5('tlen_binned', out, fx('test.bam'), hdf5_dataset='tb')
+    with fake_tables.open_file(out, mode='r') as h5:
+        e = pysamstats.load_variation_strand(fx('test.bam'), fx('ref.fa'), chrom='Pf3D7_02_v3', start=500, end=9000)
+        assert np.array_equal(h5.root.vs.read(), np.asarray(e))
+        assert np.array_equal(h5.root.tb.read(), np.asarray(pysamstats.load_tlen_binned(fx('test.bam'))))
