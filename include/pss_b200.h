@@ -175,9 +175,14 @@ int64_t pss_launch_count(const pss_ctx *ctx);
  * (bench.py's e2e.h2d_bytes_per_step / d2h_bytes_per_step). */
 void pss_transfer_bytes(const pss_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* Average device time (ms, CUDA events on the launch stream) of the pileup kernel of
- * statistic `stat` (enum pss_pileup_stat, -1 = any) over its launches since the last call;
- * those launches are then forgotten.  Used by bench.py for roofline.achieved.
- * Returns < 0 if there were none. */
+ * statistic `stat` (enum pss_pileup_stat; or one of the PSS_KTAG_* kernels below; -1 = any) over
+ * its launches since the last call; those launches are then forgotten.  Used by bench.py for
+ * roofline.achieved.  Returns < 0 if there were none. */
+#define PSS_KTAG_GC 100          /* k_gc: the sliding-window GC% column of coverage_gc */
+#define PSS_KTAG_PREP 101        /* k_prep + the depth-cap kernels (one preparation of a batch) */
+#define PSS_KTAG_BINNED_ACC 110  /* k_binned_acc: the one pass over the read records of a binned call */
+#define PSS_KTAG_BINNED_FIN 111  /* k_binned_fin */
+#define PSS_KTAG_BINNED_GC 112   /* k_binned_gc */
 double pss_pileup_kernel_ms(pss_ctx *ctx, int32_t stat, int64_t *n_launches);
 /* Enable/disable the per-launch event timing above (default off: no overhead). */
 void pss_set_kernel_timing(pss_ctx *ctx, int enabled);
@@ -330,6 +335,20 @@ int pss_binned(pss_ctx *ctx, const pss_reads *reads, const pss_binned_params *pa
 /* Same with HOST pointers (synchronous). */
 int pss_binned_host(pss_ctx *ctx, const pss_reads *reads, const pss_binned_params *params,
                     int32_t *out);
+
+/*
+ * Several binned statistics of one region in ONE pass over the read records -- the reference
+ * runs iter_binned_chrom once per statistic (opt.pyx:2026-2102, one BinnedStat per call); the
+ * read stream is what bounds the kernel, so a sweep such as coverage_binned + mapq_binned +
+ * tlen_binned reads pos / flag / mapq / tlen once instead of three times.  params[i] / outs[i]
+ * describe statistic i (layout of pss_binned); every statistic at most once, and all params
+ * share start, end, window_size, n_bins, min_mapq, no_dup (the reference span is taken from the
+ * first statistic that needs one).  DEVICE pointers / HOST pointers (synchronous).
+ */
+int pss_binned_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_binned_params *params,
+                     int32_t *const *outs, void *stream);
+int pss_binned_host_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_binned_params *params,
+                          int32_t *const *outs);
 
 #ifdef __cplusplus
 }

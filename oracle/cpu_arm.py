@@ -8,7 +8,9 @@ bench line and for ``bench.py --impl reference``; never on the product path.
 
 Each worker generates its own chunk of the synthetic 30x WGS workload (same generator and
 parameters as the GPU arm, CPU random stream), then runs ``steps`` timed passes of
-stat_variation_strand + stat_coverage_ext over it between two barriers.
+stat_variation_strand + stat_coverage_ext over it between two barriers -- or, with
+``workload='binned'``, of the binned sweep of BASELINE.json configs[4]: stat_coverage_gc
+(a pileup) + coverage_binned + mapq_binned + tlen_binned with window_size 300.
 """
 import multiprocessing as mp
 import os
@@ -18,6 +20,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 STATS = (('variation_strand', True), ('coverage_ext', False))
+BINNED_SWEEP = ('coverage', 'mapq', 'tlen')          # + the pileup statistic coverage_gc; window_size 300
 
 
 def usable_cores(cap=128):
@@ -46,7 +49,7 @@ def _pack(nb):
     return r
 
 
-def _worker(i, n_workers, chunk, depth, read_len, steps, warmup, bar, q):
+def _worker(i, n_workers, chunk, depth, read_len, steps, warmup, bar, q, workload='pileup'):
     try:
         if ROOT not in sys.path:
             sys.path.insert(0, ROOT)
@@ -72,9 +75,16 @@ def _worker(i, n_workers, chunk, depth, read_len, steps, warmup, bar, q):
         for _ in range(warmup + steps):
             bar.wait()
             rows = 0
-            for stat, withref in STATS:
-                pos, F, rc = orc.pileup_packed(stat, reads, lo, hi, ref=refb if withref else None, truncate=True)
+            if workload == 'binned':
+                pos, F, rc = orc.pileup_packed('coverage_gc', reads, lo, hi, ref=refb, truncate=True, window_size=300)
                 rows += len(pos)
+                for stat in BINNED_SWEEP:
+                    pos, F = orc.binned_packed(stat, reads, lo, hi, 300, 150, ref=refb)
+                    rows += len(pos)
+            else:
+                for stat, withref in STATS:
+                    pos, F, rc = orc.pileup_packed(stat, reads, lo, hi, ref=refb if withref else None, truncate=True)
+                    rows += len(pos)
             bar.wait()
         q.put(('done', i, rows))
     except BaseException as e:   # noqa: BLE001 -- report and release the barrier
@@ -85,13 +95,13 @@ def _worker(i, n_workers, chunk, depth, read_len, steps, warmup, bar, q):
             pass
 
 
-def run(cores=None, chunk=1000000, steps=1, warmup=0, depth=30, read_len=150):
+def run(cores=None, chunk=1000000, steps=1, warmup=0, depth=30, read_len=150, workload='pileup'):
     """Returns dict(step_seconds=[...], positions_per_step, reads_per_step, cores, chunk)."""
     cores = cores or usable_cores()
     ctx = mp.get_context('spawn')
     bar = ctx.Barrier(cores + 1)
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(i, cores, chunk, depth, read_len, steps, warmup, bar, q), daemon=True)
+    procs = [ctx.Process(target=_worker, args=(i, cores, chunk, depth, read_len, steps, warmup, bar, q, workload), daemon=True)
              for i in range(cores)]
     for p in procs:
         p.start()

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get('PSS_LIB') or os.path.join(HERE, 'csrc', 'libpss_b200.
 PSS_OK, PSS_EINVAL, PSS_ECUDA, PSS_ENOMEM, PSS_EUNSORTED, PSS_ETOOLONG = 0, -1, -2, -3, -4, -5
 PSS_FLAG_GENERIC_KERNEL = 1
 PSS_FLAG_LONG_READS = 2
+KTAG_GC, KTAG_PREP, KTAG_BINNED_ACC, KTAG_BINNED_FIN, KTAG_BINNED_GC = 100, 101, 110, 111, 112
 
 PILEUP_STATS = ('coverage', 'coverage_strand', 'coverage_ext', 'coverage_ext_strand', 'variation',
                 'variation_strand', 'tlen', 'tlen_strand', 'mapq', 'mapq_strand', 'baseq',
@@ -91,6 +92,8 @@ SYMBOLS = {
     'pss_overlap_tweak': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P, _P]),
     'pss_binned': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssBinnedParams), _P, _P]),
     'pss_binned_host': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssBinnedParams), _P]),
+    'pss_binned_multi': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.POINTER(PssBinnedParams), C.POINTER(_P), _P]),
+    'pss_binned_host_multi': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.POINTER(PssBinnedParams), C.POINTER(_P)]),
 }
 
 _lib = None
@@ -328,6 +331,18 @@ class Context(object):
     def binned(self, reads_struct, params, out, stream=None):
         self.check(self.lib.pss_binned(self.h, C.byref(reads_struct), C.byref(params), _addr(out), stream))
 
+    def binned_multi(self, reads_struct, params_list, outs, stream=None):
+        n = len(params_list)
+        pa = (PssBinnedParams * n)(*params_list)
+        oa = (_P * n)(*[_addr(o) for o in outs])
+        self.check(self.lib.pss_binned_multi(self.h, C.byref(reads_struct), n, pa, oa, stream))
+
+    def binned_host_multi(self, reads_struct, params_list, outs):
+        n = len(params_list)
+        pa = (PssBinnedParams * n)(*params_list)
+        oa = (_P * n)(*[_addr(o) for o in outs])
+        self.check(self.lib.pss_binned_host_multi(self.h, C.byref(reads_struct), n, pa, oa))
+
     def admit(self, reads_struct, stepper, max_depth, admitted, stream=None):
         self.check(self.lib.pss_admit(self.h, C.byref(reads_struct), int(stepper), int(max_depth),
                                       _addr(admitted), stream))
@@ -368,11 +383,14 @@ def default_device():
     return 0
 
 
-def get_context(device=None):
-    """Process-wide context per device (created on first use; fails loudly without a GPU)."""
+def get_context(device=None, slot=0):
+    """Process-wide context per (device, slot) (created on first use; fails loudly without a GPU).  A context serves
+    one host thread at a time; ``slot`` > 0 gives the further threads of a multi-shard call their own context on a
+    device that is listed more than once (``PSS_GPUS=0,0``)."""
     if device is None:
         device = default_device()
-    ctx = _contexts.get(device)
+    key = (int(device), int(slot))
+    ctx = _contexts.get(key)
     if ctx is None:
-        ctx = _contexts[device] = Context(device)
+        ctx = _contexts[key] = Context(device)
     return ctx

@@ -243,6 +243,27 @@ static int check_reads(pss_ctx *ctx, const pss_reads *R, bool need_qual) {
     return PSS_OK;
 }
 
+static cudaEvent_t next_event(pss_ctx *ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+// a pair of timing events tagged `tag` (a pileup statistic id or a PSS_KTAG_* constant), or NULLs when timing is off
+static void timing_pair(pss_ctx *ctx, int tag, cudaEvent_t *e0, cudaEvent_t *e1) {
+    *e0 = *e1 = nullptr;
+    if (!ctx->timing) return;
+    cudaEvent_t a = next_event(ctx), b = next_event(ctx);
+    if (!a || !b) return;
+    size_t pair = ctx->ev_used / 2 - 1;
+    if (ctx->ev_stat.size() <= pair) ctx->ev_stat.resize(pair + 1);
+    ctx->ev_stat[pair] = tag;
+    *e0 = a; *e1 = b;
+}
+
 // k_prep + depth cap (+ overlap tweak): everything that depends on the batch and on the
 // read-level parameters but not on the output position range.
 static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_depth, int min_mapq, int no_dup,
@@ -252,9 +273,13 @@ static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_
     if ((rc = ensure(ctx, ctx->ri, sizeof(RInfo) * (size_t)n)) != PSS_OK) return rc;
     RInfo *ri = (RInfo *)ctx->ri.p;
     SmallState *st = (SmallState *)ctx->small.p;
+    cudaEvent_t p0, p1;
+    timing_pair(ctx, PSS_KTAG_PREP, &p0, &p1);
+    if (p0) CU(cudaEventRecord(p0, s));
     CU(launch_prep(*R, stepper, min_mapq, no_dup, ri, st, s, &ctx->launches));
     int maxcnt = max_depth ? max_depth : 8000;   // A.0
     CU(launch_admit(ri, R->pos, n, maxcnt, st, s, &ctx->launches));
+    if (p1) CU(cudaEventRecord(p1, s));
     ctx->desc_start = ctx->desc_end = -1;   // tile descriptors belong to the previous batch
     ctx->lowq_minq = -1;
     if (need_qual && n > 0) {
@@ -273,15 +298,6 @@ static int prepare_batch(pss_ctx *ctx, const pss_reads *R, int stepper, int max_
         CU(launch_overlap(*R, ri, qual_dst, pair_dst, (int32_t *)ctx->next.p, s, &ctx->launches));
     }
     return PSS_OK;
-}
-
-static cudaEvent_t next_event(pss_ctx *ctx) {
-    if (ctx->ev_used == ctx->ev_pool.size()) {
-        cudaEvent_t e;
-        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
-        ctx->ev_pool.push_back(e);
-    }
-    return ctx->ev_pool[ctx->ev_used++];
 }
 
 // the pileup kernel (+ gc) for output positions [start, end); out[f * stride + (p - start)]
@@ -317,15 +333,8 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.out = out; a.out_stride = stride; a.rowmask = rowmask;
     a.narrow = (tile && tile_kernel_counting(P->stat)) ? narrow : 0;      // 1: uint16 columns, 2: uint8 columns + overflow flag
     a.ovf8 = ovf8;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ctx->timing) {
-        e0 = next_event(ctx); e1 = next_event(ctx);
-        if (e0 && e1) {
-            size_t pair = ctx->ev_used / 2 - 1;
-            if (ctx->ev_stat.size() <= pair) ctx->ev_stat.resize(pair + 1);
-            ctx->ev_stat[pair] = P->stat;
-        } else e0 = e1 = nullptr;
-    }
+    cudaEvent_t e0, e1;
+    timing_pair(ctx, P->stat, &e0, &e1);
     if (tile) {
         if ((rc = ensure(ctx, ctx->tdesc, tile_desc_bytes(ntiles))) != PSS_OK) return rc;
         if ((rc = ensure(ctx, ctx->refpack, tile_refpack_bytes(ntiles))) != PSS_OK) return rc;
@@ -368,9 +377,14 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
         CU(launch_pileup(P->stat, a, ntiles, !(P->flags & PSS_FLAG_LONG_READS), s, &ctx->launches));
         if (e1) CU(cudaEventRecord(e1, s));
     }
-    if (P->stat == PSS_COVERAGE_GC)
+    if (P->stat == PSS_COVERAGE_GC) {
+        cudaEvent_t g0, g1;
+        timing_pair(ctx, PSS_KTAG_GC, &g0, &g1);
+        if (g0) CU(cudaEventRecord(g0, s));
         CU(launch_gc(P->ref, P->ref_start, P->ref_len, P->contig_len, start, end, P->window_size, P->window_offset,
                      out, s, &ctx->launches));
+        if (g1) CU(cudaEventRecord(g1, s));
+    }
     return PSS_OK;
 }
 
@@ -1034,60 +1048,124 @@ extern "C" int pss_pileup_host(pss_ctx *ctx, const pss_reads *reads, const pss_p
 
 // ------------------------------------------------------------------------------ binned
 
-static int check_binned(pss_ctx *ctx, const pss_reads *R, const pss_binned_params *P, const int32_t *out) {
-    if (!P) return fail(ctx, PSS_EINVAL, "params is NULL");
-    if (P->stat < 0 || P->stat >= PSS_N_BINNED_STATS) return fail(ctx, PSS_EINVAL, "unsupported statistics type: %d", P->stat);
-    if (P->window_size <= 0) return fail(ctx, PSS_EINVAL, "window_size <= 0");
-    if (P->n_bins != pss_binned_nbins(P->start, P->end, P->window_size)) return fail(ctx, PSS_EINVAL, "n_bins mismatch");
+static bool binned_needs_cigar(int stat) { return stat == PSS_COVERAGE_EXT_BINNED || stat == PSS_ALIGNMENT_BINNED; }
+static bool binned_needs_ref(int stat) { return stat == PSS_COVERAGE_BINNED || stat == PSS_COVERAGE_EXT_BINNED; }
+
+// the statistics of one call: each at most once, one common request; *mask receives the set (bit i = statistic i),
+// by_stat[i] the caller's output pointer of statistic i
+static int check_binned(pss_ctx *ctx, const pss_reads *R, int32_t n_stats, const pss_binned_params *P, int32_t *const *outs,
+                        int *mask, int32_t **by_stat) {
+    if (n_stats < 1 || !P || !outs) return fail(ctx, PSS_EINVAL, "n_stats < 1 or a NULL array");
     if (!R) return fail(ctx, PSS_EINVAL, "reads is NULL");
     if (R->n_reads < 0 || R->n_reads > 0x7fffffff) return fail(ctx, PSS_EINVAL, "n_reads out of range");
     if (R->n_reads > 0 && (!R->pos || !R->flag || !R->mapq || !R->tlen || !R->mtid))
         return fail(ctx, PSS_EINVAL, "a required read array is NULL");
-    bool need_cigar = P->stat == PSS_COVERAGE_EXT_BINNED || P->stat == PSS_ALIGNMENT_BINNED;
-    if (R->n_reads > 0 && need_cigar && (!R->cigar || !R->cigar_off)) return fail(ctx, PSS_EINVAL, "cigar arrays are NULL");
-    bool need_ref = P->stat == PSS_COVERAGE_BINNED || P->stat == PSS_COVERAGE_EXT_BINNED;
-    if (need_ref && !P->ref) return fail(ctx, PSS_EINVAL, "ref is NULL");
-    if (!out) return fail(ctx, PSS_EINVAL, "out is NULL");
+    *mask = 0;
+    for (int i = 0; i < PSS_N_BINNED_STATS; ++i) by_stat[i] = nullptr;
+    for (int i = 0; i < n_stats; ++i) {
+        const pss_binned_params &Q = P[i];
+        if (Q.stat < 0 || Q.stat >= PSS_N_BINNED_STATS) return fail(ctx, PSS_EINVAL, "unsupported statistics type: %d", Q.stat);
+        if (Q.window_size <= 0) return fail(ctx, PSS_EINVAL, "window_size <= 0");
+        if (Q.n_bins != pss_binned_nbins(Q.start, Q.end, Q.window_size)) return fail(ctx, PSS_EINVAL, "n_bins mismatch");
+        if (Q.n_bins > 0x7fffffff) return fail(ctx, PSS_EINVAL, "too many windows for one call");
+        if (Q.start != P[0].start || Q.end != P[0].end || Q.window_size != P[0].window_size || Q.min_mapq != P[0].min_mapq ||
+            (Q.no_dup != 0) != (P[0].no_dup != 0))
+            return fail(ctx, PSS_EINVAL, "statistics of one call must share start, end, window_size, min_mapq, no_dup");
+        if (*mask >> Q.stat & 1) return fail(ctx, PSS_EINVAL, "statistic %d requested twice", Q.stat);
+        if (R->n_reads > 0 && binned_needs_cigar(Q.stat) && (!R->cigar || !R->cigar_off)) return fail(ctx, PSS_EINVAL, "cigar arrays are NULL");
+        if (binned_needs_ref(Q.stat) && !Q.ref) return fail(ctx, PSS_EINVAL, "ref is NULL");
+        if (!outs[i]) return fail(ctx, PSS_EINVAL, "out is NULL");
+        *mask |= 1 << Q.stat;
+        by_stat[Q.stat] = outs[i];
+    }
     return PSS_OK;
+}
+
+// the common request of a call, with the reference span of its first statistic that has one
+static pss_binned_params binned_common(int32_t n_stats, const pss_binned_params *P) {
+    pss_binned_params C = P[0];
+    C.ref = nullptr; C.ref_start = 0; C.ref_len = 0;
+    for (int i = 0; i < n_stats; ++i)
+        if (binned_needs_ref(P[i].stat) && P[i].ref) { C.ref = P[i].ref; C.ref_start = P[i].ref_start; C.ref_len = P[i].ref_len; break; }
+    return C;
+}
+
+static int run_binned(pss_ctx *ctx, const pss_reads *R, const pss_binned_params &C, int mask, int32_t *const *by_stat,
+                      cudaStream_t s) {
+    int rc;
+    if ((rc = ensure(ctx, ctx->bwork, binned_work_bytes(mask, C.n_bins))) != PSS_OK) return rc;
+    BinnedEvents ev = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    timing_pair(ctx, PSS_KTAG_BINNED_ACC, &ev.acc0, &ev.acc1);
+    timing_pair(ctx, PSS_KTAG_BINNED_FIN, &ev.fin0, &ev.fin1);
+    if (mask & ((1 << PSS_COVERAGE_BINNED) | (1 << PSS_COVERAGE_EXT_BINNED))) timing_pair(ctx, PSS_KTAG_BINNED_GC, &ev.gc0, &ev.gc1);
+    CU(launch_binned_multi(*R, C, mask, by_stat, ctx->bwork.p, s, &ctx->launches, ctx->timing ? &ev : nullptr));
+    return PSS_OK;
+}
+
+extern "C" int pss_binned_multi(pss_ctx *ctx, const pss_reads *reads, int32_t n_stats, const pss_binned_params *P,
+                                int32_t *const *outs, void *stream) {
+    if (!ctx) return PSS_EINVAL;
+    int rc, mask;
+    int32_t *by_stat[PSS_N_BINNED_STATS];
+    if ((rc = check_binned(ctx, reads, n_stats, P, outs, &mask, by_stat)) != PSS_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    return run_binned(ctx, reads, binned_common(n_stats, P), mask, by_stat, (cudaStream_t)stream);
 }
 
 extern "C" int pss_binned(pss_ctx *ctx, const pss_reads *reads, const pss_binned_params *P, int32_t *out, void *stream) {
     if (!ctx) return PSS_EINVAL;
-    int rc;
-    if ((rc = check_binned(ctx, reads, P, out)) != PSS_OK) return rc;
-    CU(cudaSetDevice(ctx->device));
-    if ((rc = ensure(ctx, ctx->bwork, binned_work_bytes(*P))) != PSS_OK) return rc;
-    CU(launch_binned(*reads, *P, out, ctx->bwork.p, (cudaStream_t)stream, &ctx->launches));
-    return PSS_OK;
+    if (!P) return fail(ctx, PSS_EINVAL, "params is NULL");
+    return pss_binned_multi(ctx, reads, 1, P, &out, stream);
 }
 
-extern "C" int pss_binned_host(pss_ctx *ctx, const pss_reads *H, const pss_binned_params *P, int32_t *out) {
+extern "C" int pss_binned_host_multi(pss_ctx *ctx, const pss_reads *H, int32_t n_stats, const pss_binned_params *P,
+                                     int32_t *const *outs) {
     if (!ctx) return PSS_EINVAL;
-    int rc;
-    if ((rc = check_binned(ctx, H, P, out)) != PSS_OK) return rc;
+    int rc, mask;
+    int32_t *by_stat[PSS_N_BINNED_STATS];
+    if ((rc = check_binned(ctx, H, n_stats, P, outs, &mask, by_stat)) != PSS_OK) return rc;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = nullptr;
     pss_reads D = *H;
-    size_t n = (size_t)H->n_reads;
-    bool need_cigar = P->stat == PSS_COVERAGE_EXT_BINNED || P->stat == PSS_ALIGNMENT_BINNED;
+    const size_t n = (size_t)H->n_reads;
+    bool need_cigar = false;
+    for (int i = 0; i < n_stats; ++i) need_cigar = need_cigar || binned_needs_cigar(P[i].stat);
+    // the record fields this statistic set reads, once for all of them
 #define UP(idx, field, count) if ((rc = to_device(ctx, ctx->hb[idx], H->field, (count), &D.field, s)) != PSS_OK) return rc
-    UP(0, pos, n); UP(1, flag, n); UP(2, mapq, n); UP(3, tlen, n); UP(4, mtid, n);
+    UP(0, pos, n); UP(1, flag, n); UP(2, mapq, n);
+    if (mask & ((1 << PSS_COVERAGE_EXT_BINNED) | (1 << PSS_TLEN_BINNED))) UP(3, tlen, n);
+    if (mask & (1 << PSS_COVERAGE_EXT_BINNED)) UP(4, mtid, n);
     if (need_cigar && n > 0) {
         UP(6, cigar_off, n + 1);
         if ((rc = to_device_span(ctx, ctx->hb[7], H->cigar, H->cigar_off, n, &D.cigar, s)) != PSS_OK) return rc;
     }
 #undef UP
-    pss_binned_params Pd = *P;
-    if (P->ref && P->ref_len > 0) {
-        if ((rc = to_device(ctx, ctx->hb[13], P->ref, (size_t)P->ref_len, &Pd.ref, s)) != PSS_OK) return rc;
+    pss_binned_params C = binned_common(n_stats, P);
+    if (C.ref && C.ref_len > 0) {
+        if ((rc = to_device(ctx, ctx->hb[13], C.ref, (size_t)C.ref_len, &C.ref, s)) != PSS_OK) return rc;
     }
-    const int nf = kBinnedFields[P->stat];
-    size_t obytes = sizeof(int32_t) * (size_t)nf * (size_t)P->n_bins;
-    if ((rc = ensure(ctx, ctx->outbuf[0], obytes)) != PSS_OK) return rc;
-    if ((rc = ensure(ctx, ctx->bwork, binned_work_bytes(Pd))) != PSS_OK) return rc;
-    CU(launch_binned(D, Pd, (int32_t *)ctx->outbuf[0].p, ctx->bwork.p, s, &ctx->launches));
-    CU(cudaMemcpyAsync(out, ctx->outbuf[0].p, obytes, cudaMemcpyDeviceToHost, s));
-    ctx->d2h_bytes += (int64_t)obytes;
+    // all result columns in one device buffer, one copy back per statistic
+    size_t total = 0, off[PSS_N_BINNED_STATS];
+    int32_t *dev_out[PSS_N_BINNED_STATS];
+    for (int t = 0; t < PSS_N_BINNED_STATS; ++t) {
+        off[t] = total;
+        if (mask >> t & 1) total += (size_t)kBinnedFields[t] * (size_t)C.n_bins;
+    }
+    if ((rc = ensure(ctx, ctx->outbuf[0], sizeof(int32_t) * total)) != PSS_OK) return rc;
+    for (int t = 0; t < PSS_N_BINNED_STATS; ++t) dev_out[t] = (mask >> t & 1) ? (int32_t *)ctx->outbuf[0].p + off[t] : nullptr;
+    if ((rc = run_binned(ctx, &D, C, mask, dev_out, s)) != PSS_OK) return rc;
+    for (int t = 0; t < PSS_N_BINNED_STATS; ++t) {
+        if (!(mask >> t & 1)) continue;
+        const size_t obytes = sizeof(int32_t) * (size_t)kBinnedFields[t] * (size_t)C.n_bins;
+        CU(cudaMemcpyAsync(by_stat[t], dev_out[t], obytes, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += (int64_t)obytes;
+    }
     CU(cudaStreamSynchronize(s));
     return PSS_OK;
+}
+
+extern "C" int pss_binned_host(pss_ctx *ctx, const pss_reads *H, const pss_binned_params *P, int32_t *out) {
+    if (!ctx) return PSS_EINVAL;
+    if (!P) return fail(ctx, PSS_EINVAL, "params is NULL");
+    return pss_binned_host_multi(ctx, H, 1, P, &out);
 }

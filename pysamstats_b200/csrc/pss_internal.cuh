@@ -154,8 +154,10 @@ cudaError_t launch_pileup(int stat, const PileupArgs &a, int64_t ntiles, bool st
 cudaError_t launch_gc(const uint8_t *ref, int64_t ref_start, int64_t ref_len, int64_t contig_len,
                       int64_t start, int64_t end, int window_size, int window_offset, int32_t *out_gc,
                       cudaStream_t s, int64_t *launches);
-size_t binned_work_bytes(const pss_binned_params &P);
-cudaError_t launch_binned(const pss_reads &R, const pss_binned_params &P, int32_t *out, void *work, cudaStream_t s,
-                          int64_t *launches);
+// binned statistics (pss_kernels_binned.cu): `mask` bit i = enum pss_binned_stat i
+struct BinnedEvents { cudaEvent_t acc0, acc1, fin0, fin1, gc0, gc1; };   // recorded around the kernels when not NULL
+size_t binned_work_bytes(int mask, int64_t n_bins);
+cudaError_t launch_binned_multi(const pss_reads &R, const pss_binned_params &P, int mask, int32_t *const *outs, void *work,
+                                cudaStream_t s, int64_t *launches, const BinnedEvents *ev);
 cudaError_t launch_export_admitted(const RInfo *ri, int64_t n, uint8_t *admitted, cudaStream_t s,
                                    int64_t *launches);

@@ -538,209 +538,6 @@ k_gc(const uint8_t *__restrict__ ref, int64_t ref_start, int64_t ref_len, int64_
     }
 }
 
-// ----------------------------------------------------------------- binned statistics
-//
-// iter_binned_chrom (opt.pyx:2026-2102) rolls the window while pos > bin_end (strict), so
-// window k >= 1 owns the reads with start + k*W < pos <= start + (k+1)*W, window 0 every
-// read with pos <= start + W and the last window everything beyond.  Filters (min_mapq,
-// no_dup opt.pyx:2066-2073) and the unmapped skip of every recv apply per read.
-//
-// Segmented reduction, read-parallel (the stream of read records is what bounds it):
-//   k_binned_acc   one read per thread, fully coalesced loads of the 15 bytes per read the
-//                  statistic needs; the lanes of a warp that fall into the same window form a
-//                  segment (MATCH.ANY), each sum is reduced over the segment with REDUX (64-bit
-//                  sums as three 27-bit pieces) and the segment's first lane adds it to the
-//                  window's 64-bit accumulator with one RED -- about 1.5 segments per warp
-//   k_binned_gc    one warp per window: G+C count of the window's reference bytes
-//   k_binned_fin   one thread per window: rec() -- means / root mean squares, int32 columns
-
-__device__ __forceinline__ int dev_rootmean(unsigned long long sq, long long n) {
-    return n > 0 ? (int)rint(sqrt((double)sq / (double)n)) : 0;   // opt.pyx:2159-2163
-}
-__device__ __forceinline__ int dev_mean(long long s, long long n) {
-    return n > 0 ? (int)rint((double)s / (double)n) : 0;          // opt.pyx:2166-2170
-}
-
-// number of 64-bit accumulators per window
-__host__ __device__ constexpr int binned_nsums(int stat) {
-    return stat == PSS_COVERAGE_BINNED ? 2 : stat == PSS_COVERAGE_EXT_BINNED ? 8 : stat == PSS_MAPQ_BINNED ? 3
-           : stat == PSS_ALIGNMENT_BINNED ? 10 : 6;
-}
-
-// sum of v over the lanes of `mask` (all of them call), exact modulo 2^32 / 2^64
-__device__ __forceinline__ unsigned long long seg_sum32(unsigned mask, unsigned v) { return __reduce_add_sync(mask, v); }
-__device__ __forceinline__ unsigned long long seg_sum64(unsigned mask, unsigned long long v) {
-    const unsigned long long m27 = (1ull << 27) - 1;
-    unsigned long long s0 = __reduce_add_sync(mask, (unsigned)(v & m27));
-    unsigned long long s1 = __reduce_add_sync(mask, (unsigned)((v >> 27) & m27));
-    unsigned long long s2 = __reduce_add_sync(mask, (unsigned)(v >> 54));
-    return s0 + (s1 << 27) + (s2 << 54);
-}
-
-#ifndef BINNED_U
-#define BINNED_U 4
-#endif
-// reads per lane of k_binned_acc (alignment_binned walks every CIGAR: one read per lane stays faster there)
-__host__ __device__ constexpr int binned_u(int stat) { return stat == PSS_ALIGNMENT_BINNED ? 1 : BINNED_U; }
-
-template <int STAT>
-__global__ void __launch_bounds__(256)
-k_binned_acc(pss_reads R, pss_binned_params P, unsigned long long *__restrict__ sums) {
-    constexpr int NS = binned_nsums(STAT);
-    constexpr int U = binned_u(STAT);    // reads per lane: their record loads are all in flight before the first is used
-    constexpr bool NEED_T = STAT == PSS_COVERAGE_EXT_BINNED || STAT == PSS_TLEN_BINNED;
-    const int lane = threadIdx.x & 31;
-    const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * U) + lane;
-    int pos_[U], tlen_[U], mtid_[U];
-    uint32_t flag_[U], mapq_[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int64_t i = base + 32 * u;
-        const bool live = i < R.n_reads;
-        pos_[u] = live ? R.pos[i] : 0;
-        flag_[u] = live ? R.flag[i] : 4u;
-        mapq_[u] = live ? R.mapq[i] : 0u;
-        tlen_[u] = (NEED_T && live) ? R.tlen[i] : 0;
-        mtid_[u] = (STAT == PSS_COVERAGE_EXT_BINNED && live) ? R.mtid[i] : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-    const int64_t i = base + 32 * u;
-    const bool live = i < R.n_reads;
-    long long w = -1;                    // window of this lane's read
-    unsigned c[10];                      // 32-bit safe contributions (counts, small sums, wrapping int sums)
-    unsigned long long d[4];             // 64-bit contributions (tlen)
-#pragma unroll
-    for (int k = 0; k < 10; ++k) c[k] = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) d[k] = 0;
-    if (live) {
-        const long long rel = (long long)pos_[u] - P.start - 1;
-        w = rel < 0 ? 0 : (rel >> 32) ? rel / P.window_size : (long long)((uint32_t)rel / (uint32_t)P.window_size);   // (64-bit division only when needed)
-        if (w > P.n_bins - 1) w = P.n_bins - 1;
-        const uint32_t flag = flag_[u];
-        const int mapq = (int)mapq_[u];
-        bool keep = !(flag & 4);                                   // every BinnedStat.recv
-        if (P.min_mapq > 0 && mapq < P.min_mapq) keep = false;
-        if (P.no_dup && (flag & 1024)) keep = false;
-        if (keep) {
-            const bool rev = flag & 16, pp = flag & 2;
-            if (STAT == PSS_COVERAGE_BINNED) {                         // opt.pyx:1574-1584
-                c[0] = 1; c[1] = pp;
-            } else if (STAT == PSS_COVERAGE_EXT_BINNED) {              // opt.pyx:1629-1662
-                const bool mun = flag & 8, mrev = flag & 32;
-                const int tlen = tlen_[u];
-                c[0] = 1; c[1] = pp;
-                if (mun) c[2] = 1;
-                else if (R.tid != mtid_[u]) c[3] = 1;
-                else if (rev == mrev) c[4] = 1;
-                else if ((rev && tlen > 0) || (!rev && tlen < 0)) c[5] = 1;
-                int soft = 0;
-                for (int64_t k = R.cigar_off[i]; k < R.cigar_off[i + 1]; ++k) soft |= ((R.cigar[k] & 15) == OP_S);
-                c[6] = soft;
-                c[7] = (flag & 1024) != 0;
-            } else if (STAT == PSS_MAPQ_BINNED) {                      // opt.pyx:1690-1703
-                c[0] = 1; c[1] = (mapq == 0); c[2] = (unsigned)(mapq * mapq);
-            } else if (STAT == PSS_ALIGNMENT_BINNED) {                 // opt.pyx:1733-1764: C int sums, they wrap
-                for (int64_t k = R.cigar_off[i]; k < R.cigar_off[i + 1]; ++k) {
-                    const uint32_t cw = R.cigar[k];
-                    const int op = cw & 15;
-#pragma unroll
-                    for (int o = 0; o <= OP_X; ++o) if (op == o) c[1 + o] += (cw >> 4);
-                }
-                c[0] = 1;
-            } else {                                                   // tlen opt.pyx:1801-1819
-                const long long t = tlen_[u];
-                c[0] = 1; d[0] = (unsigned long long)t; d[1] = (unsigned long long)(t * t);
-                if (pp) { c[1] = 1; d[2] = d[0]; d[3] = d[1]; }
-            }
-        }
-    }
-    // lanes of the same window (reads are start-sorted, so they are neighbours; any order works)
-    const unsigned mask = __match_any_sync(FULL, w);
-    const bool head = live && lane == __ffs(mask) - 1;
-    unsigned long long *o = sums + (head ? w : 0);
-    const int64_t nb = P.n_bins;
-#define EMIT(slot, value) do { unsigned long long t__ = (value); if (head && t__) atomicAdd(o + (int64_t)(slot) * nb, t__); } while (0)
-    if (STAT == PSS_TLEN_BINNED) {
-        // slots: n, n_pp, sum, sum_pp, sumsq, sumsq_pp
-        EMIT(0, seg_sum32(mask, c[0])); EMIT(1, seg_sum32(mask, c[1]));
-        const long long t = (long long)d[0];
-        if (__all_sync(FULL, t > -8192 && t < 8192)) {
-            // ordinary insert sizes: 32 lanes of |t| < 2^13 sum below 2^18, their squares below 2^31 -- one REDUX per sum
-            // (the signed sums are sign extended; the 64-bit accumulators wrap like the reference's C arithmetic)
-            EMIT(2, (unsigned long long)(long long)(int)__reduce_add_sync(mask, (unsigned)d[0]));
-            EMIT(3, (unsigned long long)(long long)(int)__reduce_add_sync(mask, (unsigned)d[2]));
-            EMIT(4, seg_sum32(mask, (unsigned)d[1])); EMIT(5, seg_sum32(mask, (unsigned)d[3]));
-        } else {
-            EMIT(2, seg_sum64(mask, d[0])); EMIT(3, seg_sum64(mask, d[2]));
-            EMIT(4, seg_sum64(mask, d[1])); EMIT(5, seg_sum64(mask, d[3]));
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < NS; ++k) EMIT(k, seg_sum32(mask, c[k]));
-    }
-#undef EMIT
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_binned_gc(pss_binned_params P, int32_t *__restrict__ out_gc) {
-    const int lane = threadIdx.x & 31;
-    const int64_t bin = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (bin >= P.n_bins) return;
-    // rec(): gc_content(fafile.fetch(chrom, bin_start, bin_end)) opt.pyx:1561-1562
-    const long long bstart = P.start + bin * (long long)P.window_size, bend = bstart + P.window_size;
-    long long ws = bstart < 0 ? 0 : bstart, we = bend;
-    const long long avail_hi = P.ref_start + P.ref_len;
-    if (we > avail_hi) we = avail_hi;
-    int c = 0;
-    for (long long k = ws + lane; k < we; k += 32) {
-        uint8_t ch = P.ref[k - P.ref_start] | 0x20;
-        c += (ch == 'g' || ch == 'c');
-    }
-    c = warp_sum(c);
-    // an empty window (beyond the FASTA) makes the reference's gc_content divide by zero
-    // (opt.pyx:1538, ZeroDivisionError); reported as -1, the host layer raises
-    if (lane == 0) out_gc[bin] = (we > ws) ? (int)rint((double)c * 100. / (double)(we - ws)) : -1;
-}
-
-template <int STAT>
-__global__ void __launch_bounds__(256)
-k_binned_fin(pss_binned_params P, const unsigned long long *__restrict__ sums, int32_t *__restrict__ out) {
-    constexpr int NS = binned_nsums(STAT);
-    const int64_t bin = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (bin >= P.n_bins) return;
-    const int64_t nb = P.n_bins;
-    long long acc[NS];
-#pragma unroll
-    for (int k = 0; k < NS; ++k) acc[k] = (long long)sums[(int64_t)k * nb + bin];
-    int32_t *o = out + bin;
-    if (STAT == PSS_COVERAGE_BINNED) {              // field 0 = gc (k_binned_gc)
-        o[nb] = (int)acc[0]; o[2 * nb] = (int)acc[1];
-    } else if (STAT == PSS_COVERAGE_EXT_BINNED) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[(1 + k) * nb] = (int)acc[k];
-    } else if (STAT == PSS_MAPQ_BINNED) {
-        o[0] = (int)acc[0]; o[nb] = (int)acc[1];
-        o[2 * nb] = dev_rootmean((unsigned long long)acc[2], acc[0]);
-    } else if (STAT == PSS_ALIGNMENT_BINNED) {
-        // reads_all bases_all M I D N S H P = X (config.py dtype_alignment_binned); int accumulators in the reference
-        int32_t ops[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) ops[k] = (int32_t)(uint32_t)acc[1 + k];
-        o[0] = (int)acc[0];
-        o[nb] = (int32_t)((uint32_t)ops[OP_M] + (uint32_t)ops[OP_I] + (uint32_t)ops[OP_S] + (uint32_t)ops[OP_EQ] + (uint32_t)ops[OP_X]);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) o[(2 + k) * nb] = ops[k];
-    } else {
-        o[0] = (int)acc[0]; o[nb] = (int)acc[1];
-        o[2 * nb] = dev_mean(acc[2], acc[0]); o[3 * nb] = dev_mean(acc[3], acc[1]);
-        o[4 * nb] = dev_rootmean((unsigned long long)acc[4], acc[0]);
-        o[5 * nb] = dev_rootmean((unsigned long long)acc[5], acc[1]);
-    }
-}
-
 // ------------------------------------------------------------------------ launchers
 
 #define LAUNCHED() do { if (launches) ++*launches; } while (0)
@@ -819,38 +616,3 @@ cudaError_t launch_gc(const uint8_t *ref, int64_t ref_start, int64_t ref_len, in
     return cudaGetLastError();
 }
 
-size_t binned_work_bytes(const pss_binned_params &P) {
-    return sizeof(unsigned long long) * (size_t)binned_nsums(P.stat) * (size_t)(P.n_bins > 0 ? P.n_bins : 0);
-}
-
-template <int STAT>
-static void launch_binned_one(const pss_reads &R, const pss_binned_params &P, unsigned long long *sums, int32_t *out,
-                              cudaStream_t s, int64_t *launches) {
-    if (R.n_reads > 0) {
-        k_binned_acc<STAT><<<(unsigned)((R.n_reads + 256 * binned_u(STAT) - 1) / (256 * binned_u(STAT))), 256, 0, s>>>(R, P, sums);
-        LAUNCHED();
-    }
-    k_binned_fin<STAT><<<(unsigned)((P.n_bins + 255) / 256), 256, 0, s>>>(P, sums, out);
-    LAUNCHED();
-}
-
-// `work`: binned_work_bytes(P) bytes of device scratch (the windows' 64-bit accumulators)
-cudaError_t launch_binned(const pss_reads &R, const pss_binned_params &P, int32_t *out, void *work, cudaStream_t s,
-                          int64_t *launches) {
-    if (P.n_bins <= 0) return cudaSuccess;
-    unsigned long long *sums = (unsigned long long *)work;
-    cudaError_t e = cudaMemsetAsync(sums, 0, binned_work_bytes(P), s);
-    if (e != cudaSuccess) return e;
-    switch (P.stat) {
-    case PSS_COVERAGE_BINNED: launch_binned_one<PSS_COVERAGE_BINNED>(R, P, sums, out, s, launches); break;
-    case PSS_COVERAGE_EXT_BINNED: launch_binned_one<PSS_COVERAGE_EXT_BINNED>(R, P, sums, out, s, launches); break;
-    case PSS_MAPQ_BINNED: launch_binned_one<PSS_MAPQ_BINNED>(R, P, sums, out, s, launches); break;
-    case PSS_ALIGNMENT_BINNED: launch_binned_one<PSS_ALIGNMENT_BINNED>(R, P, sums, out, s, launches); break;
-    default: launch_binned_one<PSS_TLEN_BINNED>(R, P, sums, out, s, launches); break;
-    }
-    if (P.stat == PSS_COVERAGE_BINNED || P.stat == PSS_COVERAGE_EXT_BINNED) {
-        k_binned_gc<<<(unsigned)((P.n_bins * 32 + 255) / 256), 256, 0, s>>>(P, out);
-        LAUNCHED();
-    }
-    return cudaGetLastError();
-}

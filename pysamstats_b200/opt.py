@@ -99,6 +99,17 @@ def normalise_coords(alignmentfile, chrom, start, end, one_based):
     return start, end
 
 
+def _check_region(start, end):
+    """The checks of pysam's ``AlignmentFile.parse_region``, which both reference call sites reach with the
+    normalised coordinates (``opt.pyx:1853``, ``:2036``): same exception type and message."""
+    if start > end:
+        raise ValueError('invalid coordinates: start (%i) > stop (%i)' % (start, end))
+    if start < 0:
+        raise ValueError('start out of range (%i)' % start)          # e.g. one_based=True with start=0
+    if end < 0:
+        raise ValueError('end out of range (%i)' % end)
+
+
 def _reads_struct(batch, need_qual):
     batch.padded()
     d = {k: getattr(batch, k) for k in _cabi.READ_FIELDS if need_qual or k != 'name_prev'}
@@ -148,8 +159,7 @@ def _pileup_plan(stat, alignmentfile, fafile, pad, chrom, start, end, one_based,
         if pad:
             assert c is not None, 'chromosome is None'
         s, e = normalise_coords(bam, c, start, end, one_based)
-        if s > e:
-            raise ValueError('invalid coordinates: start (%i) > stop (%i)' % (s, e))     # pysam parse_region
+        _check_region(s, e)
         batch = bam.region_batch(c, s, e)
         n = batch.n_reads
         if n == 0 and not pad:
@@ -193,7 +203,7 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
         def run_piece(piece, device):
             """One position piece on one GPU -> (pos, ref column, fields) or None when it has no rows."""
             c_lo, c_hi, reads = piece
-            pctx = _cabi.get_context(device)
+            pctx = _cabi.get_context(*device)
             cn = c_hi - c_lo
             params = pctx.pileup_params(name, start=c_lo, end=c_hi, **pkw)
             out = bamio.alloc_big((len(names), cn), np.int32)
@@ -238,8 +248,7 @@ def pileup_rows(stat, dtype, alignmentfile, fafile=None, pad=False, chrom=None, 
     name = stat.name
     names = config.value_fields(name)
     ctx = _cabi.get_context()
-    if len(_devices(ctx.device)) > 1:
-        return None
+    devs = _devices(ctx.device)
     if ctx.row_layout(name, dtype, names, chrom='') is None:
         return None
     parts = []
@@ -256,14 +265,31 @@ def pileup_rows(stat, dtype, alignmentfile, fafile=None, pad=False, chrom=None, 
         except (MemoryError, OSError, ValueError):
             return None
         n = 0
-        for c_lo, c_hi, reads in _position_chunks(batch, lo, hi, need_qual, max_depth):
-            params = ctx.pileup_params(name, start=c_lo, end=c_hi, **pkw)
-            m, neg = ctx.pileup_host_rows(reads, params, layout, buf, n, cap - n)
-            if neg:
-                # the reference stores gc = -1 for an empty window into a u1 column, which numpy
-                # refuses
-                raise OverflowError('Python integer -1 out of bounds for uint8')
-            n += m
+        if len(devs) == 1:
+            for c_lo, c_hi, reads in _position_chunks(batch, lo, hi, need_qual, max_depth):
+                params = ctx.pileup_params(name, start=c_lo, end=c_hi, **pkw)
+                m, neg = ctx.pileup_host_rows(reads, params, layout, buf, n, cap - n)
+                if neg:
+                    # the reference stores gc = -1 for an empty window into a u1 column, which numpy
+                    # refuses
+                    raise OverflowError('Python integer -1 out of bounds for uint8')
+                n += m
+        else:
+            # several GPUs (PSS_GPUS): the position pieces go to the GPUs in turn, piece [c_lo, c_hi) packing its records
+            # at row c_lo - lo (it cannot emit more rows than positions); pieces with fewer rows than positions leave
+            # gaps, closed afterwards by moving the later pieces down (nothing moves on a fully covered contig)
+            def run_rows(piece, device):
+                c_lo, c_hi, reads = piece
+                pctx = _cabi.get_context(*device)
+                params = pctx.pileup_params(name, start=c_lo, end=c_hi, **pkw)
+                m, neg = pctx.pileup_host_rows(reads, params, layout, buf, c_lo - lo, c_hi - c_lo)
+                return c_lo - lo, m, neg
+            for r0, m, neg in _run_pieces(run_rows, _position_chunks(batch, lo, hi, need_qual, max_depth), ctx.device):
+                if neg:
+                    raise OverflowError('Python integer -1 out of bounds for uint8')
+                if m and r0 != n:
+                    buf[n:n + m] = buf[r0:r0 + m]         # (numpy copies overlapping ranges correctly)
+                n += m
         if n == 0:
             continue
         if n * 2 < cap and n * dtype.itemsize < (1 << 30):
@@ -276,22 +302,27 @@ def pileup_rows(stat, dtype, alignmentfile, fafile=None, pad=False, chrom=None, 
 
 
 def _devices(default):
-    """GPUs the pieces of a contig are spread over: PSS_GPUS = a count or 'all' (default: one, the context's)."""
+    """(device, slot) pairs the pieces of a contig are spread over.  PSS_GPUS = a count, 'all', or an explicit
+    comma-separated device list; a device listed k times runs k shards at once, each on its own context (the tests
+    use ``0,0`` to run the sharded paths on a one-GPU box).  Default: one, the context's."""
     import os
     v = os.environ.get('PSS_GPUS', '').strip().lower()
     if v in ('', '0', '1'):
-        return [default]
+        return [(default, 0)]
+    if ',' in v:
+        ids = [int(x) for x in v.split(',') if x.strip() != '']
+        return [(d, ids[:i].count(d)) for i, d in enumerate(ids)] if len(ids) > 1 else [(default, 0)]
     import torch
     n = torch.cuda.device_count()
     k = n if v == 'all' else min(int(v), n)
-    return list(range(k)) if k > 1 else [default]
+    return [(d, 0) for d in range(k)] if k > 1 else [(default, 0)]
 
 
 def _run_pieces(fn, pieces, default_device):
-    """Results of fn(piece, device) in piece order.  With several GPUs (PSS_GPUS) piece i goes to GPU i mod n from a
-    thread per GPU -- the interval sharding of SURVEY.md section 8e behind the public API: contiguous position
+    """Results of fn(piece, (device, slot)) in piece order.  With several GPUs (PSS_GPUS) piece i goes to GPU i mod n
+    from a thread per GPU -- the interval sharding of SURVEY.md section 8e behind the public API: contiguous position
     intervals, the halo of reads that start before them, no collective, pieces concatenated in order -- and at most
-    n pieces are in flight, so a GPU never runs two at once."""
+    n pieces are in flight, so a context never runs two at once."""
     devs = _devices(default_device)
     if len(devs) == 1:
         for piece in pieces:
@@ -395,15 +426,18 @@ def binned_tables(stat, alignmentfile, fafile=None, chrom=None, window_size=300,
     for c in contigs:
         assert c is not None, 'chromosome is None'
         s, e = normalise_coords(bam, c, start, end, one_based)
-        if s > e:
-            raise ValueError('invalid coordinates: start (%i) > stop (%i)' % (s, e))     # pysam parse_region
+        _check_region(s, e)
         batch = bam.region_batch(c, s, e)
         refseq = fa.contig(c) if need_ref else None
-        params = ctx.binned_params(name, s, e, window_size, min_mapq=min_mapq, no_dup=no_dup,
-                                   ref=refseq, ref_start=0, ref_len=len(refseq) if need_ref else 0)
-        nb = int(params.n_bins)
+        nb = int(ctx.lib.pss_binned_nbins(int(s), int(e), window_size))
         out = np.empty((len(names), nb), dtype=np.int32)
-        ctx.binned_host(_reads_struct(batch, False), params, out)
+        devs = _devices(ctx.device)
+        if len(devs) > 1 and nb >= 2 * len(devs) and batch.n_reads:
+            _binned_across_gpus(devs, name, batch, s, e, window_size, nb, min_mapq, no_dup, refseq, out)
+        else:
+            params = ctx.binned_params(name, s, e, window_size, min_mapq=min_mapq, no_dup=no_dup,
+                                       ref=refseq, ref_start=0, ref_len=len(refseq) if need_ref else 0)
+            ctx.binned_host(_reads_struct(batch, False), params, out)
         if need_ref and nb and out[names.index('gc')].min() < 0:
             # gc_content() of an empty window (beyond the FASTA): opt.pyx:1538 divides by zero
             raise ZeroDivisionError('float division')
@@ -411,6 +445,42 @@ def binned_tables(stat, alignmentfile, fafile=None, chrom=None, window_size=300,
         if one_based:
             pos = pos + 1
         yield c, pos, None, {f: out[j] for j, f in enumerate(names)}
+
+
+def _binned_across_gpus(devs, name, batch, s, e, window_size, nb, min_mapq, no_dup, refseq, out):
+    """The windows of [s, e) spread over several GPUs (PSS_GPUS): contiguous window ranges (``shard.plan_windows``),
+    each with the reads that START in it (``shard.window_read_range``: the roll-over rule of ``opt.pyx:2050``; no halo,
+    the statistics are keyed by read start), a thread per GPU, columns written side by side into ``out`` -- no
+    collective.  A shard is the same request with start / end moved to its window range; its
+    first / last window collect exactly what the global first / last window collect because only its own reads
+    are passed."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import shard
+    batch.padded()
+    need_ref = refseq is not None
+
+    def run(job):
+        dev, (k_lo, k_hi) = job
+        if k_hi <= k_lo:
+            return
+        i0, i1 = shard.window_read_range(batch.pos, s, window_size, k_lo, k_hi, nb)
+        s_k = s + k_lo * window_size
+        e_k = e if k_hi >= nb else s + k_hi * window_size
+        d = dict(n_reads=i1 - i0, tid=batch.tid)
+        for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off'):
+            d[k] = getattr(batch, k)[i0:]
+        d['cigar'], d['seq4'] = batch.cigar, batch.seq4
+        d['qual'] = d['qual_off'] = d['name_prev'] = None
+        pctx = _cabi.get_context(*dev)
+        params = pctx.binned_params(name, s_k, e_k, window_size, min_mapq=min_mapq, no_dup=no_dup, ref=refseq,
+                                    ref_start=0, ref_len=len(refseq) if need_ref else 0)
+        assert int(params.n_bins) == k_hi - k_lo
+        part = np.empty((out.shape[0], k_hi - k_lo), dtype=np.int32)
+        pctx.binned_host(_cabi.make_reads_struct(d, n_reads=i1 - i0), params, part)
+        out[:, k_lo:k_hi] = part
+
+    with ThreadPoolExecutor(len(devs)) as ex:
+        list(ex.map(run, zip(devs, shard.plan_windows(s, e, window_size, len(devs)))))
 
 
 def iter_binned(stat, alignmentfile, fafile, chrom, window_size=300, window_offset=None, **kwargs):

@@ -70,3 +70,23 @@ for stat in config.binned_types:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
     print('%-22s %9.3f %12.3f' % (stat + '_binned', ms, n / ms / 1e6))
+# several binned statistics from one pass over the records (pss_binned_multi), with the library's per-kernel events
+for sub in (('coverage', 'mapq', 'tlen'), tuple(config.binned_types)):
+    if args.only and 'multi_binned' not in args.only.split(','):
+        continue
+    ps = [ctx.binned_params(t, 0, L, 300, ref=ref, ref_start=ref_lo, ref_len=int(ref.numel())) for t in sub]
+    outs = [torch.empty((len(config.value_fields_binned(t)), int(ps[0].n_bins)), dtype=torch.int32, device=dev) for t in sub]
+    for _ in range(2):
+        ctx.binned_multi(rs, ps, outs, stream=s)
+    torch.cuda.synchronize()
+    ctx.set_kernel_timing(True)
+    ctx.pileup_kernel_ms(-1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.reps):
+        ctx.binned_multi(rs, ps, outs, stream=s)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.reps
+    k = {name: ctx.pileup_kernel_ms(tag)[0] for name, tag in (('acc', _cabi.KTAG_BINNED_ACC), ('fin', _cabi.KTAG_BINNED_FIN), ('gc', _cabi.KTAG_BINNED_GC))}
+    ctx.set_kernel_timing(False)
+    print('%-22s %9.3f %12.3f   k_binned_acc %.3f ms, k_binned_fin %.3f ms, k_binned_gc %.3f ms' % ('+'.join(sub), ms, n / ms / 1e6, k['acc'], k['fin'], k['gc']))

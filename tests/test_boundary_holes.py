@@ -181,5 +181,8 @@ def test_chrom_none_start_end_semantics_in_the_plan(monkeypatch):
     assert all((p[1], p[2]) == (1000, 2000) for p in padded)
     lens = dict(zip(bamio.open_bam(fx('test.bam')).references, bamio.open_bam(fx('test.bam')).lengths))
     assert all((p[1], p[2]) == (0, lens[p[0]]) for p in plain)
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError, match='invalid coordinates'):
         list(opt._pileup_plan(opt.Coverage(), fx('test.bam'), None, True, 'Pf3D7_01_v3', 3000, 2000, **kw))
+    kw['one_based'] = True
+    with pytest.raises(ValueError, match='start out of range'):
+        list(opt._pileup_plan(opt.Coverage(), fx('test.bam'), None, False, 'Pf3D7_01_v3', 0, 2000, **kw))

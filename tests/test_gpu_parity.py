@@ -65,7 +65,7 @@ FILTERS = dict(min_mapq=1, min_baseq=17, no_del=True, no_dup=True)
 @pytest.mark.parametrize('stat', config.pileup_types)
 def test_region_and_filters(stat, obam, ofa):
     region = dict(chrom='Pf3D7_01_v3', start=0, end=2000)
-    for kw in (dict(region, one_based=False), dict(region, one_based=True), dict(region, **FILTERS),
+    for kw in (dict(region, one_based=False), dict(region, start=1, one_based=True), dict(region, **FILTERS),
                dict(FILTERS), dict(min_baseq=30), dict(no_del=True), dict(min_mapq=30)):
         assert_recarrays_equal(_oracle(stat, obam, ofa, 'test', **kw), _load(stat, 'test', **kw),
                                '%s %r' % (stat, kw))
@@ -296,19 +296,47 @@ def test_chunked_tables_equal_single_call(monkeypatch):
     assert rows == list(pysamstats.stat_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=1000, end=20000))
 
 
+def _gpu_list():
+    # every GPU of the box, or the one GPU twice (two shards at once, each on its own context)
+    import torch
+    n = torch.cuda.device_count()
+    return ','.join(str(i) for i in range(n)) if n > 1 else '0,0'
+
+
 def test_pieces_across_gpus(monkeypatch):
     # PSS_GPUS: the position pieces of a contig go to the GPUs of the box in turn (a thread per GPU, no collective),
-    # the host concatenates them in order -- same rows as one GPU
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs two GPUs')
+    # the host concatenates them in order -- same rows as one GPU; through the row sink and through the column tables
     cases = (('variation_strand', dict()), ('coverage_ext', dict(chrom='Pf3D7_02_v3', start=1000, end=40000, pad=True)),
-             ('mapq', dict(chrom='Pf3D7_01_v3')), ('tlen_strand', dict(chrom='Pf3D7_03_v3')))
+             ('mapq', dict(chrom='Pf3D7_01_v3')), ('tlen_strand', dict(chrom='Pf3D7_03_v3')),
+             ('coverage', dict(chrom='Pf3D7_01_v3', start=3, end=30000, pad=True, truncate=True)),
+             ('baseq_ext', dict(chrom='Pf3D7_01_v3')))                      # quality request: never cut
     expect = [_load(stat, 'test', **kw) for stat, kw in cases]
     monkeypatch.setenv('PSS_TABLE_CHUNK', '4096')
-    monkeypatch.setenv('PSS_GPUS', 'all')
-    for (stat, kw), e in zip(cases, expect):
-        assert_recarrays_equal(e, _load(stat, 'test', **kw), '%s %r on %d GPUs' % (stat, kw, torch.cuda.device_count()))
+    monkeypatch.setenv('PSS_GPUS', _gpu_list())
+    for no_rows in (False, True):
+        if no_rows:
+            monkeypatch.setenv('PSS_NO_ROWS', '1')
+        for (stat, kw), e in zip(cases, expect):
+            assert_recarrays_equal(e, _load(stat, 'test', **kw), '%s %r on %s (rows %r)' % (stat, kw, _gpu_list(), not no_rows))
+    # stat_* (the generator of dicts) over the sharded tables
+    rows = list(pysamstats.stat_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=1000, end=20000))
+    monkeypatch.delenv('PSS_GPUS')
+    assert rows == list(pysamstats.stat_coverage(fx('test.bam'), chrom='Pf3D7_01_v3', start=1000, end=20000))
+
+
+def test_binned_windows_across_gpus(obam, ofa, monkeypatch):
+    # the *_binned family behind PSS_GPUS: contiguous window ranges, reads by start window, columns side by side
+    cases = (dict(), dict(chrom='Pf3D7_01_v3', start=1000, end=20000, window_size=200, window_offset=100),
+             dict(chrom='Pf3D7_02_v3', start=777, end=50001, window_size=77, min_mapq=1, no_dup=True),
+             dict(window_size=1000, one_based=True), dict(chrom='Pf3D7_03_v3', start=10, end=40, window_size=300))
+    for stat in config.binned_types:
+        f = getattr(pysamstats, 'load_%s_binned' % stat)
+        monkeypatch.delenv('PSS_GPUS', raising=False)
+        expect = [f(fx('test.bam'), fafile=fx('ref.fa'), **kw) for kw in cases]
+        assert_recarrays_equal(orc.load_binned(stat, obam['test'], ofa, **cases[2]), expect[2], stat)
+        monkeypatch.setenv('PSS_GPUS', _gpu_list() + ',0')            # three shards
+        for kw, e in zip(cases, expect):
+            assert_recarrays_equal(e, f(fx('test.bam'), fafile=fx('ref.fa'), **kw), '%s_binned %r sharded' % (stat, kw))
 
 
 # ---- load_*: records packed by the engine (pss_pileup_host_rows) vs the column tables --------------
@@ -322,7 +350,7 @@ def test_rows_path_equals_column_path(stat, monkeypatch):
     cases = [dict(), dict(chrom='Pf3D7_01_v3', start=1000, end=20000, pad=True),
              dict(chrom='Pf3D7_02_v3', start=500, end=3000, truncate=True, one_based=True),
              dict(chrom='Pf3D7_03_v3', pad=True, min_mapq=20, no_dup=True),
-             dict(fields=['pos', 'reads_all', 'chrom']), dict(chrom='Pf3D7_01_v3', start=60000, end=70000),
+             dict(fields=['pos', 'reads_all', 'chrom']), dict(chrom='Pf3D7_01_v3', start=49000, end=70000),
              dict(chrom='Pf3D7_01_v3', start=3, end=40, pad=True, truncate=True),          # (no read starts this early)
              dict(chrom='Pf3D7_02_v3', start=100, end=100, pad=True)]
     for chunk, table_chunk in ((None, None), ('1024', None), ('512', '4096')):
@@ -375,14 +403,14 @@ def test_chrom_none_keeps_start_end_for_pad_and_binned(obam, ofa):
         assert len(a) == 16 * len(obam['test'].references)
 
 
-def test_one_based_start_zero_through_the_index(obam, ofa, monkeypatch):
-    # one_based=True, start=0 normalises to -1 (opt.pyx:2116): the BAI query treats it as 0
-    kw = dict(chrom='Pf3D7_01_v3', start=0, end=3000, one_based=True)
-    e = _oracle('coverage', obam, ofa, 'test', **kw)
-    monkeypatch.setenv('PSS_BAI_MIN_BYTES', '0')
-    from pysamstats_b200 import bamio
-    bamio._bam_cache.clear()
-    assert_recarrays_equal(e, _load('coverage', 'test', **kw), 'one_based start=0')
+def test_region_errors_of_parse_region():
+    # pysam's parse_region raises for start > end (after normalise_coords clamped end to the contig) and for a
+    # negative start -- one_based=True with start=0 normalises to -1 (opt.pyx:2116)
+    for f, kw in ((pysamstats.load_coverage, {}), (pysamstats.load_mapq_binned, {})):
+        with pytest.raises(ValueError, match='start out of range'):
+            f(fx('test.bam'), chrom='Pf3D7_01_v3', start=0, end=3000, one_based=True, **kw)
+        with pytest.raises(ValueError, match='invalid coordinates'):
+            f(fx('test.bam'), chrom='Pf3D7_01_v3', start=60000, end=70000, **kw)
 
 
 def test_unknown_fasta_contig_raises(tmp_path):

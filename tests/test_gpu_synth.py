@@ -466,3 +466,51 @@ def test_tlen_binned_small_and_huge_template_lengths(ctx, small):
         ctx.binned_host(_cabi.make_reads_struct(d), p, out)
         pos, F = orc.binned_packed('tlen', reads, 0, G, W, W // 2)
         assert np.array_equal(out.T, F), W
+
+
+def test_binned_multi_equals_single_calls(ctx, small):
+    # pss_binned_host_multi / pss_binned_multi: any set of the five statistics from ONE pass over the read records
+    # (one accumulator layout per set) == the single-statistic calls, which are oracle-checked above
+    import itertools
+    import torch
+    nb, ref, reads = small
+    d = dict(nb)
+    d['qual'] = d['qual_off'] = d['name_prev'] = None
+    rs = _cabi.make_reads_struct(d)
+    for (start, end, W, kw) in ((0, G, 300, dict()), (1234, G - 77, 77, dict(min_mapq=20, no_dup=True)), (5, 300000, 1, dict()),
+                                (100000, 100100, 1000, dict())):
+        single = {}
+        for stat in config.binned_types:
+            p = ctx.binned_params(stat, start, end, W, ref=ref, ref_start=0, ref_len=len(ref), **kw)
+            single[stat] = np.empty((len(config.value_fields_binned(stat)), int(p.n_bins)), dtype=np.int32)
+            ctx.binned_host(rs, p, single[stat])
+            if (start, end) == (0, G):
+                pos, F = orc.binned_packed(stat, reads, start, end, W, W // 2, ref=ref.tobytes(), **kw)
+                assert np.array_equal(single[stat].T, F), stat
+        subsets = [c for r in range(1, 6) for c in itertools.combinations(config.binned_types, r)]
+        for sub in (subsets if W == 300 else subsets[-6:]):
+            ps = [ctx.binned_params(t, start, end, W, ref=ref, ref_start=0, ref_len=len(ref), **kw) for t in sub]
+            outs = [np.full_like(single[t], -9) for t in sub]
+            ctx.binned_host_multi(rs, ps, outs)
+            for t, o in zip(sub, outs):
+                assert np.array_equal(o, single[t]), (sub, t, W)
+    # device entry point, the bench's sweep
+    dev = torch.device('cuda', ctx.device)
+    db = {k: (torch.from_numpy(np.ascontiguousarray(v)).to(dev) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+    db['flag'] = torch.from_numpy(nb['flag'].view(np.int16)).to(dev)
+    db['cigar'] = torch.from_numpy(nb['cigar'].view(np.int32)).to(dev)
+    rd = _cabi.make_reads_struct(db, n_reads=int(nb['n_reads']))
+    dref = torch.from_numpy(ref).to(dev)
+    sub = ('coverage', 'mapq', 'tlen')
+    ps = [ctx.binned_params(t, 0, G, 300, ref=dref, ref_start=0, ref_len=len(ref)) for t in sub]
+    outs = [torch.full((len(config.value_fields_binned(t)), int(ps[0].n_bins)), -9, dtype=torch.int32, device=dev) for t in sub]
+    ctx.binned_multi(rd, ps, outs, stream=None)
+    ctx.synchronize(None)
+    for t, o in zip(sub, outs):
+        p1 = ctx.binned_params(t, 0, G, 300, ref=ref, ref_start=0, ref_len=len(ref))
+        e = np.empty((len(config.value_fields_binned(t)), int(p1.n_bins)), dtype=np.int32)
+        ctx.binned_host(rs, p1, e)
+        assert np.array_equal(o.cpu().numpy(), e), t
+    # argument errors
+    with pytest.raises(ValueError):
+        ctx.binned_host_multi(rs, [ps[0], ps[0]], [np.empty((3, 1000), np.int32)] * 2)       # host/device mix aside: twice the same statistic
