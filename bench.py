@@ -12,7 +12,12 @@ statistics over the rank's interval.  With N ranks the genome is N x 250 Mb, cut
 interval's reads plus the halo of reads that start before it (weak scaling, no data-path
 collective; torch.distributed only provides the barrier and the max-over-ranks reduction).
 
-Numbers on the JSON line:
+Numbers on the JSON line (besides the headline workload the line carries three more objects, each measured in
+the same run: ``binned`` -- BASELINE.json configs[4], the whole-genome binned sweep coverage_gc + coverage_binned +
+mapq_binned + tlen_binned with window_size 300 on the same reads, with its own value / e2e / per-kernel rooflines /
+cpu_baseline; ``strong_scaling`` -- the ONE 250 Mb contig of configs[2] cut into N shards of 250 / N Mb with read
+halos, device-resident and end to end; ``e2e_api`` -- the public python API from a real BAM + BAI file, decode
+included):
   value     genome positions / s, whole job, read batch resident in HBM, results left in HBM
             (C ABI pss_prepare + pss_pileup_prepared per statistic, CUDA events on the launch
             stream, max over ranks)
@@ -55,6 +60,11 @@ def parse_args():
     ap.add_argument('--cpu-chunk-mb', type=float, default=1.0, help='CPU arm: positions per process, in Mb')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-binned', action='store_true', help='skip the binned sweep (BASELINE.json configs[4])')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling arm (N > 1)')
+    ap.add_argument('--no-e2e-api', action='store_true', help='skip the from-file public API measurement')
+    ap.add_argument('--api-mb', type=float, default=50.0, help='e2e_api: contig length of the BAM written for it, in Mb')
+    ap.add_argument('--window-size', type=int, default=300)
     return ap.parse_args()
 
 
@@ -114,6 +124,26 @@ class ClockSampler(object):
 
 # ----------------------------------------------------------------------- reference arm
 
+BINNED_METRIC = 'genome positions/sec (coverage_gc + coverage_binned + mapq_binned + tlen_binned sweep, window_size 300, synthetic 30x WGS)'
+BINNED_SWEEP = ('coverage', 'mapq', 'tlen')
+ALIGN = 38400      # lcm(512, 300): interval cuts are tile aligned (scatter kernel) AND window aligned (binned sweep)
+
+
+def cpu_binned(args, steps, warmup):
+    """The binned sweep on the CPU restatement of the reference (oracle port), one process per contig chunk."""
+    from oracle import cpu_arm
+    cores = cpu_arm.usable_cores()
+    chunk = int(args.cpu_chunk_mb * 1e6) // 300 * 300
+    res = cpu_arm.run(cores=cores, chunk=chunk, steps=steps, warmup=warmup, depth=args.depth, read_len=args.read_len,
+                      workload='binned')
+    ts = res['step_seconds']
+    mean = sum(ts) / len(ts)
+    return {'value': res['positions_per_step'] / mean, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'reads_per_s': res['reads_per_step'] / mean, 'ms_per_step': mean * 1e3,
+            'sample': '%d contig chunks of %.2f Mb (one per process) of the same synthetic workload per step: stat_coverage_gc + '
+                      'coverage_binned + mapq_binned + tlen_binned, window_size 300' % (cores, chunk / 1e6)}
+
+
 def run_reference(args, rank, world):
     """The reference's CPU implementation of the path on the host cores.  The reference's own
     Cython (pysamstats/opt.pyx) needs pysam/htslib, which are not available offline, so this
@@ -130,6 +160,12 @@ def run_reference(args, rank, world):
     value = res['positions_per_step'] / mean
     sample = ('%d contig chunks of %.2f Mb (one per process, %d processes) of the synthetic 30x / %d bp workload per '
               'step' % (cores, chunk / 1e6, cores, args.read_len))
+    binned = None
+    if not args.no_binned:
+        cb = cpu_binned(args, max(1, min(args.steps, 3)), min(args.warmup, 1))
+        binned = {'metric': BINNED_METRIC, 'value': cb['value'], 'unit': UNIT, 'ms_per_step': cb['ms_per_step'],
+                  'reads_per_s': cb['reads_per_s'], 'cpu_baseline': cb,
+                  'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': mean * 1e3, 'higher_is_better': True,
@@ -138,7 +174,7 @@ def run_reference(args, rank, world):
         'reads_per_s': res['reads_per_step'] / mean,
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
+        'gpu_launches': 0, 'binned': binned,
     }
     print(json.dumps(line), flush=True)
 
@@ -146,10 +182,25 @@ def run_reference(args, rank, world):
 def workload_config(args, n):
     return {'workload': 'synthetic 30x WGS-shaped reads (150 bp paired, 250 Mb contig interval per GPU), '
                         'stat_variation_strand + stat_coverage_ext',
-            'interval_positions_per_gpu': int(args.interval_mb * 1e6), 'depth': args.depth,
+            'interval_positions_per_gpu': int(args.interval_mb * 1e6) // ALIGN * ALIGN, 'depth': args.depth,
             'read_len': args.read_len, 'stats': list(STATS), 'min_baseq': 0, 'stepper': 'all', 'max_depth': 8000,
             'sharding': 'contiguous intervals + read halo, %d shard(s), no collective' % n,
+            'batch': 'records with base qualities (the same arrays the CPU arm gets); these statistics do not read them',
             'l2': 'inputs (> 5 GB of read records) and outputs (68 GB) exceed the 126 MB L2; no flush needed'}
+
+
+def peak_gbs():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def roof(kernel, alg_bytes, ms, n, peak, what):
+    """One per-kernel roofline entry: algorithmic bytes of a launch / its mean CUDA-event time."""
+    ach = alg_bytes / (ms * 1e-3) / 1e9 if ms and ms > 0 else None
+    return {'kernel': kernel, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': (ach / peak) if ach else None,
+            'kernel_ms': ms, 'launches_timed': n, 'algorithmic_bytes_per_launch': int(alg_bytes), 'bytes': what}
 
 
 # ---------------------------------------------------------------------------- main arm
@@ -166,7 +217,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from pysamstats_b200 import _cabi, shard, synth
+    from pysamstats_b200 import _cabi, config, shard, synth
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
@@ -206,105 +257,80 @@ def main():
             return float(t.item())
         return float(x)
 
-    # ---- the rank's shard of the genome ------------------------------------------------
-    per = int(args.interval_mb * 1e6) // shard.TILE * shard.TILE
-    genome = per * world
-    lo, hi = shard.plan_intervals(0, genome, world)[rank]
-    npos = hi - lo
-    t_gen = time.time()
-    batch, (ref, ref_lo) = synth.make_interval_batch(lo, hi, genome, depth=args.depth, read_len=args.read_len,
-                                                     device=dev, with_qual=False)
-    torch.cuda.synchronize()
-    t_gen = time.time() - t_gen
-    n_reads = int(batch['n_reads'])
+    peak, peak_src = peak_gbs()
     ctx = _cabi.Context(local_rank)
-    reads = _cabi.make_reads_struct(batch)
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
-
     nf = {s: int(ctx.lib.pss_pileup_nfields(_cabi.PILEUP_STATS.index(s))) for s in STATS}
-    outs = {s: torch.empty((nf[s], npos), dtype=torch.int32, device=dev) for s in STATS}
-    masks = {s: torch.empty(npos, dtype=torch.uint8, device=dev) for s in STATS}
-    params = {s: ctx.pileup_params(s, start=lo, end=hi, ref=ref if s == 'variation_strand' else None,
-                                   ref_start=ref_lo, ref_len=int(ref.numel()) if s == 'variation_strand' else 0,
-                                   contig_len=genome) for s in STATS}
+    W = args.window_size
 
-    def step():
-        # one preparation of the batch (stepper, depth cap, read filters), then both statistics
-        ctx.prepare(reads, stepper='all', max_depth=8000, stream=sptr)
-        for s in STATS:
-            ctx.pileup_prepared(params[s], outs[s], masks[s], stream=sptr)
+    def device_arm(batch, ref, ref_lo, lo, hi, contig_len, steps, warmup, timing=True):
+        """prepare + variation_strand + coverage_ext over [lo, hi), batch resident in HBM, results left in HBM.
+        Returns (ms per step: CUDA events on the launch stream, launches per run, kernel ms by tag, checksums, rows)."""
+        npos = hi - lo
+        reads = _cabi.make_reads_struct(batch)
+        outs = {s: torch.empty((nf[s], npos), dtype=torch.int32, device=dev) for s in STATS}
+        masks = {s: torch.empty(npos, dtype=torch.uint8, device=dev) for s in STATS}
+        params = {s: ctx.pileup_params(s, start=lo, end=hi, ref=ref if s == 'variation_strand' else None,
+                                       ref_start=ref_lo, ref_len=int(ref.numel()) if s == 'variation_strand' else 0,
+                                       contig_len=contig_len) for s in STATS}
 
-    # ---- device-resident throughput -----------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    ctx.synchronize(sptr)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ctx.set_kernel_timing(True)
-    ctx.pileup_kernel_ms(-1)
-    l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    dev_ms = e0.elapsed_time(e1) / args.steps
-    launches = ctx.launch_count() - l0
-    kms = {s: ctx.pileup_kernel_ms(s) for s in STATS}
-    ctx.set_kernel_timing(False)
-    ctx.synchronize(sptr)
-    dev_ms = max_over_ranks(dev_ms)
-    total_pos = sum_over_ranks(npos)
-    total_reads = sum_over_ranks(n_reads)
-    value = total_pos / (dev_ms * 1e-3)
+        def step():
+            # one preparation of the batch (stepper, depth cap, read filters), then both statistics
+            ctx.prepare(reads, stepper='all', max_depth=8000, stream=sptr)
+            for s in STATS:
+                ctx.pileup_prepared(params[s], outs[s], masks[s], stream=sptr)
 
-    # checksum of checksums (a size-independent sanity check, printed to stderr)
-    chk = {s: int(outs[s][0].sum(dtype=torch.int64).item()) for s in STATS}
-    rows = int(masks['variation_strand'].sum(dtype=torch.int64).item())
-
-    # ---- roofline of the dominant kernel (rank 0's launch) --------------------------------
-    n_cig = int(batch['n_cigar_words'])
-    n_seq = int(batch['n_seq_bytes'])
-    alg_bytes = npos * (4 * nf['variation_strand'] + 1 + 1) + n_reads * 29 + 4 * n_cig + n_seq
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    # DRAM traffic of the same kernel on the same workload from one `ncu --set full` capture
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if int(tj.get('interval_positions', -1)) == per:
-            traffic = tj['traffic_bytes_per_launch']
-    k_ms, k_n = kms['variation_strand']
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-    roofline = {'bound': 'hbm', 'kernel': 'k_tile<KIND_VAR, PSS_VARIATION_STRAND>', 'achieved': achieved,
-                'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
-                'peak_source': peak_src, 'kernel_ms': k_ms, 'kernel_launches_timed': k_n,
-                'algorithmic_bytes_per_launch': alg_bytes,
-                'kernel_share_of_step': (k_ms / dev_ms) if k_ms > 0 else None,
-                'coverage_ext_kernel_ms': kms['coverage_ext'][0]}
-
-    # ---- end to end through the host-buffer C ABI ------------------------------------------
-    e2e = None
-    if not args.no_e2e:
+        for _ in range(warmup):
+            step()
+        ctx.synchronize(sptr)
+        ctx.set_kernel_timing(timing)
+        ctx.pileup_kernel_ms(-1)
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        launches = ctx.launch_count() - l0
+        kms = {s: ctx.pileup_kernel_ms(s) for s in STATS}
+        kms['prep'] = ctx.pileup_kernel_ms(_cabi.KTAG_PREP)
+        ctx.set_kernel_timing(False)
+        ctx.pileup_kernel_ms(-1)
+        ctx.synchronize(sptr)
+        # checksum of checksums (a size-independent sanity check)
+        chk = {s: int(outs[s][0].sum(dtype=torch.int64).item()) for s in STATS}
+        rows = int(masks['variation_strand'].sum(dtype=torch.int64).item())
         del outs, masks
-        torch.cuda.empty_cache()
+        return ms, launches, kms, chk, rows
+
+    def host_copy(batch, ref):
+        """Pinned host copies of the record arrays these statistics read (the decoder's output in a real run)."""
         hb = {}
-        for k in _cabi.READ_FIELDS:
-            v = batch.get(k)
-            hb[k] = v.cpu().pin_memory().numpy() if torch.is_tensor(v) else None
+        for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'cigar', 'seq_off', 'seq4'):
+            hb[k] = batch[k].cpu().pin_memory().numpy()
         hb['flag'] = hb['flag'].view(np.uint16)
         hb['cigar'] = hb['cigar'].view(np.uint32)
-        endpos = batch['endpos'].cpu().numpy()
-        maxspan = int((endpos - hb['pos']).max()) if n_reads else 1
-        ref_h = ref.cpu().pin_memory().numpy()
+        hb['endpos'] = batch['endpos'].cpu().numpy()
+        hb['maxspan'] = int((hb['endpos'] - hb['pos']).max()) if len(hb['pos']) else 1
+        return hb, ref.cpu().pin_memory().numpy()
+
+    def host_view(hb, c_lo, c_hi):
+        """struct pss_reads over the sub-range of the pinned batch that overlaps [c_lo, c_hi) (zero copy)."""
+        i0, i1, _ = shard.halo_range(hb['pos'], hb['endpos'], c_lo, c_hi, maxspan=hb['maxspan'], mask=False)
+        view = dict(n_reads=i1 - i0, tid=0)
+        for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off'):
+            view[k] = hb[k][i0:]
+        view['cigar'], view['seq4'] = hb['cigar'], hb['seq4']
+        return _cabi.make_reads_struct(view, n_reads=i1 - i0)
+
+    def e2e_arm(hb, ref_h, ref_lo, lo, hi, contig_len, steps, warmup, expect):
+        """The same statistics through pss_pileup_host_multi: pinned HOST arrays in, HOST int32 columns out, every copy
+        inside the timed region (wall clock).  Returns (seconds per step, h2d bytes, d2h bytes per step, chunk)."""
+        npos = hi - lo
         chunk = max(shard.TILE, int(args.e2e_chunk_mb * 1e6) // shard.TILE * shard.TILE)
         chunk = min(chunk, npos)
         inner = max(shard.TILE, int(args.e2e_inner_mb * 1e6) // shard.TILE * shard.TILE)
@@ -315,12 +341,7 @@ def main():
         def e2e_step(check=False):
             for c_lo in range(lo, hi, chunk):
                 c_hi = min(hi, c_lo + chunk)
-                i0, i1, _ = shard.halo_range(hb['pos'], endpos, c_lo, c_hi, maxspan=maxspan, mask=False)
-                view = dict(n_reads=i1 - i0, tid=0)
-                for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off'):
-                    view[k] = hb[k][i0:]
-                view['cigar'], view['seq4'] = hb['cigar'], hb['seq4']
-                rs = _cabi.make_reads_struct(view, n_reads=i1 - i0)
+                rs = host_view(hb, c_lo, c_hi)
                 n = c_hi - c_lo
                 r0 = c_lo - ref_lo
                 ps, os_, ms = [], [], []
@@ -328,43 +349,255 @@ def main():
                     withref = s == 'variation_strand'
                     ps.append(ctx.pileup_params(s, start=c_lo, end=c_hi, ref=ref_h[r0:] if withref else None,
                                                 ref_start=c_lo, ref_len=(c_hi - c_lo) if withref else 0,
-                                                contig_len=genome))
+                                                contig_len=contig_len))
                     os_.append(oh[s] if n == chunk else np.ndarray((nf[s], n), dtype=np.int32, buffer=oh[s]))
                     ms.append(mh[s])
                 # one call per position chunk: the reads go up once, both statistics come back
                 if args.e2e_stream:
-                    ctx.pileup_host_stream(rs, ps, os_, ms, maxspan, inner)
+                    ctx.pileup_host_stream(rs, ps, os_, ms, hb['maxspan'], inner)
                 else:
                     ctx.pileup_host_multi(rs, ps, os_, ms)
                 if check:
                     for s, o in zip(STATS, os_):
                         checks[s] = checks.get(s, 0) + int(o[0].sum(dtype=np.int64))
 
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(max(1, min(warmup, 2))):
             checks.clear()
             e2e_step(check=True)
-        assert checks == chk, ('host path disagrees with the device path', checks, chk)
+        assert checks == expect, ('host path disagrees with the device path', checks, expect)
         h0, d0 = ctx.transfer_bytes()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             e2e_step()
         torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / args.steps
+        sec = (time.perf_counter() - t0) / steps
         barrier()
         h1, d1 = ctx.transfer_bytes()
+        return sec, (h1 - h0) / steps, (d1 - d0) / steps, chunk, inner
+
+    # ---- the rank's shard of the genome ------------------------------------------------
+    per = int(args.interval_mb * 1e6) // ALIGN * ALIGN
+    genome = per * world
+    lo, hi = shard.plan_intervals(0, genome, world, align=ALIGN)[rank]
+    npos = hi - lo
+    t_gen = time.time()
+    batch, (ref, ref_lo) = synth.make_interval_batch(lo, hi, genome, depth=args.depth, read_len=args.read_len,
+                                                     device=dev, with_qual=True)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    n_reads = int(batch['n_reads'])
+
+    # ---- device-resident throughput -----------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, launches, kms, chk, rows = device_arm(batch, ref, ref_lo, lo, hi, genome, args.steps, args.warmup)
+    dev_ms = max_over_ranks(dev_ms)
+    total_pos = sum_over_ranks(npos)
+    total_reads = sum_over_ranks(n_reads)
+    value = total_pos / (dev_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank 0's launch) --------------------------------
+    n_cig = int(batch['n_cigar_words'])
+    n_seq = int(batch['n_seq_bytes'])
+    alg_bytes = npos * (4 * nf['variation_strand'] + 1 + 1) + n_reads * 29 + 4 * n_cig + n_seq
+    # DRAM traffic of the same kernel on the same workload from one `ncu --set full` capture
+    traffic = None
+    for tname in ('r02_traffic.json', 'r01_traffic.json'):
+        tpath = os.path.join(ROOT, 'profiles', tname)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if int(tj.get('interval_positions', -1)) == per:
+                traffic = tj['traffic_bytes_per_launch']
+                break
+    k_ms, k_n = kms['variation_strand']
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    roofline = {'bound': 'hbm', 'kernel': 'k_tile<KIND_VAR, PSS_VARIATION_STRAND>', 'achieved': achieved,
+                'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
+                'peak_source': peak_src, 'kernel_ms': k_ms, 'kernel_launches_timed': k_n,
+                'algorithmic_bytes_per_launch': alg_bytes,
+                'kernel_share_of_step': (k_ms / dev_ms) if k_ms > 0 else None,
+                'coverage_ext_kernel_ms': kms['coverage_ext'][0], 'prepare_ms': kms['prep'][0]}
+
+    # ---- the binned sweep (BASELINE.json configs[4]) on the same reads, device resident ----------------------------
+    binned = None
+    if not args.no_binned:
+        # binned statistics are keyed by read START: the rank's reads are those starting in its windows (bin edges use
+        # the genome's start, so they agree between ranks; no halo)
+        nbins_all = genome // W if genome % W == 0 else genome // W + 1
+        pos_h = batch['pos'].cpu().numpy()
+        i0, i1 = shard.window_read_range(pos_h, 0, W, lo // W, -(-hi // W), nbins_all)
+        n_bin_reads = i1 - i0
+        sub = {k: (batch[k][i0:] if k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off') else batch[k])
+               for k in _cabi.READ_FIELDS if batch.get(k) is not None}
+        sub['tid'] = 0
+        rs_bin = _cabi.make_reads_struct(sub, n_reads=n_bin_reads)
+        rs_all = _cabi.make_reads_struct(batch)
+        bps = [ctx.binned_params(t, lo, hi, W, ref=ref, ref_start=ref_lo, ref_len=int(ref.numel())) for t in BINNED_SWEEP]
+        nwin = int(bps[0].n_bins)
+        bouts = [torch.empty((len(config.value_fields_binned(t)), nwin), dtype=torch.int32, device=dev) for t in BINNED_SWEEP]
+        gp = ctx.pileup_params('coverage_gc', start=lo, end=hi, ref=ref, ref_start=ref_lo, ref_len=int(ref.numel()),
+                               contig_len=genome, window_size=W)
+        gout = torch.empty((3, npos), dtype=torch.int32, device=dev)
+        gmask = torch.empty(npos, dtype=torch.uint8, device=dev)
+
+        def bstep():
+            ctx.pileup(rs_all, gp, gout, gmask, stream=sptr)           # prepare + coverage (tile kernel) + sliding GC%
+            ctx.binned_multi(rs_bin, bps, bouts, stream=sptr)          # the three binned statistics, records read once
+
+        for _ in range(args.warmup):
+            bstep()
+        ctx.synchronize(sptr)
+        ctx.set_kernel_timing(True)
+        ctx.pileup_kernel_ms(-1)
+        bl0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            bstep()
+        e1.record(stream)
+        barrier()
+        b_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        b_launches = ctx.launch_count() - bl0
+        tags = {'k_tile<KIND_COV, PSS_COVERAGE_GC>': 'coverage_gc', 'k_gc': _cabi.KTAG_GC, 'k_prep (+ depth cap)': _cabi.KTAG_PREP,
+                'k_binned_acc<coverage | mapq | tlen>': _cabi.KTAG_BINNED_ACC, 'k_binned_fin': _cabi.KTAG_BINNED_FIN,
+                'k_binned_gc': _cabi.KTAG_BINNED_GC}
+        bk = {name: ctx.pileup_kernel_ms(tag) for name, tag in tags.items()}
+        ctx.set_kernel_timing(False)
+        ctx.pileup_kernel_ms(-1)
+        ctx.synchronize(sptr)
+        nfb = sum(len(config.value_fields_binned(t)) for t in BINNED_SWEEP)
+        # algorithmic bytes per launch: what the kernel must read and write once
+        rl = [
+            roof('k_tile<KIND_COV, PSS_COVERAGE_GC>', npos * (4 * 2 + 1) + n_reads * 29 + 4 * n_cig, *bk['k_tile<KIND_COV, PSS_COVERAGE_GC>'], peak,
+                 '2 int32 columns + row mask per position; 29 B record + CIGAR words per read'),
+            roof('k_prep (+ depth cap)', n_reads * (29 + 8 + 32) + 4 * n_cig, *bk['k_prep (+ depth cap)'], peak,
+                 '29 B record + 8 B sequence offset + CIGAR words read, 32 B RInfo written per read'),
+            roof('k_gc', npos * (1 + 4), *bk['k_gc'], peak, '1 reference byte read + 1 int32 written per position'),
+            roof('k_binned_acc<coverage | mapq | tlen>', n_bin_reads * 11 + nwin * (3 * 4 + 5 * 8), *bk['k_binned_acc<coverage | mapq | tlen>'], peak,
+                 'pos 4 + flag 2 + mapq 1 + tlen 4 B per read, read ONCE for the three statistics; 3 counts + 5 sums per window'),
+            roof('k_binned_gc', npos + 4 * nwin, *bk['k_binned_gc'], peak, '1 reference byte per position, 1 int32 per window'),
+            roof('k_binned_fin', nwin * (3 * 4 + 5 * 8 + 4 * (nfb - 1)), *bk['k_binned_fin'], peak, 'accumulators read, int32 columns written per window'),
+        ]
+        alg_sweep = sum(r['algorithmic_bytes_per_launch'] for r in rl)
+        bchk = {t: int(o[1 if t == 'coverage' else 0].sum(dtype=torch.int64).item()) for t, o in zip(BINNED_SWEEP, bouts)}
+        bchk['coverage_gc'] = int(gout[1].sum(dtype=torch.int64).item())       # fields: gc, reads_all, reads_pp
+        bchk['gc'] = int(gout[0].sum(dtype=torch.int64).item())
+        assert bchk['coverage'] == bchk['mapq'] == bchk['tlen'] == sum_mapped_reads(batch, i0, i1), bchk    # every mapped read in exactly one window
+        assert bchk['coverage_gc'] == chk['coverage_ext'], (bchk, chk)                                        # same coverage as the pileup arm
+        binned = {'metric': BINNED_METRIC, 'value': total_pos / (b_ms * 1e-3), 'unit': UNIT, 'ms_per_step': b_ms,
+                  'reads_per_s': total_reads / (b_ms * 1e-3), 'windows_per_s': sum_over_ranks(nwin) / (b_ms * 1e-3),
+                  'scaling': 'weak', 'n_gpus': world, 'gpu_launches': int(b_launches),
+                  'config': {'workload': 'the same synthetic 30x reads; stat_coverage_gc (per position) + coverage_binned + mapq_binned + '
+                                         'tlen_binned (per window), window_size %d, default offset' % W,
+                             'sharding': 'contiguous window ranges (global bin edges), reads by start window, %d shard(s), no collective' % world,
+                             'windows_per_gpu': nwin, 'binned_reads_per_gpu': n_bin_reads},
+                  'roofline': dict(rl[3], peak_source=peak_src, kernel_share_of_step=(rl[3]['kernel_ms'] / b_ms) if rl[3]['kernel_ms'] else None),
+                  'kernels': rl,
+                  'sweep_algorithmic_bytes': int(alg_sweep), 'sweep_frac_of_peak': alg_sweep / (b_ms * 1e-3) / 1e9 / peak,
+                  'checksum_rank0': bchk}
+        del gout, gmask, bouts
+
+    # ---- strong scaling: ONE 250 Mb contig cut into `world` shards (BASELINE.json configs[2] as written) ------------------
+    strong = None
+    if not args.no_strong:
+        if world == 1:
+            strong = {'contig_positions': per, 'shards': 1, 'value': value, 'unit': UNIT, 'ms_per_step': dev_ms,
+                      'note': 'one shard = the headline workload'}
+        else:
+            s_lo, s_hi = shard.plan_intervals(0, per, world, align=shard.TILE)[rank]
+            sb, (sref, sref_lo) = synth.make_interval_batch(s_lo, s_hi, per, depth=args.depth, read_len=args.read_len,
+                                                            device=dev, with_qual=True)
+            torch.cuda.synchronize()
+            s_ms, s_launches, s_kms, s_chk, s_rows = device_arm(sb, sref, sref_lo, s_lo, s_hi, per, max(args.steps, 20), args.warmup)
+            s_ms = max_over_ranks(s_ms)
+            strong = {'contig_positions': per, 'shards': world, 'shard_positions_rank0': s_hi - s_lo,
+                      'shard_reads_rank0': int(sb['n_reads']), 'value': per / (s_ms * 1e-3), 'unit': UNIT, 'ms_per_step': s_ms,
+                      'launches_per_step': s_launches / max(args.steps, 20),
+                      'kernel_ms_rank0': {'variation_strand': s_kms['variation_strand'][0], 'coverage_ext': s_kms['coverage_ext'][0],
+                                          'prepare': s_kms['prep'][0]},
+                      'scaling': 'strong', 'sharding': 'plan_intervals(0, contig, N) cuts aligned to %d + read halo; no collective' % shard.TILE,
+                      'checksum_sum_over_ranks': {k: int(sum_over_ranks(v)) for k, v in s_chk.items()}}
+            if not args.no_e2e:
+                shb, sref_h = host_copy(sb, sref)
+                sec, h2d, d2h, _, _ = e2e_arm(shb, sref_h, sref_lo, s_lo, s_hi, per, max(2, min(args.steps, 5)), 1, s_chk)
+                sec = max_over_ranks(sec)
+                strong['e2e'] = {'value': per / sec, 'unit': UNIT, 'ms_per_step': sec * 1e3,
+                                 'h2d_bytes_per_step': int(sum_over_ranks(h2d)), 'd2h_bytes_per_step': int(sum_over_ranks(d2h))}
+                del shb, sref_h
+            del sb, sref
+
+    # ---- end to end through the host-buffer C ABI ------------------------------------------
+    e2e = None
+    hb = ref_h = None
+    if not args.no_e2e:
+        torch.cuda.empty_cache()
+        hb, ref_h = host_copy(batch, ref)
+        e2e_s, h2d, d2h, chunk, inner = e2e_arm(hb, ref_h, ref_lo, lo, hi, genome, args.steps, args.warmup, chk)
         e2e_s = max_over_ranks(e2e_s)
         e2e = {'value': total_pos / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
-               'h2d_bytes_per_step': int(sum_over_ranks((h1 - h0) / args.steps)),
-               'd2h_bytes_per_step': int(sum_over_ranks((d1 - d0) / args.steps)),
+               'h2d_bytes_per_step': int(sum_over_ranks(h2d)), 'd2h_bytes_per_step': int(sum_over_ranks(d2h)),
                'api': ('pss_pileup_host_stream (pinned host read arrays in, host int32 columns of both statistics out), '
                        '%d calls of %d positions per step, reads uploaded in pieces of %d positions'
                        % (-(-npos // chunk), chunk, inner)) if args.e2e_stream else
                       ('pss_pileup_host_multi (pinned host read arrays in, host int32 columns of both statistics out), '
                        '%d position chunks of %d per step' % (-(-npos // chunk), chunk))}
-    clocks = sampler.stop() if rank == 0 else None
+        # ---- the binned sweep end to end: pss_pileup_host (coverage_gc) per position chunk + pss_binned_host_multi
+        if binned is not None:
+            gchunk = chunk
+            go = torch.empty((3, gchunk), dtype=torch.int32).pin_memory().numpy()
+            gm = torch.empty(gchunk, dtype=torch.uint8).pin_memory().numpy()
+            bo = [torch.empty((len(config.value_fields_binned(t)), nwin), dtype=torch.int32).pin_memory().numpy() for t in BINNED_SWEEP]
+            hview = dict(n_reads=n_bin_reads, tid=0)
+            for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off'):
+                hview[k] = hb[k][i0:]
+            hview['cigar'], hview['seq4'] = hb['cigar'], hb['seq4']
+            rs_bin_h = _cabi.make_reads_struct(hview, n_reads=n_bin_reads)
+            bps_h = [ctx.binned_params(t, lo, hi, W, ref=ref_h, ref_start=ref_lo, ref_len=len(ref_h)) for t in BINNED_SWEEP]
+            bsum = {}
 
-    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
+            def be2e_step(check=False):
+                for c_lo in range(lo, hi, gchunk):
+                    c_hi = min(hi, c_lo + gchunk)
+                    n = c_hi - c_lo
+                    # the chunk's reference span plus the GC windows reaching beyond it
+                    r_lo, r_hi = max(ref_lo, c_lo - W), min(ref_lo + len(ref_h), c_hi + W)
+                    p = ctx.pileup_params('coverage_gc', start=c_lo, end=c_hi, ref=ref_h[r_lo - ref_lo:], ref_start=r_lo,
+                                          ref_len=r_hi - r_lo, contig_len=genome, window_size=W)
+                    o = go if n == gchunk else np.ndarray((3, n), dtype=np.int32, buffer=go)
+                    ctx.pileup_host(host_view(hb, c_lo, c_hi), p, o, gm)
+                    if check:
+                        bsum['coverage_gc'] = bsum.get('coverage_gc', 0) + int(o[1].sum(dtype=np.int64))
+                        bsum['gc'] = bsum.get('gc', 0) + int(o[0].sum(dtype=np.int64))
+                ctx.binned_host_multi(rs_bin_h, bps_h, bo)
+                if check:
+                    for t, o in zip(BINNED_SWEEP, bo):
+                        bsum[t] = int(o[1 if t == 'coverage' else 0].sum(dtype=np.int64))
+
+            be2e_step(check=True)
+            assert bsum == binned['checksum_rank0'], ('binned host path disagrees with the device path', bsum, binned['checksum_rank0'])
+            h0, d0 = ctx.transfer_bytes()
+            barrier()
+            t0 = time.perf_counter()
+            bsteps = max(2, min(args.steps, 5))
+            for _ in range(bsteps):
+                be2e_step()
+            torch.cuda.synchronize()
+            bsec = max_over_ranks((time.perf_counter() - t0) / bsteps)
+            barrier()
+            h1, d1 = ctx.transfer_bytes()
+            binned['e2e'] = {'value': total_pos / bsec, 'unit': UNIT, 'ms_per_step': bsec * 1e3, 'steps': bsteps,
+                             'h2d_bytes_per_step': int(sum_over_ranks((h1 - h0) / bsteps)),
+                             'd2h_bytes_per_step': int(sum_over_ranks((d1 - d0) / bsteps)),
+                             'api': 'pss_pileup_host (coverage_gc; %d position chunks of %d) + pss_binned_host_multi (coverage, mapq, tlen in one '
+                                    'call): pinned host read arrays in, host int32 columns out' % (-(-npos // gchunk), gchunk)}
+            del go, gm, bo
+    clocks = sampler.stop() if rank == 0 else None
+    del hb, ref_h
+
+    # ---- CPU baselines (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_arm
@@ -376,31 +609,16 @@ def main():
                'sample': '%d contig chunks of %.2f Mb, one process each, same synthetic workload and statistics; '
                          '%.1f s wall' % (cores, cchunk / 1e6, cs),
                'reads_per_s': res['reads_per_step'] / cs}
+        if binned is not None:
+            binned['cpu_baseline'] = cpu_binned(args, 1, 0)
 
-    # ---- host decode (rank 0, N = 1): synthetic BAM slice -> SoA through csrc/pss_host.cpp ----------
-    host_decode = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # ---- the public python API from a real BAM + BAI (rank 0, N = 1): decode included ----------------------
+    e2e_api = None
+    if rank == 0 and world == 1 and not args.no_e2e_api:
         try:
-            import tempfile
-            from pysamstats_b200 import bamio
-            sl = 8 * 1000 * 1000
-            sb, _ = synth.make_interval_batch(0, sl, sl, depth=args.depth, read_len=args.read_len, device=dev,
-                                              with_qual=True)
-            snb = synth.batch_to_numpy(sb)
-            with tempfile.TemporaryDirectory() as tmp:
-                path = os.path.join(tmp, 'slice.bam')
-                bamio.write_bam(path, ['chrS'], [sl], snb, level=1)
-                t0 = time.perf_counter()
-                bf = bamio.BamFile(path).load()
-                dt = time.perf_counter() - t0
-                host_decode = {'reads_per_s': snb['n_reads'] / dt, 'seconds': dt, 'reads': int(snb['n_reads']),
-                               'bam_bytes': os.path.getsize(path), 'raw_bytes': bf.decode_seconds['raw_bytes'],
-                               'inflate_seconds': bf.decode_seconds['inflate'], 'threads': os.cpu_count(),
-                               'what': 'BGZF inflate + BAM parse of an 8 Mb slice of the workload written as a real BAM '
-                                       '(libpss_host.so); not part of value / e2e'}
-            del sb, snb
-        except Exception as e:   # noqa: BLE001 -- informative only
-            host_decode = {'error': repr(e)}
+            e2e_api = run_e2e_api(args, dev)
+        except Exception as e:   # noqa: BLE001 -- reported, the headline numbers stand
+            e2e_api = {'error': repr(e)}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -408,12 +626,71 @@ def main():
                 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, world),
                 'reads_per_s': total_reads / (dev_ms * 1e-3), 'gpu_launches': int(launches),
                 'e2e': e2e, 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
-                'host_decode': host_decode, 'reads_per_gpu': n_reads, 'rows_emitted_rank0': rows, 'checksum_rank0': chk,
+                'binned': binned, 'strong_scaling': strong, 'e2e_api': e2e_api,
+                'reads_per_gpu': n_reads, 'rows_emitted_rank0': rows, 'checksum_rank0': chk,
                 'setup_seconds': {'synthetic_batch': t_gen}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def sum_mapped_reads(batch, i0, i1):
+    """Reads of batch[i0:i1] every BinnedStat.recv counts (mapped: flag & 4 == 0) -- the binned checksum."""
+    f = batch['flag'][i0:i1]
+    return int(((f & 4) == 0).sum().item())
+
+
+def run_e2e_api(args, dev):
+    """What a pysamstats user experiences: ``load_variation_strand(bam, fasta)`` + ``load_coverage_ext(bam)`` on the
+    synthetic workload written as a real BAM + BAI + FASTA, cold (decode included), host record arrays out."""
+    import tempfile
+    import numpy as np
+    import pysamstats_b200 as pysamstats
+    from pysamstats_b200 import bamio, synth
+    L = int(args.api_mb * 1e6) // ALIGN * ALIGN
+    sb, (sref, sref_lo) = synth.make_interval_batch(0, L, L, depth=args.depth, read_len=args.read_len, device=dev, with_qual=True)
+    snb = synth.batch_to_numpy(sb)
+    ref_ascii = sref.cpu().numpy()
+    del sb
+    out = {'contig_positions': L, 'reads': int(snb['n_reads'])}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, 'wgs.bam')
+        fa = os.path.join(tmp, 'wgs.fa')
+        t0 = time.perf_counter()
+        bamio.write_bam(path, ['chrS'], [L], snb, level=1)
+        bamio.index_bam(path)
+        with open(fa, 'wb') as fh:
+            fh.write(b'>chrS\n')
+            fh.write(ref_ascii[:L].tobytes())
+            fh.write(b'\n')
+        out['write_seconds'] = time.perf_counter() - t0
+        out['bam_bytes'] = os.path.getsize(path)
+        del snb
+        rows = 0
+        for rep in ('cold', 'warm'):
+            if rep == 'cold':
+                bamio._bam_cache.clear()
+                bamio._fa_cache.clear()
+            t0 = time.perf_counter()
+            a = pysamstats.load_variation_strand(path, fa, chrom='chrS')
+            t1 = time.perf_counter()
+            b = pysamstats.load_coverage_ext(path, chrom='chrS')
+            t2 = time.perf_counter()
+            rows = len(a)
+            out[rep] = {'load_variation_strand_s': t1 - t0, 'load_coverage_ext_s': t2 - t1,
+                        'positions_per_s': L / (t2 - t0), 'rows': rows, 'row_bytes': a.dtype.itemsize + b.dtype.itemsize}
+            assert int(a['reads_all'].astype(np.int64).sum()) == int(b['reads_all'].astype(np.int64).sum())
+            del a, b
+        bf = bamio.open_bam(path)
+        if getattr(bf, 'decode_seconds', None):
+            out['decode'] = dict(bf.decode_seconds)
+    out['value'] = out['cold']['positions_per_s']
+    out['unit'] = UNIT
+    out['api'] = ('pysamstats.load_variation_strand(bam, fasta, chrom) + load_coverage_ext(bam, chrom) on a %.0f Mb synthetic 30x BAM '
+                  '(BGZF level 1) + BAI + FASTA; cold = first call in the process (BGZF inflate + BAM parse inside), warm = decoded '
+                  'batch cached; result = packed host record arrays' % (L / 1e6))
+    return out
 
 
 if __name__ == '__main__':
