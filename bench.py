@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument('--no-binned', action='store_true', help='skip the binned sweep (BASELINE.json configs[4])')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling arm (N > 1)')
     ap.add_argument('--no-e2e-api', action='store_true', help='skip the from-file public API measurement')
-    ap.add_argument('--api-mb', type=float, default=50.0, help='e2e_api: contig length of the BAM written for it, in Mb')
+    ap.add_argument('--api-mb', type=float, default=250.0, help='e2e_api: contig length of the BAM written for it, in Mb')
     ap.add_argument('--window-size', type=int, default=300)
     return ap.parse_args()
 

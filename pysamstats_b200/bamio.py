@@ -335,6 +335,7 @@ class BamFile(object):
             self._init_numpy()
         self._tid_of = {r: i for i, r in enumerate(self.references)}
         self._contig_cache = {}
+        self._piece_cache = {}
 
     def _read_header(self, lib, h):
         nref = lib.pss_bam_n_ref(h)
@@ -406,7 +407,7 @@ class BamFile(object):
         finally:
             lib.pss_bam_close(h)
         b.tid = tid
-        b.name_prev = _name_prev(b.names)
+        b.name_prev = None                      # hashed on first use (only requests that read base qualities need it)
         if b.n_reads > 1 and np.any(np.diff(b.pos) < 0):
             raise ValueError('BAM file is not coordinate sorted: %r' % self.filename)
         return b
@@ -510,6 +511,56 @@ class BamFile(object):
                 raise ValueError('BAM file is not coordinate sorted: %r' % self.filename)
             self._contig_cache[chrom] = b
         return self._contig_cache[chrom]
+
+    def can_stream(self, chrom):
+        """True when the records of ``chrom`` can be decoded piece by piece through the BAI index (native decoder, an
+        index next to a file of at least PSS_BAI_MIN_BYTES) and are not already decoded in this process."""
+        if os.environ.get('PSS_NO_STREAM') or self._all is not None or chrom in self._contig_cache or host_lib() is None:
+            return False
+        return self.index_path() is not None and \
+            os.path.getsize(self.filename) >= int(os.environ.get('PSS_BAI_MIN_BYTES', 32 << 20))
+
+    def piece_batches(self, chrom, cuts, ahead=2):
+        """The records overlapping each of the consecutive position pieces ``[cuts[k], cuts[k + 1])`` of ``chrom``, as a
+        generator of ReadBatch -- the host half of the decode -> upload -> compute pipeline (SURVEY.md section 8f N3;
+        the reference streams reads as htslib inflates them, ``opt.pyx:1853-1854``, ``:2038-2048``): piece k + 1 and
+        k + 2 are inflated and parsed through the BAI index (``pss_bam_open_region``, all host threads) on a background
+        threads while the caller uploads / computes / packs piece k.  The decoded pieces are kept (``_piece_cache``), so a
+        second statistic over the same pieces does not decode again.  Yields None (once, and stops) if the index turns
+        out to be unusable."""
+        key = (chrom, tuple(int(c) for c in cuts))
+        cached = self._piece_cache.get(key)
+        if cached is not None:
+            for b in cached:
+                yield b
+            return
+        tid, bai = self._tid_of[chrom], self.index_path()
+        n = len(cuts) - 1
+        done = []
+        # (three decodes at a time: the serial parts of one -- index lookup, record walk -- run beside the threaded
+        # inflate / fill of the others)
+        with ThreadPoolExecutor(1 + ahead) as ex:
+            futs = {}
+
+            def want(k):
+                if k < n and k not in futs:
+                    futs[k] = ex.submit(self._region_native, tid, cuts[k], cuts[k + 1], bai)
+            for k in range(min(n, 1 + ahead)):
+                want(k)
+            for k in range(n):
+                b = futs.pop(k).result()
+                want(k + 1 + ahead)
+                if b is None:
+                    for f in futs.values():
+                        f.cancel()
+                    yield None
+                    return
+                done.append(b)
+                if k == n - 1:           # (before the last yield: the consumer may not come back for a StopIteration)
+                    if len(self._piece_cache) >= 2:
+                        self._piece_cache.pop(next(iter(self._piece_cache)))
+                    self._piece_cache[key] = done
+                yield b
 
     def region_batch(self, chrom, start, end):
         """Records the region iterator yields for chrom:[start, end)."""

@@ -95,7 +95,7 @@ struct FileMap {
     const uint8_t *p = nullptr;
     size_t n = 0;
     ~FileMap() { if (p) munmap((void *)p, n); }
-    bool open(const char *path) {
+    bool open(const char *path, bool whole = true) {      // whole: the entire file is about to be read front to back
         int fd = ::open(path, O_RDONLY);
         if (fd < 0) return false;
         struct stat st;
@@ -105,8 +105,10 @@ struct FileMap {
         void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
         ::close(fd);
         if (m == MAP_FAILED) { n = 0; return false; }
-        madvise(m, n, MADV_SEQUENTIAL);
-        madvise(m, n, MADV_WILLNEED);
+        if (whole) {
+            madvise(m, n, MADV_SEQUENTIAL);
+            madvise(m, n, MADV_WILLNEED);
+        }
         p = (const uint8_t *)m;
         return true;
     }
@@ -480,7 +482,11 @@ extern "C" int pss_bam_open_region(const char *path, const char *bai_path, int32
     // ---- the compressed bytes of every chunk, its block table
     struct Piece { int64_t file_lo, file_hi; size_t comp_off; int64_t first_blk, n_blk; int64_t start, stop; };   // start / stop: offsets in raw
     std::vector<Piece> pieces;
-    std::vector<uint8_t> comp;
+    // the compressed bytes are used where they lie in the page cache (a mapping of the file, no copy): comp_off and
+    // the blocks' in_off are file offsets
+    FileMap fmap;
+    if (!fmap.open(path, false)) return fail(-2, "cannot map %s", path);
+    struct { const uint8_t *p; const uint8_t *data() const { return p; } } comp{fmap.p};
     std::vector<Blk> blocks;
     int64_t total = 0;
     for (const Chunk &c : chunks) {
@@ -498,9 +504,8 @@ extern "C" int pss_bam_open_region(const char *path, const char *bai_path, int32
             hi = last + bs;
         }
         if (hi > fsize) hi = fsize;
-        Piece pc{lo, hi, comp.size(), (int64_t)blocks.size(), 0, 0, 0};
-        comp.resize(comp.size() + (size_t)(hi - lo));
-        if (!read_at(lo, hi - lo, comp.data() + pc.comp_off)) return fail(-2, "read error on %s", path);
+        Piece pc{lo, hi, (size_t)lo, (int64_t)blocks.size(), 0, 0, 0};
+        madvise((void *)(fmap.p + (lo & ~(int64_t)4095)), (size_t)(hi - (lo & ~(int64_t)4095)), MADV_WILLNEED);
         int64_t off = 0;
         pc.start = total + (int64_t)(c.beg & 0xffff);
         pc.stop = -1;

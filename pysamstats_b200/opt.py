@@ -118,7 +118,9 @@ def _reads_struct(batch, need_qual):
     if not need_qual:
         d['qual'] = d['qual_off'] = d['name_prev'] = None
         d['n_qual_bytes'] = 0
-    return _cabi.make_reads_struct(d)
+    r = _cabi.make_reads_struct(d)
+    r._keep = batch             # the struct holds raw addresses: the arrays live as long as it does
+    return r
 
 
 def _ref_column(refseq, pos):
@@ -134,11 +136,72 @@ def _ref_column(refseq, pos):
 
 # ------------------------------------------------------------------------ pileup tables
 
+def _table_chunk():
+    """Positions per piece of a contig (PSS_TABLE_CHUNK, default 16 Mi), a multiple of the scatter kernel's tile."""
+    import os
+    from . import shard
+    return max(shard.TILE * 2, int(os.environ.get('PSS_TABLE_CHUNK', 16 << 20)) // shard.TILE * shard.TILE)
+
+
+def _refusable(batch, max_depth):
+    """True when the order-dependent ``max_depth`` rule could refuse a read of this batch at all: some read has
+    ``max_depth - 1`` earlier reads starting within one maximal read span before it (start sorted: one subtraction
+    over the positions).  Cached per batch."""
+    k = (max_depth or 8000) - 1
+    key = ('cut', k)
+    if key not in batch.cache:
+        n = batch.n_reads
+        maxspan = int((batch.endpos - batch.pos).max()) if n else 1
+        batch.cache[key] = (maxspan, k <= 0 or (n > k and int((batch.pos[k:] - batch.pos[:n - k]).min()) <= maxspan))
+    return batch.cache[key]
+
+
+def _streamed_pieces(bam, c, s, e, truncate, pad, max_depth, state):
+    """Position pieces of chrom:[s, e) whose reads are decoded piece by piece through the BAI index while the earlier
+    pieces are on the GPU (``BamFile.piece_batches``): yields (c_lo, c_hi, struct pss_reads).  ``state`` receives
+    'lo' (first position that can get a row) before the first piece is yielded.
+
+    A cut is exact when every read overlapping it is admitted whatever came before (``shard`` docstring): a piece in
+    which the ``max_depth`` rule could refuse a read (``_refusable``) is therefore not followed by another cut -- the rest
+    of the region is decoded and computed as one piece."""
+    chunk = _table_chunk()
+    cuts = list(range(s, e, chunk)) + [e]
+    n = len(cuts) - 1
+    k = 0
+    tail = None
+    for batch in bam.piece_batches(c, cuts):
+        if batch is None:                               # unusable index: the rest in one ordinary region query
+            tail = bam.region_batch(c, cuts[k], e)
+        elif _refusable(batch, max_depth)[1] and k + 1 < n:
+            tail = bam._region_native(bam.get_tid(c), cuts[k], e, bam.index_path()) or bam.region_batch(c, cuts[k], e)
+        if tail is not None:
+            batch = tail
+        last = tail is not None or k == n - 1
+        g_lo, g_hi = cuts[k], (e if last else cuts[k + 1])
+        nr = batch.n_reads
+        # rows: [s, e) with truncate; else every position a fetched read covers (plus [s, e) with pad)
+        c_lo, c_hi = g_lo, g_hi
+        if not truncate and nr:
+            if k == 0:
+                c_lo = min(int(batch.pos[0]), s) if pad else int(batch.pos[0])
+            if last:
+                c_hi = max(int(batch.endpos.max()), e) if pad else int(batch.endpos.max())
+        if 'lo' not in state:
+            state['lo'] = c_lo
+        if (nr or pad) and c_hi > c_lo:
+            yield c_lo, c_hi, _reads_struct(batch, False)
+        if last:
+            return
+        k += 1
+
+
 def _pileup_plan(stat, alignmentfile, fafile, pad, chrom, start, end, one_based, truncate, stepper, max_depth,
                  min_mapq, min_baseq, no_del, no_dup):
-    """Per contig of the request: (contig, s, e, lo, hi, read batch, reference bytes, engine keyword arguments,
+    """Per contig of the request: (contig, s, e, lo, hi, pieces, reference bytes, engine keyword arguments,
     need_qual) -- [s, e) the normalised region, [lo, hi) the positions that can get a row (row selection of
-    ``iter_pileup_default`` / ``iter_pileup_padded_chrom``, ``opt.pyx:1846-1863``, ``:1936-1984``)."""
+    ``iter_pileup_default`` / ``iter_pileup_padded_chrom``, ``opt.pyx:1846-1863``, ``:1936-1984``; ``hi`` may be an
+    upper bound), ``pieces`` an iterator of (c_lo, c_hi, struct pss_reads): consecutive position pieces of [lo, hi)
+    with the reads that overlap them."""
     if stepper not in _cabi.STEPPERS:
         raise ValueError('unknown stepper: %r' % (stepper,))     # pysam raises ValueError too
     name = stat.name
@@ -160,6 +223,26 @@ def _pileup_plan(stat, alignmentfile, fafile, pad, chrom, start, end, one_based,
             assert c is not None, 'chromosome is None'
         s, e = normalise_coords(bam, c, start, end, one_based)
         _check_region(s, e)
+
+        def reference():
+            refseq = fa.contig(c) if (fa is not None and needs_ref) else np.zeros(0, np.uint8)
+            return refseq, dict(stepper=stepper, max_depth=max_depth, min_mapq=min_mapq, min_baseq=min_baseq, no_del=no_del,
+                                no_dup=no_dup, window_size=stat.window_size, window_offset=stat.window_offset,
+                                ref=refseq if len(refseq) else None, ref_start=0, ref_len=len(refseq), contig_len=len(refseq))
+
+        if not need_qual and e - s > _table_chunk() and bam.can_stream(c):
+            # decode -> upload -> compute pipeline: the first pieces are being inflated while the FASTA is read
+            state = {}
+            it = _streamed_pieces(bam, c, s, e, truncate, pad, max_depth, state)
+            first = next(it, None)
+            if first is None:
+                continue
+            refseq, pkw = reference()
+            lo = state['lo']
+            hi = max(e, bam.lengths[bam.get_tid(c)]) + (1 << 16)          # upper bound; reads do not leave the contig
+            import itertools
+            yield c, s, e, lo, hi, itertools.chain([first], it), refseq, pkw, need_qual
+            continue
         batch = bam.region_batch(c, s, e)
         n = batch.n_reads
         if n == 0 and not pad:
@@ -176,11 +259,8 @@ def _pileup_plan(stat, alignmentfile, fafile, pad, chrom, start, end, one_based,
             lo, hi = s, e
         if hi - lo <= 0:
             continue
-        refseq = fa.contig(c) if (fa is not None and needs_ref) else np.zeros(0, np.uint8)
-        pkw = dict(stepper=stepper, max_depth=max_depth, min_mapq=min_mapq, min_baseq=min_baseq, no_del=no_del,
-                   no_dup=no_dup, window_size=stat.window_size, window_offset=stat.window_offset,
-                   ref=refseq if len(refseq) else None, ref_start=0, ref_len=len(refseq), contig_len=len(refseq))
-        yield c, s, e, lo, hi, batch, refseq, pkw, need_qual
+        refseq, pkw = reference()
+        yield c, s, e, lo, hi, _position_chunks(batch, lo, hi, need_qual, max_depth), refseq, pkw, need_qual
 
 
 def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start=None, end=None,
@@ -195,7 +275,7 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
     """
     name = stat.name
     names = config.value_fields(name)
-    for c, s, e, lo, hi, batch, refseq, pkw, need_qual in _pileup_plan(
+    for c, s, e, lo, hi, pieces, refseq, pkw, need_qual in _pileup_plan(
             stat, alignmentfile, fafile, pad, chrom, start, end, one_based, truncate, stepper, max_depth, min_mapq,
             min_baseq, no_del, no_dup):
         ctx = _cabi.get_context()
@@ -212,7 +292,7 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
             rows = rowmask.view(bool)
             if pad:
                 rows = rows.copy()
-                rows[max(min(max(s, lo), c_hi) - c_lo, 0):max(min(e, hi, c_hi) - c_lo, 0)] = True
+                rows[max(min(s, c_hi) - c_lo, 0):max(min(e, c_hi) - c_lo, 0)] = True      # [s, e) within the piece
             if rows.all():
                 pos = np.arange(c_lo, c_hi, dtype=np.int64)
                 fields = {f: out[j] for j, f in enumerate(names)}
@@ -232,7 +312,7 @@ def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start
                 pos = pos + 1
             return pos, ref, fields
 
-        for res in _run_pieces(run_piece, _position_chunks(batch, lo, hi, need_qual, max_depth), ctx.device):
+        for res in _run_pieces(run_piece, pieces, ctx.device):
             if res is not None:
                 yield (c,) + res
 
@@ -252,7 +332,7 @@ def pileup_rows(stat, dtype, alignmentfile, fafile=None, pad=False, chrom=None, 
     if ctx.row_layout(name, dtype, names, chrom='') is None:
         return None
     parts = []
-    for c, s, e, lo, hi, batch, refseq, pkw, need_qual in _pileup_plan(
+    for c, s, e, lo, hi, pieces, refseq, pkw, need_qual in _pileup_plan(
             stat, alignmentfile, fafile, pad, chrom, start, end, one_based, truncate, stepper, max_depth, min_mapq,
             min_baseq, no_del, no_dup):
         layout = ctx.row_layout(name, dtype, names, chrom=c, pos_add=1 if one_based else 0,
@@ -266,7 +346,7 @@ def pileup_rows(stat, dtype, alignmentfile, fafile=None, pad=False, chrom=None, 
             return None
         n = 0
         if len(devs) == 1:
-            for c_lo, c_hi, reads in _position_chunks(batch, lo, hi, need_qual, max_depth):
+            for c_lo, c_hi, reads in pieces:
                 params = ctx.pileup_params(name, start=c_lo, end=c_hi, **pkw)
                 m, neg = ctx.pileup_host_rows(reads, params, layout, buf, n, cap - n)
                 if neg:
@@ -284,7 +364,7 @@ def pileup_rows(stat, dtype, alignmentfile, fafile=None, pad=False, chrom=None, 
                 params = pctx.pileup_params(name, start=c_lo, end=c_hi, **pkw)
                 m, neg = pctx.pileup_host_rows(reads, params, layout, buf, c_lo - lo, c_hi - c_lo)
                 return c_lo - lo, m, neg
-            for r0, m, neg in _run_pieces(run_rows, _position_chunks(batch, lo, hi, need_qual, max_depth), ctx.device):
+            for r0, m, neg in _run_pieces(run_rows, pieces, ctx.device):
                 if neg:
                     raise OverflowError('Python integer -1 out of bounds for uint8')
                 if m and r0 != n:
@@ -348,23 +428,17 @@ def _position_chunks(batch, lo, hi, need_qual, max_depth):
     The ``max_depth`` admission rule is order dependent: a read before a cut can only be refused because of
     earlier reads the next piece would not see.  So the range is only cut when no read of the batch can be
     refused at all (fewer than ``max_depth`` reads start within one maximal read span of any read)."""
-    import os
     from . import shard
     n = batch.n_reads
-    chunk = max(shard.TILE * 2, int(os.environ.get('PSS_TABLE_CHUNK', 16 << 20)) // 512 * 512)
+    chunk = _table_chunk()
     # requests that read base qualities are not cut either: the mate-overlap rewrite pairs consecutive reads of a
     # QNAME, and a piece that misses an earlier read of a three-read chain would pair the rest differently
     if hi - lo <= chunk or n == 0 or need_qual:
         yield lo, hi, _reads_struct(batch, need_qual)
         return
-    k = (max_depth or 8000) - 1
-    key = ('cut', k)
-    if key not in batch.cache:
-        maxspan = int((batch.endpos - batch.pos).max())
-        # read i has max_depth - 1 earlier reads within maxspan of its start iff pos[i] - pos[i - (max_depth - 1)] <=
-        # maxspan (the reads are start sorted): one subtraction over the batch instead of a binary search per read
-        batch.cache[key] = (maxspan, k <= 0 or (n > k and int((batch.pos[k:] - batch.pos[:n - k]).min()) <= maxspan))
-    maxspan, refusable = batch.cache[key]
+    # read i has max_depth - 1 earlier reads within maxspan of its start iff pos[i] - pos[i - (max_depth - 1)] <=
+    # maxspan (the reads are start sorted): one subtraction over the batch instead of a binary search per read
+    maxspan, refusable = _refusable(batch, max_depth)
     if refusable:
         yield lo, hi, _reads_struct(batch, need_qual)
         return

@@ -186,3 +186,34 @@ def test_chrom_none_start_end_semantics_in_the_plan(monkeypatch):
     kw['one_based'] = True
     with pytest.raises(ValueError, match='start out of range'):
         list(opt._pileup_plan(opt.Coverage(), fx('test.bam'), None, False, 'Pf3D7_01_v3', 0, 2000, **kw))
+
+
+# ------------------------------------------------------------------------ streamed piece decode
+
+@pytest.mark.skipif(bamio.host_lib() is None, reason='libpss_host.so is not built')
+def test_piece_batches_equal_region_queries(tmp_path, monkeypatch):
+    from pysamstats_b200 import synth
+    G = 600_000
+    batch, _ = synth.make_interval_batch(0, G, G, depth=8, block=200000, with_qual=True)
+    nb = synth.batch_to_numpy(batch)
+    path = str(tmp_path / 'p.bam')
+    bamio.write_bam(path, ['chrS'], [G], nb, level=1)
+    bamio.index_bam(path)
+    monkeypatch.setenv('PSS_BAI_MIN_BYTES', '0')
+    bam = bamio.BamFile(path)
+    assert bam.can_stream('chrS')
+    cuts = [1000, 150_000, 150_512, 400_000, 599_000]
+    whole = bamio.BamFile(path).load()
+    pieces = list(bam.piece_batches('chrS', cuts))
+    assert len(pieces) == len(cuts) - 1
+    for k, b in enumerate(pieces):
+        e = whole.region_batch('chrS', cuts[k], cuts[k + 1])
+        assert b.n_reads == e.n_reads > 0
+        for f in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'endpos', 'cigar', 'seq4', 'qual'):
+            assert np.array_equal(getattr(b, f), getattr(e, f)), (k, f)
+        assert np.array_equal(np.diff(b.cigar_off), np.diff(e.cigar_off))
+    again = list(bam.piece_batches('chrS', cuts))                 # served from the cache: the same objects
+    assert all(x is y for x, y in zip(pieces, again))
+    monkeypatch.setenv('PSS_NO_STREAM', '1')
+    assert not bam.can_stream('chrS')
+    assert not whole.can_stream('chrS')                             # already decoded in this process

@@ -446,3 +446,62 @@ def test_write_hdf5_through_the_engine(tmp_path, monkeypatch):
         e = pysamstats.load_variation_strand(fx('test.bam'), fx('ref.fa'), chrom='Pf3D7_02_v3', start=500, end=9000)
         assert np.array_equal(h5.root.vs.read(), np.asarray(e))
         assert np.array_equal(h5.root.tb.read(), np.asarray(pysamstats.load_tlen_binned(fx('test.bam'))))
+
+
+# ---- decode -> upload -> compute pipeline (pieces decoded through the BAI while earlier pieces are on the GPU) ----------
+
+@pytest.fixture(scope='module')
+def synthetic_bam(tmp_path_factory):
+    from pysamstats_b200 import bamio, synth
+    G = 1_500_000
+    batch, (ref, ref_lo) = synth.make_interval_batch(0, G, G, depth=12, block=500000, with_qual=True)
+    nb = synth.batch_to_numpy(batch)
+    d = tmp_path_factory.mktemp('stream')
+    path, fa = str(d / 's.bam'), str(d / 's.fa')
+    bamio.write_bam(path, ['chrS', 'chrT'], [G, 1000], nb, level=1)
+    bamio.index_bam(path)
+    with open(fa, 'wb') as fh:
+        fh.write(b'>chrS\n' + ref.numpy()[:G].tobytes() + b'\n>chrT\n' + b'A' * 1000 + b'\n')
+    return path, fa, G
+
+
+def test_streamed_decode_equals_whole_file_decode(synthetic_bam, monkeypatch):
+    from pysamstats_b200 import bamio, opt
+    path, fa, G = synthetic_bam
+    monkeypatch.setenv('PSS_BAI_MIN_BYTES', '0')
+    monkeypatch.setenv('PSS_TABLE_CHUNK', '131072')
+    cases = [('variation_strand', dict(chrom='chrS')), ('coverage_ext', dict(chrom='chrS', start=200_000, end=1_100_000)),
+             ('coverage', dict(chrom='chrS', start=100_003, end=900_001, truncate=True)),
+             ('coverage_strand', dict(chrom='chrS', start=5, end=1_400_000, pad=True)),
+             ('variation', dict(chrom='chrS', start=300_000, end=1_000_000, pad=True, truncate=True, one_based=True)),
+             ('mapq', dict(chrom='chrS', min_mapq=20, no_dup=True)), ('tlen', dict(chrom='chrS', start=1, end=700_000)),
+             ('coverage', dict(chrom='chrS', max_depth=7)),               # the depth cap acts: no cut after the first piece
+             ('coverage_ext', dict()),                                    # every contig
+             ('baseq', dict(chrom='chrS', start=0, end=400_000))]          # reads qualities: never streamed
+    streamed = []
+    real = opt._streamed_pieces
+    monkeypatch.setattr(opt, '_streamed_pieces', lambda *a, **k: streamed.append(1) or real(*a, **k))
+    for no_rows in (False, True):
+        for stat, kw in cases:
+            f = getattr(pysamstats, 'load_' + stat)
+            fasta = fa if stat in WITHREF else None
+            monkeypatch.setenv('PSS_NO_STREAM', '1')
+            bamio._bam_cache.clear()
+            monkeypatch.delenv('PSS_NO_ROWS', raising=False)
+            e = f(path, fafile=fasta, **kw)
+            monkeypatch.delenv('PSS_NO_STREAM')
+            if no_rows:
+                monkeypatch.setenv('PSS_NO_ROWS', '1')
+            bamio._bam_cache.clear()
+            n0 = len(streamed)
+            a = f(path, fafile=fasta, **kw)
+            assert (len(streamed) > n0) == (stat != 'baseq'), (stat, kw)
+            assert_recarrays_equal(e, a, 'streamed %s %r rows=%r' % (stat, kw, not no_rows))
+            b = f(path, fafile=fasta, **kw)                        # second call: the cached pieces
+            assert_recarrays_equal(e, b, 'cached pieces %s %r' % (stat, kw))
+    # the generator of dicts over streamed tables
+    bamio._bam_cache.clear()
+    rows = list(pysamstats.stat_coverage(path, chrom='chrS', start=100_000, end=400_000))
+    monkeypatch.setenv('PSS_NO_STREAM', '1')
+    bamio._bam_cache.clear()
+    assert rows == list(pysamstats.stat_coverage(path, chrom='chrS', start=100_000, end=400_000))
