@@ -544,6 +544,27 @@ def main():
                        % (-(-npos // chunk), chunk, inner)) if args.e2e_stream else
                       ('pss_pileup_host_multi (pinned host read arrays in, host int32 columns of both statistics out), '
                        '%d position chunks of %d per step' % (-(-npos // chunk), chunk))}
+        # ---- the floor under any host path: the API contract hands int32 columns to the caller, so the HOST must write
+        # 4 bytes per field and position whatever the engine does; measured write bandwidth of this box (all ranks
+        # probing at once, as they share the memory system in the timed run), non-temporal int32 stores
+        try:
+            from pysamstats_b200 import bamio
+            hl = bamio.host_lib()
+            threads = max(1, (os.cpu_count() or 1) // world)
+            barrier()
+            wbw = hl.pss_host_bandwidth(256 << 20, threads, 3, 0)
+            wid = hl.pss_host_bandwidth(256 << 20, threads, 3, 1)
+            barrier()
+            wbw_all, wid_all = sum_over_ranks(wbw), sum_over_ranks(wid)
+            int32_bytes = 4 * sum(nf.values()) * total_pos
+            e2e['host_floor'] = {'int32_result_bytes_per_step': int(int32_bytes), 'host_write_gbs': wbw_all,
+                                 'host_widen_u8_to_i32_gbs_written': wid_all, 'threads': threads * world,
+                                 'floor_ms': int32_bytes / (wbw_all * 1e9) * 1e3,
+                                 'frac': (int32_bytes / (wbw_all * 1e9)) / e2e_s,
+                                 'what': 'seconds the host needs just to WRITE the int32 columns the API contract returns (bytes / measured '
+                                         'non-temporal store bandwidth, all ranks probing together) / e2e seconds per step'}
+        except Exception as ex:   # noqa: BLE001 -- informative only
+            e2e['host_floor'] = {'error': repr(ex)}
         # ---- the binned sweep end to end: pss_pileup_host (coverage_gc) per position chunk + pss_binned_host_multi
         if binned is not None:
             gchunk = chunk

@@ -96,6 +96,11 @@ int pss_format_rows(int64_t n_rows, int32_t n_cols, const int32_t *kind, const v
                     const int32_t *src_stride, const int32_t *width, const char *delimiter, int32_t delimiter_len,
                     const char *terminator, int32_t terminator_len, int n_threads, char **out, int64_t *out_len);
 void pss_host_free(void *p);
+/* Host memory bandwidth probe (bench.py's e2e.host_floor): n_threads threads (0: all) stream `reps` times over a
+ * private buffer of `bytes` each.  mode 0: non-temporal int32 stores (what the result path does to the caller's
+ * int32 columns -- the API contract of load_* / pss_pileup_host*, /root/reference/pysamstats/util.py:61-71, fixes
+ * how many of those bytes the host must write), 1: widen u8 -> int32, 2: reads.  Returns GB/s, < 0 on failure. */
+double pss_host_bandwidth(int64_t bytes, int n_threads, int reps, int mode);
 
 /* prev[i] = index of the previous row with the same (NUL padded, fixed width) name, or -1 */
 int pss_name_prev(const uint8_t *names, int64_t n, int32_t width, int32_t *prev);

@@ -73,6 +73,8 @@ def host_lib():
                                             C.POINTER(P), C.POINTER(C.c_int64)]
             lib.pss_host_free.argtypes = [P]
             lib.pss_host_free.restype = None
+            lib.pss_host_bandwidth.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int]
+            lib.pss_host_bandwidth.restype = C.c_double
             lib.pss_bam_write.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int64,
                                           C.POINTER(HostArrays), C.c_int32, C.c_int, C.c_int]
             _host_lib = lib

@@ -7,6 +7,8 @@
 // {block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, l_seq, next_refID,
 //  next_pos, tlen, read_name, cigar, seq, qual, aux}.
 #include "../../include/pss_host.h"
+#include <emmintrin.h>
+
 #include "pss_inflate.h"
 
 #include <fcntl.h>
@@ -931,6 +933,64 @@ extern "C" int pss_format_rows(int64_t n_rows, int32_t n_cols, const int32_t *ki
 }
 
 extern "C" void pss_host_free(void *p) { free(p); }
+
+// Host memory bandwidth probe: `n_threads` threads stream over a private buffer of `bytes` each, `reps` times.
+// mode 0: non-temporal int32 stores (what the result path does to the caller's columns), 1: widen u8 -> int32
+// (1 byte read, 4 written), 2: plain reads.  Returns GB/s of bytes WRITTEN (mode 2: read), < 0 on failure.
+extern "C" double pss_host_bandwidth(int64_t bytes, int n_threads, int reps, int mode) {
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (bytes < 4096 || reps < 1) return -1.0;
+    bytes &= ~(int64_t)63;
+    std::vector<uint8_t *> bufs((size_t)n_threads, nullptr), srcs((size_t)n_threads, nullptr);
+    for (int t = 0; t < n_threads; ++t) {
+        if (posix_memalign((void **)&bufs[(size_t)t], 64, (size_t)bytes) != 0) return -1.0;
+        if (mode == 1 && posix_memalign((void **)&srcs[(size_t)t], 64, (size_t)bytes / 4) != 0) return -1.0;
+    }
+    std::atomic<int> ready(0), go(0);
+    std::atomic<uint64_t> sink(0);
+    std::vector<std::thread> th;
+    auto body = [&](int t, int r_n) {
+        uint8_t *b = bufs[(size_t)t];
+        const int64_t n4 = bytes / 4;
+        for (int r = 0; r < r_n; ++r) {
+            if (mode == 0) {
+                int *d = (int *)b;
+                const __m128i v = _mm_set1_epi32(r);
+                for (int64_t i = 0; i < n4; i += 4) _mm_stream_si128((__m128i *)(d + i), v);
+            } else if (mode == 1) {
+                const uint8_t *sp = srcs[(size_t)t];
+                int *d = (int *)b;
+                for (int64_t i = 0; i < n4; i += 4) {
+                    uint32_t w4;
+                    memcpy(&w4, sp + i, 4);
+                    const __m128i w = _mm_cvtsi32_si128((int)w4), z = _mm_setzero_si128();
+                    _mm_stream_si128((__m128i *)(d + i), _mm_unpacklo_epi16(_mm_unpacklo_epi8(w, z), z));
+                }
+            } else {
+                const uint64_t *q = (const uint64_t *)b;
+                uint64_t acc = 0;
+                for (int64_t i = 0; i < bytes / 8; ++i) acc += q[i];
+                sink += acc;
+            }
+        }
+    };
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t] {
+            memset(bufs[(size_t)t], 1, (size_t)bytes);                 // first touch outside the timed part
+            if (mode == 1) memset(srcs[(size_t)t], 3, (size_t)bytes / 4);
+            ready.fetch_add(1);
+            while (!go.load()) std::this_thread::yield();
+            body(t, reps);
+        });
+    while (ready.load() < n_threads) std::this_thread::yield();
+    const double t0 = now();
+    go.store(1);
+    for (auto &x : th) x.join();
+    const double dt = now() - t0;
+    for (auto p2 : bufs) free(p2);
+    for (auto p2 : srcs) free(p2);
+    return dt > 0 ? (double)bytes * n_threads * reps / dt / 1e9 : -1.0;
+}
 
 // ------------------------------------------------------------------------------ name_prev
 
