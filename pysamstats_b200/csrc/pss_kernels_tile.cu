@@ -51,6 +51,16 @@
 #endif
 template <int KIND> struct KindLaunch { static const int NT = TTHREADS_COV, CTAS = TCTAS_COV; };
 template <> struct KindLaunch<2 /* KIND_VAR */> { static const int NT = TTHREADS, CTAS = TCTAS; };
+// variation (no strand split): half the counter arrays (45 KB of shared memory per CTA), so five CTAs fit an SM; measured
+// per 50 Mb (threads / CTAs the kernel is compiled for): 384/3 1.96, 320/3 1.85, 320/4 1.72, 256/4 1.68, 256/5 1.58,
+// 192/6 1.51 ms -- more, smaller CTAs overlap the phases of their tiles better
+#ifndef TTHREADS_VAR1
+#define TTHREADS_VAR1 192
+#endif
+#ifndef TCTAS_VAR1
+#define TCTAS_VAR1 6
+#endif
+template <> struct KindLaunch<6 /* KIND_VAR1 */> { static const int NT = TTHREADS_VAR1, CTAS = TCTAS_VAR1; };
 #define NQUAD (TT / 4)        // finalisation: quads of positions
 #ifndef TCH
 #define TCH 192               // reads staged per chunk
@@ -69,7 +79,7 @@ template <> struct KindLaunch<2 /* KIND_VAR */> { static const int NT = TTHREADS
 #define TPREFETCH 176         // tiles ahead whose staging data a CTA asks into L2 (0: off); 64 .. 300 measure the same
 #endif
 
-enum { KIND_COV = 0, KIND_EXT = 1, KIND_VAR = 2 };
+enum { KIND_COV = 0, KIND_EXT = 1, KIND_VAR = 2, KIND_VAR1 = 6 };    // (3 .. 5: the quality kinds below)
 
 // Word arrays per kind (each word = two 16-bit counters, see the accessors below).
 // NDIFF difference arrays come first (they are prefix-summed), then NPOINT point arrays.
@@ -80,6 +90,10 @@ template <> struct KindInfo<KIND_COV> { static const int NDIFF = 2, NPOINT = 0; 
 template <> struct KindInfo<KIND_EXT> { static const int NDIFF = 8, NPOINT = 0; };
 // all[pp], match[2 + pp], del[4 + pp] | ins[6 + pp], mismatches[8 + pp], mismatch class c = A,C,G,T,N: [10 + 2 c + pp]
 template <> struct KindInfo<KIND_VAR> { static const int NDIFF = 6, NPOINT = 14; };
+// variation without the strand split (opt.pyx:435-535 reports all / pp only): ONE word array per group, all reads in the
+// low half, proper pairs in the high half -- all[0] match[1] del[2] | ins[3] mismatches[4] mismatch class c: [5 + c].
+// Half the shared memory of KIND_VAR (four CTAs per SM), half the arrays to zero, scan and finalise.
+template <> struct KindInfo<KIND_VAR1> { static const int NDIFF = 3, NPOINT = 7; };
 
 // per-tile descriptor written by k_tile_desc (+ k_refpack for the flag)
 struct __align__(16) TileDesc {
@@ -191,12 +205,18 @@ __device__ __forceinline__ void interval_add(uint32_t *arr, int x, int l, int t0
 // (bank >> 1 selects the word array, the strand the half).  LayBqx: baseq_ext(_strand), one
 // 32-bit word array per bank (so any depth fits one pass; root mean squares are not additive
 // over passes) and the squared qualities of mismatching bases as 64-bit point sums.
-struct LayVar { static const bool PACKED = true, VAR = true, DEFER = false; enum { ALL = W_ALL, MATCH = W_MATCH, DEL = W_DEL, INS = W_INS, MMT = W_MMT }; };
-struct LayBqx { static const bool PACKED = false, VAR = false, DEFER = false; enum { ALL = 0, MATCH = 4, DEL = 0, INS = 0, MMT = 8, SQMM = 20 }; };
+// LayVar1: variation without the strand split, one word array per group, all | proper pair << 16 (PER = word arrays per group).
+struct LayVar { static const bool PACKED = true, VAR = true, DEFER = false; enum { PER = 2, ALL = W_ALL, MATCH = W_MATCH, DEL = W_DEL, INS = W_INS, MMT = W_MMT, MMC = W_MMC }; };
+struct LayVar1 { static const bool PACKED = true, VAR = true, DEFER = false; enum { PER = 1, ALL = 0, MATCH = 1, DEL = 2, INS = 3, MMT = 4, MMC = 5 }; };
+struct LayBqx { static const bool PACKED = false, VAR = false, DEFER = false; enum { PER = 4, ALL = 0, MATCH = 4, DEL = 0, INS = 0, MMT = 8, MMC = 0, SQMM = 20 }; };
 template <class L> __device__ __forceinline__ uint32_t *carr(const TileCtx &T, int group, int bank) {
-    return T.cnt + (group + (L::PACKED ? (bank >> 1) : bank)) * TT;
+    return T.cnt + (group + (L::PER == 2 ? (bank >> 1) : L::PER == 1 ? 0 : bank)) * TT;
 }
-template <class L> __device__ __forceinline__ uint32_t cinc(int bank) { return L::PACKED ? half_inc(bank) : 1u; }
+template <class L> __device__ __forceinline__ uint32_t cinc(int bank) {
+    return L::PER == 2 ? half_inc(bank) : L::PER == 1 ? (1u | ((uint32_t)(bank >> 1) << 16)) : 1u;
+}
+template <int KIND> struct KindLay { typedef LayVar type; };
+template <> struct KindLay<KIND_VAR1> { typedef LayVar1 type; };
 
 // qidx: index of the base's quality in T.qual (LayBqx), < 0: no quality (reads without sequence)
 template <class L>
@@ -208,7 +228,7 @@ __device__ __forceinline__ void var_mismatch(const TileCtx &T, int bank, int p, 
     atomicAdd(carr<L>(T, L::MMT, bank) + p, inc);
     if (L::VAR) {
         const int c = mm_class(code);
-        if (c < 5) atomicAdd(T.cnt + (W_MMC + 2 * c + (bank >> 1)) * TT + p, inc);
+        if (c < 5) atomicAdd(carr<L>(T, L::MMC + L::PER * c, bank) + p, inc);
     } else {
         const unsigned long long q = qidx >= 0 ? T.qual[qidx] : 0;
         if (q) atomicAdd(reinterpret_cast<unsigned long long *>(T.cnt + LayBqx::SQMM * TT) + bank * TT + p, q * q);
@@ -609,12 +629,13 @@ __device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int 
 
 // variation kinds (LayVar).  Reads without sequence have quality 0 at every base: they keep only their
 // deletion / ref-skip events, which var_read is told through `drop_bases`.
+template <class L>
 __device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t *cg, const RInfo &r, uint32_t sn0, int ridx,
                              int part, int nparts) {
     const uint32_t cls = r.cls;
     if (!(cls & CLS_COUNTED) || (cls & CLS_NOREF) || !(cls & CLS_HASSEQ)) return;
-    const int bank = cls & 3u, pp = bank >> 1;
-    const uint32_t inc = half_inc(bank);
+    const int bank = cls & 3u;
+    const uint32_t inc = cinc<L>(bank);
     const uint32_t *mw = A.lowq + (r.seq_off >> 4) + ridx;
     const int nc = (int)r.n_cigar;
     int x = r.pos, y = 0;
@@ -625,7 +646,7 @@ __device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t
             if (x + l > T.t0) {
                 const bool ins = ins_follows(cg, nc, k);
                 lowq_span(mw, x, l, y, T.t0, [&](int p, int qi, bool last) {
-                    uint32_t *al = T.cnt + (W_ALL + pp) * TT + p;
+                    uint32_t *al = carr<L>(T, L::ALL, bank) + p;
                     atomicAdd(al, 0u - inc);
                     if (p + 1 < TT) atomicAdd(al + 1, inc);
                     const uint32_t kk = sn0 + (uint32_t)qi;
@@ -636,15 +657,15 @@ __device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t
                         rc = (T.ref && ro >= 0 && ro < T.ref_len) ? c_refcode[__ldg(T.ref + ro)] : 16;
                     } else rc = (T.refn[p >> 3] >> ((7 - (p & 7)) << 2)) & 15;
                     if (code == rc) {
-                        uint32_t *m = T.cnt + (W_MATCH + pp) * TT + p;
+                        uint32_t *m = carr<L>(T, L::MATCH, bank) + p;
                         atomicAdd(m, 0u - inc);
                         if (p + 1 < TT) atomicAdd(m + 1, inc);
                     } else {
-                        atomicAdd(T.cnt + (W_MMT + pp) * TT + p, 0u - inc);
+                        atomicAdd(carr<L>(T, L::MMT, bank) + p, 0u - inc);
                         const int c = mm_class(code);
-                        if (c < 5) atomicAdd(T.cnt + (W_MMC + 2 * c + pp) * TT + p, 0u - inc);
+                        if (c < 5) atomicAdd(carr<L>(T, L::MMC + L::PER * c, bank) + p, 0u - inc);
                     }
-                    if (last && ins) atomicAdd(T.cnt + (W_INS + pp) * TT + p, 0u - inc);
+                    if (last && ins) atomicAdd(carr<L>(T, L::INS, bank) + p, 0u - inc);
                 }, part, nparts);
             }
             x += l; y += l;
@@ -703,9 +724,10 @@ __device__ void noseq_minq_read(const TileCtx &T, const TileArgs &A, const RInfo
     if (!(cls & CLS_COUNTED) || T.no_del) return;
     const int bank = cls & 3u;
     if (cls & CLS_NOREF) {         // one deletion-like event at pos
-        if (KIND == KIND_VAR) {
-            interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, r.pos, 1, T.t0, half_inc(bank));
-            interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, r.pos, 1, T.t0, half_inc(bank));
+        if (KIND == KIND_VAR || KIND == KIND_VAR1) {
+            typedef typename KindLay<KIND>::type L;
+            interval_add(carr<L>(T, L::ALL, bank), r.pos, 1, T.t0, cinc<L>(bank));
+            interval_add(carr<L>(T, L::DEL, bank), r.pos, 1, T.t0, cinc<L>(bank));
         } else cover_segment<KIND>(T, cls, r.pos, 1);
         return;
     }
@@ -718,9 +740,10 @@ __device__ void noseq_minq_read(const TileCtx &T, const TileArgs &A, const RInfo
         if (op_is_match(op)) x += l;
         else if (op == OP_D || op == OP_N) {
             if (x + l > T.t0) {
-                if (KIND == KIND_VAR) {
-                    interval_add(T.cnt + (W_ALL + (bank >> 1)) * TT, x, l, T.t0, half_inc(bank));
-                    if (op == OP_D) interval_add(T.cnt + (W_DEL + (bank >> 1)) * TT, x, l, T.t0, half_inc(bank));
+                if (KIND == KIND_VAR || KIND == KIND_VAR1) {
+                    typedef typename KindLay<KIND>::type L;
+                    interval_add(carr<L>(T, L::ALL, bank), x, l, T.t0, cinc<L>(bank));
+                    if (op == OP_D) interval_add(carr<L>(T, L::DEL, bank), x, l, T.t0, cinc<L>(bank));
                 } else cover_segment<KIND>(T, cls, x, l);
             }
             x += l;
@@ -871,6 +894,34 @@ __device__ __forceinline__ uint4 tile_finalize(const uint32_t *cnt, const uint32
                 if (STAT == PSS_COVERAGE_EXT_STRAND) { O.put(f); O.put(r); }
             }
         }
+    } else if (STAT == PSS_VARIATION) {
+        // LayVar1: one word per group and position, all | proper pair << 16.  Groups and sub-parts as below.
+        typedef LayVar1 L1;
+        const int g0 = part == 0 ? 0 : part == 1 ? 3 : part == 2 ? 6 : 8, g1 = part == 0 ? 3 : part == 1 ? 6 : part == 2 ? 8 : 10;
+        // counter array (4 bits) per group: reads, matches, mismatches, deletions, insertions, A, C, T, G, N
+        const unsigned long long ARR = (unsigned long long)L1::ALL | ((unsigned long long)L1::MATCH << 4) | ((unsigned long long)L1::MMT << 8) |
+                                       ((unsigned long long)L1::DEL << 12) | ((unsigned long long)L1::INS << 16) | ((unsigned long long)(L1::MMC + 0) << 20) |
+                                       ((unsigned long long)(L1::MMC + 1) << 24) | ((unsigned long long)(L1::MMC + 3) << 28) |
+                                       ((unsigned long long)(L1::MMC + 2) << 32) | ((unsigned long long)(L1::MMC + 4) << 36);
+        const unsigned long long CODE = (1ull << 20) | (2ull << 24) | (8ull << 28) | (4ull << 32) | (15ull << 36);
+        O.skip(g0 * 2);
+        uint4 m = make_uint4(0, 0, 0, 0);
+        uint32_t rc4 = 0;
+        if (part != 0) {
+            const uint32_t rw = refn[q >> 1];
+            rc4 = (q & 1) ? (rw & 0xffffu) : (rw >> 16);
+            m = ld4(cnt, L1::MATCH, q);
+        }
+#pragma unroll
+        for (int g = g0; g < g1; ++g) {
+            const int arr = (int)((ARR >> (4 * g)) & 15u);
+            const uint32_t code = (uint32_t)((CODE >> (4 * g)) & 15u);
+            uint4 a = ld4(cnt, arr, q);
+            if (g == 0) all = lo16(a);
+            if (code) a = base_count(a, m, rc4, code);
+            O.put(lo16(a));
+            O.put(hi16(a));
+        }
     } else {
         // groups: 0 reads, 1 matches, 2 mismatches, 3 deletions, 4 insertions, 5 A, 6 C, 7 T, 8 G, 9 N
         // part 0 -> groups 0-2, part 1 -> 3-5, part 2 -> 6-7, part 3 -> 8-9 (contiguous fields)
@@ -985,6 +1036,8 @@ template <int KIND, int STAT, bool MINQ>
 __global__ void __launch_bounds__(KindLaunch<KIND>::NT, KindLaunch<KIND>::CTAS)
 k_tile(TileArgs A) {
     constexpr int NT = KindLaunch<KIND>::NT, NWARPS = NT / 32;
+    constexpr bool IS_VAR = KIND == KIND_VAR || KIND == KIND_VAR1;
+    typedef typename KindLay<KIND>::type LV;               // counter layout of the variation kinds
     static_assert(NT % 32 == 0 && NQUAD % 32 == 0, "whole warps per finalisation sub-part");
     static_assert(TCH <= NT, "one thread per staged read at least");
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1022,9 +1075,9 @@ k_tile(TileArgs A) {
         // the whole descriptor in one round trip (thread 0 needs all of it before it can issue the copies)
         const uint4 *dp = reinterpret_cast<const uint4 *>(A.desc + tile);
         const uint4 d0 = __ldg(dp);
-        if (KIND == KIND_VAR && tid == 0) { d1 = __ldg(dp + 1); d2 = __ldg(dp + 2); }
+        if (IS_VAR && tid == 0) { d1 = __ldg(dp + 1); d2 = __ldg(dp + 2); }
         d.x = (int)d0.x; d.y = (int)d0.y; d.n0 = (int)d0.z;
-        d.flags = (KIND == KIND_VAR) ? __ldg(A.tflags + tile) : 0u;
+        d.flags = IS_VAR ? __ldg(A.tflags + tile) : 0u;
     }
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -1032,7 +1085,7 @@ k_tile(TileArgs A) {
         uint32_t bytes = 0, sbytes = 0, cbytes = 0;
         const uint8_t *src = nullptr, *csrc = nullptr;
         const int n = d.n0;
-        if (KIND == KIND_VAR && n > 0) {
+        if (IS_VAR && n > 0) {
             long long lo = (long long)(((uint64_t)d1.y << 32) | d1.x), hi = (long long)(((uint64_t)d1.w << 32) | d1.z);
             stage_span(A.seq4, lo, hi, 1, &src, &sbytes, &s_seqlo);
             long long clo = (long long)(((uint64_t)d2.y << 32) | d2.x), chi = (long long)(((uint64_t)d2.w << 32) | d2.z);
@@ -1041,12 +1094,12 @@ k_tile(TileArgs A) {
         }
         s_n = n;
         if (n > 0) {
-            bytes = (uint32_t)n * (uint32_t)sizeof(RInfo) + sbytes + cbytes + (KIND == KIND_VAR ? (REFN_WORDS + 4) * 4 : 0);
+            bytes = (uint32_t)n * (uint32_t)sizeof(RInfo) + sbytes + cbytes + (IS_VAR ? (REFN_WORDS + 4) * 4 : 0);
             mbar_arrive_expect_tx(&s_bar, bytes);
             bulk_g2s(s_ri, A.ri + d.x, (uint32_t)n * (uint32_t)sizeof(RInfo), &s_bar);
             if (sbytes) bulk_g2s(s_seq, src, sbytes, &s_bar);
             if (cbytes) bulk_g2s(s_cig, csrc, cbytes, &s_bar);
-            if (KIND == KIND_VAR) bulk_g2s(s_refn, A.refpack + (size_t)tile * REFN_WORDS, (REFN_WORDS + 4) * 4, &s_bar);
+            if (IS_VAR) bulk_g2s(s_refn, A.refpack + (size_t)tile * REFN_WORDS, (REFN_WORDS + 4) * 4, &s_bar);
         } else mbar_arrive_expect_tx(&s_bar, 0);
     }
     STAMP(1);
@@ -1063,7 +1116,7 @@ k_tile(TileArgs A) {
             uint32_t nb;
             long long first;
             bulk_prefetch_l2(A.ri + (int)p0.x, (uint32_t)pn * (uint32_t)sizeof(RInfo));
-            if (KIND == KIND_VAR) {
+            if (IS_VAR) {
             const long long lo = (long long)(((uint64_t)p1.y << 32) | p1.x), hi = (long long)(((uint64_t)p1.w << 32) | p1.z);
             stage_span(A.seq4, lo, hi, 1, &src, &nb, &first);
             if (nb) bulk_prefetch_l2(src, nb);
@@ -1118,7 +1171,7 @@ k_tile(TileArgs A) {
 #ifndef PSS_EXP_SKIP_WALK
                         var_emit_spans(T, cg, r, sn0, rawp, s_span, &s_nspan);
 #endif
-                        if (MINQ) var_lowq_fix(T, A, cg, r, sn0, cb + tid, 0, 1);
+                        if (MINQ) var_lowq_fix<LayVar>(T, A, cg, r, sn0, cb + tid, 0, 1);
                     }
                 }
                 __syncthreads();
@@ -1141,7 +1194,7 @@ k_tile(TileArgs A) {
                 __syncwarp();
                 const int quota = (total + NT - 1) / NT;
                 var_walk_words(T, s_span, ns, tid * quota, min(total, (tid + 1) * quota));
-            } else if (KIND == KIND_VAR) {
+            } else if (IS_VAR) {
                 // up to four threads share a read: threads [k n, (k + 1) n) are part k of reads 0 .. n-1
                 const int nparts = min(4, NT / n);
                 const int part = tid / n;
@@ -1154,9 +1207,9 @@ k_tile(TileArgs A) {
                     } else {
                         if (MINQ) lowq_prefetch(A, r, cb + tid - part * n);
 #ifndef PSS_EXP_SKIP_WALK      // experiment builds only (scripts/build_variant.sh): time of the phases in isolation
-                        var_read<LayVar>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
+                        var_read<LV>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts);
 #endif
-                        if (MINQ) var_lowq_fix(T, A, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), cb + tid - part * n, part, nparts);
+                        if (MINQ) var_lowq_fix<LV>(T, A, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), cb + tid - part * n, part, nparts);
                     }
                 }
             } else if (tid < n) {
@@ -1177,7 +1230,7 @@ k_tile(TileArgs A) {
                 int m = min(TCH, d.y - cb);
                 uint32_t sbytes = 0, cbytes = 0;
                 const uint8_t *src = nullptr, *csrc = nullptr;
-                if (KIND == KIND_VAR) {
+                if (IS_VAR) {
                     long long lo = A.seq_off[cb], hi = A.seq_off[cb + m];
                     while (m > 1 && hi - lo + 32 > TSEQ_BYTES) { m >>= 1; hi = A.seq_off[cb + m]; }
                     if (hi - lo + 32 > TSEQ_BYTES) { atomicOr(&A.st->toolong, 1); m = 0; }
@@ -1985,7 +2038,7 @@ template <int KIND>
 static size_t tile_smem_bytes() {
     size_t narr = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT + 1;   // + raw
     size_t b = narr * TT * 4 + sizeof(RInfo) * TCH;
-    if (KIND == KIND_VAR) b += (REFN_WORDS + 4) * 4 + TSEQ_BYTES + 32 + (TCIG_WORDS + 8) * 4 + (TBAL ? SPAN_MAX * sizeof(SpanRec) : 0) + (LayVar::DEFER ? EV_SLOTS * EV_STRIDE * 2 : 0);
+    if (KIND == KIND_VAR || KIND == KIND_VAR1) b += (REFN_WORDS + 4) * 4 + TSEQ_BYTES + 32 + (TCIG_WORDS + 8) * 4 + (TBAL ? SPAN_MAX * sizeof(SpanRec) : 0) + (LayVar::DEFER ? EV_SLOTS * EV_STRIDE * 2 : 0);
     return b;
 }
 
@@ -2156,7 +2209,7 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     case PSS_COVERAGE_GC: e = launch_tile_one<KIND_COV, PSS_COVERAGE_GC>(a, ntiles, s); break;
     case PSS_COVERAGE_EXT: e = launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT>(a, ntiles, s); break;
     case PSS_COVERAGE_EXT_STRAND: e = launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT_STRAND>(a, ntiles, s); break;
-    case PSS_VARIATION: e = launch_tile_one<KIND_VAR, PSS_VARIATION>(a, ntiles, s); break;
+    case PSS_VARIATION: e = launch_tile_one<KIND_VAR1, PSS_VARIATION>(a, ntiles, s); break;
     case PSS_VARIATION_STRAND: e = launch_tile_one<KIND_VAR, PSS_VARIATION_STRAND>(a, ntiles, s); break;
     case PSS_MAPQ: e = launch_tileq_one<KIND_MAPQ, PSS_MAPQ>(a, ntiles, s); break;
     case PSS_MAPQ_STRAND: e = launch_tileq_one<KIND_MAPQ, PSS_MAPQ_STRAND>(a, ntiles, s); break;
