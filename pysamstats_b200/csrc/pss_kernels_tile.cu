@@ -37,11 +37,16 @@
 #define FULL 0xffffffffu
 
 #define TT PSS_TTILE          // positions per tile
+// variation_strand: 256 threads x FOUR CTAs per SM.  The 20 counter arrays are 40 KB; with a 136-read staging chunk, 192
+// staged CIGAR words and the row mask's own counter array only when a read-level filter needs it, a CTA takes 56.8 KB
+// of shared memory and a fourth fits (227 KB per SM).  Measured on 100 Mb (kernel ms): 320 threads x 3 CTAs, 192-read
+// chunks 5.00 (0.80 of the HBM roofline); 256 x 4 with 128-read chunks 4.83, with 136-read chunks 4.80 (0.84); 224 x 4
+// 5.23; 192 x 4 5.08; 320 x 3 with 128-read chunks 5.71 -- the store phase of one CTA hides behind the walks of more others.
 #ifndef TTHREADS
-#define TTHREADS 320
+#define TTHREADS 256
 #endif
 #ifndef TCTAS
-#define TCTAS 3               // CTAs per SM the variation kernels are compiled for
+#define TCTAS 4               // CTAs per SM the variation kernels are compiled for
 #endif
 #ifndef TTHREADS_COV
 #define TTHREADS_COV 192      // coverage kinds: little work per tile, so more, smaller CTAs per SM
@@ -63,11 +68,16 @@ template <> struct KindLaunch<2 /* KIND_VAR */> { static const int NT = TTHREADS
 template <> struct KindLaunch<6 /* KIND_VAR1 */> { static const int NT = TTHREADS_VAR1, CTAS = TCTAS_VAR1; };
 #define NQUAD (TT / 4)        // finalisation: quads of positions
 #ifndef TCH
-#define TCH 192               // reads staged per chunk
+#define TCH 136               // reads staged per chunk, variation kinds (a 512-position tile of 30x / 150 bp has ~134 candidates);
+#endif                        // also the first chunk the tile descriptors describe
+#ifndef TCH_COV
+#define TCH_COV 192           // coverage kinds (records only: 6 KB)
 #endif
 #define TSEQ_BYTES (TCH * 76 + 64)   // staged sequence bytes per chunk (150 bp reads fit a full chunk)
 #define REFN_WORDS (TT / 8)
-#define TCIG_WORDS 384        // staged CIGAR words per chunk (else the chunk's reads load them from global)
+#ifndef TCIG_WORDS
+#define TCIG_WORDS 192        // staged CIGAR words per chunk (else the chunk's reads load them from global)
+#endif
 #define PASS_READS 65535      // reads per pass: what a 16-bit counter can hold
 #ifndef TFIN_LOOP
 #define TFIN_LOOP 1           // variation_strand: the finalisation as a rolled loop over the field groups
@@ -1039,14 +1049,15 @@ k_tile(TileArgs A) {
     constexpr bool IS_VAR = KIND == KIND_VAR || KIND == KIND_VAR1;
     typedef typename KindLay<KIND>::type LV;               // counter layout of the variation kinds
     static_assert(NT % 32 == 0 && NQUAD % 32 == 0, "whole warps per finalisation sub-part");
-    static_assert(TCH <= NT, "one thread per staged read at least");
+    constexpr int CH = IS_VAR ? TCH : TCH_COV;             // reads staged per chunk
+    static_assert(CH <= NT, "one thread per staged read at least");
     extern __shared__ __align__(128) uint8_t smem[];
     const int NARR = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *raw = cnt + NARR * TT;                                   // only touched when need_raw
-    RInfo *s_ri = reinterpret_cast<RInfo *>(raw + TT);
+    uint32_t *raw = cnt + NARR * TT;                                   // exists only when need_raw (tile_smem_bytes)
+    RInfo *s_ri = reinterpret_cast<RInfo *>(raw + (A.need_raw ? TT : 0));
     // the rest exists for KIND_VAR only (see tile_smem_bytes)
-    uint32_t *s_refn = reinterpret_cast<uint32_t *>(s_ri + TCH);       // REFN_WORDS + 4 words
+    uint32_t *s_refn = reinterpret_cast<uint32_t *>(s_ri + CH);        // REFN_WORDS + 4 words
     uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_refn + REFN_WORDS + 4);   // TSEQ_BYTES + 32
     uint32_t *s_cig = reinterpret_cast<uint32_t *>(s_seq + TSEQ_BYTES + 32);  // TCIG_WORDS + 8
     SpanRec *s_span = reinterpret_cast<SpanRec *>(s_cig + TCIG_WORDS + 8);     // SPAN_MAX records (balanced walk)
@@ -1084,7 +1095,7 @@ k_tile(TileArgs A) {
         s_nspan = 0;
         uint32_t bytes = 0, sbytes = 0, cbytes = 0;
         const uint8_t *src = nullptr, *csrc = nullptr;
-        const int n = d.n0;
+        const int n = IS_VAR ? d.n0 : min(CH, d.y - d.x);      // (the descriptor's first chunk is sized for the variation kinds)
         if (IS_VAR && n > 0) {
             long long lo = (long long)(((uint64_t)d1.y << 32) | d1.x), hi = (long long)(((uint64_t)d1.w << 32) | d1.z);
             stage_span(A.seq4, lo, hi, 1, &src, &sbytes, &s_seqlo);
@@ -1227,7 +1238,7 @@ k_tile(TileArgs A) {
             if (cb >= d.y) { more = false; break; }
             __syncthreads();                       // staging buffers free again
             if (tid == 0) {
-                int m = min(TCH, d.y - cb);
+                int m = min(CH, d.y - cb);
                 uint32_t sbytes = 0, cbytes = 0;
                 const uint8_t *src = nullptr, *csrc = nullptr;
                 if (IS_VAR) {
@@ -2035,9 +2046,9 @@ k_refpack(const uint8_t *__restrict__ ref, int64_t ref_start, int64_t ref_len, i
 }
 
 template <int KIND>
-static size_t tile_smem_bytes() {
-    size_t narr = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT + 1;   // + raw
-    size_t b = narr * TT * 4 + sizeof(RInfo) * TCH;
+static size_t tile_smem_bytes(bool need_raw = true) {
+    size_t narr = KindInfo<KIND>::NDIFF + KindInfo<KIND>::NPOINT + (need_raw ? 1 : 0);   // + raw (the row mask's own counter)
+    size_t b = narr * TT * 4 + sizeof(RInfo) * ((KIND == KIND_VAR || KIND == KIND_VAR1) ? TCH : TCH_COV);
     if (KIND == KIND_VAR || KIND == KIND_VAR1) b += (REFN_WORDS + 4) * 4 + TSEQ_BYTES + 32 + (TCIG_WORDS + 8) * 4 + (TBAL ? SPAN_MAX * sizeof(SpanRec) : 0) + (LayVar::DEFER ? EV_SLOTS * EV_STRIDE * 2 : 0);
     return b;
 }
@@ -2054,7 +2065,7 @@ static cudaError_t launch_tile_mq(const TileArgs &a, int64_t ntiles, cudaStream_
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_tile<KIND, STAT, MINQ><<<(unsigned)ntiles, KindLaunch<KIND>::NT, smem, s>>>(a);
+    k_tile<KIND, STAT, MINQ><<<(unsigned)ntiles, KindLaunch<KIND>::NT, tile_smem_bytes<KIND>(a.need_raw != 0), s>>>(a);
     return cudaGetLastError();
 }
 template <int KIND, int STAT>

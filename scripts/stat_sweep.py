@@ -35,7 +35,7 @@ for stat in config.pileup_types:
                           ref_len=int(ref.numel()) if withref else 0, contig_len=L,
                           flags=_cabi.PSS_FLAG_GENERIC_KERNEL if args.generic else 0, min_baseq=args.min_baseq, no_dup=args.no_dup)
     ctx.prepare(rs, with_qual=need_qual, no_dup=args.no_dup, stream=s)
-    for _ in range(2):
+    for _ in range(int(os.environ.get('SWEEP_WARMUP', 2))):
         ctx.pileup_prepared(p, out, mask, stream=s)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
