@@ -132,6 +132,7 @@ struct TileArgs {
     int64_t start, end;
     int64_t stride;            // elements between consecutive fields of `out`
     int32_t no_del;
+    int32_t min_baseq;         // > 0 with lowq set: events of bases below it are dropped (opt.pyx:1900-1903)
     int32_t need_raw;          // read-level filters active: the row mask needs its own counter
     int32_t narrow;            // 1: out is uint16 [field][stride], 2: uint8 [field][stride] (padded rows): the host entry points' transport
     int32_t *ovf8;             // narrow == 2: set when a count does not fit 8 bits
@@ -637,6 +638,31 @@ __device__ __forceinline__ void lowq_span(const uint32_t *mw, int x, int l, int 
     for (int w = w0 + part; w <= w1; w += nparts) word(__ldg(mw + w), w);       // the threads sharing a read take words in turn
 }
 
+// The same over maximal RUNS of marked bases: calls f(p, len) with the tile-relative position of a run's first base.
+// What a dropped event takes out of an interval-add counter is linear, so a run costs one interval (two atomics)
+// whatever its length -- and marks come in runs: the mate-overlap rewrite zeroes the whole overlap of one mate
+// (SURVEY.md A.3), 50 bases and more in a row.  (A run that crosses a 32-bit mark word is reported in two pieces.)
+template <class F>
+__device__ __forceinline__ void lowq_runs(const uint32_t *mw, int x, int l, int y, int t0, F f) {
+    const int a = max(x - t0, 0), b = min(x + l - t0, TT);
+    if (a >= b) return;
+    const int qa = y + (a + t0 - x), qb = y + (b + t0 - x);       // query range [qa, qb)
+    const int w0 = qa >> 5, w1 = (qb - 1) >> 5;
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t m = __ldg(mw + w);
+        const int base = w << 5;
+        if (base < qa) m &= 0xffffffffu << (qa - base);
+        if (base + 32 > qb) m &= 0xffffffffu >> (base + 32 - qb);
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            const uint32_t inv = ~(m >> bit);
+            const int len = inv ? __ffs(inv) - 1 : 32 - bit;
+            f(a + (base + bit - qa), len);
+            m = (len + bit >= 32) ? 0u : (m & (0xffffffffu << (bit + len)));
+        }
+    }
+}
+
 // variation kinds (LayVar).  Reads without sequence have quality 0 at every base: they keep only their
 // deletion / ref-skip events, which var_read is told through `drop_bases`.
 template <class L>
@@ -692,33 +718,34 @@ __device__ void cover_lowq_fix(const TileCtx &T, const TileArgs &A, const RInfo 
     const uint32_t *mw = A.lowq + (r.seq_off >> 4) + ridx;
     const uint32_t *cg = A.cigar + r.cigar_off;
     const int nc = (int)r.n_cigar;
-    auto undo = [&](int p, int, bool) {
+    auto undo = [&](int p, int len) {              // a run of marked bases [p, p + len): one interval per counter word
+        const int e = p + len;
         if (KIND == KIND_COV) {
             const uint32_t inc = half_inc(cls & CLS_REV ? 1 : 0);
-            uint32_t *al = T.cnt + ((cls >> 1) & 1u) * TT + p;
-            atomicAdd(al, 0u - inc);
-            if (p + 1 < TT) atomicAdd(al + 1, inc);
+            uint32_t *al = T.cnt + ((cls >> 1) & 1u) * TT;
+            atomicAdd(al + p, 0u - inc);
+            if (e < TT) atomicAdd(al + e, inc);
         } else {
             const uint32_t m = (cls >> CLS_EXT_SHIFT) & 255u;
-            uint32_t *base = T.cnt + (cls & CLS_REV ? 4 : 0) * TT + p;
+            uint32_t *base = T.cnt + (cls & CLS_REV ? 4 : 0) * TT;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const uint32_t bits = (m >> (2 * g)) & 3u;
                 if (bits) {
                     const uint32_t v = (bits & 1u) | ((bits >> 1) << 16);
-                    atomicAdd(base + g * TT, 0u - v);
-                    if (p + 1 < TT) atomicAdd(base + g * TT + 1, v);
+                    atomicAdd(base + g * TT + p, 0u - v);
+                    if (e < TT) atomicAdd(base + g * TT + e, v);
                 }
             }
         }
     };
-    if (cls & CLS_SIMPLE) { lowq_span(mw, r.pos, r.end - r.pos, 0, T.t0, undo); return; }
+    if (cls & CLS_SIMPLE) { lowq_runs(mw, r.pos, r.end - r.pos, 0, T.t0, undo); return; }
     int x = r.pos, y = 0;
     for (int k = 0; k < nc && x < T.t1; ++k) {
         const uint32_t w = __ldg(cg + k);
         const int op = w & 15, l = (int)(w >> 4);
         if (op_is_match(op)) {
-            if (x + l > T.t0) lowq_span(mw, x, l, y, T.t0, undo);
+            if (x + l > T.t0) lowq_runs(mw, x, l, y, T.t0, undo);
             x += l; y += l;
         } else if (op == OP_D || op == OP_N) x += l;
         else if (op == OP_I || op == OP_S) y += l;
@@ -1382,15 +1409,16 @@ __device__ __forceinline__ int q_rootmean(unsigned long long sq, uint32_t n) {
 }
 
 // one aligned span [x, x + l) of a read whose first base is query index y: the lanes' four positions
+// (minq: events of bases below min_baseq are dropped, opt.pyx:1900-1903; 0 keeps everything)
 template <int BANK>
-__device__ __forceinline__ void q_gather_span(uint32_t (&acc)[4][4], const uint8_t *qual, int p0, int x, int l, int y) {
+__device__ __forceinline__ void q_gather_span(uint32_t (&acc)[4][4], const uint8_t *qual, int p0, int x, int l, int y, uint32_t minq) {
     const int off0 = p0 - x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int off = off0 + i;
         if ((unsigned)off < (unsigned)l) {
             const uint32_t q = qual[y + off];
-            acc[BANK][i] += q * q;
+            if (q >= minq) acc[BANK][i] += q * q;
         }
     }
 }
@@ -1495,6 +1523,8 @@ k_tileq(TileArgs A) {
     uint32_t *rawp = A.need_raw ? raw : nullptr;
     __syncthreads();           // barrier initialised, counters zeroed
     const int maxspan = A.st->maxspan;
+    const bool minq = A.lowq != nullptr;                   // min_baseq > 0: the marked bases' events are dropped
+    const uint32_t gminq = minq ? (uint32_t)A.min_baseq : 0u;
 
     // gather state: this warp's window and read parity; per bank, per owned position
     const int gw0 = T.t0 + (warp & 3) * 128, gw1 = gw0 + 128, gpar = warp >> 2;
@@ -1540,20 +1570,47 @@ k_tileq(TileArgs A) {
                             if (sq & 255u) interval_add(cnt + (8 + bank) * TT, r.pos, r.end - r.pos, T.t0, sq & 255u);
                             if (sq >> 8) interval_add(cnt + (12 + bank) * TT, r.pos, r.end - r.pos, T.t0, sq >> 8);
                         }
+                    } else if (minq && !(cls & CLS_HASSEQ)) {
+                        // KIND_BQ under min_baseq, no sequence: quality 0 at every base -- only the deletion / ref-skip events remain
+                        if (!T.no_del) {
+                            if (cls & CLS_NOREF) interval_add(cnt + bank * TT, r.pos, 1, T.t0, 1u);
+                            else {
+                                const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
+                                int x = r.pos;
+                                for (int k = 0; k < (int)r.n_cigar && x < T.t1; ++k) {
+                                    const uint32_t w = cg[k];
+                                    const int op = w & 15, l = (int)(w >> 4);
+                                    if (op_is_match(op)) x += l;
+                                    else if (op == OP_D || op == OP_N) { if (x + l > T.t0) interval_add(cnt + bank * TT, x, l, T.t0, 1u); x += l; }
+                                }
+                            }
+                        }
                     } else {                       // KIND_BQ: n counts every event, nnd the non-deletions (opt.pyx:1108-1112)
                         if (!T.no_del) interval_add(cnt + bank * TT, r.pos, r.end - r.pos, T.t0, 1u);
-                        if (cls & CLS_SIMPLE) interval_add(cnt + (4 + bank) * TT, r.pos, r.end - r.pos, T.t0, 1u);
-                        else if (!(cls & CLS_NOREF)) {
+                        // under min_baseq the marked bases (k_lowq) are taken back out of both counts
+                        const uint32_t *mw = minq ? A.lowq + (r.seq_off >> 4) + (cb + tid) : nullptr;
+                        auto undo = [&](int p, int run) {
+                            if (!T.no_del) interval_add(cnt + bank * TT, T.t0 + p, run, T.t0, 0u - 1u);
+                            interval_add(cnt + (4 + bank) * TT, T.t0 + p, run, T.t0, 0u - 1u);
+                        };
+                        if (cls & CLS_SIMPLE) {
+                            interval_add(cnt + (4 + bank) * TT, r.pos, r.end - r.pos, T.t0, 1u);
+                            if (minq) lowq_runs(mw, r.pos, r.end - r.pos, 0, T.t0, undo);
+                        } else if (!(cls & CLS_NOREF)) {
                             const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
                             const int nc = (int)r.n_cigar;
-                            int x = r.pos;
+                            int x = r.pos, y = 0;
                             for (int k = 0; k < nc && x < T.t1; ++k) {
                                 const uint32_t w = cg[k];
                                 const int op = w & 15, l = (int)(w >> 4);
                                 if (op_is_match(op)) {
-                                    if (x + l > T.t0) interval_add(cnt + (4 + bank) * TT, x, l, T.t0, 1u);
-                                    x += l;
+                                    if (x + l > T.t0) {
+                                        interval_add(cnt + (4 + bank) * TT, x, l, T.t0, 1u);
+                                        if (minq) lowq_runs(mw, x, l, y, T.t0, undo);
+                                    }
+                                    x += l; y += l;
                                 } else if (op == OP_D || op == OP_N) x += l;
+                                else if (op == OP_I || op == OP_S) y += l;
                             }
                         }
                     }
@@ -1604,7 +1661,7 @@ k_tileq(TileArgs A) {
                     // counted, with sequence (else quality 0) and with bases at all
                     if (rend <= gw0 || (cls & (CLS_COUNTED | CLS_HASSEQ | CLS_NOREF)) != (CLS_COUNTED | CLS_HASSEQ)) continue;
                     const uint8_t *qual = s_qual + (int)(qoff - quallo);
-#define QSPAN(B, x, l, y) q_gather_span<B>(acc, qual, gp0, x, l, y)
+#define QSPAN(B, x, l, y) q_gather_span<B>(acc, qual, gp0, x, l, y, gminq)
 #define QSPANS(x, l, y) do { switch (bank) { case 0: QSPAN(0, x, l, y); break; case 1: QSPAN(1, x, l, y); break; \
                                              case 2: QSPAN(2, x, l, y); break; default: QSPAN(3, x, l, y); break; } } while (0)
                     if (cls & CLS_SIMPLE) QSPANS(rpos, rend - rpos, 0);
@@ -1757,6 +1814,9 @@ k_tileq(TileArgs A) {
 // difference arrays) | sum[c] 64-bit at words 6.., sumsq[c] 64-bit at words 14.. (64-bit difference arrays)
 #define TLEN_NW 22
 #define TLEN_NT 256
+#ifndef TLEN_CTAS
+#define TLEN_CTAS 4           // 52 KB of shared memory per CTA: a fourth fits (tlen_strand 5.49 -> 4.92 ms per 50 Mb)
+#endif
 
 __device__ __forceinline__ void interval_add64(unsigned long long *arr, int x, int l, int t0, unsigned long long inc) {
     int a = max(x - t0, 0), b = min(x + l - t0, TT);
@@ -1823,7 +1883,7 @@ __device__ __forceinline__ TlenOut tlen_class(unsigned n, long long S, unsigned 
 }
 
 template <int STAT>
-__global__ void __launch_bounds__(TLEN_NT, 3)
+__global__ void __launch_bounds__(TLEN_NT, TLEN_CTAS)
 k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ tile_redo, float force) {
     constexpr int NWARPS = TLEN_NT / 32;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1878,6 +1938,7 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ tile
         for (int k = tid; k < nw4; k += TLEN_NT) reinterpret_cast<uint4 *>(cnt)[k] = z;
     }
     uint32_t *rawp = A.need_raw ? raw : nullptr;
+    const bool minq = A.lowq != nullptr;
     __syncthreads();
     uint32_t parity = 0;
     for (int cb = dx; cb < dy;) {
@@ -1895,15 +1956,54 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ tile
                 if (cls & CLS_COUNTED) {
                     const int rev = cls & CLS_REV ? 1 : 0;
                     const long long t = s_tlen[tid + tskew];
-                    interval_add(cnt + rev * TT, r.pos, len, t0, 1u);
+                    // the read's contribution to [x, x + l): +1 / +t / +t^2 per class (sign: taken back out again)
+                    auto contrib = [&](int x, int l, bool neg) {
+                        interval_add(cnt + rev * TT, x, l, t0, neg ? 0u - 1u : 1u);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        if (cls & (g ? CLS_PP : CLS_PAIRED)) {
-                            const int c = 2 * g + rev;
-                            interval_add(cnt + (2 + c) * TT, r.pos, len, t0, 1u);
-                            if (t) {
-                                interval_add64(sum + c * TT, r.pos, len, t0, (unsigned long long)t);
-                                interval_add64(sumsq + c * TT, r.pos, len, t0, (unsigned long long)(t * t));
+                        for (int g = 0; g < 2; ++g) {
+                            if (cls & (g ? CLS_PP : CLS_PAIRED)) {
+                                const int c = 2 * g + rev;
+                                interval_add(cnt + (2 + c) * TT, x, l, t0, neg ? 0u - 1u : 1u);
+                                if (t) {
+                                    const unsigned long long ut = (unsigned long long)t, uq = (unsigned long long)(t * t);
+                                    interval_add64(sum + c * TT, x, l, t0, neg ? 0ull - ut : ut);
+                                    interval_add64(sumsq + c * TT, x, l, t0, neg ? 0ull - uq : uq);
+                                }
+                            }
+                        }
+                    };
+                    if (!minq) contrib(r.pos, len, false);
+                    else if (!(cls & CLS_HASSEQ)) {
+                        // min_baseq > 0, no sequence: quality 0 at every base -- only the deletion / ref-skip events remain
+                        if (cls & CLS_NOREF) contrib(r.pos, 1, false);
+                        else {
+                            const uint32_t *cg = A.cigar + r.cigar_off;
+                            int x = r.pos;
+                            for (int k = 0; k < (int)r.n_cigar && x < t0 + TT; ++k) {
+                                const uint32_t w = __ldg(cg + k);
+                                const int op = w & 15, l = (int)(w >> 4);
+                                if (op_is_match(op)) x += l;
+                                else if (op == OP_D || op == OP_N) { if (x + l > t0) contrib(x, l, false); x += l; }
+                            }
+                        }
+                    } else {
+                        // min_baseq > 0: as if every base passed, then the marked bases (k_lowq) are taken back out
+                        lowq_prefetch(A, r, cb + tid);
+                        contrib(r.pos, len, false);
+                        if (!(cls & CLS_NOREF)) {
+                            const uint32_t *mw = A.lowq + (r.seq_off >> 4) + (cb + tid);
+                            auto undo = [&](int p, int run) { contrib(t0 + p, run, true); };
+                            if (cls & CLS_SIMPLE) lowq_runs(mw, r.pos, len, 0, t0, undo);
+                            else {
+                                const uint32_t *cg = A.cigar + r.cigar_off;
+                                int x = r.pos, y = 0;
+                                for (int k = 0; k < (int)r.n_cigar && x < t0 + TT; ++k) {
+                                    const uint32_t w = __ldg(cg + k);
+                                    const int op = w & 15, l = (int)(w >> 4);
+                                    if (op_is_match(op)) { if (x + l > t0) lowq_runs(mw, x, l, y, t0, undo); x += l; y += l; }
+                                    else if (op == OP_D || op == OP_N) x += l;
+                                    else if (op == OP_I || op == OP_S) y += l;
+                                }
                             }
                         }
                     }
@@ -2148,11 +2248,11 @@ static cudaError_t launch_tilet_one(const TileArgs &a, const int32_t *tlen, int3
 
 bool tile_kernel_supports(int stat, int min_baseq, int no_del) {
     if (tile_kernel_counting(stat)) return true;      // min_baseq > 0: the bases below it are taken back out (k_lowq)
-    if (min_baseq > 0) return false;                  // the other kinds: every event depends on its base, generic kernel
     switch (stat) {
-    case PSS_TLEN: case PSS_TLEN_STRAND: return !no_del;     // intervals are whole reads: deletions need the CIGAR
-    case PSS_MAPQ: case PSS_MAPQ_STRAND: return !no_del;     // the max needs the CIGAR then: generic kernel
-    case PSS_BASEQ: case PSS_BASEQ_STRAND: case PSS_BASEQ_EXT: case PSS_BASEQ_EXT_STRAND: return true;
+    case PSS_TLEN: case PSS_TLEN_STRAND: return !no_del;     // intervals are whole reads: deletions need the CIGAR (min_baseq: k_lowq marks)
+    case PSS_MAPQ: case PSS_MAPQ_STRAND: return !no_del && min_baseq <= 0;   // the max needs every event's CIGAR / quality then: generic kernel
+    case PSS_BASEQ: case PSS_BASEQ_STRAND: return true;      // min_baseq: k_lowq marks for the counts, the threshold in the gather
+    case PSS_BASEQ_EXT: case PSS_BASEQ_EXT_STRAND: return min_baseq <= 0;
     default: return false;
     }
 }
@@ -2195,7 +2295,8 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     TileArgs a;
     a.ri = p.ri; a.cigar = p.cigar; a.seq4 = p.seq4; a.seq_off = seq_off; a.desc = desc;
     a.qual = p.qual; a.qual_off = p.qual_off;
-    a.lowq = (p.min_baseq > 0 && tile_kernel_counting(stat)) ? p.lowq : nullptr;
+    a.lowq = p.min_baseq > 0 ? p.lowq : nullptr;
+    a.min_baseq = p.min_baseq;
     a.refpack = (const uint32_t *)refpack_buf;
     a.tflags = (const uint32_t *)refpack_buf + (ntiles * REFN_WORDS + 8);
     a.ref = p.ref; a.ref_start = p.ref_start; a.ref_len = p.ref_len; a.start = p.start; a.end = p.end;

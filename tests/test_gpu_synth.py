@@ -76,7 +76,8 @@ def test_synthetic_vs_oracle(stat, ctx, small):
 @pytest.mark.parametrize('stat', TILE_STATS)
 def test_tile_kernel_equals_generic_kernel(stat, ctx, small):
     nb, ref, _ = small
-    for kw in (dict(), dict(no_del=True, min_mapq=30)):
+    for kw in (dict(), dict(no_del=True, min_mapq=30), dict(min_baseq=25), dict(min_baseq=36, no_dup=True),
+               dict(min_baseq=30, no_del=True)):
         a, ma = _run_host(ctx, nb, ref, stat, 1000, G - 777, **kw)
         b, mb = _run_host(ctx, nb, ref, stat, 1000, G - 777, flags=_cabi.PSS_FLAG_GENERIC_KERNEL, **kw)
         assert np.array_equal(a, b) and np.array_equal(ma, mb), (stat, kw)
