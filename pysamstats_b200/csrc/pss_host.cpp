@@ -7,7 +7,7 @@
 // {block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, l_seq, next_refID,
 //  next_pos, tlen, read_name, cigar, seq, qual, aux}.
 #include "../../include/pss_host.h"
-#include <emmintrin.h>
+#include <immintrin.h>
 
 #include "pss_inflate.h"
 
@@ -934,6 +934,22 @@ extern "C" int pss_format_rows(int64_t n_rows, int32_t n_cols, const int32_t *ki
 
 extern "C" void pss_host_free(void *p) { free(p); }
 
+// modes 3 / 4 of the probe below: the same stores as whole 64-byte lines (AVX-512)
+__attribute__((target("avx512f,avx512bw"))) static void bw_avx512(uint8_t *b, const uint8_t *sp, int64_t bytes, int reps) {
+    const int64_t n4 = bytes / 4;
+    for (int r = 0; r < reps; ++r) {
+        int *d = (int *)b;
+        if (!sp) {
+            const __m512i v = _mm512_set1_epi32(r);
+            for (int64_t i = 0; i < n4; i += 16) _mm512_stream_si512((__m512i *)(d + i), v);
+        } else {
+            for (int64_t i = 0; i < n4; i += 16)
+                _mm512_stream_si512((__m512i *)(d + i), _mm512_cvtepu8_epi32(_mm_loadu_si128((const __m128i *)(sp + i))));
+        }
+    }
+    _mm_sfence();
+}
+
 // Host memory bandwidth probe: `n_threads` threads stream over a private buffer of `bytes` each, `reps` times.
 // mode 0: non-temporal int32 stores (what the result path does to the caller's columns), 1: widen u8 -> int32
 // (1 byte read, 4 written), 2: plain reads.  Returns GB/s of bytes WRITTEN (mode 2: read), < 0 on failure.
@@ -944,12 +960,14 @@ extern "C" double pss_host_bandwidth(int64_t bytes, int n_threads, int reps, int
     std::vector<uint8_t *> bufs((size_t)n_threads, nullptr), srcs((size_t)n_threads, nullptr);
     for (int t = 0; t < n_threads; ++t) {
         if (posix_memalign((void **)&bufs[(size_t)t], 64, (size_t)bytes) != 0) return -1.0;
-        if (mode == 1 && posix_memalign((void **)&srcs[(size_t)t], 64, (size_t)bytes / 4) != 0) return -1.0;
+        if ((mode == 1 || mode == 4) && posix_memalign((void **)&srcs[(size_t)t], 64, (size_t)bytes / 4) != 0) return -1.0;
     }
     std::atomic<int> ready(0), go(0);
     std::atomic<uint64_t> sink(0);
     std::vector<std::thread> th;
+    if ((mode == 3 || mode == 4) && !__builtin_cpu_supports("avx512f")) return -2.0;
     auto body = [&](int t, int r_n) {
+        if (mode == 3 || mode == 4) { bw_avx512(bufs[(size_t)t], mode == 4 ? srcs[(size_t)t] : nullptr, bytes, r_n); return; }
         uint8_t *b = bufs[(size_t)t];
         const int64_t n4 = bytes / 4;
         for (int r = 0; r < r_n; ++r) {
@@ -977,7 +995,7 @@ extern "C" double pss_host_bandwidth(int64_t bytes, int n_threads, int reps, int
     for (int t = 0; t < n_threads; ++t)
         th.emplace_back([&, t] {
             memset(bufs[(size_t)t], 1, (size_t)bytes);                 // first touch outside the timed part
-            if (mode == 1) memset(srcs[(size_t)t], 3, (size_t)bytes / 4);
+            if (mode == 1 || mode == 4) memset(srcs[(size_t)t], 3, (size_t)bytes / 4);
             ready.fetch_add(1);
             while (!go.load()) std::this_thread::yield();
             body(t, reps);
