@@ -669,7 +669,7 @@ template <class L>
 __device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t *cg, const RInfo &r, uint32_t sn0, int ridx,
                              int part, int nparts) {
     const uint32_t cls = r.cls;
-    if (!(cls & CLS_COUNTED) || (cls & CLS_NOREF) || !(cls & CLS_HASSEQ)) return;
+    if (part != 0 || !(cls & CLS_COUNTED) || (cls & CLS_NOREF) || !(cls & CLS_HASSEQ)) return;
     const int bank = cls & 3u;
     const uint32_t inc = cinc<L>(bank);
     const uint32_t *mw = A.lowq + (r.seq_off >> 4) + ridx;
@@ -681,28 +681,47 @@ __device__ void var_lowq_fix(const TileCtx &T, const TileArgs &A, const uint32_t
         if (op_is_match(op)) {
             if (x + l > T.t0) {
                 const bool ins = ins_follows(cg, nc, k);
-                lowq_span(mw, x, l, y, T.t0, [&](int p, int qi, bool last) {
-                    uint32_t *al = carr<L>(T, L::ALL, bank) + p;
-                    atomicAdd(al, 0u - inc);
-                    if (p + 1 < TT) atomicAdd(al + 1, inc);
-                    const uint32_t kk = sn0 + (uint32_t)qi;
-                    const int code = (T.seqw[kk >> 3] >> (((kk & 7) ^ 1) << 2)) & 15;
-                    int rc;
-                    if (T.slow) {
-                        const int64_t ro = (int64_t)T.t0 + p - T.ref_start;
-                        rc = (T.ref && ro >= 0 && ro < T.ref_len) ? c_refcode[__ldg(T.ref + ro)] : 16;
-                    } else rc = (T.refn[p >> 3] >> ((7 - (p & 7)) << 2)) & 15;
-                    if (code == rc) {
-                        uint32_t *m = carr<L>(T, L::MATCH, bank) + p;
-                        atomicAdd(m, 0u - inc);
-                        if (p + 1 < TT) atomicAdd(m + 1, inc);
-                    } else {
-                        atomicAdd(carr<L>(T, L::MMT, bank) + p, 0u - inc);
+                // a RUN of marked bases [p, p + len) leaves the read count and the match count as one interval each (the
+                // mate-overlap rewrite marks whole overlaps); only its mismatching bases -- which the walk had already
+                // taken out of the match count -- are handled one by one
+                lowq_runs(mw, x, l, y, T.t0, [&](int p, int len) {
+                    const int e = p + len;
+                    uint32_t *al = carr<L>(T, L::ALL, bank), *mt = carr<L>(T, L::MATCH, bank);
+                    atomicAdd(al + p, 0u - inc);
+                    atomicAdd(mt + p, 0u - inc);
+                    if (e < TT) { atomicAdd(al + e, inc); atomicAdd(mt + e, inc); }
+                    const int qi0 = y + (T.t0 + p - x);
+                    auto mismatch = [&](int pj, int code) {
+                        atomicAdd(mt + pj, inc);                       // it was no match: undo the interval here
+                        if (pj + 1 < TT) atomicAdd(mt + pj + 1, 0u - inc);
+                        atomicAdd(carr<L>(T, L::MMT, bank) + pj, 0u - inc);
                         const int c = mm_class(code);
-                        if (c < 5) atomicAdd(carr<L>(T, L::MMC + L::PER * c, bank) + p, 0u - inc);
+                        if (c < 5) atomicAdd(carr<L>(T, L::MMC + L::PER * c, bank) + pj, 0u - inc);
+                    };
+                    if (T.slow) {               // a reference position of this tile has no 4-bit code: base by base
+                        for (int j = 0; j < len; ++j) {
+                            const uint32_t kk = sn0 + (uint32_t)(qi0 + j);
+                            const int code = (T.seqw[kk >> 3] >> (((kk & 7) ^ 1) << 2)) & 15;
+                            const int64_t ro = (int64_t)T.t0 + p + j - T.ref_start;
+                            const int rc = (T.ref && ro >= 0 && ro < T.ref_len) ? c_refcode[__ldg(T.ref + ro)] : 16;
+                            if (code != rc) mismatch(p + j, code);
+                        }
+                    } else {                    // eight bases per step, as the walk compares them
+                        for (int j = 0; j < len; j += 8) {
+                            const uint32_t sn = sn0 + (uint32_t)(qi0 + j), rn = (uint32_t)(p + j);
+                            const uint32_t *sp = T.seqw + (sn >> 3), *rp = T.refn + (rn >> 3);
+                            const uint32_t sw = __funnelshift_l(__byte_perm(sp[1], 0, 0x0123), __byte_perm(sp[0], 0, 0x0123), (sn & 7) << 2);
+                            uint32_t xr = sw ^ __funnelshift_l(rp[1], rp[0], (rn & 7) << 2);
+                            if (len - j < 8) xr &= 0xffffffffu << ((8 - (len - j)) << 2);
+                            while (xr) {
+                                const int lz = __clz(xr) >> 2, sh = 28 - (lz << 2);
+                                mismatch(p + j + lz, (sw >> sh) & 15);
+                                xr &= ~(0xfu << sh);
+                            }
+                        }
                     }
-                    if (last && ins) atomicAdd(carr<L>(T, L::INS, bank) + p, 0u - inc);
-                }, part, nparts);
+                    if (ins && qi0 + len - 1 == y + l - 1) atomicAdd(carr<L>(T, L::INS, bank) + e - 1, 0u - inc);
+                });
             }
             x += l; y += l;
         } else if (op == OP_D || op == OP_N) x += l;
