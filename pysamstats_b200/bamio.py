@@ -351,8 +351,10 @@ class BamFile(object):
                 return cand
         return None
 
-    def _decode(self, lib, h):
-        """SoA arrays of the records behind an open native handle -> (ReadBatch, tid array)."""
+    def _decode(self, lib, h, light=False):
+        """SoA arrays of the records behind an open native handle -> (ReadBatch, tid array).  ``light``: without base
+        qualities and read names (150 + ~10 of the ~300 bytes of a record that requests which do not read qualities never
+        look at: not allocated, not copied)."""
         n, nc, ns, nq, w = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
         _host_check(lib, lib.pss_bam_sizes(h, C.byref(n), C.byref(nc), C.byref(ns), C.byref(nq), C.byref(w)))
         n, nc, ns, nq, w = n.value, nc.value, ns.value, nq.value, w.value
@@ -364,16 +366,22 @@ class BamFile(object):
         A.endpos = np.empty(n, 'i8')
         A.cigar_off, A.cigar = np.empty(n + 1, 'i8'), np.empty(max(nc, 1), 'u4')
         A.seq_off, A.seq4 = np.empty(n + 1, 'i8'), np.empty(max(ns, 1), 'u1')
-        A.qual_off, A.qual = np.empty(n + 1, 'i8'), np.empty(max(nq, 1), 'u1')
-        names = np.zeros(n, dtype='S%d' % w)
+        if light:
+            A.qual_off, A.qual, names = None, np.zeros(1, 'u1'), None
+        else:
+            A.qual_off, A.qual = np.empty(n + 1, 'i8'), np.empty(max(nq, 1), 'u1')
+            names = np.zeros(n, dtype='S%d' % w)
         ha = HostArrays()
         ha.tid = tid.ctypes.data
         for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'endpos', 'cigar_off', 'cigar', 'seq_off',
-                  'seq4', 'qual_off', 'qual'):
+                  'seq4') + (() if light else ('qual_off', 'qual')):
             setattr(ha, k, getattr(A, k).ctypes.data)
-        ha.names = names.ctypes.data
+        if not light:
+            ha.names = names.ctypes.data
         _host_check(lib, lib.pss_bam_fill(h, C.byref(ha)))
-        A.cigar, A.seq4, A.qual = A.cigar[:nc], A.seq4[:ns], A.qual[:nq]
+        A.cigar, A.seq4 = A.cigar[:nc], A.seq4[:ns]
+        if not light:
+            A.qual = A.qual[:nq]
         A.names = names
         A.name_prev = None
         tr, ti, tx, rb = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
@@ -393,7 +401,7 @@ class BamFile(object):
                 lib.pss_bam_close(h)
         return self._all
 
-    def _region_native(self, tid, start, end, bai):
+    def _region_native(self, tid, start, end, bai, light=False):
         lib = host_lib()
         h = C.c_void_p()
         rc = lib.pss_bam_open_region(self.filename.encode(), bai.encode(), int(tid), int(start), int(end),
@@ -405,7 +413,7 @@ class BamFile(object):
             return None
         _host_check(lib, rc)
         try:
-            b, _ = self._decode(lib, h)
+            b, _ = self._decode(lib, h, light)
         finally:
             lib.pss_bam_close(h)
         b.tid = tid
@@ -546,7 +554,7 @@ class BamFile(object):
 
             def want(k):
                 if k < n and k not in futs:
-                    futs[k] = ex.submit(self._region_native, tid, cuts[k], cuts[k + 1], bai)
+                    futs[k] = ex.submit(self._region_native, tid, cuts[k], cuts[k + 1], bai, True)   # (streamed requests never read qualities)
             for k in range(min(n, 1 + ahead)):
                 want(k)
             for k in range(n):

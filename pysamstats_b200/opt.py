@@ -173,7 +173,7 @@ def _streamed_pieces(bam, c, s, e, truncate, pad, max_depth, state):
         if batch is None:                               # unusable index: the rest in one ordinary region query
             tail = bam.region_batch(c, cuts[k], e)
         elif _refusable(batch, max_depth)[1] and k + 1 < n:
-            tail = bam._region_native(bam.get_tid(c), cuts[k], e, bam.index_path()) or bam.region_batch(c, cuts[k], e)
+            tail = bam._region_native(bam.get_tid(c), cuts[k], e, bam.index_path(), True) or bam.region_batch(c, cuts[k], e)
         if tail is not None:
             batch = tail
         last = tail is not None or k == n - 1
