@@ -382,7 +382,9 @@ def main():
     lo, hi = shard.plan_intervals(0, genome, world, align=ALIGN)[rank]
     npos = hi - lo
     t_gen = time.time()
-    batch, (ref, ref_lo) = synth.make_interval_batch(lo, hi, genome, depth=args.depth, read_len=args.read_len,
+    # (the batch reaches one position beyond the interval: a read that starts exactly at `hi` belongs to the rank's last
+    # window under the strict roll-over of opt.pyx:2050; it covers no position of [lo, hi))
+    batch, (ref, ref_lo) = synth.make_interval_batch(lo, min(hi + 1, genome), genome, depth=args.depth, read_len=args.read_len,
                                                      device=dev, with_qual=True)
     torch.cuda.synchronize()
     t_gen = time.time() - t_gen

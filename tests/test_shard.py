@@ -104,8 +104,10 @@ def _rank_main(rank, world, port, G, stat, tmp):
     from oracle import oracle as orc
     from _util import oracle_reads_from_arrays
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    lo, hi = shard.plan_intervals(0, G, world)[rank]
-    batch, (ref, ref_lo) = synth.make_interval_batch(lo, hi, G, block=100000, with_qual=True)
+    lo, hi = shard.plan_intervals(0, G, world, align=38400)[rank]       # lcm(512, 300): tile AND window aligned, as bench.py cuts
+    # (reads that start exactly at hi belong to the rank's last window -- strict roll-over, opt.pyx:2050 -- so the batch reaches one
+    # position further than the pileup range; they cover no position below hi)
+    batch, (ref, ref_lo) = synth.make_interval_batch(lo, min(hi + 1, G), G, block=100000, with_qual=True)
     nb = synth.batch_to_numpy(batch)
     refb = np.zeros(ref_lo + ref.numel(), 'u1')
     refb[ref_lo:] = ref.numpy()
@@ -115,9 +117,21 @@ def _rank_main(rank, world, port, G, stat, tmp):
     dist.gather_object((pos, F), gathered, dst=0)
     n_rows = torch.tensor([len(pos)], dtype=torch.int64)
     dist.all_reduce(n_rows)                      # the only reduction bench.py does: counts / max time
+    # the binned sweep of bench.py's `binned` arm: the rank's windows (global bin edges), the reads that START in them
+    W = 300
+    n_all = -(-G // W)
+    i0, i1 = shard.window_read_range(nb['pos'], 0, W, lo // W, -(-hi // W), n_all)
+    sub = {k: (v[i0:i1] if k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'endpos', 'name_prev') else v) for k, v in nb.items()}
+    for off in ('cigar_off', 'seq_off', 'qual_off'):
+        sub[off] = nb[off][i0:i1 + 1]
+    sub['n_reads'] = i1 - i0
+    binned = {t: orc.binned_packed(t, oracle_reads_from_arrays(sub), lo, hi, W, W // 2, ref=refb.tobytes())[1] for t in ('coverage', 'mapq', 'tlen')}
+    bg = [None] * world if rank == 0 else None
+    dist.gather_object(binned, bg, dst=0)
     if rank == 0:
         out = shard.concat_shards([(p, f.T) for p, f in gathered])
-        np.savez(tmp, pos=out[0], F=out[1].T, total=int(n_rows))
+        np.savez(tmp, pos=out[0], F=out[1].T, total=int(n_rows),
+                 **{'binned_' + t: np.concatenate([b[t] for b in bg]) for t in ('coverage', 'mapq', 'tlen')})
     dist.barrier()
     dist.destroy_process_group()
 
@@ -139,3 +153,7 @@ def test_world_size_2_gloo(tmp_path):
                                   ref=ref.numpy().tobytes(), truncate=True)
     assert int(got['total']) == len(pos)
     assert np.array_equal(got['pos'], pos) and np.array_equal(got['F'], F)
+    reads = oracle_reads_from_arrays(synth.batch_to_numpy(batch))
+    for t in ('coverage', 'mapq', 'tlen'):       # window ranges side by side == the whole contig
+        e = orc.binned_packed(t, reads, 0, G, 300, 150, ref=ref.numpy().tobytes())[1]
+        assert np.array_equal(got['binned_' + t], e), t
