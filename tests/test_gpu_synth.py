@@ -183,6 +183,17 @@ def test_very_deep_single_position(ctx):
     for b, base in enumerate('ACGT'):
         e = np.zeros(400, 'i8'); e[100 + b:200:4] = n
         assert np.array_equal(col[base], e), base
+    # variation without the strand split (one packed word per group: all | proper pair << 16): the same tile in two
+    # passes, every third read a proper pair
+    nbp = dict(nb, flag=(nb['flag'] | np.where(np.arange(n) % 3 == 0, 3, 0)).astype('u2'))
+    out, mask = _run_host(ctx, nbp, ref, 'variation', 900, 1300, max_depth=1000000)
+    col = {f: out[j] for j, f in enumerate(config.value_fields('variation'))}
+    npp = (n + 2) // 3
+    assert np.array_equal(col['reads_all'], cov) and np.array_equal(col['reads_pp'], cov // n * npp)
+    assert np.array_equal(col['matches'], cov) and np.array_equal(col['matches_pp'], cov // n * npp) and col['mismatches'].sum() == 0
+    for b, base in enumerate('ACGT'):
+        e = np.zeros(400, 'i8'); e[100 + b:200:4] = n
+        assert np.array_equal(col[base], e) and np.array_equal(col[base + '_pp'], e // n * npp), base
     # the depth cap at the default 8000: the first read is always admitted, then up to the cap
     out, mask = _run_host(ctx, nb, ref, 'coverage', 900, 1300)
     assert out[0][150] == 8000
