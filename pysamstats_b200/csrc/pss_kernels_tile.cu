@@ -1363,10 +1363,17 @@ k_tile(TileArgs A) {
 // rec() is fused as in k_tile; the fp64 rootmean (opt.pyx:2159-2163) is evaluated per field.
 
 enum { KIND_MAPQ = 3, KIND_BQ = 4, KIND_BQX = 5 };
+#ifndef QCH
 #define QCH 160                        // reads staged per chunk (a 512-position tile of 30x / 150 bp has ~135 candidates)
+#endif
+#ifndef BQ_CTAS
+#define BQ_CTAS 3
+#endif
 #define QSEQ_BYTES (QCH * 76 + 64)
 #define QQUAL_BYTES (QCH * 152 + 64)
+#ifndef QCIG_WORDS
 #define QCIG_WORDS 256
+#endif
 
 // word arrays of TT (bank = rev | pp << 1):
 //   KIND_MAPQ  n[0..3] nz[4..7] sqlo[8..11] sqhi[12..15] (difference arrays)  max[16..19]
@@ -1375,7 +1382,7 @@ enum { KIND_MAPQ = 3, KIND_BQ = 4, KIND_BQX = 5 };
 template <int KIND> struct QKind;
 // NT: threads per CTA (the first 8 warps gather; baseq_ext wants two threads per staged read in the scatter)
 template <> struct QKind<KIND_MAPQ> { static const int NDIFF = 16, NWORDS = 20, SQ = 0, NT = 256, CTAS = 4; static const bool QUAL = false, SEQ = false, CIG = false; };
-template <> struct QKind<KIND_BQ> { static const int NDIFF = 8, NWORDS = 16, SQ = 8, NT = 256, CTAS = 3; static const bool QUAL = true, SEQ = false, CIG = true; };
+template <> struct QKind<KIND_BQ> { static const int NDIFF = 8, NWORDS = 16, SQ = 8, NT = 256, CTAS = BQ_CTAS; static const bool QUAL = true, SEQ = false, CIG = true; };
 template <> struct QKind<KIND_BQX> { static const int NDIFF = 8, NWORDS = 28, SQ = 12, NT = 320, CTAS = 2; static const bool QUAL = true, SEQ = true, CIG = true; };
 
 struct QSmem {       // byte offsets into the dynamic shared memory
@@ -1429,7 +1436,7 @@ __device__ __forceinline__ int q_rootmean(unsigned long long sq, uint32_t n) {
 
 // one aligned span [x, x + l) of a read whose first base is query index y: the lanes' four positions
 // (minq: events of bases below min_baseq are dropped, opt.pyx:1900-1903; 0 keeps everything)
-template <int BANK>
+template <int BANK, bool MINQ>
 __device__ __forceinline__ void q_gather_span(uint32_t (&acc)[4][4], const uint8_t *qual, int p0, int x, int l, int y, uint32_t minq) {
     const int off0 = p0 - x;
 #pragma unroll
@@ -1437,12 +1444,14 @@ __device__ __forceinline__ void q_gather_span(uint32_t (&acc)[4][4], const uint8
         const int off = off0 + i;
         if ((unsigned)off < (unsigned)l) {
             const uint32_t q = qual[y + off];
-            if (q >= minq) acc[BANK][i] += q * q;
+            if (!MINQ || q >= minq) acc[BANK][i] += q * q;
         }
     }
 }
 
-template <int KIND, int STAT>
+// MINQ (baseq / baseq_strand only): min_baseq > 0 -- a compile-time switch, so the kernels of the default case keep
+// their instruction stream (a run-time test in the gather cost baseq 2.93 -> 3.84 ms per 50 Mb)
+template <int KIND, int STAT, bool MINQ>
 __global__ void __launch_bounds__(QKind<KIND>::NT, QKind<KIND>::CTAS)
 k_tileq(TileArgs A) {
     constexpr QSmem L = q_layout<KIND>();
@@ -1542,8 +1551,8 @@ k_tileq(TileArgs A) {
     uint32_t *rawp = A.need_raw ? raw : nullptr;
     __syncthreads();           // barrier initialised, counters zeroed
     const int maxspan = A.st->maxspan;
-    const bool minq = A.lowq != nullptr;                   // min_baseq > 0: the marked bases' events are dropped
-    const uint32_t gminq = minq ? (uint32_t)A.min_baseq : 0u;
+    constexpr bool minq = MINQ;                            // min_baseq > 0: the marked bases' events are dropped
+    const uint32_t gminq = MINQ ? (uint32_t)A.min_baseq : 0u;
 
     // gather state: this warp's window and read parity; per bank, per owned position
     const int gw0 = T.t0 + (warp & 3) * 128, gw1 = gw0 + 128, gpar = warp >> 2;
@@ -1680,7 +1689,7 @@ k_tileq(TileArgs A) {
                     // counted, with sequence (else quality 0) and with bases at all
                     if (rend <= gw0 || (cls & (CLS_COUNTED | CLS_HASSEQ | CLS_NOREF)) != (CLS_COUNTED | CLS_HASSEQ)) continue;
                     const uint8_t *qual = s_qual + (int)(qoff - quallo);
-#define QSPAN(B, x, l, y) q_gather_span<B>(acc, qual, gp0, x, l, y, gminq)
+#define QSPAN(B, x, l, y) q_gather_span<B, MINQ>(acc, qual, gp0, x, l, y, gminq)
 #define QSPANS(x, l, y) do { switch (bank) { case 0: QSPAN(0, x, l, y); break; case 1: QSPAN(1, x, l, y); break; \
                                              case 2: QSPAN(2, x, l, y); break; default: QSPAN(3, x, l, y); break; } } while (0)
                     if (cls & CLS_SIMPLE) QSPANS(rpos, rend - rpos, 0);
@@ -2221,7 +2230,7 @@ cudaError_t launch_lowq(const pss_reads &R, const uint8_t *qual, int min_baseq, 
     return cudaGetLastError();
 }
 
-template <int KIND, int STAT>
+template <int KIND, int STAT, bool MINQ = false>
 static cudaError_t launch_tileq_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
     const size_t smem = (size_t)q_layout<KIND>().total;
     static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
@@ -2229,11 +2238,11 @@ static cudaError_t launch_tileq_one(const TileArgs &a, int64_t ntiles, cudaStrea
     cudaGetDevice(&dev__);
     bool &configured = configured_dev[dev__ & 63];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_tileq<KIND, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_tileq<KIND, STAT, MINQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_tileq<KIND, STAT><<<(unsigned)ntiles, QKind<KIND>::NT, smem, s>>>(a);
+    k_tileq<KIND, STAT, MINQ><<<(unsigned)ntiles, QKind<KIND>::NT, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -2344,8 +2353,9 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     case PSS_VARIATION_STRAND: e = launch_tile_one<KIND_VAR, PSS_VARIATION_STRAND>(a, ntiles, s); break;
     case PSS_MAPQ: e = launch_tileq_one<KIND_MAPQ, PSS_MAPQ>(a, ntiles, s); break;
     case PSS_MAPQ_STRAND: e = launch_tileq_one<KIND_MAPQ, PSS_MAPQ_STRAND>(a, ntiles, s); break;
-    case PSS_BASEQ: e = launch_tileq_one<KIND_BQ, PSS_BASEQ>(a, ntiles, s); break;
-    case PSS_BASEQ_STRAND: e = launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND>(a, ntiles, s); break;
+    case PSS_BASEQ: e = a.lowq ? launch_tileq_one<KIND_BQ, PSS_BASEQ, true>(a, ntiles, s) : launch_tileq_one<KIND_BQ, PSS_BASEQ>(a, ntiles, s); break;
+    case PSS_BASEQ_STRAND: e = a.lowq ? launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND, true>(a, ntiles, s)
+                                      : launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND>(a, ntiles, s); break;
     case PSS_BASEQ_EXT: e = launch_tileq_one<KIND_BQX, PSS_BASEQ_EXT>(a, ntiles, s); break;
     case PSS_BASEQ_EXT_STRAND: e = launch_tileq_one<KIND_BQX, PSS_BASEQ_EXT_STRAND>(a, ntiles, s); break;
     case PSS_TLEN: e = launch_tilet_one<PSS_TLEN>(a, p.tlen, p.tile_redo, ntiles, s); break;
