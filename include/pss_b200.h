@@ -320,6 +320,18 @@ int pss_admit(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max
 int pss_overlap_tweak(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth,
                       uint8_t *qual_out, int32_t *pair_first, void *stream);
 
+/*
+ * The PAIRS of that rewrite for a whole batch, from the read metadata alone: pair_first[i] as above, for
+ * reads->n_reads reads, computed from pos / flag / cigar / name_prev (sequences and qualities are neither
+ * needed nor copied; seq4 / qual may point anywhere).  This is what lets a caller cut a request that reads
+ * base qualities into position pieces (the reference streams such a request through htslib's overlap hash,
+ * call site opt.pyx:1853; the hash keys on QNAMEs, so which reads pair depends on reads a piece does not
+ * hold): a piece passes name_prev[b] = a - first for every pair (a, b) whose reads both lie in the piece and
+ * -1 everywhere else, and pairs exactly as the whole batch does.  HOST pointers, synchronous.
+ */
+int pss_pairs_host(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth,
+                   int32_t *pair_first);
+
 /* ---- binned statistics ------------------------------------------------------------ */
 
 /*

@@ -90,6 +90,7 @@ SYMBOLS = {
                                          C.POINTER(_P), C.POINTER(_P), C.c_int64, C.c_int64]),
     'pss_admit': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P]),
     'pss_overlap_tweak': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P, _P, _P]),
+    'pss_pairs_host': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.c_int32, _P]),
     'pss_binned': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssBinnedParams), _P, _P]),
     'pss_binned_host': (C.c_int, [_P, C.POINTER(PssReads), C.POINTER(PssBinnedParams), _P]),
     'pss_binned_multi': (C.c_int, [_P, C.POINTER(PssReads), C.c_int32, C.POINTER(PssBinnedParams), C.POINTER(_P), _P]),
@@ -350,6 +351,14 @@ class Context(object):
     def overlap_tweak(self, reads_struct, stepper, max_depth, qual_out, pair_first=None, stream=None):
         self.check(self.lib.pss_overlap_tweak(self.h, C.byref(reads_struct), int(stepper), int(max_depth),
                                               _addr(qual_out), _addr(pair_first), stream))
+
+    def pairs_host(self, reads_struct, stepper, max_depth):
+        """pair_first (int32 per read: index of the earlier mate the read's qualities are rewritten against, or -1) of a
+        whole host batch from its metadata alone -- no sequences or qualities cross the bus (pss_pairs_host)."""
+        pair = np.full(int(reads_struct.n_reads), -1, dtype=np.int32)
+        step = STEPPERS[stepper] if isinstance(stepper, str) else int(stepper)
+        self.check(self.lib.pss_pairs_host(self.h, C.byref(reads_struct), step, int(max_depth or 0), _addr(pair)))
+        return pair
 
     def synchronize(self, stream=None):
         self.check(self.lib.pss_synchronize(self.h, stream))

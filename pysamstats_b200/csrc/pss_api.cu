@@ -844,6 +844,32 @@ extern "C" int pss_pileup_host_multi(pss_ctx *ctx, const pss_reads *reads, int32
     return rc;
 }
 
+// The pairs of the mate-overlap rewrite for a whole batch from its read metadata alone (no sequences, no qualities):
+// what lets a caller cut a request that reads base qualities into position pieces -- see include/pss_b200.h.
+extern "C" int pss_pairs_host(pss_ctx *ctx, const pss_reads *reads, int32_t stepper, int32_t max_depth, int32_t *pair_first) {
+    if (!ctx) return PSS_EINVAL;
+    int rc;
+    if ((rc = check_reads(ctx, reads, false)) != PSS_OK) return rc;
+    if (stepper < 0 || stepper > 2) return fail(ctx, PSS_EINVAL, "unknown stepper: %d", stepper);
+    if (max_depth < 0) return fail(ctx, PSS_EINVAL, "max_depth < 0");
+    const int64_t n = reads->n_reads;
+    if (n == 0) return PSS_OK;
+    if (!reads->name_prev || !pair_first) return fail(ctx, PSS_EINVAL, "name_prev / pair_first is NULL");
+    CU(cudaSetDevice(ctx->device));
+    ctx->prepared = false;
+    cudaStream_t s = nullptr;
+    pss_reads D;
+    if ((rc = upload_reads(ctx, reads, &D, false, false, s)) != PSS_OK) return rc;
+    if ((rc = to_device(ctx, ctx->hb[12], reads->name_prev, (size_t)n, &D.name_prev, s)) != PSS_OK) return rc;
+    if ((rc = prepare_batch(ctx, &D, stepper, max_depth, 0, 0, false, nullptr, nullptr, s)) != PSS_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pair, sizeof(int32_t) * (size_t)n)) != PSS_OK) return rc;
+    if ((rc = ensure(ctx, ctx->next, sizeof(int32_t) * (size_t)n)) != PSS_OK) return rc;
+    CU(launch_overlap(D, (const RInfo *)ctx->ri.p, nullptr, (int32_t *)ctx->pair.p, (int32_t *)ctx->next.p, s, &ctx->launches));
+    CU(cudaMemcpyAsync(pair_first, ctx->pair.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += (int64_t)(sizeof(int32_t) * (size_t)n);
+    return pss_synchronize(ctx, s);
+}
+
 // ---------------------------------------------------------------------- pileup rows (host)
 
 // One statistic as packed records: the narrow pipeline with a row sink; statistics without narrow output (the

@@ -590,8 +590,10 @@ cudaError_t launch_overlap(const pss_reads &R, const RInfo *ri, uint8_t *qual_wo
     LAUNCHED();
     k_pair<<<grid, 256, 0, s>>>(ri, R.name_prev, name_next, n, pair_first);
     LAUNCHED();
-    k_tweak<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ri, R.cigar, R.seq4, R.qual_off, pair_first, n, qual_work);
-    LAUNCHED();
+    if (qual_work) {     // NULL: the pairs only (pss_pairs_host)
+        k_tweak<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ri, R.cigar, R.seq4, R.qual_off, pair_first, n, qual_work);
+        LAUNCHED();
+    }
     return cudaGetLastError();
 }
 

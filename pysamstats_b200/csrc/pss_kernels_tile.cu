@@ -29,6 +29,8 @@
 // Shared-memory atomics are few (a handful per read), so the kernel is bound by the output
 // stream to HBM.
 #include "pss_internal.cuh"
+#include "pss_imax.cuh"
+#include "pss_lowq.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -807,11 +809,12 @@ __device__ void noseq_minq_read(const TileCtx &T, const TileArgs &A, const RInfo
     }
 }
 
-// ---- in-place inclusive prefix sum of one TT-word array by one warp --------------------------
-// lane l owns words [128 k + 4 l, 128 k + 4 l + 4) for k = 0 .. TT/128-1 (conflict-free 128-bit
+// ---- in-place inclusive prefix sum of one N-word array (TT by default) by one warp -----------
+// lane l owns words [128 k + 4 l, 128 k + 4 l + 4) for k = 0 .. N/128-1 (conflict-free 128-bit
 // accesses).
+template <int N = TT>
 __device__ __forceinline__ void warp_scan_array(uint32_t *arr, int lane) {
-    const int NK = TT / 128;
+    const int NK = N / 128;
     uint4 v[NK];
     uint32_t s[NK];
 #pragma unroll
@@ -1823,6 +1826,346 @@ k_tileq(TileArgs A) {
     }
 }
 
+// ------------------------------------------------------------------ mapq, mapq_strand: k_tilem
+//
+// Mapq / MapqStrand (opt.pyx:912-1100) for ANY min_baseq / no_del.  Everything MapqHelper keeps is constant along the
+// intervals in which a read contributes events -- the whole read (M, D and N spans alike), its aligned spans only
+// under no_del, the runs of bases at or above the threshold under min_baseq -- so n, nz and sum(mapq^2) are interval
+// adds as in the coverage kinds, and max(mapq) is an interval MAXIMUM: at most four shared-memory atomic maxima per
+// interval into the block structure of pss_imax.cuh, resolved once per tile.  No per-position gather is left
+// (k_tileq<KIND_MAPQ> walked every read once per 128-position window it reaches: 21 thousand warp instructions per
+// tile for mapq_strand, about two thirds of them in the gather).
+//
+// Counters (bank = rev | pp << 1), words of shared memory:
+//   a tile with at most 65535 candidate reads ("shallow": every tile of ordinary sequencing depth)
+//       [bank][TT]      n | nz << 16   -- neither half can exceed the candidate count
+//       [4 + bank][TT]  sum(mapq^2)    -- <= 65535 * 255^2 < 2^32
+//   a deeper tile: the same 8 TT words hold SIXTEEN arrays of TT / 2 positions (n, nz, the low byte plane and the high
+//       plane of sum(mapq^2), 32-bit each, as k_tileq kept them) and the tile is done in two sweeps over its reads,
+//       one per half of its positions -- root mean squares are not additive over passes of reads, but the positions
+//       of a tile are independent of each other;
+//   sfx / pfx / pt [bank][TT], tab [level][bank][32]: the interval maxima, always over the whole tile (first sweep).
+#define MQ_CH 160                      // reads staged per chunk (a 512-position tile of 30x / 150 bp has ~135 candidates)
+#define MQ_NT 256
+#ifndef MQ_CTAS
+#define MQ_CTAS 4
+#endif
+#define MQ_NB (TT / IMAX_BLK)          // blocks per tile: one lane each in the resolution
+#define MQ_NLEV 6                      // table levels 0 .. log2(MQ_NB)
+static_assert(MQ_NB == 32 && imax_levels(MQ_NB) == MQ_NLEV, "one warp resolves a bank: 32 blocks of 16 positions");
+#define MQ_WORDS (20 * TT + MQ_NLEV * 4 * MQ_NB)      // cnt 8 TT | sfx 4 TT | pfx 4 TT | pt 4 TT | tab
+
+struct AtomicMaxOp {
+    __device__ __forceinline__ void operator()(uint32_t *p, uint32_t v) const { atomicMax(p, v); }
+};
+__device__ __forceinline__ uint4 max4(uint4 a, uint4 b) { return make_uint4(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z), max(a.w, b.w)); }
+
+// Four positions of a bank's counters (cq = cnt + 4 quad; counter arrays are tw words apart): n, nz, and the root mean
+// square over the banks of MASK (CountPpStrand: all 0b1111, fwd 0b0101, rev 0b1010, pp 0b1100, pp_fwd 0b0100, pp_rev 0b1000).
+__device__ __forceinline__ uint4 mq_ldn(const uint32_t *cq, int b, int tw, bool deep) {
+    const uint4 w = *reinterpret_cast<const uint4 *>(cq + b * tw);
+    return deep ? w : lo16(w);
+}
+__device__ __forceinline__ uint4 mq_ldz(const uint32_t *cq, int b, int tw, bool deep) {
+    return deep ? *reinterpret_cast<const uint4 *>(cq + (4 + b) * tw) : hi16(*reinterpret_cast<const uint4 *>(cq + b * tw));
+}
+template <int MASK>
+__device__ __forceinline__ uint4 mq_rms(const uint32_t *cq, int tw, bool deep) {
+    uint4 n = make_uint4(0, 0, 0, 0);
+    unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (!((MASK >> b) & 1)) continue;
+        n = n + mq_ldn(cq, b, tw, deep);
+        const uint4 l = *reinterpret_cast<const uint4 *>(cq + ((deep ? 8 : 4) + b) * tw);
+        s0 += l.x; s1 += l.y; s2 += l.z; s3 += l.w;
+        if (deep) {
+            const uint4 h = *reinterpret_cast<const uint4 *>(cq + (12 + b) * tw);
+            s0 += (unsigned long long)h.x << 8; s1 += (unsigned long long)h.y << 8;
+            s2 += (unsigned long long)h.z << 8; s3 += (unsigned long long)h.w << 8;
+        }
+    }
+    return make_uint4((uint32_t)q_rootmean(s0, n.x), (uint32_t)q_rootmean(s1, n.y), (uint32_t)q_rootmean(s2, n.z),
+                      (uint32_t)q_rootmean(s3, n.w));
+}
+
+template <int STAT, bool MINQ>
+__global__ void __launch_bounds__(MQ_NT, MQ_CTAS)
+k_tilem(TileArgs A) {
+    constexpr bool STRAND = STAT == PSS_MAPQ_STRAND;
+    constexpr int NWARPS = MQ_NT / 32;
+    static_assert(MQ_NT >= MQ_CH && NWARPS == 8, "one scatter thread per staged read; eight warps share the scans");
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *sfx = cnt + 8 * TT, *pfx = cnt + 12 * TT, *pt = cnt + 16 * TT, *tab = cnt + 20 * TT;
+    uint32_t *raw = cnt + MQ_WORDS;                                          // exists only when need_raw
+    RInfo *s_ri = reinterpret_cast<RInfo *>(raw + (A.need_raw ? TT : 0));
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_n;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int64_t t0l = A.start + (int64_t)tile * TT;
+    const int t0 = (int)t0l;
+    int dx, dy;
+    {
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile));
+        dx = (int)d0.x; dy = (int)d0.y;
+    }
+    const bool deep = dy - dx > 65535;
+    const int tw = deep ? TT / 2 : TT;                   // positions per sweep = length of a counter array
+    auto issue = [&](int cb) {
+        const int n = min(MQ_CH, dy - cb);
+        s_n = n;
+        fence_proxy_async();
+        if (n > 0) {
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)n * (uint32_t)sizeof(RInfo));
+            bulk_g2s(s_ri, A.ri + cb, (uint32_t)n * (uint32_t)sizeof(RInfo), &s_bar);
+        } else mbar_arrive_expect_tx(&s_bar, 0);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        issue(dx);
+    }
+#if TPREFETCH > 0
+    if (tid == MQ_NT - 32 && tile + TPREFETCH < (int)gridDim.x) {      // a later tile's records into L2, as in k_tile
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile + TPREFETCH));
+        const int px = (int)p0.x, pn = min(MQ_CH, (int)p0.y - px);
+        if (pn > 0) bulk_prefetch_l2(A.ri + px, (uint32_t)pn * (uint32_t)sizeof(RInfo));
+    }
+#endif
+    {   // zero the counters, the maxima (+ raw)
+        const int nw4 = (MQ_WORDS + (A.need_raw ? TT : 0)) / 4;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < nw4; k += MQ_NT) reinterpret_cast<uint4 *>(cnt)[k] = z;
+    }
+    uint32_t *rawp = A.need_raw ? raw : nullptr;
+    __syncthreads();           // barrier initialised, counters zeroed
+
+    uint32_t parity = 0;
+    for (int sweep = 0;; ++sweep) {
+        const int h0 = t0 + sweep * tw;                  // this sweep counts the positions [h0, h0 + tw)
+        for (int cb = dx; cb < dy;) {
+            mbar_wait(&s_bar, parity);
+            parity ^= 1;
+            const int n = s_n;
+            if (n == 0) break;
+            if (tid < n) {
+                const RInfo r = s_ri[tid];
+                const uint32_t cls = r.cls;
+                if (cls & CLS_ADMITTED) {
+                    if (MINQ && (cls & CLS_COUNTED) && (cls & CLS_HASSEQ)) lowq_prefetch(A, r, cb + tid);
+                    if (rawp) {
+                        const int a = max(r.pos - h0, 0), b = min(r.end - h0, tw);
+                        if (a < b) { atomicAdd(rawp + a, 1u); if (b < tw) atomicAdd(rawp + b, 0u - 1u); }
+                    }
+                    if (cls & CLS_COUNTED) {
+                        const int bank = cls & 3u;
+                        const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u, sq = q * q;
+                        // the read has an event at every position of the reference interval [x, x + l)
+                        auto emit = [&](int x, int l) {
+                            const int a = max(x - h0, 0), b = min(x + l - h0, tw);
+                            if (a < b) {
+                                uint32_t *p = cnt + bank * tw;
+                                if (!deep) {
+                                    const uint32_t inc = q ? 1u : 0x10001u;              // n | nz << 16
+                                    atomicAdd(p + a, inc);
+                                    if (b < tw) atomicAdd(p + b, 0u - inc);
+                                    if (q) {
+                                        p += 4 * tw;
+                                        atomicAdd(p + a, sq);
+                                        if (b < tw) atomicAdd(p + b, 0u - sq);
+                                    }
+                                } else {
+                                    atomicAdd(p + a, 1u);
+                                    if (b < tw) atomicAdd(p + b, 0u - 1u);
+                                    if (!q) {
+                                        p += 4 * tw;
+                                        atomicAdd(p + a, 1u);
+                                        if (b < tw) atomicAdd(p + b, 0u - 1u);
+                                    } else {
+                                        const uint32_t lo = sq & 255u, hi = sq >> 8;
+                                        if (lo) { uint32_t *pl = p + 8 * tw; atomicAdd(pl + a, lo); if (b < tw) atomicAdd(pl + b, 0u - lo); }
+                                        if (hi) { uint32_t *ph = p + 12 * tw; atomicAdd(ph + a, hi); if (b < tw) atomicAdd(ph + b, 0u - hi); }
+                                    }
+                                }
+                            }
+                            if (sweep == 0 && q) {
+                                const int a2 = max(x - t0, 0), b2 = min(x + l - t0, TT);
+                                if (a2 < b2)
+                                    imax_update(a2, b2, q, sfx + bank * TT, pfx + bank * TT, pt + bank * TT, tab + bank * MQ_NB,
+                                                4 * MQ_NB, AtomicMaxOp());
+                            }
+                        };
+                        if (!MINQ && !A.no_del) emit(r.pos, r.end - r.pos);              // M, D and N spans all count (opt.pyx:1904-1906)
+                        else if (cls & CLS_NOREF) { if (!A.no_del) emit(r.pos, 1); }     // one deletion-like event at pos
+                        else if (!MINQ && (cls & CLS_SIMPLE)) emit(r.pos, r.end - r.pos);
+                        else {
+                            // no_del: the aligned spans only; min_baseq: of those, the runs of bases at or above the threshold
+                            // (a read without sequence has quality 0 everywhere: only its deletion / ref-skip events remain)
+                            const bool bases = !MINQ || (cls & CLS_HASSEQ);
+                            const uint32_t *mw = MINQ ? A.lowq + (r.seq_off >> 4) + (cb + tid) : nullptr;
+                            const uint32_t *cg = A.cigar + r.cigar_off;
+                            const int nc = (int)r.n_cigar;
+                            int x = r.pos, y = 0;
+                            for (int k = 0; k < nc && x < t0 + TT; ++k) {
+                                const uint32_t w = __ldg(cg + k);
+                                const int op = w & 15, l = (int)(w >> 4);
+                                if (op_is_match(op)) {
+                                    if (bases && x + l > t0) {
+                                        if (MINQ) lowq_gaps(mw, x, l, y, t0, TT, [&](int p, int len) { emit(t0 + p, len); });
+                                        else emit(x, l);
+                                    }
+                                    x += l; y += l;
+                                } else if (op == OP_D || op == OP_N) {
+                                    if (!A.no_del && x + l > t0) emit(x, l);
+                                    x += l;
+                                } else if (op == OP_I || op == OP_S) y += l;
+                            }
+                        }
+                    }
+                }
+            }
+            cb += n;
+            if (cb >= dy) break;
+            __syncthreads();                       // staging buffer free again
+            if (tid == 0) issue(cb);
+        }
+        __syncthreads();
+        // ---- the maxima (first sweep): warp b resolves bank b, lane = block ----------------------------------
+        if (sweep == 0 && warp < 4) {
+            uint32_t v[MQ_NLEV];
+#pragma unroll
+            for (int k = 0; k < MQ_NLEV; ++k) v[k] = tab[(k * 4 + warp) * MQ_NB + lane];
+#pragma unroll
+            for (int k = MQ_NLEV - 1; k >= 1; --k) {       // push-down (imax_pushdown_ref with one lane per block)
+                const int h = 1 << (k - 1);
+                const uint32_t up = __shfl_up_sync(FULL, v[k], h);
+                uint32_t m = max(v[k - 1], v[k]);
+                if (lane >= h) m = max(m, up);
+                v[k - 1] = m;
+            }
+            const uint32_t body = v[0];
+            // imax_resolve_block on the block's 16 positions, 128-bit accesses
+            const uint4 *sp = reinterpret_cast<const uint4 *>(sfx + warp * TT + IMAX_BLK * lane);
+            const uint4 *pp = reinterpret_cast<const uint4 *>(pfx + warp * TT + IMAX_BLK * lane);
+            uint4 *tp = reinterpret_cast<uint4 *>(pt + warp * TT + IMAX_BLK * lane);
+            uint32_t s[IMAX_BLK];
+            uint32_t run = 0;
+#pragma unroll
+            for (int j = 0; j < IMAX_BLK / 4; ++j) {
+                const uint4 f = sp[j];
+                run = max(run, f.x); s[4 * j] = run;
+                run = max(run, f.y); s[4 * j + 1] = run;
+                run = max(run, f.z); s[4 * j + 2] = run;
+                run = max(run, f.w); s[4 * j + 3] = run;
+            }
+            run = 0;
+#pragma unroll
+            for (int j = IMAX_BLK / 4 - 1; j >= 0; --j) {
+                const uint4 f = pp[j];
+                uint4 t = tp[j];
+                run = max(run, f.w); t.w = max(max(t.w, body), max(s[4 * j + 3], run));
+                run = max(run, f.z); t.z = max(max(t.z, body), max(s[4 * j + 2], run));
+                run = max(run, f.y); t.y = max(max(t.y, body), max(s[4 * j + 1], run));
+                run = max(run, f.x); t.x = max(max(t.x, body), max(s[4 * j], run));
+                tp[j] = t;
+            }
+        }
+        {   // prefix sums of the difference arrays (+ raw); warps 4-7 first: 0-3 have the maxima too
+            const int nsc = deep ? 16 : 8;
+            for (int a = (warp + 4) & 7; a < nsc + (A.need_raw ? 1 : 0); a += NWARPS) {
+                uint32_t *arr = a < nsc ? cnt + a * tw : raw;
+                if (deep) warp_scan_array<TT / 2>(arr, lane);
+                else warp_scan_array<TT>(arr, lane);
+            }
+        }
+        __syncthreads();
+        // ---- rec(): (group of fields, quad of positions) tasks, 128-bit stores -------------------------------
+        {
+            const int64_t h0l = t0l + (int64_t)sweep * tw;
+            const int qshift = deep ? 6 : 7, nquad = 1 << qshift;                  // tw / 4 quads: a warp holds one group
+            const bool aligned = ((reinterpret_cast<uintptr_t>(A.out) & 15) == 0) && ((A.stride & 3) == 0) &&
+                                 (((h0l - A.start) & 3) == 0);
+            // groups of fields, in the order the tasks are dealt (the root mean squares first: they are the long tasks)
+            //   strand: rms[0..2] | rms[3..5] | n[0..5] | nz[0..5] | max[0..5]      else: (rms, max) | (n, nz)
+            constexpr int NG = STRAND ? 5 : 2;
+#pragma unroll 1
+            for (int task = tid; task < NG * nquad; task += MQ_NT) {
+                const int g = task >> qshift, qd = task & (nquad - 1);
+                const int64_t pl = h0l + 4 * qd;
+                const int64_t rem = A.end - pl;
+                if (rem <= 0) continue;
+                QuadOut<OUT_STORE> O;
+                O.p = A.out + (pl - A.start);
+                O.stride = A.stride;
+                O.seen = 0;
+                O.nvalid = rem > 4 ? 4 : (int)rem;
+                O.vec = aligned && (O.nvalid == 4 || (pl - A.start) + 4 <= A.stride);
+                const uint32_t *cq = cnt + 4 * qd;
+                if (STRAND ? g < 2 : g == 0) {
+                    // CountPpStrand order: all, fwd, rev, pp, pp_fwd, pp_rev = banks 0123, 02, 13, 23, 2, 3
+                    if (STRAND) {
+                        O.skip(12 + 3 * g);
+                        if (g == 0) { O.put(mq_rms<15>(cq, tw, deep)); O.put(mq_rms<5>(cq, tw, deep)); O.put(mq_rms<10>(cq, tw, deep)); }
+                        else { O.put(mq_rms<12>(cq, tw, deep)); O.put(mq_rms<4>(cq, tw, deep)); O.put(mq_rms<8>(cq, tw, deep)); }
+                    } else {
+                        O.skip(4);
+                        O.put(mq_rms<15>(cq, tw, deep)); O.put(mq_rms<12>(cq, tw, deep));
+                        const uint4 *mp = reinterpret_cast<const uint4 *>(pt + sweep * tw + 4 * qd);
+                        const uint4 m_pp = max4(mp[2 * TT / 4], mp[3 * TT / 4]);
+                        O.put(max4(max4(mp[0], mp[TT / 4]), m_pp));
+                        O.put(m_pp);
+                    }
+                } else if (STRAND && g == 4) {
+                    O.skip(18);
+                    const uint4 *mp = reinterpret_cast<const uint4 *>(pt + sweep * tw + 4 * qd);
+                    const uint4 m0 = mp[0], m1 = mp[TT / 4], m2 = mp[2 * TT / 4], m3 = mp[3 * TT / 4];
+                    const uint4 m_pp = max4(m2, m3);
+                    O.put(max4(max4(m0, m1), m_pp)); O.put(max4(m0, m2)); O.put(max4(m1, m3)); O.put(m_pp); O.put(m2); O.put(m3);
+                } else {
+                    // the counts: n (and the row mask), nz
+                    const bool zs = STRAND && g == 3;            // this task writes the mapq == 0 counts
+                    uint4 c[4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) c[b] = zs ? mq_ldz(cq, b, tw, deep) : mq_ldn(cq, b, tw, deep);
+                    const uint4 c_all = (c[0] + c[1]) + (c[2] + c[3]);
+                    if (STRAND) {
+                        if (zs) O.skip(6);
+                        O.put(c_all); O.put(c[0] + c[2]); O.put(c[1] + c[3]); O.put(c[2] + c[3]); O.put(c[2]); O.put(c[3]);
+                    } else {
+                        O.put(c_all); O.put(c[2] + c[3]);
+                        const uint4 z2 = mq_ldz(cq, 2, tw, deep), z3 = mq_ldz(cq, 3, tw, deep);
+                        O.put((mq_ldz(cq, 0, tw, deep) + mq_ldz(cq, 1, tw, deep)) + (z2 + z3)); O.put(z2 + z3);
+                    }
+                    if (!zs) {
+                        // the row mask: htslib emits a column wherever an admitted read has an event
+                        const uint4 all = A.need_raw ? *reinterpret_cast<const uint4 *>(raw + 4 * qd) : c_all;
+                        uint8_t *m = A.rowmask + (pl - A.start);
+                        if (O.nvalid == 4 && (reinterpret_cast<uintptr_t>(m) & 3) == 0) {
+                            *reinterpret_cast<uint32_t *>(m) = (all.x ? 1u : 0u) | (all.y ? 0x100u : 0u) | (all.z ? 0x10000u : 0u) | (all.w ? 0x1000000u : 0u);
+                        } else {
+                            if (O.nvalid > 0) m[0] = all.x ? 1 : 0;
+                            if (O.nvalid > 1) m[1] = all.y ? 1 : 0;
+                            if (O.nvalid > 2) m[2] = all.z ? 1 : 0;
+                            if (O.nvalid > 3) m[3] = all.w ? 1 : 0;
+                        }
+                    }
+                }
+            }
+        }
+        if (!deep || sweep == 1) break;
+        __syncthreads();           // everyone is done with the counters of the first half
+        {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int k = tid; k < 8 * TT / 4; k += MQ_NT) reinterpret_cast<uint4 *>(cnt)[k] = z;
+            if (A.need_raw) for (int k = tid; k < TT / 4; k += MQ_NT) reinterpret_cast<uint4 *>(raw)[k] = z;
+        }
+        if (tid == 0) issue(dx);
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ tlen, tlen_strand
 //
 // TlenHelper (opt.pyx:679-727) keeps, per class, n, sum(tlen), sum(tlen^2) -- constant along a read, so pure
@@ -2000,7 +2343,31 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ tile
                             }
                         }
                     };
-                    if (!minq) contrib(r.pos, len, false);
+                    if (A.no_del) {
+                        // deletion-like events are dropped (opt.pyx:1904-1906): the aligned spans only, and under min_baseq
+                        // the runs of bases at or above the threshold in them (none for a read without sequence)
+                        if (!(cls & CLS_NOREF) && (!minq || (cls & CLS_HASSEQ))) {
+                            if (minq) lowq_prefetch(A, r, cb + tid);
+                            if (!minq && (cls & CLS_SIMPLE)) contrib(r.pos, len, false);
+                            else {
+                                const uint32_t *mw = minq ? A.lowq + (r.seq_off >> 4) + (cb + tid) : nullptr;
+                                const uint32_t *cg = A.cigar + r.cigar_off;
+                                int x = r.pos, y = 0;
+                                for (int k = 0; k < (int)r.n_cigar && x < t0 + TT; ++k) {
+                                    const uint32_t w = __ldg(cg + k);
+                                    const int op = w & 15, l = (int)(w >> 4);
+                                    if (op_is_match(op)) {
+                                        if (x + l > t0) {
+                                            if (minq) lowq_gaps(mw, x, l, y, t0, TT, [&](int p, int run) { contrib(t0 + p, run, false); });
+                                            else contrib(x, l, false);
+                                        }
+                                        x += l; y += l;
+                                    } else if (op == OP_D || op == OP_N) x += l;
+                                    else if (op == OP_I || op == OP_S) y += l;
+                                }
+                            }
+                        }
+                    } else if (!minq) contrib(r.pos, len, false);
                     else if (!(cls & CLS_HASSEQ)) {
                         // min_baseq > 0, no sequence: quality 0 at every base -- only the deletion / ref-skip events remain
                         if (cls & CLS_NOREF) contrib(r.pos, 1, false);
@@ -2246,6 +2613,25 @@ static cudaError_t launch_tileq_one(const TileArgs &a, int64_t ntiles, cudaStrea
     return cudaGetLastError();
 }
 
+template <int STAT>
+static cudaError_t launch_tilem_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
+    const size_t smem_max = (size_t)(MQ_WORDS + TT) * 4 + (size_t)MQ_CH * sizeof(RInfo);
+    static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
+    int dev__ = 0;
+    cudaGetDevice(&dev__);
+    bool &configured = configured_dev[dev__ & 63];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_tilem<STAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tilem<STAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const size_t smem = smem_max - (a.need_raw ? 0 : (size_t)TT * 4);
+    if (a.lowq) k_tilem<STAT, true><<<(unsigned)ntiles, MQ_NT, smem, s>>>(a);
+    else k_tilem<STAT, false><<<(unsigned)ntiles, MQ_NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 // statistics whose counts come back through the narrow (8- / 16-bit) host transport
 bool tile_kernel_counting(int stat) {
     switch (stat) {
@@ -2277,12 +2663,18 @@ static cudaError_t launch_tilet_one(const TileArgs &a, const int32_t *tlen, int3
 bool tile_kernel_supports(int stat, int min_baseq, int no_del) {
     if (tile_kernel_counting(stat)) return true;      // min_baseq > 0: the bases below it are taken back out (k_lowq)
     switch (stat) {
-    case PSS_TLEN: case PSS_TLEN_STRAND: return !no_del;     // intervals are whole reads: deletions need the CIGAR (min_baseq: k_lowq marks)
-    case PSS_MAPQ: case PSS_MAPQ_STRAND: return !no_del && min_baseq <= 0;   // the max needs every event's CIGAR / quality then: generic kernel
+    case PSS_TLEN: case PSS_TLEN_STRAND: return true;        // intervals of events: whole reads, aligned spans under no_del, kept runs under min_baseq
+    case PSS_MAPQ: case PSS_MAPQ_STRAND: return true;        // k_tilem: intervals of events, whatever the filters
     case PSS_BASEQ: case PSS_BASEQ_STRAND: return true;      // min_baseq: k_lowq marks for the counts, the threshold in the gather
     case PSS_BASEQ_EXT: case PSS_BASEQ_EXT_STRAND: return min_baseq <= 0;
     default: return false;
     }
+}
+
+// PSS_MAPQ_GATHER=1: the round-1 position-owned gather (k_tileq<KIND_MAPQ>) where it applies, for A / B timing
+static bool mapq_gather(const TileArgs &a) {
+    static const bool want = getenv("PSS_MAPQ_GATHER") != nullptr;
+    return want && !a.lowq && !a.no_del;
 }
 
 size_t tile_desc_bytes(int64_t ntiles) { return sizeof(TileDesc) * (size_t)ntiles; }
@@ -2351,8 +2743,12 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     case PSS_COVERAGE_EXT_STRAND: e = launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT_STRAND>(a, ntiles, s); break;
     case PSS_VARIATION: e = launch_tile_one<KIND_VAR1, PSS_VARIATION>(a, ntiles, s); break;
     case PSS_VARIATION_STRAND: e = launch_tile_one<KIND_VAR, PSS_VARIATION_STRAND>(a, ntiles, s); break;
-    case PSS_MAPQ: e = launch_tileq_one<KIND_MAPQ, PSS_MAPQ>(a, ntiles, s); break;
-    case PSS_MAPQ_STRAND: e = launch_tileq_one<KIND_MAPQ, PSS_MAPQ_STRAND>(a, ntiles, s); break;
+    case PSS_MAPQ:
+        e = mapq_gather(a) ? launch_tileq_one<KIND_MAPQ, PSS_MAPQ>(a, ntiles, s) : launch_tilem_one<PSS_MAPQ>(a, ntiles, s);
+        break;
+    case PSS_MAPQ_STRAND:
+        e = mapq_gather(a) ? launch_tileq_one<KIND_MAPQ, PSS_MAPQ_STRAND>(a, ntiles, s) : launch_tilem_one<PSS_MAPQ_STRAND>(a, ntiles, s);
+        break;
     case PSS_BASEQ: e = a.lowq ? launch_tileq_one<KIND_BQ, PSS_BASEQ, true>(a, ntiles, s) : launch_tileq_one<KIND_BQ, PSS_BASEQ>(a, ntiles, s); break;
     case PSS_BASEQ_STRAND: e = a.lowq ? launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND, true>(a, ntiles, s)
                                       : launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND>(a, ntiles, s); break;

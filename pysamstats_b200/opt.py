@@ -260,7 +260,7 @@ def _pileup_plan(stat, alignmentfile, fafile, pad, chrom, start, end, one_based,
         if hi - lo <= 0:
             continue
         refseq, pkw = reference()
-        yield c, s, e, lo, hi, _position_chunks(batch, lo, hi, need_qual, max_depth), refseq, pkw, need_qual
+        yield c, s, e, lo, hi, _position_chunks(batch, lo, hi, need_qual, max_depth, stepper), refseq, pkw, need_qual
 
 
 def pileup_tables(stat, alignmentfile, fafile=None, pad=False, chrom=None, start=None, end=None,
@@ -420,20 +420,37 @@ def _run_pieces(fn, pieces, default_device):
             yield pending.popleft().result()
 
 
-def _position_chunks(batch, lo, hi, need_qual, max_depth):
+def _pair_links(batch, stepper, max_depth):
+    """``pair_first`` of the whole batch (``pss_pairs_host``): for every read the index of the earlier mate its base
+    qualities are rewritten against (htslib's overlap hash under pysam's ``ignore_overlaps=True``, call site
+    ``opt.pyx:1853``), -1 for the rest -- from the read metadata alone.  Cached per batch."""
+    key = ('pairs', stepper, max_depth or 8000)
+    if key not in batch.cache:
+        ctx = _cabi.get_context()
+        batch.cache[key] = ctx.pairs_host(_reads_struct(batch, True), stepper, max_depth)
+    return batch.cache[key]
+
+
+def _position_chunks(batch, lo, hi, need_qual, max_depth, stepper='all', pair_links=None):
     """Cut the positions [lo, hi) of one contig batch into pieces of PSS_TABLE_CHUNK (default 16 Mi) positions,
     each with the sub-batch of reads that overlap it (a zero-copy view: the reads are start sorted), so a whole
-    chromosome streams through bounded host memory.  Yields (c_lo, c_hi, struct pss_reads).
+    chromosome streams through bounded device (and result) memory.  Yields (c_lo, c_hi, struct pss_reads).
 
     The ``max_depth`` admission rule is order dependent: a read before a cut can only be refused because of
     earlier reads the next piece would not see.  So the range is only cut when no read of the batch can be
-    refused at all (fewer than ``max_depth`` reads start within one maximal read span of any read)."""
+    refused at all (fewer than ``max_depth`` reads start within one maximal read span of any read).
+
+    Requests that read base qualities: the mate-overlap rewrite pairs reads through a QNAME-keyed table, so which
+    reads pair depends on every earlier read of the name -- a piece that misses the first read of a three-read chain
+    would pair the other two.  The pairs are therefore computed ONCE for the whole batch from its metadata
+    (``_pair_links``; ``pair_links`` replaces that call in tests without a GPU) and handed to every piece as its
+    ``name_prev`` links: ``name_prev[b] = a`` for a pair (a, b) inside the piece, -1 everywhere else -- chains of
+    at most two reads, which the engine pairs exactly as the whole batch did.  A pair with only one read in the
+    piece rewrites qualities at positions both reads cover, i.e. outside the piece."""
     from . import shard
     n = batch.n_reads
     chunk = _table_chunk()
-    # requests that read base qualities are not cut either: the mate-overlap rewrite pairs consecutive reads of a
-    # QNAME, and a piece that misses an earlier read of a three-read chain would pair the rest differently
-    if hi - lo <= chunk or n == 0 or need_qual:
+    if hi - lo <= chunk or n == 0:
         yield lo, hi, _reads_struct(batch, need_qual)
         return
     # read i has max_depth - 1 earlier reads within maxspan of its start iff pos[i] - pos[i - (max_depth - 1)] <=
@@ -443,6 +460,9 @@ def _position_chunks(batch, lo, hi, need_qual, max_depth):
         yield lo, hi, _reads_struct(batch, need_qual)
         return
     batch.padded()
+    links = None
+    if need_qual:
+        links = (pair_links or _pair_links)(batch, stepper, max_depth)
     for c_lo in range(lo, hi, chunk):
         c_hi = min(hi, c_lo + chunk)
         i0, i1, _ = shard.halo_range(batch.pos, batch.endpos, c_lo, c_hi, maxspan=maxspan, mask=False)
@@ -450,8 +470,17 @@ def _position_chunks(batch, lo, hi, need_qual, max_depth):
         for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'seq_off'):
             d[k] = getattr(batch, k)[i0:]
         d['cigar'], d['seq4'] = batch.cigar, batch.seq4
-        d['qual'] = d['qual_off'] = d['name_prev'] = None
-        yield c_lo, c_hi, _cabi.make_reads_struct(d, n_reads=i1 - i0)
+        keep = None
+        if need_qual:
+            keep = links[i0:i1]
+            keep = np.where(keep >= i0, keep - i0, -1).astype(np.int32)      # the piece's own indices
+            d['qual'], d['qual_off'], d['name_prev'] = batch.qual, batch.qual_off[i0:], keep
+            d['n_qual_bytes'] = int(batch.qual_off[i1] - batch.qual_off[i0])
+        else:
+            d['qual'] = d['qual_off'] = d['name_prev'] = None
+        r = _cabi.make_reads_struct(d, n_reads=i1 - i0)
+        r._keep = (batch, keep)     # the struct holds raw addresses
+        yield c_lo, c_hi, r
 
 
 _ITER_BLOCK = 1 << 16

@@ -14,6 +14,7 @@ ap.add_argument('--generic', action='store_true')
 ap.add_argument('--only', default='')
 ap.add_argument('--min-baseq', type=int, default=0)
 ap.add_argument('--no-dup', action='store_true')
+ap.add_argument('--no-del', action='store_true')
 args = ap.parse_args()
 dev = torch.device('cuda', 0)
 L = int(args.mb * 1e6) // 512 * 512
@@ -33,7 +34,8 @@ for stat in config.pileup_types:
     need_qual = stat.startswith('baseq') or args.min_baseq > 0
     p = ctx.pileup_params(stat, start=0, end=L, ref=ref if withref else None, ref_start=ref_lo,
                           ref_len=int(ref.numel()) if withref else 0, contig_len=L,
-                          flags=_cabi.PSS_FLAG_GENERIC_KERNEL if args.generic else 0, min_baseq=args.min_baseq, no_dup=args.no_dup)
+                          flags=_cabi.PSS_FLAG_GENERIC_KERNEL if args.generic else 0, min_baseq=args.min_baseq, no_dup=args.no_dup,
+                          no_del=args.no_del)
     ctx.prepare(rs, with_qual=need_qual, no_dup=args.no_dup, stream=s)
     for _ in range(int(os.environ.get('SWEEP_WARMUP', 2))):
         ctx.pileup_prepared(p, out, mask, stream=s)

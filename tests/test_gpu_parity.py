@@ -286,7 +286,12 @@ def test_chunked_tables_equal_single_call(monkeypatch):
     cases = (('variation_strand', dict()), ('coverage_ext', dict(chrom='Pf3D7_02_v3', start=1000, end=40000, pad=True)),
              ('coverage', dict(chrom='Pf3D7_01_v3', start=500, end=30000, truncate=True, one_based=True)),
              ('mapq_strand', dict(chrom='Pf3D7_03_v3')), ('tlen', dict(chrom='Pf3D7_01_v3', pad=True, start=0, end=50000)),
-             ('variation', dict(no_del=True, min_mapq=20)))
+             ('variation', dict(no_del=True, min_mapq=20)),
+             # requests that read base qualities are cut too: the pairs of the mate-overlap rewrite come from one
+             # pass over the contig's read metadata (pss_pairs_host), every piece gets them as its name chains
+             ('baseq_strand', dict(chrom='Pf3D7_01_v3')), ('baseq_ext_strand', dict()),
+             ('mapq', dict(chrom='Pf3D7_02_v3', min_baseq=17)), ('coverage_ext', dict(min_baseq=25, stepper='nofilter')),
+             ('tlen', dict(chrom='Pf3D7_03_v3', min_baseq=20, no_del=True)))
     expect = [_load(stat, 'test', **kw) for stat, kw in cases]
     monkeypatch.setenv('PSS_TABLE_CHUNK', '4096')
     for (stat, kw), e in zip(cases, expect):
@@ -309,7 +314,7 @@ def test_pieces_across_gpus(monkeypatch):
     cases = (('variation_strand', dict()), ('coverage_ext', dict(chrom='Pf3D7_02_v3', start=1000, end=40000, pad=True)),
              ('mapq', dict(chrom='Pf3D7_01_v3')), ('tlen_strand', dict(chrom='Pf3D7_03_v3')),
              ('coverage', dict(chrom='Pf3D7_01_v3', start=3, end=30000, pad=True, truncate=True)),
-             ('baseq_ext', dict(chrom='Pf3D7_01_v3')))                      # quality request: never cut
+             ('baseq_ext', dict(chrom='Pf3D7_01_v3')))                      # quality request: pieces with the contig's pairs
     expect = [_load(stat, 'test', **kw) for stat, kw in cases]
     monkeypatch.setenv('PSS_TABLE_CHUNK', '4096')
     monkeypatch.setenv('PSS_GPUS', _gpu_list())

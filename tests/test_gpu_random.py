@@ -161,6 +161,58 @@ def test_random_batches(stat, seed):
     check(ctx, nb, ref, reads, stat, 777, 1999)          # odd range inside the data
 
 
+def _read_batch(nb):
+    from pysamstats_b200 import bamio
+    b = bamio.ReadBatch()
+    for k in ('pos', 'flag', 'mapq', 'tlen', 'mtid', 'l_seq', 'cigar_off', 'cigar', 'seq_off', 'seq4', 'qual_off', 'qual'):
+        setattr(b, k, nb[k])
+    b.name_prev = nb['name_prev']
+    b.endpos = np.array([orc_endpos(nb, i) for i in range(nb['n_reads'])], dtype='i4')
+    b.tid, b.names = 0, None
+    return b
+
+
+@pytest.mark.parametrize('seed', [11, 12])
+def test_quality_requests_in_position_pieces(seed, monkeypatch):
+    # a request that reads base qualities is cut into position pieces: the pairs of the mate-overlap rewrite are
+    # computed once for the whole batch from its metadata (pss_pairs_host) and every piece receives them as
+    # two-read name chains in its own indices (opt._position_chunks) -- the pieces side by side must be the single
+    # call, and the pairs must be the ones the whole-batch rewrite forms (pss_overlap_tweak).  QNAMEs shared by two,
+    # three and more reads, arbitrary CIGARs / flags, dense enough that hundreds of mates overlap
+    import torch
+    from pysamstats_b200 import opt
+    ctx = _cabi.get_context()
+    nb, ref = random_batch(seed, n_reads=4000, span=6000, maxlen=70)
+    b = _read_batch(nb)
+    monkeypatch.setenv('PSS_TABLE_CHUNK', '1024')
+    lo, hi = 0, int(nb['pos'].max()) + 900
+    for stepper in ('all', 'nofilter'):
+        links = ctx.pairs_host(_cabi.make_reads_struct(nb), stepper, 8000)
+        dev = torch.device('cuda', ctx.device)
+        dn = {k: (torch.from_numpy(np.ascontiguousarray(v)).to(dev) if isinstance(v, np.ndarray) else v) for k, v in nb.items()}
+        qout = torch.empty(len(nb['qual']), dtype=torch.uint8, device=dev)
+        pf = torch.empty(nb['n_reads'], dtype=torch.int32, device=dev)
+        ctx.overlap_tweak(_cabi.make_reads_struct(dn), _cabi.STEPPERS[stepper], 8000, qout, pf)
+        ctx.synchronize()
+        assert np.array_equal(links, pf.cpu().numpy()) and (links >= 0).sum() > 50, stepper
+    for stat, kw in (('baseq_strand', dict()), ('baseq_ext', dict(stepper='nofilter')), ('mapq', dict(min_baseq=20)),
+                     ('tlen_strand', dict(min_baseq=13, no_del=True)), ('variation', dict(min_baseq=30)),
+                     ('baseq_ext_strand', dict(min_baseq=10, no_dup=True))):
+        whole, wmask = run(ctx, nb, ref, stat, lo, hi, **kw)
+        pieces = list(opt._position_chunks(b, lo, hi, True, 8000, kw.get('stepper', 'all')))
+        assert len(pieces) >= 6
+        withref = stat in config.stats_types_withref
+        for c_lo, c_hi, rs in pieces:
+            p = ctx.pileup_params(stat, start=c_lo, end=c_hi, ref=ref if withref else None, ref_start=0,
+                                  ref_len=len(ref) if withref else 0, contig_len=len(ref), **kw)
+            out = np.empty((whole.shape[0], c_hi - c_lo), dtype=np.int32)
+            mask = np.empty(c_hi - c_lo, dtype=np.uint8)
+            ctx.pileup_host(rs, p, out, mask)
+            assert np.array_equal(mask, wmask[c_lo - lo:c_hi - lo]), (stat, kw, c_lo)
+            rows = np.flatnonzero(mask)
+            assert np.array_equal(out[:, rows], whole[:, c_lo - lo:c_hi - lo][:, rows]), (stat, kw, c_lo)
+
+
 def test_random_binned():
     ctx = _cabi.get_context()
     for seed in (4, 5):

@@ -209,6 +209,37 @@ def test_very_deep_single_position(ctx):
             assert np.array_equal(col['max_mapq_fwd'], np.where(cov > 0, 60, 0))
 
 
+@pytest.mark.parametrize('stat', ('mapq', 'mapq_strand'))
+def test_mapq_tile_deeper_than_16_bits(stat, ctx):
+    # k_tilem packs n | nz << 16 per bank while a tile has at most 65535 candidate reads; a deeper tile is done in two
+    # sweeps, one per half of its positions, with full-word counters.  72 000 reads in one 512-position tile (70 000 of
+    # them over the same positions), starts in both halves, every mapping quality incl. 0, deletions and a ref-skip in the CIGARs, against the oracle --
+    # plain, min_baseq (events of low bases dropped: the kept runs are the intervals) and no_del (aligned spans only)
+    rng = np.random.default_rng(7)
+    n, L = 72000, 60
+    pos = np.sort(np.concatenate([rng.integers(1000, 1010, 35000), rng.integers(1020, 1030, 35000),
+                                  rng.integers(1290, 1330, 2000)])).astype('i4')
+    kind = rng.integers(0, 4, n)                      # 60M | 20M 5D 40M | 30M 40N 30M | 10S 50M
+    cig, off = [], [0]
+    for k in kind:
+        ops = ([(0, 60)], [(0, 20), (2, 5), (0, 40)], [(0, 30), (3, 40), (0, 30)], [(4, 10), (0, 50)])[k]
+        cig += [(l << 4) | op for op, l in ops]
+        off.append(len(cig))
+    flag = (np.where(rng.random(n) < 0.5, 16, 0) | np.where(rng.random(n) < 0.6, 3, 1)).astype('u2')
+    nb = dict(n_reads=n, tid=0, pos=pos, flag=flag, mapq=rng.choice([0, 0, 1, 13, 29, 60, 254, 255], n).astype('u1'),
+              tlen=np.zeros(n, 'i4'), mtid=np.zeros(n, 'i4'), l_seq=np.full(n, L, 'i4'),
+              cigar_off=np.array(off, 'i8'), cigar=np.array(cig, 'u4'), seq_off=np.arange(n + 1, dtype='i8') * (L // 2),
+              seq4=rng.choice(np.array([0x11, 0x12, 0x48, 0x84], 'u1'), n * L // 2),
+              qual=rng.integers(0, 41, n * L).astype('u1'), qual_off=np.arange(n + 1, dtype='i8') * L,
+              name_prev=np.full(n, -1, 'i4'))
+    ref = np.frombuffer(b'ACGT' * 600, dtype='u1')
+    reads = oracle_reads_from_arrays(nb)
+    for kw in (dict(), dict(min_baseq=20), dict(no_del=True), dict(min_baseq=30, no_del=True, min_mapq=1)):
+        out, mask = _run_host(ctx, nb, ref, stat, 900, 1500, max_depth=1000000, **kw)
+        p, F = _oracle(stat, reads, ref, 900, 1500, max_depth=1000000, **kw)
+        _compare(out, mask, p, F, 900, '%s %r' % (stat, kw))
+
+
 @pytest.mark.parametrize('stat', config.binned_types)
 def test_binned_synthetic_vs_oracle_and_sharded(stat, ctx, small):
     nb, ref, reads = small

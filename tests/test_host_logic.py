@@ -355,9 +355,29 @@ def test_position_chunks_cover_every_overlapping_read(monkeypatch):
         want = np.flatnonzero((b.pos < c_hi) & (b.endpos > c_lo))
         assert len(want) == 0 or (i0 <= want[0] and want[-1] < i1), (c_lo, c_hi)
         assert rs.qual is None or C.cast(rs.qual, C.c_void_p).value is None      # no qualities requested
-    # qualities wanted, or max_depth within reach of the local read density: one piece
-    assert len(list(opt._position_chunks(b, lo, hi, True, 8000))) == 1
+    # max_depth within reach of the local read density: one piece, with or without qualities
     assert len(list(opt._position_chunks(b, lo, hi, False, 20))) == 1
+    assert len(list(opt._position_chunks(b, lo, hi, True, 20, pair_links=lambda *a: None))) == 1
+    # qualities wanted: the same pieces, each with its qualities and with the batch-wide pairs of the mate-overlap
+    # rewrite as two-read name chains in the piece's own indices (here a stand-in for pss_pairs_host: every read
+    # paired with the previous read of its name)
+    links = np.asarray(b.name_prev, dtype=np.int32)
+    qpieces = list(opt._position_chunks(b, lo, hi, True, 8000, pair_links=lambda *a: links))
+    assert [(p[0], p[1]) for p in qpieces] == [(p[0], p[1]) for p in pieces]
+    n_cross = 0
+    for (c_lo, c_hi, rs), (_, _, rs0) in zip(qpieces, pieces):
+        i0 = (C.cast(rs.pos, C.c_void_p).value - addr0) // 4
+        i1 = i0 + rs.n_reads
+        assert (i0, rs.n_reads) == ((C.cast(rs0.pos, C.c_void_p).value - addr0) // 4, rs0.n_reads)
+        assert C.cast(rs.qual, C.c_void_p).value == b.qual.ctypes.data
+        assert C.cast(rs.qual_off, C.c_void_p).value == b.qual_off.ctypes.data + 8 * i0
+        assert rs.n_qual_bytes == int(b.qual_off[i1] - b.qual_off[i0])
+        prev = np.ctypeslib.as_array(C.cast(rs.name_prev, C.POINTER(C.c_int32)), shape=(rs.n_reads,))
+        want = np.where(links[i0:i1] >= i0, links[i0:i1] - i0, -1)
+        assert np.array_equal(prev, want)
+        n_cross += int(((links[i0:i1] >= 0) & (links[i0:i1] < i0)).sum())
+        assert prev.max(initial=-1) < rs.n_reads and np.all(prev < np.arange(rs.n_reads))
+    assert n_cross > 0          # some pairs do straddle a piece's first read: their links are dropped there
 
 
 def test_row_sink_packer_cpp(tmp_path):
@@ -371,6 +391,19 @@ def test_row_sink_packer_cpp(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count('bad 0') == 21
+
+
+def test_interval_maximum_structure_cpp(tmp_path):
+    # the max(mapq) structure of k_tilem (csrc/pss_imax.cuh: at most four atomic maxima per interval, resolved per
+    # block) and the kept-run enumeration under min_baseq (csrc/pss_lowq.cuh), compiled for the host and run against
+    # brute force: tests/cpp/imax_test.cpp
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, 'pysamstats_b200', 'csrc')
+    exe = str(tmp_path / 'imax_test')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-I', csrc, '-o', exe, os.path.join(root, 'tests', 'cpp', 'imax_test.cpp')])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and 'imax_test: ok' in out.stdout, out.stdout
 
 
 def test_own_inflate_equals_zlib():
