@@ -39,11 +39,18 @@ IMAX_HD int imax_floor_log2(uint32_t v) {       // v > 0
 #endif
 }
 
+// Where position p lives in sfx / pfx / pt: four words of padding after every 32 positions.  The resolution gives one
+// lane a whole block (16 consecutive words, read as four 128-bit accesses); without the padding the lanes of a quarter
+// warp would sit 16 words apart -- two bank groups for eight lanes, a four-way conflict on every access (ncu: 38 % of the
+// kernel's shared-memory wavefronts) -- with it they spread over all eight.  A block stays contiguous and 16-byte aligned.
+IMAX_HD int imax_idx(int p) { return p + ((p >> 5) << 2); }
+constexpr int imax_padded(int n) { return n + n / 8; }      // words of an array for n positions
+
 // number of table levels for a tile of `nblk` blocks (a power of two): levels 0 .. log2(nblk)
 constexpr int imax_levels(int nblk) { return nblk <= 1 ? 1 : 1 + imax_levels(nblk >> 1); }
 
 // One interval [a, b) (tile relative, 0 <= a < b <= tile length), value q > 0.
-//   sfx, pfx, pt: the bank's arrays of one word per position
+//   sfx, pfx, pt: the bank's arrays, position p at word imax_idx(p)
 //   tab: the bank's level-0 row; level k lives at tab + k * tab_stride
 //   amax(uint32_t *, uint32_t): atomic max
 template <class AMax>
@@ -52,8 +59,8 @@ IMAX_HD void imax_update(int a, int b, uint32_t q, uint32_t *sfx, uint32_t *pfx,
     const int ba = (a + IMAX_BLK - 1) >> IMAX_LOG, bb = b >> IMAX_LOG;      // whole blocks [ba, bb)
     if (ba <= bb) {
         // a <= 16 ba <= 16 bb <= b: head [a, 16 ba) and tail [16 bb, b) are a suffix / a prefix of their blocks
-        if (a & (IMAX_BLK - 1)) amax(sfx + a, q);
-        if (b & (IMAX_BLK - 1)) amax(pfx + b - 1, q);
+        if (a & (IMAX_BLK - 1)) amax(sfx + imax_idx(a), q);
+        if (b & (IMAX_BLK - 1)) amax(pfx + imax_idx(b - 1), q);
         if (ba < bb) {
             const int nb = bb - ba, k = imax_floor_log2((uint32_t)nb);
             amax(tab + k * tab_stride + ba, q);
@@ -61,7 +68,7 @@ IMAX_HD void imax_update(int a, int b, uint32_t q, uint32_t *sfx, uint32_t *pfx,
         }
     } else {
         // strictly inside one block, touching neither of its ends
-        for (int p = a; p < b; ++p) amax(pt + p, q);
+        for (int p = a; p < b; ++p) amax(pt + imax_idx(p), q);
     }
 }
 

@@ -1852,12 +1852,62 @@ k_tileq(TileArgs A) {
 #endif
 #define MQ_NB (TT / IMAX_BLK)          // blocks per tile: one lane each in the resolution
 #define MQ_NLEV 6                      // table levels 0 .. log2(MQ_NB)
-static_assert(MQ_NB == 32 && imax_levels(MQ_NB) == MQ_NLEV, "one warp resolves a bank: 32 blocks of 16 positions");
-#define MQ_WORDS (20 * TT + MQ_NLEV * 4 * MQ_NB)      // cnt 8 TT | sfx 4 TT | pfx 4 TT | pt 4 TT | tab
+#define MQ_PS (TT + TT / 8)            // = imax_padded(TT): words of one bank's sfx / pfx / pt array (position p at imax_idx(p))
+static_assert(MQ_NB == 32 && imax_levels(MQ_NB) == MQ_NLEV && MQ_PS == imax_padded(TT), "one warp resolves a bank: 32 blocks of 16 positions");
+#define MQ_WORDS (8 * TT + 12 * MQ_PS + MQ_NLEV * 4 * MQ_NB)      // cnt 8 TT | sfx 4 PS | pfx 4 PS | pt 4 PS | tab
 
+// shared-memory reductions by explicit state space: mq_emit below is deliberately NOT inlined (one copy instead of one per
+// CIGAR case of the read walk), and through a generic pointer the compiler would emit generic atomics
+__device__ __forceinline__ void sred_add(uint32_t *p, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 struct AtomicMaxOp {
-    __device__ __forceinline__ void operator()(uint32_t *p, uint32_t v) const { atomicMax(p, v); }
+    __device__ __forceinline__ void operator()(uint32_t *p, uint32_t v) const {
+        asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+    }
 };
+
+// One interval of events of a read -- reference positions [x, x + l) -- into the counters of the sweep's window
+// [h0, h0 + tw) and (first sweep) into the tile's interval maxima.  flags: deep | first sweep << 1 | bank << 2.
+__device__ __noinline__ void mq_emit(uint32_t *cnt, int tw, int h0, int t0, uint32_t flags, uint32_t q, int x, int l) {
+    const bool deep = flags & 1u;
+    const int bank = (int)(flags >> 2);
+    const int a = max(x - h0, 0), b = min(x + l - h0, tw);
+    if (a < b) {
+        uint32_t *p = cnt + bank * tw;
+        const uint32_t sq = q * q;
+        if (!deep) {
+            const uint32_t inc = q ? 1u : 0x10001u;              // n | nz << 16
+            sred_add(p + a, inc);
+            if (b < tw) sred_add(p + b, 0u - inc);
+            if (q) {
+                p += 4 * tw;
+                sred_add(p + a, sq);
+                if (b < tw) sred_add(p + b, 0u - sq);
+            }
+        } else {
+            sred_add(p + a, 1u);
+            if (b < tw) sred_add(p + b, 0u - 1u);
+            if (!q) {
+                p += 4 * tw;
+                sred_add(p + a, 1u);
+                if (b < tw) sred_add(p + b, 0u - 1u);
+            } else {
+                const uint32_t lo = sq & 255u, hi = sq >> 8;
+                if (lo) { uint32_t *pl = p + 8 * tw; sred_add(pl + a, lo); if (b < tw) sred_add(pl + b, 0u - lo); }
+                if (hi) { uint32_t *ph = p + 12 * tw; sred_add(ph + a, hi); if (b < tw) sred_add(ph + b, 0u - hi); }
+            }
+        }
+    }
+    if ((flags & 2u) && q) {
+        const int a2 = max(x - t0, 0), b2 = min(x + l - t0, TT);
+        if (a2 < b2) {
+            uint32_t *sfx = cnt + 8 * TT + bank * MQ_PS;
+            imax_update(a2, b2, q, sfx, sfx + 4 * MQ_PS, sfx + 8 * MQ_PS, cnt + 8 * TT + 12 * MQ_PS + bank * MQ_NB, 4 * MQ_NB,
+                        AtomicMaxOp());
+        }
+    }
+}
 __device__ __forceinline__ uint4 max4(uint4 a, uint4 b) { return make_uint4(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z), max(a.w, b.w)); }
 
 // Four positions of a bank's counters (cq = cnt + 4 quad; counter arrays are tw words apart): n, nz, and the root mean
@@ -1869,24 +1919,59 @@ __device__ __forceinline__ uint4 mq_ldn(const uint32_t *cq, int b, int tw, bool 
 __device__ __forceinline__ uint4 mq_ldz(const uint32_t *cq, int b, int tw, bool deep) {
     return deep ? *reinterpret_cast<const uint4 *>(cq + (4 + b) * tw) : hi16(*reinterpret_cast<const uint4 *>(cq + b * tw));
 }
+// rootmean (opt.pyx:2159-2163) of a shallow tile: n <= 65535 and sq <= 255^2 n < 2^32, so the answer is at most 255.
+// A float estimate of sqrt(sq / n) is off by < 2e-4 there (two approximate operations, 2 ulp each, on values <= 255), so
+// unless it lies within 1e-3 of a half its nearest integer IS the answer, and only the (rare) estimates next to a half
+// take the exact integer decision, out of line.  The first version inlined q_rootmean -- two 64-bit boundary checks and a
+// copy of its double-precision fallback -- at each of the 24 places of the finalisation: 5088 SASS instructions, ncu
+// showed 3.1 warps per issue waiting for the instruction cache and 37 % of the executed instructions in those checks.
+// (scripts/mq_root_check.cpp runs this logic against the reference's double formula around every boundary.)
+__device__ __noinline__ uint32_t mq_root_tie(uint32_t sq, uint32_t n, uint32_t r, bool above) {
+    // the estimate lies in [r, r + 0.5] or in [r - 0.5, r): only the boundary on that side can be crossed (r >= 1 below).
+    // Boundary c / 2 with c = 2 r +- 1:  sqrt(sq / n) <=> c / 2  is  4 sq <=> c^2 n  is  sq <=> t (+ rem / 4); a tie (equality,
+    // which the reference's correctly rounded double operations see too) goes to the even neighbour
+    const uint32_t c = above ? 2 * r + 1 : 2 * r - 1;
+    const unsigned long long cn = (unsigned long long)(c * c) * n;             // c^2 <= 511^2, n < 2^16: cn / 4 < 2^32
+    const uint32_t t = (uint32_t)(cn >> 2);
+    const bool exact = ((uint32_t)cn & 3u) == 0, odd = r & 1u, eq = sq == t;
+    const bool up = above & ((sq > t) | (eq & exact & odd));
+    const bool dn = !above & ((sq < t) | (eq & (!exact | odd)));
+    return r + (up ? 1u : 0u) - (dn ? 1u : 0u);
+}
+__device__ __forceinline__ uint32_t mq_root32(uint32_t sq, uint32_t n) {
+    const float x = __fdividef((float)sq, (float)n);
+    const float rf = x * rsqrtf(x);                         // (sq == 0: NaN, discarded below; n == 0 has sq == 0)
+    const float rr = rintf(rf);
+    uint32_t r = (uint32_t)rr;
+    if (fabsf(rf - rr) > 0.499f) r = mq_root_tie(sq, n, r, rf >= rr);
+    return sq ? r : 0u;
+}
+__device__ __noinline__ uint32_t mq_root_any(unsigned long long sq, uint32_t n) { return (uint32_t)q_rootmean(sq, n); }
+
 template <int MASK>
 __device__ __forceinline__ uint4 mq_rms(const uint32_t *cq, int tw, bool deep) {
     uint4 n = make_uint4(0, 0, 0, 0);
-    unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (!deep) {
+        // all the reads of the tile together have sum(mapq^2) <= 65535 * 255^2 < 2^32: word sums over the banks
+        uint4 s = n;
 #pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (!((MASK >> b) & 1)) continue;
+            n = n + lo16(*reinterpret_cast<const uint4 *>(cq + b * tw));
+            s = s + *reinterpret_cast<const uint4 *>(cq + (4 + b) * tw);
+        }
+        return make_uint4(mq_root32(s.x, n.x), mq_root32(s.y, n.y), mq_root32(s.z, n.z), mq_root32(s.w, n.w));
+    }
+    unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 1
     for (int b = 0; b < 4; ++b) {
         if (!((MASK >> b) & 1)) continue;
-        n = n + mq_ldn(cq, b, tw, deep);
-        const uint4 l = *reinterpret_cast<const uint4 *>(cq + ((deep ? 8 : 4) + b) * tw);
-        s0 += l.x; s1 += l.y; s2 += l.z; s3 += l.w;
-        if (deep) {
-            const uint4 h = *reinterpret_cast<const uint4 *>(cq + (12 + b) * tw);
-            s0 += (unsigned long long)h.x << 8; s1 += (unsigned long long)h.y << 8;
-            s2 += (unsigned long long)h.z << 8; s3 += (unsigned long long)h.w << 8;
-        }
+        n = n + *reinterpret_cast<const uint4 *>(cq + b * tw);
+        const uint4 l = *reinterpret_cast<const uint4 *>(cq + (8 + b) * tw), h = *reinterpret_cast<const uint4 *>(cq + (12 + b) * tw);
+        s0 += l.x + ((unsigned long long)h.x << 8); s1 += l.y + ((unsigned long long)h.y << 8);
+        s2 += l.z + ((unsigned long long)h.z << 8); s3 += l.w + ((unsigned long long)h.w << 8);
     }
-    return make_uint4((uint32_t)q_rootmean(s0, n.x), (uint32_t)q_rootmean(s1, n.y), (uint32_t)q_rootmean(s2, n.z),
-                      (uint32_t)q_rootmean(s3, n.w));
+    return make_uint4(mq_root_any(s0, n.x), mq_root_any(s1, n.y), mq_root_any(s2, n.z), mq_root_any(s3, n.w));
 }
 
 template <int STAT, bool MINQ>
@@ -1897,7 +1982,7 @@ k_tilem(TileArgs A) {
     static_assert(MQ_NT >= MQ_CH && NWARPS == 8, "one scatter thread per staged read; eight warps share the scans");
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *sfx = cnt + 8 * TT, *pfx = cnt + 12 * TT, *pt = cnt + 16 * TT, *tab = cnt + 20 * TT;
+    uint32_t *sfx = cnt + 8 * TT, *pfx = sfx + 4 * MQ_PS, *pt = pfx + 4 * MQ_PS, *tab = pt + 4 * MQ_PS;
     uint32_t *raw = cnt + MQ_WORDS;                                          // exists only when need_raw
     RInfo *s_ri = reinterpret_cast<RInfo *>(raw + (A.need_raw ? TT : 0));
     __shared__ __align__(8) uint64_t s_bar;
@@ -1961,42 +2046,10 @@ k_tilem(TileArgs A) {
                     }
                     if (cls & CLS_COUNTED) {
                         const int bank = cls & 3u;
-                        const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u, sq = q * q;
+                        const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u;
+                        const uint32_t fl = (deep ? 1u : 0u) | (sweep == 0 ? 2u : 0u) | ((uint32_t)bank << 2);
                         // the read has an event at every position of the reference interval [x, x + l)
-                        auto emit = [&](int x, int l) {
-                            const int a = max(x - h0, 0), b = min(x + l - h0, tw);
-                            if (a < b) {
-                                uint32_t *p = cnt + bank * tw;
-                                if (!deep) {
-                                    const uint32_t inc = q ? 1u : 0x10001u;              // n | nz << 16
-                                    atomicAdd(p + a, inc);
-                                    if (b < tw) atomicAdd(p + b, 0u - inc);
-                                    if (q) {
-                                        p += 4 * tw;
-                                        atomicAdd(p + a, sq);
-                                        if (b < tw) atomicAdd(p + b, 0u - sq);
-                                    }
-                                } else {
-                                    atomicAdd(p + a, 1u);
-                                    if (b < tw) atomicAdd(p + b, 0u - 1u);
-                                    if (!q) {
-                                        p += 4 * tw;
-                                        atomicAdd(p + a, 1u);
-                                        if (b < tw) atomicAdd(p + b, 0u - 1u);
-                                    } else {
-                                        const uint32_t lo = sq & 255u, hi = sq >> 8;
-                                        if (lo) { uint32_t *pl = p + 8 * tw; atomicAdd(pl + a, lo); if (b < tw) atomicAdd(pl + b, 0u - lo); }
-                                        if (hi) { uint32_t *ph = p + 12 * tw; atomicAdd(ph + a, hi); if (b < tw) atomicAdd(ph + b, 0u - hi); }
-                                    }
-                                }
-                            }
-                            if (sweep == 0 && q) {
-                                const int a2 = max(x - t0, 0), b2 = min(x + l - t0, TT);
-                                if (a2 < b2)
-                                    imax_update(a2, b2, q, sfx + bank * TT, pfx + bank * TT, pt + bank * TT, tab + bank * MQ_NB,
-                                                4 * MQ_NB, AtomicMaxOp());
-                            }
-                        };
+                        auto emit = [&](int x, int l) { mq_emit(cnt, tw, h0, t0, fl, q, x, l); };
                         if (!MINQ && !A.no_del) emit(r.pos, r.end - r.pos);              // M, D and N spans all count (opt.pyx:1904-1906)
                         else if (cls & CLS_NOREF) { if (!A.no_del) emit(r.pos, 1); }     // one deletion-like event at pos
                         else if (!MINQ && (cls & CLS_SIMPLE)) emit(r.pos, r.end - r.pos);
@@ -2047,9 +2100,10 @@ k_tilem(TileArgs A) {
             }
             const uint32_t body = v[0];
             // imax_resolve_block on the block's 16 positions, 128-bit accesses
-            const uint4 *sp = reinterpret_cast<const uint4 *>(sfx + warp * TT + IMAX_BLK * lane);
-            const uint4 *pp = reinterpret_cast<const uint4 *>(pfx + warp * TT + IMAX_BLK * lane);
-            uint4 *tp = reinterpret_cast<uint4 *>(pt + warp * TT + IMAX_BLK * lane);
+            const int bo = warp * MQ_PS + imax_idx(IMAX_BLK * lane);
+            const uint4 *sp = reinterpret_cast<const uint4 *>(sfx + bo);
+            const uint4 *pp = reinterpret_cast<const uint4 *>(pfx + bo);
+            uint4 *tp = reinterpret_cast<uint4 *>(pt + bo);
             uint32_t s[IMAX_BLK];
             uint32_t run = 0;
 #pragma unroll
@@ -2112,15 +2166,15 @@ k_tilem(TileArgs A) {
                     } else {
                         O.skip(4);
                         O.put(mq_rms<15>(cq, tw, deep)); O.put(mq_rms<12>(cq, tw, deep));
-                        const uint4 *mp = reinterpret_cast<const uint4 *>(pt + sweep * tw + 4 * qd);
-                        const uint4 m_pp = max4(mp[2 * TT / 4], mp[3 * TT / 4]);
-                        O.put(max4(max4(mp[0], mp[TT / 4]), m_pp));
+                        const uint4 *mp = reinterpret_cast<const uint4 *>(pt + imax_idx(sweep * tw + 4 * qd));
+                        const uint4 m_pp = max4(mp[2 * MQ_PS / 4], mp[3 * MQ_PS / 4]);
+                        O.put(max4(max4(mp[0], mp[MQ_PS / 4]), m_pp));
                         O.put(m_pp);
                     }
                 } else if (STRAND && g == 4) {
                     O.skip(18);
-                    const uint4 *mp = reinterpret_cast<const uint4 *>(pt + sweep * tw + 4 * qd);
-                    const uint4 m0 = mp[0], m1 = mp[TT / 4], m2 = mp[2 * TT / 4], m3 = mp[3 * TT / 4];
+                    const uint4 *mp = reinterpret_cast<const uint4 *>(pt + imax_idx(sweep * tw + 4 * qd));
+                    const uint4 m0 = mp[0], m1 = mp[MQ_PS / 4], m2 = mp[2 * MQ_PS / 4], m3 = mp[3 * MQ_PS / 4];
                     const uint4 m_pp = max4(m2, m3);
                     O.put(max4(max4(m0, m1), m_pp)); O.put(max4(m0, m2)); O.put(max4(m1, m3)); O.put(m_pp); O.put(m2); O.put(m3);
                 } else {
@@ -2244,12 +2298,55 @@ __device__ __forceinline__ int tlen_std(long long n, long long S, unsigned long 
 }
 
 struct TlenOut { int n, mean, rms, sd; };
+
+// The exact forms, out of line: what the finalisation used for every class of every position until ncu showed them to be
+// ~80 % of tlen_strand's instructions (a double division + square root + 64- / 128-bit boundary products per value, inlined
+// six times: 4976 SASS instructions).  Now only the values the float screening below cannot decide come here.
+__device__ __noinline__ int tlen_mean_exact(long long S, unsigned n) {
+    return n > 0 ? (int)rint((double)S / (double)n) : 0;                    // opt.pyx:2166-2170
+}
+__device__ __noinline__ int tlen_rms_exact(unsigned long long Q, unsigned n) { return q_rootmean(Q, n); }   // opt.pyx:2159-2163
+__device__ __noinline__ unsigned tlen_std_exact(unsigned n, long long S, unsigned long long Q, float force) {   // sd | ambiguous << 31
+    bool amb = false;
+    const int sd = tlen_std((long long)n, S, Q, &amb, force);
+    return (unsigned)sd | (amb ? 0x80000000u : 0u);
+}
+
+// mean, rms and std of one class from n, sum(t), sum(t^2).  Each is rint() of a real number; a FLOAT estimate e of that
+// number is off by less than 5e-7 |e| (conversions 2^-24 each, the approximate reciprocal / division and reciprocal square
+// root 2 ulp each, the products 2^-24; the square root halves what enters under it), so whenever
+// |e - rint(e)| <= 0.4999 - 1e-6 |e| the real number is less than 0.5 away from rint(e): that IS its rounding and no tie
+// is near.  For std the margin is 0.4995: the order-dependent Welford value of the reference can differ from the exact one
+// only within the ambiguity bound of tlen_std_t, which with sum(t^2) < 2^32 is at most 2.4e-4 in std -- so an accepted
+// position need not be replayed either.  Everything else -- estimates next to a half (one value in a thousand), sums beyond
+// 32 bits, n >= 65536, the forced replay of the tests -- takes the exact forms above.  scripts/tlen_fast_check.cpp runs
+// this screening against the exact forms on adversarial and random multisets with the estimates perturbed by 1e-6.
 __device__ __forceinline__ TlenOut tlen_class(unsigned n, long long S, unsigned long long Q, bool *amb, float force) {
     TlenOut o;
     o.n = (int)n;
-    o.mean = n > 0 ? (int)rint((double)S / (double)n) : 0;                 // opt.pyx:2166-2170
-    o.rms = q_rootmean(Q, n);                                              // opt.pyx:2159-2163, decided in integers
-    o.sd = tlen_std((long long)n, S, Q, amb, force);
+    if (n == 0) { o.mean = o.rms = o.sd = 0; return o; }
+    const bool small = force == 0.0f && n < 65536u && (Q >> 32) == 0 && (long long)(int)S == S;
+    const float inv = __fdividef(1.0f, (float)n);
+    {   // mean
+        const float e = (float)(int)S * inv, r = rintf(e);
+        o.mean = (small && fabsf(e - r) <= 0.4999f - 1e-6f * fabsf(e)) ? (int)r : tlen_mean_exact(S, n);
+    }
+    {   // root mean square
+        const float x = (float)(unsigned)Q * inv, e = x * rsqrtf(x), r = rintf(e);      // (Q == 0: NaN, never accepted)
+        o.rms = Q == 0 ? 0 : (small && fabsf(e - r) <= 0.4999f - 1e-6f * e) ? (int)r : tlen_rms_exact(Q, n);
+    }
+    if (n < 2) { o.sd = 0; return o; }
+    {   // standard deviation: sqrt(A / (n (n - 1))), A = n sum(t^2) - sum(t)^2 exactly (n < 2^16, sum(t^2) < 2^32, |sum(t)| < 2^31)
+        const unsigned long long nq = (unsigned long long)n * (unsigned)Q, ss = (unsigned long long)(S * S);
+        const unsigned long long Aex = nq >= ss ? nq - ss : 0;
+        const float v = __fdividef((float)Aex, (float)(n * (n - 1u))), e = v * rsqrtf(v), r = rintf(e);   // (A == 0: NaN)
+        if (small && (Aex == 0 || fabsf(e - r) <= 0.4995f - 1e-6f * e)) o.sd = Aex == 0 ? 0 : (int)r;
+        else {
+            const unsigned w = tlen_std_exact(n, S, Q, force);
+            o.sd = (int)(w & 0x7fffffffu);
+            if (w >> 31) *amb = true;
+        }
+    }
     return o;
 }
 

@@ -15,7 +15,7 @@ static uint32_t rnd() { static uint64_t s = 0x9E3779B97F4A7C15ull; s ^= s << 13;
 
 static long test_tile(int TTN, int n_iv, int shape) {
     const int NB = TTN / IMAX_BLK, NLEV = imax_levels(NB);
-    std::vector<uint32_t> sfx(TTN, 0), pfx(TTN, 0), pt(TTN, 0), tab((size_t)NLEV * NB, 0), want(TTN, 0);
+    std::vector<uint32_t> sfx(imax_padded(TTN), 0), pfx(imax_padded(TTN), 0), pt(imax_padded(TTN), 0), tab((size_t)NLEV * NB, 0), want(TTN, 0);
     auto amax = [](uint32_t *p, uint32_t v) { if (v > *p) *p = v; };
     for (int i = 0; i < n_iv; ++i) {
         int a, b;
@@ -34,9 +34,10 @@ static long test_tile(int TTN, int n_iv, int shape) {
     }
     imax_pushdown_ref(tab.data(), NB, NB);
     for (int blk = 0; blk < NB; ++blk)
-        imax_resolve_block(sfx.data() + blk * IMAX_BLK, pfx.data() + blk * IMAX_BLK, pt.data() + blk * IMAX_BLK, tab[blk]);
+        imax_resolve_block(sfx.data() + imax_idx(blk * IMAX_BLK), pfx.data() + imax_idx(blk * IMAX_BLK), pt.data() + imax_idx(blk * IMAX_BLK), tab[blk]);
     long bad = 0;
-    for (int p = 0; p < TTN; ++p) bad += pt[p] != want[p];
+    for (int p = 0; p < TTN; ++p) bad += pt[imax_idx(p)] != want[p];
+    for (int p = 32; p < imax_padded(TTN); p += 36) for (int k = 0; k < 4; ++k) bad += (sfx[p + k] | pfx[p + k] | pt[p + k]) != 0;   // padding untouched
     return bad;
 }
 

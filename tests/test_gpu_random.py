@@ -183,6 +183,25 @@ def test_quality_requests_in_position_pieces(seed, monkeypatch):
     from pysamstats_b200 import opt
     ctx = _cabi.get_context()
     nb, ref = random_batch(seed, n_reads=4000, span=6000, maxlen=70)
+    # QNAMEs shared by two or three NEARBY reads (a stored read expires from htslib's table once the pileup has moved
+    # past it), most of them qualifying for the rewrite (proper pair, mate mapped, |tlen| < 2 l_seq)
+    rng = np.random.default_rng(seed)
+    n = nb['n_reads']
+    order = np.concatenate([k + rng.permutation(min(12, n - k)) for k in range(0, n, 12)])
+    names = np.empty(n, 'i8')
+    i = g = 0
+    while i < n:
+        k = int(rng.choice([2, 2, 3, 1]))
+        names[order[i:i + k]] = g
+        i, g = i + k, g + 1
+    last, prev = {}, np.full(n, -1, 'i4')
+    for i, nm in enumerate(names.tolist()):
+        prev[i] = last.get(nm, -1)
+        last[nm] = i
+    ovl = rng.random(n) < 0.8
+    nb['name_prev'] = prev
+    nb['flag'] = np.where(ovl, (nb['flag'] | 3) & ~np.uint16(8), nb['flag']).astype('u2')
+    nb['tlen'] = np.where(ovl, rng.choice([40, -40, 25, -90], n), nb['tlen']).astype('i4')
     b = _read_batch(nb)
     monkeypatch.setenv('PSS_TABLE_CHUNK', '1024')
     lo, hi = 0, int(nb['pos'].max()) + 900
