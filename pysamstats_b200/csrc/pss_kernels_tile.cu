@@ -1437,6 +1437,19 @@ __device__ __forceinline__ int q_rootmean(unsigned long long sq, uint32_t n) {
     return (int)r;
 }
 
+// The same value through a float screening: the estimate e of sqrt(sq / n) is off by less than 5e-7 e (conversions, one
+// approximate division and one reciprocal square root at 2 ulp each), so |e - rint(e)| <= 0.4999 - 1e-6 e leaves the real
+// number less than 0.5 away from rint(e) -- its rounding, with no tie near.  Only estimates next to a half (and sums
+// beyond 32 bits) take the integer decision above, out of line: the finalisation of baseq_ext_strand evaluates 18 root
+// mean squares per position, and inlining the full form 18 times was a quarter of its instructions.
+// (scripts/tlen_fast_check.cpp checks the screening -- its rms column -- against the exact form.)
+__device__ __noinline__ int q_rootmean_exact(unsigned long long sq, uint32_t n) { return q_rootmean(sq, n); }
+__device__ __forceinline__ int q_rootmean_scr(unsigned long long sq, uint32_t n) {
+    const float x = __fdividef((float)(uint32_t)sq, (float)n), e = x * rsqrtf(x), r = rintf(e);   // (sq == 0: NaN, not accepted)
+    if (sq == 0) return 0;                                                                          // (n == 0 has sq == 0)
+    return ((sq >> 32) == 0 && fabsf(e - r) <= 0.4999f - 1e-6f * e) ? (int)r : q_rootmean_exact(sq, n);
+}
+
 // one aligned span [x, x + l) of a read whose first base is query index y: the lanes' four positions
 // (minq: events of bases below min_baseq are dropped, opt.pyx:1900-1903; 0 keeps everything)
 template <int BANK, bool MINQ>
@@ -1764,13 +1777,13 @@ k_tileq(TileArgs A) {
                                    max(mb[2], mb[3]), mb[2], mb[3]};
             if (STAT == PSS_MAPQ) {
                 o[0] = N[0]; o[st] = N[3]; o[2 * st] = Z[0]; o[3 * st] = Z[3];
-                o[4 * st] = q_rootmean(S[0], N[0]); o[5 * st] = q_rootmean(S[3], N[3]);
+                o[4 * st] = q_rootmean_scr(S[0], N[0]); o[5 * st] = q_rootmean_scr(S[3], N[3]);
                 o[6 * st] = M[0]; o[7 * st] = M[3];
             } else {
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
                     o[k * st] = N[k]; o[(6 + k) * st] = Z[k];
-                    o[(12 + k) * st] = q_rootmean(S[k], N[k]); o[(18 + k) * st] = M[k];
+                    o[(12 + k) * st] = q_rootmean_scr(S[k], N[k]); o[(18 + k) * st] = M[k];
                 }
             }
         } else {
@@ -1788,10 +1801,10 @@ k_tileq(TileArgs A) {
                 }
                 six32(nb, N); six32(db, D);
                 if (STAT == PSS_BASEQ) {
-                    o[0] = N[0]; o[st] = N[3]; o[2 * st] = q_rootmean(S[0], D[0]); o[3 * st] = q_rootmean(S[3], D[3]);
+                    o[0] = N[0]; o[st] = N[3]; o[2 * st] = q_rootmean_scr(S[0], D[0]); o[3 * st] = q_rootmean_scr(S[3], D[3]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) { o[k * st] = N[k]; o[(6 + k) * st] = q_rootmean(S[k], D[k]); }
+                    for (int k = 0; k < 6; ++k) { o[k * st] = N[k]; o[(6 + k) * st] = q_rootmean_scr(S[k], D[k]); }
                 }
             } else {
                 uint32_t mtb[4], mmb[4], Mn[6], Mm[6];
@@ -1809,15 +1822,15 @@ k_tileq(TileArgs A) {
                     for (int jx = 0; jx < 2; ++jx) {
                         const int k = idx[jx];
                         o[jx * st] = N[k]; o[(2 + jx) * st] = Mn[k]; o[(4 + jx) * st] = Mm[k];
-                        o[(6 + jx) * st] = q_rootmean(S[k], Mn[k] + Mm[k]); o[(8 + jx) * st] = q_rootmean(S[k] - Sm[k], Mn[k]);
-                        o[(10 + jx) * st] = q_rootmean(Sm[k], Mm[k]);
+                        o[(6 + jx) * st] = q_rootmean_scr(S[k], Mn[k] + Mm[k]); o[(8 + jx) * st] = q_rootmean_scr(S[k] - Sm[k], Mn[k]);
+                        o[(10 + jx) * st] = q_rootmean_scr(Sm[k], Mm[k]);
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         o[k * st] = N[k]; o[(6 + k) * st] = Mn[k]; o[(12 + k) * st] = Mm[k];
-                        o[(18 + k) * st] = q_rootmean(S[k], Mn[k] + Mm[k]); o[(24 + k) * st] = q_rootmean(S[k] - Sm[k], Mn[k]);
-                        o[(30 + k) * st] = q_rootmean(Sm[k], Mm[k]);
+                        o[(18 + k) * st] = q_rootmean_scr(S[k], Mn[k] + Mm[k]); o[(24 + k) * st] = q_rootmean_scr(S[k] - Sm[k], Mn[k]);
+                        o[(30 + k) * st] = q_rootmean_scr(Sm[k], Mm[k]);
                     }
                 }
             }
@@ -2243,21 +2256,38 @@ k_tilem(TileArgs A) {
 #define TLEN_CTAS 4           // 52 KB of shared memory per CTA: a fourth fits (tlen_strand 5.49 -> 4.92 ms per 50 Mb)
 #endif
 
+// 64-bit add into shared memory as two 32-bit atomic adds: the carry out of the low word is seen by exactly the add that
+// causes it (old + lo wraps), so low and high word together always hold the sum of all increments mod 2^64 whatever the
+// interleaving.  The native form is a compare-and-swap loop (ATOMS.CAST.SPIN.64: a load, the CAS, retries under
+// contention); a typical increment here -- a template length, or its two's complement at the interval's end, whose high
+// word 0xffffffff is cancelled by the carry -- is ONE 32-bit add.
+__device__ __forceinline__ void sadd64(unsigned long long *p, unsigned long long inc) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(p);
+    const uint32_t lo = (uint32_t)inc;
+    uint32_t hi = (uint32_t)(inc >> 32);
+    if (lo) {
+        const uint32_t old = atomicAdd(w, lo);
+        hi += ((uint32_t)(old + lo) < lo) ? 1u : 0u;
+    }
+    if (hi) atomicAdd(w + 1, hi);
+}
 __device__ __forceinline__ void interval_add64(unsigned long long *arr, int x, int l, int t0, unsigned long long inc) {
     int a = max(x - t0, 0), b = min(x + l - t0, TT);
     if (a < b) {
-        atomicAdd(arr + a, inc);
-        if (b < TT) atomicAdd(arr + b, 0ull - inc);
+        sadd64(arr + a, inc);
+        if (b < TT) sadd64(arr + b, 0ull - inc);
     }
 }
 
-// in-place inclusive prefix sum of TT 64-bit words by one warp (lane l owns words [64 k + 2 l, 64 k + 2 l + 2))
+// in-place inclusive prefix sum of TT 64-bit words by one warp (lane l owns words [128 k + 4 l, 128 k + 4 l + 4): four
+// rounds of the five-step shuffle scan instead of eight with two words per lane)
 __device__ __forceinline__ void warp_scan_array64(unsigned long long *arr, int lane) {
     unsigned long long carry = 0;
 #pragma unroll 1
-    for (int k = 0; k < TT / 64; ++k) {
-        ulonglong2 v = *reinterpret_cast<ulonglong2 *>(arr + 64 * k + 2 * lane);
-        v.y += v.x;
+    for (int k = 0; k < TT / 128; ++k) {
+        ulonglong2 *p = reinterpret_cast<ulonglong2 *>(arr + 128 * k + 4 * lane);
+        ulonglong2 u = p[0], v = p[1];
+        u.y += u.x; v.x += u.y; v.y += v.x;
         unsigned long long inc = v.y;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -2266,8 +2296,8 @@ __device__ __forceinline__ void warp_scan_array64(unsigned long long *arr, int l
         }
         const unsigned long long off = carry + inc - v.y;
         carry += __shfl_sync(FULL, inc, 31);
-        v.x += off; v.y += off;
-        *reinterpret_cast<ulonglong2 *>(arr + 64 * k + 2 * lane) = v;
+        u.x += off; u.y += off; v.x += off; v.y += off;
+        p[0] = u; p[1] = v;
     }
 }
 
@@ -2305,7 +2335,7 @@ struct TlenOut { int n, mean, rms, sd; };
 __device__ __noinline__ int tlen_mean_exact(long long S, unsigned n) {
     return n > 0 ? (int)rint((double)S / (double)n) : 0;                    // opt.pyx:2166-2170
 }
-__device__ __noinline__ int tlen_rms_exact(unsigned long long Q, unsigned n) { return q_rootmean(Q, n); }   // opt.pyx:2159-2163
+__device__ __forceinline__ int tlen_rms_exact(unsigned long long Q, unsigned n) { return q_rootmean_exact(Q, n); }   // opt.pyx:2159-2163
 __device__ __noinline__ unsigned tlen_std_exact(unsigned n, long long S, unsigned long long Q, float force) {   // sd | ambiguous << 31
     bool amb = false;
     const int sd = tlen_std((long long)n, S, Q, &amb, force);
