@@ -324,7 +324,7 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
     a.toolong = &((SmallState *)ctx->small.p)->toolong;
     a.tlen = (P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND) ? R->tlen : nullptr;
     a.tile_rng = nullptr;
-    a.tile_redo = nullptr;
+    a.redo = nullptr;
     a.lowq = nullptr;
     a.n_reads = R->n_reads;
     a.ref = P->ref; a.ref_start = P->ref_start; a.ref_len = P->ref_len;
@@ -352,21 +352,22 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
         const bool is_tlen = P->stat == PSS_TLEN || P->stat == PSS_TLEN_STRAND;
         if (is_tlen) {
             if ((rc = ensure(ctx, ctx->redo, tile_redo_bytes(ntiles))) != PSS_OK) return rc;
-            CU(cudaMemsetAsync(ctx->redo.p, 0, tile_redo_bytes(ntiles), s));
-            a.tile_redo = (int32_t *)ctx->redo.p;
+            CU(cudaMemsetAsync(ctx->redo.p, 0, sizeof(int32_t), s));        // the list's length
+            a.redo = (int32_t *)ctx->redo.p;
         }
         CU(launch_tile(P->stat, a, R->seq_off, R->n_reads, (SmallState *)ctx->small.p, need_raw, ntiles, ctx->tdesc.p,
                        ctx->refpack.p, desc_valid, s, &ctx->launches, e0, e1));
         ctx->desc_start = start; ctx->desc_end = end;
         if (is_tlen) {
             // the in-order Welford replay for the tiles whose std_tlen is too close to a rounding boundary to be
-            // decided from the exact sums (its CTAs return at once for every other tile)
+            // decided from the exact sums: a fixed small grid walking the list k_tilet wrote
             const int64_t gtiles = (npos + PSS_TILE - 1) / PSS_TILE;
             if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)gtiles)) != PSS_OK) return rc;
             CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, gtiles,
                                   PSS_TILE, (int2 *)ctx->rng.p, s, &ctx->launches));
             a.tile_rng = (const int2 *)ctx->rng.p;
-            CU(launch_pileup(P->stat, a, gtiles, true, s, &ctx->launches));
+            CU(launch_pileup(P->stat, a, gtiles < 1184 ? gtiles : 1184, true, s, &ctx->launches));     // 148 SMs x 8
+            a.redo = nullptr;
         }
     } else {
         if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)ntiles)) != PSS_OK) return rc;

@@ -67,8 +67,9 @@ struct PileupArgs {
     const int32_t *tlen;
     const int2 *tile_rng;       // candidate read range [x, y) per tile
     const uint32_t *lowq;       // tile kernel, min_baseq > 0: bit per base below the threshold (k_lowq)
-    int32_t *tile_redo;         // tlen: per 512-position tile, set by k_tilet when the in-order replay must redo it;
-                                // k_pileup (256-position tiles) returns at once for tiles whose flag is 0
+    int32_t *redo;              // tlen: the in-order replay list -- [0] = number of 256-position tiles to redo, [1..] their
+                                // indices: k_tilet appends the halves of a 512-position tile it cannot decide, the
+                                // replay launch of k_pileup (a small fixed grid) walks the list
     int64_t n_reads;
     const uint8_t *ref;
     int64_t ref_start, ref_len;

@@ -491,10 +491,17 @@ k_pileup(PileupArgs a) {
     // constant cache would serialise
     __shared__ uint2 s_lut[17];
 
-    const int tile = blockIdx.x;
     const int tid = threadIdx.x;
-    // replay pass behind k_tilet: only the 512-position tiles it flagged
-    if (a.tile_redo && a.tile_redo[(int64_t)tile * PSS_TILE / PSS_TTILE] == 0) return;
+    // The replay pass behind k_tilet (a.redo != NULL) runs on a small fixed grid: a.redo[0] = number of flagged
+    // 256-position tiles, a.redo[1..] = their indices, CTA b takes entries b, b + gridDim.x, ...  (One CTA per tile of the
+    // range, returning at once for the unflagged ones, cost 0.75 ms per 50 Mb in block launches alone -- a quarter of
+    // tlen_strand.)  An ordinary launch has one tile per CTA and runs the loop body once.
+    const int n_mine = a.redo ? a.redo[0] : (int)gridDim.x;
+    if (STAGED && tid == 0) mbar_init(&s_bar, 1);
+    if (tid < 17) s_lut[tid] = c_var_lut[tid];
+    uint32_t parity = 0;          // every bulk-copy phase issued below is waited for exactly once: the parity carries over
+    for (int it = blockIdx.x; it < n_mine; it += gridDim.x) {
+    const int tile = a.redo ? a.redo[1 + it] : it;
     const int64_t t0 = a.start + (int64_t)tile * PSS_TILE;
     const int64_t pl = t0 + tid;
     const bool valid = pl < a.end;
@@ -536,11 +543,8 @@ k_pileup(PileupArgs a) {
         } else mbar_arrive_expect_tx(&s_bar, 0);
     };
 
-    if (STAGED && tid == 0) {
-        mbar_init(&s_bar, 1);
-        issue(rng.x);
-    }
-    if (tid < 17) s_lut[tid] = c_var_lut[tid];
+    __syncthreads();              // barrier initialised (first round) / everyone done with the staging buffers (later rounds)
+    if (STAGED && tid == 0 && rng.x < rng.y) issue(rng.x);
     ACC acc;
     acc.init();
     acc.setup(s_lut);
@@ -558,7 +562,6 @@ k_pileup(PileupArgs a) {
     bool raw = false;
     bool done = false;
     int nproc = 0;
-    uint32_t parity = 0;
     for (int base = rng.x; base < rng.y;) {
         int cnt;
         if (STAGED) {
@@ -619,6 +622,7 @@ k_pileup(PileupArgs a) {
     if (valid) {
         acc.store(a.out + (pl - a.start), a.out_stride);
         a.rowmask[pl - a.start] = raw ? 1 : 0;
+    }
     }
 }
 

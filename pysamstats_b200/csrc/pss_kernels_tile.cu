@@ -2251,6 +2251,7 @@ k_tilem(TileArgs A) {
 // word arrays of TT: nfwd[0] nrev[1] | class c = paired fwd, paired rev, pp fwd, pp rev: n[2 + c] (32-bit
 // difference arrays) | sum[c] 64-bit at words 6.., sumsq[c] 64-bit at words 14.. (64-bit difference arrays)
 #define TLEN_NW 22
+static_assert(PSS_TTILE == 2 * PSS_TILE, "k_tilet hands the two halves of its tile to the replay kernel");
 #define TLEN_NT 256
 #ifndef TLEN_CTAS
 #define TLEN_CTAS 4           // 52 KB of shared memory per CTA: a fourth fits (tlen_strand 5.49 -> 4.92 ms per 50 Mb)
@@ -2382,7 +2383,7 @@ __device__ __forceinline__ TlenOut tlen_class(unsigned n, long long S, unsigned 
 
 template <int STAT>
 __global__ void __launch_bounds__(TLEN_NT, TLEN_CTAS)
-k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ tile_redo, float force) {
+k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo, float force) {
     constexpr int NWARPS = TLEN_NT / 32;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
@@ -2583,7 +2584,14 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ tile
     }
     if (amb) s_amb = 1;
     __syncthreads();
-    if (tid == 0 && s_amb) tile_redo[tile] = 1;
+    if (tid == 0 && s_amb) {
+        // both 256-position halves of this tile go on the replay list (redo[0] = its length)
+        const int g0 = 2 * tile, gtiles = (int)((A.end - A.start + PSS_TILE - 1) / PSS_TILE);
+        const int two = g0 + 1 < gtiles ? 1 : 0;
+        const int k = atomicAdd(redo, 1 + two);
+        redo[1 + k] = g0;
+        if (two) redo[2 + k] = g0 + 1;
+    }
 }
 
 // ------------------------------------------------------- descriptors + packed reference
@@ -2768,7 +2776,7 @@ bool tile_kernel_counting(int stat) {
     }
 }
 
-size_t tile_redo_bytes(int64_t ntiles) { return sizeof(int32_t) * (size_t)ntiles; }
+size_t tile_redo_bytes(int64_t ntiles) { return sizeof(int32_t) * (size_t)(2 * ntiles + 2); }    // length + two halves per tile
 
 template <int STAT>
 static cudaError_t launch_tilet_one(const TileArgs &a, const int32_t *tlen, int32_t *redo, int64_t ntiles, cudaStream_t s) {
@@ -2881,8 +2889,8 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
                                       : launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND>(a, ntiles, s); break;
     case PSS_BASEQ_EXT: e = launch_tileq_one<KIND_BQX, PSS_BASEQ_EXT>(a, ntiles, s); break;
     case PSS_BASEQ_EXT_STRAND: e = launch_tileq_one<KIND_BQX, PSS_BASEQ_EXT_STRAND>(a, ntiles, s); break;
-    case PSS_TLEN: e = launch_tilet_one<PSS_TLEN>(a, p.tlen, p.tile_redo, ntiles, s); break;
-    case PSS_TLEN_STRAND: e = launch_tilet_one<PSS_TLEN_STRAND>(a, p.tlen, p.tile_redo, ntiles, s); break;
+    case PSS_TLEN: e = launch_tilet_one<PSS_TLEN>(a, p.tlen, p.redo, ntiles, s); break;
+    case PSS_TLEN_STRAND: e = launch_tilet_one<PSS_TLEN_STRAND>(a, p.tlen, p.redo, ntiles, s); break;
     default: e = cudaErrorInvalidValue;
     }
     if (e1) cudaEventRecord(e1, s);
