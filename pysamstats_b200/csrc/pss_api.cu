@@ -362,10 +362,9 @@ static int run_range(pss_ctx *ctx, const pss_reads *R, const pss_pileup_params *
             // the in-order Welford replay for the tiles whose std_tlen is too close to a rounding boundary to be
             // decided from the exact sums: a fixed small grid walking the list k_tilet wrote
             const int64_t gtiles = (npos + PSS_TILE - 1) / PSS_TILE;
-            if ((rc = ensure(ctx, ctx->rng, sizeof(int2) * (size_t)gtiles)) != PSS_OK) return rc;
-            CU(launch_tile_ranges((const RInfo *)ctx->ri.p, R->n_reads, (const SmallState *)ctx->small.p, start, gtiles,
-                                  PSS_TILE, (int2 *)ctx->rng.p, s, &ctx->launches));
-            a.tile_rng = (const int2 *)ctx->rng.p;
+            // candidate reads of a listed 256-position tile: those of the 512-position tile it is half of, straight from
+            // the tile kernel's descriptors (a superset in file order is all the replay needs)
+            a.tile_rng = (const int2 *)ctx->tdesc.p;
             CU(launch_pileup(P->stat, a, gtiles < 1184 ? gtiles : 1184, true, s, &ctx->launches));     // 148 SMs x 8
             a.redo = nullptr;
         }

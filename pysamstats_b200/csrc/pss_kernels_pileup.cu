@@ -507,7 +507,8 @@ k_pileup(PileupArgs a) {
     const bool valid = pl < a.end;
     const int p = (int)pl;
     const int w0 = (int)(t0 + (tid & ~31)), w1 = w0 + 32;
-    const int2 rng = a.tile_rng[tile];
+    // (replay: the first eight bytes of the 48-byte descriptor of the 512-position tile this one is half of)
+    const int2 rng = a.redo ? a.tile_rng[(size_t)(tile >> 1) * 6] : a.tile_rng[tile];
     const bool need_seq = ACC::REF, need_qual = a.qual != nullptr, need_tlen = a.tlen != nullptr;
 
     // one chunk: thread 0 sizes it and issues the bulk copies

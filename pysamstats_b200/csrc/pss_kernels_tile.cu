@@ -32,6 +32,7 @@
 #include "pss_imax.cuh"
 #include "pss_lowq.cuh"
 
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
@@ -117,6 +118,9 @@ struct __align__(16) TileDesc {
     int64_t cig_lo;      // CIGAR word span of the first chunk, cig_hi == cig_lo: not staged
     int64_t cig_hi;
 };
+
+static_assert(sizeof(TileDesc) == 48 && offsetof(TileDesc, x) == 0 && offsetof(TileDesc, y) == 4,
+              "the tlen replay (k_pileup) reads a tile's candidate range as the int2 at the start of its descriptor");
 
 struct TileArgs {
     const RInfo *ri;
@@ -1365,7 +1369,7 @@ k_tile(TileArgs A) {
 // pass whatever its depth: root mean squares are not additive over passes.
 // rec() is fused as in k_tile; the fp64 rootmean (opt.pyx:2159-2163) is evaluated per field.
 
-enum { KIND_MAPQ = 3, KIND_BQ = 4, KIND_BQX = 5 };
+enum { KIND_BQ = 4, KIND_BQX = 5 };          // (3 was mapq on this kernel until k_tilem below)
 #ifndef QCH
 #define QCH 160                        // reads staged per chunk (a 512-position tile of 30x / 150 bp has ~135 candidates)
 #endif
@@ -1379,12 +1383,10 @@ enum { KIND_MAPQ = 3, KIND_BQ = 4, KIND_BQX = 5 };
 #endif
 
 // word arrays of TT (bank = rev | pp << 1):
-//   KIND_MAPQ  n[0..3] nz[4..7] sqlo[8..11] sqhi[12..15] (difference arrays)  max[16..19]
 //   KIND_BQ    n[0..3] nnd[4..7] (difference arrays)  sq64[8..15]
 //   KIND_BQX   n[0..3] match[4..7] (difference arrays)  mmt[8..11]  sq64[12..19]  sqmm64[20..27]   (LayBqx)
 template <int KIND> struct QKind;
 // NT: threads per CTA (the first 8 warps gather; baseq_ext wants two threads per staged read in the scatter)
-template <> struct QKind<KIND_MAPQ> { static const int NDIFF = 16, NWORDS = 20, SQ = 0, NT = 256, CTAS = 4; static const bool QUAL = false, SEQ = false, CIG = false; };
 template <> struct QKind<KIND_BQ> { static const int NDIFF = 8, NWORDS = 16, SQ = 8, NT = 256, CTAS = BQ_CTAS; static const bool QUAL = true, SEQ = false, CIG = true; };
 template <> struct QKind<KIND_BQX> { static const int NDIFF = 8, NWORDS = 28, SQ = 12, NT = 320, CTAS = 2; static const bool QUAL = true, SEQ = true, CIG = true; };
 
@@ -1605,16 +1607,7 @@ k_tileq(TileArgs A) {
                 if (rawp) interval_add(rawp, r.pos, r.end - r.pos, T.t0, 1u);
                 if (cls & CLS_COUNTED) {
                     const int bank = cls & 3u;
-                    if (KIND == KIND_MAPQ) {       // every event of the column counts, deletions included (opt.pyx:927-937)
-                        const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u;
-                        interval_add(cnt + bank * TT, r.pos, r.end - r.pos, T.t0, 1u);
-                        if (q == 0) interval_add(cnt + (4 + bank) * TT, r.pos, r.end - r.pos, T.t0, 1u);
-                        else {
-                            const uint32_t sq = q * q;
-                            if (sq & 255u) interval_add(cnt + (8 + bank) * TT, r.pos, r.end - r.pos, T.t0, sq & 255u);
-                            if (sq >> 8) interval_add(cnt + (12 + bank) * TT, r.pos, r.end - r.pos, T.t0, sq >> 8);
-                        }
-                    } else if (minq && !(cls & CLS_HASSEQ)) {
+                    if (minq && !(cls & CLS_HASSEQ)) {
                         // KIND_BQ under min_baseq, no sequence: quality 0 at every base -- only the deletion / ref-skip events remain
                         if (!T.no_del) {
                             if (cls & CLS_NOREF) interval_add(cnt + bank * TT, r.pos, 1, T.t0, 1u);
@@ -1673,48 +1666,43 @@ k_tileq(TileArgs A) {
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_ri[mid].pos < key) lo = mid + 1; else hi = mid; }
                 j = lo + (((lo ^ cb) & 1) != gpar);     // parity of the read's index in the batch
             }
-            // the record of the next read is loaded before the current one is processed (its latency
-            // hides behind the span work); s_ri has room for the read past the last one
-            uint4 h = *reinterpret_cast<const uint4 *>(&s_ri[min(j, QCH - 1)]);     // pos, end, cls, n_cigar
-            long long qo = K::QUAL ? s_qoff[min(j, QCH - 1) + qskew] : 0;
-            for (; j < n; j += 2) {
-                const int rpos = (int)h.x, rend = (int)h.y, nc = (int)h.w;
-                const uint32_t cls = h.z;
-                const long long qoff = qo;
-                const int jj = j;
-                {
-                    const int jn = min(j + 2, QCH - 1);
-                    h = *reinterpret_cast<const uint4 *>(&s_ri[jn]);
-                    if (K::QUAL) qo = s_qoff[jn + qskew];
+            // Thirty-two reads of this warp's parity at a time: lane k decodes read j + 2 k into four words -- start, end
+            // (INT_MIN when the read has no base event to give: not counted, no sequence i.e. quality 0, no reference
+            // span), offset of its qualities in the staged bytes, bank | simple << 2 -- and the warp then takes the
+            // reads in file order with one shuffle per word.  (The first form loaded and decoded every record in every
+            // lane: 19 of the 63 instructions per read and window, ncu r2b6.)
+            bool past = false;
+            for (; j < n && !past; j += 64) {
+                const int mine = j + 2 * lane;
+                int l_pos = 0x7fffffff, l_end = (int)0x80000000, l_qb = 0, l_fl = 0;
+                if (mine < n) {
+                    const uint4 h = *reinterpret_cast<const uint4 *>(&s_ri[mine]);     // pos, end, cls, n_cigar
+                    const bool gives = (h.z & (CLS_COUNTED | CLS_HASSEQ | CLS_NOREF)) == (CLS_COUNTED | CLS_HASSEQ);
+                    l_pos = (int)h.x;
+                    l_end = gives ? (int)h.y : (int)0x80000000;
+                    l_qb = (int)(s_qoff[mine + qskew] - quallo);
+                    l_fl = (int)(h.z & 3u) | ((h.z & CLS_SIMPLE) ? 4 : 0);
                 }
-                if (rpos >= gw1) break;
-                const int bank = cls & 3u;
-                if (KIND == KIND_MAPQ) {
-                    const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u;
-                    if (rend <= gw0 || !(cls & CLS_COUNTED) || q == 0) continue;
-                    const int off0 = gp0 - rpos, l = rend - rpos;
-#define QMAX(B) _Pragma("unroll") for (int i = 0; i < 4; ++i) if ((unsigned)(off0 + i) < (unsigned)l) acc[B][i] = max(acc[B][i], q);
-                    switch (bank) {
-                    case 0: QMAX(0) break;
-                    case 1: QMAX(1) break;
-                    case 2: QMAX(2) break;
-                    default: QMAX(3) break;
-                    }
-#undef QMAX
-                } else {
-                    // counted, with sequence (else quality 0) and with bases at all
-                    if (rend <= gw0 || (cls & (CLS_COUNTED | CLS_HASSEQ | CLS_NOREF)) != (CLS_COUNTED | CLS_HASSEQ)) continue;
-                    const uint8_t *qual = s_qual + (int)(qoff - quallo);
+                const int cnt32 = min(32, (n - j + 1) >> 1);
+                for (int k = 0; k < cnt32; ++k) {
+                    const int rpos = __shfl_sync(FULL, l_pos, k), rend = __shfl_sync(FULL, l_end, k);
+                    if (rpos >= gw1) { past = true; break; }       // (warp-uniform: every lane holds the same read)
+                    if (rend <= gw0) continue;
+                    const int fl = __shfl_sync(FULL, l_fl, k);
+                    const uint8_t *qual = s_qual + __shfl_sync(FULL, l_qb, k);
+                    const int bank = fl & 3;
 #define QSPAN(B, x, l, y) q_gather_span<B, MINQ>(acc, qual, gp0, x, l, y, gminq)
 #define QSPANS(x, l, y) do { switch (bank) { case 0: QSPAN(0, x, l, y); break; case 1: QSPAN(1, x, l, y); break; \
                                              case 2: QSPAN(2, x, l, y); break; default: QSPAN(3, x, l, y); break; } } while (0)
-                    if (cls & CLS_SIMPLE) QSPANS(rpos, rend - rpos, 0);
+                    if (fl & 4) QSPANS(rpos, rend - rpos, 0);
                     else {
-                        const long long co = (long long)(((uint64_t)s_ri[jj].cigar_off));
+                        const RInfo &rr = s_ri[j + 2 * k];
+                        const int nc = (int)rr.n_cigar;
+                        const long long co = rr.cigar_off;
                         const uint32_t *cg = ciglo >= 0 ? s_cig + (co - ciglo) : A.cigar + co;
                         int x = rpos, y = 0;
-                        for (int k = 0; k < nc && x < gw1; ++k) {
-                            const uint32_t w = cg[k];
+                        for (int c = 0; c < nc && x < gw1; ++c) {
+                            const uint32_t w = cg[c];
                             const int op = w & 15, l = (int)(w >> 4);
                             if (op_is_match(op)) {
                                 if (x + l > gw0) QSPANS(x, l, y);
@@ -1741,8 +1729,7 @@ k_tileq(TileArgs A) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (acc[b][i]) {
-                    if (KIND == KIND_MAPQ) atomicMax(cnt + (16 + b) * TT + pi + i, acc[b][i]);
-                    else atomicAdd(reinterpret_cast<unsigned long long *>(cnt + K::SQ * TT) + b * TT + pi + i,
+                    atomicAdd(reinterpret_cast<unsigned long long *>(cnt + K::SQ * TT) + b * TT + pi + i,
                                    (unsigned long long)acc[b][i]);
                 }
     }
@@ -1763,30 +1750,7 @@ k_tileq(TileArgs A) {
         uint32_t nb[4], N[6];
 #pragma unroll
         for (int b = 0; b < 4; ++b) nb[b] = cnt[b * TT + p];
-        if (KIND == KIND_MAPQ) {
-            uint32_t zb[4], mb[4], Z[6];
-            unsigned long long sb[4], S[6];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                zb[b] = cnt[(4 + b) * TT + p];
-                sb[b] = (unsigned long long)cnt[(8 + b) * TT + p] + ((unsigned long long)cnt[(12 + b) * TT + p] << 8);
-                mb[b] = cnt[(16 + b) * TT + p];
-            }
-            six32(nb, N); six32(zb, Z); six64(sb, S);
-            const uint32_t M[6] = {max(max(mb[0], mb[1]), max(mb[2], mb[3])), max(mb[0], mb[2]), max(mb[1], mb[3]),
-                                   max(mb[2], mb[3]), mb[2], mb[3]};
-            if (STAT == PSS_MAPQ) {
-                o[0] = N[0]; o[st] = N[3]; o[2 * st] = Z[0]; o[3 * st] = Z[3];
-                o[4 * st] = q_rootmean_scr(S[0], N[0]); o[5 * st] = q_rootmean_scr(S[3], N[3]);
-                o[6 * st] = M[0]; o[7 * st] = M[3];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    o[k * st] = N[k]; o[(6 + k) * st] = Z[k];
-                    o[(12 + k) * st] = q_rootmean_scr(S[k], N[k]); o[(18 + k) * st] = M[k];
-                }
-            }
-        } else {
+        {
             uint32_t db[4], D[6];
             unsigned long long sb[4], S[6];
 #pragma unroll
@@ -2806,12 +2770,6 @@ bool tile_kernel_supports(int stat, int min_baseq, int no_del) {
     }
 }
 
-// PSS_MAPQ_GATHER=1: the round-1 position-owned gather (k_tileq<KIND_MAPQ>) where it applies, for A / B timing
-static bool mapq_gather(const TileArgs &a) {
-    static const bool want = getenv("PSS_MAPQ_GATHER") != nullptr;
-    return want && !a.lowq && !a.no_del;
-}
-
 size_t tile_desc_bytes(int64_t ntiles) { return sizeof(TileDesc) * (size_t)ntiles; }
 size_t tile_refpack_bytes(int64_t ntiles) { return ((size_t)ntiles * REFN_WORDS + 8 + (size_t)ntiles) * 4; }   // packed reference + tile flags
 
@@ -2878,12 +2836,8 @@ cudaError_t launch_tile(int stat, const PileupArgs &p, const int64_t *seq_off, i
     case PSS_COVERAGE_EXT_STRAND: e = launch_tile_one<KIND_EXT, PSS_COVERAGE_EXT_STRAND>(a, ntiles, s); break;
     case PSS_VARIATION: e = launch_tile_one<KIND_VAR1, PSS_VARIATION>(a, ntiles, s); break;
     case PSS_VARIATION_STRAND: e = launch_tile_one<KIND_VAR, PSS_VARIATION_STRAND>(a, ntiles, s); break;
-    case PSS_MAPQ:
-        e = mapq_gather(a) ? launch_tileq_one<KIND_MAPQ, PSS_MAPQ>(a, ntiles, s) : launch_tilem_one<PSS_MAPQ>(a, ntiles, s);
-        break;
-    case PSS_MAPQ_STRAND:
-        e = mapq_gather(a) ? launch_tileq_one<KIND_MAPQ, PSS_MAPQ_STRAND>(a, ntiles, s) : launch_tilem_one<PSS_MAPQ_STRAND>(a, ntiles, s);
-        break;
+    case PSS_MAPQ: e = launch_tilem_one<PSS_MAPQ>(a, ntiles, s); break;
+    case PSS_MAPQ_STRAND: e = launch_tilem_one<PSS_MAPQ_STRAND>(a, ntiles, s); break;
     case PSS_BASEQ: e = a.lowq ? launch_tileq_one<KIND_BQ, PSS_BASEQ, true>(a, ntiles, s) : launch_tileq_one<KIND_BQ, PSS_BASEQ>(a, ntiles, s); break;
     case PSS_BASEQ_STRAND: e = a.lowq ? launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND, true>(a, ntiles, s)
                                       : launch_tileq_one<KIND_BQ, PSS_BASEQ_STRAND>(a, ntiles, s); break;
