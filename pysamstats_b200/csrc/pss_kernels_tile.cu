@@ -1666,43 +1666,38 @@ k_tileq(TileArgs A) {
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_ri[mid].pos < key) lo = mid + 1; else hi = mid; }
                 j = lo + (((lo ^ cb) & 1) != gpar);     // parity of the read's index in the batch
             }
-            // Thirty-two reads of this warp's parity at a time: lane k decodes read j + 2 k into four words -- start, end
-            // (INT_MIN when the read has no base event to give: not counted, no sequence i.e. quality 0, no reference
-            // span), offset of its qualities in the staged bytes, bank | simple << 2 -- and the warp then takes the
-            // reads in file order with one shuffle per word.  (The first form loaded and decoded every record in every
-            // lane: 19 of the 63 instructions per read and window, ncu r2b6.)
-            bool past = false;
-            for (; j < n && !past; j += 64) {
-                const int mine = j + 2 * lane;
-                int l_pos = 0x7fffffff, l_end = (int)0x80000000, l_qb = 0, l_fl = 0;
-                if (mine < n) {
-                    const uint4 h = *reinterpret_cast<const uint4 *>(&s_ri[mine]);     // pos, end, cls, n_cigar
-                    const bool gives = (h.z & (CLS_COUNTED | CLS_HASSEQ | CLS_NOREF)) == (CLS_COUNTED | CLS_HASSEQ);
-                    l_pos = (int)h.x;
-                    l_end = gives ? (int)h.y : (int)0x80000000;
-                    l_qb = (int)(s_qoff[mine + qskew] - quallo);
-                    l_fl = (int)(h.z & 3u) | ((h.z & CLS_SIMPLE) ? 4 : 0);
+            // the record of the next read is loaded before the current one is processed (its latency
+            // hides behind the span work); s_ri has room for the read past the last one.  (Decoding 32 reads once, one
+            // per lane, and broadcasting the four words a read needs by shuffles was measured: fewer instructions, but
+            // the shuffle -> compare -> branch chain is exposed -- baseq 2.84 -> 2.90 ms, baseq_ext 5.69 -> 6.20 ms.)
+            uint4 h = *reinterpret_cast<const uint4 *>(&s_ri[min(j, QCH - 1)]);     // pos, end, cls, n_cigar
+            long long qo = K::QUAL ? s_qoff[min(j, QCH - 1) + qskew] : 0;
+            for (; j < n; j += 2) {
+                const int rpos = (int)h.x, rend = (int)h.y, nc = (int)h.w;
+                const uint32_t cls = h.z;
+                const long long qoff = qo;
+                const int jj = j;
+                {
+                    const int jn = min(j + 2, QCH - 1);
+                    h = *reinterpret_cast<const uint4 *>(&s_ri[jn]);
+                    if (K::QUAL) qo = s_qoff[jn + qskew];
                 }
-                const int cnt32 = min(32, (n - j + 1) >> 1);
-                for (int k = 0; k < cnt32; ++k) {
-                    const int rpos = __shfl_sync(FULL, l_pos, k), rend = __shfl_sync(FULL, l_end, k);
-                    if (rpos >= gw1) { past = true; break; }       // (warp-uniform: every lane holds the same read)
-                    if (rend <= gw0) continue;
-                    const int fl = __shfl_sync(FULL, l_fl, k);
-                    const uint8_t *qual = s_qual + __shfl_sync(FULL, l_qb, k);
-                    const int bank = fl & 3;
+                if (rpos >= gw1) break;
+                const int bank = cls & 3u;
+                {
+                    // counted, with sequence (else quality 0) and with bases at all
+                    if (rend <= gw0 || (cls & (CLS_COUNTED | CLS_HASSEQ | CLS_NOREF)) != (CLS_COUNTED | CLS_HASSEQ)) continue;
+                    const uint8_t *qual = s_qual + (int)(qoff - quallo);
 #define QSPAN(B, x, l, y) q_gather_span<B, MINQ>(acc, qual, gp0, x, l, y, gminq)
 #define QSPANS(x, l, y) do { switch (bank) { case 0: QSPAN(0, x, l, y); break; case 1: QSPAN(1, x, l, y); break; \
                                              case 2: QSPAN(2, x, l, y); break; default: QSPAN(3, x, l, y); break; } } while (0)
-                    if (fl & 4) QSPANS(rpos, rend - rpos, 0);
+                    if (cls & CLS_SIMPLE) QSPANS(rpos, rend - rpos, 0);
                     else {
-                        const RInfo &rr = s_ri[j + 2 * k];
-                        const int nc = (int)rr.n_cigar;
-                        const long long co = rr.cigar_off;
+                        const long long co = (long long)(((uint64_t)s_ri[jj].cigar_off));
                         const uint32_t *cg = ciglo >= 0 ? s_cig + (co - ciglo) : A.cigar + co;
                         int x = rpos, y = 0;
-                        for (int c = 0; c < nc && x < gw1; ++c) {
-                            const uint32_t w = cg[c];
+                        for (int k = 0; k < nc && x < gw1; ++k) {
+                            const uint32_t w = cg[k];
                             const int op = w & 15, l = (int)(w >> 4);
                             if (op_is_match(op)) {
                                 if (x + l > gw0) QSPANS(x, l, y);
