@@ -1808,25 +1808,27 @@ k_tileq(TileArgs A) {
 // (k_tileq<KIND_MAPQ> walked every read once per 128-position window it reaches: 21 thousand warp instructions per
 // tile for mapq_strand, about two thirds of them in the gather).
 //
-// Counters (bank = rev | pp << 1), words of shared memory:
+// Counters (NBK banks: rev | pp << 1 for mapq_strand, pp for mapq), words of shared memory:
 //   a tile with at most 65535 candidate reads ("shallow": every tile of ordinary sequencing depth)
-//       [bank][TT]      n | nz << 16   -- neither half can exceed the candidate count
-//       [4 + bank][TT]  sum(mapq^2)    -- <= 65535 * 255^2 < 2^32
-//   a deeper tile: the same 8 TT words hold SIXTEEN arrays of TT / 2 positions (n, nz, the low byte plane and the high
+//       [bank][TT]        n | nz << 16   -- neither half can exceed the candidate count
+//       [NBK + bank][TT]  sum(mapq^2)    -- <= 65535 * 255^2 < 2^32
+//   a deeper tile: the same 2 NBK TT words hold 4 NBK arrays of TT / 2 positions (n, nz, the low byte plane and the high
 //       plane of sum(mapq^2), 32-bit each, as k_tileq kept them) and the tile is done in two sweeps over its reads,
 //       one per half of its positions -- root mean squares are not additive over passes of reads, but the positions
 //       of a tile are independent of each other;
 //   sfx / pfx / pt [bank][TT], tab [level][bank][32]: the interval maxima, always over the whole tile (first sweep).
-#define MQ_CH 160                      // reads staged per chunk (a 512-position tile of 30x / 150 bp has ~135 candidates)
-#define MQ_NT 256
-#ifndef MQ_CTAS
-#define MQ_CTAS 4
-#endif
+// mapq_strand: banks rev | pp << 1, 256 threads x 4 CTAs per SM (47 KB of shared memory each).  mapq reports all / pp only:
+// TWO banks (pp or not) -- half the arrays to zero, scan and resolve, 27 KB -- and 128 threads x 8 CTAs per SM: the phases
+// of a tile are short and separated by block barriers, so more, smaller CTAs cover each other's barriers better (ncu of
+// the four-bank form on mapq: 2.9 warps per issue waiting at barriers, 44 % of the warp slots active).
+template <int STAT> struct MqCfg { static const int NBK = 4, NT = 256, CTAS = 4, CH = 160; };     // CH: reads staged per chunk
+template <> struct MqCfg<PSS_MAPQ> { static const int NBK = 2, NT = 128, CTAS = 8, CH = 136; };  // (a tile of 30x / 150 bp has ~135 candidates)
 #define MQ_NB (TT / IMAX_BLK)          // blocks per tile: one lane each in the resolution
 #define MQ_NLEV 6                      // table levels 0 .. log2(MQ_NB)
 #define MQ_PS (TT + TT / 8)            // = imax_padded(TT): words of one bank's sfx / pfx / pt array (position p at imax_idx(p))
 static_assert(MQ_NB == 32 && imax_levels(MQ_NB) == MQ_NLEV && MQ_PS == imax_padded(TT), "one warp resolves a bank: 32 blocks of 16 positions");
-#define MQ_WORDS (8 * TT + 12 * MQ_PS + MQ_NLEV * 4 * MQ_NB)      // cnt 8 TT | sfx 4 PS | pfx 4 PS | pt 4 PS | tab
+// words of shared memory for NBK banks: cnt 2 NBK TT | sfx NBK PS | pfx NBK PS | pt NBK PS | tab [level][bank][32]
+__host__ __device__ constexpr int mq_words(int nbk) { return 2 * nbk * TT + 3 * nbk * MQ_PS + MQ_NLEV * nbk * MQ_NB; }
 
 // shared-memory reductions by explicit state space: mq_emit below is deliberately NOT inlined (one copy instead of one per
 // CIGAR case of the read walk), and through a generic pointer the compiler would emit generic atomics
@@ -1841,6 +1843,7 @@ struct AtomicMaxOp {
 
 // One interval of events of a read -- reference positions [x, x + l) -- into the counters of the sweep's window
 // [h0, h0 + tw) and (first sweep) into the tile's interval maxima.  flags: deep | first sweep << 1 | bank << 2.
+template <int NBK>
 __device__ __noinline__ void mq_emit(uint32_t *cnt, int tw, int h0, int t0, uint32_t flags, uint32_t q, int x, int l) {
     const bool deep = flags & 1u;
     const int bank = (int)(flags >> 2);
@@ -1853,7 +1856,7 @@ __device__ __noinline__ void mq_emit(uint32_t *cnt, int tw, int h0, int t0, uint
             sred_add(p + a, inc);
             if (b < tw) sred_add(p + b, 0u - inc);
             if (q) {
-                p += 4 * tw;
+                p += NBK * tw;
                 sred_add(p + a, sq);
                 if (b < tw) sred_add(p + b, 0u - sq);
             }
@@ -1861,35 +1864,37 @@ __device__ __noinline__ void mq_emit(uint32_t *cnt, int tw, int h0, int t0, uint
             sred_add(p + a, 1u);
             if (b < tw) sred_add(p + b, 0u - 1u);
             if (!q) {
-                p += 4 * tw;
+                p += NBK * tw;
                 sred_add(p + a, 1u);
                 if (b < tw) sred_add(p + b, 0u - 1u);
             } else {
                 const uint32_t lo = sq & 255u, hi = sq >> 8;
-                if (lo) { uint32_t *pl = p + 8 * tw; sred_add(pl + a, lo); if (b < tw) sred_add(pl + b, 0u - lo); }
-                if (hi) { uint32_t *ph = p + 12 * tw; sred_add(ph + a, hi); if (b < tw) sred_add(ph + b, 0u - hi); }
+                if (lo) { uint32_t *pl = p + 2 * NBK * tw; sred_add(pl + a, lo); if (b < tw) sred_add(pl + b, 0u - lo); }
+                if (hi) { uint32_t *ph = p + 3 * NBK * tw; sred_add(ph + a, hi); if (b < tw) sred_add(ph + b, 0u - hi); }
             }
         }
     }
     if ((flags & 2u) && q) {
         const int a2 = max(x - t0, 0), b2 = min(x + l - t0, TT);
         if (a2 < b2) {
-            uint32_t *sfx = cnt + 8 * TT + bank * MQ_PS;
-            imax_update(a2, b2, q, sfx, sfx + 4 * MQ_PS, sfx + 8 * MQ_PS, cnt + 8 * TT + 12 * MQ_PS + bank * MQ_NB, 4 * MQ_NB,
-                        AtomicMaxOp());
+            uint32_t *sfx = cnt + 2 * NBK * TT + bank * MQ_PS;
+            imax_update(a2, b2, q, sfx, sfx + NBK * MQ_PS, sfx + 2 * NBK * MQ_PS, cnt + 2 * NBK * TT + 3 * NBK * MQ_PS + bank * MQ_NB,
+                        NBK * MQ_NB, AtomicMaxOp());
         }
     }
 }
 __device__ __forceinline__ uint4 max4(uint4 a, uint4 b) { return make_uint4(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z), max(a.w, b.w)); }
 
 // Four positions of a bank's counters (cq = cnt + 4 quad; counter arrays are tw words apart): n, nz, and the root mean
-// square over the banks of MASK (CountPpStrand: all 0b1111, fwd 0b0101, rev 0b1010, pp 0b1100, pp_fwd 0b0100, pp_rev 0b1000).
+// square over the banks of MASK (four banks, CountPpStrand: all 0b1111, fwd 0b0101, rev 0b1010, pp 0b1100, pp_fwd 0b0100,
+// pp_rev 0b1000; two banks: all 0b11, pp 0b10).
 __device__ __forceinline__ uint4 mq_ldn(const uint32_t *cq, int b, int tw, bool deep) {
     const uint4 w = *reinterpret_cast<const uint4 *>(cq + b * tw);
     return deep ? w : lo16(w);
 }
+template <int NBK>
 __device__ __forceinline__ uint4 mq_ldz(const uint32_t *cq, int b, int tw, bool deep) {
-    return deep ? *reinterpret_cast<const uint4 *>(cq + (4 + b) * tw) : hi16(*reinterpret_cast<const uint4 *>(cq + b * tw));
+    return deep ? *reinterpret_cast<const uint4 *>(cq + (NBK + b) * tw) : hi16(*reinterpret_cast<const uint4 *>(cq + b * tw));
 }
 // rootmean (opt.pyx:2159-2163) of a shallow tile: n <= 65535 and sq <= 255^2 n < 2^32, so the answer is at most 255.
 // A float estimate of sqrt(sq / n) is off by < 2e-4 there (two approximate operations, 2 ulp each, on values <= 255), so
@@ -1920,26 +1925,26 @@ __device__ __forceinline__ uint32_t mq_root32(uint32_t sq, uint32_t n) {
 }
 __device__ __noinline__ uint32_t mq_root_any(unsigned long long sq, uint32_t n) { return (uint32_t)q_rootmean(sq, n); }
 
-template <int MASK>
+template <int MASK, int NBK>
 __device__ __forceinline__ uint4 mq_rms(const uint32_t *cq, int tw, bool deep) {
     uint4 n = make_uint4(0, 0, 0, 0);
     if (!deep) {
         // all the reads of the tile together have sum(mapq^2) <= 65535 * 255^2 < 2^32: word sums over the banks
         uint4 s = n;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < NBK; ++b) {
             if (!((MASK >> b) & 1)) continue;
             n = n + lo16(*reinterpret_cast<const uint4 *>(cq + b * tw));
-            s = s + *reinterpret_cast<const uint4 *>(cq + (4 + b) * tw);
+            s = s + *reinterpret_cast<const uint4 *>(cq + (NBK + b) * tw);
         }
         return make_uint4(mq_root32(s.x, n.x), mq_root32(s.y, n.y), mq_root32(s.z, n.z), mq_root32(s.w, n.w));
     }
     unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll 1
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < NBK; ++b) {
         if (!((MASK >> b) & 1)) continue;
         n = n + *reinterpret_cast<const uint4 *>(cq + b * tw);
-        const uint4 l = *reinterpret_cast<const uint4 *>(cq + (8 + b) * tw), h = *reinterpret_cast<const uint4 *>(cq + (12 + b) * tw);
+        const uint4 l = *reinterpret_cast<const uint4 *>(cq + (2 * NBK + b) * tw), h = *reinterpret_cast<const uint4 *>(cq + (3 * NBK + b) * tw);
         s0 += l.x + ((unsigned long long)h.x << 8); s1 += l.y + ((unsigned long long)h.y << 8);
         s2 += l.z + ((unsigned long long)h.z << 8); s3 += l.w + ((unsigned long long)h.w << 8);
     }
@@ -1947,14 +1952,15 @@ __device__ __forceinline__ uint4 mq_rms(const uint32_t *cq, int tw, bool deep) {
 }
 
 template <int STAT, bool MINQ>
-__global__ void __launch_bounds__(MQ_NT, MQ_CTAS)
+__global__ void __launch_bounds__(MqCfg<STAT>::NT, MqCfg<STAT>::CTAS)
 k_tilem(TileArgs A) {
     constexpr bool STRAND = STAT == PSS_MAPQ_STRAND;
+    constexpr int NBK = MqCfg<STAT>::NBK, MQ_NT = MqCfg<STAT>::NT, MQ_CH = MqCfg<STAT>::CH, MQ_WORDS = mq_words(NBK);
     constexpr int NWARPS = MQ_NT / 32;
-    static_assert(MQ_NT >= MQ_CH && NWARPS == 8, "one scatter thread per staged read; eight warps share the scans");
+    static_assert(NWARPS == 2 * NBK && (NWARPS & (NWARPS - 1)) == 0, "a warp per counter array in the scans, a warp per bank in the resolution");
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *sfx = cnt + 8 * TT, *pfx = sfx + 4 * MQ_PS, *pt = pfx + 4 * MQ_PS, *tab = pt + 4 * MQ_PS;
+    uint32_t *sfx = cnt + 2 * NBK * TT, *pfx = sfx + NBK * MQ_PS, *pt = pfx + NBK * MQ_PS, *tab = pt + NBK * MQ_PS;
     uint32_t *raw = cnt + MQ_WORDS;                                          // exists only when need_raw
     RInfo *s_ri = reinterpret_cast<RInfo *>(raw + (A.need_raw ? TT : 0));
     __shared__ __align__(8) uint64_t s_bar;
@@ -2007,21 +2013,21 @@ k_tilem(TileArgs A) {
             parity ^= 1;
             const int n = s_n;
             if (n == 0) break;
-            if (tid < n) {
-                const RInfo r = s_ri[tid];
+            for (int ir = tid; ir < n; ir += MQ_NT) {
+                const RInfo r = s_ri[ir];
                 const uint32_t cls = r.cls;
                 if (cls & CLS_ADMITTED) {
-                    if (MINQ && (cls & CLS_COUNTED) && (cls & CLS_HASSEQ)) lowq_prefetch(A, r, cb + tid);
+                    if (MINQ && (cls & CLS_COUNTED) && (cls & CLS_HASSEQ)) lowq_prefetch(A, r, cb + ir);
                     if (rawp) {
                         const int a = max(r.pos - h0, 0), b = min(r.end - h0, tw);
                         if (a < b) { atomicAdd(rawp + a, 1u); if (b < tw) atomicAdd(rawp + b, 0u - 1u); }
                     }
                     if (cls & CLS_COUNTED) {
-                        const int bank = cls & 3u;
+                        const int bank = STRAND ? (int)(cls & 3u) : (int)((cls >> 1) & 1u);
                         const uint32_t q = (cls >> CLS_MAPQ_SHIFT) & 255u;
                         const uint32_t fl = (deep ? 1u : 0u) | (sweep == 0 ? 2u : 0u) | ((uint32_t)bank << 2);
                         // the read has an event at every position of the reference interval [x, x + l)
-                        auto emit = [&](int x, int l) { mq_emit(cnt, tw, h0, t0, fl, q, x, l); };
+                        auto emit = [&](int x, int l) { mq_emit<NBK>(cnt, tw, h0, t0, fl, q, x, l); };
                         if (!MINQ && !A.no_del) emit(r.pos, r.end - r.pos);              // M, D and N spans all count (opt.pyx:1904-1906)
                         else if (cls & CLS_NOREF) { if (!A.no_del) emit(r.pos, 1); }     // one deletion-like event at pos
                         else if (!MINQ && (cls & CLS_SIMPLE)) emit(r.pos, r.end - r.pos);
@@ -2029,7 +2035,7 @@ k_tilem(TileArgs A) {
                             // no_del: the aligned spans only; min_baseq: of those, the runs of bases at or above the threshold
                             // (a read without sequence has quality 0 everywhere: only its deletion / ref-skip events remain)
                             const bool bases = !MINQ || (cls & CLS_HASSEQ);
-                            const uint32_t *mw = MINQ ? A.lowq + (r.seq_off >> 4) + (cb + tid) : nullptr;
+                            const uint32_t *mw = MINQ ? A.lowq + (r.seq_off >> 4) + (cb + ir) : nullptr;
                             const uint32_t *cg = A.cigar + r.cigar_off;
                             const int nc = (int)r.n_cigar;
                             int x = r.pos, y = 0;
@@ -2058,10 +2064,10 @@ k_tilem(TileArgs A) {
         }
         __syncthreads();
         // ---- the maxima (first sweep): warp b resolves bank b, lane = block ----------------------------------
-        if (sweep == 0 && warp < 4) {
+        if (sweep == 0 && warp < NBK) {
             uint32_t v[MQ_NLEV];
 #pragma unroll
-            for (int k = 0; k < MQ_NLEV; ++k) v[k] = tab[(k * 4 + warp) * MQ_NB + lane];
+            for (int k = 0; k < MQ_NLEV; ++k) v[k] = tab[(k * NBK + warp) * MQ_NB + lane];
 #pragma unroll
             for (int k = MQ_NLEV - 1; k >= 1; --k) {       // push-down (imax_pushdown_ref with one lane per block)
                 const int h = 1 << (k - 1);
@@ -2098,9 +2104,9 @@ k_tilem(TileArgs A) {
                 tp[j] = t;
             }
         }
-        {   // prefix sums of the difference arrays (+ raw); warps 4-7 first: 0-3 have the maxima too
-            const int nsc = deep ? 16 : 8;
-            for (int a = (warp + 4) & 7; a < nsc + (A.need_raw ? 1 : 0); a += NWARPS) {
+        {   // prefix sums of the difference arrays (+ raw); the upper half of the warps first: the lower has the maxima too
+            const int nsc = deep ? 4 * NBK : 2 * NBK;
+            for (int a = (warp + NBK) & (NWARPS - 1); a < nsc + (A.need_raw ? 1 : 0); a += NWARPS) {
                 uint32_t *arr = a < nsc ? cnt + a * tw : raw;
                 if (deep) warp_scan_array<TT / 2>(arr, lane);
                 else warp_scan_array<TT>(arr, lane);
@@ -2133,14 +2139,15 @@ k_tilem(TileArgs A) {
                     // CountPpStrand order: all, fwd, rev, pp, pp_fwd, pp_rev = banks 0123, 02, 13, 23, 2, 3
                     if (STRAND) {
                         O.skip(12 + 3 * g);
-                        if (g == 0) { O.put(mq_rms<15>(cq, tw, deep)); O.put(mq_rms<5>(cq, tw, deep)); O.put(mq_rms<10>(cq, tw, deep)); }
-                        else { O.put(mq_rms<12>(cq, tw, deep)); O.put(mq_rms<4>(cq, tw, deep)); O.put(mq_rms<8>(cq, tw, deep)); }
+                        if (g == 0) { O.put(mq_rms<15, NBK>(cq, tw, deep)); O.put(mq_rms<5, NBK>(cq, tw, deep)); O.put(mq_rms<10, NBK>(cq, tw, deep)); }
+                        else { O.put(mq_rms<12, NBK>(cq, tw, deep)); O.put(mq_rms<4, NBK>(cq, tw, deep)); O.put(mq_rms<8, NBK>(cq, tw, deep)); }
                     } else {
+                        // two banks: not proper pair, proper pair
                         O.skip(4);
-                        O.put(mq_rms<15>(cq, tw, deep)); O.put(mq_rms<12>(cq, tw, deep));
+                        O.put(mq_rms<3, NBK>(cq, tw, deep)); O.put(mq_rms<2, NBK>(cq, tw, deep));
                         const uint4 *mp = reinterpret_cast<const uint4 *>(pt + imax_idx(sweep * tw + 4 * qd));
-                        const uint4 m_pp = max4(mp[2 * MQ_PS / 4], mp[3 * MQ_PS / 4]);
-                        O.put(max4(max4(mp[0], mp[MQ_PS / 4]), m_pp));
+                        const uint4 m_pp = mp[MQ_PS / 4];
+                        O.put(max4(mp[0], m_pp));
                         O.put(m_pp);
                     }
                 } else if (STRAND && g == 4) {
@@ -2152,17 +2159,18 @@ k_tilem(TileArgs A) {
                 } else {
                     // the counts: n (and the row mask), nz
                     const bool zs = STRAND && g == 3;            // this task writes the mapq == 0 counts
-                    uint4 c[4];
+                    uint4 c[NBK];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) c[b] = zs ? mq_ldz(cq, b, tw, deep) : mq_ldn(cq, b, tw, deep);
-                    const uint4 c_all = (c[0] + c[1]) + (c[2] + c[3]);
+                    for (int b = 0; b < NBK; ++b) c[b] = zs ? mq_ldz<NBK>(cq, b, tw, deep) : mq_ldn(cq, b, tw, deep);
+                    uint4 c_all = c[0] + c[1];
                     if (STRAND) {
+                        c_all = c_all + (c[NBK - 2] + c[NBK - 1]);
                         if (zs) O.skip(6);
-                        O.put(c_all); O.put(c[0] + c[2]); O.put(c[1] + c[3]); O.put(c[2] + c[3]); O.put(c[2]); O.put(c[3]);
+                        O.put(c_all); O.put(c[0] + c[NBK - 2]); O.put(c[1] + c[NBK - 1]); O.put(c[NBK - 2] + c[NBK - 1]); O.put(c[NBK - 2]); O.put(c[NBK - 1]);
                     } else {
-                        O.put(c_all); O.put(c[2] + c[3]);
-                        const uint4 z2 = mq_ldz(cq, 2, tw, deep), z3 = mq_ldz(cq, 3, tw, deep);
-                        O.put((mq_ldz(cq, 0, tw, deep) + mq_ldz(cq, 1, tw, deep)) + (z2 + z3)); O.put(z2 + z3);
+                        O.put(c_all); O.put(c[1]);
+                        const uint4 z1 = mq_ldz<NBK>(cq, 1, tw, deep);
+                        O.put(mq_ldz<NBK>(cq, 0, tw, deep) + z1); O.put(z1);
                     }
                     if (!zs) {
                         // the row mask: htslib emits a column wherever an admitted read has an event
@@ -2184,7 +2192,7 @@ k_tilem(TileArgs A) {
         __syncthreads();           // everyone is done with the counters of the first half
         {
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (int k = tid; k < 8 * TT / 4; k += MQ_NT) reinterpret_cast<uint4 *>(cnt)[k] = z;
+            for (int k = tid; k < 2 * NBK * TT / 4; k += MQ_NT) reinterpret_cast<uint4 *>(cnt)[k] = z;
             if (A.need_raw) for (int k = tid; k < TT / 4; k += MQ_NT) reinterpret_cast<uint4 *>(raw)[k] = z;
         }
         if (tid == 0) issue(dx);
@@ -2709,7 +2717,7 @@ static cudaError_t launch_tileq_one(const TileArgs &a, int64_t ntiles, cudaStrea
 
 template <int STAT>
 static cudaError_t launch_tilem_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
-    const size_t smem_max = (size_t)(MQ_WORDS + TT) * 4 + (size_t)MQ_CH * sizeof(RInfo);
+    const size_t smem_max = (size_t)(mq_words(MqCfg<STAT>::NBK) + TT) * 4 + (size_t)MqCfg<STAT>::CH * sizeof(RInfo);
     static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
     int dev__ = 0;
     cudaGetDevice(&dev__);
@@ -2721,8 +2729,8 @@ static cudaError_t launch_tilem_one(const TileArgs &a, int64_t ntiles, cudaStrea
         configured = true;
     }
     const size_t smem = smem_max - (a.need_raw ? 0 : (size_t)TT * 4);
-    if (a.lowq) k_tilem<STAT, true><<<(unsigned)ntiles, MQ_NT, smem, s>>>(a);
-    else k_tilem<STAT, false><<<(unsigned)ntiles, MQ_NT, smem, s>>>(a);
+    if (a.lowq) k_tilem<STAT, true><<<(unsigned)ntiles, MqCfg<STAT>::NT, smem, s>>>(a);
+    else k_tilem<STAT, false><<<(unsigned)ntiles, MqCfg<STAT>::NT, smem, s>>>(a);
     return cudaGetLastError();
 }
 
