@@ -1384,6 +1384,8 @@ enum { KIND_BQ = 4, KIND_BQX = 5 };          // (3 was mapq on this kernel until
 
 // word arrays of TT (bank = rev | pp << 1):
 //   KIND_BQ    n[0..3] nnd[4..7] (difference arrays)  sq64[8..15]
+//              baseq (no strand split in its output): TWO banks, pp or not -- n[0..1] nnd[2..3] sq64[4..7] -- half the
+//              arrays to zero, scan and finalise, half the gather's accumulators, and 50 KB per CTA: a fourth CTA per SM
 //   KIND_BQX   n[0..3] match[4..7] (difference arrays)  mmt[8..11]  sq64[12..19]  sqmm64[20..27]   (LayBqx)
 template <int KIND> struct QKind;
 // NT: threads per CTA (the first 8 warps gather; baseq_ext wants two threads per staged read in the scatter)
@@ -1393,10 +1395,13 @@ template <> struct QKind<KIND_BQX> { static const int NDIFF = 8, NWORDS = 28, SQ
 struct QSmem {       // byte offsets into the dynamic shared memory
     int raw, ri, qoff, refn, seq, qual, cig, total;
 };
-template <int KIND>
+// banks of a (kind, statistic), CTAs per SM it is compiled for
+template <int KIND, int STAT> struct QBanks { static const int NBK = 4, CTAS = QKind<KIND>::CTAS; };
+template <> struct QBanks<KIND_BQ, PSS_BASEQ> { static const int NBK = 2, CTAS = 4; };
+template <int KIND, int NBK = 4>
 __host__ __device__ constexpr QSmem q_layout() {
     QSmem L{};
-    int o = QKind<KIND>::NWORDS * TT * 4;
+    int o = (KIND == KIND_BQ ? 4 * NBK : QKind<KIND>::NWORDS) * TT * 4;
     L.raw = o; o += TT * 4;
     L.ri = o; o += QCH * 32;
     L.qoff = o; if (QKind<KIND>::QUAL) o += (QCH + 4) * 8;
@@ -1454,8 +1459,8 @@ __device__ __forceinline__ int q_rootmean_scr(unsigned long long sq, uint32_t n)
 
 // one aligned span [x, x + l) of a read whose first base is query index y: the lanes' four positions
 // (minq: events of bases below min_baseq are dropped, opt.pyx:1900-1903; 0 keeps everything)
-template <int BANK, bool MINQ>
-__device__ __forceinline__ void q_gather_span(uint32_t (&acc)[4][4], const uint8_t *qual, int p0, int x, int l, int y, uint32_t minq) {
+template <int BANK, bool MINQ, int NBK>
+__device__ __forceinline__ void q_gather_span(uint32_t (&acc)[NBK][4], const uint8_t *qual, int p0, int x, int l, int y, uint32_t minq) {
     const int off0 = p0 - x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1470,10 +1475,14 @@ __device__ __forceinline__ void q_gather_span(uint32_t (&acc)[4][4], const uint8
 // MINQ (baseq / baseq_strand only): min_baseq > 0 -- a compile-time switch, so the kernels of the default case keep
 // their instruction stream (a run-time test in the gather cost baseq 2.93 -> 3.84 ms per 50 Mb)
 template <int KIND, int STAT, bool MINQ>
-__global__ void __launch_bounds__(QKind<KIND>::NT, QKind<KIND>::CTAS)
+__global__ void __launch_bounds__(QKind<KIND>::NT, QBanks<KIND, STAT>::CTAS)
 k_tileq(TileArgs A) {
-    constexpr QSmem L = q_layout<KIND>();
     using K = QKind<KIND>;
+    constexpr int NBK = QBanks<KIND, STAT>::NBK;
+    constexpr QSmem L = q_layout<KIND, NBK>();
+    // (KIND_BQ: n[NBK] nnd[NBK] sq64[NBK])
+    constexpr int K_NDIFF = KIND == KIND_BQ ? 2 * NBK : K::NDIFF, K_NWORDS = KIND == KIND_BQ ? 4 * NBK : K::NWORDS,
+                  K_SQ = KIND == KIND_BQ ? 2 * NBK : K::SQ;
     constexpr int QNT = K::NT, NWARPS = QNT / 32;
     static_assert(QNT >= 256 && QNT >= QCH, "eight gather warps, one scatter thread per staged read");
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1558,7 +1567,7 @@ k_tileq(TileArgs A) {
     }
 #endif
     {   // zero the counters (+ raw)
-        const int nw4 = (K::NWORDS + 1) * TT / 4;
+        const int nw4 = (K_NWORDS + 1) * TT / 4;
         const uint4 z = make_uint4(0, 0, 0, 0);
         for (int k = tid; k < nw4; k += QNT) reinterpret_cast<uint4 *>(cnt)[k] = z;
     }
@@ -1575,9 +1584,9 @@ k_tileq(TileArgs A) {
     // gather state: this warp's window and read parity; per bank, per owned position
     const int gw0 = T.t0 + (warp & 3) * 128, gw1 = gw0 + 128, gpar = warp >> 2;
     const int gp0 = gw0 + 4 * lane;
-    uint32_t acc[4][4];
+    uint32_t acc[NBK][4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int b = 0; b < NBK; ++b)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[b][i] = 0;
 
@@ -1606,7 +1615,7 @@ k_tileq(TileArgs A) {
             if (cls & CLS_ADMITTED) {
                 if (rawp) interval_add(rawp, r.pos, r.end - r.pos, T.t0, 1u);
                 if (cls & CLS_COUNTED) {
-                    const int bank = cls & 3u;
+                    const int bank = NBK == 2 ? (int)((cls >> 1) & 1u) : (int)(cls & 3u);
                     if (minq && !(cls & CLS_HASSEQ)) {
                         // KIND_BQ under min_baseq, no sequence: quality 0 at every base -- only the deletion / ref-skip events remain
                         if (!T.no_del) {
@@ -1628,10 +1637,10 @@ k_tileq(TileArgs A) {
                         const uint32_t *mw = minq ? A.lowq + (r.seq_off >> 4) + (cb + tid) : nullptr;
                         auto undo = [&](int p, int run) {
                             if (!T.no_del) interval_add(cnt + bank * TT, T.t0 + p, run, T.t0, 0u - 1u);
-                            interval_add(cnt + (4 + bank) * TT, T.t0 + p, run, T.t0, 0u - 1u);
+                            interval_add(cnt + (NBK + bank) * TT, T.t0 + p, run, T.t0, 0u - 1u);
                         };
                         if (cls & CLS_SIMPLE) {
-                            interval_add(cnt + (4 + bank) * TT, r.pos, r.end - r.pos, T.t0, 1u);
+                            interval_add(cnt + (NBK + bank) * TT, r.pos, r.end - r.pos, T.t0, 1u);
                             if (minq) lowq_runs(mw, r.pos, r.end - r.pos, 0, T.t0, undo);
                         } else if (!(cls & CLS_NOREF)) {
                             const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
@@ -1642,7 +1651,7 @@ k_tileq(TileArgs A) {
                                 const int op = w & 15, l = (int)(w >> 4);
                                 if (op_is_match(op)) {
                                     if (x + l > T.t0) {
-                                        interval_add(cnt + (4 + bank) * TT, x, l, T.t0, 1u);
+                                        interval_add(cnt + (NBK + bank) * TT, x, l, T.t0, 1u);
                                         if (minq) lowq_runs(mw, x, l, y, T.t0, undo);
                                     }
                                     x += l; y += l;
@@ -1683,14 +1692,15 @@ k_tileq(TileArgs A) {
                     if (K::QUAL) qo = s_qoff[jn + qskew];
                 }
                 if (rpos >= gw1) break;
-                const int bank = cls & 3u;
+                const int bank = NBK == 2 ? (int)((cls >> 1) & 1u) : (int)(cls & 3u);
                 {
                     // counted, with sequence (else quality 0) and with bases at all
                     if (rend <= gw0 || (cls & (CLS_COUNTED | CLS_HASSEQ | CLS_NOREF)) != (CLS_COUNTED | CLS_HASSEQ)) continue;
                     const uint8_t *qual = s_qual + (int)(qoff - quallo);
 #define QSPAN(B, x, l, y) q_gather_span<B, MINQ>(acc, qual, gp0, x, l, y, gminq)
-#define QSPANS(x, l, y) do { switch (bank) { case 0: QSPAN(0, x, l, y); break; case 1: QSPAN(1, x, l, y); break; \
-                                             case 2: QSPAN(2, x, l, y); break; default: QSPAN(3, x, l, y); break; } } while (0)
+#define QSPANS(x, l, y) do { if (NBK == 2) { if (bank) QSPAN(NBK - 1, x, l, y); else QSPAN(0, x, l, y); } \
+                             else switch (bank) { case 0: QSPAN(0, x, l, y); break; case 1: QSPAN(1, x, l, y); break; \
+                                                  case 2: QSPAN(NBK - 2, x, l, y); break; default: QSPAN(NBK - 1, x, l, y); break; } } while (0)
                     if (cls & CLS_SIMPLE) QSPANS(rpos, rend - rpos, 0);
                     else {
                         const long long co = (long long)(((uint64_t)s_ri[jj].cigar_off));
@@ -1720,28 +1730,37 @@ k_tileq(TileArgs A) {
     if (warp < 8) {
         const int pi = (warp & 3) * 128 + 4 * lane;
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < NBK; ++b)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (acc[b][i]) {
-                    atomicAdd(reinterpret_cast<unsigned long long *>(cnt + K::SQ * TT) + b * TT + pi + i,
+                    atomicAdd(reinterpret_cast<unsigned long long *>(cnt + K_SQ * TT) + b * TT + pi + i,
                                    (unsigned long long)acc[b][i]);
                 }
     }
     __syncthreads();
     {   // prefix sums of the difference arrays (+ raw)
-        const int nscan = K::NDIFF + (A.need_raw ? 1 : 0);
-        for (int a = warp; a < nscan; a += NWARPS) warp_scan_array(a < K::NDIFF ? cnt + a * TT : raw, lane);
+        const int nscan = K_NDIFF + (A.need_raw ? 1 : 0);
+        for (int a = warp; a < nscan; a += NWARPS) warp_scan_array(a < K_NDIFF ? cnt + a * TT : raw, lane);
     }
     __syncthreads();
     // ---- rec(): one position per thread and iteration, 128-byte rows per warp and field ------------
-    const unsigned long long *sq64 = reinterpret_cast<const unsigned long long *>(cnt + K::SQ * TT);
+    const unsigned long long *sq64 = reinterpret_cast<const unsigned long long *>(cnt + K_SQ * TT);
     const int64_t st = A.stride;
 #pragma unroll 1
     for (int p = tid; p < TT; p += QNT) {
         const int64_t pl = t0l + p;
         if (pl >= A.end) break;
         int32_t *o = A.out + (pl - A.start);
+        if (NBK == 2) {
+            // baseq: banks not-pp, pp -> reads_all, reads_pp, rms_baseq, rms_baseq_pp (n counts every event, nnd the
+            // non-deletions, opt.pyx:1108-1112; under no_del the deletions are not counted at all)
+            const uint32_t d0 = cnt[NBK * TT + p], d1 = cnt[(NBK + 1) * TT + p];
+            const uint32_t n0 = A.no_del ? d0 : cnt[p], n1 = A.no_del ? d1 : cnt[TT + p];
+            const unsigned long long s0 = sq64[p], s1 = sq64[TT + p];
+            o[0] = n0 + n1; o[st] = n1; o[2 * st] = q_rootmean_scr(s0 + s1, d0 + d1); o[3 * st] = q_rootmean_scr(s1, d1);
+            A.rowmask[pl - A.start] = (A.need_raw ? raw[p] : n0 + n1) ? 1 : 0;
+        } else {
         uint32_t nb[4], N[6];
 #pragma unroll
         for (int b = 0; b < 4; ++b) nb[b] = cnt[b * TT + p];
@@ -1795,6 +1814,7 @@ k_tileq(TileArgs A) {
             }
         }
         A.rowmask[pl - A.start] = (A.need_raw ? raw[p] : N[0]) ? 1 : 0;
+        }
     }
 }
 
@@ -2212,17 +2232,17 @@ k_tilem(TileArgs A) {
 // variance; Chan, Golub & LeVeque 1983), so whenever |4 A - (2k + 1)^2 n (n - 1)| is above
 // 256 n^2 sum(t^2) u -- 64x that bound -- the rounded value is the reference's whatever the order.
 // Positions that are closer to a rounding boundary than that (in practice: exact ties, e.g. std = 0.5)
-// flag their tile, and k_pileup<AccTlen> -- the in-order Welford replay -- recomputes the flagged
-// tiles right after this kernel (its CTAs return at once for all other tiles).
+// put their tile on the replay list, and k_pileup<AccTlen> -- the in-order Welford replay -- recomputes the listed
+// tiles right after this kernel (a small fixed grid walking the list).
 //
-// word arrays of TT: nfwd[0] nrev[1] | class c = paired fwd, paired rev, pp fwd, pp rev: n[2 + c] (32-bit
-// difference arrays) | sum[c] 64-bit at words 6.., sumsq[c] 64-bit at words 14.. (64-bit difference arrays)
-#define TLEN_NW 22
+// word arrays of TT.  tlen_strand: nfwd[0] nrev[1] | class c = paired fwd, paired rev, pp fwd, pp rev: n[2 + c] (32-bit
+// difference arrays) | sum[c] 64-bit at words 6.., sumsq[c] 64-bit at words 14.. (64-bit difference arrays): 22 words per
+// position, 256 threads x 4 CTAs per SM.  tlen reports all / paired / pp without the strand split: nall[0] | class
+// c = paired, pp: n[1 + c] | sum[c] at words 3.., sumsq[c] at words 7..: 11 words, half the arrays to zero and scan,
+// 128 threads x 8 CTAs per SM (27 KB each) -- the layout that took mapq from 0.82 to 0.53 ms per 50 Mb.
+template <int STAT> struct TlCfg { static const int NN = 2, NC = 4, NT = 256, CTAS = 4, CH = 160; };       // tlen_strand
+template <> struct TlCfg<PSS_TLEN> { static const int NN = 1, NC = 2, NT = 128, CTAS = 8, CH = 136; };
 static_assert(PSS_TTILE == 2 * PSS_TILE, "k_tilet hands the two halves of its tile to the replay kernel");
-#define TLEN_NT 256
-#ifndef TLEN_CTAS
-#define TLEN_CTAS 4           // 52 KB of shared memory per CTA: a fourth fits (tlen_strand 5.49 -> 4.92 ms per 50 Mb)
-#endif
 
 // 64-bit add into shared memory as two 32-bit atomic adds: the carry out of the low word is seen by exactly the add that
 // causes it (old + lo wraps), so low and high word together always hold the sum of all increments mod 2^64 whatever the
@@ -2349,16 +2369,19 @@ __device__ __forceinline__ TlenOut tlen_class(unsigned n, long long S, unsigned 
 }
 
 template <int STAT>
-__global__ void __launch_bounds__(TLEN_NT, TLEN_CTAS)
+__global__ void __launch_bounds__(TlCfg<STAT>::NT, TlCfg<STAT>::CTAS)
 k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo, float force) {
+    using C = TlCfg<STAT>;
+    constexpr bool STRAND = STAT == PSS_TLEN_STRAND;
+    constexpr int NN = C::NN, NC = C::NC, TLEN_NW = NN + 5 * NC, TLEN_NT = C::NT, TCHK = C::CH;
     constexpr int NWARPS = TLEN_NT / 32;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *raw = cnt + TLEN_NW * TT;
-    RInfo *s_ri = reinterpret_cast<RInfo *>(raw + TT);
-    int32_t *s_tlen = reinterpret_cast<int32_t *>(s_ri + QCH);            // QCH + 8
-    unsigned long long *sum = reinterpret_cast<unsigned long long *>(cnt + 6 * TT);
-    unsigned long long *sumsq = reinterpret_cast<unsigned long long *>(cnt + 14 * TT);
+    uint32_t *raw = cnt + TLEN_NW * TT;                                   // exists only when need_raw
+    RInfo *s_ri = reinterpret_cast<RInfo *>(raw + (A.need_raw ? TT : 0));
+    int32_t *s_tlen = reinterpret_cast<int32_t *>(s_ri + TCHK);           // TCHK + 8
+    unsigned long long *sum = reinterpret_cast<unsigned long long *>(cnt + (NN + NC) * TT);
+    unsigned long long *sumsq = sum + NC * TT;
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_n;
     __shared__ long long s_tlenlo;
@@ -2374,7 +2397,7 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo
         dx = (int)d0.x; dy = (int)d0.y;
     }
     auto issue = [&](int cb) {
-        const int n = min(QCH, dy - cb);
+        const int n = min(TCHK, dy - cb);
         uint32_t b1 = 0;
         const uint8_t *p1 = nullptr;
         if (n > 0) stage_span(tlen, (long long)cb, (long long)cb + n, 4, &p1, &b1, &s_tlenlo);
@@ -2394,12 +2417,12 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo
 #if TPREFETCH > 0
     if (tid == TLEN_NT - 32 && tile + TPREFETCH < (int)gridDim.x) {
         const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(A.desc + tile + TPREFETCH));
-        const int px = (int)p0.x, pn = min(QCH, (int)p0.y - px);
+        const int px = (int)p0.x, pn = min(TCHK, (int)p0.y - px);
         if (pn > 0) bulk_prefetch_l2(A.ri + px, (uint32_t)pn * (uint32_t)sizeof(RInfo));
     }
 #endif
     {
-        const int nw4 = (TLEN_NW + 1) * TT / 4;
+        const int nw4 = (TLEN_NW + (A.need_raw ? 1 : 0)) * TT / 4;
         const uint4 z = make_uint4(0, 0, 0, 0);
         for (int k = tid; k < nw4; k += TLEN_NT) reinterpret_cast<uint4 *>(cnt)[k] = z;
     }
@@ -2413,23 +2436,23 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo
         const int n = s_n;
         if (n == 0) break;
         const int tskew = (int)(cb - s_tlenlo);
-        if (tid < n) {
-            const RInfo r = s_ri[tid];
+        for (int ir = tid; ir < n; ir += TLEN_NT) {
+            const RInfo r = s_ri[ir];
             const uint32_t cls = r.cls;
             if (cls & CLS_ADMITTED) {
                 const int len = r.end - r.pos;                    // every event of the column counts (opt.pyx:700-727)
                 if (rawp) interval_add(rawp, r.pos, len, t0, 1u);
                 if (cls & CLS_COUNTED) {
-                    const int rev = cls & CLS_REV ? 1 : 0;
-                    const long long t = s_tlen[tid + tskew];
+                    const int rev = (STRAND && (cls & CLS_REV)) ? 1 : 0;
+                    const long long t = s_tlen[ir + tskew];
                     // the read's contribution to [x, x + l): +1 / +t / +t^2 per class (sign: taken back out again)
                     auto contrib = [&](int x, int l, bool neg) {
                         interval_add(cnt + rev * TT, x, l, t0, neg ? 0u - 1u : 1u);
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
                             if (cls & (g ? CLS_PP : CLS_PAIRED)) {
-                                const int c = 2 * g + rev;
-                                interval_add(cnt + (2 + c) * TT, x, l, t0, neg ? 0u - 1u : 1u);
+                                const int c = STRAND ? 2 * g + rev : g;
+                                interval_add(cnt + (NN + c) * TT, x, l, t0, neg ? 0u - 1u : 1u);
                                 if (t) {
                                     const unsigned long long ut = (unsigned long long)t, uq = (unsigned long long)(t * t);
                                     interval_add64(sum + c * TT, x, l, t0, neg ? 0ull - ut : ut);
@@ -2442,10 +2465,10 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo
                         // deletion-like events are dropped (opt.pyx:1904-1906): the aligned spans only, and under min_baseq
                         // the runs of bases at or above the threshold in them (none for a read without sequence)
                         if (!(cls & CLS_NOREF) && (!minq || (cls & CLS_HASSEQ))) {
-                            if (minq) lowq_prefetch(A, r, cb + tid);
+                            if (minq) lowq_prefetch(A, r, cb + ir);
                             if (!minq && (cls & CLS_SIMPLE)) contrib(r.pos, len, false);
                             else {
-                                const uint32_t *mw = minq ? A.lowq + (r.seq_off >> 4) + (cb + tid) : nullptr;
+                                const uint32_t *mw = minq ? A.lowq + (r.seq_off >> 4) + (cb + ir) : nullptr;
                                 const uint32_t *cg = A.cigar + r.cigar_off;
                                 int x = r.pos, y = 0;
                                 for (int k = 0; k < (int)r.n_cigar && x < t0 + TT; ++k) {
@@ -2478,10 +2501,10 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo
                         }
                     } else {
                         // min_baseq > 0: as if every base passed, then the marked bases (k_lowq) are taken back out
-                        lowq_prefetch(A, r, cb + tid);
+                        lowq_prefetch(A, r, cb + ir);
                         contrib(r.pos, len, false);
                         if (!(cls & CLS_NOREF)) {
-                            const uint32_t *mw = A.lowq + (r.seq_off >> 4) + (cb + tid);
+                            const uint32_t *mw = A.lowq + (r.seq_off >> 4) + (cb + ir);
                             auto undo = [&](int p, int run) { contrib(t0 + p, run, true); };
                             if (cls & CLS_SIMPLE) lowq_runs(mw, r.pos, len, 0, t0, undo);
                             else {
@@ -2506,12 +2529,12 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo
         if (tid == 0) issue(cb);
     }
     __syncthreads();
-    {   // 6 (+ raw) 32-bit and 8 64-bit difference arrays
-        const int n32 = 6 + (A.need_raw ? 1 : 0);
-        for (int a = warp; a < n32 + 8; a += NWARPS) {
-            if (a < 6) warp_scan_array(cnt + a * TT, lane);
-            else if (a < n32) warp_scan_array(raw, lane);
-            else warp_scan_array64(sum + (a - n32) * TT, lane);          // sum[0..3] and sumsq[0..3] are contiguous
+    {   // NN + NC (+ raw) 32-bit and 2 NC 64-bit difference arrays; the 64-bit ones (the longer scans) first
+        const int n64 = 2 * NC, n32 = NN + NC;
+        for (int a = warp; a < n64 + n32 + (A.need_raw ? 1 : 0); a += NWARPS) {
+            if (a < n64) warp_scan_array64(sum + a * TT, lane);            // sum[] and sumsq[] are contiguous
+            else if (a < n64 + n32) warp_scan_array(cnt + (a - n64) * TT, lane);
+            else warp_scan_array(raw, lane);
         }
     }
     __syncthreads();
@@ -2522,24 +2545,24 @@ k_tilet(TileArgs A, const int32_t *__restrict__ tlen, int32_t *__restrict__ redo
         const int64_t pl = t0l + p;
         if (pl >= A.end) break;
         int32_t *o = A.out + (pl - A.start);
-        const uint32_t nf = cnt[p], nr = cnt[TT + p];
-        uint32_t nc[4];
-        long long S[4];
-        unsigned long long Q[4];
+        const uint32_t nf = cnt[p], nr = STRAND ? cnt[TT + p] : 0u;       // (no strand split: nf counts every read)
+        uint32_t nc[NC];
+        long long S[NC];
+        unsigned long long Q[NC];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { nc[c] = cnt[(2 + c) * TT + p]; S[c] = (long long)sum[c * TT + p]; Q[c] = sumsq[c * TT + p]; }
-        if (STAT == PSS_TLEN) {
-            const TlenOut h0 = tlen_class(nc[0] + nc[1], S[0] + S[1], Q[0] + Q[1], &amb, force);
-            const TlenOut h1 = tlen_class(nc[2] + nc[3], S[2] + S[3], Q[2] + Q[3], &amb, force);
-            o[0] = nf + nr; o[st] = h0.n; o[2 * st] = h1.n; o[3 * st] = h0.mean; o[4 * st] = h1.mean;
+        for (int c = 0; c < NC; ++c) { nc[c] = cnt[(NN + c) * TT + p]; S[c] = (long long)sum[c * TT + p]; Q[c] = sumsq[c * TT + p]; }
+        if (!STRAND) {
+            const TlenOut h0 = tlen_class(nc[0], S[0], Q[0], &amb, force);
+            const TlenOut h1 = tlen_class(nc[1], S[1], Q[1], &amb, force);
+            o[0] = nf; o[st] = h0.n; o[2 * st] = h1.n; o[3 * st] = h0.mean; o[4 * st] = h1.mean;
             o[5 * st] = h0.rms; o[6 * st] = h1.rms; o[7 * st] = h0.sd; o[8 * st] = h1.sd;
         } else {
             o[0] = nf + nr; o[st] = nf; o[2 * st] = nr;
 #pragma unroll 1
             for (int g = 0; g < 2; ++g) {          // paired, pp: all, fwd, rev
-                const int c = 2 * g;
-                const TlenOut h[3] = {tlen_class(nc[c] + nc[c + 1], S[c] + S[c + 1], Q[c] + Q[c + 1], &amb, force),
-                                      tlen_class(nc[c], S[c], Q[c], &amb, force), tlen_class(nc[c + 1], S[c + 1], Q[c + 1], &amb, force)};
+                const int c = (2 * g) & (NC - 1), c1 = (c + 1) & (NC - 1);        // (masks: NC == 4 on this path)
+                const TlenOut h[3] = {tlen_class(nc[c] + nc[c1], S[c] + S[c1], Q[c] + Q[c1], &amb, force),
+                                      tlen_class(nc[c], S[c], Q[c], &amb, force), tlen_class(nc[c1], S[c1], Q[c1], &amb, force)};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int f = 3 * g + k;
@@ -2701,7 +2724,7 @@ cudaError_t launch_lowq(const pss_reads &R, const uint8_t *qual, int min_baseq, 
 
 template <int KIND, int STAT, bool MINQ = false>
 static cudaError_t launch_tileq_one(const TileArgs &a, int64_t ntiles, cudaStream_t s) {
-    const size_t smem = (size_t)q_layout<KIND>().total;
+    const size_t smem = (size_t)q_layout<KIND, QBanks<KIND, STAT>::NBK>().total;
     static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
     int dev__ = 0;
     cudaGetDevice(&dev__);
@@ -2747,18 +2770,20 @@ size_t tile_redo_bytes(int64_t ntiles) { return sizeof(int32_t) * (size_t)(2 * n
 
 template <int STAT>
 static cudaError_t launch_tilet_one(const TileArgs &a, const int32_t *tlen, int32_t *redo, int64_t ntiles, cudaStream_t s) {
-    const size_t smem = (size_t)(TLEN_NW + 1) * TT * 4 + (size_t)QCH * sizeof(RInfo) + (QCH + 8) * 4;
+    using C = TlCfg<STAT>;
+    const size_t smem_max = (size_t)(C::NN + 5 * C::NC + 1) * TT * 4 + (size_t)C::CH * sizeof(RInfo) + (C::CH + 8) * 4;
+    const size_t smem = smem_max - (a.need_raw ? 0 : (size_t)TT * 4);
     static bool configured_dev[64] = {false};     // per instantiation and device (attributes are per device)
     int dev__ = 0;
     cudaGetDevice(&dev__);
     bool &configured = configured_dev[dev__ & 63];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_tilet<STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_tilet<STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const float force = getenv("PSS_TLEN_FORCE_REPLAY") ? 3.0e38f : 0.0f;   // tests: every tile takes the replay
-    k_tilet<STAT><<<(unsigned)ntiles, TLEN_NT, smem, s>>>(a, tlen, redo, force);
+    k_tilet<STAT><<<(unsigned)ntiles, C::NT, smem, s>>>(a, tlen, redo, force);
     return cudaGetLastError();
 }
 
