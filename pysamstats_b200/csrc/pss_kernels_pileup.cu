@@ -479,7 +479,14 @@ struct GatherSmem {
 // are staged in shared memory by bulk async copies (cp.async.bulk + mbarrier); each warp then
 // binary-searches its first relevant read.  !STAGED: sequence / qualities are read from
 // global memory (any read length).
-template <class ACC, bool STAGED>
+// the accumulators the replay pass behind k_tilet uses (the only ones instantiated with LIST)
+template <class A> struct IsTlenAcc { static const bool V = false; };
+template <int STAT> struct IsTlenAcc<AccTlen<STAT>> { static const bool V = true; };
+
+// LIST: the replay pass (a.redo: a list of tiles walked by a small fixed grid).  A compile-time switch: an ordinary launch
+// has one tile per CTA, and its loop below must be visibly a single round -- as a run-time loop it cost the generic
+// kernel of baseq_ext_strand 14 % (8.0 -> 9.1 ms per 50 Mb at min_baseq 20: registers held across the back edge).
+template <class ACC, bool STAGED, bool LIST = false>
 __global__ void __launch_bounds__(PSS_TILE)
 k_pileup(PileupArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -496,19 +503,19 @@ k_pileup(PileupArgs a) {
     // 256-position tiles, a.redo[1..] = their indices, CTA b takes entries b, b + gridDim.x, ...  (One CTA per tile of the
     // range, returning at once for the unflagged ones, cost 0.75 ms per 50 Mb in block launches alone -- a quarter of
     // tlen_strand.)  An ordinary launch has one tile per CTA and runs the loop body once.
-    const int n_mine = a.redo ? a.redo[0] : (int)gridDim.x;
-    if (STAGED && tid == 0) mbar_init(&s_bar, 1);
+    const int n_mine = LIST ? a.redo[0] : (int)gridDim.x;
     if (tid < 17) s_lut[tid] = c_var_lut[tid];
     uint32_t parity = 0;          // every bulk-copy phase issued below is waited for exactly once: the parity carries over
+    bool first = true;
     for (int it = blockIdx.x; it < n_mine; it += gridDim.x) {
-    const int tile = a.redo ? a.redo[1 + it] : it;
+    const int tile = LIST ? a.redo[1 + it] : it;
     const int64_t t0 = a.start + (int64_t)tile * PSS_TILE;
     const int64_t pl = t0 + tid;
     const bool valid = pl < a.end;
     const int p = (int)pl;
     const int w0 = (int)(t0 + (tid & ~31)), w1 = w0 + 32;
     // (replay: the first eight bytes of the 48-byte descriptor of the 512-position tile this one is half of)
-    const int2 rng = a.redo ? a.tile_rng[(size_t)(tile >> 1) * 6] : a.tile_rng[tile];
+    const int2 rng = LIST ? a.tile_rng[(size_t)(tile >> 1) * 6] : a.tile_rng[tile];
     const bool need_seq = ACC::REF, need_qual = a.qual != nullptr, need_tlen = a.tlen != nullptr;
 
     // one chunk: thread 0 sizes it and issues the bulk copies
@@ -544,8 +551,12 @@ k_pileup(PileupArgs a) {
         } else mbar_arrive_expect_tx(&s_bar, 0);
     };
 
-    __syncthreads();              // barrier initialised (first round) / everyone done with the staging buffers (later rounds)
-    if (STAGED && tid == 0 && rng.x < rng.y) issue(rng.x);
+    if (!first) __syncthreads();  // later rounds of the replay: everyone is done with the staging buffers
+    if (STAGED && tid == 0) {     // thread 0 starts the bulk copies of the first chunk before anything else happens
+        if (first) mbar_init(&s_bar, 1);
+        if (rng.x < rng.y) issue(rng.x);
+    }
+    first = false;
     ACC acc;
     acc.init();
     acc.setup(s_lut);
@@ -624,6 +635,7 @@ k_pileup(PileupArgs a) {
         acc.store(a.out + (pl - a.start), a.out_stride);
         a.rowmask[pl - a.start] = raw ? 1 : 0;
     }
+    if (!LIST) break;
     }
 }
 
@@ -640,6 +652,18 @@ static cudaError_t launch_one(const PileupArgs &a, int64_t ntiles, bool staged, 
             e = cudaFuncSetAttribute(k_pileup<ACC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
+    }
+    if (a.redo) {
+        if constexpr (IsTlenAcc<ACC>::V) {
+            static bool configured_list[64] = {false};
+            if (!configured_list[dev__ & 63]) {
+                cudaError_t e = cudaFuncSetAttribute(k_pileup<ACC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                configured_list[dev__ & 63] = true;
+            }
+            k_pileup<ACC, true, true><<<(unsigned)ntiles, PSS_TILE, smem, s>>>(a);
+            return cudaGetLastError();
+        } else return cudaErrorInvalidValue;
     }
     if (staged) k_pileup<ACC, true><<<(unsigned)ntiles, PSS_TILE, smem, s>>>(a);
     else k_pileup<ACC, false><<<(unsigned)ntiles, PSS_TILE, smem, s>>>(a);
