@@ -223,11 +223,14 @@ __device__ __forceinline__ void interval_add(uint32_t *arr, int x, int l, int t0
 // 32-bit word array per bank (so any depth fits one pass; root mean squares are not additive
 // over passes) and the squared qualities of mismatching bases as 64-bit point sums.
 // LayVar1: variation without the strand split, one word array per group, all | proper pair << 16 (PER = word arrays per group).
-struct LayVar { static const bool PACKED = true, VAR = true, DEFER = false; enum { PER = 2, ALL = W_ALL, MATCH = W_MATCH, DEL = W_DEL, INS = W_INS, MMT = W_MMT, MMC = W_MMC }; };
-struct LayVar1 { static const bool PACKED = true, VAR = true, DEFER = false; enum { PER = 1, ALL = 0, MATCH = 1, DEL = 2, INS = 3, MMT = 4, MMC = 5 }; };
+// LayBqx2: baseq_ext without the strand split, TWO unpacked banks (pp or not): PER = 3 addresses like PER = 2 (bank >> 1)
+// and counts like PER = 4 (full words).
+struct LayVar { static const bool PACKED = true, VAR = true, DEFER = false; enum { PER = 2, ALL = W_ALL, MATCH = W_MATCH, DEL = W_DEL, INS = W_INS, MMT = W_MMT, MMC = W_MMC, SQMM = 0 }; };
+struct LayVar1 { static const bool PACKED = true, VAR = true, DEFER = false; enum { PER = 1, ALL = 0, MATCH = 1, DEL = 2, INS = 3, MMT = 4, MMC = 5, SQMM = 0 }; };
 struct LayBqx { static const bool PACKED = false, VAR = false, DEFER = false; enum { PER = 4, ALL = 0, MATCH = 4, DEL = 0, INS = 0, MMT = 8, MMC = 0, SQMM = 20 }; };
+struct LayBqx2 { static const bool PACKED = false, VAR = false, DEFER = false; enum { PER = 3, ALL = 0, MATCH = 2, DEL = 0, INS = 0, MMT = 4, MMC = 0, SQMM = 10 }; };
 template <class L> __device__ __forceinline__ uint32_t *carr(const TileCtx &T, int group, int bank) {
-    return T.cnt + (group + (L::PER == 2 ? (bank >> 1) : L::PER == 1 ? 0 : bank)) * TT;
+    return T.cnt + (group + ((L::PER == 2 || L::PER == 3) ? (bank >> 1) : L::PER == 1 ? 0 : bank)) * TT;
 }
 template <class L> __device__ __forceinline__ uint32_t cinc(int bank) {
     return L::PER == 2 ? half_inc(bank) : L::PER == 1 ? (1u | ((uint32_t)(bank >> 1) << 16)) : 1u;
@@ -248,7 +251,7 @@ __device__ __forceinline__ void var_mismatch(const TileCtx &T, int bank, int p, 
         if (c < 5) atomicAdd(carr<L>(T, L::MMC + L::PER * c, bank) + p, inc);
     } else {
         const unsigned long long q = qidx >= 0 ? T.qual[qidx] : 0;
-        if (q) atomicAdd(reinterpret_cast<unsigned long long *>(T.cnt + LayBqx::SQMM * TT) + bank * TT + p, q * q);
+        if (q) atomicAdd(reinterpret_cast<unsigned long long *>(T.cnt + L::SQMM * TT) + (L::PER == 3 ? (bank >> 1) : bank) * TT + p, q * q);
     }
 }
 
@@ -1398,10 +1401,13 @@ struct QSmem {       // byte offsets into the dynamic shared memory
 // banks of a (kind, statistic), CTAs per SM it is compiled for
 template <int KIND, int STAT> struct QBanks { static const int NBK = 4, CTAS = QKind<KIND>::CTAS; };
 template <> struct QBanks<KIND_BQ, PSS_BASEQ> { static const int NBK = 2, CTAS = 4; };
+template <> struct QBanks<KIND_BQX, PSS_BASEQ_EXT> { static const int NBK = 2, CTAS = 3; };     // 14 word arrays: 73 KB per CTA
+template <int NBK> struct BqxLay { typedef LayBqx type; };
+template <> struct BqxLay<2> { typedef LayBqx2 type; };
 template <int KIND, int NBK = 4>
 __host__ __device__ constexpr QSmem q_layout() {
     QSmem L{};
-    int o = (KIND == KIND_BQ ? 4 * NBK : QKind<KIND>::NWORDS) * TT * 4;
+    int o = (KIND == KIND_BQ ? 4 * NBK : 7 * NBK) * TT * 4;
     L.raw = o; o += TT * 4;
     L.ri = o; o += QCH * 32;
     L.qoff = o; if (QKind<KIND>::QUAL) o += (QCH + 4) * 8;
@@ -1480,9 +1486,10 @@ k_tileq(TileArgs A) {
     using K = QKind<KIND>;
     constexpr int NBK = QBanks<KIND, STAT>::NBK;
     constexpr QSmem L = q_layout<KIND, NBK>();
-    // (KIND_BQ: n[NBK] nnd[NBK] sq64[NBK])
-    constexpr int K_NDIFF = KIND == KIND_BQ ? 2 * NBK : K::NDIFF, K_NWORDS = KIND == KIND_BQ ? 4 * NBK : K::NWORDS,
-                  K_SQ = KIND == KIND_BQ ? 2 * NBK : K::SQ;
+    // KIND_BQ: n[NBK] nnd[NBK] sq64[NBK]; KIND_BQX: n[NBK] match[NBK] mmt[NBK] sq64[NBK] sqmm64[NBK] (LayBqx / LayBqx2)
+    constexpr int K_NDIFF = 2 * NBK, K_NWORDS = KIND == KIND_BQ ? 4 * NBK : 7 * NBK, K_SQ = KIND == KIND_BQ ? 2 * NBK : 3 * NBK;
+    typedef typename BqxLay<NBK>::type LX;
+    static_assert(KIND == KIND_BQ || (LX::MATCH == NBK && LX::MMT == 2 * NBK && LX::SQMM == 5 * NBK), "LayBqx* offsets");
     constexpr int QNT = K::NT, NWARPS = QNT / 32;
     static_assert(QNT >= 256 && QNT >= QCH, "eight gather warps, one scatter thread per staged read");
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1606,7 +1613,7 @@ k_tileq(TileArgs A) {
                 const int j = tid - part * n;
                 const RInfo r = s_ri[j];
                 const uint32_t *cg = ciglo >= 0 ? s_cig + (r.cigar_off - ciglo) : A.cigar + r.cigar_off;
-                var_read<LayBqx>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts,
+                var_read<LX>(T, cg, r, (uint32_t)((r.seq_off - s_seqlo) << 1), rawp, part, nparts,
                                  (int)(s_qoff[j + qskew] - quallo));
             }
         } else if (tid < n) {
@@ -1752,7 +1759,7 @@ k_tileq(TileArgs A) {
         const int64_t pl = t0l + p;
         if (pl >= A.end) break;
         int32_t *o = A.out + (pl - A.start);
-        if (NBK == 2) {
+        if (NBK == 2 && KIND == KIND_BQ) {
             // baseq: banks not-pp, pp -> reads_all, reads_pp, rms_baseq, rms_baseq_pp (n counts every event, nnd the
             // non-deletions, opt.pyx:1108-1112; under no_del the deletions are not counted at all)
             const uint32_t d0 = cnt[NBK * TT + p], d1 = cnt[(NBK + 1) * TT + p];
@@ -1760,6 +1767,26 @@ k_tileq(TileArgs A) {
             const unsigned long long s0 = sq64[p], s1 = sq64[TT + p];
             o[0] = n0 + n1; o[st] = n1; o[2 * st] = q_rootmean_scr(s0 + s1, d0 + d1); o[3 * st] = q_rootmean_scr(s1, d1);
             A.rowmask[pl - A.start] = (A.need_raw ? raw[p] : n0 + n1) ? 1 : 0;
+        } else if (NBK == 2) {
+            // baseq_ext: banks not-pp, pp -> reads, matches, mismatches, rms_baseq, rms_baseq_matches, rms_baseq_mismatches,
+            // each all / pp (opt.pyx:1239-1330)
+            const unsigned long long *sqmm = reinterpret_cast<const unsigned long long *>(cnt + LX::SQMM * TT);
+            uint32_t nn[2], mt[2], mm[2];
+            unsigned long long sq[2], sm[2];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                nn[b] = cnt[b * TT + p]; mt[b] = cnt[(LX::MATCH + b) * TT + p]; mm[b] = cnt[(LX::MMT + b) * TT + p];
+                sq[b] = sq64[b * TT + p]; sm[b] = sqmm[b * TT + p];
+            }
+#pragma unroll
+            for (int jx = 0; jx < 2; ++jx) {          // all = both banks, pp = bank 1
+                const uint32_t N = jx ? nn[1] : nn[0] + nn[1], Mn = jx ? mt[1] : mt[0] + mt[1], Mm = jx ? mm[1] : mm[0] + mm[1];
+                const unsigned long long S = jx ? sq[1] : sq[0] + sq[1], Sm = jx ? sm[1] : sm[0] + sm[1];
+                o[jx * st] = N; o[(2 + jx) * st] = Mn; o[(4 + jx) * st] = Mm;
+                o[(6 + jx) * st] = q_rootmean_scr(S, Mn + Mm); o[(8 + jx) * st] = q_rootmean_scr(S - Sm, Mn);
+                o[(10 + jx) * st] = q_rootmean_scr(Sm, Mm);
+            }
+            A.rowmask[pl - A.start] = (A.need_raw ? raw[p] : nn[0] + nn[1]) ? 1 : 0;
         } else {
         uint32_t nb[4], N[6];
 #pragma unroll
