@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument('--no-binned', action='store_true', help='skip the binned sweep (BASELINE.json configs[4])')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling arm (N > 1)')
     ap.add_argument('--no-e2e-api', action='store_true', help='skip the from-file public API measurement')
+    ap.add_argument('--no-stats', action='store_true', help='skip the per-statistic device timings (pileup_stats)')
+    ap.add_argument('--stats-mb', type=float, default=50.0, help='pileup_stats: interval length, in Mb')
     ap.add_argument('--api-mb', type=float, default=250.0, help='e2e_api: contig length of the BAM written for it, in Mb')
     ap.add_argument('--window-size', type=int, default=300)
     return ap.parse_args()
@@ -643,19 +645,77 @@ def main():
         except Exception as e:   # noqa: BLE001 -- reported, the headline numbers stand
             e2e_api = {'error': repr(e)}
 
+    # ---- every pileup statistic device-resident on one interval (rank 0): the kernels beside the headline pair ------
+    pileup_stats = None
+    if rank == 0 and not args.no_stats:
+        try:
+            pileup_stats = run_pileup_stats(args, dev, peak)
+        except Exception as e:   # noqa: BLE001 -- reported, the headline numbers stand
+            pileup_stats = {'error': repr(e)}
+
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': dev_ms, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, world),
                 'reads_per_s': total_reads / (dev_ms * 1e-3), 'gpu_launches': int(launches),
                 'e2e': e2e, 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
-                'binned': binned, 'strong_scaling': strong, 'e2e_api': e2e_api,
+                'binned': binned, 'strong_scaling': strong, 'e2e_api': e2e_api, 'pileup_stats': pileup_stats,
                 'reads_per_gpu': n_reads, 'rows_emitted_rank0': rows, 'checksum_rank0': chk,
                 'setup_seconds': {'synthetic_batch': t_gen}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_pileup_stats(args, dev, peak):
+    """Device-resident time of EVERY pileup statistic (the 15 types of pysamstats/config.py) on one synthetic interval
+    of --stats-mb Mb with base qualities, default filters and min_baseq = 20: ms per call (CUDA events, 3 calls after
+    2 warm-up calls, outputs larger than L2), and the fraction of the measured HBM copy bandwidth its algorithmic bytes
+    -- 4 F + 2 per position, 29 + CIGAR (+ packed bases) (+ qualities) per read -- reach.  scripts/stat_sweep.py is the
+    stand-alone form of this."""
+    import torch
+    from pysamstats_b200 import _cabi, config, synth
+    L = int(args.stats_mb * 1e6) // 512 * 512
+    batch, (ref, ref_lo) = synth.make_interval_batch(0, L, L, depth=args.depth, read_len=args.read_len, device=dev, with_qual=True)
+    n = int(batch['n_reads'])
+    ctx = _cabi.Context(dev.index)
+    rs = _cabi.make_reads_struct(batch)
+    s = torch.cuda.current_stream().cuda_stream
+    out_stats = {}
+    for minq in (0, 20):
+        ctx.prepare(rs, with_qual=True, stream=s)
+        for stat in config.pileup_types:
+            nf = len(config.value_fields(stat))
+            out = torch.empty((nf, L), dtype=torch.int32, device=dev)
+            mask = torch.empty(L, dtype=torch.uint8, device=dev)
+            withref = stat in config.stats_types_withref
+            p = ctx.pileup_params(stat, start=0, end=L, ref=ref if withref else None, ref_start=ref_lo,
+                                  ref_len=int(ref.numel()) if withref else 0, contig_len=L, min_baseq=minq)
+            for _ in range(2):
+                ctx.pileup_prepared(p, out, mask, stream=s)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                ctx.pileup_prepared(p, out, mask, stream=s)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            need_qual = stat.startswith('baseq') or minq > 0
+            alg = (L * (4 * nf + 2) + n * 29 + 4 * int(batch['n_cigar_words'])
+                   + (int(batch['n_seq_bytes']) if (withref and stat != 'coverage_gc') or need_qual else 0)
+                   + (int(batch['n_qual_bytes']) if need_qual else 0))
+            d = out_stats.setdefault(stat, {})
+            if minq == 0:
+                d.update(ms=ms, positions_per_s=L / (ms * 1e-3), frac=alg / (ms * 1e-3) / 1e9 / peak)
+            else:
+                d.update(ms_min_baseq_20=ms)
+            del out, mask
+    ctx.close()
+    return {'what': 'every pileup statistic, device resident, one %g Mb interval (%d reads, base qualities staged); ms per call, '
+                    'frac = algorithmic bytes / time / measured HBM copy bandwidth' % (L / 1e6, n),
+            'interval_mb': L / 1e6, 'reads': n, 'peak_gbs': peak, 'stats': out_stats}
 
 
 def sum_mapped_reads(batch, i0, i1):

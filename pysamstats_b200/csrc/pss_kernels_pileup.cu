@@ -484,8 +484,8 @@ template <class A> struct IsTlenAcc { static const bool V = false; };
 template <int STAT> struct IsTlenAcc<AccTlen<STAT>> { static const bool V = true; };
 
 // LIST: the replay pass (a.redo: a list of tiles walked by a small fixed grid).  A compile-time switch: an ordinary launch
-// has one tile per CTA, and its loop below must be visibly a single round -- as a run-time loop it cost the generic
-// kernel of baseq_ext_strand 14 % (8.0 -> 9.1 ms per 50 Mb at min_baseq 20: registers held across the back edge).
+// has one tile per CTA and its loop below is visibly a single round, so the kernels of the other statistics keep the code
+// (and the register allocation) they had before the replay list existed.
 template <class ACC, bool STAGED, bool LIST = false>
 __global__ void __launch_bounds__(PSS_TILE)
 k_pileup(PileupArgs a) {

@@ -19,7 +19,9 @@ What crosses a shard boundary besides the halo reads:
   only holds the reads overlapping its interval can pair the rest of a chain differently.  Requests
   that read base qualities (``pss_pileup_needs_qual``: the baseq* statistics, any ``min_baseq > 0``)
   are therefore NOT cut by these helpers: ``plan_intervals(..., need_qual=True)`` returns one shard
-  holding the whole range (the same rule as ``opt._position_chunks``).
+  holding the whole range.  (``opt._position_chunks`` does cut such requests: it has the whole contig's
+  reads at hand, computes the pairs once from their metadata -- ``pss_pairs_host`` -- and hands every piece
+  its pairs as two-read name chains; a rank that only ever sees its own shard cannot do that.)
 """
 import numpy as np
 
