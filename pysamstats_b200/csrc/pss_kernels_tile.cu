@@ -51,13 +51,30 @@
 #ifndef TCTAS
 #define TCTAS 4               // CTAs per SM the variation kernels are compiled for
 #endif
+// Coverage kinds: little work per tile, so more, smaller CTAs per SM.  Measured per 50 Mb (threads x CTAs the kernel is
+// compiled for; coverage / coverage_strand / coverage_gc | coverage_ext / coverage_ext_strand, ms; profiles/
+// r02b_cov_launch_shapes.txt): 192 x 8 (rounds 1-2a) 0.217 / 0.300 / 0.306 | 0.449 / 0.819; 256 x 6 0.260 / 0.316 / 0.349 |
+// 0.486 / 0.861; 160 x 10 0.183 / 0.303 / 0.273 | 0.491 / 1.016; 128 x 10 0.198 / 0.265 / 0.287 | 0.396 / 0.786; 128 x 12
+// 0.190 / 0.255 / 0.278 | 0.458 / 0.891; 128 x 14 0.175 / 0.358 / 0.270 (36 registers: coverage_strand's six columns
+// spill) ; 96 x 16 0.176 / 0.273 / 0.265 | 0.418 / 0.816.  So: 128 threads; 12 CTAs for the COV kind, 14 for its
+// two-column statistics (coverage, coverage_gc), 10 for the EXT kind.
 #ifndef TTHREADS_COV
-#define TTHREADS_COV 192      // coverage kinds: little work per tile, so more, smaller CTAs per SM
+#define TTHREADS_COV 128
 #endif
 #ifndef TCTAS_COV
-#define TCTAS_COV 8
+#define TCTAS_COV 12
+#endif
+#ifndef TCTAS_COV2
+#define TCTAS_COV2 14         // coverage, coverage_gc
+#endif
+#ifndef TTHREADS_EXT
+#define TTHREADS_EXT 128
+#endif
+#ifndef TCTAS_EXT
+#define TCTAS_EXT 10
 #endif
 template <int KIND> struct KindLaunch { static const int NT = TTHREADS_COV, CTAS = TCTAS_COV; };
+template <> struct KindLaunch<1 /* KIND_EXT */> { static const int NT = TTHREADS_EXT, CTAS = TCTAS_EXT; };
 template <> struct KindLaunch<2 /* KIND_VAR */> { static const int NT = TTHREADS, CTAS = TCTAS; };
 // variation (no strand split): half the counter arrays (45 KB of shared memory per CTA), so five CTAs fit an SM; measured
 // per 50 Mb (threads / CTAs the kernel is compiled for): 384/3 1.96, 320/3 1.85, 320/4 1.72, 256/4 1.68, 256/5 1.58,
@@ -69,12 +86,16 @@ template <> struct KindLaunch<2 /* KIND_VAR */> { static const int NT = TTHREADS
 #define TCTAS_VAR1 6
 #endif
 template <> struct KindLaunch<6 /* KIND_VAR1 */> { static const int NT = TTHREADS_VAR1, CTAS = TCTAS_VAR1; };
+// CTAs per SM a (kind, statistic) is compiled for
+template <int KIND, int STAT> struct StatCtas { static const int V = KindLaunch<KIND>::CTAS; };
+template <> struct StatCtas<0 /* KIND_COV */, PSS_COVERAGE> { static const int V = TCTAS_COV2; };
+template <> struct StatCtas<0 /* KIND_COV */, PSS_COVERAGE_GC> { static const int V = TCTAS_COV2; };
 #define NQUAD (TT / 4)        // finalisation: quads of positions
 #ifndef TCH
 #define TCH 136               // reads staged per chunk, variation kinds (a 512-position tile of 30x / 150 bp has ~134 candidates);
 #endif                        // also the first chunk the tile descriptors describe
 #ifndef TCH_COV
-#define TCH_COV 192           // coverage kinds (records only: 6 KB)
+#define TCH_COV 128           // coverage kinds (records only: 4 KB; one staged read per thread)
 #endif
 #define TSEQ_BYTES (TCH * 76 + 64)   // staged sequence bytes per chunk (150 bp reads fit a full chunk)
 #define REFN_WORDS (TT / 8)
@@ -1099,7 +1120,7 @@ __device__ __forceinline__ void tile_output(const TileArgs &A, const uint32_t *c
 // ------------------------------------------------------------------------------ the kernel
 
 template <int KIND, int STAT, bool MINQ>
-__global__ void __launch_bounds__(KindLaunch<KIND>::NT, KindLaunch<KIND>::CTAS)
+__global__ void __launch_bounds__(KindLaunch<KIND>::NT, StatCtas<KIND, STAT>::V)
 k_tile(TileArgs A) {
     constexpr int NT = KindLaunch<KIND>::NT, NWARPS = NT / 32;
     constexpr bool IS_VAR = KIND == KIND_VAR || KIND == KIND_VAR1;
