@@ -12,8 +12,9 @@ statistics over the rank's interval.  With N ranks the genome is N x 250 Mb, cut
 interval's reads plus the halo of reads that start before it (weak scaling, no data-path
 collective; torch.distributed only provides the barrier and the max-over-ranks reduction).
 
-Numbers on the JSON line (besides the headline workload the line carries three more objects, each measured in
-the same run: ``binned`` -- BASELINE.json configs[4], the whole-genome binned sweep coverage_gc + coverage_binned +
+Numbers on the JSON line (besides the headline workload the line carries four more objects, each measured in
+the same run: ``pileup_stats`` -- at N = 1, EVERY pileup statistic device-resident on one 50 Mb interval, default filters
+and min_baseq = 20, each with the fraction of the HBM roofline its algorithmic bytes reach; ``binned`` -- BASELINE.json configs[4], the whole-genome binned sweep coverage_gc + coverage_binned +
 mapq_binned + tlen_binned with window_size 300 on the same reads, with its own value / e2e / per-kernel rooflines /
 cpu_baseline; ``strong_scaling`` -- the ONE 250 Mb contig of configs[2] cut into N shards of 250 / N Mb with read
 halos, device-resident and end to end; ``e2e_api`` -- the public python API from a real BAM + BAI file, decode
@@ -645,9 +646,9 @@ def main():
         except Exception as e:   # noqa: BLE001 -- reported, the headline numbers stand
             e2e_api = {'error': repr(e)}
 
-    # ---- every pileup statistic device-resident on one interval (rank 0): the kernels beside the headline pair ------
+    # ---- every pileup statistic device-resident on one interval (N = 1): the kernels beside the headline pair ------
     pileup_stats = None
-    if rank == 0 and not args.no_stats:
+    if rank == 0 and world == 1 and not args.no_stats:
         try:
             pileup_stats = run_pileup_stats(args, dev, peak)
         except Exception as e:   # noqa: BLE001 -- reported, the headline numbers stand
