@@ -703,10 +703,9 @@ def run_pileup_stats(args, dev, peak):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 3
-            need_qual = stat.startswith('baseq') or minq > 0
             alg = (L * (4 * nf + 2) + n * 29 + 4 * int(batch['n_cigar_words'])
-                   + (int(batch['n_seq_bytes']) if (withref and stat != 'coverage_gc') or need_qual else 0)
-                   + (int(batch['n_qual_bytes']) if need_qual else 0))
+                   + (int(batch['n_seq_bytes']) if (withref and stat != 'coverage_gc') else 0)
+                   + (int(batch['n_qual_bytes']) if stat.startswith('baseq') else 0))
             d = out_stats.setdefault(stat, {})
             if minq == 0:
                 d.update(ms=ms, positions_per_s=L / (ms * 1e-3), frac=alg / (ms * 1e-3) / 1e9 / peak)

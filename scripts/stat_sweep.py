@@ -46,8 +46,11 @@ for stat in config.pileup_types:
         ctx.pileup_prepared(p, out, mask, stream=s)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
-    seqb = int(batch['n_seq_bytes']) if (withref and stat != 'coverage_gc') or need_qual else 0
-    qb = int(batch['n_qual_bytes']) if need_qual else 0
+    # bytes a statistic has to touch: packed bases when it compares them with the reference, qualities when it sums them;
+    # a min_baseq threshold alone costs the one mark bit per base k_lowq leaves (the marks are made once per batch)
+    reads_q = stat.startswith('baseq')
+    seqb = int(batch['n_seq_bytes']) if (withref and stat != 'coverage_gc') else 0
+    qb = int(batch['n_qual_bytes']) if reads_q else (int(batch['n_qual_bytes']) // 8 if args.min_baseq > 0 else 0)
     alg = L * (4 * nf + 2) + n * 29 + 4 * int(batch['n_cigar_words']) + seqb + qb
     rows.append((stat, ms, L / ms / 1e6, alg / ms / 1e6))
     del out, mask
